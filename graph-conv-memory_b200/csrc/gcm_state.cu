@@ -1,0 +1,334 @@
+// State conversion (log + bitmasks <-> the reference's dense hidden state), the cross-batch
+// Euclidean distance, the selectors' own dense forward, and the library's error plumbing.
+#include <stdarg.h>
+
+#include "gcm_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void gcm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gcm_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    gcm_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
+  return GCM_OK;
+}
+
+int gcm_num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
+}
+
+extern "C" int gcm_version(void) { return GCM_ABI_VERSION; }
+extern "C" const char* gcm_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// materialize: log/bitmask state -> reference layout (gcm.py:194-211)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_materialize(const gcm_dense_state st, float* nodes_out,
+                                                     float* adj_out, int64_t* nn_out) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = st.N, C = st.C, F = st.F, W = st.W;
+  const int cnt = st.count[b];
+  const int nvalid = min(cnt, N);
+  const int start = cnt - nvalid;
+  if (nn_out && tid == 0) nn_out[b] = nvalid;
+  const float* nodes_b = st.nodes + (size_t)b * C * F;
+  if (nodes_out) {
+    float* out = nodes_out + (size_t)b * N * F;
+    for (int idx = tid; idx < N * F; idx += blockDim.x) {
+      const int l = idx / F, f = idx - l * F;
+      out[idx] = nodes_b[(size_t)gcm_slot(start + l, C) * F + f];
+    }
+  }
+  if (adj_out) {
+    const uint32_t* masks_b = st.masks + (size_t)b * C * 2 * W;
+    float* out = adj_out + (size_t)b * N * N;
+    for (int idx = tid; idx < N * N; idx += blockDim.x) {
+      const int l = idx / N, m = idx - l * N;
+      float v = 0.0f;
+      if (l < nvalid && m < nvalid) {
+        const uint32_t* mrow = masks_b + (size_t)gcm_slot(start + l, C) * 2 * W;
+        const int e = m <= l ? l - m : m - l;
+        const uint32_t word = mrow[(m <= l ? 0 : W) + (e >> 5)];
+        v = (float)((word >> (e & 31)) & 1u);
+      }
+      out[idx] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_materialize_grad(const gcm_dense_state st, const float* d_nodes,
+                                                          float* out_all) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int N = st.N, C = st.C, F = st.F;
+  const int cnt = st.count[b];
+  const int nvalid = min(cnt, N);
+  const int start = cnt - nvalid;
+  const float* src = d_nodes + (size_t)b * C * F;
+  float* out = out_all + (size_t)b * N * F;
+  for (int idx = tid; idx < N * F; idx += blockDim.x) {
+    const int l = idx / F, f = idx - l * F;
+    out[idx] = l < nvalid ? src[(size_t)gcm_slot(start + l, C) * F + f] : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest: reference layout -> log/bitmask state (positions == logical indices)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ingest(const gcm_dense_state st, const float* nodes_in,
+                                                const float* adj_in, const int64_t* nn_in,
+                                                int32_t* status) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int N = st.N, C = st.C, F = st.F, W = st.W;
+  long long n64 = nn_in[b];
+  unsigned int flags = 0u;
+  if (n64 < 0 || n64 > N) {
+    flags |= GCM_FLAG_BADCOUNT;
+    n64 = n64 < 0 ? 0 : N;
+  }
+  const int n = (int)n64;
+  if (tid == 0) st.count[b] = n;
+  float* nodes_b = st.nodes + (size_t)b * C * F;
+  const float* src = nodes_in + (size_t)b * N * F;
+  for (int idx = tid; idx < N * F; idx += blockDim.x) nodes_b[idx] = src[idx];  // slot l == row l
+  for (int idx = N * F + tid; idx < C * F; idx += blockDim.x) nodes_b[idx] = 0.0f;
+
+  uint32_t* masks_b = st.masks + (size_t)b * C * 2 * W;
+  const float* adj_b = adj_in + (size_t)b * N * N;
+  // one warp per (row l, past|future, word w): lane i <-> offset e = 32 w + i
+  for (int item = warp; item < C * 2 * W; item += nwarps) {
+    const int l = item / (2 * W);
+    const int rem = item - l * 2 * W;
+    const int which = rem / W, w = rem - which * W;
+    uint32_t word = 0u;
+    if (l < N) {
+      const int e = w * 32 + lane;
+      const int m = which ? l + e : l - e;
+      const bool inb = which ? (e >= 1 && m < N) : (m >= 0);
+      const float v = inb ? adj_b[(size_t)l * N + m] : 0.0f;
+      const bool set = v == 1.0f;
+      if (inb && ((v != 0.0f && v != 1.0f) || (set && (l >= n || m >= n)))) flags |= GCM_FLAG_UNCLEAN;
+      word = __ballot_sync(GCM_FULL_MASK, set && l < n && m < n);
+    }
+    if (lane == 0) masks_b[item] = word;
+  }
+  if (flags) atomicOr(reinterpret_cast<unsigned int*>(status), flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// EuclideanEdge distance (distance.py:48-49): mean over ALL current observations
+// ------------------------------------------------------------------------------------------------
+constexpr int EU_TR = 64, EU_TP = 64, EU_FC = 32;
+
+__global__ void __launch_bounds__(256) k_euclid_batchmean(const float* nodes, long long n_rows, int F,
+                                                          const float* cur, int n_cur,
+                                                          const float* dist_param, float* dist) {
+  __shared__ float rs[EU_TR][EU_FC + 1];
+  __shared__ float cs[EU_TP][EU_FC + 1];
+  __shared__ float red[EU_TR][16 + 1];
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4, tp = tid & 15;  // 16 x 16 threads, each a 4 x 4 (row, cur) register tile
+  const long long row0 = (long long)blockIdx.x * EU_TR;
+  float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p0 = 0; p0 < n_cur; p0 += EU_TP) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int f0 = 0; f0 < F; f0 += EU_FC) {
+      for (int idx = tid; idx < EU_TR * EU_FC; idx += 256) {
+        const int r = idx / EU_FC, f = idx - r * EU_FC;
+        const long long gr = row0 + r;
+        rs[r][f] = (gr < n_rows && f0 + f < F) ? nodes[gr * F + f0 + f] : 0.f;
+        const int gp = p0 + r;
+        cs[r][f] = (gp < n_cur && f0 + f < F) ? cur[(size_t)gp * F + f0 + f] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int f = 0; f < EU_FC; ++f) {
+        float rv[4], cv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rv[i] = rs[tr * 4 + i][f];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cv[j] = cs[tp * 4 + j][f];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float df = rv[i] - cv[j];
+            acc[i][j] = fmaf(df, df, acc[i][j]);
+          }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p0 + tp * 4 + j < n_cur) rowsum[i] += sqrtf(acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[tr * 4 + i][tp] = rowsum[i];
+  __syncthreads();
+  if (tid < EU_TR) {
+    float s = 0.f;
+    for (int j = 0; j < 16; ++j) s += red[tid][j];
+    const long long gr = row0 + tid;
+    const float scale = dist_param ? 1.0f / fabsf(*dist_param) : 1.0f;
+    if (gr < n_rows) dist[gr] = s / (float)n_cur * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the selectors' own forward on the reference's dense tensors
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_select_dense(const float* nodes, float* adj,
+                                                      const int64_t* num_nodes, int N, int F,
+                                                      const gcm_selector sel) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const long long t64 = num_nodes[b];
+  if (t64 < 0 || t64 >= N) return;  // the reference would raise an index error here
+  const int t = (int)t64;
+  float* adj_b = adj + (size_t)b * N * N;
+  const float* nodes_b = nodes + (size_t)b * N * F;
+  if (sel.kind == GCM_SEL_TEMPORAL) {
+    if (tid < sel.n_hops) {
+      const int hop = sel.hops[tid];
+      if (hop >= 0 && hop <= t) {
+        if (sel.direction != GCM_DIR_BACKWARD) adj_b[(size_t)t * N + (t - hop)] = 1.0f;
+        if (sel.direction != GCM_DIR_FORWARD) adj_b[(size_t)(t - hop) * N + t] = 1.0f;
+      }
+    }
+  } else if (sel.kind == GCM_SEL_DENSE) {
+    for (int j = tid; j <= t; j += blockDim.x) {
+      adj_b[(size_t)t * N + j] = 1.0f;
+      adj_b[(size_t)j * N + t] = 1.0f;
+    }
+  } else if (sel.kind != GCM_SEL_NONE) {
+    const bool learned = sel.dist_param != nullptr;
+    const float thr = learned ? 1.0f : sel.max_distance;
+    const float scale = learned ? 1.0f / fabsf(*sel.dist_param) : 1.0f;
+    const float* cur = nodes_b + (size_t)t * F;
+    float cur_norm = 0.f;
+    if (sel.kind == GCM_SEL_COSINE) {
+      float s = 0.f;
+      for (int f = lane; f < F; f += 32) s += cur[f] * cur[f];
+      cur_norm = fmaxf(sqrtf(gcm_warp_sum(s)), 1e-8f);
+    }
+    for (int j = warp; j < t; j += nwarps) {
+      const float* row = nodes_b + (size_t)j * F;
+      float dist;
+      if (sel.kind == GCM_SEL_EUCLIDEAN) {
+        dist = sel.dist[(size_t)b * N + j];
+      } else if (sel.kind == GCM_SEL_COSINE) {
+        float dot = 0.f, nb = 0.f;
+        for (int f = lane; f < F; f += 32) {
+          const float v = row[f];
+          dot += cur[f] * v;
+          nb += v * v;
+        }
+        dot = gcm_warp_sum(dot);
+        nb = fmaxf(sqrtf(gcm_warp_sum(nb)), 1e-8f);
+        dist = dot / (cur_norm * nb);
+      } else {
+        float s = 0.f;
+        for (int k = lane; k < sel.slice_len; k += 32) {
+          const float df = cur[sel.a_start + k * sel.a_step] - row[sel.b_start + k * sel.b_step];
+          s += df * df;
+        }
+        dist = sqrtf(gcm_warp_sum(s)) * scale;
+      }
+      if (lane == 0 && dist < thr) adj_b[(size_t)t * N + j] = 1.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int check_state(const gcm_dense_state* st) {
+  GCM_REQUIRE(st && st->nodes && st->masks && st->count, "state: null pointer");
+  GCM_REQUIRE(st->N >= 1 && st->N <= GCM_MAX_N && st->C >= st->N && st->F >= 1 && st->B >= 0 &&
+                  st->W == (st->N + 31) / 32,
+              "state: bad dims B=%d N=%d C=%d F=%d W=%d", st->B, st->N, st->C, st->F, st->W);
+  return GCM_OK;
+}
+
+extern "C" int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out, float* adj_out,
+                                     int64_t* num_nodes_out, void* stream) {
+  if (int rc = check_state(st)) return rc;
+  if (st->B == 0) return GCM_OK;
+  k_materialize<<<st->B, 256, 0, (cudaStream_t)stream>>>(*st, nodes_out, adj_out, num_nodes_out);
+  return gcm_check_launch("k_materialize");
+}
+
+extern "C" int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes,
+                                          float* d_nodes_out, void* stream) {
+  if (int rc = check_state(st)) return rc;
+  GCM_REQUIRE(d_nodes && d_nodes_out, "materialize_grad: null pointer");
+  if (st->B == 0) return GCM_OK;
+  k_materialize_grad<<<st->B, 256, 0, (cudaStream_t)stream>>>(*st, d_nodes, d_nodes_out);
+  return gcm_check_launch("k_materialize_grad");
+}
+
+extern "C" int gcm_state_ingest(const gcm_dense_state* st, const float* nodes_in, const float* adj_in,
+                                const int64_t* num_nodes_in, int32_t* status, void* stream) {
+  if (int rc = check_state(st)) return rc;
+  GCM_REQUIRE(nodes_in && adj_in && num_nodes_in && status, "ingest: null pointer");
+  if (st->B == 0) return GCM_OK;
+  k_ingest<<<st->B, 256, 0, (cudaStream_t)stream>>>(*st, nodes_in, adj_in, num_nodes_in, status);
+  return gcm_check_launch("k_ingest");
+}
+
+extern "C" int gcm_euclid_batchmean(const gcm_dense_state* st, const float* cur, int n_cur,
+                                    const float* dist_param, float* dist, void* stream) {
+  if (int rc = check_state(st)) return rc;
+  GCM_REQUIRE(cur && dist && n_cur >= 1, "euclid_batchmean: bad arguments");
+  const long long n_rows = (long long)st->B * st->C;
+  if (n_rows == 0) return GCM_OK;
+  const long long grid = (n_rows + EU_TR - 1) / EU_TR;
+  GCM_REQUIRE(grid < 2147483647LL, "euclid_batchmean: too many rows");
+  k_euclid_batchmean<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(st->nodes, n_rows, st->F, cur, n_cur,
+                                                                      dist_param, dist);
+  return gcm_check_launch("k_euclid_batchmean");
+}
+
+extern "C" int gcm_select_dense(const float* nodes, float* adj, const int64_t* num_nodes, int B, int N,
+                                int F, const gcm_selector* sel, void* stream) {
+  GCM_REQUIRE(adj && num_nodes && sel && B >= 0 && N >= 1 && F >= 1, "select_dense: bad arguments");
+  GCM_REQUIRE(sel->kind >= GCM_SEL_NONE && sel->kind <= GCM_SEL_SPATIAL, "select_dense: bad kind %d", sel->kind);
+  GCM_REQUIRE(sel->n_hops >= 0 && sel->n_hops <= GCM_MAX_HOPS, "select_dense: n_hops=%d", sel->n_hops);
+  if (sel->kind >= GCM_SEL_EUCLIDEAN) GCM_REQUIRE(nodes, "select_dense: distance selector needs nodes");
+  if (sel->kind == GCM_SEL_EUCLIDEAN) GCM_REQUIRE(sel->dist, "select_dense: euclidean needs dist");
+  if (sel->kind == GCM_SEL_SPATIAL)
+    GCM_REQUIRE(sel->slice_len >= 0 && sel->a_step >= 1 && sel->b_step >= 1 && sel->a_start >= 0 &&
+                    sel->b_start >= 0 &&
+                    (sel->slice_len == 0 || (sel->a_start + (sel->slice_len - 1) * sel->a_step < F &&
+                                             sel->b_start + (sel->slice_len - 1) * sel->b_step < F)),
+                "select_dense: spatial slice outside [0,F)");
+  if (B == 0) return GCM_OK;
+  k_select_dense<<<B, 256, 0, (cudaStream_t)stream>>>(nodes, adj, num_nodes, N, F, *sel);
+  return gcm_check_launch("k_select_dense");
+}

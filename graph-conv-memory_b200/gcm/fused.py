@@ -1,0 +1,278 @@
+"""Fused-path planning and execution for DenseGCM.
+
+`build_plan` pattern-matches a DenseGCM configuration: a user GNN made of two
+DenseGraphConv layers (+ tanh / relu / no activation) and an edge-selector chain built from
+TemporalBackedge / DenseEdge / EuclideanEdge / CosineEdge / SpatialEdge.  A matched
+configuration runs through `gcm_dense_step_fwd` / `gcm_dense_step_bwd`; anything else
+(learned edges, preprocessors, positional encoders, arbitrary GNNs) is outside the hot path
+and is executed by DenseGCM's generic torch-op path.
+
+Training: each step is one autograd node (`_StepFn`).  Nothing but the step index is saved:
+the backward kernel recomputes the step from the node log, which keeps every row a BPTT
+window needs because the log has spare capacity (C > N) while gradients are being recorded.
+dL/dnodes lives in a side buffer (`DenseState.d_nodes`) that the backward kernels of later
+steps accumulate into; a one-element token tensor threaded through the steps makes autograd
+run them newest-first, so when a step's backward runs its own row of that buffer already
+holds the full gradient of its observation (checklist item 11).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from gcm import _cabi
+from gcm.edge_selectors._base import FusedSelectorSpec
+from gcm.state import DenseHidden, DenseState
+
+_ACT_OF = {"Tanh": "tanh", "ReLU": "relu", "Identity": "none"}
+
+
+def _is_dense_conv(m: torch.nn.Module) -> bool:
+    return (type(m).__name__ == "DenseGraphConv" and isinstance(getattr(m, "lin_rel", None), torch.nn.Linear)
+            and isinstance(getattr(m, "lin_root", None), torch.nn.Linear))
+
+
+def _atoms(gnn: torch.nn.Module) -> Optional[List[object]]:
+    """Flatten the GNN into conv / activation atoms in registration order; None if anything else."""
+    out: List[object] = []
+
+    def walk(m: torch.nn.Module) -> bool:
+        if _is_dense_conv(m):
+            if getattr(m, "aggr", "add") != "add":
+                return False
+            out.append(m)
+            return True
+        name = type(m).__name__
+        kids = list(m.children())
+        if not kids:
+            if name in _ACT_OF:
+                out.append(_ACT_OF[name])
+                return True
+            return False
+        if any(f is not None for f in getattr(m, "fns", [])):  # gcm.nn.Sequential with lambdas
+            return False
+        if any(True for _ in m.parameters(recurse=False)):
+            return False
+        return all(walk(k) for k in kids)
+
+    if any(f is not None for f in getattr(gnn, "fns", [])):
+        return None
+    kids = list(gnn.children())
+    if not kids or not all(walk(k) for k in kids):
+        return None
+    if any(True for _ in gnn.parameters(recurse=False)):
+        return None
+    return out
+
+
+class GnnPlan:
+    """Two DenseGraphConv layers + activations, with the packed weights the kernels read."""
+
+    def __init__(self, conv1, conv2, act1: str, act2: str):
+        self.conv1, self.conv2, self.act1, self.act2 = conv1, conv2, act1, act2
+        self.F = conv1.lin_rel.in_features
+        self.H1 = conv1.lin_rel.out_features
+        self.H2 = conv2.lin_rel.out_features
+        self._key = None
+        self._packed = None
+
+    def params(self) -> List[torch.Tensor]:
+        ps = []
+        for conv in (self.conv1, self.conv2):
+            for lin in (conv.lin_rel, conv.lin_root):
+                ps.append(lin.weight)
+                if lin.bias is not None:
+                    ps.append(lin.bias)
+        return ps
+
+    def _bias(self, conv) -> Optional[torch.Tensor]:
+        b_rel, b_root = conv.lin_rel.bias, conv.lin_root.bias
+        if b_rel is not None and b_root is not None:
+            return (b_rel + b_root).detach()
+        b = b_rel if b_rel is not None else b_root
+        return None if b is None else b.detach()
+
+    def packed(self, device):
+        """K-major weight packs (include/gcm_b200.h: gcm_gnn), rebuilt only when a parameter changed."""
+        key = tuple((p.data_ptr(), p._version) for p in self.params()) + (str(device),)
+        if key != self._key:
+            def kmajor(conv):
+                return torch.cat([conv.lin_rel.weight.detach().t(), conv.lin_root.weight.detach().t()],
+                                 dim=0).to(device=device, dtype=torch.float32).contiguous()
+
+            def dev(t):
+                return None if t is None else t.to(device=device, dtype=torch.float32).contiguous()
+
+            t = {
+                "w1t": kmajor(self.conv1), "w2t": kmajor(self.conv2),
+                "b1": dev(self._bias(self.conv1)), "b2": dev(self._bias(self.conv2)),
+                "w_rel1": dev(self.conv1.lin_rel.weight.detach()), "w_root1": dev(self.conv1.lin_root.weight.detach()),
+                "w_rel2": dev(self.conv2.lin_rel.weight.detach()), "w_root2": dev(self.conv2.lin_root.weight.detach()),
+            }
+            c = _cabi.GnnC(
+                _cabi.ptr(t["w1t"]), _cabi.ptr(t["b1"]), _cabi.ptr(t["w2t"]), _cabi.ptr(t["b2"]),
+                _cabi.ptr(t["w_rel1"]), _cabi.ptr(t["w_root1"]), _cabi.ptr(t["w_rel2"]), _cabi.ptr(t["w_root2"]),
+                self.F, self.H1, self.H2, _cabi.ACT[self.act1], _cabi.ACT[self.act2])
+            self._key, self._packed = key, (c, t)
+        return self._packed[0]
+
+
+def match_gnn(gnn: torch.nn.Module) -> Optional[GnnPlan]:
+    atoms = _atoms(gnn)
+    if atoms is None:
+        return None
+    convs = [a for a in atoms if not isinstance(a, str)]
+    if len(convs) != 2:
+        return None
+    shape = "".join("a" if isinstance(a, str) else "c" for a in atoms)
+    acts = [a for a in atoms if isinstance(a, str)]
+    if shape == "caca":
+        a1, a2 = acts
+    elif shape == "cca":      # README.md:52-62: one activation module applied after both layers
+        a1 = a2 = acts[0]
+    elif shape == "cc":
+        a1 = a2 = "none"
+    elif shape == "cac":
+        a1, a2 = acts[0], "none"
+    else:
+        return None
+    c1, c2 = convs
+    if c1.lin_rel.out_features != c2.lin_rel.in_features:
+        return None
+    for c in convs:
+        if c.lin_rel.weight.dtype != torch.float32:
+            return None
+    if max(c1.lin_rel.in_features, c1.lin_rel.out_features, c2.lin_rel.out_features) > _cabi.GCM_MAX_FEAT:
+        return None
+    return GnnPlan(c1, c2, a1, a2)
+
+
+def match_selectors(sel: Optional[torch.nn.Module]) -> Optional[List[FusedSelectorSpec]]:
+    """Selector chain -> specs; [] for no selector; None if not fusable."""
+    if sel is None:
+        return []
+    if hasattr(sel, "fused_spec"):
+        if getattr(sel, "learned", False) and not hasattr(sel, "dist_param"):
+            return None
+        return [sel.fused_spec()]
+    if type(sel).__name__ == "Sequential" and hasattr(sel, "steps"):
+        want_in = ["x", "adj", "weights", "num_nodes", "B"]
+        if [a for a in sel.input_args] != want_in:
+            return None
+        specs: List[FusedSelectorSpec] = []
+        for ins, outs, f in sel.steps():
+            if ins != want_in or outs != ["adj", "weights"] or not hasattr(f, "fused_spec"):
+                return None
+            specs.append(f.fused_spec())
+        return specs if len(specs) <= _cabi.GCM_MAX_SELECTORS else None
+    return None
+
+
+class FusedPlan:
+    def __init__(self, gnn: GnnPlan, sels: List[FusedSelectorSpec]):
+        self.gnn = gnn
+        self.sels = sels
+        self.temporal_key = (tuple(s.key() for s in sels)
+                             if sels and all(s.kind == _cabi.SEL_TEMPORAL for s in sels) else None)
+        self.needs_euclid = any(s.kind == _cabi.SEL_EUCLIDEAN for s in sels)
+        self.validated = False
+        self._sel_cache = None
+
+    def selectors_c(self, F: int, dist: Optional[torch.Tensor]):
+        n = len(self.sels)
+        if n == 0:
+            return None, 0
+        key = (F, None if dist is None else dist.data_ptr())
+        if self._sel_cache is None or self._sel_cache[0] != key:
+            arr = (_cabi.SelectorC * n)()
+            for i, s in enumerate(self.sels):
+                arr[i] = s.to_c(F, dist if s.kind == _cabi.SEL_EUCLIDEAN else None)
+            self._sel_cache = (key, arr)
+        return self._sel_cache[1], n
+
+
+def build_plan(module) -> Optional[FusedPlan]:
+    """DenseGCM -> FusedPlan, or None when the configuration is outside the fused hot path."""
+    if module.preprocessor is not None or module.aux_edge_selectors is not None:
+        return None
+    if module.positional_encoder is not None or module.pooled:
+        return None
+    gnn = match_gnn(module.gnn)
+    if gnn is None:
+        return None
+    sels = match_selectors(module.edge_selectors)
+    if sels is None:
+        return None
+    return FusedPlan(gnn, sels)
+
+
+# ------------------------------------------------------------------------------------------------
+# execution
+# ------------------------------------------------------------------------------------------------
+def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: torch.Tensor) -> None:
+    lib = _cabi.lib()
+    dev = state.device
+    stream = _cabi.stream_ptr(dev)
+    dist = None
+    if plan.needs_euclid:
+        # reference quirk (distance.py:48-49): distance to node j is averaged over the current
+        # observation of EVERY graph in the batch.  Under batch sharding the caller all-gathers x.
+        dist = state.__dict__.setdefault("_euclid_dist", torch.empty(state.B, state.C, device=dev))
+        euc = next(s for s in plan.sels if s.kind == _cabi.SEL_EUCLIDEAN)
+        cur = state.__dict__.get("_euclid_cur_all")
+        cur = x if cur is None else cur
+        _cabi.check(lib.gcm_euclid_batchmean(state.c_ref(), cur.data_ptr(), cur.shape[0],
+                                             _cabi.ptr(euc.dist_param), dist.data_ptr(), stream),
+                    "gcm_euclid_batchmean")
+    sels, n = plan.selectors_c(state.F, dist)
+    flags = 0
+    if plan.temporal_key is not None and state.pure_key is not None and state.pure_key in ((), plan.temporal_key):
+        flags |= _cabi.STEP_PURE_TEMPORAL
+        state.pure_key = plan.temporal_key
+    else:
+        state.pure_key = None
+    gnn_c = plan.gnn.packed(dev)
+    _cabi.check(lib.gcm_dense_step_fwd(state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(),
+                                       state.status.data_ptr(), flags, stream), "gcm_dense_step_fwd")
+    state.version += 1
+    state.steps += 1
+    if state.host_count is not None:
+        state.host_count += 1
+
+
+def fused_step_nograd(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> torch.Tensor:
+    belief = torch.empty(state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)
+    _launch_fwd(plan, state, x, belief)
+    return belief
+
+
+def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tensor) -> bool:
+    """One-time check that the matched structure computes what the user's GNN module computes:
+    run the module itself on the materialised state of a few graphs and compare beliefs."""
+    nb = min(state.B, 8)
+    nodes = torch.empty(nb, state.N, state.F, device=state.device)
+    adj = torch.empty(nb, state.N, state.N, device=state.device)
+    nn = torch.empty(nb, device=state.device, dtype=torch.long)
+    sub = state.sub(nb)
+    _cabi.check(_cabi.lib().gcm_state_materialize(C.byref(sub), nodes.data_ptr(), adj.data_ptr(), nn.data_ptr(),
+                                                  _cabi.stream_ptr(state.device)), "gcm_state_materialize")
+    with torch.no_grad():
+        feats = module.gnn(nodes, adj, torch.zeros(0, device=state.device), nb, state.N)
+        ref = feats[torch.arange(nb, device=state.device), nn - 1]
+    ok = ref.shape == belief[:nb].shape and torch.allclose(ref, belief[:nb].detach(), rtol=1e-3, atol=1e-4)
+    if not ok:
+        warnings.warn(
+            "gcm: the GNN looked like a 2-layer DenseGraphConv stack but does not compute one; "
+            "falling back to the generic (unfused) path for this module")
+    return bool(ok)
+
+
+def fused_step_grad(plan: FusedPlan, state: DenseState, x: torch.Tensor, token, bptt_capacity: int):
+    raise NotImplementedError("training path lands with gcm_dense_step_bwd")
+
+
+def ingest_token(state: DenseState, nodes: torch.Tensor):
+    raise NotImplementedError("training path lands with gcm_dense_step_bwd")

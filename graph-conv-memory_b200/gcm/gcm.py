@@ -1,0 +1,290 @@
+"""DenseGCM — drop-in for the reference's `gcm.gcm.DenseGCM` (/root/reference/src/gcm/gcm.py:151-355).
+
+Same constructor, same `forward(x[B,F], hidden) -> (belief[B,H], hidden)` contract, same error
+behaviour.  When the configuration is one the hot path covers (two DenseGraphConv layers +
+activation, TemporalBackedge / DenseEdge / EuclideanEdge / CosineEdge / SpatialEdge selectors,
+see gcm.fused.build_plan) a step is ONE kernel launch on an in-place, bit-packed graph state
+(`gcm_dense_step_fwd`); the returned `hidden` is a `DenseHidden` that unpacks like the
+reference's (nodes, adj, weights, num_nodes) tuple.  Everything else (learned edges,
+preprocessors, positional encoders, arbitrary user GNNs) takes `_forward_generic`, which
+evaluates the reference's step semantics with torch ops on whatever device the tensors live on.
+The fused path is CUDA-only and has no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple, Union
+
+import torch
+
+import gcm.util
+from gcm import _cabi, fused
+from gcm.state import DenseHidden, DenseState
+
+
+class SparseToDense(torch.nn.Module):
+    """edge_index -> dense adjacency (reference gcm.py:10-21; legacy adapter, torch ops)."""
+
+    def forward(self, x, edge_index, batch_idx, B, N):
+        feat = x.shape[-1]
+        dense_x = x.new_zeros(B * N, feat)
+        counts = torch.bincount(batch_idx, minlength=B)
+        starts = torch.cumsum(counts, 0) - counts
+        pos = torch.arange(batch_idx.numel(), device=x.device) - starts[batch_idx]
+        dense_x[batch_idx * N + pos] = x
+        adj = x.new_zeros(B, N, N)
+        eb = batch_idx[edge_index[0]]
+        adj.index_put_((eb, edge_index[0] - starts[eb], edge_index[1] - starts[eb]),
+                       x.new_ones(eb.numel()), accumulate=True)
+        return dense_x.view(B, N, feat), adj
+
+
+class DenseToSparse(torch.nn.Module):
+    """dense adjacency -> edge_index (reference gcm.py:24-53; legacy adapter, torch ops)."""
+
+    def forward(self, x, adj, mask=None):
+        assert x.dim() == adj.dim() == 3
+        if mask:
+            raise NotImplementedError()
+        B, N = x.shape[0], x.shape[1]
+        b, row, col = torch.nonzero(adj > 0).t()
+        edge_index = torch.stack([row + b * N, col + b * N], dim=0).long()
+        batch_idx = torch.arange(B, device=x.device).repeat_interleave(N)
+        return x.reshape(B * N, x.shape[-1]), edge_index, batch_idx
+
+
+def _sincos_table(max_len: int, width: int, device) -> torch.Tensor:
+    d_model = math.ceil(width / 2) * 2
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model, device=device)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+class RelativePositionalEncoding(torch.nn.Module):
+    """Reference gcm.py:56-89 (only used together with aux_edge_selectors; generic path)."""
+
+    def __init__(self, max_len: int = 5000):
+        super().__init__()
+        self.max_len = max_len
+
+    def forward(self, nodes: torch.Tensor, num_nodes: torch.Tensor) -> torch.Tensor:
+        if not hasattr(self, "pe"):
+            self.register_buffer("pe", _sincos_table(self.max_len, nodes.shape[-1], nodes.device))
+        for b in range(nodes.shape[0]):
+            c = int(num_nodes[b])
+            pe = self.pe.roll(c, 0)
+            nodes[b, : c + 1] = nodes[b, : c + 1] + pe[: c + 1, : nodes.shape[-1]]
+        return nodes
+
+
+class PositionalEncoding(torch.nn.Module):
+    """Reference gcm.py:92-143: sinusoidal encoding added to / concatenated onto rows <= num_nodes."""
+
+    def __init__(self, max_len: int = 5000, mode="add", cat_dim: int = 8):
+        super().__init__()
+        assert mode in ["add", "cat"]
+        self.max_len, self.mode, self.cat_dim = max_len, mode, cat_dim
+
+    def forward(self, x: torch.Tensor, num_nodes: torch.Tensor) -> torch.Tensor:
+        if not hasattr(self, "pe"):
+            self.register_buffer("pe", _sincos_table(self.max_len, x.shape[-1], x.device))
+            if self.mode == "cat":
+                self.reproject = torch.nn.Linear(x.shape[-1], x.shape[-1] - self.cat_dim, device=x.device)
+        b_idxs, n_idxs = gcm.util.idxs_up_to_including_num_nodes(x, num_nodes)
+        if self.mode == "add":
+            x[b_idxs, n_idxs] = x[b_idxs, n_idxs] + self.pe[n_idxs, : x.shape[-1]]
+            return x
+        x_reproj = self.reproject(x[b_idxs, n_idxs]).reshape(len(b_idxs), x.shape[-1] - self.cat_dim)
+        x = x.clone()
+        x[b_idxs, n_idxs, : self.cat_dim] = self.pe[n_idxs, : self.cat_dim]
+        x[b_idxs, n_idxs, self.cat_dim:] = x_reproj
+        return x
+
+
+def overflow(num_nodes: torch.Tensor, N: int):
+    return torch.any(num_nodes + 1 > N)
+
+
+class DenseGCM(torch.nn.Module):
+    """Graph Associative Memory"""
+
+    did_warn = False
+
+    def __init__(
+        self,
+        gnn: torch.nn.Module,
+        preprocessor: torch.nn.Module = None,
+        edge_selectors: torch.nn.Module = None,
+        aux_edge_selectors: torch.nn.Module = None,
+        graph_size: int = 128,
+        pooled: bool = False,
+        positional_encoder: torch.nn.Module = None,
+        edge_weights: bool = False,
+    ):
+        super().__init__()
+        self.preprocessor = preprocessor
+        self.gnn = gnn
+        self.graph_size = graph_size
+        self.edge_selectors = edge_selectors
+        self.aux_edge_selectors = aux_edge_selectors
+        self.pooled = pooled
+        self.edge_weights = edge_weights
+        self.positional_encoder = positional_encoder
+        self._plan = None
+        self._plan_built = False
+        # extra log rows kept while autograd is recording, so that a BPTT window of up to this many
+        # steps can be recomputed in backward without any per-step saved activations
+        self.bptt_capacity = 128
+
+    # ------------------------------------------------------------------ reference API
+    def get_initial_hidden_state(self, x):
+        """Zeros hidden state in the reference layout (gcm.py:194-211)."""
+        assert x.dim() == 2
+        B, feats = x.shape
+        edges = torch.zeros(B, self.graph_size, self.graph_size, device=x.device)
+        nodes = torch.zeros(B, self.graph_size, feats, device=x.device)
+        if self.edge_weights:
+            weights = torch.zeros(B, self.graph_size, self.graph_size, device=x.device)
+        else:
+            weights = torch.zeros(0, device=x.device)
+        num_nodes = torch.zeros(B, dtype=torch.long, device=x.device)
+        return nodes, edges, weights, num_nodes
+
+    def fused_plan(self):
+        if not self._plan_built:
+            self._plan = fused.build_plan(self)
+            self._plan_built = True
+        return self._plan
+
+    def forward(self, x, hidden) -> Tuple[torch.Tensor, Union[DenseHidden, Tuple[torch.Tensor, ...]]]:
+        """Add observation x [B,F] to the graph and query the memory for it.
+
+        hidden: None, the previous call's returned hidden, or a reference-style tuple
+        (nodes[B,N,F], adj[B,N,N], weights [B,N,N] or empty, num_nodes[B] int64).
+        Returns (belief [B,H], hidden)."""
+        plan = self.fused_plan()
+        if plan is None:
+            return self._forward_generic(x, hidden)
+
+        assert x.dtype == torch.float32
+        _cabi.require_cuda(x, "DenseGCM.forward(x)")
+        assert x.dim() == 2 and x.shape[1] == plan.gnn.F, "x must be [B, obs_size] matching the GNN input"
+        B = x.shape[0]
+        recording = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in plan.gnn.params())
+            or (isinstance(hidden, DenseHidden) and hidden.token is not None))
+
+        if hidden is None:
+            state = DenseState(B, self.graph_size, x.shape[1], x.device,
+                               self.graph_size + (self.bptt_capacity if recording else 0))
+            token = None
+        elif isinstance(hidden, DenseHidden):
+            state = hidden.claim()
+            token = hidden.token
+            assert state.B == B and state.F == x.shape[1]
+        else:
+            nodes, adj, weights, num_nodes = hidden
+            assert nodes.dtype == torch.float
+            assert weights.dtype == torch.float
+            assert num_nodes.dtype == torch.long
+            assert num_nodes.dim() == 1
+            N = nodes.shape[1]
+            assert N == adj.shape[1] == adj.shape[2], "N must be equal for adj mat and node mat"
+            if adj.requires_grad or (weights.numel() != 0 and weights.requires_grad):
+                return self._forward_generic(x, hidden)   # learned / weighted adjacency
+            state, flags = DenseState.ingest(nodes, adj, weights, num_nodes,
+                                             N + (self.bptt_capacity if recording else 0))
+            if flags & (_cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT):
+                return self._forward_generic(x, hidden)   # not a {0,1} graph over the valid block
+            token = None
+            if recording and nodes.requires_grad:
+                token = fused.ingest_token(state, nodes)
+            recording = recording or token is not None
+
+        if not DenseGCM.did_warn and self._would_overflow(state):
+            print("Overflow detected, wrapping around. Will not warn again")
+            DenseGCM.did_warn = True
+
+        xc = x.contiguous()
+        if recording:
+            belief, token = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
+        else:
+            belief = fused.fused_step_nograd(plan, state, xc.detach())
+            token = None
+        if not plan.validated:
+            plan.validated = True
+            if not fused.validate_plan(plan, self, state, belief):
+                self._plan = None
+                nodes, adj, num_nodes = state.materialize()
+                feats = self.gnn(nodes, adj, state.materialize_weights(), B, state.N)
+                belief = feats[torch.arange(B, device=x.device), num_nodes - 1]
+        return belief, DenseHidden(state, token)
+
+    def _would_overflow(self, state: DenseState) -> bool:
+        # host-side mirror only (no device sync): graphs started empty overflow after N steps
+        return state.host_count is not None and state.host_count >= state.N
+
+    # ------------------------------------------------------------------ generic (unfused) path
+    def _forward_generic(self, x, hidden):
+        """Reference step semantics (gcm.py:213-321) with torch ops, for configurations outside the
+        fused hot path.  Device-agnostic; selectors from gcm.edge_selectors still run their CUDA
+        kernels on the dense adjacency."""
+        if hidden is None:
+            hidden = self.get_initial_hidden_state(x)
+        nodes, adj, weights, num_nodes = hidden
+        assert x.dtype == torch.float32
+        assert nodes.dtype == torch.float
+        assert weights.dtype == torch.float
+        assert num_nodes.dtype == torch.long
+        assert num_nodes.dim() == 1
+        N = nodes.shape[1]
+        B = x.shape[0]
+        assert N == adj.shape[1] == adj.shape[2], "N must be equal for adj mat and node mat"
+        b_idx = torch.arange(B, device=x.device)
+
+        full = num_nodes + 1 > N
+        if bool(full.any()):
+            if not DenseGCM.did_warn:
+                print("Overflow detected, wrapping around. Will not warn again")
+                DenseGCM.did_warn = True
+            nodes, adj, weights, num_nodes = self.wrap_overflow(nodes.clone(), adj.clone(), weights.clone(),
+                                                                num_nodes.clone())
+        nodes = nodes.clone()
+        nodes[b_idx, num_nodes] = x
+        dirty_nodes = nodes.clone()
+        if self.edge_selectors:
+            adj, weights = self.edge_selectors(dirty_nodes, adj.clone(), weights.clone(), num_nodes, B)
+        if self.preprocessor:
+            dirty_nodes = self.preprocessor(dirty_nodes)
+        if self.aux_edge_selectors:
+            sel_in = (self.positional_encoder(dirty_nodes, num_nodes) if self.positional_encoder
+                      else dirty_nodes)
+            adj, weights = self.aux_edge_selectors(sel_in, adj.clone(), weights.clone(), num_nodes, B)
+        node_feats = self.gnn(dirty_nodes, adj, weights, B, N)
+        mx = node_feats if self.pooled else node_feats[b_idx, num_nodes]
+        assert torch.all(torch.isfinite(mx)), "Got NaN in returned memory, try using tanh activation"
+        return mx, (nodes, adj, weights, num_nodes + 1)
+
+    def wrap_overflow(self, nodes, adj, weights, num_nodes):
+        """Drop node 0 of every full graph and shift the rest down one slot (reference gcm.py:323-355).
+        Mutates and returns its arguments, like the reference."""
+        N = nodes.shape[1]
+        full = num_nodes + 1 > N
+        idx = full.nonzero().flatten()
+        if idx.numel():
+            def shift2(m):
+                out = torch.zeros_like(m)
+                out[:, : N - 1, : N - 1] = m[:, 1:, 1:]
+                return out
+
+            sub = torch.zeros_like(nodes[idx])
+            sub[:, : N - 1] = nodes[idx][:, 1:]
+            nodes[idx] = sub
+            adj[idx] = shift2(adj[idx])
+            if weights.numel() != 0:
+                weights[idx] = shift2(weights[idx])
+            num_nodes[idx] = num_nodes[idx] - 1
+        return nodes, adj, weights, num_nodes

@@ -1,0 +1,205 @@
+/*
+ * gcm_b200.h — C ABI of libgcm_b200.so: the B200 (sm_100a) hot path of Graph
+ * Convolutional Memory (proroklab/graph-conv-memory), memory-update-and-aggregate.
+ *
+ * The reference is pure Python; its "FFI" for this path is the set of Python
+ * call sites listed beside each entry point (paths under /root/reference/src/gcm).
+ * Everything here is plain C: raw DEVICE pointers, sizes and a cudaStream_t
+ * (passed as void*).  No torch types, no exceptions: every function returns 0
+ * on success and a negative gcm_status on failure; gcm_last_error() gives the
+ * text.  Kernels are enqueued on the given stream and never synchronise.
+ *
+ * State layout (all in HBM, owned by the caller):
+ *   nodes  float32 [B, C, F]       node log; node with absolute position p lives in
+ *                                  slot p % C.  C >= N (C == N: in-place ring).
+ *   masks  uint32  [B, C, 2, W]    per node two N-bit masks, W = ceil(N/32):
+ *                                  [..,0,:] past  : bit d set  <=>  edge (p-d) -> p  (d = 0: self loop)
+ *                                  [..,1,:] future: bit d set  <=>  edge (p+d) -> p  (d >= 1)
+ *                                  a bit is live only while its source is inside the window, so the
+ *                                  reference's "drop node 0 and shift" (gcm.py:323-355) costs nothing.
+ *   count  int32   [B]             nodes ever written; the next node gets position count[b].
+ * The reference's visible hidden state (gcm.py:194-211) is nodes[B,N,F] f32, adj[B,N,N] f32
+ * (adj[i,j] = 1: j -> i), num_nodes[B] i64 = min(count, N); gcm_state_materialize /
+ * gcm_state_ingest convert between the two.
+ */
+#ifndef GCM_B200_H
+#define GCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCM_ABI_VERSION 1
+#define GCM_MAX_HOPS 16
+#define GCM_MAX_SELECTORS 4
+#define GCM_MAX_N 1024 /* graph_size limit of the packed representation   */
+#define GCM_MAX_FEAT 256 /* F, H1, H2 limit of the fused kernels           */
+
+typedef enum gcm_status {
+  GCM_OK = 0,
+  GCM_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+  GCM_ERR_CUDA = -2,        /* a CUDA runtime call failed                  */
+  GCM_ERR_UNSUPPORTED = -3  /* valid request the fused path does not cover */
+} gcm_status;
+
+/* device-side status word bits (int32 written with atomicOr, polled lazily by the host) */
+#define GCM_FLAG_NONFINITE 1u   /* belief has NaN/Inf  (gcm.py:316-318 assertion)            */
+#define GCM_FLAG_UNCLEAN 2u     /* ingest: adj not {0,1} or edges touching rows >= num_nodes  */
+#define GCM_FLAG_BADCOUNT 4u    /* ingest: num_nodes outside [0, N]                           */
+#define GCM_FLAG_OVERFLOW 8u    /* sparse: T + tau > N  (sparse_gcm.py:120-121)               */
+#define GCM_FLAG_NONCAUSAL 16u  /* sparse: edge with source >= sink (sparse_gcm.py:171)       */
+
+typedef enum gcm_selector_kind {
+  GCM_SEL_NONE = 0,
+  GCM_SEL_TEMPORAL = 1,  /* edge_selectors/temporal.py:72-88 (deterministic branch) */
+  GCM_SEL_DENSE = 2,     /* edge_selectors/dense.py:11-23                            */
+  GCM_SEL_EUCLIDEAN = 3, /* edge_selectors/distance.py:18-39 + 48-49                 */
+  GCM_SEL_COSINE = 4,    /* edge_selectors/distance.py:18-39 + 59-61                 */
+  GCM_SEL_SPATIAL = 5    /* edge_selectors/distance.py:18-39 + 77-81                 */
+} gcm_selector_kind;
+
+typedef enum gcm_direction { GCM_DIR_FORWARD = 0, GCM_DIR_BACKWARD = 1, GCM_DIR_BOTH = 2 } gcm_direction;
+typedef enum gcm_act { GCM_ACT_NONE = 0, GCM_ACT_TANH = 1, GCM_ACT_RELU = 2 } gcm_act;
+
+typedef struct gcm_dense_state {
+  float* nodes;    /* [B, C, F]    */
+  uint32_t* masks; /* [B, C, 2, W] */
+  int32_t* count;  /* [B]          */
+  int32_t B, N, C, F, W;
+} gcm_dense_state;
+
+typedef struct gcm_selector {
+  int32_t kind;      /* gcm_selector_kind */
+  int32_t direction; /* temporal only     */
+  int32_t n_hops;
+  int32_t hops[GCM_MAX_HOPS];
+  float max_distance;                   /* strict '<' (distance.py:27)                          */
+  int32_t a_start, a_step;              /* spatial: slice of the CURRENT node (a_pose_slice)     */
+  int32_t b_start, b_step;              /* spatial: slice of the PAST nodes   (b_pose_slice)     */
+  int32_t slice_len;
+  const float* dist_param;              /* learned=True: device scalar, nodes are divided by it  */
+  const float* dist;                    /* euclidean: [B, C] batch-mean distance per slot, from  */
+                                        /* gcm_euclid_batchmean (the reference's cdist quirk)    */
+} gcm_selector;
+
+/* 2-layer DenseGraphConv stack (torch_geometric.nn.DenseGraphConv, call sites README.md:52-62):
+ *   out = act2(lin_rel2(A h) + lin_root2(h)),  h = act1(lin_rel1(A x) + lin_root1(x))
+ * w1t/w2t are K-major packs for the forward; w_rel / w_root are the layers' own [out,in] weights
+ * (used by the backward).  One bias per layer (on lin_rel in PyG >= 2.0, lin_root in 1.x). */
+typedef struct gcm_gnn {
+  const float* w1t; /* [2F,  H1]: rows 0..F-1 = lin_rel1.weight^T, rows F..2F-1 = lin_root1.weight^T */
+  const float* b1;  /* [H1] or NULL */
+  const float* w2t; /* [2H1, H2] */
+  const float* b2;  /* [H2] or NULL */
+  const float* w_rel1;  /* [H1, F]  */
+  const float* w_root1; /* [H1, F]  */
+  const float* w_rel2;  /* [H2, H1] */
+  const float* w_root2; /* [H2, H1] */
+  int32_t F, H1, H2, act1, act2;
+} gcm_gnn;
+
+/* gradient accumulators of the backward (all device, float32, ACCUMULATED into) */
+typedef struct gcm_gnn_grads {
+  float* d_w_rel1;  /* [H1, F]  */
+  float* d_w_root1; /* [H1, F]  */
+  float* d_b1;      /* [H1] or NULL */
+  float* d_w_rel2;  /* [H2, H1] */
+  float* d_w_root2; /* [H2, H1] */
+  float* d_b2;      /* [H2] or NULL */
+} gcm_gnn_grads;
+
+int gcm_version(void);
+const char* gcm_last_error(void);
+
+/* One DenseGCM.forward step for the whole batch (replaces gcm.py:262-321: node write at
+ * nodes[b, num_nodes[b]] (:274), overflow wrap (:263-271, :323-355), edge selectors (:284-287),
+ * gnn (:308), belief extraction (:314), finite check (:316-318), num_nodes + 1 (:320)).
+ * The state is updated IN PLACE.  belief: [B, H2].  status: device int32 (flags OR-ed in).
+ * flags: bit 0 = the state is "pure temporal" (built from empty by this same TEMPORAL-only
+ *        selector chain), which enables the implicit-adjacency fast kernel. */
+#define GCM_STEP_PURE_TEMPORAL 1
+int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
+                       int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
+                       void* stream);
+
+/* Backward of step `steps_back` steps ago (0 = the most recent step), recomputed from the node
+ * log (requires that no slot of that step's window was overwritten since: count_now - start <= C).
+ * Replaces autograd through gcm.py:262-321.  d_belief [B,H2] in; d_nodes [B,C,F] is the running
+ * dL/dnodes buffer (accumulated); d_obs [B,F] out = dL/dx of that step (its d_nodes row, which is
+ * then zeroed).  Weight gradients are accumulated into `grads`. */
+int gcm_dense_step_bwd(const gcm_dense_state* st, int steps_back, const gcm_gnn* gnn,
+                       const float* d_belief, float* d_nodes, float* d_obs,
+                       const gcm_gnn_grads* grads, void* stream);
+
+/* ring/log + bitmasks -> the reference's hidden-state tensors (gcm.py:194-211 layout).
+ * Any of nodes_out / adj_out / num_nodes_out may be NULL. */
+int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out, float* adj_out,
+                          int64_t* num_nodes_out, void* stream);
+/* dL/dnodes in log layout -> [B,N,F] reference layout (rows >= num_nodes are zero) */
+int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes, float* d_nodes_out,
+                               void* stream);
+
+/* the inverse: a caller-supplied hidden state (nodes[B,N,F] f32, adj[B,N,N] f32, num_nodes i64)
+ * -> log layout with positions == logical indices.  Sets GCM_FLAG_UNCLEAN / GCM_FLAG_BADCOUNT. */
+int gcm_state_ingest(const gcm_dense_state* st, const float* nodes_in, const float* adj_in,
+                     const int64_t* num_nodes_in, int32_t* status, void* stream);
+
+/* EuclideanEdge's distance (distance.py:48-49): dist[b, slot] = mean_p || cur[p] - nodes[b, slot] ||_2
+ * over ALL n_cur current observations (cur [n_cur, F], already including this step's obs), for the
+ * slots of the nodes currently in the window.  Runs BEFORE gcm_dense_step_fwd of the same step. */
+int gcm_euclid_batchmean(const gcm_dense_state* st, const float* cur, int n_cur,
+                         const float* dist_param, float* dist, void* stream);
+
+/* The selectors' own forward(nodes, adj_mats, edge_weights, num_nodes, B) on the reference's DENSE
+ * tensors (edge_selectors/{temporal,dense,distance}.py): ORs 1s into adj [B,N,N] f32 in place.
+ * nodes [B,N,F]; num_nodes i64 [B]. */
+int gcm_select_dense(const float* nodes, float* adj, const int64_t* num_nodes, int B, int N, int F,
+                     const gcm_selector* sel, void* stream);
+
+/* ---- sparse path (sparse_gcm.py:72-212) -------------------------------------------------- */
+
+/* Node write (sparse_gcm.py:111-123) + flat gather (util.py:426-452): nodes[b, T_b + k] = x[b, k]
+ * for k < tau_b; flat[offset_b + k] = nodes[b, k] for k < T_b + tau_b, offset = exclusive
+ * cumsum(T + tau) (util.py:234-240), supplied by the caller in `offsets` [B+1] (int64).
+ * out_idx[j] = flat index of the j-th new node (ordered by b, then k). */
+int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, const int64_t* taus,
+                             const int64_t* offsets, const int64_t* tau_offsets, int B, int N, int F,
+                             int tmax, float* flat, int64_t* out_idx, int32_t* status, void* stream);
+
+/* TemporalEdge (sparse_edge_selectors/temporal.py:19-63): counts / fills edges (b, sink, source) for
+ * the new nodes.  Two-pass: call with edges == NULL to get per-new-node degrees in `deg`
+ * [n_new], then with the exclusive scan of deg in `edge_off` to fill `edges` int64 [3, E]. */
+int gcm_sparse_temporal_edges(const int64_t* T, const int64_t* taus, const int64_t* tau_offsets, int B,
+                              const int32_t* hops, int n_hops, int64_t n_new, int32_t* deg,
+                              const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
+
+/* SpatialRadiusEdge, causal (sparse_edge_selectors/spatial.py:74-115): same two-pass protocol; the
+ * candidate sources of new node s are all k < s of the same graph with ||pos_s - pos_k||_2 < radius. */
+int gcm_sparse_radius_edges(const float* nodes, const int64_t* T, const int64_t* taus,
+                            const int64_t* tau_offsets, int B, int N, int F, int pos_start, int pos_step,
+                            int pos_len, float radius, int64_t n_new, int32_t* deg,
+                            const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
+
+/* GraphConv over a CSR grouped by sink (torch_geometric.nn.GraphConv; call sites
+ * ray_sparse_gcm.py:37-40, invoked at sparse_gcm.py:178,199):
+ *   out[i] = act(W_rel (sum_{e in row i} w_e x[col[e]]) + b + W_root x[i])
+ * x [n, Fin]; rowptr int64 [n+1]; col int64 [E]; ew float [E] or NULL (== 1); wt = K-major pack
+ * [2 Fin, Fout] as in gcm_gnn.  Deterministic (segmented gather-reduce, no atomics). */
+int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew,
+                             int64_t n, int Fin, int Fout, const float* wt, const float* bias, int act,
+                             float* agg_out /* [n, Fin] or NULL: saved for backward */, float* out,
+                             void* stream);
+/* Backward: given d_out [n,Fout], out (post-activation), x, agg and the TRANSPOSED csr (grouped by
+ * source): d_x [n,Fin] (written), weight grads accumulated. */
+int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
+                             const int64_t* t_rowptr, const int64_t* t_col, const float* t_ew, int64_t n,
+                             int Fin, int Fout, const float* w_rel, const float* w_root, int act,
+                             float* d_x, float* d_w_rel, float* d_w_root, float* d_b,
+                             float* scratch /* [n, Fin] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCM_B200_H */

@@ -1,0 +1,169 @@
+"""GPU tier: the fused CUDA path (through the C ABI) against the golden vectors of the reference and
+against the oracle on seeded inputs.  Tolerances are BASELINE.json's: adjacency / node slots /
+num_nodes bit-exact, beliefs within 1e-5 relative (fp32)."""
+import pytest
+import torch
+
+import gcm_oracle as oracle
+from helpers import dense_cases, load_golden, make_dense_gnn, make_selector, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _run_case(g, style="readme", keep_tuple_every=None):
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    gnn, _ = make_dense_gnn(g["F"], g["H"], g["params"], g["acts"], style)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(g["spec"]), graph_size=g["N"])
+    if mod.edge_selectors is not None:
+        mod.edge_selectors.to(dev)
+    assert mod.fused_plan() is not None, "configuration should take the fused path"
+    hidden = None if g["init"] is None else tuple(t.to(dev) for t in g["init"])
+    with torch.no_grad():
+        for t in range(g["T"]):
+            belief, hidden = mod(g["obs"][t].to(dev), hidden)
+            assert rel_err(belief, g["beliefs"][t]) < TOL, (g["name"], t)
+            if t in g["snaps"]:
+                for a, b in zip(hidden, g["snaps"][t]):
+                    assert torch.equal(a.cpu().float(), b.float()), (g["name"], t)
+            if keep_tuple_every and t % keep_tuple_every == 0:
+                hidden = tuple(hidden)          # force the ingest path (what RayDenseGCM does)
+    assert mod.fused_plan() is not None and mod.fused_plan().validated
+    nodes, adj, weights, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), g["final"][0])
+    assert torch.equal(adj.cpu(), g["final"][1].float())
+    assert torch.equal(num_nodes.cpu(), g["final"][3])
+    assert num_nodes.dtype == torch.long and adj.dtype == torch.float32
+
+
+@pytest.mark.parametrize("name", dense_cases())
+def test_fused_matches_reference_golden(name):
+    _run_case(load_golden(name))
+
+
+@pytest.mark.parametrize("name", ["dense_temporal124_fwd", "dense_denseedge_wrap", "dense_temporal13_both",
+                                  "dense_cosine"])
+def test_fused_sequential_gnn_and_reingest(name):
+    """Same cases with a gcm.nn.Sequential GNN and the hidden state round-tripped through plain
+    tensors every 3 steps (materialize -> ingest)."""
+    _run_case(load_golden(name), style="sequential", keep_tuple_every=3)
+
+
+SEEDED = [
+    # B, N, F, H, T, spec
+    (33, 128, 32, 32, 140, [("temporal", (1, 2, 4), "forward")]),      # BASELINE cfg 2 shape, wraps
+    (16, 128, 8, 32, 20, [("temporal", (1,), "forward")]),             # BASELINE cfg 1 (README)
+    (5, 40, 16, 32, 50, [("temporal", (1, 3), "both")]),
+    (4, 33, 20, 24, 70, [("temporal", (2, 5), "backward"), ("temporal", (1,), "forward")]),
+    (3, 64, 48, 40, 70, [("dense",)]),
+    (2, 256, 128, 128, 12, [("dense",)]),                              # BASELINE cfg 3 shape (fp32 path)
+    (6, 96, 64, 64, 100, [("cosine", 0.5)]),                           # BASELINE cfg 4 shape, reduced N
+    (6, 96, 64, 64, 100, [("euclidean", 2.0)]),
+    (4, 70, 12, 16, 80, [("spatial", 1.0, slice(0, 2), None)]),
+    (3, 1024, 8, 8, 5, [("temporal", (1, 512), "forward")]),           # maximum graph_size
+    (2, 20, 256, 256, 4, [("dense",)]),                                # maximum feature width
+    (3, 12, 5, 7, 30, []),                                             # no selector at all
+]
+
+
+def _clustered(gen, T, B, F, K=8, noise=0.03):
+    centres = torch.randn(K, F, generator=gen) * 1.5
+    sched = torch.randint(0, K, (T,), generator=gen)
+    return (centres[sched].unsqueeze(1).expand(T, B, F) + noise * torch.randn(T, B, F, generator=gen)).contiguous()
+
+
+@pytest.mark.parametrize("B,N,F,H,T,spec", SEEDED)
+def test_fused_matches_oracle_seeded(B, N, F, H, T, spec):
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(1234 + N + F)
+    distance = bool(spec) and spec[0][0] in ("cosine", "euclidean", "spatial")
+    obs = _clustered(gen, T, B, F) if distance else torch.randn(T, B, F, generator=gen)
+    p = oracle.make_params(F, H)
+    gnn, _ = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    hidden, o_hidden = None, None
+    with torch.no_grad():
+        for t in range(T):
+            belief, hidden = mod(obs[t].to(dev), hidden)
+            ref, o_hidden = oracle.dense_gcm_step(obs[t], o_hidden, spec, p, graph_size=N)
+            assert rel_err(belief, ref) < TOL, t
+    if distance:
+        # the edge set depends on a float comparison: the inputs must keep a margin
+        kind = spec[0][0]
+        nodes_o, _, _, nn_o = o_hidden
+        _, d = oracle.distance_edges(nodes_o, torch.zeros(B, N, N), (nn_o - 1).clamp(min=0), kind, spec[0][1],
+                                     *(spec[0][2:4] if kind == "spatial" else ()), return_dists=True)
+        assert float((d - spec[0][1]).abs().min()) > 1e-3
+    nodes, adj, weights, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), o_hidden[0])
+    assert torch.equal(adj.cpu(), o_hidden[1])
+    assert torch.equal(num_nodes.cpu(), o_hidden[3])
+
+
+def test_selectors_standalone_dense_forward():
+    """The selectors' own forward(nodes, adj_mats, edge_weights, num_nodes, B) on dense tensors."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    B, N, F = 7, 19, 6
+    nodes = _clustered(gen, N, B, F).permute(1, 0, 2).contiguous()
+    num_nodes = torch.randint(0, N, (B,), generator=gen)
+    base = (torch.rand(B, N, N, generator=gen) < 0.1).float()
+    for spec in ([("temporal", (1, 3), "both")], [("temporal", (2,), "backward")], [("dense",)],
+                 [("cosine", 0.4)], [("euclidean", 2.5)], [("spatial", 0.8, slice(1, 4), slice(0, 3))]):
+        want = oracle.apply_selectors(nodes, base.clone(), num_nodes, spec)
+        sel = make_selector(spec).to(dev)
+        adj = base.clone().to(dev)
+        got, w = sel(nodes.to(dev), adj, torch.zeros(0, device=dev), num_nodes.to(dev), B)
+        assert got.data_ptr() == adj.data_ptr()                       # in place, like the reference
+        assert torch.equal(got.cpu(), want), spec
+
+
+def test_stale_hidden_raises_and_snapshot_is_stable():
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    p = oracle.make_params(4, 8)
+    gnn, _ = make_dense_gnn(4, 8, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector([("temporal", (1,), "forward")]), graph_size=6)
+    x = torch.randn(3, 4, device=dev)
+    with torch.no_grad():
+        _, h1 = mod(x, None)
+        pinned = tuple(h1)
+        nodes_before = pinned[0].clone()
+        _, h2 = mod(x + 1, h1)
+        assert torch.equal(pinned[0], nodes_before)       # materialised tensors never change
+        assert tuple(h1)[0] is pinned[0]                  # cached snapshot stays readable
+        _, h3 = mod(x, h2)
+        with pytest.raises(RuntimeError, match="stale"):
+            tuple(h2)
+        with pytest.raises(RuntimeError, match="stale"):
+            mod(x, h2)
+
+
+def test_nan_flag_raises_reference_message():
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    p = oracle.make_params(4, 8)
+    gnn, _ = make_dense_gnn(4, 8, p, ("relu", "none"))
+    mod = DenseGCM(gnn.to(dev), graph_size=6)
+    x = torch.full((2, 4), float("nan"), device=dev)
+    with torch.no_grad():
+        _, h = mod(x, None)
+    with pytest.raises(AssertionError, match="Got NaN in returned memory"):
+        tuple(h)
+
+
+def test_cpu_tensors_fail_loudly():
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    p = oracle.make_params(4, 8)
+    gnn, _ = make_dense_gnn(4, 8, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn, edge_selectors=make_selector([("temporal", (1,), "forward")]), graph_size=6)
+    with pytest.raises(_cabi.GcmLibraryError, match="no CPU fallback"):
+        mod(torch.randn(2, 4), None)
