@@ -571,6 +571,278 @@ static int launch_temporal(const TemporalArgs& a, cudaStream_t stream) {
   return gcm_check_launch("k_step_temporal");
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pure-temporal pipelined kernel: a producer warp streams each graph's window of past rows and the
+// observation tile into a shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx); eight consumer warps run the two layers out of shared memory with the layer
+// weights resident in registers.  One persistent CTA per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int TW_G = 32;        // graphs per pipeline stage (one per producer lane)
+constexpr int TW_STAGES = 3;
+constexpr int TW_CONS = 8;      // consumer warps
+constexpr int TW_THREADS = (TW_CONS + 1) * 32;
+constexpr int TW_MAXWIN = 16;   // rows of history staged per graph
+
+struct TemporalWinArgs {
+  gcm_dense_state st;
+  const float* obs;
+  gcm_gnn gnn;
+  float* belief;
+  int32_t* status;
+  TemporalProg prog;
+  int win;            // rows of history per graph = largest offset in prog.doff
+  int uniform_count;  // >= 0: every graph has this count (host mirror), the counter is not read
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int F>
+__global__ void __launch_bounds__(TW_THREADS, 1) k_step_temporal_win(const TemporalWinArgs a) {
+  constexpr int H = 32;
+  constexpr int K1 = 2 * F;
+  extern __shared__ __align__(128) unsigned char tw_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = a.st.N, C = a.st.C, W = a.st.W, B = a.st.B;
+  const int win = a.win;
+  const TemporalProg& P = a.prog;
+
+  // shared-memory carve-up
+  const int stage_floats = TW_G * win * F + TW_G * F;     // history windows + observation tile
+  float* stage_base = reinterpret_cast<float*>(tw_raw);
+  int* cnt_base = reinterpret_cast<int*>(stage_base + (size_t)TW_STAGES * stage_floats);  // [STAGES][G]
+  float* scratch = reinterpret_cast<float*>(cnt_base + TW_STAGES * TW_G);                 // per consumer warp
+  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + TW_CONS * (4 * K1 + 2 * H));
+  uint64_t* empty = full + TW_STAGES;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TW_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, TW_CONS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int n_tiles = (B + TW_G - 1) / TW_G;
+
+  if (warp == TW_CONS) {
+    // ===================== producer warp: lane i feeds graph i of the tile =====================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % TW_STAGES;
+      const uint32_t ph = (it / TW_STAGES) & 1;
+      mbar_wait(empty + s, ph ^ 1);
+      float* st_win = stage_base + (size_t)s * stage_floats;
+      float* st_obs = st_win + TW_G * win * F;
+      const int g = tile * TW_G + lane;
+      const int gt = min(TW_G, B - tile * TW_G);
+      int cnt = 0, nrows = 0;
+      if (lane < gt) {
+        cnt = a.uniform_count >= 0 ? a.uniform_count : __ldcg(a.st.count + g);
+        nrows = min(min(cnt, N - 1), win);   // in-window history rows (the window holds N-1 older nodes)
+      }
+      cnt_base[s * TW_G + lane] = cnt;
+      uint32_t bytes = (uint32_t)nrows * F * 4u;
+      uint32_t total = bytes;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(GCM_FULL_MASK, total, o);
+      total += (uint32_t)gt * F * 4u;
+      __syncwarp();  // the per-lane counts above must be visible before the barrier is armed
+      if (lane == 0) mbar_expect_tx(full + s, total);
+      __syncwarp();
+      if (lane == 0) bulk_g2s(st_obs, a.obs + (size_t)tile * TW_G * F, (uint32_t)gt * F * 4u, full + s);
+      if (nrows > 0) {
+        const float* nodes_g = a.st.nodes + (size_t)g * C * F;
+        float* dst = st_win + ((size_t)lane * win + (win - nrows)) * F;
+        const int first = gcm_slot(cnt - nrows, C);
+        const int n1 = min(nrows, C - first);
+        bulk_g2s(dst, nodes_g + (size_t)first * F, (uint32_t)n1 * F * 4u, full + s);
+        if (n1 < nrows) bulk_g2s(dst + (size_t)n1 * F, nodes_g, (uint32_t)(nrows - n1) * F * 4u, full + s);
+      }
+    }
+    return;
+  }
+
+  // ============================== consumer warps ==============================
+  float* aggx = scratch + warp * (4 * K1 + 2 * H);
+  float* l2in = aggx + 4 * K1;
+  float w1[K1], w2[2 * H];
+#pragma unroll
+  for (int k = 0; k < K1; ++k) w1[k] = __ldg(a.gnn.w1t + k * H + lane);
+#pragma unroll
+  for (int k = 0; k < 2 * H; ++k) w2[k] = __ldg(a.gnn.w2t + k * H + lane);
+  const float bias1 = a.gnn.b1 ? __ldg(a.gnn.b1 + lane) : 0.0f;
+  const float bias2 = a.gnn.b2 ? __ldg(a.gnn.b2 + lane) : 0.0f;
+  const int act1 = a.gnn.act1, act2 = a.gnn.act2;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % TW_STAGES;
+    const uint32_t ph = (it / TW_STAGES) & 1;
+    mbar_wait(full + s, ph);
+    const float* st_win = stage_base + (size_t)s * stage_floats;
+    const float* st_obs = st_win + TW_G * win * F;
+    const int gt = min(TW_G, B - tile * TW_G);
+    for (int gi = warp; gi < gt; gi += TW_CONS) {
+      const int g = tile * TW_G + gi;
+      const int cnt = cnt_base[s * TW_G + gi];
+      const int tpos = cnt;
+      const int lt = min(cnt, N - 1);
+      const int tslot = gcm_slot(tpos, C);
+      const float* wrow = st_win + (size_t)gi * win * F;   // row i <-> offset (win - i) from t
+      float xobs = 0.0f;
+      if (lane < F) {
+        xobs = st_obs[gi * F + lane];
+        a.st.nodes[((size_t)g * C + tslot) * F + lane] = xobs;   // node write (gcm.py:274)
+      }
+      {
+        uint32_t* masks_g = a.st.masks + (size_t)g * C * 2 * W;
+        uint32_t pw = 0u;
+        for (int i = 0; i < P.n_past; ++i) {
+          const int hop = P.past[i];
+          if (hop <= lt && (hop >> 5) == lane) pw |= 1u << (hop & 31);
+        }
+        if (lane < W) {
+          gcm_st_mask(masks_g + ((size_t)tslot * 2 + 0) * W + lane, pw);
+          gcm_st_mask(masks_g + ((size_t)tslot * 2 + 1) * W + lane, 0u);
+        }
+        if (lane < P.n_future) {
+          const int hop = P.future[lane];
+          if (hop <= lt)
+            atomicOr(masks_g + ((size_t)gcm_slot(tpos - hop, C) * 2 + 1) * W + (hop >> 5), 1u << (hop & 31));
+        }
+        if (lane == 0) __stcg(a.st.count + g, cnt + 1);
+      }
+      auto xrow = [&](int di) -> float {   // feature `lane` of the row at program offset doff[di]
+        const int o = P.doff[di];
+        if (o == 0) return xobs;
+        return (o <= lt && lane < F) ? wrow[(win - o) * F + lane] : 0.0f;
+      };
+
+      float h1t = 0.0f, agg2 = 0.0f;
+      for (int c0 = 0; c0 < P.nR; c0 += 4) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = c0 + rr;
+          float ag = 0.0f, xv = 0.0f;
+          if (r < P.nR) {
+            for (int q = 0; q < P.nnb[r]; ++q) ag += xrow(P.nb[r][q]);
+            xv = xrow(P.rD[r]);
+          }
+          if (lane < F) {
+            aggx[rr * K1 + lane] = ag;
+            aggx[rr * K1 + F + lane] = xv;
+          }
+        }
+        __syncwarp();
+        float z0 = bias1, z1 = bias1, z2 = bias1, z3 = bias1;
+#pragma unroll
+        for (int k = 0; k < K1; k += 4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(aggx + 0 * K1 + k);
+          const float4 a1 = *reinterpret_cast<const float4*>(aggx + 1 * K1 + k);
+          const float4 a2 = *reinterpret_cast<const float4*>(aggx + 2 * K1 + k);
+          const float4 a3 = *reinterpret_cast<const float4*>(aggx + 3 * K1 + k);
+          z0 = fmaf(a0.x, w1[k], z0); z0 = fmaf(a0.y, w1[k + 1], z0);
+          z0 = fmaf(a0.z, w1[k + 2], z0); z0 = fmaf(a0.w, w1[k + 3], z0);
+          z1 = fmaf(a1.x, w1[k], z1); z1 = fmaf(a1.y, w1[k + 1], z1);
+          z1 = fmaf(a1.z, w1[k + 2], z1); z1 = fmaf(a1.w, w1[k + 3], z1);
+          z2 = fmaf(a2.x, w1[k], z2); z2 = fmaf(a2.y, w1[k + 1], z2);
+          z2 = fmaf(a2.z, w1[k + 2], z2); z2 = fmaf(a2.w, w1[k + 3], z2);
+          z3 = fmaf(a3.x, w1[k], z3); z3 = fmaf(a3.y, w1[k + 1], z3);
+          z3 = fmaf(a3.z, w1[k + 2], z3); z3 = fmaf(a3.w, w1[k + 3], z3);
+        }
+        const float zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = c0 + rr;
+          if (r < P.nR) {
+            const float hv = gcm_act_fwd(zz[rr], act1);
+            if (r == 0) h1t = hv;
+            else if (P.rd[r] <= lt) agg2 += hv;
+          }
+        }
+        __syncwarp();
+      }
+      l2in[lane] = agg2;
+      l2in[H + lane] = h1t;
+      __syncwarp();
+      float o0 = bias2, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 2 * H; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(l2in + k);
+        o0 = fmaf(v.x, w2[k], o0);
+        o1 = fmaf(v.y, w2[k + 1], o1);
+        o2 = fmaf(v.z, w2[k + 2], o2);
+        o3 = fmaf(v.w, w2[k + 3], o3);
+      }
+      const float out = gcm_act_fwd((o0 + o1) + (o2 + o3), act2);
+      a.belief[(size_t)g * H + lane] = out;
+      if (!isfinite(out)) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
+      __syncwarp();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+}
+
+static size_t tw_smem_bytes(int F, int win) {
+  size_t fl = (size_t)TW_STAGES * (TW_G * win * F + TW_G * F) + (size_t)TW_CONS * (4 * 2 * F + 64);
+  return fl * 4 + (size_t)TW_STAGES * TW_G * 4 + 2 * TW_STAGES * 8 + 128;
+}
+
+template <int F>
+static int launch_temporal_win(const TemporalWinArgs& a, cudaStream_t stream) {
+  const size_t smem = tw_smem_bytes(F, a.win);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_step_temporal_win<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) {
+      gcm_set_error("cudaFuncSetAttribute(temporal_win): %s", cudaGetErrorString(e));
+      return GCM_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int n_tiles = (a.st.B + TW_G - 1) / TW_G;
+  int grid = gcm_num_sms();
+  if (grid > n_tiles) grid = n_tiles;
+  k_step_temporal_win<F><<<grid, TW_THREADS, smem, stream>>>(a);
+  return gcm_check_launch("k_step_temporal_win");
+}
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -616,6 +888,27 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
       (st->F == 8 || st->F == 16 || st->F == 32)) {
     TemporalArgs ta;
     if (build_temporal_prog(sels, n_sels, ta.prog)) {
+      int win = 0;
+      for (int i = 0; i < ta.prog.nD; ++i) win = ta.prog.doff[i] > win ? ta.prog.doff[i] : win;
+      // stage a contiguous history window when it is small and mostly needed rows
+      if (win >= 1 && win <= TW_MAXWIN && win <= 2 * (ta.prog.nD - 1) + 1 &&
+          tw_smem_bytes(st->F, win) <= 200 * 1024 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(st->nodes) & 15) == 0) {
+        TemporalWinArgs wa;
+        wa.st = *st;
+        wa.obs = obs;
+        wa.gnn = *gnn;
+        wa.belief = belief;
+        wa.status = status;
+        wa.prog = ta.prog;
+        wa.win = win;
+        wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
+        switch (st->F) {
+          case 8: return launch_temporal_win<8>(wa, stream);
+          case 16: return launch_temporal_win<16>(wa, stream);
+          default: return launch_temporal_win<32>(wa, stream);
+        }
+      }
       ta.st = *st;
       ta.obs = obs;
       ta.gnn = *gnn;

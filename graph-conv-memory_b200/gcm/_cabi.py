@@ -28,6 +28,8 @@ SEL_NONE, SEL_TEMPORAL, SEL_DENSE, SEL_EUCLIDEAN, SEL_COSINE, SEL_SPATIAL = rang
 DIR = {"forward": 0, "backward": 1, "both": 2}
 ACT = {"none": 0, "tanh": 1, "relu": 2}
 STEP_PURE_TEMPORAL = 1
+STEP_UNIFORM_COUNT = 2
+STEP_COUNT_SHIFT = 8
 
 _LIB_NAME = "libgcm_b200.so"
 _LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib")

@@ -232,6 +232,9 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     if plan.temporal_key is not None and state.pure_key is not None and state.pure_key in ((), plan.temporal_key):
         flags |= _cabi.STEP_PURE_TEMPORAL
         state.pure_key = plan.temporal_key
+        if state.host_count is not None and not torch.cuda.is_current_stream_capturing():
+            # every graph has the same count and the host knows it: spare the kernel the dependent load
+            flags |= _cabi.STEP_UNIFORM_COUNT | (state.host_count << _cabi.STEP_COUNT_SHIFT)
     else:
         state.pure_key = None
     gnn_c = plan.gnn.packed(dev)

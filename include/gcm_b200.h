@@ -120,6 +120,10 @@ const char* gcm_last_error(void);
  * flags: bit 0 = the state is "pure temporal" (built from empty by this same TEMPORAL-only
  *        selector chain), which enables the implicit-adjacency fast kernel. */
 #define GCM_STEP_PURE_TEMPORAL 1
+/*        bit 1 = every graph has the same count, given in bits 8.. of `flags` (host mirror; saves the
+ *        dependent counter load in the pipelined kernel). */
+#define GCM_STEP_UNIFORM_COUNT 2
+#define GCM_STEP_COUNT_SHIFT 8
 int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                        int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
                        void* stream);
