@@ -356,6 +356,7 @@ struct TemporalProg {
   int rD[TP_MAXR];            // index into doff of row r itself
   int nnb[TP_MAXR];
   int nb[TP_MAXR][TP_MAXNB];  // indices into doff of the in-neighbours of row r
+  uint32_t nbmask[TP_MAXR];   // the same as a bitmask over doff indices (valid when nD <= 32)
   int n_past, past[GCM_MAX_HOPS];      // hops written into row t's past mask
   int n_future, future[GCM_MAX_HOPS];  // hops written into the future mask of row t - hop
 };
@@ -545,7 +546,11 @@ static bool build_temporal_prog(const gcm_selector* sels, int n_sels, TemporalPr
       P.nb[r][n++] = ix;
     }
     P.nnb[r] = n;
+    P.nbmask[r] = 0u;
+    for (int q = 0; q < n; ++q)
+      if (P.nb[r][q] < 32) P.nbmask[r] |= 1u << P.nb[r][q];
   }
+  for (int r = P.nR; r < TP_MAXR; ++r) P.nbmask[r] = 0u;
   P.n_past = np;
   P.n_future = nf;
   for (int i = 0; i < np; ++i) P.past[i] = past[i];
@@ -580,7 +585,8 @@ static int launch_temporal(const TemporalArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr int TW_G = 32;        // graphs per pipeline stage (one per producer lane)
 constexpr int TW_STAGES = 3;
-constexpr int TW_CONS = 8;      // consumer warps
+constexpr int TW_CONS = 11;     // consumer warps
+constexpr int TW_MAXD = 12;     // distinct rows of the 2-hop in-neighbourhood (statically unrolled)
 constexpr int TW_THREADS = (TW_CONS + 1) * 32;
 constexpr int TW_MAXWIN = 16;   // rows of history staged per graph
 
@@ -746,56 +752,55 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_step_temporal_win(const Tempo
         }
         if (lane == 0) __stcg(a.st.count + g, cnt + 1);
       }
-      auto xrow = [&](int di) -> float {   // feature `lane` of the row at program offset doff[di]
-        const int o = P.doff[di];
-        if (o == 0) return xobs;
-        return (o <= lt && lane < F) ? wrow[(win - o) * F + lane] : 0.0f;
-      };
-
-      float h1t = 0.0f, agg2 = 0.0f;
-      for (int c0 = 0; c0 < P.nR; c0 += 4) {
+      // distinct rows of the 2-hop in-neighbourhood, feature `lane` of each (statically unrolled: the
+      // program lives in the constant bank, so every index below is an immediate operand)
+      float xv[TW_MAXD];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int r = c0 + rr;
-          float ag = 0.0f, xv = 0.0f;
-          if (r < P.nR) {
-            for (int q = 0; q < P.nnb[r]; ++q) ag += xrow(P.nb[r][q]);
-            xv = xrow(P.rD[r]);
-          }
-          if (lane < F) {
-            aggx[rr * K1 + lane] = ag;
-            aggx[rr * K1 + F + lane] = xv;
-          }
+      for (int i = 0; i < TW_MAXD; ++i) {
+        xv[i] = 0.0f;
+        if (i == 0) {
+          xv[i] = xobs;
+        } else if (i < P.nD) {
+          const int o = P.doff[i];
+          if (o <= lt && lane < F) xv[i] = wrow[(win - o) * F + lane];
         }
-        __syncwarp();
-        float z0 = bias1, z1 = bias1, z2 = bias1, z3 = bias1;
-#pragma unroll
-        for (int k = 0; k < K1; k += 4) {
-          const float4 a0 = *reinterpret_cast<const float4*>(aggx + 0 * K1 + k);
-          const float4 a1 = *reinterpret_cast<const float4*>(aggx + 1 * K1 + k);
-          const float4 a2 = *reinterpret_cast<const float4*>(aggx + 2 * K1 + k);
-          const float4 a3 = *reinterpret_cast<const float4*>(aggx + 3 * K1 + k);
-          z0 = fmaf(a0.x, w1[k], z0); z0 = fmaf(a0.y, w1[k + 1], z0);
-          z0 = fmaf(a0.z, w1[k + 2], z0); z0 = fmaf(a0.w, w1[k + 3], z0);
-          z1 = fmaf(a1.x, w1[k], z1); z1 = fmaf(a1.y, w1[k + 1], z1);
-          z1 = fmaf(a1.z, w1[k + 2], z1); z1 = fmaf(a1.w, w1[k + 3], z1);
-          z2 = fmaf(a2.x, w1[k], z2); z2 = fmaf(a2.y, w1[k + 1], z2);
-          z2 = fmaf(a2.z, w1[k + 2], z2); z2 = fmaf(a2.w, w1[k + 3], z2);
-          z3 = fmaf(a3.x, w1[k], z3); z3 = fmaf(a3.y, w1[k + 1], z3);
-          z3 = fmaf(a3.z, w1[k + 2], z3); z3 = fmaf(a3.w, w1[k + 3], z3);
-        }
-        const float zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int r = c0 + rr;
-          if (r < P.nR) {
-            const float hv = gcm_act_fwd(zz[rr], act1);
-            if (r == 0) h1t = hv;
-            else if (P.rd[r] <= lt) agg2 += hv;
-          }
-        }
-        __syncwarp();
       }
+      // rows of R1 (row r sits at program index r): [sum of in-neighbours | own features]
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const uint32_t m = P.nbmask[rr];
+        float ag = 0.0f;
+#pragma unroll
+        for (int i = 0; i < TW_MAXD; ++i)
+          if ((m >> i) & 1u) ag += xv[i];
+        if (lane < F) {
+          aggx[rr * K1 + lane] = ag;
+          aggx[rr * K1 + F + lane] = xv[rr];
+        }
+      }
+      __syncwarp();
+      float z0 = bias1, z1 = bias1, z2 = bias1, z3 = bias1;
+#pragma unroll
+      for (int k = 0; k < K1; k += 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(aggx + 0 * K1 + k);
+        const float4 a1 = *reinterpret_cast<const float4*>(aggx + 1 * K1 + k);
+        const float4 a2 = *reinterpret_cast<const float4*>(aggx + 2 * K1 + k);
+        const float4 a3 = *reinterpret_cast<const float4*>(aggx + 3 * K1 + k);
+        z0 = fmaf(a0.x, w1[k], z0); z0 = fmaf(a0.y, w1[k + 1], z0);
+        z0 = fmaf(a0.z, w1[k + 2], z0); z0 = fmaf(a0.w, w1[k + 3], z0);
+        z1 = fmaf(a1.x, w1[k], z1); z1 = fmaf(a1.y, w1[k + 1], z1);
+        z1 = fmaf(a1.z, w1[k + 2], z1); z1 = fmaf(a1.w, w1[k + 3], z1);
+        z2 = fmaf(a2.x, w1[k], z2); z2 = fmaf(a2.y, w1[k + 1], z2);
+        z2 = fmaf(a2.z, w1[k + 2], z2); z2 = fmaf(a2.w, w1[k + 3], z2);
+        z3 = fmaf(a3.x, w1[k], z3); z3 = fmaf(a3.y, w1[k + 1], z3);
+        z3 = fmaf(a3.z, w1[k + 2], z3); z3 = fmaf(a3.w, w1[k + 3], z3);
+      }
+      const float h1t = gcm_act_fast(z0, act1);
+      float agg2 = 0.0f;
+      if (1 < P.nR && P.rd[1] <= lt) agg2 += gcm_act_fast(z1, act1);
+      if (2 < P.nR && P.rd[2] <= lt) agg2 += gcm_act_fast(z2, act1);
+      if (3 < P.nR && P.rd[3] <= lt) agg2 += gcm_act_fast(z3, act1);
+      __syncwarp();
       l2in[lane] = agg2;
       l2in[H + lane] = h1t;
       __syncwarp();
@@ -808,7 +813,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) k_step_temporal_win(const Tempo
         o2 = fmaf(v.z, w2[k + 2], o2);
         o3 = fmaf(v.w, w2[k + 3], o3);
       }
-      const float out = gcm_act_fwd((o0 + o1) + (o2 + o3), act2);
+      const float out = gcm_act_fast((o0 + o1) + (o2 + o3), act2);
       a.belief[(size_t)g * H + lane] = out;
       if (!isfinite(out)) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
       __syncwarp();
@@ -891,7 +896,8 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
       int win = 0;
       for (int i = 0; i < ta.prog.nD; ++i) win = ta.prog.doff[i] > win ? ta.prog.doff[i] : win;
       // stage a contiguous history window when it is small and mostly needed rows
-      if (win >= 1 && win <= TW_MAXWIN && win <= 2 * (ta.prog.nD - 1) + 1 &&
+      if (win >= 1 && win <= TW_MAXWIN && win <= 2 * (ta.prog.nD - 1) + 1 && ta.prog.nR <= 4 &&
+          ta.prog.nD <= TW_MAXD &&
           tw_smem_bytes(st->F, win) <= 200 * 1024 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0 &&
           (reinterpret_cast<uintptr_t>(st->nodes) & 15) == 0) {
         TemporalWinArgs wa;

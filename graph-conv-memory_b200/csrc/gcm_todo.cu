@@ -6,8 +6,6 @@
   gcm_set_error(name ": not implemented yet"); \
   return GCM_ERR_UNSUPPORTED
 
-extern "C" int gcm_dense_step_bwd(const gcm_dense_state*, int, const gcm_gnn*, const float*, float*, float*,
-                                  const gcm_gnn_grads*, void*) { GCM_TODO("gcm_dense_step_bwd"); }
 extern "C" int gcm_sparse_write_flatten(float*, const float*, const int64_t*, const int64_t*, const int64_t*,
                                         const int64_t*, int, int, int, int, float*, int64_t*, int32_t*, void*) {
   GCM_TODO("gcm_sparse_write_flatten");

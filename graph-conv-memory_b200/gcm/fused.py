@@ -95,9 +95,12 @@ class GnnPlan:
         b = b_rel if b_rel is not None else b_root
         return None if b is None else b.detach()
 
+    def current_key(self, device):
+        return tuple((p.data_ptr(), p._version) for p in self.params()) + (str(device),)
+
     def packed(self, device):
         """K-major weight packs (include/gcm_b200.h: gcm_gnn), rebuilt only when a parameter changed."""
-        key = tuple((p.data_ptr(), p._version) for p in self.params()) + (str(device),)
+        key = self.current_key(device)
         if key != self._key:
             def kmajor(conv):
                 return torch.cat([conv.lin_rel.weight.detach().t(), conv.lin_root.weight.detach().t()],
@@ -265,7 +268,7 @@ def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tens
     with torch.no_grad():
         feats = module.gnn(nodes, adj, torch.zeros(0, device=state.device), nb, state.N)
         ref = feats[torch.arange(nb, device=state.device), nn - 1]
-    ok = ref.shape == belief[:nb].shape and torch.allclose(ref, belief[:nb].detach(), rtol=1e-3, atol=1e-4)
+    ok = ref.shape == belief[:nb].shape and torch.allclose(ref, belief[:nb].detach(), rtol=1e-3, atol=1e-4, equal_nan=True)
     if not ok:
         warnings.warn(
             "gcm: the GNN looked like a 2-layer DenseGraphConv stack but does not compute one; "
@@ -273,9 +276,128 @@ def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tens
     return bool(ok)
 
 
+class _RootFn(torch.autograd.Function):
+    """Start of a recorded chain of steps.  Runs LAST in backward: clears the running dL/dnodes
+    buffer so the next backward pass over these buffers starts from zero."""
+
+    @staticmethod
+    def forward(ctx, anchor, state):
+        ctx.state = state
+        return anchor.clone()
+
+    @staticmethod
+    def backward(ctx, d_token):
+        st = ctx.state
+        if st.d_nodes is not None:
+            st.d_nodes.zero_()
+        return torch.zeros_like(d_token), None
+
+
+class _IngestFn(torch.autograd.Function):
+    """Chain start for a caller-supplied `nodes` tensor that requires grad (reference
+    tests/test_gcm.py:355-365): routes the accumulated dL/dnodes back to it."""
+
+    @staticmethod
+    def forward(ctx, nodes, state):
+        ctx.state = state
+        ctx.n0 = state.count.clone()
+        return torch.zeros(1, device=nodes.device)
+
+    @staticmethod
+    def backward(ctx, d_token):
+        st = ctx.state
+        B, N, F = st.B, st.N, st.F
+        if st.d_nodes is None:
+            return torch.zeros(B, N, F, device=st.device), None
+        # at ingest time positions == logical indices, so the caller's rows are slots 0..n0-1
+        keep = torch.arange(N, device=st.device).view(1, N, 1) < ctx.n0.view(B, 1, 1)
+        g = st.d_nodes[:, :N, :] * keep
+        st.d_nodes.zero_()
+        return g, None
+
+
+class _StepFn(torch.autograd.Function):
+    """One fused DenseGCM step.  Saves nothing but its step index; backward recomputes from the log."""
+
+    @staticmethod
+    def forward(ctx, x, token, plan, state, *params):
+        belief = torch.empty(state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)
+        _launch_fwd(plan, state, x.detach(), belief)
+        ctx.plan, ctx.state = plan, state
+        ctx.step_index = state.steps
+        ctx.packed = plan.gnn._packed          # keeps the weight packs the kernels point at alive
+        ctx.pkey = plan.gnn._key
+        ctx.has_token = token is not None
+        return belief, torch.zeros(1, device=state.device)
+
+    @staticmethod
+    def backward(ctx, d_belief, d_token):
+        plan, st = ctx.plan, ctx.state
+        gnn = plan.gnn
+        if gnn.current_key(st.device) != ctx.pkey:
+            raise RuntimeError("GNN parameters were modified in place between forward and backward")
+        steps_back = st.steps - ctx.step_index
+        if steps_back > st.C - st.N:
+            raise RuntimeError(
+                f"BPTT window too long for the node log: this step is {steps_back} steps old but the log "
+                f"keeps {st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
+        if st.d_nodes is None:
+            st.d_nodes = torch.zeros(st.B, st.C, st.F, device=st.device, dtype=torch.float32)
+        dev = st.device
+        c1, c2 = gnn.conv1, gnn.conv2
+        g = {
+            "w_rel1": torch.zeros_like(c1.lin_rel.weight, device=dev), "w_root1": torch.zeros_like(c1.lin_root.weight, device=dev),
+            "w_rel2": torch.zeros_like(c2.lin_rel.weight, device=dev), "w_root2": torch.zeros_like(c2.lin_root.weight, device=dev),
+            "b1": torch.zeros(gnn.H1, device=dev), "b2": torch.zeros(gnn.H2, device=dev),
+        }
+        grads = _cabi.GnnGradsC(g["w_rel1"].data_ptr(), g["w_root1"].data_ptr(), g["b1"].data_ptr(),
+                                g["w_rel2"].data_ptr(), g["w_root2"].data_ptr(), g["b2"].data_ptr())
+        d_obs = torch.empty(st.B, st.F, device=dev, dtype=torch.float32)
+        db = d_belief.contiguous().float()
+        _cabi.check(_cabi.lib().gcm_dense_step_bwd(st.c_ref(), steps_back, C.byref(ctx.packed[0]), db.data_ptr(),
+                                                   st.d_nodes.data_ptr(), d_obs.data_ptr(), C.byref(grads),
+                                                   _cabi.stream_ptr(dev)), "gcm_dense_step_bwd")
+        out = []
+        for conv, wr, wo, bb in ((c1, "w_rel1", "w_root1", "b1"), (c2, "w_rel2", "w_root2", "b2")):
+            out.append(g[wr])
+            if conv.lin_rel.bias is not None:
+                out.append(g[bb])
+            out.append(g[wo])
+            if conv.lin_root.bias is not None:
+                out.append(g[bb])
+        return (d_obs, torch.zeros(1, device=dev) if ctx.has_token else None, None, None, *out)
+
+
+def grow_state(state: DenseState, capacity: int) -> DenseState:
+    """Re-home a state in a log with more spare rows (needed before gradients can be recorded on a
+    state that was built without spare capacity)."""
+    nodes, adj, num_nodes = state.materialize()
+    w = state.weights0 if state.weights0 is None else state.materialize_weights()
+    new, _ = DenseState.ingest(nodes, adj, w if w is not None else torch.zeros(0, device=state.device),
+                               num_nodes, capacity)
+    new.pure_key = state.pure_key
+    new.host_count = None if state.host_count is None else min(state.host_count, state.N)
+    new.status = state.status
+    return new
+
+
 def fused_step_grad(plan: FusedPlan, state: DenseState, x: torch.Tensor, token, bptt_capacity: int):
-    raise NotImplementedError("training path lands with gcm_dense_step_bwd")
+    """Recording step.  Returns (belief, token, state) -- the state may have been re-homed."""
+    if state.C - state.N < 1:
+        state = grow_state(state, state.N + max(int(bptt_capacity), 1))
+        token = None
+    if token is None:
+        anchor = torch.zeros(1, device=state.device, requires_grad=True)
+        token = _RootFn.apply(anchor, state)
+        state.chain_start = state.steps
+    elif state.steps + 1 - getattr(state, "chain_start", 0) > state.C - state.N + 1:
+        raise RuntimeError(
+            f"more than {state.C - state.N + 1} recorded steps on one hidden state; raise "
+            "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+    belief, token = _StepFn.apply(x, token, plan, state, *plan.gnn.params())
+    return belief, token, state
 
 
 def ingest_token(state: DenseState, nodes: torch.Tensor):
-    raise NotImplementedError("training path lands with gcm_dense_step_bwd")
+    state.chain_start = state.steps
+    return _IngestFn.apply(nodes, state)

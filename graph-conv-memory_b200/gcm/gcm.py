@@ -210,7 +210,7 @@ class DenseGCM(torch.nn.Module):
 
         xc = x.contiguous()
         if recording:
-            belief, token = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
+            belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
         else:
             belief = fused.fused_step_nograd(plan, state, xc.detach())
             token = None

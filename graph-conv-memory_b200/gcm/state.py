@@ -157,6 +157,10 @@ class DenseHidden:
     def __getitem__(self, i):
         return self.snapshot()[i]
 
+    def detach(self) -> "DenseHidden":
+        """Same graph state, cut from the autograd history (truncated BPTT)."""
+        return DenseHidden(self.claim(), None)
+
     @property
     def num_nodes(self) -> torch.Tensor:
         st = self.claim()

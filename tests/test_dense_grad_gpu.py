@@ -1,0 +1,154 @@
+"""GPU tier: BPTT through the fused path (gcm_dense_step_bwd) against the gradients of the
+unmodified reference (golden) and of the fp64 oracle (autograd on CPU)."""
+import pytest
+import torch
+
+import gcm_oracle as oracle
+from helpers import dense_cases, load_golden, make_dense_gnn, make_selector, named_grads, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _bptt(mod, convs, obs_dev, loss_w, hidden=None):
+    outs = []
+    for t in range(obs_dev.shape[0]):
+        belief, hidden = mod(obs_dev[t], hidden)
+        outs.append(belief)
+    outs = torch.stack(outs)
+    (outs * loss_w).sum().backward()
+    return outs, hidden
+
+
+@pytest.mark.parametrize("name", [n for n in dense_cases() if "grad" in n])
+def test_bptt_matches_reference_golden(name):
+    from gcm.gcm import DenseGCM
+
+    g = load_golden(name)
+    dev = torch.device("cuda:0")
+    gnn, convs = make_dense_gnn(g["F"], g["H"], g["params"], g["acts"])
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(g["spec"]), graph_size=g["N"])
+    obs = g["obs"].to(dev).requires_grad_(True)
+    outs, _ = _bptt(mod, convs, obs, g["loss_w"].to(dev))
+    assert rel_err(outs, g["beliefs"]) < TOL
+    assert rel_err(obs.grad, g["d_obs"]) < 5 * TOL, name
+    got = named_grads(convs)
+    for k, v in g["d_params"].items():
+        assert rel_err(got[k], v) < 5 * TOL, (name, k)
+
+
+SEEDED = [
+    (9, 16, 32, 32, 24, [("temporal", (1, 2, 4), "forward")], ("tanh", "tanh")),   # wraps inside the window
+    (4, 12, 8, 32, 10, [("temporal", (1,), "both")], ("tanh", "tanh")),
+    (3, 10, 20, 12, 14, [("dense",)], ("tanh", "relu")),                           # wraps, complement trick off
+    (2, 40, 16, 24, 30, [("dense",)], ("tanh", "tanh")),                           # nR > 16: complement trick on
+    (3, 24, 12, 10, 30, [("cosine", 0.5)], ("tanh", "tanh")),
+    (3, 9, 70, 40, 6, [("temporal", (2,), "backward"), ("temporal", (1,), "forward")], ("relu", "none")),
+]
+
+
+@pytest.mark.parametrize("B,N,F,H,T,spec,acts", SEEDED)
+def test_bptt_matches_fp64_oracle(B, N, F, H, T, spec, acts):
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4321 + N + F)
+    if spec[0][0] == "cosine":
+        centres = torch.randn(4, F, generator=gen) * 1.5
+        obs = centres[torch.randint(0, 4, (T,), generator=gen)].unsqueeze(1).expand(T, B, F) \
+            + 0.03 * torch.randn(T, B, F, generator=gen)
+        obs = obs.contiguous()
+    else:
+        obs = torch.randn(T, B, F, generator=gen) * 0.5
+    w = torch.randn(T, B, H, generator=gen)
+    p = oracle.make_params(F, H)
+    # fp64 oracle (autograd) is the ground truth; the fp32 oracle gives the reference's own rounding distance
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        o = obs.to(dt).clone().requires_grad_(True)
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in p.items()}
+        outs, _ = oracle.dense_gcm_rollout(o, None, spec, pp, acts, graph_size=N)
+        (outs * w.to(dt)).sum().backward()
+        res[dt] = (o.grad, {k: v.grad for k, v in pp.items()})
+    gnn, convs = make_dense_gnn(F, H, p, acts)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    x = obs.to(dev).requires_grad_(True)
+    _bptt(mod, convs, x, w.to(dev))
+    ref64, ref32 = res[torch.float64], res[torch.float32]
+    assert rel_err(x.grad, ref64[0]) < TOL + rel_err(ref32[0], ref64[0])
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], ref64[1][k]) < TOL + rel_err(ref32[1][k], ref64[1][k]), k
+
+
+def test_grad_reaches_user_supplied_nodes():
+    """Reference tests/test_gcm.py:355-365: gradients flow into a caller-supplied `nodes` tensor."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H = 3, 7, 5, 6
+    gen = torch.Generator().manual_seed(3)
+    p = oracle.make_params(F, H)
+    nodes0 = torch.randn(B, N, F, generator=gen)
+    nn0 = torch.tensor([2, 7, 4])
+    adj0 = torch.zeros(B, N, N)
+    for b in range(B):
+        nodes0[b, int(nn0[b]):] = 0
+        for i in range(1, int(nn0[b])):
+            adj0[b, i, i - 1] = 1
+    obs = torch.randn(4, B, F, generator=gen)
+    spec = [("temporal", (1, 2), "forward")]
+    # oracle
+    n_o = nodes0.clone().requires_grad_(True)
+    hidden = (n_o, adj0, torch.zeros(0), nn0)
+    outs = []
+    for t in range(4):
+        mx, hidden = oracle.dense_gcm_step(obs[t], hidden, spec, p, graph_size=N)
+        outs.append(mx)
+    torch.stack(outs).sum().backward()
+    # fused
+    gnn, convs = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    n_f = nodes0.clone().to(dev).requires_grad_(True)
+    hidden = (n_f, adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
+    outs = []
+    for t in range(4):
+        mx, hidden = mod(obs[t].to(dev), hidden)
+        outs.append(mx)
+    torch.stack(outs).sum().backward()
+    assert rel_err(n_f.grad, n_o.grad) < 5 * TOL
+
+
+def test_it_learns_and_detach():
+    """Reference tests/test_gcm.py:412-439 ("it learns"): 20 Adam steps reduce the loss; truncated BPTT
+    through m_t.detach() keeps working on the same in-place state."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T = 5, 10, 11, 11, 4
+    p = oracle.make_params(F, H)
+    gnn, convs = make_dense_gnn(F, H, p, ("relu", "relu"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector([("temporal", (1,), "forward")]), graph_size=N)
+    opt = torch.optim.Adam(mod.parameters(), lr=0.005)
+    losses = []
+    for _ in range(20):
+        opt.zero_grad()
+        obs, hidden = torch.ones(B, F, device=dev), None
+        for t in range(T):
+            obs, hidden = mod(obs, hidden)
+        loss = torch.norm(obs)
+        loss.backward()
+        losses.append(float(loss))
+        opt.step()
+    assert losses[-1] < losses[0]
+    hidden = None
+    for window in range(3):
+        opt.zero_grad()
+        tot = 0
+        for t in range(6):
+            out, hidden = mod(torch.randn(B, F, device=dev), hidden)
+            tot = tot + out.pow(2).mean()
+        tot.backward()
+        opt.step()
+        hidden = hidden.detach()
+    assert int(tuple(hidden)[3].max()) == N
