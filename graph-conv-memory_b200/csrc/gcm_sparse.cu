@@ -1,0 +1,437 @@
+// Sparse GCM path (reference /root/reference/src/gcm/sparse_gcm.py:72-212):
+//   * node write + flatten of the valid rows            (sparse_gcm.py:111-123, util.py:426-452)
+//   * fused edge generation: TemporalEdge + SpatialRadiusEdge, emitted already coalesced
+//     (sorted by (batch, sink, source), duplicates merged) -- no sort, no COO coalesce
+//                                                        (sparse_edge_selectors/temporal.py:19-63,
+//                                                         sparse_edge_selectors/spatial.py:74-115)
+//   * GraphConv as a CSR segmented gather-reduce fused with the two Linear layers + activation
+//     (torch_geometric.nn.GraphConv; invoked at sparse_gcm.py:178,199), deterministic, and its
+//     backward (transposed-CSR gather for dL/dx, split-K accumulation for the weight gradients).
+#include "gcm_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// node write + flatten
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sparse_write_flatten(float* nodes, const float* x, const int64_t* T,
+                                                              const int64_t* taus, const int64_t* offsets, int N,
+                                                              int F, int tmax, float* flat) {
+  const int b = blockIdx.x;
+  const int t0 = (int)T[b], tau = (int)taus[b];
+  float* nodes_b = nodes + (size_t)b * N * F;
+  const float* x_b = x + (size_t)b * tmax * F;
+  for (int i = threadIdx.x; i < tau * F; i += blockDim.x) {
+    const int k = i / F, f = i - k * F;
+    if (t0 + k < N) nodes_b[(size_t)(t0 + k) * F + f] = x_b[i];
+  }
+  __syncthreads();
+  if (flat) {
+    float* out = flat + offsets[b] * F;
+    const int n = min(t0 + tau, N);
+    for (int i = threadIdx.x; i < n * F; i += blockDim.x) out[i] = nodes_b[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused edge generation
+// ------------------------------------------------------------------------------------------------
+constexpr int EG_SINKS = 128;  // new nodes handled per CTA
+struct EdgeGenArgs {
+  const float* nodes;
+  const int64_t* T;
+  const int64_t* taus;
+  const int64_t* new_off;  // [B+1] exclusive cumsum of taus
+  int N, F;
+  int n_hops;
+  int hops[GCM_MAX_HOPS];
+  int use_radius, pos_start, pos_step, pos_len;
+  float radius;
+  int32_t* deg;             // pass 1: [n_new]
+  const int64_t* edge_off;  // pass 2: [n_new + 1] exclusive cumsum of deg
+  int64_t* edges;           // pass 2: [3, E]
+  int64_t E;
+};
+
+__global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
+  extern __shared__ float eg_pos[];  // [n_src][pos_len] positions of the candidate sources
+  const int b = blockIdx.x;
+  const int t0 = (int)a.T[b], tau = (int)a.taus[b];
+  const int s_begin = t0 + blockIdx.y * EG_SINKS;
+  const int s_end = min(t0 + tau, s_begin + EG_SINKS);
+  if (s_begin >= s_end) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float* nodes_b = a.nodes + (size_t)b * a.N * a.F;
+  if (a.use_radius) {
+    for (int i = threadIdx.x; i < s_end * a.pos_len; i += blockDim.x) {
+      const int k = i / a.pos_len, c = i - k * a.pos_len;
+      eg_pos[i] = nodes_b[(size_t)k * a.F + a.pos_start + c * a.pos_step];
+    }
+    __syncthreads();
+  }
+  for (int s = s_begin + warp; s < s_end; s += nwarps) {
+    const int64_t slot = a.new_off[b] + (s - t0);
+    int64_t base = a.edges ? a.edge_off[slot] : 0;
+    int count = 0;
+    for (int k0 = 0; k0 < s; k0 += 32) {
+      const int k = k0 + lane;
+      bool hit = false;
+      if (k < s) {
+        const int dlt = s - k;
+        for (int h = 0; h < a.n_hops; ++h) hit |= (a.hops[h] == dlt);
+        if (!hit && a.use_radius) {
+          float d2 = 0.0f;
+          for (int c = 0; c < a.pos_len; ++c) {
+            const float df = eg_pos[s * a.pos_len + c] - eg_pos[k * a.pos_len + c];
+            d2 += df * df;
+          }
+          hit = sqrtf(d2) < a.radius;
+        }
+      }
+      const unsigned bal = __ballot_sync(GCM_FULL_MASK, hit);
+      if (a.edges && hit) {
+        const int64_t e = base + __popc(bal & ((1u << lane) - 1u));
+        a.edges[e] = b;
+        a.edges[a.E + e] = s;
+        a.edges[2 * a.E + e] = k;
+      }
+      base += __popc(bal);
+      count += __popc(bal);
+    }
+    if (!a.edges && lane == 0) a.deg[slot] = count;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GraphConv forward: tile of GC_TM rows; gather-reduce into smem, then a register-tiled product with
+// the K-major weight pack streamed through smem in K chunks.
+// ------------------------------------------------------------------------------------------------
+constexpr int GC_TM = 64;      // rows per CTA tile
+constexpr int GC_THREADS = 256;
+constexpr int GC_KC = 32;      // K chunk of the weight pack staged in smem
+
+struct GraphConvFwdArgs {
+  const float* x;         // [n, Fin]
+  const int64_t* rowptr;  // [n+1]
+  const int64_t* col;     // [E]
+  const float* ew;        // [E] or NULL
+  const int64_t* rows;    // [m] rows to evaluate, or NULL for all n
+  int64_t m;
+  int Fin, Fout;
+  const float* wt;        // [2 Fin, Fout]
+  const float* bias;      // [Fout] or NULL
+  int act;
+  float* agg_out;         // [m, Fin] or NULL
+  float* out;             // [m, Fout]
+};
+
+// thread tile: 4 rows x (Fout / 16) columns, Fout in {16, 32, 64, 128} handled via NT = Fout / 16
+template <int NT>
+__global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwdArgs a) {
+  extern __shared__ __align__(16) float gc_smem[];
+  const int Fin = a.Fin, Fout = a.Fout, K = 2 * Fin;
+  float* As = gc_smem;                     // [GC_TM][K + 1]
+  float* Ws = As + GC_TM * (K + 1);        // [GC_KC][Fout]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * GC_TM;
+
+  // ---- phase 1: [sum of in-neighbours | own features] for every row of the tile ----
+  for (int r = warp; r < GC_TM; r += GC_THREADS / 32) {
+    const int64_t li = row0 + r;
+    float* dst = As + r * (K + 1);
+    if (li < a.m) {
+      const int64_t i = a.rows ? a.rows[li] : li;
+      const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+      for (int f0 = 0; f0 < Fin; f0 += 32) {
+        const int f = f0 + lane;
+        float acc = 0.0f;
+        if (f < Fin) {
+          int64_t e = e0;
+          for (; e + 4 <= e1; e += 4) {   // 4 independent gathers in flight
+            const int64_t c0 = a.col[e], c1 = a.col[e + 1], c2 = a.col[e + 2], c3 = a.col[e + 3];
+            float v0 = a.x[c0 * Fin + f], v1 = a.x[c1 * Fin + f], v2 = a.x[c2 * Fin + f], v3 = a.x[c3 * Fin + f];
+            if (a.ew) {
+              v0 *= a.ew[e]; v1 *= a.ew[e + 1]; v2 *= a.ew[e + 2]; v3 *= a.ew[e + 3];
+            }
+            acc += v0; acc += v1; acc += v2; acc += v3;
+          }
+          for (; e < e1; ++e) {
+            float v = a.x[a.col[e] * Fin + f];
+            if (a.ew) v *= a.ew[e];
+            acc += v;
+          }
+          dst[f] = acc;
+          dst[Fin + f] = a.x[i * Fin + f];
+          if (a.agg_out) a.agg_out[li * Fin + f] = acc;
+        }
+      }
+    } else {
+      for (int f = lane; f < K; f += 32) dst[f] = 0.0f;
+    }
+  }
+
+  // ---- phase 2: out = act(A W + b), 4 x NT register tile per thread ----
+  const int tr = tid >> 4, tc = tid & 15;   // 16 row groups x 16 column groups
+  float acc[4][NT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += GC_KC) {
+    __syncthreads();
+    const int kc = min(GC_KC, K - k0);
+    for (int i = tid; i < kc * Fout; i += GC_THREADS) Ws[i] = __ldg(a.wt + (size_t)k0 * Fout + i);
+    __syncthreads();
+    for (int kk = 0; kk < kc; ++kk) {
+      float av[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[(tr * 4 + i) * (K + 1) + k0 + kk];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = tc + 16 * j;
+        const float wv = c < Fout ? Ws[kk * Fout + c] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(av[i], wv, acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t li = row0 + tr * 4 + i;
+    if (li < a.m) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = tc + 16 * j;
+        if (c < Fout) {
+          const float z = acc[i][j] + (a.bias ? __ldg(a.bias + c) : 0.0f);
+          a.out[li * Fout + c] = gcm_act_fwd(z, a.act);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GraphConv backward
+//   kernel A (per tile of rows): dz = d_out * act'(out); d[agg | x_root] = dz [W_rel | W_root];
+//                                weight gradients accumulated per CTA, flushed with atomics
+//   kernel B (per node):         d_x[j] = d_xroot[j] + sum over out-edges (j -> i) of w * d_agg[i]
+// ------------------------------------------------------------------------------------------------
+struct GraphConvBwdArgs {
+  const float* x;        // [n, Fin] layer input
+  const float* agg;      // [m, Fin] saved aggregation of the evaluated rows
+  const float* out;      // [m, Fout] post-activation output
+  const float* d_out;    // [m, Fout]
+  const int64_t* rows;   // [m] or NULL
+  int64_t m, n;
+  int Fin, Fout;
+  const float* w_rel;    // [Fout, Fin]
+  const float* w_root;   // [Fout, Fin]
+  int act;
+  float* d_agg;          // [m, Fin]  (scratch, written)
+  float* d_x;            // [n, Fin]  (root term accumulated here; must be zero-initialised)
+  float* d_w_rel;
+  float* d_w_root;
+  float* d_b;
+};
+
+constexpr int GB_TM = 32;  // rows per CTA iteration
+__global__ void __launch_bounds__(256) k_graphconv_bwd_rows(const GraphConvBwdArgs a) {
+  extern __shared__ __align__(16) float gb_smem[];
+  const int Fin = a.Fin, Fout = a.Fout;
+  float* dz = gb_smem;                        // [GB_TM][Fout]
+  float* in = dz + GB_TM * Fout;              // [GB_TM][2 Fin]  (agg | x)
+  float* accW = in + GB_TM * 2 * Fin;         // [2 Fin][Fout]  element-owned accumulators
+  float* accB = accW + 2 * Fin * Fout;        // [Fout]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * Fin * Fout + Fout; i += blockDim.x) accW[i] = 0.0f;
+  const int64_t n_tiles = (a.m + GB_TM - 1) / GB_TM;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * GB_TM;
+    __syncthreads();
+    for (int i = tid; i < GB_TM * Fout; i += blockDim.x) {
+      const int r = i / Fout, c = i - r * Fout;
+      const int64_t li = row0 + r;
+      float g = 0.0f;
+      if (li < a.m) g = a.d_out[li * Fout + c] * gcm_act_grad(a.out[li * Fout + c], a.act);
+      dz[i] = g;
+    }
+    for (int i = tid; i < GB_TM * Fin; i += blockDim.x) {
+      const int r = i / Fin, f = i - r * Fin;
+      const int64_t li = row0 + r;
+      float va = 0.0f, vx = 0.0f;
+      if (li < a.m) {
+        va = a.agg[li * Fin + f];
+        vx = a.x[(a.rows ? a.rows[li] : li) * Fin + f];
+      }
+      in[r * 2 * Fin + f] = va;
+      in[r * 2 * Fin + Fin + f] = vx;
+    }
+    __syncthreads();
+    // weight gradients: acc[k][c] += sum_r in[r][k] dz[r][c]
+    for (int e = tid; e < 2 * Fin * Fout; e += blockDim.x) {
+      const int k = e / Fout, c = e - k * Fout;
+      float v = 0.0f;
+#pragma unroll 8
+      for (int r = 0; r < GB_TM; ++r) v = fmaf(in[r * 2 * Fin + k], dz[r * Fout + c], v);
+      accW[e] += v;
+    }
+    for (int c = tid; c < Fout; c += blockDim.x) {
+      float v = 0.0f;
+      for (int r = 0; r < GB_TM; ++r) v += dz[r * Fout + c];
+      accB[c] += v;
+    }
+    // input gradients: d_agg[r][f] = sum_c dz[r][c] W_rel[c][f];  d_x[row][f] += sum_c dz[r][c] W_root[c][f]
+    for (int i = tid; i < GB_TM * Fin; i += blockDim.x) {
+      const int r = i / Fin, f = i - r * Fin;
+      const int64_t li = row0 + r;
+      if (li >= a.m) continue;
+      float ga = 0.0f, gx = 0.0f;
+      for (int c = 0; c < Fout; ++c) {
+        const float g = dz[r * Fout + c];
+        ga = fmaf(g, __ldg(a.w_rel + (size_t)c * Fin + f), ga);
+        gx = fmaf(g, __ldg(a.w_root + (size_t)c * Fin + f), gx);
+      }
+      a.d_agg[li * Fin + f] = ga;
+      a.d_x[(a.rows ? a.rows[li] : li) * Fin + f] = gx;   // each evaluated row is unique
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * Fin * Fout; e += blockDim.x) {
+    const int k = e / Fout, c = e - k * Fout;
+    const float v = accW[e];
+    if (v != 0.0f) atomicAdd((k < Fin ? a.d_w_rel + (size_t)c * Fin + k : a.d_w_root + (size_t)c * Fin + (k - Fin)), v);
+  }
+  if (a.d_b)
+    for (int c = tid; c < Fout; c += blockDim.x) atomicAdd(a.d_b + c, accB[c]);
+}
+
+// transposed gather: t_rowptr/t_col group the edges by SOURCE node; t_col holds the LOCAL index (into
+// the m evaluated rows) of each edge's sink.  d_x[j] += sum w * d_agg[t_col[e]]
+__global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg, const int64_t* t_rowptr,
+                                                             const int64_t* t_col, const float* t_ew,
+                                                             int64_t n, int Fin, float* d_x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const int64_t e0 = t_rowptr[j], e1 = t_rowptr[j + 1];
+  if (e0 == e1) return;
+  for (int f0 = 0; f0 < Fin; f0 += 32) {
+    const int f = f0 + lane;
+    if (f >= Fin) break;
+    float acc = 0.0f;
+    for (int64_t e = e0; e < e1; ++e) {
+      float v = d_agg[t_col[e] * Fin + f];
+      if (t_ew) v *= t_ew[e];
+      acc += v;
+    }
+    d_x[j * Fin + f] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, const int64_t* taus,
+                                        const int64_t* offsets, int B, int N, int F, int tmax, float* flat,
+                                        void* stream) {
+  GCM_REQUIRE(nodes && x && T && taus && offsets && B >= 0 && N >= 1 && F >= 1 && tmax >= 0,
+              "sparse_write_flatten: bad arguments");
+  if (B == 0) return GCM_OK;
+  k_sparse_write_flatten<<<B, 256, 0, (cudaStream_t)stream>>>(nodes, x, T, taus, offsets, N, F, tmax, flat);
+  return gcm_check_launch("k_sparse_write_flatten");
+}
+
+extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* taus,
+                                      const int64_t* new_off, int B, int N, int F, int tmax, const int32_t* hops,
+                                      int n_hops, int use_radius, int pos_start, int pos_step, int pos_len,
+                                      float radius, int32_t* deg, const int64_t* edge_off, int64_t* edges,
+                                      int64_t E, void* stream) {
+  GCM_REQUIRE(T && taus && new_off && B >= 0 && N >= 1 && F >= 1, "sparse_build_edges: bad arguments");
+  GCM_REQUIRE(n_hops >= 0 && n_hops <= GCM_MAX_HOPS && (n_hops == 0 || hops), "sparse_build_edges: n_hops=%d", n_hops);
+  GCM_REQUIRE((edges == nullptr) == (edge_off == nullptr), "sparse_build_edges: edges and edge_off go together");
+  GCM_REQUIRE(edges || deg, "sparse_build_edges: pass 1 needs deg");
+  if (use_radius) {
+    GCM_REQUIRE(nodes && pos_len >= 1 && pos_step >= 1 && pos_start >= 0 && pos_start + (pos_len - 1) * pos_step < F,
+                "sparse_build_edges: position slice outside [0,F)");
+    GCM_REQUIRE((size_t)N * pos_len * 4 <= 200 * 1024, "sparse_build_edges: N * pos_len too large for shared memory");
+  }
+  if (B == 0 || tmax == 0) return GCM_OK;
+  EdgeGenArgs a;
+  a.nodes = nodes; a.T = T; a.taus = taus; a.new_off = new_off; a.N = N; a.F = F;
+  a.n_hops = n_hops;
+  for (int i = 0; i < n_hops; ++i) {
+    GCM_REQUIRE(hops[i] >= 1, "sparse_build_edges: hops must be >= 1 (a self edge violates causality)");
+    a.hops[i] = hops[i];
+  }
+  a.use_radius = use_radius; a.pos_start = pos_start; a.pos_step = pos_step; a.pos_len = pos_len;
+  a.radius = radius; a.deg = deg; a.edge_off = edge_off; a.edges = edges; a.E = E;
+  const size_t smem = use_radius ? (size_t)N * pos_len * 4 : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_sparse_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      gcm_set_error("cudaFuncSetAttribute(edges): %s", cudaGetErrorString(e));
+      return GCM_ERR_CUDA;
+    }
+  }
+  dim3 grid(B, (tmax + EG_SINKS - 1) / EG_SINKS);
+  k_sparse_edges<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_sparse_edges");
+}
+
+extern "C" int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew,
+                                        const int64_t* rows, int64_t m, int Fin, int Fout, const float* wt,
+                                        const float* bias, int act, float* agg_out, float* out, void* stream) {
+  GCM_REQUIRE(x && rowptr && wt && out && m >= 0, "sparse_graphconv_fwd: bad arguments");
+  GCM_REQUIRE(Fin >= 1 && Fin <= 128 && Fout >= 1 && Fout <= 128, "sparse_graphconv_fwd: Fin=%d Fout=%d outside [1,128]",
+              Fin, Fout);
+  if (m == 0) return GCM_OK;
+  GraphConvFwdArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out};
+  const size_t smem = ((size_t)GC_TM * (2 * Fin + 1) + (size_t)GC_KC * Fout) * 4;
+  const int64_t grid = (m + GC_TM - 1) / GC_TM;
+  GCM_REQUIRE(grid < 2147483647LL, "sparse_graphconv_fwd: too many rows");
+  const int nt = (Fout + 15) / 16;
+  cudaError_t e = cudaSuccess;
+#define GC_LAUNCH(NT)                                                                                          \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      e = cudaFuncSetAttribute(k_graphconv_fwd<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e == cudaSuccess) k_graphconv_fwd<NT><<<(unsigned)grid, GC_THREADS, smem, (cudaStream_t)stream>>>(a);  \
+  } while (0)
+  if (nt <= 1) GC_LAUNCH(1);
+  else if (nt <= 2) GC_LAUNCH(2);
+  else if (nt <= 4) GC_LAUNCH(4);
+  else GC_LAUNCH(8);
+#undef GC_LAUNCH
+  if (e != cudaSuccess) {
+    gcm_set_error("cudaFuncSetAttribute(graphconv_fwd): %s", cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
+  return gcm_check_launch("k_graphconv_fwd");
+}
+
+extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
+                                        const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
+                                        const int64_t* t_col, const float* t_ew, int Fin, int Fout,
+                                        const float* w_rel, const float* w_root, int act, float* d_agg, float* d_x,
+                                        float* d_w_rel, float* d_w_root, float* d_b, void* stream) {
+  GCM_REQUIRE(x && agg && out && d_out && t_rowptr && w_rel && w_root && d_agg && d_x && d_w_rel && d_w_root,
+              "sparse_graphconv_bwd: null pointer");
+  GCM_REQUIRE(Fin >= 1 && Fin <= 128 && Fout >= 1 && Fout <= 128 && m >= 0 && n >= 0,
+              "sparse_graphconv_bwd: bad dims");
+  if (m == 0 || n == 0) return GCM_OK;
+  GraphConvBwdArgs a{x, agg, out, d_out, rows, m, n, Fin, Fout, w_rel, w_root, act, d_agg, d_x, d_w_rel, d_w_root, d_b};
+  const size_t smem = ((size_t)GB_TM * Fout + (size_t)GB_TM * 2 * Fin + (size_t)2 * Fin * Fout + Fout) * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_graphconv_bwd_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    gcm_set_error("cudaFuncSetAttribute(graphconv_bwd): %s", cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
+  const int64_t n_tiles = (m + GB_TM - 1) / GB_TM;
+  int grid = 2 * gcm_num_sms();
+  if (grid > n_tiles) grid = (int)n_tiles;
+  k_graphconv_bwd_rows<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  if (int rc = gcm_check_launch("k_graphconv_bwd_rows")) return rc;
+  const int64_t g2 = (n + 7) / 8;
+  GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
+  k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+  return gcm_check_launch("k_graphconv_bwd_gather");
+}

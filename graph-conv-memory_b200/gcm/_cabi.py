@@ -83,13 +83,12 @@ _SIGNATURES = {
     "gcm_state_ingest": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P, _P]),
     "gcm_euclid_batchmean": (_I, [C.POINTER(DenseStateC), _P, _I, _P, _P, _P]),
     "gcm_select_dense": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(SelectorC), _P]),
-    "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "gcm_sparse_temporal_edges": (_I, [_P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _L, _P]),
-    "gcm_sparse_radius_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_float, _L, _P, _P, _P,
-                                     _L, _P]),
-    "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
-    "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P,
-                                      _P, _P, _P]),
+    "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
+                                    _P, _P, _L, _P]),
+    "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
+                                      _P, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,0 +1,200 @@
+"""Host side of the sparse GCM kernels (csrc/gcm_sparse.cu): edge generation, CSR bookkeeping and
+the GraphConv autograd function.  torch is used for allocation and for the small index arithmetic
+(cumsum / bincount over per-graph or per-row counters); gathers, reductions, the Linear layers and
+their gradients run in the CUDA kernels behind the C ABI.  CUDA only, no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from gcm import _cabi
+
+
+def _excl_cumsum(v: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros(v.numel() + 1, dtype=torch.long, device=v.device)
+    torch.cumsum(v, 0, out=out[1:])
+    return out
+
+
+def ragged_arange(lengths: torch.Tensor, total: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(owner, position-within-owner) of every element of a ragged batch with the given lengths."""
+    lengths = lengths.long()
+    owners = torch.repeat_interleave(torch.arange(lengths.numel(), device=lengths.device), lengths,
+                                     output_size=total)
+    starts = torch.cumsum(lengths, 0) - lengths
+    pos = torch.arange(owners.numel(), device=lengths.device) - starts[owners]
+    return owners, pos
+
+
+def write_flatten(nodes: torch.Tensor, x: torch.Tensor, T: torch.Tensor, taus: torch.Tensor,
+                  offsets: torch.Tensor, n_flat: int, want_flat: bool = True):
+    """In place: nodes[b, T_b + k] = x[b, k]; returns flat [n_flat, F] (valid rows of every graph)."""
+    _cabi.require_cuda(nodes, "SparseGCM nodes")
+    B, N, F = nodes.shape
+    flat = torch.empty(n_flat, F, device=nodes.device, dtype=torch.float32) if want_flat else None
+    _cabi.check(_cabi.lib().gcm_sparse_write_flatten(nodes.data_ptr(), x.data_ptr(), T.data_ptr(), taus.data_ptr(),
+                                                     offsets.data_ptr(), B, N, F, x.shape[1], _cabi.ptr(flat),
+                                                     _cabi.stream_ptr(nodes.device)), "gcm_sparse_write_flatten")
+    return flat
+
+
+class _WriteFlattenFn(torch.autograd.Function):
+    """nodes_out = nodes with the new observations written; flat = valid rows of nodes_out."""
+
+    @staticmethod
+    def forward(ctx, nodes, x, T, taus, offsets, n_flat):
+        out = nodes.detach().clone()
+        flat = write_flatten(out, x.detach().contiguous(), T, taus, offsets, n_flat)
+        ctx.meta = (T, taus, offsets, nodes.shape, x.shape)
+        return out, flat
+
+    @staticmethod
+    def backward(ctx, d_nodes_out, d_flat):
+        T, taus, offsets, nshape, xshape = ctx.meta
+        B, N, F = nshape
+        dev = T.device
+        vb, vk = ragged_arange(T + taus)                    # every valid row of the flat layout
+        d_nodes = torch.zeros(nshape, device=dev) if d_nodes_out is None else d_nodes_out.clone()
+        if d_flat is not None:
+            d_nodes[vb, vk] += d_flat
+        nb, nk = ragged_arange(taus)                        # the rows that came from x
+        d_x = torch.zeros(xshape, device=dev)
+        d_x[nb, nk] = d_nodes[nb, nk + T[nb]]
+        d_nodes[nb, nk + T[nb]] = 0
+        return d_nodes, d_x, None, None, None, None
+
+
+def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_off: torch.Tensor, n_new: int,
+                tmax: int, hops: Sequence[int], radius: Optional[Tuple[slice, float]]) -> torch.Tensor:
+    """Coalesced edges (batch, sink, source) int64 [3, E] of the new nodes (gcm_sparse_build_edges)."""
+    _cabi.require_cuda(nodes, "sparse edge selector")
+    B, N, F = nodes.shape
+    dev = nodes.device
+    if n_new == 0 or (not hops and radius is None):
+        return torch.zeros(3, 0, dtype=torch.long, device=dev)
+    hops_t = torch.tensor(sorted(set(int(h) for h in hops)), dtype=torch.int32)
+    hops_c = (_cabi.C.c_int32 * max(len(hops_t), 1))(*hops_t.tolist())
+    use_r, p0, pst, pl, rad = 0, 0, 1, 0, 0.0
+    if radius is not None:
+        sl, rad = radius
+        p0, p1, pst = sl.indices(F)
+        pl = len(range(p0, p1, pst))
+        use_r = 1
+        if pst < 1 or pl < 1:
+            raise _cabi.GcmLibraryError("SpatialRadiusEdge: empty or negative-step position slice")
+    nodes_c = nodes.detach().contiguous()
+    lib = _cabi.lib()
+    stream = _cabi.stream_ptr(dev)
+    deg = torch.empty(n_new, dtype=torch.int32, device=dev)
+    args = (nodes_c.data_ptr(), T.data_ptr(), taus.data_ptr(), new_off.data_ptr(), B, N, F, tmax, hops_c,
+            len(hops_t), use_r, p0, pst, pl, float(rad))
+    _cabi.check(lib.gcm_sparse_build_edges(*args, deg.data_ptr(), None, None, 0, stream), "gcm_sparse_build_edges")
+    edge_off = _excl_cumsum(deg.long())
+    E = int(edge_off[-1].item())
+    edges = torch.empty(3, E, dtype=torch.long, device=dev)
+    if E:
+        _cabi.check(lib.gcm_sparse_build_edges(*args, None, edge_off.data_ptr(), edges.data_ptr(), E, stream),
+                    "gcm_sparse_build_edges")
+    return edges
+
+
+class Csr:
+    """Edges grouped by sink over the flat node numbering, plus (lazily) the transposed grouping."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n: int):
+        self.rowptr, self.col, self.n = rowptr, col, n
+        self._t = {}
+
+    @classmethod
+    def from_sorted_edges(cls, flat_sink: torch.Tensor, flat_src: torch.Tensor, n: int) -> "Csr":
+        counts = torch.bincount(flat_sink, minlength=n) if flat_sink.numel() else torch.zeros(
+            n, dtype=torch.long, device=flat_sink.device)
+        return cls(_excl_cumsum(counts), flat_src.contiguous(), n)
+
+    def transposed(self, rows: Optional[torch.Tensor]):
+        """(t_rowptr [n+1], t_col [E']) grouping by SOURCE the edges whose sink is an evaluated row;
+        t_col = position of that sink among the evaluated rows."""
+        key = None if rows is None else rows.data_ptr()
+        if key not in self._t:
+            dev = self.col.device
+            if rows is None:
+                deg = self.rowptr[1:] - self.rowptr[:-1]
+                local = torch.repeat_interleave(torch.arange(self.n, device=dev), deg, output_size=self.col.numel())
+                src = self.col
+            else:
+                deg = self.rowptr[rows + 1] - self.rowptr[rows]
+                owner, pos = ragged_arange(deg)
+                src = self.col[self.rowptr[rows][owner] + pos]
+                local = owner
+            perm = torch.argsort(src, stable=True)
+            counts = torch.bincount(src, minlength=self.n) if src.numel() else torch.zeros(
+                self.n, dtype=torch.long, device=dev)
+            self._t[key] = (_excl_cumsum(counts), local[perm].contiguous())
+        return self._t[key]
+
+
+def _kmajor(w_rel: torch.Tensor, w_root: torch.Tensor) -> torch.Tensor:
+    return torch.cat([w_rel.detach().t(), w_root.detach().t()], dim=0).contiguous()
+
+
+class _GraphConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_rel, bias, w_root, csr: Csr, rows, act: int):
+        x = x.contiguous()
+        n, Fin = x.shape
+        Fout = w_rel.shape[0]
+        m = n if rows is None else rows.numel()
+        dev = x.device
+        need_grad = any(t is not None and t.requires_grad for t in (x, w_rel, bias, w_root))
+        agg = torch.empty(m, Fin, device=dev) if need_grad else None
+        out = torch.empty(m, Fout, device=dev)
+        wt = _kmajor(w_rel, w_root)
+        b = None if bias is None else bias.detach().contiguous()
+        _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
+            x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), None, _cabi.ptr(rows), m, Fin, Fout,
+            wt.data_ptr(), _cabi.ptr(b), act, _cabi.ptr(agg), out.data_ptr(), _cabi.stream_ptr(dev)),
+            "gcm_sparse_graphconv_fwd")
+        ctx.csr, ctx.rows, ctx.act, ctx.has_bias = csr, rows, act, bias is not None
+        ctx.save_for_backward(x, agg, out, w_rel, w_root)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, agg, out, w_rel, w_root = ctx.saved_tensors
+        csr, rows = ctx.csr, ctx.rows
+        n, Fin = x.shape
+        Fout = w_rel.shape[0]
+        m = out.shape[0]
+        dev = x.device
+        t_rowptr, t_col = csr.transposed(rows)
+        d_x = torch.zeros(n, Fin, device=dev)
+        d_agg = torch.empty(m, Fin, device=dev)
+        d_w_rel = torch.zeros_like(w_rel)
+        d_w_root = torch.zeros_like(w_root)
+        d_b = torch.zeros(Fout, device=dev) if ctx.has_bias else None
+        _cabi.check(_cabi.lib().gcm_sparse_graphconv_bwd(
+            x.data_ptr(), agg.data_ptr(), out.data_ptr(), d_out.contiguous().data_ptr(), _cabi.ptr(rows), m, n,
+            t_rowptr.data_ptr(), t_col.data_ptr(), None, Fin, Fout, w_rel.detach().contiguous().data_ptr(),
+            w_root.detach().contiguous().data_ptr(), ctx.act, d_agg.data_ptr(), d_x.data_ptr(),
+            d_w_rel.data_ptr(), d_w_root.data_ptr(), _cabi.ptr(d_b), _cabi.stream_ptr(dev)),
+            "gcm_sparse_graphconv_bwd")
+        return d_x, d_w_rel, d_b, d_w_root, None, None, None
+
+
+def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none"):
+    return _GraphConvFn.apply(x, w_rel, bias, w_root, csr, rows, _cabi.ACT[act])
+
+
+def graph_conv(x, edge_index, edge_weight, w_rel, bias, w_root, act: str = "none"):
+    """GraphConv on a PyG-style edge_index [2, E] (row 0 = source, row 1 = sink).  Edge weights other
+    than 1 are not part of the hot path (the reference forces them to 1, sparse_gcm.py:160-164)."""
+    _cabi.require_cuda(x, "GraphConv")
+    if edge_weight is not None and edge_weight.numel() and not bool((edge_weight == 1).all()):
+        raise _cabi.GcmLibraryError("GraphConv kernels support unit edge weights only")
+    n = x.shape[0]
+    src, dst = edge_index[0], edge_index[1]
+    order = torch.argsort(dst * n + src) if src.numel() else src
+    csr = Csr.from_sorted_edges(dst[order], src[order], n)
+    return graph_conv_csr(x, csr, None, w_rel, bias, w_root, act)

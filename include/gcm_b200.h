@@ -165,43 +165,45 @@ int gcm_select_dense(const float* nodes, float* adj, const int64_t* num_nodes, i
 /* ---- sparse path (sparse_gcm.py:72-212) -------------------------------------------------- */
 
 /* Node write (sparse_gcm.py:111-123) + flat gather (util.py:426-452): nodes[b, T_b + k] = x[b, k]
- * for k < tau_b; flat[offset_b + k] = nodes[b, k] for k < T_b + tau_b, offset = exclusive
- * cumsum(T + tau) (util.py:234-240), supplied by the caller in `offsets` [B+1] (int64).
- * out_idx[j] = flat index of the j-th new node (ordered by b, then k). */
+ * for k < tau_b (x is [B, tmax, F], zero padded); flat[offsets[b] + k] = nodes[b, k] for
+ * k < T_b + tau_b, offsets = exclusive cumsum(T + tau) (util.py:234-240), [B+1] int64.
+ * `nodes` [B,N,F] is updated in place (the caller clones, like sparse_gcm.py:109). flat may be NULL. */
 int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, const int64_t* taus,
-                             const int64_t* offsets, const int64_t* tau_offsets, int B, int N, int F,
-                             int tmax, float* flat, int64_t* out_idx, int32_t* status, void* stream);
+                             const int64_t* offsets, int B, int N, int F, int tmax, float* flat,
+                             void* stream);
 
-/* TemporalEdge (sparse_edge_selectors/temporal.py:19-63): counts / fills edges (b, sink, source) for
- * the new nodes.  Two-pass: call with edges == NULL to get per-new-node degrees in `deg`
- * [n_new], then with the exclusive scan of deg in `edge_off` to fill `edges` int64 [3, E]. */
-int gcm_sparse_temporal_edges(const int64_t* T, const int64_t* taus, const int64_t* tau_offsets, int B,
-                              const int32_t* hops, int n_hops, int64_t n_new, int32_t* deg,
-                              const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
-
-/* SpatialRadiusEdge, causal (sparse_edge_selectors/spatial.py:74-115): same two-pass protocol; the
- * candidate sources of new node s are all k < s of the same graph with ||pos_s - pos_k||_2 < radius. */
-int gcm_sparse_radius_edges(const float* nodes, const int64_t* T, const int64_t* taus,
-                            const int64_t* tau_offsets, int B, int N, int F, int pos_start, int pos_step,
-                            int pos_len, float radius, int64_t n_new, int32_t* deg,
-                            const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
+/* Fused edge selectors for the new nodes s in [T_b, T_b + tau_b): sources k < s with
+ * (s - k in hops) [TemporalEdge, sparse_edge_selectors/temporal.py:19-63] OR
+ * ||pos_s - pos_k||_2 < radius [SpatialRadiusEdge causal, sparse_edge_selectors/spatial.py:74-115;
+ * pos = nodes[..., pos_start + c * pos_step], c < pos_len].  Edges come out as rows
+ * (batch, sink, source) already coalesced: sorted, duplicates merged -- what the reference obtains
+ * from three COO coalesces (sparse_gcm.py:132-139,152).  Two passes: edges == NULL writes the
+ * in-degree of every new node to deg [n_new] (ordered by b, then s; new_off = exclusive cumsum of
+ * taus, [B+1]); with edge_off = exclusive cumsum of deg ([n_new+1]) the second call fills
+ * edges int64 [3, E]. */
+int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* taus, const int64_t* new_off,
+                           int B, int N, int F, int tmax, const int32_t* hops, int n_hops, int use_radius,
+                           int pos_start, int pos_step, int pos_len, float radius, int32_t* deg,
+                           const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
 
 /* GraphConv over a CSR grouped by sink (torch_geometric.nn.GraphConv; call sites
  * ray_sparse_gcm.py:37-40, invoked at sparse_gcm.py:178,199):
- *   out[i] = act(W_rel (sum_{e in row i} w_e x[col[e]]) + b + W_root x[i])
- * x [n, Fin]; rowptr int64 [n+1]; col int64 [E]; ew float [E] or NULL (== 1); wt = K-major pack
- * [2 Fin, Fout] as in gcm_gnn.  Deterministic (segmented gather-reduce, no atomics). */
+ *   out[r] = act(W_rel (sum_{e in row i} w_e x[col[e]]) + b + W_root x[i]),  i = rows ? rows[r] : r
+ * x [n, Fin]; rowptr int64 [n+1]; col int64 [E]; ew float [E] or NULL (== 1); rows int64 [m] or NULL
+ * (all rows, m == n); wt = K-major pack [2 Fin, Fout] as in gcm_gnn.  Deterministic segmented
+ * gather-reduce (no atomics).  agg_out [m, Fin] (or NULL) receives the aggregation for the backward. */
 int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew,
-                             int64_t n, int Fin, int Fout, const float* wt, const float* bias, int act,
-                             float* agg_out /* [n, Fin] or NULL: saved for backward */, float* out,
-                             void* stream);
-/* Backward: given d_out [n,Fout], out (post-activation), x, agg and the TRANSPOSED csr (grouped by
- * source): d_x [n,Fin] (written), weight grads accumulated. */
+                             const int64_t* rows, int64_t m, int Fin, int Fout, const float* wt,
+                             const float* bias, int act, float* agg_out, float* out, void* stream);
+
+/* Backward of the above.  t_rowptr [n+1] / t_col [E] / t_ew group the same edges by SOURCE node, with
+ * t_col holding the position (in 0..m-1) of the edge's sink among the evaluated rows.  d_x [n, Fin]
+ * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate. */
 int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
-                             const int64_t* t_rowptr, const int64_t* t_col, const float* t_ew, int64_t n,
-                             int Fin, int Fout, const float* w_rel, const float* w_root, int act,
-                             float* d_x, float* d_w_rel, float* d_w_root, float* d_b,
-                             float* scratch /* [n, Fin] */, void* stream);
+                             const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
+                             const int64_t* t_col, const float* t_ew, int Fin, int Fout, const float* w_rel,
+                             const float* w_root, int act, float* d_agg, float* d_x, float* d_w_rel,
+                             float* d_w_root, float* d_b, void* stream);
 
 #ifdef __cplusplus
 }

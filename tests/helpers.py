@@ -88,3 +88,48 @@ def rel_err(a, b):
     """max |a-b| / max(1, max|b|): the parity tolerances of BASELINE.json are relative."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def make_sparse_gnn(F, H, params, acts, style="readme"):
+    from gcm.nn import GraphConv, Sequential
+
+    if style == "sequential":
+        g = Sequential("x, edges, weights", [
+            (GraphConv(F, H), "x, edges, weights -> x"), ACT[acts[0]](),
+            (GraphConv(H, H), "x, edges, weights -> x"), ACT[acts[1]](),
+        ])
+        convs = [m for m in g.modules() if type(m).__name__ == "GraphConv"]
+    else:
+        class GNN(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.gc0 = GraphConv(F, H)
+                self.a0 = ACT[acts[0]]()
+                self.gc1 = GraphConv(H, H)
+                self.a1 = ACT[acts[1]]()
+
+            def forward(self, x, edges, weights):
+                x = self.a0(self.gc0(x, edges, weights))
+                return self.a1(self.gc1(x, edges, weights))
+
+        g = GNN()
+        convs = [g.gc0, g.gc1]
+    with torch.no_grad():
+        convs[0].lin_rel.weight.copy_(params["w_rel1"]); convs[0].lin_rel.bias.copy_(params["b1"])
+        convs[0].lin_root.weight.copy_(params["w_root1"])
+        convs[1].lin_rel.weight.copy_(params["w_rel2"]); convs[1].lin_rel.bias.copy_(params["b2"])
+        convs[1].lin_root.weight.copy_(params["w_root2"])
+    return g, convs
+
+
+def make_sparse_selector(spec):
+    from gcm.sparse_edge_selectors.spatial import SpatialRadiusEdge
+    from gcm.sparse_edge_selectors.temporal import TemporalEdge
+
+    if not spec:
+        return None
+    assert len(spec) == 1
+    s = spec[0]
+    if s[0] == "temporal":
+        return TemporalEdge(list(s[1]))
+    return SpatialRadiusEdge(s[1], s[2])

@@ -1,0 +1,161 @@
+"""GPU tier: the sparse GCM path (edge generation, CSR GraphConv fwd/bwd through the C ABI) against the
+golden vectors of the unmodified reference and against the oracle on seeded inputs.  Edge lists,
+node slots and T bit-exact; outputs and gradients within 1e-5 relative (fp32)."""
+import pytest
+import torch
+
+import gcm_oracle as oracle
+from helpers import (load_golden, make_dense_gnn, make_selector, make_sparse_gnn, make_sparse_selector,
+                     named_grads, rel_err, sparse_cases)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", sparse_cases())
+@pytest.mark.parametrize("style", ["readme", "sequential"])
+def test_sparse_matches_reference_golden(name, style):
+    from gcm.sparse_gcm import SparseGCM
+
+    g = load_golden(name)
+    dev = torch.device("cuda:0")
+    gnn, convs = make_sparse_gnn(g["F"], g["H"], g["params"], g["acts"], style)
+    mod = SparseGCM(gnn.to(dev), edge_selectors=make_sparse_selector(g["spec"]),
+                    aux_edge_selectors=make_sparse_selector(g["aux"]), graph_size=g["N"], max_hops=g["max_hops"])
+    assert mod.fused_plan() is not None
+    hidden = None
+    xs, outs = [], []
+    for (x, taus), want in zip(g["calls"], g["outs"]):
+        xd = x.to(dev).requires_grad_("d_x" in g)
+        mx, hidden = mod(xd, taus.to(dev), hidden)
+        assert rel_err(mx, want) < TOL, name
+        xs.append(xd)
+        outs.append(mx)
+    nodes, adj, T = hidden
+    assert torch.equal(nodes.detach().cpu(), g["final_nodes"])
+    assert adj.is_sparse and tuple(adj.shape) == (g["B"], g["N"], g["N"])
+    assert torch.equal(adj.coalesce().indices().cpu(), g["final_edges"])       # (batch, sink, source), coalesced
+    assert torch.equal(adj.coalesce().values().cpu(), torch.ones(g["final_edges"].shape[1]))
+    assert torch.equal(T.cpu(), g["final_T"]) and T.dtype == torch.long
+    if "d_x" in g:
+        sum((o * w.to(dev)).sum() for o, w in zip(outs, g["loss_w"])).backward()
+        for xd, want in zip(xs, g["d_x"]):
+            assert rel_err(xd.grad, want) < 5 * TOL, name
+        got = named_grads(convs)
+        for k, v in g["d_params"].items():
+            assert rel_err(got[k], v) < 5 * TOL, (name, k)
+
+
+SEEDED = [
+    # B, N, F, H, calls (list of taus), temporal hops, radius
+    (5, 64, 64, 64, [[64, 40, 1, 17, 33]], (1,), 0.25),             # BASELINE cfg 5 shape, reduced N/B
+    (3, 96, 16, 32, [[30, 20, 10], [25, 30, 5], [40, 46, 81]], (1, 2, 4), None),
+    (2, 300, 8, 24, [[300, 150]], (), 0.4),
+    (4, 20, 100, 128, [[5, 5, 5, 5], [1, 2, 3, 4]], (2,), 0.6),     # widest supported layer
+    (3, 12, 6, 7, [[0, 3, 12]], (1,), None),                        # an empty update in the batch
+]
+
+
+@pytest.mark.parametrize("B,N,F,H,calls,hops,radius", SEEDED)
+def test_sparse_matches_oracle_seeded(B, N, F, H, calls, hops, radius):
+    from gcm.sparse_gcm import SparseGCM
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(77 + N + F)
+    p = oracle.make_params(F, H)
+    spec = [("temporal", hops)] if hops else None
+    aux = [("spatial_radius", slice(0, 2), radius)] if radius else None
+    gnn, convs = make_sparse_gnn(F, H, p, ("tanh", "tanh"))
+    mod = SparseGCM(gnn.to(dev), edge_selectors=make_sparse_selector(spec), aux_edge_selectors=make_sparse_selector(aux),
+                    graph_size=N)
+    p_or = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    hidden, o_hidden = None, None
+    pairs, loss, o_loss = [], 0, 0
+    for taus in calls:
+        taus = torch.tensor(taus)
+        tmax = int(taus.max())
+        x = torch.randn(B, tmax, F, generator=gen) * 0.5
+        x[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, tmax, 2, generator=gen), dim=1)
+        for b in range(B):
+            x[b, int(taus[b]):] = 0
+        w = torch.randn(B, tmax, H, generator=gen)
+        xd = x.to(dev).requires_grad_(True)
+        xo = x.clone().requires_grad_(True)
+        mx, hidden = mod(xd, taus.to(dev), hidden)
+        omx, o_hidden = oracle.sparse_gcm_forward(xo, taus, o_hidden, spec, p_or, graph_size=N, aux_selectors=aux)
+        assert rel_err(mx, omx) < TOL
+        assert torch.equal(hidden[0].detach().cpu(), o_hidden[0].detach())
+        assert torch.equal(hidden[1].coalesce().indices().cpu(), o_hidden[1])
+        assert torch.equal(hidden[2].cpu(), o_hidden[2])
+        loss = loss + (mx * w.to(dev)).sum()
+        o_loss = o_loss + (omx * w).sum()
+        pairs.append((xd, xo))
+    loss.backward()
+    o_loss.backward()
+    for xd, xo in pairs:
+        assert rel_err(xd.grad, xo.grad) < 5 * TOL
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], p_or[k].grad) < 5 * TOL, k
+
+
+def test_dense_and_sparse_agree():
+    """Reference tests/test_sparse_gcm.py:427-462 (TestDenseVsSparse.test_temporal_edges): the same weights in
+    DenseGraphConv and GraphConv stacks give the same beliefs, nodes and edge sets."""
+    from gcm.gcm import DenseGCM
+    from gcm.sparse_gcm import SparseGCM
+
+    dev = torch.device("cuda:0")
+    F, B, ts, N = 3, 3, 8, 8
+    p = oracle.make_params(F, F)
+    dgnn, _ = make_dense_gnn(F, F, p, ("none", "none"), style="sequential")
+    sgnn, _ = make_sparse_gnn(F, F, p, ("none", "none"), style="sequential")
+    sgnn.load_state_dict(dgnn.state_dict())                      # same state_dict keys, like PyG >= 2.0
+    dense = DenseGCM(dgnn.to(dev), edge_selectors=make_selector([("temporal", (1, 2), "forward")]), graph_size=N)
+    sparse = SparseGCM(sgnn.to(dev), edge_selectors=make_sparse_selector([("temporal", (1, 2))]), graph_size=N)
+    obs = torch.arange(B * ts * F, dtype=torch.float32).reshape(B, ts, F).to(dev) * 0.01
+    with torch.no_grad():
+        d_outs, d_hidden = [], None
+        for i in range(ts):
+            o, d_hidden = dense(obs[:, i].contiguous(), d_hidden)
+            d_outs.append(o)
+        d_outs = torch.stack(d_outs, dim=1)
+        s_outs, s_hidden = sparse(obs, torch.full((B,), ts, device=dev), None)
+        step_outs, step_hidden = [], None
+        for i in range(ts):
+            o, step_hidden = sparse(obs[:, i:i + 1].contiguous(), torch.ones(B, dtype=torch.long, device=dev), step_hidden)
+            step_outs.append(o)
+        step_outs = torch.cat(step_outs, dim=1)
+    assert rel_err(s_outs, d_outs) < TOL and rel_err(step_outs, d_outs) < TOL
+    d_nodes, d_adj, _, _ = d_hidden
+    assert torch.equal(d_nodes, s_hidden[0]) and torch.equal(d_nodes, step_hidden[0])
+    assert torch.equal(d_adj.nonzero().T, s_hidden[1].coalesce().indices())
+    assert torch.equal(d_adj.nonzero().T, step_hidden[1].coalesce().indices())
+
+
+def test_sparse_overflow_raises():
+    from gcm.sparse_gcm import SparseGCM
+
+    dev = torch.device("cuda:0")
+    p = oracle.make_params(4, 4)
+    gnn, _ = make_sparse_gnn(4, 4, p, ("tanh", "tanh"))
+    mod = SparseGCM(gnn.to(dev), edge_selectors=make_sparse_selector([("temporal", (1,))]), graph_size=5)
+    with pytest.raises(Exception, match="Overflow"):
+        mod(torch.randn(2, 6, 4, device=dev), torch.tensor([6, 2], device=dev), None)
+
+
+def test_sparse_selectors_standalone_return_coo():
+    from gcm.sparse_edge_selectors.spatial import SpatialRadiusEdge
+    from gcm.sparse_edge_selectors.temporal import TemporalEdge
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(9)
+    B, N, F = 3, 10, 4
+    nodes = torch.randn(B, N, F, generator=gen) * 0.3
+    T, taus = torch.tensor([2, 0, 5]), torch.tensor([3, 4, 5])
+    want_t = oracle.temporal_edges_sparse(T, taus, (1, 3))
+    got = TemporalEdge([1, 3])(nodes.to(dev), T.to(dev), taus.to(dev), B)
+    assert got.is_sparse and torch.equal(got.coalesce().indices().cpu(), oracle.coalesce_edges(want_t))
+    want_r = oracle.spatial_radius_edges_sparse(nodes, T, taus, slice(0, 2), 0.5)
+    got = SpatialRadiusEdge(slice(0, 2), 0.5)(nodes.to(dev), T.to(dev), taus.to(dev), B)
+    assert torch.equal(got.coalesce().indices().cpu(), oracle.coalesce_edges(want_r))
