@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py — GCM env-steps/s on B200 (BASELINE.json metric), one process per GPU.
 
-A "step" is one DenseGCM.forward over the whole batch of independent graphs (BASELINE.json
-configs[1]: graph_size 128, hidden 32, TemporalBackedge([1,2,4]), batch 65536 rollout).  The batch
-shards across ranks with no data-path collective (weak scaling: every rank holds --batch graphs).
+Default workload = BASELINE.json configs[1] ("cfg2"): DenseGCM graph_size 128, hidden 32,
+TemporalBackedge([1,2,4]), 65536 graphs per GPU, forward rollout in steady state (graphs full, the
+oldest node is dropped every step).  A "step" is one DenseGCM.forward over the whole batch = ONE launch
+of the fused step kernel.  Graphs are independent, so the batch shards across ranks with no data-path
+collective (weak scaling: every rank owns --batch graphs).
 
-  value   env-steps/s with the step's observations already resident in HBM (CUDA events, max over ranks)
-  e2e     same metric through the public API with HOST observations: every step copies its [B,F]
-          observation from pinned host memory and reads the [B,H] belief back
-  roofline  algorithmic bytes/step (1440 B per graph-step for cfg 2) / kernel time
-  cpu_baseline  the oracle port of the reference step on the host cores, bounded sample
+JSON line (rank 0):
+  value        env-steps/s, observations already resident in HBM (CUDA events, max over ranks)
+  e2e          same metric through the public API from HOST buffers: every step copies its [B,F]
+               observation from pinned host memory and reads the [B,H] belief back
+  roofline     algorithmic bytes per launch / kernel duration (CUDA events around
+               back-to-back launches), against MEASURED_PEAKS.json
+  cpu_baseline the oracle port of the reference step on the host cores (bounded sample)
 
-`--impl reference` times the oracle port (the reference's algorithm on CPU) for the same metric.
+Other workloads (`--workload cfg1|cfg3|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
+configs with the same line format; `--impl reference` times the oracle port of the reference on CPU.
 """
 import argparse
 import json
@@ -28,9 +33,21 @@ for p in (os.path.join(ROOT, "graph-conv-memory_b200"), os.path.join(ROOT, "orac
 
 import torch  # noqa: E402
 
-WORKLOAD = "cfg2: DenseGCM graph_size=128 F=32 H=32 TemporalBackedge([1,2,4]) rollout fwd"
-N, F, H, HOPS = 128, 32, 32, (1, 2, 4)
-ALGO_BYTES_PER_GRAPH_STEP = 1440  # SURVEY.md §8(d) primary (k-hop) figure for cfg 2
+# name -> (description, B, N, F, H, selector spec, mode)
+WORKLOADS = {
+    "cfg1": ("cfg1 README quickstart: DenseGCM N=128 F=8 H=32 TemporalBackedge([1]) B=16 rollout fwd",
+             16, 128, 8, 32, [("temporal", (1,), "forward")], "rollout"),
+    "cfg2": ("cfg2: DenseGCM N=128 F=32 H=32 TemporalBackedge([1,2,4]) rollout fwd",
+             65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "rollout"),
+    "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (fp32 general kernels)",
+             16384, 256, 128, 128, [("dense",)], "bptt"),
+    "cfg4-cosine": ("cfg4: DenseGCM CosineEdge(0.5) N=512 F=64 H=64 rollout fwd",
+                    4096, 512, 64, 64, [("cosine", 0.5)], "rollout"),
+    "cfg4-euclid": ("cfg4: DenseGCM EuclideanEdge(2.0) N=512 F=64 H=64 rollout fwd (cross-batch mean)",
+                    4096, 512, 64, 64, [("euclidean", 2.0)], "rollout"),
+    "cfg5": ("cfg5: SparseGCM TemporalEdge([1]) + SpatialRadiusEdge(0.25) N=4096 F=H=64 all-at-once",
+             1024, 4096, 64, 64, None, "sparse"),
+}
 
 
 def peaks():
@@ -42,7 +59,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons while the benchmark runs (B200_PROFILING.md recipe)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -54,33 +71,51 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.1)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_module(dev):
+def make_selector(spec):
+    from gcm.edge_selectors.dense import DenseEdge
+    from gcm.edge_selectors.distance import CosineEdge, EuclideanEdge
     from gcm.edge_selectors.temporal import TemporalBackedge
+
+    s = spec[0]
+    if s[0] == "temporal":
+        return TemporalBackedge(list(s[1]), direction=s[2])
+    if s[0] == "dense":
+        return DenseEdge()
+    if s[0] == "cosine":
+        return CosineEdge(s[1])
+    return EuclideanEdge(s[1])
+
+
+def build_dense(dev, N, F, H, spec):
     from gcm.gcm import DenseGCM
     from gcm.nn import DenseGraphConv
 
-    class GNN(torch.nn.Module):
+    class GNN(torch.nn.Module):          # the README's user GNN (README.md:52-62 of the reference)
         def __init__(self):
             super().__init__()
             self.gc0 = DenseGraphConv(F, H)
@@ -92,73 +127,140 @@ def build_module(dev):
             return self.act(self.gc1(x, adj))
 
     torch.manual_seed(7)
-    return DenseGCM(GNN().to(dev), edge_selectors=TemporalBackedge(list(HOPS)), graph_size=N)
+    return DenseGCM(GNN().to(dev), edge_selectors=make_selector(spec), graph_size=N)
 
 
-def oracle_params(mod):
-    g = mod.gnn
-    return {"w_rel1": g.gc0.lin_rel.weight, "b1": g.gc0.lin_rel.bias, "w_root1": g.gc0.lin_root.weight,
-            "w_rel2": g.gc1.lin_rel.weight, "b2": g.gc1.lin_rel.bias, "w_root2": g.gc1.lin_root.weight}
+def build_sparse(dev, N, F, H):
+    from gcm.nn import GraphConv
+    from gcm.sparse_edge_selectors.spatial import SpatialRadiusEdge
+    from gcm.sparse_edge_selectors.temporal import TemporalEdge
+    from gcm.sparse_gcm import SparseGCM
+
+    class GNN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gc0 = GraphConv(F, H)
+            self.gc1 = GraphConv(H, H)
+            self.act = torch.nn.Tanh()
+
+        def forward(self, x, edges, weights):
+            x = self.act(self.gc0(x, edges, weights))
+            return self.act(self.gc1(x, edges, weights))
+
+    torch.manual_seed(7)
+    return SparseGCM(GNN().to(dev), edge_selectors=TemporalEdge([1]),
+                     aux_edge_selectors=SpatialRadiusEdge(slice(0, 2), 0.25), graph_size=N)
 
 
-def cpu_reference_rate(batch, steps, warm):
-    """The oracle port of the reference step (oracle/gcm_oracle.py) on the host cores, steady state."""
+def synth_obs(gen, n, B, F, spec):
+    """N(0,1) observations; clustered (K=16 centres, shared schedule) for distance edges."""
+    if spec and spec[0][0] in ("cosine", "euclidean"):
+        centres = torch.randn(16, F, generator=gen)
+        sched = torch.randint(0, 16, (n,), generator=gen)
+        return (centres[sched].unsqueeze(1) + 0.05 * torch.randn(n, B, F, generator=gen)).contiguous()
+    return torch.randn(n, B, F, generator=gen)
+
+
+def algorithmic(workload, B, N, F, H, extra=None):
+    """(bound, per-step algorithmic quantity, unit) — SURVEY.md §8(d)."""
+    if workload in ("cfg1", "cfg2"):
+        hops = WORKLOADS[workload][5][0][1]
+        r2 = len({0} | set(hops) | {a + b for a in hops for b in hops})
+        per = r2 * F * 4 + F * 4 + F * 4 + N // 8 + H * 4 + 16
+        return "hbm", per * B, "bytes"
+    if workload.startswith("cfg4"):
+        if workload == "cfg4-euclid":
+            return "fp32", 2.0 * B * B * N * F, "flop"
+        per = N * F * 4 + 2 * F * 4 + N // 8 * 2 + H * 4 + 16
+        return "hbm", per * B, "bytes"
+    if workload == "cfg3":
+        n = N
+        return "hbm", B * (n * F * 4 + 2 * F * 4 + H * 4 + 16) * 3, "bytes"   # fwd + 2x for bwd, fp32 nodes
+    if workload == "cfg5":
+        n, E = extra
+        per_layer = n * F * 4 + E * 8 + (n + 1) * 8 + n * H * 4
+        return "hbm", 2 * per_layer, "bytes"
+    raise ValueError(workload)
+
+
+def cpu_reference_rate(workload, batch, steps, warm):
+    """The oracle port of the reference (oracle/gcm_oracle.py) on the host cores."""
     import gcm_oracle as oracle
 
+    desc, _, N, F, H, spec, mode = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     p = oracle.make_params(F, H)
-    spec = [("temporal", HOPS, "forward")]
     gen = torch.Generator().manual_seed(1002)
-    # start full so every timed step includes the overflow shift, like the GPU arm's steady state
+    if mode == "sparse":
+        n_obs = min(N, 512)
+        x = torch.randn(batch, n_obs, F, generator=gen)
+        x[..., 0:2] = torch.cumsum(0.1 * torch.randn(batch, n_obs, 2, generator=gen), dim=1)
+        taus = torch.full((batch,), n_obs)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            for _ in range(max(1, steps)):
+                oracle.sparse_gcm_forward(x, taus, None, [("temporal", (1,))], p, graph_size=N,
+                                          aux_selectors=[("spatial_radius", slice(0, 2), 0.25)])
+            dt = time.perf_counter() - t0
+        return batch * n_obs * max(1, steps) / dt, dt / max(1, steps), cores, f"B={batch}, {n_obs} obs per graph"
+    # dense: start full so every timed step includes the overflow shift, like the GPU arm's steady state
     hidden = (torch.randn(batch, N, F, generator=gen), torch.zeros(batch, N, N), torch.zeros(0),
               torch.full((batch,), N, dtype=torch.long))
-    obs = torch.randn(batch, F, generator=gen)
-    with torch.no_grad():
-        for _ in range(warm):
-            _, hidden = oracle.dense_gcm_step(obs, hidden, spec, p, graph_size=N)
+    obs = synth_obs(gen, 4, batch, F, spec)
+    ctx = torch.no_grad() if mode == "rollout" else torch.enable_grad()
+    with ctx:
+        for i in range(warm):
+            _, hidden = oracle.dense_gcm_step(obs[i % 4], hidden, spec, p, graph_size=N)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            _, hidden = oracle.dense_gcm_step(obs, hidden, spec, p, graph_size=N)
+        for i in range(steps):
+            _, hidden = oracle.dense_gcm_step(obs[i % 4], hidden, spec, p, graph_size=N)
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, cores
+    return batch * steps / dt, dt / steps, cores, f"B={batch} full graphs (wrap every step)"
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank):
     if rank != 0:
         return
-    batch = args.cpu_batch
-    rate, per, cores = cpu_reference_rate(batch, args.steps, args.warmup)
-    sample = f"oracle port of the reference step, B={batch} graphs (of {args.batch}), full graphs (wrap every step)"
-    line = {
+    desc = WORKLOADS[args.workload][0]
+    rate, per, cores, what = cpu_reference_rate(args.workload, args.cpu_batch, args.steps, min(args.warmup, 4))
+    sample = f"oracle port of the reference ({what}; GPU arm runs {args.batch or WORKLOADS[args.workload][1]} graphs per GPU)"
+    print(json.dumps({
         "impl": "reference", "metric": "GCM env-steps/sec (fwd)", "value": rate, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": batch, "timing": "host wall clock, CPU only"},
+        "config": {"workload": desc, "batch_per_step": args.cpu_batch, "timing": "host wall clock, CPU only"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    print(json.dumps(line))
+    }))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=136)   # N + 8: fill the graphs, then steady state (wrapping)
-    ap.add_argument("--batch", type=int, default=65536, help="graphs per GPU")
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, B0, N, F, H, spec, mode = WORKLOADS[args.workload]
+    if args.warmup is None:
+        args.warmup = N + 8 if mode == "rollout" else 3   # fill the graphs, then steady state
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "cfg5":
+            args.cpu_batch = min(args.cpu_batch, 16)
+        elif args.workload != "cfg2":
+            args.cpu_batch = min(args.cpu_batch, 64)
+        run_reference(args, rank)
         return
 
     dev = torch.device("cuda", local)
@@ -168,110 +270,196 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-
-    B = args.batch
-    mod = build_module(dev)
-    gen = torch.Generator().manual_seed(1002 + rank)
+    B = args.batch or B0
     K, W = args.steps, args.warmup
-    n_obs = 16  # distinct observation batches cycled through (fresh data every step)
-    obs_host = torch.randn(n_obs, B, F, generator=gen).pin_memory()
-    obs_dev = obs_host.to(dev)
+    gen = torch.Generator().manual_seed(1002 + rank)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing (value) ----------------
-    hidden = None
-    with torch.no_grad():
-        for i in range(W):
-            belief, hidden = mod(obs_dev[i % n_obs], hidden)
-        barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-        ev[0].record()
-        for i in range(K):
-            belief, hidden = mod(obs_dev[i % n_obs], hidden)
-            ev[i + 1].record()
-        barrier()
-        total_ms = ev[0].elapsed_time(ev[K])
-        clocks = sampler.stop()
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = B * world * K / (total_ms * 1e-3)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # kernel-only duration: consecutive launches without host work in between (CUDA graph replay)
-    g = torch.cuda.CUDAGraph()
-    with torch.no_grad():
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            belief, hidden = mod(obs_dev[0], hidden)
-        torch.cuda.current_stream().wait_stream(s)
-        with torch.cuda.graph(g):
-            for i in range(8):
+    sampler = ClockSampler(local)
+    sampler.start()
+    extra, launches, e2e, kern_ms, kernel_name = None, K, None, None, None
+    unit_per_step = B
+
+    if mode == "rollout":
+        mod = build_dense(dev, N, F, H, spec)
+        n_obs = 16 if args.workload != "cfg4-euclid" else 4
+        obs_host = synth_obs(gen, n_obs, B, F, spec).pin_memory()
+        obs_dev = obs_host.to(dev)
+        hidden = None
+        with torch.no_grad():
+            for i in range(W):
                 belief, hidden = mod(obs_dev[i % n_obs], hidden)
-        g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(4, K // 8)
-        e0.record()
-        for _ in range(reps):
+            barrier()
+            t_lo = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                belief, hidden = mod(obs_dev[i % n_obs], hidden)
+            e1.record()
+            barrier()
+            total_ms = max_over_ranks(e0.elapsed_time(e1))
+            launches = K * (2 if args.workload == "cfg4-euclid" else 1)
+            # kernel-only duration: back-to-back launches replayed from a CUDA graph (no host work between)
+            per_graph = 8
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                belief, hidden = mod(obs_dev[0], hidden)
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(g):
+                for i in range(per_graph):
+                    belief, hidden = mod(obs_dev[i % n_obs], hidden)
             g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        kern_ms = e0.elapsed_time(e1) / (reps * 8)
+            torch.cuda.synchronize()
+            reps = max(4, K // per_graph)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            kern_ms = e0.elapsed_time(e1) / (reps * per_graph)
+            kernel_name = "k_step_temporal_win<32>" if args.workload == "cfg2" else (
+                "k_step_temporal_win<8>" if args.workload == "cfg1" else "k_step_general")
+            # end to end through the public API from host buffers
+            belief_host = torch.empty(B, H).pin_memory()
+            for i in range(3):
+                belief, hidden = mod(obs_host[i % n_obs].to(dev, non_blocking=True), hidden)
+                belief_host.copy_(belief, non_blocking=True)
+            barrier()
+            e0.record()
+            for i in range(K):
+                belief, hidden = mod(obs_host[i % n_obs].to(dev, non_blocking=True), hidden)
+                belief_host.copy_(belief, non_blocking=True)
+            e1.record()
+            barrier()
+            e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+            t_hi = time.perf_counter()
+        e2e = {"value": B * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
+               "d2h_bytes_per_step": B * H * 4}
+        hidden.claim().check_flags()
+    elif mode == "bptt":
+        from gcm import dist as gdist
 
-    # ---------------- end to end through the public API with host buffers ----------------
-    belief_host = torch.empty(B, H).pin_memory()
-    with torch.no_grad():
-        for i in range(3):
-            belief, hidden = mod(obs_host[i % n_obs].to(dev, non_blocking=True), hidden)
-            belief_host.copy_(belief, non_blocking=True)
+        T = 64
+        mod = build_dense(dev, N, F, H, spec)
+        mod.bptt_capacity = T
+        opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
+        obs_host = (0.5 * torch.randn(T, B, F, generator=gen)).pin_memory()
+        obs_dev = obs_host.to(dev)
+        nn0 = torch.full((B,), N - T, dtype=torch.long, device=dev)            # pre-filled with N - T nodes
+        nodes0 = 0.5 * torch.randn(B, N, F, device=dev)
+        nodes0[:, N - T:] = 0
+        adj0 = torch.zeros(B, N, N, device=dev)
+        adj0[:, : N - T, : N - T] = 1                                            # DenseEdge history: all ones
+
+        def window(obs):
+            hidden = (nodes0, adj0, torch.zeros(0, device=dev), nn0)
+            opt.zero_grad(set_to_none=True)
+            tot = 0
+            for t in range(T):
+                belief, hidden = mod(obs[t], hidden)
+                tot = tot + belief.mean()
+            (tot / T).backward()
+            gdist.allreduce_grads(mod.parameters(), average=True)               # the one NCCL collective
+            opt.step()
+            return tot
+
+        for _ in range(min(W, 2)):
+            window(obs_dev)
         barrier()
+        t_lo = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(K):
-            belief, hidden = mod(obs_host[i % n_obs].to(dev, non_blocking=True), hidden)
-            belief_host.copy_(belief, non_blocking=True)
+        for _ in range(K):
+            window(obs_dev)
         e1.record()
         barrier()
-        e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * K / (float(t.item()) * 1e-3)
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        t_hi = time.perf_counter()
+        unit_per_step = B * T
+        launches = K * T * 2
+        kern_ms = total_ms / (K * T)
+        kernel_name = "k_step_general + k_step_bwd_general"
+    else:  # sparse, all-at-once
+        mod = build_sparse(dev, N, F, H)
+        x = torch.randn(B, N, F, generator=gen)
+        x[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, N, 2, generator=gen), dim=1)
+        x_host = x.pin_memory()
+        x_dev = x_host.to(dev)
+        taus = torch.full((B,), N, dtype=torch.long, device=dev)
+        with torch.no_grad():
+            for _ in range(W):
+                out, hid = mod(x_dev, taus, None)
+            barrier()
+            t_lo = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                out, hid = mod(x_dev, taus, None)
+            e1.record()
+            barrier()
+            total_ms = max_over_ranks(e0.elapsed_time(e1))
+            t_hi = time.perf_counter()
+        E = int(hid[1]._nnz())
+        extra = (B * N, E)
+        unit_per_step = B * N
+        launches = K * 5
+        kernel_name = "k_graphconv_fwd x2 (+ edge build)"
+        kern_ms = total_ms / K
+
+    value = unit_per_step * world * K / (total_ms * 1e-3)
+    clocks = sampler.stop(t_lo, t_hi)
 
     if rank == 0:
         pk, pk_kind = peaks()
-        algo = ALGO_BYTES_PER_GRAPH_STEP * B
-        achieved = algo / (kern_ms * 1e-3) / 1e9
+        bound, algo, algo_unit = algorithmic(args.workload, B, N, F, H, extra)
+        if algo_unit == "bytes":
+            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+        else:
+            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e12, 72.0, "TFLOP/s"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload)
         line = {
-            "metric": "GCM env-steps/sec (fwd)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "metric": "GCM env-steps/sec (fwd)" if mode != "bptt" else "GCM env-steps/sec (fwd+bwd)",
+            "value": value, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "graph_size": N, "obs_size": F, "hidden": H,
-                       "state": "in-place ring + bit-packed adjacency, graphs full (overflow every step)",
-                       "l2": f"state {B * N * F * 4 / 1e6:.0f} MB per GPU > 126 MB L2; fresh obs each step",
-                       "parallelism": f"batch-sharded x{world}, no collective"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
-                    "d2h_bytes_per_step": B * H * 4},
-            "gpu_launches": K,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
-                         "kernel": "k_step_temporal<32>", "kernel_ms": kern_ms,
-                         "algo_bytes_per_launch": algo},
+            "config": {"workload": desc, "batch_per_gpu": B, "graph_size": N, "obs_size": F, "hidden": H,
+                       "state": "in-place node log + bit-packed adjacency; steady state (graphs full)"
+                       if mode == "rollout" else mode,
+                       "l2": f"per-GPU state {B * N * F * 4 / 1e6:.0f} MB vs 126 MB L2; fresh observations every step",
+                       "parallelism": f"batch-sharded x{world}, no data-path collective"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind if unit == "GB/s"
+                         else "fp32 FMA nominal (CUDA cores)", "kernel": kernel_name, "kernel_ms": kern_ms,
+                         "algorithmic_per_launch": algo},
         }
+        if e2e is not None:
+            line["e2e"] = e2e
+        else:
+            line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "device-resident only for this auxiliary workload"}
+        if extra is not None:
+            line["config"]["flat_nodes"], line["config"]["edges"] = extra
         if world == 1 and not args.no_cpu_baseline:
-            rate, per, cores = cpu_reference_rate(args.cpu_batch, 8, 2)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                "sample": f"oracle port, B={args.cpu_batch} full graphs, 8 steps ({per * 1e3:.1f} ms/step)"}
+            cb = {"cfg2": args.cpu_batch, "cfg5": 8}.get(args.workload, 64)
+            rate, per, cores, what = cpu_reference_rate(args.workload, cb, 6 if mode != "sparse" else 1, 2)
+            line["cpu_baseline"] = {"value": rate, "unit": line["unit"], "cores": cores, "kind": "port",
+                                    "sample": f"oracle port of the reference, {what}, {per * 1e3:.1f} ms/step"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

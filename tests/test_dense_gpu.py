@@ -160,14 +160,3 @@ def test_nan_flag_raises_reference_message():
         _, h = mod(x, None)
     with pytest.raises(AssertionError, match="Got NaN in returned memory"):
         tuple(h)
-
-
-def test_cpu_tensors_fail_loudly():
-    from gcm import _cabi
-    from gcm.gcm import DenseGCM
-
-    p = oracle.make_params(4, 8)
-    gnn, _ = make_dense_gnn(4, 8, p, ("tanh", "tanh"))
-    mod = DenseGCM(gnn, edge_selectors=make_selector([("temporal", (1,), "forward")]), graph_size=6)
-    with pytest.raises(_cabi.GcmLibraryError, match="no CPU fallback"):
-        mod(torch.randn(2, 4), None)
