@@ -1,0 +1,101 @@
+// Self-test of the tcgen05 building block used by the tensor-core step kernels:
+//   D[128, N] = A[128, K] * B[N, K]^T   in "3xTF32" (fp32-accurate) arithmetic,
+// A written to TMEM by the row-owning threads (tcgen05.st), B staged in shared memory in the canonical
+// K-major no-swizzle layout, accumulator in TMEM, read back with tcgen05.ld.
+#include "gcm_common.cuh"
+#include "gcm_tc.cuh"
+
+__global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float* B, float* D, int K, int N,
+                                                     int passes) {
+  extern __shared__ __align__(128) unsigned char st_raw[];
+  float* Bhi = reinterpret_cast<float*>(st_raw);        // [N x K] canonical
+  float* Blo = Bhi + N * K;
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(Blo + N * K);
+  uint64_t* bar_d = bar_a + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tc::mbar_init(bar_a, 128);
+    tc::mbar_init(bar_d, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < N * K; i += blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    uint32_t hi, lo;
+    tc::split_tf32(B[i], hi, lo);
+    Bhi[tc::kmajor_off(n, k, K)] = __uint_as_float(hi);
+    Blo[tc::kmajor_off(n, k, K)] = __uint_as_float(lo);
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t col_ahi = 0, col_alo = 128, col_d = 256;
+
+  if (warp < 4) {
+    const int row = tid;  // TMEM lane
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tc::split_tf32(A[(size_t)row * K + k0 + j], hi[j], lo[j]);
+      tc::tmem_st16(lane_addr + col_ahi + k0, hi);
+      tc::tmem_st16(lane_addr + col_alo + k0, lo);
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    tc::mbar_arrive(bar_a);
+    tc::mbar_wait(bar_d, 0);
+    tc::fence_after_sync();
+    for (int n0 = 0; n0 < N; n0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(lane_addr + col_d + n0, v);
+      tc::wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[(size_t)row * N + n0 + j] = __uint_as_float(v[j]);
+    }
+    tc::fence_before_sync();
+  } else {
+    // MMA issuer: one thread
+    tc::mbar_wait(bar_a, 0);
+    tc::fence_after_sync();
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_tf32(128, N);
+      const uint32_t sbo = (uint32_t)(K / 4) * 128u;
+      bool acc = false;
+      for (int pass = 0; pass < passes; ++pass) {
+        // passes == 3: lo*Bhi, hi*Blo, hi*Bhi ; passes == 1: hi*Bhi only (plain tf32)
+        const int which = passes == 3 ? pass : 2;
+        const uint32_t a_col = (which == 0) ? col_alo : col_ahi;
+        const float* bsrc = (which == 1) ? Blo : Bhi;
+        for (int ks = 0; ks < K / 8; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
+          tc::mma_tf32_ts(tbase + col_d, tbase + a_col + ks * 8, bdesc, idesc, acc);
+          acc = true;
+        }
+      }
+      tc::mma_commit(bar_d);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tbase, 512);
+}
+
+extern "C" int gcm_tc_selftest(const float* A, const float* B, float* D, int K, int N, int passes, void* stream) {
+  GCM_REQUIRE(A && B && D, "tc_selftest: null pointer");
+  GCM_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 256,
+              "tc_selftest: K=%d must be a multiple of 16 in [16,128], N=%d a multiple of 16 in [16,256]", K, N);
+  GCM_REQUIRE(passes == 1 || passes == 3, "tc_selftest: passes must be 1 or 3");
+  const size_t smem = (size_t)2 * N * K * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    gcm_set_error("cudaFuncSetAttribute(tc_selftest): %s", cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
+  k_tc_selftest<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, D, K, N, passes);
+  return gcm_check_launch("k_tc_selftest");
+}

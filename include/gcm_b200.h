@@ -205,6 +205,10 @@ int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out,
                              const float* w_root, int act, float* d_agg, float* d_x, float* d_w_rel,
                              float* d_w_root, float* d_b, void* stream);
 
+/* Self-test of the tcgen05/TMEM building block of the tensor-core step kernels:
+ * D[128,N] = A[128,K] B[N,K]^T, passes = 3 (3xTF32, fp32-accurate) or 1 (plain tf32).  Test hook only. */
+int gcm_tc_selftest(const float* A, const float* B, float* D, int K, int N, int passes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
