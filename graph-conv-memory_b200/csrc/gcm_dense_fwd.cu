@@ -10,7 +10,10 @@
 //   k_step_temporal<F>     one warp per graph, persistent; "pure temporal" states only (implicit
 //                          adjacency: the neighbour offsets are a static program), H1 = H2 = 32,
 //                          layer weights resident in registers.
+#include <stdlib.h>
+
 #include "gcm_common.cuh"
+#include "gcm_temporal.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // general kernel
@@ -342,25 +345,6 @@ static int launch_general_h(const DenseStepArgs& a, int hr, cudaStream_t stream)
 // ------------------------------------------------------------------------------------------------
 // pure-temporal fast kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int TP_MAXD = 48;   // distinct node offsets gathered per graph
-constexpr int TP_MAXR = 8;    // rows of R1 (1 + number of forward hops)
-constexpr int TP_MAXNB = 16;  // in-neighbours per row
-constexpr int TP_THREADS = 256;
-constexpr int TP_NW = TP_THREADS / 32;
-
-struct TemporalProg {
-  int nD;
-  int doff[TP_MAXD];          // offsets from t of the distinct rows, doff[0] = 0
-  int nR;
-  int rd[TP_MAXR];            // offset of row r (rd[0] = 0; r >= 1 are the in-neighbours of t)
-  int rD[TP_MAXR];            // index into doff of row r itself
-  int nnb[TP_MAXR];
-  int nb[TP_MAXR][TP_MAXNB];  // indices into doff of the in-neighbours of row r
-  uint32_t nbmask[TP_MAXR];   // the same as a bitmask over doff indices (valid when nD <= 32)
-  int n_past, past[GCM_MAX_HOPS];      // hops written into row t's past mask
-  int n_future, future[GCM_MAX_HOPS];  // hops written into the future mask of row t - hop
-};
-
 struct TemporalArgs {
   gcm_dense_state st;
   const float* obs;
@@ -583,24 +567,6 @@ static int launch_temporal(const TemporalArgs& a, cudaStream_t stream) {
 // complete_tx); eight consumer warps run the two layers out of shared memory with the layer
 // weights resident in registers.  One persistent CTA per SM.
 // ------------------------------------------------------------------------------------------------
-constexpr int TW_G = 32;        // graphs per pipeline stage (one per producer lane)
-constexpr int TW_STAGES = 3;
-constexpr int TW_CONS = 11;     // consumer warps
-constexpr int TW_MAXD = 12;     // distinct rows of the 2-hop in-neighbourhood (statically unrolled)
-constexpr int TW_THREADS = (TW_CONS + 1) * 32;
-constexpr int TW_MAXWIN = 16;   // rows of history staged per graph
-
-struct TemporalWinArgs {
-  gcm_dense_state st;
-  const float* obs;
-  gcm_gnn gnn;
-  float* belief;
-  int32_t* status;
-  TemporalProg prog;
-  int win;            // rows of history per graph = largest offset in prog.doff
-  int uniform_count;  // >= 0: every graph has this count (host mirror), the counter is not read
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -909,6 +875,11 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
         wa.prog = ta.prog;
         wa.win = win;
         wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
+        static const bool no_tc = getenv("GCM_B200_NO_TC") != nullptr;   // A/B switch for profiling
+        if (!no_tc) {
+          const int rc = gcm_launch_temporal_tc(wa, stream);
+          if (rc != GCM_ERR_UNSUPPORTED) return rc;
+        }
         switch (st->F) {
           case 8: return launch_temporal_win<8>(wa, stream);
           case 16: return launch_temporal_win<16>(wa, stream);
