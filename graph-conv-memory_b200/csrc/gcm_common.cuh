@@ -27,17 +27,33 @@ __device__ __forceinline__ float gcm_act_fwd(float z, int kind) {
   return z;
 }
 
-// tanh through ex2.approx + rcp.approx: |error| < 4e-7 absolute (budget: 1e-5 relative parity), ~6
-// instructions instead of tanhf's ~25.  Saturates correctly for large |z|; NaN propagates.
+// tanh(z) = 1 - 2 / (2^(2 z log2 e) + 1) through ex2.approx.ftz + rcp.approx.ftz: 5 instructions (2 MUFU),
+// |error| < 5e-7 absolute (budget: 1e-5 relative parity).  Saturates to +-1 for large |z| (2^t -> inf -> rcp 0,
+// 2^t -> 0 -> rcp 1); NaN propagates.
 __device__ __forceinline__ float gcm_tanh_fast(float z) {
-  const float e = __expf(2.0f * z);
-  return 1.0f - __fdividef(2.0f, e + 1.0f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
 }
 
 __device__ __forceinline__ float gcm_act_fast(float z, int kind) {
   if (kind == GCM_ACT_TANH) return gcm_tanh_fast(z);
   if (kind == GCM_ACT_RELU) return z <= 0.0f ? 0.0f : z;
   return z;
+}
+
+// activation of a register array with ONE warp-uniform branch on the kind (a per-element switch compiles to
+// a BSSY/BSYNC pair per element and dominated the tensor-core epilogues, profiles/c2_step_temporal_tg_r1.md)
+template <int NV>
+__device__ __forceinline__ void gcm_act_fast_vec(float (&v)[NV], int kind) {
+  if (kind == GCM_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = gcm_tanh_fast(v[j]);
+  } else if (kind == GCM_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = v[j] <= 0.0f ? 0.0f : v[j];
+  }
 }
 
 // derivative of the activation expressed through its OUTPUT value

@@ -875,7 +875,12 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
         wa.prog = ta.prog;
         wa.win = win;
         wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
-        static const bool no_tc = getenv("GCM_B200_NO_TC") != nullptr;   // A/B switch for profiling
+        static const bool no_tg = getenv("GCM_B200_NO_TG") != nullptr;   // A/B switches for profiling
+        static const bool no_tc = getenv("GCM_B200_NO_TC") != nullptr;
+        if (!no_tg && !no_tc) {
+          const int rc = gcm_launch_temporal_tg(wa, stream);
+          if (rc != GCM_ERR_UNSUPPORTED) return rc;
+        }
         if (!no_tc) {
           const int rc = gcm_launch_temporal_tc(wa, stream);
           if (rc != GCM_ERR_UNSUPPORTED) return rc;

@@ -366,20 +366,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_step_temporal_tc(const Tempor
         tc::tmem_ld16(taddr + TC_COL_D1 + 16, v1);
         tc::wait_ld();
         uint32_t hi[16], lo[16];
+        float h[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float h = gcm_act_fast(__uint_as_float(v0[q]) + bias_s[q], act1);
-          if (!row_valid) h = 0.0f;                       // rows outside the window contribute nothing
-          tc::split_tf32(h, hi[q], lo[q]);
-        }
+        for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v0[q]) + bias_s[q];
+        gcm_act_fast_vec(h, act1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tc::split_tf32(row_valid ? h[q] : 0.0f, hi[q], lo[q]);   // rows outside the window: 0
         tc::tmem_st16(taddr + 0, hi);
         tc::tmem_st16(taddr + 32, lo);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float h = gcm_act_fast(__uint_as_float(v1[q]) + bias_s[16 + q], act1);
-          if (!row_valid) h = 0.0f;
-          tc::split_tf32(h, hi[q], lo[q]);
-        }
+        for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v1[q]) + bias_s[16 + q];
+        gcm_act_fast_vec(h, act1);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tc::split_tf32(row_valid ? h[q] : 0.0f, hi[q], lo[q]);
         tc::tmem_st16(taddr + 16, hi);
         tc::tmem_st16(taddr + 48, lo);
       }
@@ -430,12 +429,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_step_temporal_tc(const Tempor
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
           const int hh = r * 8 + h;
-          const float z = ((red_g[(0 * TC_H + hh) * TC_G + lane] + red_g[(1 * TC_H + hh) * TC_G + lane]) +
-                           (red_g[(2 * TC_H + hh) * TC_G + lane] + red_g[(3 * TC_H + hh) * TC_G + lane])) +
-                          bias_s[TC_H + hh];
-          outv[h] = gcm_act_fast(z, act2);
-          bad |= !isfinite(outv[h]);
+          outv[h] = ((red_g[(0 * TC_H + hh) * TC_G + lane] + red_g[(1 * TC_H + hh) * TC_G + lane]) +
+                     (red_g[(2 * TC_H + hh) * TC_G + lane] + red_g[(3 * TC_H + hh) * TC_G + lane])) +
+                    bias_s[TC_H + hh];
         }
+        gcm_act_fast_vec(outv, act2);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) bad |= !isfinite(outv[h]);
         float4* dst = reinterpret_cast<float4*>(a.belief + (size_t)(g0 + lane) * TC_H + r * 8);
         dst[0] = make_float4(outv[0], outv[1], outv[2], outv[3]);
         dst[1] = make_float4(outv[4], outv[5], outv[6], outv[7]);

@@ -4,13 +4,15 @@
 // K-major no-swizzle layout, accumulator in TMEM, read back with tcgen05.ld.
 #include "gcm_common.cuh"
 #include "gcm_tc.cuh"
+#include <cuda_bf16.h>
 
 __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float* B, float* D, int K, int N,
                                                      int passes) {
   extern __shared__ __align__(128) unsigned char st_raw[];
   float* Bhi = reinterpret_cast<float*>(st_raw);        // [N x K] canonical
   float* Blo = Bhi + N * K;
-  uint64_t* bar_a = reinterpret_cast<uint64_t*>(Blo + N * K);
+  __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(Blo + N * K);   // [N x K] canonical, bf16 (passes == 4)
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(Bbf + N * K);
   uint64_t* bar_d = bar_a + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -27,6 +29,7 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
     tc::split_tf32(B[i], hi, lo);
     Bhi[tc::kmajor_off(n, k, K)] = __uint_as_float(hi);
     Blo[tc::kmajor_off(n, k, K)] = __uint_as_float(lo);
+    Bbf[tc::kmajor_off_bf16(n, k, K)] = __float2bfloat16_rn(B[i]);
   }
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -43,7 +46,14 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
 #pragma unroll
       for (int j = 0; j < 16; ++j) tc::split_tf32(A[(size_t)row * K + k0 + j], hi[j], lo[j]);
       tc::tmem_st16(lane_addr + col_ahi + k0, hi);
-      tc::tmem_st16(lane_addr + col_alo + k0, lo);
+      if (passes == 4) {   // lo part as packed bf16: column c holds k = 2c (low half) and 2c + 1
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = tc::pack_bf16(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+        tc::tmem_st8(lane_addr + col_alo + k0 / 2, pk);
+      } else {
+        tc::tmem_st16(lane_addr + col_alo + k0, lo);
+      }
     }
     tc::wait_st();
     tc::fence_before_sync();
@@ -66,9 +76,19 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
       const uint32_t idesc = tc::idesc_tf32(128, N);
       const uint32_t sbo = (uint32_t)(K / 4) * 128u;
       bool acc = false;
-      for (int pass = 0; pass < passes; ++pass) {
-        // passes == 3: lo*Bhi, hi*Blo, hi*Bhi ; passes == 1: hi*Bhi only (plain tf32)
-        const int which = passes == 3 ? pass : 2;
+      if (passes == 4) {   // lo(bf16, TMEM) * B(bf16): 16 elements of K per instruction
+        const uint32_t idesc16 = tc::idesc_bf16(128, N);
+        const uint32_t sbo16 = (uint32_t)(K / 8) * 128u;
+        for (int ks = 0; ks < K / 16; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(Bbf) + ks * 256, 128, sbo16);
+          tc::mma_bf16_ts(tbase + col_d, tbase + col_alo + ks * 8, bdesc, idesc16, acc);
+          acc = true;
+        }
+      }
+      for (int pass = (passes == 4 ? 1 : 0); pass < (passes == 4 ? 3 : passes); ++pass) {
+        // passes == 3: lo*Bhi, hi*Blo, hi*Bhi ; passes == 1: hi*Bhi only (plain tf32);
+        // passes == 4: the lo*B term was issued above in bf16, then hi*Blo, hi*Bhi
+        const int which = passes >= 3 ? pass : 2;
         const uint32_t a_col = (which == 0) ? col_alo : col_ahi;
         const float* bsrc = (which == 1) ? Blo : Bhi;
         for (int ks = 0; ks < K / 8; ++ks) {
@@ -89,8 +109,8 @@ extern "C" int gcm_tc_selftest(const float* A, const float* B, float* D, int K, 
   GCM_REQUIRE(A && B && D, "tc_selftest: null pointer");
   GCM_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 256,
               "tc_selftest: K=%d must be a multiple of 16 in [16,128], N=%d a multiple of 16 in [16,256]", K, N);
-  GCM_REQUIRE(passes == 1 || passes == 3, "tc_selftest: passes must be 1 or 3");
-  const size_t smem = (size_t)2 * N * K * 4 + 64;
+  GCM_REQUIRE(passes == 1 || passes == 3 || passes == 4, "tc_selftest: passes must be 1, 3 or 4");
+  const size_t smem = (size_t)2 * N * K * 4 + (size_t)N * K * 2 + 64;
   cudaError_t e = cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     gcm_set_error("cudaFuncSetAttribute(tc_selftest): %s", cudaGetErrorString(e));

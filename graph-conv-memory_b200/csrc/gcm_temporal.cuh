@@ -41,5 +41,6 @@ struct TemporalWinArgs {
 };
 
 
-// tensor-core variant (gcm_dense_fwd_tc.cu); returns GCM_ERR_UNSUPPORTED when the shape does not fit
-int gcm_launch_temporal_tc(const TemporalWinArgs& a, cudaStream_t stream);
+// tensor-core variants; each returns GCM_ERR_UNSUPPORTED when the shape does not fit
+int gcm_launch_temporal_tg(const TemporalWinArgs& a, cudaStream_t stream);   // gcm_dense_fwd_tg.cu: thread = graph
+int gcm_launch_temporal_tc(const TemporalWinArgs& a, cudaStream_t stream);   // gcm_dense_fwd_tc.cu: lane = (row, graph)
