@@ -826,9 +826,24 @@ static int validate_state(const gcm_dense_state* st) {
   return GCM_OK;
 }
 
+static int g_temporal_kernel = GCM_TK_AUTO;
+extern "C" int gcm_set_temporal_kernel(int which) {
+  GCM_REQUIRE(which >= GCM_TK_AUTO && which <= GCM_TK_ROWS, "set_temporal_kernel: bad variant %d", which);
+  g_temporal_kernel = which;
+  return GCM_OK;
+}
+
 extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                                   int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
                                   int flags, void* stream_) {
+  return gcm_dense_step_fwd_cached(st, obs, sels, n_sels, gnn, belief, status, flags, nullptr, 0, nullptr, stream_);
+}
+
+extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
+                                         int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
+                                         int flags, float* hcache, int hc_ring, int* cache_written,
+                                         void* stream_) {
+  if (cache_written) *cache_written = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = validate_state(st)) return rc;
   GCM_REQUIRE(obs && gnn && belief && status, "dense_step_fwd: null pointer");
@@ -862,7 +877,8 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
       int win = 0;
       for (int i = 0; i < ta.prog.nD; ++i) win = ta.prog.doff[i] > win ? ta.prog.doff[i] : win;
       // stage a contiguous history window when it is small and mostly needed rows
-      if (win >= 1 && win <= TW_MAXWIN && win <= 2 * (ta.prog.nD - 1) + 1 && ta.prog.nR <= 4 &&
+      if (g_temporal_kernel != GCM_TK_ROWS && win >= 1 && win <= TW_MAXWIN && win <= 2 * (ta.prog.nD - 1) + 1 &&
+          ta.prog.nR <= 4 &&
           ta.prog.nD <= TW_MAXD &&
           tw_smem_bytes(st->F, win) <= 200 * 1024 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0 &&
           (reinterpret_cast<uintptr_t>(st->nodes) & 15) == 0) {
@@ -875,16 +891,29 @@ extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, c
         wa.prog = ta.prog;
         wa.win = win;
         wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
-        static const bool no_tg = getenv("GCM_B200_NO_TG") != nullptr;   // A/B switches for profiling
-        static const bool no_tc = getenv("GCM_B200_NO_TC") != nullptr;
-        if (!no_tg && !no_tc) {
-          const int rc = gcm_launch_temporal_tg(wa, stream);
-          if (rc != GCM_ERR_UNSUPPORTED) return rc;
+        wa.hcache = hcache;
+        wa.hc_ring = hc_ring;
+        const bool cache_ok = hcache && gcm_temporal_hc_shape_ok(wa);
+        if (!cache_ok) wa.hcache = nullptr;
+        // Measured on B200 at cfg2 (profiles/): hc 2x faster than tc, tc 3x faster than win.  AUTO takes the
+        // fastest that fits; gcm_set_temporal_kernel() forces a variant (tests, A/B profiling).  hc needs every
+        // cached row it reads to be valid (GCM_STEP_HCACHE_VALID, the host's bookkeeping); tc fills the cache.
+        const int want = g_temporal_kernel;
+        if (cache_ok && (flags & GCM_STEP_HCACHE_VALID) && (want == GCM_TK_AUTO || want == GCM_TK_HC)) {
+          const int rc = gcm_launch_temporal_hc(wa, stream);
+          if (rc != GCM_ERR_UNSUPPORTED) {
+            if (cache_written) *cache_written = 1;
+            return rc;
+          }
         }
-        if (!no_tc) {
+        if (want == GCM_TK_AUTO || want == GCM_TK_TC || want == GCM_TK_HC) {
           const int rc = gcm_launch_temporal_tc(wa, stream);
-          if (rc != GCM_ERR_UNSUPPORTED) return rc;
+          if (rc != GCM_ERR_UNSUPPORTED) {
+            if (cache_written) *cache_written = cache_ok ? 1 : 0;
+            return rc;
+          }
         }
+        wa.hcache = nullptr;
         switch (st->F) {
           case 8: return launch_temporal_win<8>(wa, stream);
           case 16: return launch_temporal_win<16>(wa, stream);

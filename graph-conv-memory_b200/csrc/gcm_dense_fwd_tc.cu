@@ -370,6 +370,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_step_temporal_tc(const Tempor
 #pragma unroll
         for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v0[q]) + bias_s[q];
         gcm_act_fast_vec(h, act1);
+        // row 0 is the new node itself: keep its layer-1 output for the cached-row kernel (gcm_dense_fwd_hc.cu)
+        float4* hc_dst = nullptr;
+        if (r == 0 && live && a.hcache)
+          hc_dst = reinterpret_cast<float4*>(a.hcache + ((size_t)(g0 + lane) * a.hc_ring + (cnt & (a.hc_ring - 1))) * TC_H);
+        if (hc_dst) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) __stcg(hc_dst + q, make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]));
+        }
 #pragma unroll
         for (int q = 0; q < 16; ++q) tc::split_tf32(row_valid ? h[q] : 0.0f, hi[q], lo[q]);   // rows outside the window: 0
         tc::tmem_st16(taddr + 0, hi);
@@ -377,6 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_step_temporal_tc(const Tempor
 #pragma unroll
         for (int q = 0; q < 16; ++q) h[q] = __uint_as_float(v1[q]) + bias_s[16 + q];
         gcm_act_fast_vec(h, act1);
+        if (hc_dst) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) __stcg(hc_dst + 4 + q, make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]));
+        }
 #pragma unroll
         for (int q = 0; q < 16; ++q) tc::split_tf32(row_valid ? h[q] : 0.0f, hi[q], lo[q]);
         tc::tmem_st16(taddr + 16, hi);

@@ -8,6 +8,8 @@
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static thread_local const char* g_last_kernel = "";
+static long long g_launches = 0;
 
 void gcm_set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,6 +24,8 @@ int gcm_check_launch(const char* what) {
     gcm_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     return GCM_ERR_CUDA;
   }
+  g_last_kernel = what;
+  ++g_launches;
   return GCM_OK;
 }
 
@@ -39,6 +43,8 @@ int gcm_num_sms() {
 
 extern "C" int gcm_version(void) { return GCM_ABI_VERSION; }
 extern "C" const char* gcm_last_error(void) { return g_err; }
+extern "C" const char* gcm_last_kernel(void) { return g_last_kernel; }
+extern "C" long long gcm_launch_count(void) { return g_launches; }
 
 // ------------------------------------------------------------------------------------------------
 // materialize: log/bitmask state -> reference layout (gcm.py:194-211)

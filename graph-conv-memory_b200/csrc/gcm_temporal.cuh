@@ -1,4 +1,4 @@
-// Shared declarations of the pure-temporal step kernels (gcm_dense_fwd.cu, gcm_dense_fwd_tc.cu).
+// Shared declarations of the pure-temporal step kernels (gcm_dense_fwd.cu, gcm_dense_fwd_tc.cu, gcm_dense_fwd_hc.cu).
 #pragma once
 #include "gcm_common.cuh"
 
@@ -38,9 +38,12 @@ struct TemporalWinArgs {
   TemporalProg prog;
   int win;            // rows of history per graph = largest offset in prog.doff
   int uniform_count;  // >= 0: every graph has this count (host mirror), the counter is not read
+  float* hcache;      // [B, hc_ring, 32] layer-1 output of the last hc_ring nodes (slot = position % hc_ring), or NULL
+  int hc_ring;        // power of two
 };
 
 
 // tensor-core variants; each returns GCM_ERR_UNSUPPORTED when the shape does not fit
-int gcm_launch_temporal_tg(const TemporalWinArgs& a, cudaStream_t stream);   // gcm_dense_fwd_tg.cu: thread = graph
+int gcm_launch_temporal_hc(const TemporalWinArgs& a, cudaStream_t stream);   // gcm_dense_fwd_hc.cu: cached layer-1 rows
 int gcm_launch_temporal_tc(const TemporalWinArgs& a, cudaStream_t stream);   // gcm_dense_fwd_tc.cu: lane = (row, graph)
+bool gcm_temporal_hc_shape_ok(const TemporalWinArgs& a);                     // may the cache be kept for this shape?

@@ -27,8 +27,10 @@ FLAG_NONCAUSAL = 16
 SEL_NONE, SEL_TEMPORAL, SEL_DENSE, SEL_EUCLIDEAN, SEL_COSINE, SEL_SPATIAL = range(6)
 DIR = {"forward": 0, "backward": 1, "both": 2}
 ACT = {"none": 0, "tanh": 1, "relu": 2}
+TK_AUTO, TK_HC, TK_TC, TK_WIN, TK_ROWS = range(5)
 STEP_PURE_TEMPORAL = 1
 STEP_UNIFORM_COUNT = 2
+STEP_HCACHE_VALID = 4
 STEP_COUNT_SHIFT = 8
 
 _LIB_NAME = "libgcm_b200.so"
@@ -74,8 +76,13 @@ _L = C.c_int64
 _SIGNATURES = {
     "gcm_version": (C.c_int, []),
     "gcm_last_error": (C.c_char_p, []),
+    "gcm_last_kernel": (C.c_char_p, []),
+    "gcm_launch_count": (C.c_longlong, []),
     "gcm_dense_step_fwd": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), _I, C.POINTER(GnnC),
                                 _P, _P, _I, _P]),
+    "gcm_dense_step_fwd_cached": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), _I, C.POINTER(GnnC),
+                                       _P, _P, _I, _P, _I, C.POINTER(C.c_int), _P]),
+    "gcm_set_temporal_kernel": (_I, [_I]),
     "gcm_dense_step_bwd": (_I, [C.POINTER(DenseStateC), _I, C.POINTER(GnnC), _P, _P, _P,
                                 C.POINTER(GnnGradsC), _P]),
     "gcm_state_materialize": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P]),

@@ -181,6 +181,14 @@ class FusedPlan:
         self.temporal_key = (tuple(s.key() for s in sels)
                              if sels and all(s.kind == _cabi.SEL_TEMPORAL for s in sels) else None)
         self.needs_euclid = any(s.kind == _cabi.SEL_EUCLIDEAN for s in sels)
+        # layer-1 row cache: forward-only temporal chains with 32 hidden channels (the library re-checks the shape)
+        self.max_hop, self.hc_ring = 0, 0
+        if (self.temporal_key is not None and gnn.H1 == 32 and gnn.H2 == 32
+                and all(s.direction == _cabi.DIR["forward"] for s in sels)):
+            hops = [h for s in sels for h in s.hops]
+            if hops and max(hops) < 16:
+                self.max_hop = max(hops)
+                self.hc_ring = 1 << max(self.max_hop, 1).bit_length()      # power of two > max_hop
         self.validated = False
         self._sel_cache = None
 
@@ -232,17 +240,43 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
                     "gcm_euclid_batchmean")
     sels, n = plan.selectors_c(state.F, dist)
     flags = 0
+    gnn_c = plan.gnn.packed(dev)
+    hcache, ring = None, 0
     if plan.temporal_key is not None and state.pure_key is not None and state.pure_key in ((), plan.temporal_key):
         flags |= _cabi.STEP_PURE_TEMPORAL
         state.pure_key = plan.temporal_key
-        if state.host_count is not None and not torch.cuda.is_current_stream_capturing():
+        if torch.cuda.is_current_stream_capturing():
+            # a captured launch is replayed with these arguments: nothing the host mirrors may be baked in,
+            # and after replays the mirrors are unknown
+            state.host_count = None
+            state.hc_fresh = -(1 << 30)
+        if state.host_count is not None:
             # every graph has the same count and the host knows it: spare the kernel the dependent load
             flags |= _cabi.STEP_UNIFORM_COUNT | (state.host_count << _cabi.STEP_COUNT_SHIFT)
+        if plan.hc_ring:
+            # layer-1 row cache (include/gcm_b200.h: gcm_dense_step_fwd_cached).  hc_fresh counts the newest
+            # nodes whose cached row was written under the current weights; the cached-row kernel may run once
+            # that covers every node within max_hop of the new one.
+            if state.hcache is None:
+                state.hcache = torch.empty(state.B, plan.hc_ring, plan.gnn.H1, device=dev, dtype=torch.float32)
+                state.hc_key, state.hc_fresh = None, 0
+            if state.hc_key != plan.gnn._key:
+                state.hc_key, state.hc_fresh = plan.gnn._key, 0
+            need = plan.max_hop if state.host_count is None else min(plan.max_hop, state.host_count)
+            if state.hc_fresh >= need:
+                flags |= _cabi.STEP_HCACHE_VALID
+            hcache, ring = state.hcache.data_ptr(), plan.hc_ring
     else:
         state.pure_key = None
-    gnn_c = plan.gnn.packed(dev)
-    _cabi.check(lib.gcm_dense_step_fwd(state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(),
-                                       state.status.data_ptr(), flags, stream), "gcm_dense_step_fwd")
+    written = C.c_int(0)
+    _cabi.check(lib.gcm_dense_step_fwd_cached(state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(),
+                                              state.status.data_ptr(), flags, hcache, ring, C.byref(written),
+                                              stream), "gcm_dense_step_fwd")
+    if hcache is not None:
+        if state.hc_fresh < 0:           # captured launch: replays run without the host, start over afterwards
+            state.hc_fresh = 0
+        else:
+            state.hc_fresh = min(state.hc_fresh + 1, plan.max_hop) if written.value else 0
     state.version += 1
     state.steps += 1
     if state.host_count is not None:

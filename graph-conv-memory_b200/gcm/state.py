@@ -45,6 +45,9 @@ class DenseState:
         self.weights0: Optional[torch.Tensor] = None  # caller-supplied edge weights (passed through)
         self.d_nodes: Optional[torch.Tensor] = None   # dL/dnodes accumulation buffer (training)
         self.grad_floor = 0         # first step index whose window is fully inside the log
+        self.hcache: Optional[torch.Tensor] = None    # layer-1 row cache [B, ring, H1] (gcm.fused._launch_fwd)
+        self.hc_key = None          # weights key the cached rows were computed under
+        self.hc_fresh = 0           # newest nodes whose cached row is valid under hc_key
         self._c = _cabi.DenseStateC(self.nodes.data_ptr(), self.masks.data_ptr(), self.count.data_ptr(),
                                     B, N, self.C, F, self.W)
 

@@ -112,6 +112,10 @@ typedef struct gcm_gnn_grads {
 
 int gcm_version(void);
 const char* gcm_last_error(void);
+/* Introspection for benchmarks / tests: name of the kernel most recently launched by the calling thread,
+ * and the number of kernels this library has launched in the process so far. */
+const char* gcm_last_kernel(void);
+long long gcm_launch_count(void);
 
 /* One DenseGCM.forward step for the whole batch (replaces gcm.py:262-321: node write at
  * nodes[b, num_nodes[b]] (:274), overflow wrap (:263-271, :323-355), edge selectors (:284-287),
@@ -127,6 +131,31 @@ const char* gcm_last_error(void);
 int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                        int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
                        void* stream);
+
+/* The same step with a layer-1 row cache.  For forward-only TemporalBackedge chains the layer-1 output h_p of
+ * a node never changes once computed (its in-edges are fixed at creation, edge_selectors/temporal.py:72-88),
+ * provided the layer weights stay the same and N - 1 >= 2 max_hop.  hcache [B, hc_ring, H1] float32 (hc_ring a
+ * power of two > max_hop; slot = node position % hc_ring) holds the most recent rows.  Protocol: every step that
+ * reports *cache_written = 1 stored h of the node it created.  The caller sets GCM_STEP_HCACHE_VALID in `flags`
+ * once the last min(max_hop, count) nodes were all written under the CURRENT weights; the library then reads
+ * the cached rows instead of recomputing them (1 layer-1 row per graph instead of 1 + #hops).  Shapes the cache
+ * does not apply to behave exactly like gcm_dense_step_fwd and report *cache_written = 0. */
+#define GCM_STEP_HCACHE_VALID 4
+int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
+                              int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
+                              float* hcache, int hc_ring, int* cache_written, void* stream);
+
+/* Which kernel serves GCM_STEP_PURE_TEMPORAL steps (process-wide; default AUTO = fastest that fits the
+ * shape).  All variants compute the same step; the switch exists for parity tests and A/B profiling. */
+typedef enum gcm_temporal_kernel {
+  GCM_TK_AUTO = 0,
+  GCM_TK_HC = 1,   /* tcgen05, cached layer-1 rows, thread = graph (gcm_dense_fwd_hc.cu); falls back to
+                      TC while the cache is being filled */
+  GCM_TK_TC = 2,   /* tcgen05, lane = (row, graph), 32-graph tiles (gcm_dense_fwd_tc.cu) */
+  GCM_TK_WIN = 3,  /* CUDA cores, pipelined history window        (k_step_temporal_win) */
+  GCM_TK_ROWS = 4  /* CUDA cores, per-row gathers                 (k_step_temporal)     */
+} gcm_temporal_kernel;
+int gcm_set_temporal_kernel(int which);
 
 /* Backward of step `steps_back` steps ago (0 = the most recent step), recomputed from the node
  * log (requires that no slot of that step's window was overwritten since: count_now - start <= C).

@@ -160,3 +160,85 @@ def test_nan_flag_raises_reference_message():
         _, h = mod(x, None)
     with pytest.raises(AssertionError, match="Got NaN in returned memory"):
         tuple(h)
+
+
+@pytest.mark.parametrize("variant", ["hc", "tc", "win", "rows"])
+@pytest.mark.parametrize("B,N,F,T,hops", [(70, 128, 32, 135, (1, 2, 4)), (33, 24, 8, 30, (1,)), (200, 16, 16, 20, (1, 3)),
+                                          (130, 8, 32, 20, (1, 4))])
+def test_every_temporal_kernel_variant_matches_oracle(variant, B, N, F, T, hops):
+    """The pure-temporal step has four kernels (include/gcm_b200.h: gcm_temporal_kernel); each one is forced
+    in turn and must reproduce the oracle, including the wrap (T > N) and batches that are not tile multiples.
+    The last shape has N - 1 < 2 max_hop, where cached layer-1 rows would be wrong: hc must decline."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    which = {"hc": _cabi.TK_HC, "tc": _cabi.TK_TC, "win": _cabi.TK_WIN, "rows": _cabi.TK_ROWS}[variant]
+    expect = {"hc": "k_step_temporal_hc" if N - 1 >= 2 * max(hops) else "k_step_temporal_tc",
+              "tc": "k_step_temporal_tc", "win": "k_step_temporal_win", "rows": "k_step_temporal"}[variant]
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(99 + N + F)
+    obs = torch.randn(T, B, F, generator=gen)
+    p = oracle.make_params(F, 32)
+    gnn, _ = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    _cabi.check(lib.gcm_set_temporal_kernel(which), "gcm_set_temporal_kernel")
+    try:
+        hidden, o_hidden, o64 = None, None, None
+        p64 = {k: v.double() for k, v in p.items()}
+        with torch.no_grad():
+            for t in range(T):
+                belief, hidden = mod(obs[t].to(dev), hidden)
+                assert t == 0 or lib.gcm_last_kernel().decode() == expect   # step 0 ends with the plan validation
+                ref, o_hidden = oracle.dense_gcm_step(obs[t], o_hidden, spec, p, graph_size=N)
+                ref64, o64 = oracle.dense_gcm_step(obs[t].double(), o64, spec, p64, graph_size=N)
+                assert rel_err(belief, ref64) < TOL + rel_err(ref, ref64), (t, rel_err(belief, ref))
+        nodes, adj, weights, num_nodes = hidden
+        assert torch.equal(nodes.cpu(), o_hidden[0])
+        assert torch.equal(adj.cpu(), o_hidden[1])
+        assert torch.equal(num_nodes.cpu(), o_hidden[3])
+    finally:
+        lib.gcm_set_temporal_kernel(_cabi.TK_AUTO)
+
+
+def test_row_cache_follows_weight_updates_and_reingest():
+    """The layer-1 row cache is only read while every row it would use was written under the current weights:
+    after an in-place weight update the recomputing kernel runs for max_hop steps, then the cached-row kernel
+    resumes; a state that went through materialise -> ingest is no longer 'pure temporal' and takes the general
+    kernel.  Every step is checked against the oracle evaluated with the weights of that step."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    B, N, F, T, hops = 45, 32, 32, 60, (1, 2, 4)
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(4242)
+    obs = torch.randn(T, B, F, generator=gen)
+    p = oracle.make_params(F, 32)
+    gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    hidden, o_hidden = None, None
+    names = []
+    with torch.no_grad():
+        for t in range(T):
+            if t in (10, 40):       # "optimizer step": every weight changes in place
+                for k in p:
+                    p[k] = p[k] + 0.05 * torch.randn(p[k].shape, generator=gen)
+                convs[0].lin_rel.weight.copy_(p["w_rel1"]); convs[0].lin_rel.bias.copy_(p["b1"])
+                convs[0].lin_root.weight.copy_(p["w_root1"])
+                convs[1].lin_rel.weight.copy_(p["w_rel2"]); convs[1].lin_rel.bias.copy_(p["b2"])
+                convs[1].lin_root.weight.copy_(p["w_root2"])
+            if t == 50:
+                hidden = tuple(hidden)
+            belief, hidden = mod(obs[t].to(dev), hidden)
+            names.append(lib.gcm_last_kernel().decode() if t else "k_step_temporal_hc")   # step 0 ends with the plan validation
+            ref, o_hidden = oracle.dense_gcm_step(obs[t], o_hidden, spec, p, graph_size=N)
+            assert rel_err(belief, ref) < 2e-5, (t, names[-1], rel_err(belief, ref))
+    assert names[:10] == ["k_step_temporal_hc"] * 10
+    assert names[10:14] == ["k_step_temporal_tc"] * 4 and names[14] == "k_step_temporal_hc"
+    assert names[40:44] == ["k_step_temporal_tc"] * 4 and names[44] == "k_step_temporal_hc"
+    assert all(n == "k_step_general" for n in names[50:])
+    nodes, adj, weights, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
