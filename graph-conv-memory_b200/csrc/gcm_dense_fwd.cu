@@ -893,6 +893,7 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
         wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
         wa.hcache = hcache;
         wa.hc_ring = hc_ring;
+        wa.weights_stable = (flags & GCM_STEP_WEIGHTS_STABLE) ? 1 : 0;
         const bool cache_ok = hcache && gcm_temporal_hc_shape_ok(wa);
         if (!cache_ok) wa.hcache = nullptr;
         // Measured on B200 at cfg2 (profiles/): hc 2x faster than tc, tc 3x faster than win.  AUTO takes the

@@ -15,25 +15,27 @@
 // kernel when every cached row it reads was written under the current weights; until then the tc kernel
 // (gcm_dense_fwd_tc.cu) runs and fills the cache.  Same arithmetic as there: 3xTF32, fp32 accumulate.
 //
-// One persistent CTA per SM, 10 warps:
+// One persistent CTA per SM, 12 warps:
 //   warps 0-7   two consumer groups of 4 warps; a group owns a tile of QPG quarter tiles (32 graphs each; QPG = 3
 //               or 4, as many stages as fit in shared memory), warp q < QPG its graphs 32q..32q+31 (TMEM lane
 //               quadrant q; with QPG = 3 the last quadrant of the M = 128 MMA is idle).  Each thread builds its
 //               graph's operands straight into TMEM
-//               (tcgen05.st), warp 0 of the group issues the MMAs after a named-barrier hand-off, every warp
+//               (tcgen05.st), warp 3 of the group (warp 0 if QPG = 4) issues the MMAs after a named-barrier hand-off, every builder
 //               does the state update of its own quarter (node row, adjacency row, counter) while the tensor
 //               core works, then bias + activation on the accumulators (tcgen05.ld).
-//   warps 8-9   producers: 16-byte cp.async of each graph's needed rows (#hops node rows, #hops cached h
+//   warps 8-11  producers (3 active with 6 stages): 16-byte cp.async of each graph's needed rows (#hops node rows, #hops cached h
 //               rows, the observation) into the quarter-tile stages, ONE STAGE PER ACTIVE CONSUMER WARP
 //               (stage = group * QPG + q), completion by cp.async.mbarrier.arrive.  A stage is released right
 //               after the operand build, so the next tile's loads run under the MMAs and epilogues.
 // TMEM columns per group (256): A1 hi [0,64) | A1 lo [64,128) | D1 [128,160) | sum-h hi [160,192) |
 // sum-h lo [192,224) | D2 [224,256); h_t (hi | lo) overlays A1 hi once the layer-1 MMAs have completed.
+#include <stdlib.h>
+
 #include "gcm_tc.cuh"
 #include "gcm_temporal.cuh"
 
 constexpr int HC_Q = 32;                   // graphs per quarter tile (one warp's lanes)
-constexpr int HC_NPROD = 2;
+constexpr int HC_NPROD = 4;                // producer warps launched; 3 are used with 6 stages, 4 (or 2) with 8
 constexpr int HC_GROUPS = 2;
 constexpr int HC_CONS_THREADS = HC_GROUPS * 4 * 32;
 constexpr int HC_THREADS = HC_CONS_THREADS + HC_NPROD * 32;
@@ -95,6 +97,37 @@ __device__ __noinline__ void hc_wait(uint64_t* bar, uint32_t parity, int code) {
 #define HC_WAIT(bar, parity, code) tc::mbar_wait(bar, parity)
 #endif
 
+#ifdef HC_TRACE
+// debug build: per-warp phase timestamps (globaltimer ns) of CTA 0, read back with gcm_debug_hc_trace()
+__device__ unsigned long long g_hc_trace[12][8][8];
+__device__ unsigned long long g_hc_cta[160][2];
+extern "C" int gcm_debug_hc_cta(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_hc_cta, sizeof(g_hc_cta)) == cudaSuccess ? 0 : -2;
+}
+__device__ __forceinline__ void hc_cta_stamp(int which) {
+  if (threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_hc_cta[blockIdx.x][which] = t;
+  }
+}
+#define HC_CTA_STAMP(w) hc_cta_stamp(w)
+__device__ __forceinline__ void hc_stamp(int warp, int it, int phase) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < 8) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_hc_trace[warp][it][phase] = t;
+  }
+}
+extern "C" int gcm_debug_hc_trace(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_hc_trace, sizeof(g_hc_trace)) == cudaSuccess ? 0 : -2;
+}
+#define HC_STAMP(it, phase) hc_stamp(warp, it, phase)
+#else
+#define HC_STAMP(it, phase)
+#define HC_CTA_STAMP(w)
+#endif
+
 __device__ __forceinline__ void hc_cp16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -103,6 +136,13 @@ __device__ __forceinline__ void hc_cp_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void hc_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void hc_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Programmatic dependent launch: back-to-back steps are launched with programmatic stream serialization, so the
+// next step's CTAs take an SM as soon as this step's CTA leaves it and run their prologue (barrier init, TMEM
+// allocation, weight staging: nothing that depends on earlier kernels) while the rest of this grid drains;
+// pdl_wait() then blocks until every earlier kernel in the stream has completed and flushed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // 16 fp32 values -> hi / lo tf32 halves, 16 TMEM columns each, of this thread's lane
 __device__ __forceinline__ void hc_store_split16(uint32_t addr_hi, uint32_t addr_lo, const float (&v)[16]) {
@@ -147,6 +187,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
   const int nq = q_end - q_begin;
   const int my_tiles = (nq + (L.ns >> 1) - 1) / (L.ns >> 1);
 
+  HC_CTA_STAMP(0);
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
       tc::mbar_init(full + i, 32);               // one cp.async-completion arrival per producer lane
@@ -167,9 +209,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
 
   if (warp >= 8) {
     // =============================== producers ===============================
+    // A stage must always be refilled by the SAME producer warp (its mbarrier phases are tracked by parity), so
+    // the number of active producers divides the number of stages: producer p serves quarter q = p of both
+    // groups, and the quarter tiles of one tile are fetched concurrently instead of one after the other.
     const int p = warp - 8;
+    const int nprod = (NS % 3 == 0) ? 3 : 4;
+    pdl_wait();                                  // the state and the observations come from earlier kernels
     const int xch = np * CPR, hch = np * 8, tch = xch + hch + CPR;    // 16-byte chunks per graph
-    for (int s = p; s < nq; s += HC_NPROD) {
+    for (int s = p; s < nq && p < nprod; s += nprod) {
       const int slot = s % NS, use = s / NS;
       const int g0 = (q_begin + s) * HC_Q;
       const int gt = min(HC_Q, B - g0);
@@ -177,7 +224,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       int cnt_l = 0;
       if (uni) cnt_l = a.uniform_count;
       else if (lane < gt) cnt_l = __ldcg(a.st.count + g0 + lane);
+      HC_STAMP(s / nprod, 0);
       HC_WAIT(empty + slot, (use & 1) ^ 1, 100 + s);
+      HC_STAMP(s / nprod, 1);
       for (int c0 = 0; c0 < tch; c0 += 32) {
         const int c = c0 + lane;
         // decode the chunk: which row of which array, and its offset inside the per-graph stage
@@ -226,10 +275,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
         }
       }
       hc_cp_arrive(full + slot);
+      HC_STAMP(s / nprod, 2);
     }
   } else {
     // =============================== consumers ===============================
     const int grp = warp >> 2, q = warp & 3;
+    // The weights may only be read ahead of pdl_wait() when the host vouches that nothing wrote them since the
+    // previous step of this state (GCM_STEP_WEIGHTS_STABLE); otherwise wait first.
+    if (!a.weights_stable) pdl_wait();
     // ---- layer weights -> canonical K-major B operands, split hi / lo (loads first, then the stores) ----
     {
       constexpr int PER1 = (HC_H * K1) / HC_CONS_THREADS;     // F = 8: 2, 16: 4, 32: 8
@@ -271,22 +324,26 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       tc::fence_proxy_async();           // the tensor core reads the operands through the async proxy
       hc_bar_sync(HC_BAR_W, HC_CONS_THREADS);
     }
+    if (a.weights_stable) pdl_wait();    // everything below touches state written by earlier kernels
 
     const uint32_t tcol = tbase + grp * HC_COL_GROUP;
     const uint32_t taddr = tcol + ((uint32_t)(q * 32) << 16);
     const int act1 = a.gnn.act1, act2 = a.gnn.act2;
-    const int QPG = NS >> 1;                 // active warps (= quarter tiles) per group: 3 or 4
-    const bool issuer = q == 0;
+    const int QPG = NS >> 1;                 // builder warps (= quarter tiles) per group: 3 or 4
+    const bool builder = q < QPG;
+    // with 3 builders the 4th warp of the group does nothing but issue the MMAs (measured: an issuing builder
+    // delays its own state update and epilogue by ~1.5 us per tile, and the whole group waits for it)
+    const bool issuer = QPG == 3 ? q == 3 : q == 0;
     const uint32_t idesc = tc::idesc_tf32(128, HC_H);
     const uint32_t sbo1 = (uint32_t)(K1 / 4) * 128u, sbo2 = (uint32_t)(64 / 4) * 128u;
     const uint32_t b1hi = tc::smem_u32(B1hi), b1lo = tc::smem_u32(B1lo);
     const uint32_t b2hi = tc::smem_u32(B2hi), b2lo = tc::smem_u32(B2lo);
 
     int it = 0;
-    for (int j = grp; j < my_tiles && q < QPG; j += HC_GROUPS, ++it) {
+    for (int j = grp; j < my_tiles; j += HC_GROUPS, ++it) {
       const uint32_t ph = it & 1;
       const int s = QPG * j + q;               // quarter sequence number; slot = grp * QPG + q, use = it
-      const bool has = s < nq;
+      const bool has = builder && s < nq;
       const int slot = s % NS, use = s / NS;
       const int g0 = (q_begin + s) * HC_Q;
       const int gt = has ? min(HC_Q, B - g0) : 0;
@@ -299,7 +356,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       const float* mine = st_base + (size_t)lane * gs;
 
       if (has) {
+        HC_STAMP(it, 0);
         HC_WAIT(full + slot, use & 1, 200 + s);
+        HC_STAMP(it, 1);
         const float* xp[HC_MAXP];
         const float* hp[HC_MAXP];
 #pragma unroll
@@ -348,13 +407,16 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           }
           hc_store_split16(taddr + HC_COL_SHI + c0, taddr + HC_COL_SLO + c0, v);
         }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(empty + slot);        // everything was read: the stage can be refilled
         tc::wait_st();
+        HC_STAMP(it, 2);
       }
       tc::fence_before_sync();
       if (!issuer) {
-        hc_bar_arrive(HC_BAR_A1 + grp, QPG * 32);
+        hc_bar_arrive(HC_BAR_A1 + grp, 128);
       } else {
-        hc_bar_sync(HC_BAR_A1 + grp, QPG * 32);
+        hc_bar_sync(HC_BAR_A1 + grp, 128);
         tc::fence_after_sync();
         if (lane == 0) {
           bool acc = false;
@@ -376,13 +438,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       // ---- state update of this warp's quarter while the tensor core works ----
       if (has) {
         const int tslot = gcm_slot(cnt, C);
-        // node rows: 32 / CPR graphs per instruction, 128-bit coalesced stores
+        // node write (gcm.py:274): the stage is already released, so the observation tile (contiguous, L2-hot)
+        // is read again: 32 / CPR graphs per instruction, 128-bit coalesced loads and stores
 #pragma unroll
         for (int i = 0; i < CPR; ++i) {
           const int gi = i * (32 / CPR) + lane / CPR, col = lane % CPR;
           const int ts = __shfl_sync(GCM_FULL_MASK, tslot, gi);
           if (gi < gt) {
-            const float4 v = *reinterpret_cast<const float4*>(st_base + (size_t)gi * gs + np * F + np * HC_H + col * 4);
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)(g0 + gi) * F + col * 4));
             *reinterpret_cast<float4*>(a.st.nodes + ((size_t)(g0 + gi) * C + ts) * F + col * 4) = v;
           }
         }
@@ -417,12 +480,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           }
           __stcg(a.st.count + g0 + lane, cnt + 1);
         }
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(empty + slot);        // the stage can be refilled
       }
 
       // ---- layer-1 epilogue: h_t = act(D1 + b1) -> cache row + first half of the layer-2 operand ----
+      HC_STAMP(it, 3);
+      if (builder) {
       HC_WAIT(d1_ready + grp, ph, 300 + j);
+      HC_STAMP(it, 4);
       tc::fence_after_sync();
       {
         uint32_t v0[16], v1[16];
@@ -449,11 +513,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
         hc_store_split16(taddr + 16, taddr + 48, h1);
       }
       tc::wait_st();
+      }
       tc::fence_before_sync();
       if (!issuer) {
-        hc_bar_arrive(HC_BAR_A2 + grp, QPG * 32);
+        hc_bar_arrive(HC_BAR_A2 + grp, 128);
       } else {
-        hc_bar_sync(HC_BAR_A2 + grp, QPG * 32);
+        hc_bar_sync(HC_BAR_A2 + grp, 128);
         tc::fence_after_sync();
         if (lane == 0) {
           bool acc = false;
@@ -475,7 +540,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       }
 
       // ---- layer-2 epilogue: belief row of this thread's graph ----
+      HC_STAMP(it, 5);
+      if (builder) {
       HC_WAIT(d2_ready + grp, ph, 400 + j);
+      HC_STAMP(it, 6);
       tc::fence_after_sync();
       {
         uint32_t v0[16], v1[16];
@@ -503,10 +571,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           if (bad) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
         }
       }
+      }
+      HC_STAMP(it, 7);
       tc::fence_before_sync();
     }
   }
   __syncthreads();
+  HC_CTA_STAMP(1);
   if (warp == 8) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tbase, 512);
@@ -530,7 +601,22 @@ static int launch_hc(const TemporalWinArgs& a, cudaStream_t stream) {
   const int nq = (a.st.B + HC_Q - 1) / HC_Q;
   int grid = gcm_num_sms();
   if (grid > nq) grid = nq;
-  k_step_temporal_hc<F><<<grid, HC_THREADS, L.total + 128, stream>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(HC_THREADS);
+  cfg.dynamicSmemBytes = L.total + 128;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool no_pdl = getenv("GCM_B200_NO_PDL") != nullptr;   // A/B switch for profiling
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_step_temporal_hc<F>, a);
+  if (e != cudaSuccess) {
+    gcm_set_error("k_step_temporal_hc: launch failed: %s", cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
   return gcm_check_launch("k_step_temporal_hc");
 }
 

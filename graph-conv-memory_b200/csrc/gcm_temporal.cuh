@@ -40,6 +40,7 @@ struct TemporalWinArgs {
   int uniform_count;  // >= 0: every graph has this count (host mirror), the counter is not read
   float* hcache;      // [B, hc_ring, 32] layer-1 output of the last hc_ring nodes (slot = position % hc_ring), or NULL
   int hc_ring;        // power of two
+  int weights_stable; // GCM_STEP_WEIGHTS_STABLE: the weights were not written since the previous step of this state
 };
 
 

@@ -31,6 +31,7 @@ TK_AUTO, TK_HC, TK_TC, TK_WIN, TK_ROWS = range(5)
 STEP_PURE_TEMPORAL = 1
 STEP_UNIFORM_COUNT = 2
 STEP_HCACHE_VALID = 4
+STEP_WEIGHTS_STABLE = 8
 STEP_COUNT_SHIFT = 8
 
 _LIB_NAME = "libgcm_b200.so"

@@ -265,6 +265,10 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
             need = plan.max_hop if state.host_count is None else min(plan.max_hop, state.host_count)
             if state.hc_fresh >= need:
                 flags |= _cabi.STEP_HCACHE_VALID
+            if state.hc_fresh >= 1:
+                # the previous step of this state ran under the same weights key: any write to the weights since
+                # would have bumped a parameter version and reset hc_fresh
+                flags |= _cabi.STEP_WEIGHTS_STABLE
             hcache, ring = state.hcache.data_ptr(), plan.hc_ring
     else:
         state.pure_key = None

@@ -141,6 +141,10 @@ int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_se
  * the cached rows instead of recomputing them (1 layer-1 row per graph instead of 1 + #hops).  Shapes the cache
  * does not apply to behave exactly like gcm_dense_step_fwd and report *cache_written = 0. */
 #define GCM_STEP_HCACHE_VALID 4
+/* bit 3: the layer weights were not written by anything since the previous step of this state.  The cached-row
+ * kernel is launched with programmatic stream serialization; with this bit it stages the weights while the
+ * previous kernel in the stream is still draining (it always waits for that kernel before touching state). */
+#define GCM_STEP_WEIGHTS_STABLE 8
 int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                               int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
                               float* hcache, int hc_ring, int* cache_written, void* stream);
