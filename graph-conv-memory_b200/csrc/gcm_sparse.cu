@@ -100,6 +100,182 @@ __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused edge generation with a spatial hash (the radius selector at BASELINE cfg5 sizes)
+//
+// The brute-force kernel above tests every causal pair, N^2 / 2 per graph (8.4 M at N = 4096) in each of
+// the two passes.  Here a CTA bins the graph's node positions into cells of side `radius` (first two
+// position coordinates; a hash of the integer cell coordinates picks one of EH_BUCKETS buckets, counting
+// sort in shared memory), and a sink only tests the nodes in the 3 x 3 cells around its own.  The cell
+// test is a conservative filter (|dx| < r  =>  cells differ by at most 1; the side is widened by 2^-10 to
+// absorb the rounding of x / side), hash collisions only add candidates, and every candidate goes through
+// the SAME float comparison as the brute-force kernel, so the edge set is identical.  Hits are collected in
+// a per-warp bitmask over the sources, which de-duplicates (temporal hop == radius hit) and gives the
+// ascending source order of a coalesced COO for free.
+// ------------------------------------------------------------------------------------------------
+constexpr int EH_BUCKETS = 8192;
+constexpr int EH_THREADS = 512;
+constexpr int EH_SINKS = 1024;   // new nodes handled per CTA
+
+__device__ __forceinline__ int eh_cell(float x, float inv_side) {
+  const float c = floorf(x * inv_side);
+  return c != c ? 0 : (c > 1.0e9f ? 1000000000 : (c < -1.0e9f ? -1000000000 : (int)c));
+}
+__device__ __forceinline__ int eh_bucket(int cx, int cy) {
+  return (int)(((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u)) & (EH_BUCKETS - 1);
+}
+
+__global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenArgs a) {
+  extern __shared__ __align__(16) unsigned char eh_smem[];
+  const int b = blockIdx.x;
+  const int t0 = (int)a.T[b], tau = (int)a.taus[b];
+  const int s_begin = t0 + blockIdx.y * EH_SINKS;
+  const int s_end = min(t0 + tau, s_begin + EH_SINKS);
+  if (s_begin >= s_end) return;
+  const int n = s_end;                       // sources of these sinks are < s_end
+  const int W = (a.N + 31) >> 5;
+  const int PL = a.pos_len;
+  float* pos = reinterpret_cast<float*>(eh_smem);                        // [n][PL]
+  uint32_t* bits = reinterpret_cast<uint32_t*>(pos + (size_t)a.N * PL);  // [warps][W]
+  uint16_t* bstart = reinterpret_cast<uint16_t*>(bits + (EH_THREADS / 32) * W);   // [EH_BUCKETS + 1]
+  uint16_t* bfill = bstart + EH_BUCKETS + 2;                             // [EH_BUCKETS] running fill offsets
+  uint16_t* sorted = bfill + EH_BUCKETS;                                 // [n] node ids grouped by bucket
+  uint16_t* bkt = sorted + a.N;                                          // [n] bucket of every node
+  __shared__ int scan_tmp[EH_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = EH_THREADS / 32;
+  const float* nodes_b = a.nodes + (size_t)b * a.N * a.F;
+  const float inv_side = 1.0f / (a.radius * 1.0009765625f);
+
+  for (int i = tid; i < n * PL; i += EH_THREADS) {
+    const int k = i / PL, c = i - k * PL;
+    pos[i] = nodes_b[(size_t)k * a.F + a.pos_start + c * a.pos_step];
+  }
+  for (int i = tid; i <= EH_BUCKETS; i += EH_THREADS) bstart[i] = 0;
+  __syncthreads();
+  // counting sort by bucket: histogram (into bstart[bucket + 1]), exclusive scan, fill
+  // (16-bit counters, two per 32-bit atomic: a bucket holds at most n <= 65535 nodes, so halves never carry)
+  for (int k = tid; k < n; k += EH_THREADS) {
+    const int cx = eh_cell(pos[k * PL], inv_side);
+    const int cy = PL > 1 ? eh_cell(pos[k * PL + 1], inv_side) : 0;
+    const int bk = eh_bucket(cx, cy);
+    bkt[k] = (uint16_t)bk;
+    // two buckets share one 32-bit word of bstart (offset by one so that the scan is exclusive)
+    atomicAdd(reinterpret_cast<unsigned int*>(bstart) + ((bk + 1) >> 1), ((bk + 1) & 1) ? 0x10000u : 1u);
+  }
+  __syncthreads();
+  {
+    // exclusive scan of EH_BUCKETS + 1 counters: 16 + 1 per thread, then a block scan of the thread totals
+    constexpr int PER = EH_BUCKETS / EH_THREADS;   // 16
+    const int base = tid * PER + 1;                // counters 1..EH_BUCKETS hold the histogram
+    int local[PER];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      local[i] = bstart[base + i];
+      sum += local[i];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(GCM_FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) scan_tmp[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
+    int run = woff + incl - sum;                   // exclusive prefix of this thread's first counter
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      run += local[i];
+      bstart[base + i] = (uint16_t)run;            // bstart[j + 1] = end of bucket j = start of bucket j + 1
+    }
+    // bstart[0] stays 0
+  }
+  __syncthreads();
+  for (int i = tid; i < EH_BUCKETS; i += EH_THREADS) bfill[i] = bstart[i];
+  __syncthreads();
+  for (int k = tid; k < n; k += EH_THREADS) {
+    const int bk = bkt[k];
+    // 16-bit slot counter inside a 32-bit atomic
+    const unsigned int old = atomicAdd(reinterpret_cast<unsigned int*>(bfill) + (bk >> 1), (bk & 1) ? 0x10000u : 1u);
+    const int at = (bk & 1) ? (int)(old >> 16) : (int)(old & 0xffffu);
+    sorted[at] = (uint16_t)k;
+  }
+  __syncthreads();
+
+  uint32_t* my = bits + warp * W;
+  const int wpl = (W + 31) / 32;                   // bitmask words per lane (contiguous chunk)
+  for (int s = s_begin + warp; s < s_end; s += nwarps) {
+    for (int w = lane; w < W; w += 32) my[w] = 0u;
+    __syncwarp();
+    if (lane < a.n_hops) {
+      const int k = s - a.hops[lane];
+      if (k >= 0) atomicOr(my + (k >> 5), 1u << (k & 31));
+    }
+    if (s > 0) {
+      const int cx = eh_cell(pos[s * PL], inv_side);
+      const int cy = PL > 1 ? eh_cell(pos[s * PL + 1], inv_side) : 0;
+      const int ncell = PL > 1 ? 9 : 3;
+      for (int c = 0; c < ncell; ++c) {
+        const int dx = c % 3 - 1, dy = PL > 1 ? c / 3 - 1 : 0;
+        const int bk = eh_bucket(cx + dx, cy + dy);
+        const int i0 = bstart[bk], i1 = bstart[bk + 1];
+        for (int i = i0 + lane; i < i1; i += 32) {
+          const int k = sorted[i];
+          if (k < s) {
+            float d2 = 0.0f;
+            for (int cc = 0; cc < PL; ++cc) {
+              const float df = pos[s * PL + cc] - pos[k * PL + cc];
+              d2 += df * df;
+            }
+            if (sqrtf(d2) < a.radius) atomicOr(my + (k >> 5), 1u << (k & 31));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // count / emit in ascending source order
+    int cnt = 0;
+    for (int j = 0; j < wpl; ++j) {
+      const int w = lane * wpl + j;
+      if (w < W) cnt += __popc(my[w]);
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(GCM_FULL_MASK, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int64_t slot = a.new_off[b] + (s - t0);
+    if (!a.edges) {
+      if (lane == 31) a.deg[slot] = incl;
+    } else {
+      int64_t e = a.edge_off[slot] + (incl - cnt);
+      for (int j = 0; j < wpl; ++j) {
+        const int w = lane * wpl + j;
+        uint32_t m = w < W ? my[w] : 0u;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          a.edges[e] = b;
+          a.edges[a.E + e] = s;
+          a.edges[2 * a.E + e] = w * 32 + bit;
+          ++e;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+static size_t eh_smem_bytes(int N, int pos_len) {
+  const int W = (N + 31) / 32;
+  return (size_t)N * pos_len * 4 + (size_t)(EH_THREADS / 32) * W * 4 + (size_t)(EH_BUCKETS + 2) * 2 +
+         (size_t)EH_BUCKETS * 2 + (size_t)N * 2 * 2 + 16;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GraphConv forward: tile of GC_TM rows; gather-reduce into smem, then a register-tiled product with
 // the K-major weight pack streamed through smem in K chunks.
@@ -340,6 +516,13 @@ extern "C" int gcm_sparse_write_flatten(float* nodes, const float* x, const int6
   return gcm_check_launch("k_sparse_write_flatten");
 }
 
+static int g_edge_builder = GCM_EB_AUTO;
+extern "C" int gcm_set_edge_builder(int which) {
+  GCM_REQUIRE(which >= GCM_EB_AUTO && which <= GCM_EB_HASH, "set_edge_builder: bad variant %d", which);
+  g_edge_builder = which;
+  return GCM_OK;
+}
+
 extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* taus,
                                       const int64_t* new_off, int B, int N, int F, int tmax, const int32_t* hops,
                                       int n_hops, int use_radius, int pos_start, int pos_step, int pos_len,
@@ -364,6 +547,19 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
   }
   a.use_radius = use_radius; a.pos_start = pos_start; a.pos_step = pos_step; a.pos_len = pos_len;
   a.radius = radius; a.deg = deg; a.edge_off = edge_off; a.edges = edges; a.E = E;
+  // radius selector on graphs large enough for the pair test to dominate: spatial hash
+  const bool hash_fits = N <= 65535 && radius > 0.0f && radius < 1.0e30f && eh_smem_bytes(N, pos_len) <= 160 * 1024;
+  if (use_radius && hash_fits && (g_edge_builder == GCM_EB_HASH || (g_edge_builder == GCM_EB_AUTO && N >= 256))) {
+    const size_t hsmem = eh_smem_bytes(N, pos_len);
+    cudaError_t e = cudaFuncSetAttribute(k_sparse_edges_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+    if (e != cudaSuccess) {
+      gcm_set_error("cudaFuncSetAttribute(edges_hash): %s", cudaGetErrorString(e));
+      return GCM_ERR_CUDA;
+    }
+    dim3 hgrid(B, (tmax + EH_SINKS - 1) / EH_SINKS);
+    k_sparse_edges_hash<<<hgrid, EH_THREADS, hsmem, (cudaStream_t)stream>>>(a);
+    return gcm_check_launch("k_sparse_edges_hash");
+  }
   const size_t smem = use_radius ? (size_t)N * pos_len * 4 : 0;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_sparse_edges, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

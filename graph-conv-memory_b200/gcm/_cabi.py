@@ -28,6 +28,7 @@ SEL_NONE, SEL_TEMPORAL, SEL_DENSE, SEL_EUCLIDEAN, SEL_COSINE, SEL_SPATIAL = rang
 DIR = {"forward": 0, "backward": 1, "both": 2}
 ACT = {"none": 0, "tanh": 1, "relu": 2}
 TK_AUTO, TK_HC, TK_TC, TK_WIN, TK_ROWS = range(5)
+EB_AUTO, EB_PAIRS, EB_HASH = range(3)
 STEP_PURE_TEMPORAL = 1
 STEP_UNIFORM_COUNT = 2
 STEP_HCACHE_VALID = 4
@@ -94,6 +95,7 @@ _SIGNATURES = {
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
                                     _P, _P, _L, _P]),
+    "gcm_set_edge_builder": (_I, [_I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
                                       _P, _P, _P, _P]),
@@ -146,7 +148,14 @@ def check(rc: int, what: str) -> None:
 
 
 def stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream on `device` (the kernels are enqueued there)."""
+    idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    try:
+        return torch._C._cuda_getCurrentRawStream(idx)
+    except AttributeError:      # older / newer torch without the private accessor
+        return torch.cuda.current_stream(idx).cuda_stream
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -78,14 +78,20 @@ class GnnPlan:
         self.H2 = conv2.lin_rel.out_features
         self._key = None
         self._packed = None
+        self._lins = None
 
     def params(self) -> List[torch.Tensor]:
+        # looked up through the modules' parameter dicts on every call (a parameter may be re-assigned), without
+        # nn.Module.__getattr__: this runs once per step
+        if self._lins is None:
+            self._lins = [lin for conv in (self.conv1, self.conv2) for lin in (conv.lin_rel, conv.lin_root)]
         ps = []
-        for conv in (self.conv1, self.conv2):
-            for lin in (conv.lin_rel, conv.lin_root):
-                ps.append(lin.weight)
-                if lin.bias is not None:
-                    ps.append(lin.bias)
+        for lin in self._lins:
+            d = lin._parameters
+            ps.append(d["weight"])
+            b = d.get("bias")
+            if b is not None:
+                ps.append(b)
         return ps
 
     def _bias(self, conv) -> Optional[torch.Tensor]:
@@ -96,7 +102,7 @@ class GnnPlan:
         return None if b is None else b.detach()
 
     def current_key(self, device):
-        return tuple((p.data_ptr(), p._version) for p in self.params()) + (str(device),)
+        return tuple([(p.data_ptr(), p._version) for p in self.params()]) + (device,)
 
     def packed(self, device):
         """K-major weight packs (include/gcm_b200.h: gcm_gnn), rebuilt only when a parameter changed."""

@@ -219,6 +219,12 @@ int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* 
                            int pos_start, int pos_step, int pos_len, float radius, int32_t* deg,
                            const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
 
+/* Which kernel evaluates the radius selector (process-wide).  AUTO: all-pairs test for small graphs, spatial
+ * hash (cells of side `radius`, 3 x 3 neighbourhood, same float comparison) from N = 256.  Both produce the
+ * same edges; the switch exists for parity tests and A/B profiling. */
+typedef enum gcm_edge_builder { GCM_EB_AUTO = 0, GCM_EB_PAIRS = 1, GCM_EB_HASH = 2 } gcm_edge_builder;
+int gcm_set_edge_builder(int which);
+
 /* GraphConv over a CSR grouped by sink (torch_geometric.nn.GraphConv; call sites
  * ray_sparse_gcm.py:37-40, invoked at sparse_gcm.py:178,199):
  *   out[r] = act(W_rel (sum_{e in row i} w_e x[col[e]]) + b + W_root x[i]),  i = rows ? rows[r] : r

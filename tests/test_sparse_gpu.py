@@ -159,3 +159,41 @@ def test_sparse_selectors_standalone_return_coo():
     want_r = oracle.spatial_radius_edges_sparse(nodes, T, taus, slice(0, 2), 0.5)
     got = SpatialRadiusEdge(slice(0, 2), 0.5)(nodes.to(dev), T.to(dev), taus.to(dev), B)
     assert torch.equal(got.coalesce().indices().cpu(), oracle.coalesce_edges(want_r))
+
+
+@pytest.mark.parametrize("B,N,PL,radius,walk", [(6, 700, 2, 0.25, True), (3, 4096, 2, 0.25, True), (4, 512, 3, 0.6, False),
+                                                (5, 300, 1, 0.02, False), (3, 260, 2, 1.0e-3, True), (2, 1024, 2, 50.0, False)])
+def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
+    """gcm_sparse_build_edges has two kernels for the radius selector (include/gcm_b200.h: gcm_edge_builder):
+    the all-pairs test and the spatial hash.  They must emit identical coalesced edge lists: clustered random
+    walks (BASELINE cfg5's observations), uniform clouds, 1-D / 3-D positions, ragged T / tau, a radius that
+    catches nothing and one that catches everything, with temporal hops merged in."""
+    from gcm import _cabi, sparse_ops
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(N * 7 + PL)
+    F = 8
+    nodes = torch.randn(B, N, F, generator=gen)
+    if walk:
+        nodes[..., 1:1 + PL] = torch.cumsum(0.1 * torch.randn(B, N, PL, generator=gen), dim=1)
+    else:
+        nodes[..., 1:1 + PL] = torch.rand(B, N, PL, generator=gen) * 4 - 2
+    nodes[0, 5, 1] = float("nan")                       # NaN positions never match (NaN < r is false)
+    T = torch.randint(0, N // 3, (B,), generator=gen)
+    taus = torch.tensor([int(torch.randint(1, N - int(t) + 1, (1,), generator=gen)) for t in T])
+    taus[0] = N - int(T[0])                              # one graph filled to the brim
+    nodes, T, taus = nodes.to(dev), T.to(dev), taus.to(dev)
+    new_off = sparse_ops._excl_cumsum(taus)
+    n_new, tmax = int(taus.sum()), int(taus.max())
+    got = {}
+    try:
+        for name, which in (("pairs", _cabi.EB_PAIRS), ("hash", _cabi.EB_HASH)):
+            _cabi.check(lib.gcm_set_edge_builder(which), "gcm_set_edge_builder")
+            got[name] = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, (1, 3), (slice(1, 1 + PL), radius))
+            want_kernel = "k_sparse_edges_hash" if name == "hash" else "k_sparse_edges"
+            assert lib.gcm_last_kernel().decode() == want_kernel
+    finally:
+        lib.gcm_set_edge_builder(_cabi.EB_AUTO)
+    assert got["pairs"].shape[1] > 0
+    assert torch.equal(got["pairs"], got["hash"])
