@@ -1,0 +1,412 @@
+// DenseEdge-only DenseGCM step ("ones" path), sm_100a.
+//
+// DenseEdge (edge_selectors/dense.py:11-23) connects every pair of valid nodes, self loops included, so on a
+// state built by DenseEdge alone the adjacency is the all-ones n x n block and the 2-layer DenseGraphConv stack
+// (README.md:52-62) collapses:  with S = sum_i x_i over the window,
+//     c    = W_rel1 S + b1                                   (the aggregation is the SAME vector for every row)
+//     h_i  = act1(c + W_root1 x_i)                           for every valid row i
+//     out  = act2(W_rel2 (sum_i h_i) + b2 + W_root2 h_t)     (only row t of layer 2 is ever read, gcm.py:314)
+// R_i = W_root1 x_i does not change while the weights stay the same, so it is kept per node in HBM next to the
+// node log (rcache [B, C, H1]; refilled with one GEMM when W_root1 changes), S is maintained incrementally,
+// and a step is
+//     k_ones_update        node write, eviction of the oldest node when full, S update, counter
+//     k_linear2 x2         c = S W_rel1^T + b1 ;  R_t = x_t W_root1^T                      ([B,F] x [F,H1])
+//     k_ones_stream_fwd    G = sum_i act1(c + R_i), h_t            <- the only pass over per-node data:
+//                                                                     n * H1 * 4 bytes per graph, HBM-bound
+//     k_linear2            belief = act2(G W_rel2^T + b2 + h_t W_root2^T)
+// instead of the reference's [B,N,N] x [B,N,F] bmm + 4 GEMMs over all N rows.  The adjacency itself is implicit
+// on this path; k_fill_dense_masks writes the bit masks when the state is materialised or leaves the path.
+// Backward (BPTT): dz_i = dh_i * act1'(h_i) is accumulated per node in DZ [B, C, H1] by k_ones_stream_bwd; the
+// two products with x_i (dW_root1 = sum_i DZ_i x_i^T, dx_i = W_root1^T DZ_i) are linear in DZ and are applied
+// ONCE per BPTT window, not once per step.
+#include "gcm_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// state update
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ones_update(const gcm_dense_state st, const float* obs, float* xsum) {
+  const int F4 = st.F >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)st.B * F4) return;
+  const int b = (int)(i / F4), c = (int)(i - (long long)b * F4);
+  const int cnt = __ldcg(st.count + b);
+  const int slot = gcm_slot(cnt, st.C);
+  float4* nodes_b = reinterpret_cast<float4*>(st.nodes + (size_t)b * st.C * st.F);
+  float4 s = reinterpret_cast<float4*>(xsum)[(size_t)b * F4 + c];
+  const float4 x = reinterpret_cast<const float4*>(obs)[(size_t)b * F4 + c];
+  if (cnt >= st.N) {   // full: the oldest node leaves the window (gcm.py:323-355)
+    const float4 old = nodes_b[(size_t)gcm_slot(cnt - st.N, st.C) * F4 + c];
+    s.x -= old.x; s.y -= old.y; s.z -= old.z; s.w -= old.w;
+  }
+  s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+  reinterpret_cast<float4*>(xsum)[(size_t)b * F4 + c] = s;
+  nodes_b[(size_t)slot * F4 + c] = x;
+}
+__global__ void __launch_bounds__(256) k_ones_bump(int32_t* count, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) count[b] += 1;
+}
+
+// S from scratch: sum of the rows inside the window
+__global__ void __launch_bounds__(128) k_ones_xsum(const gcm_dense_state st, float* xsum) {
+  const int b = blockIdx.x;
+  const int cnt = st.count[b];
+  const int n = min(cnt, st.N);
+  const float* nodes_b = st.nodes + (size_t)b * st.C * st.F;
+  for (int f = threadIdx.x; f < st.F; f += blockDim.x) {
+    float s = 0.0f;
+    for (int l = 0; l < n; ++l) s += nodes_b[(size_t)gcm_slot(cnt - n + l, st.C) * st.F + f];
+    xsum[(size_t)b * st.F + f] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[r, :] = act(A1[r, :] W1^T + A2[r, :] W2^T + bias)        W row-major [Ho, K] (torch.nn.Linear layout)
+// 64-row tile per CTA, K streamed through shared memory in chunks of 32, 4 x NT register tile per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int L2_TM = 64, L2_KC = 32, L2_THREADS = 256;
+struct Linear2Args {
+  const float* A1; const float* W1; int K1; long long lda1;
+  const float* A2; const float* W2; int K2; long long lda2;
+  const float* bias;
+  int act;
+  long long rows;
+  int Ho;
+  float* out; long long ldo;
+  int32_t* status;   // GCM_FLAG_NONFINITE is OR-ed in when an output is not finite (may be NULL)
+  int accumulate;    // out += result instead of out = result
+};
+
+template <int NT>
+__global__ void __launch_bounds__(L2_THREADS) k_linear2(const Linear2Args a) {
+  __shared__ float As[L2_TM][L2_KC + 1];
+  __shared__ float Ws[L2_KC][16 * NT + 1];
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4, tc = tid & 15;       // 16 row groups x 16 column groups
+  const long long row0 = (long long)blockIdx.x * L2_TM;
+  const int Ho = a.Ho;
+  float acc[4][NT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.0f;
+  for (int part = 0; part < 2; ++part) {
+    const float* A = part ? a.A2 : a.A1;
+    const float* Wm = part ? a.W2 : a.W1;
+    const int K = part ? a.K2 : a.K1;
+    const long long lda = part ? a.lda2 : a.lda1;
+    if (!A) continue;
+    for (int k0 = 0; k0 < K; k0 += L2_KC) {
+      const int kc = min(L2_KC, K - k0);
+      __syncthreads();
+      for (int i = tid; i < L2_TM * L2_KC; i += L2_THREADS) {
+        const int r = i / L2_KC, kk = i - r * L2_KC;
+        const long long gr = row0 + r;
+        As[r][kk] = (gr < a.rows && kk < kc) ? A[gr * lda + k0 + kk] : 0.0f;
+      }
+      for (int i = tid; i < 16 * NT * L2_KC; i += L2_THREADS) {
+        const int o = i / L2_KC, kk = i - o * L2_KC;
+        Ws[kk][o] = (o < Ho && kk < kc) ? __ldg(Wm + (size_t)o * K + k0 + kk) : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < L2_KC; ++kk) {
+        float av[4], wv[NT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[tr * 4 + i][kk];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) wv[j] = Ws[kk][tc + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+    }
+  }
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long gr = row0 + tr * 4 + i;
+    if (gr < a.rows) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int c = tc + 16 * j;
+        if (c < Ho) {
+          float v = gcm_act_fwd(acc[i][j] + (a.bias ? __ldg(a.bias + c) : 0.0f), a.act);
+          if (a.accumulate) v += a.out[gr * a.ldo + c];
+          a.out[gr * a.ldo + c] = v;
+          bad |= !isfinite(v);
+        }
+      }
+    }
+  }
+  if (a.status && bad) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW[o, i] += sum_r A[r, o] X[r, i]  (and db[o] += sum_r A[r, o]): reduction over the rows (graphs, or graph
+// x node rows).  A CTA owns a contiguous chunk of rows and the full [Ho, Hi] tile in registers (8 x 8 per
+// thread), flushed with one atomicAdd per element.
+// ------------------------------------------------------------------------------------------------
+constexpr int OR_THREADS = 256, OR_RC = 32;
+struct OuterArgs {
+  const float* A; long long lda; int Ho;
+  const float* X; long long ldx; int Hi;
+  long long rows, rows_per_cta;
+  float* dW;   // [Ho, Hi]
+  float* db;   // [Ho] or NULL
+};
+__global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(const OuterArgs a) {
+  __shared__ float As[OR_RC][128 + 1];
+  __shared__ float Xs[OR_RC][128 + 1];
+  const int tid = threadIdx.x;
+  const int to = tid >> 4, ti = tid & 15;       // output rows to + 16 p, columns ti + 16 q
+  float acc[8][8];
+  float accb[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    accb[p] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[p][q] = 0.0f;
+  }
+  const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
+  const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
+  for (long long r0 = r_begin; r0 < r_end; r0 += OR_RC) {
+    __syncthreads();
+    for (int i = tid; i < OR_RC * 128; i += OR_THREADS) {
+      const int r = i >> 7, c = i & 127;
+      const long long gr = r0 + r;
+      As[r][c] = (gr < r_end && c < a.Ho) ? a.A[gr * a.lda + c] : 0.0f;
+      Xs[r][c] = (gr < r_end && c < a.Hi) ? a.X[gr * a.ldx + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < OR_RC; ++r) {
+      float av[8], xv[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) av[p] = As[r][to + 16 * p];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) xv[q] = Xs[r][ti + 16 * q];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        accb[p] += av[p];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(av[p], xv[q], acc[p][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int o = to + 16 * p;
+    if (o < a.Ho) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = ti + 16 * q;
+        if (i < a.Hi && acc[p][q] != 0.0f) atomicAdd(a.dW + (size_t)o * a.Hi + i, acc[p][q]);
+      }
+      if (a.db && ti == 0 && accb[p] != 0.0f) atomicAdd(a.db + o, accb[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the pass over the per-node cache.  One CTA per graph, thread = hidden channel (H1 <= 128), rows of the
+// window streamed with 8 independent loads in flight per thread (a row is one coalesced H1 * 4-byte read).
+// Forward:  G = sum_i act1(c + R_i), h_t = act1(c + R_t);  R_t (this step's new row) is stored on the way.
+// Backward: dz_i = (dG + [i == t] dh_t) * act1'(act1(c + R_i)) accumulated into DZ_i; dc = sum_i dz_i; the
+//           finished DZ row of node t is also returned (dL/dx_t = W_root1^T DZ_t + running dS).
+// `back` = how many steps ago the step was taken (0 = the most recent): window and t are derived from count.
+// ------------------------------------------------------------------------------------------------
+struct OnesStreamArgs {
+  gcm_dense_state st;
+  int H1, act1, back;
+  float* rcache;        // [B, C, H1]
+  const float* c;       // [B, H1]
+  const float* r_t;     // fwd: [B, H1] new row (stored into rcache)
+  float* G;             // fwd out [B, H1]
+  float* h_t;           // fwd out [B, H1]
+  const float* dG;      // bwd in  [B, H1]
+  const float* dh_t;    // bwd in  [B, H1]
+  float* DZ;            // bwd: [B, C, H1] accumulated
+  float* dc;            // bwd out [B, H1]
+  float* dz_t;          // bwd out [B, H1]
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) k_ones_stream(const OnesStreamArgs a) {
+  const int b = blockIdx.x, ch = threadIdx.x;
+  const int H1 = a.H1, C = a.st.C, N = a.st.N;
+  if (ch >= H1) return;
+  const int cnt = __ldcg(a.st.count + b) - a.back;    // nodes written up to and including this step
+  const int t = cnt - 1;                              // position of the step's own node
+  const int n = min(cnt, N);
+  const int first = cnt - n;
+  float* R = a.rcache + (size_t)b * C * H1;
+  const float cv = a.c[(size_t)b * H1 + ch];
+  const int act = a.act1;
+  if (!BWD) {
+    const float rt = a.r_t[(size_t)b * H1 + ch];
+    R[(size_t)gcm_slot(t, C) * H1 + ch] = rt;
+    float g = 0.0f;
+    int l = 0;
+    for (; l + 8 <= n - 1; l += 8) {                  // rows first .. t-1
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(R + (size_t)gcm_slot(first + l + u, C) * H1 + ch);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g += gcm_act_fast(cv + v[u], act);
+    }
+    for (; l < n - 1; ++l) g += gcm_act_fast(cv + __ldcs(R + (size_t)gcm_slot(first + l, C) * H1 + ch), act);
+    const float ht = gcm_act_fast(cv + rt, act);
+    a.G[(size_t)b * H1 + ch] = g + ht;
+    a.h_t[(size_t)b * H1 + ch] = ht;
+  } else {
+    float* DZ = a.DZ + (size_t)b * C * H1;
+    const float dg = a.dG[(size_t)b * H1 + ch];
+    float dcs = 0.0f;
+    int l = 0;
+    for (; l + 8 <= n - 1; l += 8) {
+      float v[8], z[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const size_t off = (size_t)gcm_slot(first + l + u, C) * H1 + ch;
+        v[u] = __ldcs(R + off);
+        z[u] = DZ[off];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float h = gcm_act_fast(cv + v[u], act);
+        const float d = dg * gcm_act_grad(h, act);
+        dcs += d;
+        DZ[(size_t)gcm_slot(first + l + u, C) * H1 + ch] = z[u] + d;
+      }
+    }
+    for (; l < n - 1; ++l) {
+      const size_t off = (size_t)gcm_slot(first + l, C) * H1 + ch;
+      const float h = gcm_act_fast(cv + __ldcs(R + off), act);
+      const float d = dg * gcm_act_grad(h, act);
+      dcs += d;
+      DZ[off] += d;
+    }
+    {   // the step's own node also feeds lin_root2
+      const size_t off = (size_t)gcm_slot(t, C) * H1 + ch;
+      const float h = gcm_act_fast(cv + R[off], act);
+      const float d = (dg + a.dh_t[(size_t)b * H1 + ch]) * gcm_act_grad(h, act);
+      dcs += d;
+      const float tot = DZ[off] + d;
+      DZ[off] = tot;
+      a.dz_t[(size_t)b * H1 + ch] = tot;
+    }
+    a.dc[(size_t)b * H1 + ch] = dcs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// explicit adjacency of a DenseEdge-only state: every node of the window is linked to every other one and to
+// itself.  One warp per node row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fill_dense_masks(const gcm_dense_state st) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int cnt = st.count[b];
+  const int n = min(cnt, st.N), first = cnt - n, W = st.W;
+  uint32_t* masks_b = st.masks + (size_t)b * st.C * 2 * W;
+  for (int l = warp; l < n; l += nwarps) {
+    uint32_t* row = masks_b + (size_t)gcm_slot(first + l, st.C) * 2 * W;
+    for (int w = lane; w < W; w += 32) {
+      row[w] = gcm_range_word(w, 0, l);                  // past: offsets 0 (self loop) .. l
+      row[W + w] = gcm_range_word(w, 1, n - 1 - l);      // future: offsets 1 .. n-1-l
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int ones_check_state(const gcm_dense_state* st, const char* what) {
+  GCM_REQUIRE(st && st->nodes && st->count && st->B >= 0 && st->N >= 1 && st->C >= st->N && st->F >= 4 &&
+                  (st->F & 3) == 0 && st->F <= 128,
+              "%s: bad state (F must be a multiple of 4, <= 128)", what);
+  return GCM_OK;
+}
+
+extern "C" int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, float* xsum, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_update")) return rc;
+  GCM_REQUIRE(obs && xsum, "dense_ones_update: null pointer");
+  if (st->B == 0) return GCM_OK;
+  const long long work = (long long)st->B * (st->F / 4);
+  k_ones_update<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, obs, xsum);
+  if (int rc = gcm_check_launch("k_ones_update")) return rc;
+  k_ones_bump<<<(st->B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st->count, st->B);
+  return gcm_check_launch("k_ones_bump");
+}
+
+extern "C" int gcm_dense_ones_xsum(const gcm_dense_state* st, float* xsum, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_xsum")) return rc;
+  GCM_REQUIRE(xsum, "dense_ones_xsum: null pointer");
+  if (st->B == 0) return GCM_OK;
+  k_ones_xsum<<<st->B, 128, 0, (cudaStream_t)stream>>>(*st, xsum);
+  return gcm_check_launch("k_ones_xsum");
+}
+
+extern "C" int gcm_linear2(const float* A1, int K1, long long lda1, const float* W1, const float* A2, int K2,
+                           long long lda2, const float* W2, const float* bias, int act, long long rows, int Ho,
+                           float* out, long long ldo, int32_t* status, int accumulate, void* stream) {
+  GCM_REQUIRE(A1 && W1 && out && K1 >= 1 && Ho >= 1 && Ho <= 128 && rows >= 0, "linear2: bad arguments");
+  GCM_REQUIRE((A2 == nullptr) == (W2 == nullptr) && (!A2 || K2 >= 1), "linear2: A2 and W2 go together");
+  if (rows == 0) return GCM_OK;
+  Linear2Args a{A1, W1, K1, lda1, A2, W2, K2, lda2, bias, act, rows, Ho, out, ldo, status, accumulate};
+  const long long grid = (rows + L2_TM - 1) / L2_TM;
+  GCM_REQUIRE(grid < 2147483647LL, "linear2: too many rows");
+  if (Ho <= 32) k_linear2<2><<<(unsigned)grid, L2_THREADS, 0, (cudaStream_t)stream>>>(a);
+  else if (Ho <= 64) k_linear2<4><<<(unsigned)grid, L2_THREADS, 0, (cudaStream_t)stream>>>(a);
+  else k_linear2<8><<<(unsigned)grid, L2_THREADS, 0, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_linear2");
+}
+
+extern "C" int gcm_outer_reduce(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi,
+                                long long rows, float* dW, float* db, void* stream) {
+  GCM_REQUIRE(A && X && dW && Ho >= 1 && Ho <= 128 && Hi >= 1 && Hi <= 128 && rows >= 0, "outer_reduce: bad arguments");
+  if (rows == 0) return GCM_OK;
+  // enough CTAs to fill the machine, at least 256 rows each so that the atomic flush stays negligible
+  long long ctas = (rows + 255) / 256;
+  const long long cap = 2LL * gcm_num_sms();
+  if (ctas > cap) ctas = cap;
+  long long per = (rows + ctas - 1) / ctas;
+  per = (per + OR_RC - 1) / OR_RC * OR_RC;
+  ctas = (rows + per - 1) / per;
+  OuterArgs a{A, lda, Ho, X, ldx, Hi, rows, per, dW, db};
+  k_outer_reduce<<<(unsigned)ctas, OR_THREADS, 0, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_outer_reduce");
+}
+
+extern "C" int gcm_dense_ones_stream_fwd(const gcm_dense_state* st, int H1, int act1, float* rcache, const float* c,
+                                         const float* r_t, float* G, float* h_t, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_stream_fwd")) return rc;
+  GCM_REQUIRE(H1 >= 1 && H1 <= 128 && rcache && c && r_t && G && h_t, "dense_ones_stream_fwd: bad arguments");
+  if (st->B == 0) return GCM_OK;
+  OnesStreamArgs a{};
+  a.st = *st; a.H1 = H1; a.act1 = act1; a.back = 0; a.rcache = rcache; a.c = c; a.r_t = r_t; a.G = G; a.h_t = h_t;
+  k_ones_stream<false><<<st->B, 128, 0, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_ones_stream_fwd");
+}
+
+extern "C" int gcm_dense_ones_stream_bwd(const gcm_dense_state* st, int steps_back, int H1, int act1, float* rcache,
+                                         const float* c, const float* dG, const float* dh_t, float* DZ, float* dc,
+                                         float* dz_t, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_stream_bwd")) return rc;
+  GCM_REQUIRE(H1 >= 1 && H1 <= 128 && steps_back >= 0 && rcache && c && dG && dh_t && DZ && dc && dz_t,
+              "dense_ones_stream_bwd: bad arguments");
+  if (st->B == 0) return GCM_OK;
+  OnesStreamArgs a{};
+  a.st = *st; a.H1 = H1; a.act1 = act1; a.back = steps_back; a.rcache = rcache; a.c = c; a.dG = dG; a.dh_t = dh_t;
+  a.DZ = DZ; a.dc = dc; a.dz_t = dz_t;
+  k_ones_stream<true><<<st->B, 128, 0, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_ones_stream_bwd");
+}
+
+extern "C" int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream) {
+  GCM_REQUIRE(st && st->masks && st->count && st->B >= 0 && st->W == (st->N + 31) / 32, "dense_fill_masks: bad state");
+  if (st->B == 0) return GCM_OK;
+  k_fill_dense_masks<<<st->B, 256, 0, (cudaStream_t)stream>>>(*st);
+  return gcm_check_launch("k_fill_dense_masks");
+}

@@ -134,11 +134,13 @@ __global__ void __launch_bounds__(256) k_ingest(const gcm_dense_state st, const 
       const float v = inb ? adj_b[(size_t)l * N + m] : 0.0f;
       const bool set = v == 1.0f;
       if (inb && ((v != 0.0f && v != 1.0f) || (set && (l >= n || m >= n)))) flags |= GCM_FLAG_UNCLEAN;
+      if (inb && l < n && m < n && !set) flags |= GCM_FLAG_NOTDENSE;   // DenseEdge states are all ones here
       word = __ballot_sync(GCM_FULL_MASK, set && l < n && m < n);
     }
     if (lane == 0) masks_b[item] = word;
   }
   if (flags) atomicOr(reinterpret_cast<unsigned int*>(status), flags);
+  if (tid == 0) atomicMax(status + 1, n);
 }
 
 // ------------------------------------------------------------------------------------------------

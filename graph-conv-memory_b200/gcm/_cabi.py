@@ -23,6 +23,7 @@ FLAG_UNCLEAN = 2
 FLAG_BADCOUNT = 4
 FLAG_OVERFLOW = 8
 FLAG_NONCAUSAL = 16
+FLAG_NOTDENSE = 32
 
 SEL_NONE, SEL_TEMPORAL, SEL_DENSE, SEL_EUCLIDEAN, SEL_COSINE, SEL_SPATIAL = range(6)
 DIR = {"forward": 0, "backward": 1, "both": 2}
@@ -95,6 +96,14 @@ _SIGNATURES = {
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
                                     _P, _P, _L, _P]),
+    "gcm_dense_ones_update": (_I, [C.POINTER(DenseStateC), _P, _P, _P]),
+    "gcm_dense_ones_xsum": (_I, [C.POINTER(DenseStateC), _P, _P]),
+    "gcm_linear2": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P,
+                         C.c_longlong, _P, _I, _P]),
+    "gcm_outer_reduce": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P]),
+    "gcm_dense_ones_stream_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _P, _P, _P, _P, _P, _P]),
+    "gcm_dense_ones_stream_bwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),
     "gcm_set_edge_builder": (_I, [_I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,

@@ -129,6 +129,19 @@ class GnnPlan:
         return self._packed[0]
 
 
+def _transposed(self, device):
+    """Transposed copies of the layer weights for the backward products (rebuilt when a parameter changed)."""
+    self.packed(device)
+    if getattr(self, "_tkey", None) != self._key:
+        t = self._packed[1]
+        self._t = {k + "_t": t[k].t().contiguous() for k in ("w_rel1", "w_root1", "w_rel2", "w_root2")}
+        self._tkey = self._key
+    return self._t
+
+
+GnnPlan.transposed = _transposed
+
+
 def match_gnn(gnn: torch.nn.Module) -> Optional[GnnPlan]:
     atoms = _atoms(gnn)
     if atoms is None:
@@ -187,6 +200,8 @@ class FusedPlan:
         self.temporal_key = (tuple(s.key() for s in sels)
                              if sels and all(s.kind == _cabi.SEL_TEMPORAL for s in sels) else None)
         self.needs_euclid = any(s.kind == _cabi.SEL_EUCLIDEAN for s in sels)
+        from gcm import ones as _ones
+        self.ones = _ones.plan_supports(self)          # DenseEdge-only chain: the all-ones fast path (gcm.ones)
         # layer-1 row cache: forward-only temporal chains with 32 hidden channels (the library re-checks the shape)
         self.max_hop, self.hc_ring = 0, 0
         if (self.temporal_key is not None and gnn.H1 == 32 and gnn.H2 == 32
@@ -233,6 +248,10 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     lib = _cabi.lib()
     dev = state.device
     stream = _cabi.stream_ptr(dev)
+    state.sync_masks()                       # the general kernels read the bit masks
+    state.xsum, state.rc_key = None, None    # ... and do not maintain the buffers of the ones path
+    state.dense_ok = state.dense_ok and plan.ones
+    state.max_count += 1
     dist = None
     if plan.needs_euclid:
         # reference quirk (distance.py:48-49): distance to node j is averaged over the current
@@ -303,6 +322,7 @@ def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tens
     """One-time check that the matched structure computes what the user's GNN module computes:
     run the module itself on the materialised state of a few graphs and compare beliefs."""
     nb = min(state.B, 8)
+    state.sync_masks()
     nodes = torch.empty(nb, state.N, state.F, device=state.device)
     adj = torch.empty(nb, state.N, state.N, device=state.device)
     nn = torch.empty(nb, device=state.device, dtype=torch.long)
@@ -420,6 +440,7 @@ def grow_state(state: DenseState, capacity: int) -> DenseState:
     new, _ = DenseState.ingest(nodes, adj, w if w is not None else torch.zeros(0, device=state.device),
                                num_nodes, capacity)
     new.pure_key = state.pure_key
+    new.dense_ok = state.dense_ok
     new.host_count = None if state.host_count is None else min(state.host_count, state.N)
     new.status = state.status
     return new

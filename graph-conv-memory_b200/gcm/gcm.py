@@ -18,7 +18,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 import gcm.util
-from gcm import _cabi, fused
+from gcm import _cabi, fused, ones
 from gcm.state import DenseHidden, DenseState
 
 
@@ -173,6 +173,7 @@ class DenseGCM(torch.nn.Module):
         _cabi.require_cuda(x, "DenseGCM.forward(x)")
         assert x.dim() == 2 and x.shape[1] == plan.gnn.F, "x must be [B, obs_size] matching the GNN input"
         B = x.shape[0]
+        ingest_grad = False
         recording = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in plan.gnn.params())
             or (isinstance(hidden, DenseHidden) and hidden.token is not None))
@@ -201,6 +202,7 @@ class DenseGCM(torch.nn.Module):
                 return self._forward_generic(x, hidden)   # not a {0,1} graph over the valid block
             token = None
             if recording and nodes.requires_grad:
+                ingest_grad = True
                 token = fused.ingest_token(state, nodes)
             recording = recording or token is not None
 
@@ -209,7 +211,18 @@ class DenseGCM(torch.nn.Module):
             DenseGCM.did_warn = True
 
         xc = x.contiguous()
-        if recording:
+        if plan.ones and state.dense_ok and not ingest_grad and (token is None or getattr(token, "_gcm_ones", False)):
+            # DenseEdge-only state: implicit all-ones adjacency, per-node cache (gcm.ones)
+            if recording:
+                if state.C - state.N < 1:
+                    state = fused.grow_state(state, state.N + max(int(self.bptt_capacity), 1))
+                    token = None
+                belief, token = ones.step_grad(plan, state, xc, token)
+                token._gcm_ones = True
+            else:
+                belief = ones.step_nograd(plan, state, xc.detach())
+                token = None
+        elif recording:
             belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
         else:
             belief = fused.fused_step_nograd(plan, state, xc.detach())

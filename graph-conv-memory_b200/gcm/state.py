@@ -37,7 +37,7 @@ class DenseState:
         self.nodes = torch.zeros(B, self.C, F, device=device, dtype=torch.float32)
         self.masks = torch.zeros(B, self.C, 2, self.W, device=device, dtype=torch.int32)
         self.count = torch.zeros(B, device=device, dtype=torch.int32)
-        self.status = torch.zeros(1, device=device, dtype=torch.int32)
+        self.status = torch.zeros(2, device=device, dtype=torch.int32)   # [flags, max count at ingest]
         self.version = 0            # bumped by every in-place step
         self.steps = 0              # steps applied to these buffers (host mirror of count - count0)
         self.pure_key = ()          # selector-chain key if built from empty by one chain, else None
@@ -45,6 +45,16 @@ class DenseState:
         self.weights0: Optional[torch.Tensor] = None  # caller-supplied edge weights (passed through)
         self.d_nodes: Optional[torch.Tensor] = None   # dL/dnodes accumulation buffer (training)
         self.grad_floor = 0         # first step index whose window is fully inside the log
+        # DenseEdge-only path (gcm.ones): the adjacency is implicit (all ones over the valid block)
+        self.dense_ok = True        # adjacency known to be the all-ones valid block (an empty state is)
+        self.masks_stale = False    # steps were taken on the ones path: the bit masks must be rebuilt before use
+        self.max_count = 0          # host-side upper bound of count[b]
+        self.xsum: Optional[torch.Tensor] = None      # [B, F] sum of the window's rows
+        self.rcache: Optional[torch.Tensor] = None    # [B, C, H1] W_root1 x_i per node
+        self.rc_key = None
+        self.DZ: Optional[torch.Tensor] = None        # [B, C, H1] accumulated dL/d(pre-activation) (training)
+        self.ds_run: Optional[torch.Tensor] = None    # [B, F] running dL/dS over the later steps
+        self.ds_snap = {}
         self.hcache: Optional[torch.Tensor] = None    # layer-1 row cache [B, ring, H1] (gcm.fused._launch_fwd)
         self.hc_key = None          # weights key the cached rows were computed under
         self.hc_fresh = 0           # newest nodes whose cached row is valid under hc_key
@@ -78,13 +88,24 @@ class DenseState:
             _cabi.lib().gcm_state_ingest(st.c_ref(), nodes_c.data_ptr(), adj_c.data_ptr(), nn_c.data_ptr(),
                                          st.status.data_ptr(), _cabi.stream_ptr(nodes.device)),
             "gcm_state_ingest")
-        flags = int(st.status.item())
+        flags, max_count = (int(v) for v in st.status.tolist())
+        st.status.zero_()
+        st.dense_ok = not (flags & (_cabi.FLAG_NOTDENSE | _cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT))
+        st.max_count = max_count
         if weights is not None and weights.numel() != 0:
             st.weights0 = weights
         return st, flags
 
     # -- materialisation ------------------------------------------------------------------------
+    def sync_masks(self) -> None:
+        """The ones path does not maintain the adjacency bit masks; write them before anything reads them."""
+        if self.masks_stale:
+            _cabi.check(_cabi.lib().gcm_dense_fill_masks(self.c_ref(), _cabi.stream_ptr(self.device)),
+                        "gcm_dense_fill_masks")
+            self.masks_stale = False
+
     def materialize(self, want_adj: bool = True):
+        self.sync_masks()
         nodes = torch.empty(self.B, self.N, self.F, device=self.device, dtype=torch.float32)
         adj = torch.empty(self.B, self.N, self.N, device=self.device, dtype=torch.float32) if want_adj else None
         num_nodes = torch.empty(self.B, device=self.device, dtype=torch.long)
@@ -113,7 +134,7 @@ class DenseState:
 
     def check_flags(self) -> None:
         """Lazy poll of the device status word (one host sync).  Keeps the reference's error text."""
-        flags = int(self.status.item())
+        flags = int(self.status[0].item())
         if flags & _cabi.FLAG_NONFINITE:
             self.status.zero_()
             raise AssertionError("Got NaN in returned memory, try using tanh activation")

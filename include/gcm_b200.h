@@ -195,6 +195,42 @@ int gcm_euclid_batchmean(const gcm_dense_state* st, const float* cur, int n_cur,
 int gcm_select_dense(const float* nodes, float* adj, const int64_t* num_nodes, int B, int N, int F,
                      const gcm_selector* sel, void* stream);
 
+/* ---- DenseEdge-only states ("ones" path, csrc/gcm_dense_ones.cu) ------------------------------------
+ * On a state built by DenseEdge alone (edge_selectors/dense.py:11-23) the adjacency is the all-ones block over
+ * the valid nodes, so the 2-layer stack of gcm.py:308 reduces to
+ *   c = W_rel1 S + b1 (S = sum of the window's rows),  h_i = act1(c + W_root1 x_i),
+ *   belief = act2(W_rel2 sum_i h_i + b2 + W_root2 h_t).
+ * The caller keeps, next to the node log: xsum [B,F] (= S), rcache [B,C,H1] (R_i = W_root1 x_i, slot = position
+ * % C) and, while training, DZ [B,C,H1] (accumulated dL/d(pre-activation) per node).  The adjacency bit masks
+ * are NOT maintained on this path; gcm_dense_fill_masks writes them when they are needed.
+ * GCM_FLAG_NOTDENSE is set by gcm_state_ingest when the valid block of a caller-supplied adjacency is not all
+ * ones; status[1] receives max(num_nodes) (status must then have two words). */
+#define GCM_FLAG_NOTDENSE 32u
+/* node write (gcm.py:274) + overflow eviction (gcm.py:323-355) + S update + num_nodes + 1 */
+int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, float* xsum, void* stream);
+/* S recomputed from the log */
+int gcm_dense_ones_xsum(const gcm_dense_state* st, float* xsum, void* stream);
+/* out[r,:Ho] = act(A1[r,:K1] W1^T + A2[r,:K2] W2^T + bias); W row-major [Ho,K] (torch.nn.Linear.weight); A2/W2 and
+ * bias may be NULL; lda / ldo = row strides in floats.  Ho <= 128.  (lin_rel / lin_root of DenseGraphConv.)
+ * status (or NULL): GCM_FLAG_NONFINITE is OR-ed in if an output is not finite; accumulate: out += result. */
+int gcm_linear2(const float* A1, int K1, long long lda1, const float* W1, const float* A2, int K2, long long lda2,
+                const float* W2, const float* bias, int act, long long rows, int Ho, float* out, long long ldo,
+                int32_t* status, int accumulate, void* stream);
+/* dW[o,i] += sum_r A[r,o] X[r,i];  db[o] += sum_r A[r,o] (db may be NULL).  Ho, Hi <= 128.  (weight gradients) */
+int gcm_outer_reduce(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
+                     float* dW, float* db, void* stream);
+/* After gcm_dense_ones_update: stores r_t as the new node's cache row, G = sum_i act1(c + R_i) over the window,
+ * h_t = act1(c + r_t).  c, r_t, G, h_t: [B,H1]. */
+int gcm_dense_ones_stream_fwd(const gcm_dense_state* st, int H1, int act1, float* rcache, const float* c,
+                              const float* r_t, float* G, float* h_t, void* stream);
+/* Backward of the step taken `steps_back` steps ago: DZ_i += (dG + [i==t] dh_t) * act1'(h_i) over that step's
+ * window, dc = sum_i of the same, dz_t = the (now final) DZ row of that step's own node. */
+int gcm_dense_ones_stream_bwd(const gcm_dense_state* st, int steps_back, int H1, int act1, float* rcache,
+                              const float* c, const float* dG, const float* dh_t, float* DZ, float* dc, float* dz_t,
+                              void* stream);
+/* writes the bit masks of the all-ones valid block (every node of the window linked to every node, self loops) */
+int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream);
+
 /* ---- sparse path (sparse_gcm.py:72-212) -------------------------------------------------- */
 
 /* Node write (sparse_gcm.py:111-123) + flat gather (util.py:426-452): nodes[b, T_b + k] = x[b, k]

@@ -152,3 +152,68 @@ def test_it_learns_and_detach():
         opt.step()
         hidden = hidden.detach()
     assert int(tuple(hidden)[3].max()) == N
+
+
+@pytest.mark.parametrize("T,n0", [(8, 10), (20, 10), (5, 24)])
+def test_ones_path_bptt_from_prefilled_dense_state(T, n0):
+    """BASELINE cfg3's protocol at a reduced size: a caller-supplied hidden state whose adjacency is DenseEdge's
+    all-ones block (ragged counts), T recorded steps (with and without the window wrapping inside the chain),
+    gradients of the observations and of all six weight tensors against the fp64 oracle; then a second window
+    on the detached state (truncated BPTT).  The DenseEdge-only kernels (csrc/gcm_dense_ones.cu) must be the
+    ones that ran."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H = 4, 24, 16, 12
+    spec = [("dense",)]
+    acts = ("tanh", "tanh")
+    gen = torch.Generator().manual_seed(77 + T)
+    p = oracle.make_params(F, H)
+    nn0 = torch.tensor([n0, max(n0 - 3, 0), n0, max(n0 - 1, 0)])
+    nodes0 = 0.5 * torch.randn(B, N, F, generator=gen)
+    adj0 = torch.zeros(B, N, N)
+    for b in range(B):
+        nodes0[b, int(nn0[b]):] = 0
+        adj0[b, : int(nn0[b]), : int(nn0[b])] = 1
+    obs = 0.5 * torch.randn(T, B, F, generator=gen)
+    w = torch.randn(T, B, H, generator=gen)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        o = obs.to(dt).clone().requires_grad_(True)
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in p.items()}
+        outs, _ = oracle.dense_gcm_rollout(o, (nodes0.to(dt), adj0.to(dt), torch.zeros(0, dtype=dt), nn0.clone()),
+                                           spec, pp, acts, graph_size=N)
+        (outs * w.to(dt)).sum().backward()
+        res[dt] = (outs.detach(), o.grad, {k: v.grad for k, v in pp.items()})
+    gnn, convs = make_dense_gnn(F, H, p, acts)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    x = obs.to(dev).requires_grad_(True)
+    hidden = (nodes0.to(dev), adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
+    outs, hidden = _bptt(mod, convs, x, w.to(dev), hidden)
+    assert _cabi.lib().gcm_last_kernel().decode() in ("k_outer_reduce", "k_linear2", "k_ones_stream_bwd")
+    ref64, ref32 = res[torch.float64], res[torch.float32]
+    assert rel_err(outs, ref64[0]) < TOL + rel_err(ref32[0], ref64[0])
+    assert rel_err(x.grad, ref64[1]) < TOL + rel_err(ref32[1], ref64[1])
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], ref64[2][k]) < TOL + rel_err(ref32[2][k], ref64[2][k]), k
+    # the state the caller sees is the reference's (adjacency materialised from the implicit all-ones block)
+    _, o_hidden = oracle.dense_gcm_rollout(obs, (nodes0, adj0, torch.zeros(0), nn0.clone()), spec, p, acts, graph_size=N)
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
+    assert torch.equal(num_nodes.cpu(), o_hidden[3])
+    # truncated BPTT: a second window on the detached in-place state
+    for q in convs:
+        q.zero_grad()
+    x2 = obs[:3].to(dev).requires_grad_(True)
+    _bptt(mod, convs, x2, w[:3].to(dev), hidden.detach())
+    o2 = obs[:3].double().clone().requires_grad_(True)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    outs2, _ = oracle.dense_gcm_rollout(o2, tuple(t.double() if t.is_floating_point() else t for t in o_hidden), spec, pp,
+                                        acts, graph_size=N)
+    (outs2 * w[:3].double()).sum().backward()
+    assert rel_err(x2.grad, o2.grad) < 5 * TOL
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], pp[k].grad) < 5 * TOL, k
