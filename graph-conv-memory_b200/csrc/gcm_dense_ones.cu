@@ -244,19 +244,26 @@ __global__ void __launch_bounds__(128) k_ones_stream(const OnesStreamArgs a) {
   float* R = a.rcache + (size_t)b * C * H1;
   const float cv = a.c[(size_t)b * H1 + ch];
   const int act = a.act1;
+  // rows first .. t-1 live in slots slot0, slot0 + 1, ... (mod C): one division per graph, not per row
+  int slot = gcm_slot(first, C);
+  auto next_off = [&]() {
+    const size_t off = (size_t)slot * H1 + ch;
+    slot = slot + 1 == C ? 0 : slot + 1;
+    return off;
+  };
   if (!BWD) {
     const float rt = a.r_t[(size_t)b * H1 + ch];
     R[(size_t)gcm_slot(t, C) * H1 + ch] = rt;
     float g = 0.0f;
     int l = 0;
-    for (; l + 8 <= n - 1; l += 8) {                  // rows first .. t-1
+    for (; l + 8 <= n - 1; l += 8) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcs(R + (size_t)gcm_slot(first + l + u, C) * H1 + ch);
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(R + next_off());
 #pragma unroll
       for (int u = 0; u < 8; ++u) g += gcm_act_fast(cv + v[u], act);
     }
-    for (; l < n - 1; ++l) g += gcm_act_fast(cv + __ldcs(R + (size_t)gcm_slot(first + l, C) * H1 + ch), act);
+    for (; l < n - 1; ++l) g += gcm_act_fast(cv + __ldcs(R + next_off()), act);
     const float ht = gcm_act_fast(cv + rt, act);
     a.G[(size_t)b * H1 + ch] = g + ht;
     a.h_t[(size_t)b * H1 + ch] = ht;
@@ -267,22 +274,23 @@ __global__ void __launch_bounds__(128) k_ones_stream(const OnesStreamArgs a) {
     int l = 0;
     for (; l + 8 <= n - 1; l += 8) {
       float v[8], z[8];
+      size_t offs[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const size_t off = (size_t)gcm_slot(first + l + u, C) * H1 + ch;
-        v[u] = __ldcs(R + off);
-        z[u] = DZ[off];
+        offs[u] = next_off();
+        v[u] = __ldcs(R + offs[u]);
+        z[u] = __ldcs(DZ + offs[u]);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float h = gcm_act_fast(cv + v[u], act);
         const float d = dg * gcm_act_grad(h, act);
         dcs += d;
-        DZ[(size_t)gcm_slot(first + l + u, C) * H1 + ch] = z[u] + d;
+        DZ[offs[u]] = z[u] + d;
       }
     }
     for (; l < n - 1; ++l) {
-      const size_t off = (size_t)gcm_slot(first + l, C) * H1 + ch;
+      const size_t off = next_off();
       const float h = gcm_act_fast(cv + __ldcs(R + off), act);
       const float d = dg * gcm_act_grad(h, act);
       dcs += d;
@@ -367,9 +375,10 @@ extern "C" int gcm_outer_reduce(const float* A, long long lda, int Ho, const flo
                                 long long rows, float* dW, float* db, void* stream) {
   GCM_REQUIRE(A && X && dW && Ho >= 1 && Ho <= 128 && Hi >= 1 && Hi <= 128 && rows >= 0, "outer_reduce: bad arguments");
   if (rows == 0) return GCM_OK;
-  // enough CTAs to fill the machine, at least 256 rows each so that the atomic flush stays negligible
-  long long ctas = (rows + 255) / 256;
-  const long long cap = 2LL * gcm_num_sms();
+  // enough CTAs to fill the machine (2 resident per SM), at least 64 rows each so that the atomic flush
+  // (Ho * Hi adds per CTA) stays small next to the products
+  long long ctas = (rows + 63) / 64;
+  const long long cap = 4LL * gcm_num_sms();
   if (ctas > cap) ctas = cap;
   long long per = (rows + ctas - 1) / ctas;
   per = (per + OR_RC - 1) / OR_RC * OR_RC;
