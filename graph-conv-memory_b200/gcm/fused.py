@@ -202,6 +202,9 @@ class FusedPlan:
         self.needs_euclid = any(s.kind == _cabi.SEL_EUCLIDEAN for s in sels)
         from gcm import ones as _ones
         self.ones = _ones.plan_supports(self)          # DenseEdge-only chain: the all-ones fast path (gcm.ones)
+        # exactly one distance selector: per-node pre-activation cache (zc_step)
+        self.zc = (len(sels) == 1 and sels[0].kind in (_cabi.SEL_EUCLIDEAN, _cabi.SEL_COSINE, _cabi.SEL_SPATIAL)
+                   and max(gnn.F, gnn.H1, gnn.H2) <= 128)
         # layer-1 row cache: forward-only temporal chains with 32 hidden channels (the library re-checks the shape)
         self.max_hop, self.hc_ring = 0, 0
         if (self.temporal_key is not None and gnn.H1 == 32 and gnn.H2 == 32
@@ -251,6 +254,7 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     state.sync_masks()                       # the general kernels read the bit masks
     state.xsum, state.rc_key = None, None    # ... and do not maintain the buffers of the ones path
     state.dense_ok = state.dense_ok and plan.ones
+    state.zc_ok = False                      # ... nor the pre-activation cache of the zc path
     state.max_count += 1
     dist = None
     if plan.needs_euclid:
@@ -310,6 +314,44 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     state.steps += 1
     if state.host_count is not None:
         state.host_count += 1
+
+
+def zc_step(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """No-grad step of a single-distance-selector plan through gcm_dense_step_fwd_zc (include/gcm_b200.h).
+    Returns None when the cache cannot be trusted any more (weights changed): the caller takes the general kernel,
+    which also retires the cache for this state."""
+    lib = _cabi.lib()
+    dev = state.device
+    stream = _cabi.stream_ptr(dev)
+    gnn_c = plan.gnn.packed(dev)
+    key = plan.gnn._key
+    if state.zcache is None:
+        state.zcache = torch.empty(state.B, state.C, plan.gnn.H1, device=dev, dtype=torch.float32)
+        state.zc_key = key
+    elif state.zc_key != key:
+        return None
+    dist = None
+    if plan.needs_euclid:
+        dist = state.__dict__.setdefault("_euclid_dist", torch.empty(state.B, state.C, device=dev))
+        cur = state.__dict__.get("_euclid_cur_all")
+        cur = x if cur is None else cur
+        _cabi.check(lib.gcm_euclid_batchmean(state.c_ref(), cur.data_ptr(), cur.shape[0],
+                                             _cabi.ptr(plan.sels[0].dist_param), dist.data_ptr(), stream),
+                    "gcm_euclid_batchmean")
+    sels, _ = plan.selectors_c(state.F, dist)
+    belief = torch.empty(state.B, plan.gnn.H2, device=dev, dtype=torch.float32)
+    _cabi.check(lib.gcm_dense_step_fwd_zc(state.c_ref(), x.data_ptr(), sels, C.byref(gnn_c), state.zcache.data_ptr(),
+                                          belief.data_ptr(), state.status.data_ptr(), stream),
+                "gcm_dense_step_fwd_zc")
+    state.pure_key = None
+    state.dense_ok = False
+    state.xsum, state.rc_key = None, None
+    state.version += 1
+    state.steps += 1
+    state.max_count += 1
+    if state.host_count is not None:
+        state.host_count += 1
+    return belief
 
 
 def fused_step_nograd(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> torch.Tensor:

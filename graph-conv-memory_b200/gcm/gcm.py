@@ -225,7 +225,12 @@ class DenseGCM(torch.nn.Module):
         elif recording:
             belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
         else:
-            belief = fused.fused_step_nograd(plan, state, xc.detach())
+            belief = None
+            if plan.zc and state.zc_ok:
+                # one distance selector, rollout: per-node pre-activation cache (csrc/gcm_dense_zc.cu)
+                belief = fused.zc_step(plan, state, xc.detach())
+            if belief is None:
+                belief = fused.fused_step_nograd(plan, state, xc.detach())
             token = None
         if not plan.validated:
             plan.validated = True

@@ -55,6 +55,10 @@ class DenseState:
         self.DZ: Optional[torch.Tensor] = None        # [B, C, H1] accumulated dL/d(pre-activation) (training)
         self.ds_run: Optional[torch.Tensor] = None    # [B, F] running dL/dS over the later steps
         self.ds_snap = {}
+        # single distance selector (gcm.fused.zc_step): per-node pre-activation cache
+        self.zc_ok = True           # every step so far went through the zc kernel (an empty state qualifies)
+        self.zcache: Optional[torch.Tensor] = None    # [B, C, H1]
+        self.zc_key = None
         self.hcache: Optional[torch.Tensor] = None    # layer-1 row cache [B, ring, H1] (gcm.fused._launch_fwd)
         self.hc_key = None          # weights key the cached rows were computed under
         self.hc_fresh = 0           # newest nodes whose cached row is valid under hc_key
@@ -92,6 +96,7 @@ class DenseState:
         st.status.zero_()
         st.dense_ok = not (flags & (_cabi.FLAG_NOTDENSE | _cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT))
         st.max_count = max_count
+        st.zc_ok = False
         if weights is not None and weights.numel() != 0:
             st.weights0 = weights
         return st, flags

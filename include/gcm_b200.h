@@ -231,6 +231,16 @@ int gcm_dense_ones_stream_bwd(const gcm_dense_state* st, int steps_back, int H1,
 /* writes the bit masks of the all-ones valid block (every node of the window linked to every node, self loops) */
 int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream);
 
+/* ---- one distance selector with a per-node pre-activation cache ("zc" path, csrc/gcm_dense_zc.cu) ----
+ * Same step as gcm_dense_step_fwd for a selector chain made of exactly one EuclideanEdge / CosineEdge /
+ * SpatialEdge (edge_selectors/distance.py).  Those selectors only write row t of the adjacency, so the layer-1
+ * pre-activation z_i of an existing node changes only when one of its in-neighbours leaves the window; the
+ * caller keeps zcache [B, C, H1] float32 next to the node log and the step is two streaming passes per graph.
+ * Valid only if EVERY step of this state went through this entry point under the SAME weights (the caller's
+ * bookkeeping; otherwise use gcm_dense_step_fwd).  sel->dist as for gcm_dense_step_fwd (euclidean). */
+int gcm_dense_step_fwd_zc(const gcm_dense_state* st, const float* obs, const gcm_selector* sel, const gcm_gnn* gnn,
+                          float* zcache, float* belief, int32_t* status, void* stream);
+
 /* ---- sparse path (sparse_gcm.py:72-212) -------------------------------------------------- */
 
 /* Node write (sparse_gcm.py:111-123) + flat gather (util.py:426-452): nodes[b, T_b + k] = x[b, k]

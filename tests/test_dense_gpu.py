@@ -242,3 +242,41 @@ def test_row_cache_follows_weight_updates_and_reingest():
     assert all(n == "k_step_general" for n in names[50:])
     nodes, adj, weights, num_nodes = hidden
     assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
+
+
+@pytest.mark.parametrize("spec", [[("cosine", 0.5)], [("spatial", 1.0, slice(0, 2), None)], [("euclidean", 2.0)]])
+def test_distance_selector_cache_path_and_its_retirement(spec):
+    """A rollout with exactly one distance selector runs on the per-node pre-activation cache
+    (csrc/gcm_dense_zc.cu), including the eviction correction once the window is full; an in-place weight update
+    retires the cache for that state and the general kernel takes over.  Every step against the oracle."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    B, N, F, H, T = 5, 40, 24, 20, 130
+    gen = torch.Generator().manual_seed(2024)
+    obs = _clustered(gen, T, B, F)
+    p = oracle.make_params(F, H)
+    gnn, convs = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    hidden, o_hidden, o64 = None, None, None
+    names = []
+    with torch.no_grad():
+        for t in range(T):
+            if t == 100:
+                p = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in p.items()}
+                convs[0].lin_rel.weight.copy_(p["w_rel1"]); convs[0].lin_rel.bias.copy_(p["b1"])
+                convs[0].lin_root.weight.copy_(p["w_root1"])
+                convs[1].lin_rel.weight.copy_(p["w_rel2"]); convs[1].lin_rel.bias.copy_(p["b2"])
+                convs[1].lin_root.weight.copy_(p["w_root2"])
+            belief, hidden = mod(obs[t].to(dev), hidden)
+            names.append(lib.gcm_last_kernel().decode())
+            ref, o_hidden = oracle.dense_gcm_step(obs[t], o_hidden, spec, p, graph_size=N)
+            ref64, o64 = oracle.dense_gcm_step(obs[t].double(), o64, spec, {k: v.double() for k, v in p.items()},
+                                               graph_size=N)
+            assert rel_err(belief, ref64) < TOL + rel_err(ref, ref64), (t, names[-1], rel_err(belief, ref))
+    assert all(n == "k_step_dist_zc" for n in names[1:100])
+    assert all(n == "k_step_general" for n in names[100:])
+    nodes, adj, weights, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
