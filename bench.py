@@ -39,7 +39,7 @@ WORKLOADS = {
              16, 128, 8, 32, [("temporal", (1,), "forward")], "rollout"),
     "cfg2": ("cfg2: DenseGCM N=128 F=32 H=32 TemporalBackedge([1,2,4]) rollout fwd",
              65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "rollout"),
-    "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, fp32 per-node cache)",
+    "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, bf16 per-node cache, fp32 accumulate)",
              16384, 256, 128, 128, [("dense",)], "bptt"),
     "cfg4-cosine": ("cfg4: DenseGCM CosineEdge(0.5) N=512 F=64 H=64 rollout fwd",
                     4096, 512, 64, 64, [("cosine", 0.5)], "rollout"),
@@ -175,7 +175,7 @@ def algorithmic(workload, B, N, F, H, extra=None):
         return "hbm", per * B, "bytes"
     if workload == "cfg3":
         # SURVEY.md 8(d), all-ones structure exploited: 66.8 KB per graph-step forward (bf16 node rows at n = N),
-        # forward + backward = 3x.  (The kernels keep the per-node cache in fp32, so they move more than this.)
+        # forward + backward = 3x.  (The backward here is one pass per WINDOW, so the kernels move less than this.)
         return "hbm", B * (N * F * 2 + 2 * F * 4 + N // 8 + H * 4 + 16) * 3, "bytes"
     if workload == "cfg5":
         n, E = extra
@@ -229,7 +229,8 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": "GCM env-steps/sec (fwd)", "value": rate, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 cache / f32 accumulate" if (mode == "bptt" and args.cache == "bf16") else "f32",
+            "data": "synthetic",
         "config": {"workload": desc, "batch_per_step": args.cpu_batch, "timing": "host wall clock, CPU only"},
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,6 +248,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache", default="bf16", choices=["bf16", "f32"],
+                    help="cfg3: element type of the per-node cache (bf16 = the config's stated precision)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -377,6 +380,7 @@ def main():
         T = 64
         mod = build_dense(dev, N, F, H, spec)
         mod.bptt_capacity = T
+        mod.compute_dtype = torch.bfloat16 if args.cache == "bf16" else None
         opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
         obs_host = (0.5 * torch.randn(T, B, F, generator=gen)).pin_memory()
         obs_dev = obs_host.to(dev)
@@ -417,7 +421,7 @@ def main():
         torch.cuda.synchronize()
         launches = int(_cabi.lib().gcm_launch_count() - n_l0) * K
         kern_ms = total_ms / (K * T)
-        kernel_name = "k_ones_stream_fwd + k_ones_stream_bwd (+ k_linear2, k_outer_reduce, k_ones_update) per step"
+        kernel_name = "k_ones_fwd per step + k_ones_window_bwd per window (+ k_linear2, k_outer_reduce, k_ones_update)"
     else:  # sparse, all-at-once
         mod = build_sparse(dev, N, F, H)
         x = torch.randn(B, N, F, generator=gen)
@@ -463,7 +467,8 @@ def main():
             "metric": "GCM env-steps/sec (fwd)" if mode != "bptt" else "GCM env-steps/sec (fwd+bwd)",
             "value": value, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16 cache / f32 accumulate" if (mode == "bptt" and args.cache == "bf16") else "f32",
+            "data": "synthetic",
             "config": {"workload": desc, "batch_per_gpu": B, "graph_size": N, "obs_size": F, "hidden": H,
                        "state": "in-place node log + bit-packed adjacency; steady state (graphs full)"
                        if mode == "rollout" else mode,

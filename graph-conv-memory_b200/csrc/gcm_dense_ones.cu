@@ -6,25 +6,28 @@
 //     c    = W_rel1 S + b1                                   (the aggregation is the SAME vector for every row)
 //     h_i  = act1(c + W_root1 x_i)                           for every valid row i
 //     out  = act2(W_rel2 (sum_i h_i) + b2 + W_root2 h_t)     (only row t of layer 2 is ever read, gcm.py:314)
-// R_i = W_root1 x_i does not change while the weights stay the same, so it is kept per node in HBM next to the
-// node log (rcache [B, C, H1]; refilled with one GEMM when W_root1 changes), S is maintained incrementally,
-// and a step is
+// R_i = W_root1 x_i does not change while the weights stay the same, so a function of it is kept per node in HBM
+// next to the node log (cache [B, C, H1]; refilled with one GEMM when W_root1 changes), S is maintained
+// incrementally, and a step is
 //     k_ones_update        node write, eviction of the oldest node when full, S update, counter
-//     k_linear2 x2         c = S W_rel1^T + b1 ;  R_t = x_t W_root1^T                      ([B,F] x [F,H1])
-//     k_ones_stream_fwd    G = sum_i act1(c + R_i), h_t            <- the only pass over per-node data:
-//                                                                     n * H1 * 4 bytes per graph, HBM-bound
+//     k_linear2 x2         c = S W_rel1^T + b1 ;  r_t = x_t W_root1^T                      ([B,F] x [F,H1])
+//     k_ones_fwd           G = sum_i act1(c + R_i), h_t            <- the only pass over per-node data:
+//                                                                     n * H1 cache elements per graph, HBM-bound
 //     k_linear2            belief = act2(G W_rel2^T + b2 + h_t W_root2^T)
 // instead of the reference's [B,N,N] x [B,N,F] bmm + 4 GEMMs over all N rows.  The adjacency itself is implicit
 // on this path; k_fill_dense_masks writes the bit masks when the state is materialised or leaves the path.
-// Backward (BPTT): dz_i = dh_i * act1'(h_i) is accumulated per node in DZ [B, C, H1] by k_ones_stream_bwd; the
-// two products with x_i (dW_root1 = sum_i DZ_i x_i^T, dx_i = W_root1^T DZ_i) are linear in DZ and are applied
-// ONCE per BPTT window, not once per step.
+// Backward (BPTT): see "The per-node cache and the passes over it" below - one pass per WINDOW, not per step;
+// every weight gradient is one reduction over the window's saved [steps, B, .] buffers (k_outer_reduce).
+#include <cuda_bf16.h>
+
 #include "gcm_common.cuh"
+
 
 // ------------------------------------------------------------------------------------------------
 // state update
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ones_update(const gcm_dense_state st, const float* obs, float* xsum) {
+__global__ void __launch_bounds__(256) k_ones_update(const gcm_dense_state st, const float* obs, const float* xsum_in,
+                                                     float* xsum) {
   const int F4 = st.F >> 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)st.B * F4) return;
@@ -32,7 +35,7 @@ __global__ void __launch_bounds__(256) k_ones_update(const gcm_dense_state st, c
   const int cnt = __ldcg(st.count + b);
   const int slot = gcm_slot(cnt, st.C);
   float4* nodes_b = reinterpret_cast<float4*>(st.nodes + (size_t)b * st.C * st.F);
-  float4 s = reinterpret_cast<float4*>(xsum)[(size_t)b * F4 + c];
+  float4 s = reinterpret_cast<const float4*>(xsum_in)[(size_t)b * F4 + c];
   const float4 x = reinterpret_cast<const float4*>(obs)[(size_t)b * F4 + c];
   if (cnt >= st.N) {   // full: the oldest node leaves the window (gcm.py:323-355)
     const float4 old = nodes_b[(size_t)gcm_slot(cnt - st.N, st.C) * F4 + c];
@@ -62,8 +65,23 @@ __global__ void __launch_bounds__(128) k_ones_xsum(const gcm_dense_state st, flo
 
 // ------------------------------------------------------------------------------------------------
 // out[r, :] = act(A1[r, :] W1^T + A2[r, :] W2^T + bias)        W row-major [Ho, K] (torch.nn.Linear layout)
-// 64-row tile per CTA, K streamed through shared memory in chunks of 32, 4 x NT register tile per thread.
+// 64-row tile per CTA, K streamed through shared memory in chunks of 32 (A tile stored transposed so that a
+// thread's 4 rows / 4 columns are one 128-bit shared load each), 4 x NT register tile per thread.
 // ------------------------------------------------------------------------------------------------
+constexpr float ONES_CLAMP = 40.0f;
+__device__ __forceinline__ float ones_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exp(2 clamp(z)); NaN propagates
+__device__ __forceinline__ float ones_exp2x(float z) {
+  const float zc = fminf(fmaxf(z, -ONES_CLAMP), ONES_CLAMP);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zc * 2.8853900817779268f));
+  return z == z ? e : z;
+}
+
 constexpr int L2_TM = 64, L2_KC = 32, L2_THREADS = 256;
 struct Linear2Args {
   const float* A1; const float* W1; int K1; long long lda1;
@@ -79,10 +97,12 @@ struct Linear2Args {
 
 template <int NT>
 __global__ void __launch_bounds__(L2_THREADS) k_linear2(const Linear2Args a) {
-  __shared__ float As[L2_TM][L2_KC + 1];
-  __shared__ float Ws[L2_KC][16 * NT + 1];
+  constexpr int NV = NT < 4 ? NT : 4;           // contiguous columns per thread and group
+  constexpr int NG = NT / NV;                   // column groups, 16 * NV apart
+  __shared__ __align__(16) float As[L2_KC][L2_TM + 4];       // [k][row]
+  __shared__ __align__(16) float Ws[L2_KC][16 * NT + 4];     // [k][column]
   const int tid = threadIdx.x;
-  const int tr = tid >> 4, tc = tid & 15;       // 16 row groups x 16 column groups
+  const int tr = tid >> 4, tc = tid & 15;       // rows tr*4 .. tr*4+3; columns g*16*NV + tc*NV + v
   const long long row0 = (long long)blockIdx.x * L2_TM;
   const int Ho = a.Ho;
   float acc[4][NT];
@@ -102,7 +122,7 @@ __global__ void __launch_bounds__(L2_THREADS) k_linear2(const Linear2Args a) {
       for (int i = tid; i < L2_TM * L2_KC; i += L2_THREADS) {
         const int r = i / L2_KC, kk = i - r * L2_KC;
         const long long gr = row0 + r;
-        As[r][kk] = (gr < a.rows && kk < kc) ? A[gr * lda + k0 + kk] : 0.0f;
+        As[kk][r] = (gr < a.rows && kk < kc) ? A[gr * lda + k0 + kk] : 0.0f;
       }
       for (int i = tid; i < 16 * NT * L2_KC; i += L2_THREADS) {
         const int o = i / L2_KC, kk = i - o * L2_KC;
@@ -111,11 +131,19 @@ __global__ void __launch_bounds__(L2_THREADS) k_linear2(const Linear2Args a) {
       __syncthreads();
 #pragma unroll 8
       for (int kk = 0; kk < L2_KC; ++kk) {
-        float av[4], wv[NT];
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tr * 4]);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+        float wv[NT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = As[tr * 4 + i][kk];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) wv[j] = Ws[kk][tc + 16 * j];
+        for (int g = 0; g < NG; ++g) {
+          if (NV == 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][g * 64 + tc * 4]);
+            wv[g * 4] = w4.x; wv[g * 4 + 1] = w4.y; wv[g * 4 + 2] = w4.z; wv[g * 4 + 3] = w4.w;
+          } else {
+            const float2 w2 = *reinterpret_cast<const float2*>(&Ws[kk][tc * 2]);
+            wv[0] = w2.x; wv[1] = w2.y;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -130,9 +158,10 @@ __global__ void __launch_bounds__(L2_THREADS) k_linear2(const Linear2Args a) {
     if (gr < a.rows) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const int c = tc + 16 * j;
+        const int c = (j / NV) * (16 * NV) + tc * NV + (j % NV);
         if (c < Ho) {
-          float v = gcm_act_fwd(acc[i][j] + (a.bias ? __ldg(a.bias + c) : 0.0f), a.act);
+          const float z = acc[i][j] + (a.bias ? __ldg(a.bias + c) : 0.0f);
+          float v = a.act == GCM_ACT_EXP2X ? ones_exp2x(z) : gcm_act_fwd(z, a.act);
           if (a.accumulate) v += a.out[gr * a.ldo + c];
           a.out[gr * a.ldo + c] = v;
           bad |= !isfinite(v);
@@ -210,103 +239,307 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(const OuterArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the pass over the per-node cache.  One CTA per graph, thread = hidden channel (H1 <= 128), rows of the
-// window streamed with 8 independent loads in flight per thread (a row is one coalesced H1 * 4-byte read).
-// Forward:  G = sum_i act1(c + R_i), h_t = act1(c + R_t);  R_t (this step's new row) is stored on the way.
-// Backward: dz_i = (dG + [i == t] dh_t) * act1'(act1(c + R_i)) accumulated into DZ_i; dc = sum_i dz_i; the
-//           finished DZ row of node t is also returned (dL/dx_t = W_root1^T DZ_t + running dS).
-// `back` = how many steps ago the step was taken (0 = the most recent): window and t are derived from count.
+// The per-node cache and the passes over it.
+//
+// tanh (the README's activation): h_i = tanh(c + R_i) = 1 - 2 / (exp(2c) exp(2 R_i) + 1).  The cache holds
+// Q_i = exp(2 R_i) and the step supplies E = exp(2c) (both written by gcm_linear2 with the EXP2X epilogue,
+// arguments clamped to +-40 so that neither factor over/underflows), so one element costs one multiply, one
+// add and ONE MUFU (rcp) instead of two:  u = 1 / (E Q_i + 1),  h_i = 1 - 2u,  1 - h_i^2 = 4u(1 - u).
+// relu / identity keep R_i itself in the cache.  G = sum_i h_i,  P = sum_i act1'(c + R_i).
+// Cache element type: float32, or bfloat16 (BASELINE cfg3's stated precision; halves the only per-node
+// stream of the step; a bf16 Q has the dynamic range of fp32 and 2^-9 relative precision).
+//
+// Forward  (k_ones_fwd, once per step, CTA per graph): stores the new row, streams the n - 1 older rows of the
+//          window with 16-byte loads (4 in flight per thread), writes G, h_t and - while recording - P.
+// Backward is NOT a per-step pass.  GCM has no recurrence through the belief (the state is the observation
+// log), so dL/d(pre-activation) of node i summed over the steps of a BPTT window,
+//          DZ_i = sum_k dG_k * act1'(c_k + R_i)  [+ the lin_root2 term of the node's own step],
+// is computed for all nodes by ONE pass over the cache at the end of the window (k_ones_window_bwd: E_k and
+// dG_k of every step staged in shared memory, each cache row read once), and dc_k = dG_k * P_k + (own term)
+// needs no pass at all.  k_ones_node_bwd computes the DZ row of one node (dL/dx_k for callers whose
+// observations require grad).
 // ------------------------------------------------------------------------------------------------
-struct OnesStreamArgs {
-  gcm_dense_state st;
-  int H1, act1, back;
-  float* rcache;        // [B, C, H1]
-  const float* c;       // [B, H1]
-  const float* r_t;     // fwd: [B, H1] new row (stored into rcache)
-  float* G;             // fwd out [B, H1]
-  float* h_t;           // fwd out [B, H1]
-  const float* dG;      // bwd in  [B, H1]
-  const float* dh_t;    // bwd in  [B, H1]
-  float* DZ;            // bwd: [B, C, H1] accumulated
-  float* dc;            // bwd out [B, H1]
-  float* dz_t;          // bwd out [B, H1]
+template <typename CT> struct OnesCache;
+template <> struct OnesCache<float> {
+  static constexpr int VN = 4;   // elements per 16-byte load
+  static __device__ __forceinline__ void load16(const float* p, float (&v)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void load4(const float* p, float (&v)[4]) { load16(p, v); }
+  static __device__ __forceinline__ float load1(const float* p) { return *p; }
+  static __device__ __forceinline__ float round(float x) { return x; }
+  static __device__ __forceinline__ void store1(float* p, float x) { *p = x; }
+};
+template <> struct OnesCache<__nv_bfloat16> {
+  static constexpr int VN = 8;
+  static __device__ __forceinline__ void unpack(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void load16(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(p));
+    unpack(t.x, v[0], v[1]); unpack(t.y, v[2], v[3]); unpack(t.z, v[4], v[5]); unpack(t.w, v[6], v[7]);
+  }
+  static __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = __ldcs(reinterpret_cast<const uint2*>(p));
+    unpack(t.x, v[0], v[1]); unpack(t.y, v[2], v[3]);
+  }
+  static __device__ __forceinline__ float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+  static __device__ __forceinline__ void store1(__nv_bfloat16* p, float x) { *p = __float2bfloat16_rn(x); }
 };
 
-template <bool BWD>
-__global__ void __launch_bounds__(128) k_ones_stream(const OnesStreamArgs a) {
+// value and derivative of act1 at one (step, node, channel): `e` is the step's E (tanh) or c, `q` the cached
+// Q (tanh) or R.  Returns h = act1(c + R); `d` = act1'(c + R)  (tanh: 1 - h^2 = 4 u (1 - u), exact when saturated).
+template <int ACT>
+__device__ __forceinline__ float ones_eval(float e, float q, float& d) {
+  if (ACT == GCM_ACT_TANH) {
+    const float u = ones_rcp(fmaf(e, q, 1.0f));
+    d = 4.0f * u * (1.0f - u);
+    return fmaf(-2.0f, u, 1.0f);
+  } else if (ACT == GCM_ACT_RELU) {
+    const float z = e + q;
+    d = z > 0.0f ? 1.0f : 0.0f;
+    return z <= 0.0f ? 0.0f : z;
+  } else {
+    d = 1.0f;
+    return e + q;
+  }
+}
+
+struct OnesFwdArgs {
+  gcm_dense_state st;
+  int H1;
+  void* cache;          // [B, C, H1] float32 / bfloat16
+  const float* e_c;     // [B, H1]  exp(2c) (tanh) or c
+  const float* q_t;     // [B, H1]  exp(2 r_t) (tanh) or r_t: the new node's row (stored into the cache)
+  float* G;             // [B, H1]  out
+  float* P;             // [B, H1]  out (REC only)
+  float* h_t;           // [B, H1]  out
+};
+
+template <typename CT, int ACT, bool REC>
+__global__ void __launch_bounds__(128) k_ones_fwd(const OnesFwdArgs a) {
+  constexpr int VN = OnesCache<CT>::VN;
+  __shared__ float red_u[128 * VN];
+  __shared__ float red_p[REC ? 128 * VN : 1];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int H1 = a.H1, C = a.st.C, N = a.st.N;
+  const int tpr = H1 / VN;                      // threads per row (host: H1 % VN == 0)
+  const int rpp = 128 / tpr;                    // rows per pass
+  const int rl = tid / tpr, vl = tid - rl * tpr;
+  const int cnt = __ldcg(a.st.count + b);       // nodes written so far, this step's included
+  const int t = cnt - 1;
+  const int n = min(cnt, N);
+  const int s0 = (cnt - n) % C;                 // slot of the oldest row of the window
+  CT* cache = reinterpret_cast<CT*>(a.cache) + (size_t)b * C * H1;
+  float su[VN], sp[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) su[j] = 0.0f, sp[j] = 0.0f;
+  if (rl < rpp) {
+    float ec[VN];
+#pragma unroll
+    for (int j = 0; j < VN; j += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(a.e_c + (size_t)b * H1 + vl * VN + j);
+      ec[j] = t4.x; ec[j + 1] = t4.y; ec[j + 2] = t4.z; ec[j + 3] = t4.w;
+    }
+    const CT* base = cache + vl * VN;
+    auto row_ptr = [&](int l) {
+      int s = s0 + l;
+      s = s >= C ? s - C : s;
+      return base + (size_t)s * H1;
+    };
+    auto consume = [&](const float (&q)[VN]) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        float d;
+        su[j] += ones_eval<ACT>(ec[j], q[j], d);
+        if (REC) sp[j] += d;
+      }
+    };
+    const int last = n - 1;                     // rows 0 .. n-2 of the window are older nodes; n-1 is node t
+    int l = rl;
+    for (; l + 3 * rpp < last; l += 4 * rpp) {
+      float q0[VN], q1[VN], q2[VN], q3[VN];
+      OnesCache<CT>::load16(row_ptr(l), q0);
+      OnesCache<CT>::load16(row_ptr(l + rpp), q1);
+      OnesCache<CT>::load16(row_ptr(l + 2 * rpp), q2);
+      OnesCache<CT>::load16(row_ptr(l + 3 * rpp), q3);
+      consume(q0); consume(q1); consume(q2); consume(q3);
+    }
+    for (; l < last; l += rpp) {
+      float q0[VN];
+      OnesCache<CT>::load16(row_ptr(l), q0);
+      consume(q0);
+    }
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      red_u[rl * H1 + vl * VN + j] = su[j];
+      if (REC) red_p[rl * H1 + vl * VN + j] = sp[j];
+    }
+  }
+  __syncthreads();
+  if (tid < H1) {
+    float U = 0.0f, Q2 = 0.0f;
+    for (int r = 0; r < rpp; ++r) {
+      U += red_u[r * H1 + tid];
+      if (REC) Q2 += red_p[r * H1 + tid];
+    }
+    // the step's own node: its row enters the cache (rounded to the cache type) and the sums
+    const float q = OnesCache<CT>::round(a.q_t[(size_t)b * H1 + tid]);
+    OnesCache<CT>::store1(cache + (size_t)(t % C) * H1 + tid, a.q_t[(size_t)b * H1 + tid]);
+    float d;
+    const float ht = ones_eval<ACT>(a.e_c[(size_t)b * H1 + tid], q, d);
+    const float g = U + ht, p = Q2 + d;
+    a.G[(size_t)b * H1 + tid] = g;
+    if (REC) a.P[(size_t)b * H1 + tid] = p;
+    a.h_t[(size_t)b * H1 + tid] = ht;
+  }
+}
+
+// ---- window-level backward -------------------------------------------------------------------------
+struct OnesWinArgs {
+  gcm_dense_state st;
+  int H1;
+  const void* cache;
+  int steps_total;      // steps taken on the state since the chain started (count0 = count - steps_total)
+  int steps_used;       // chain steps 0 .. steps_used-1 carry gradient
+  const float* wE;      // [K, B, H1]   E_k (tanh) or c_k
+  const float* wdG;     // [K, B, H1]   dL/dG_k
+  const float* wdzo;    // [K, B, H1]   lin_root2 term of the step's own node, already times act1'(h_t)
+  long long sstride;    // floats between consecutive steps of the three buffers
+  float* DZ;            // [B, C, H1]   out (every slot written; zero where no gradient arrives)
+  int kchunk;           // steps staged in shared memory at a time
+};
+
+template <typename CT, int ACT>
+__global__ void __launch_bounds__(256) k_ones_window_bwd(const OnesWinArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int H1 = a.H1, C = a.st.C, N = a.st.N;
+  const int tpr = H1 >> 2;                      // host: H1 % 4 == 0, H1 <= 128
+  const int rpp = 256 / tpr;
+  const int rl = tid / tpr, vl = tid - rl * tpr;
+  const int count0 = __ldcg(a.st.count + b) - a.steps_total;
+  const int Kc = a.steps_used;
+  const int lo = max(0, count0 + 1 - N);        // oldest node any step of the chain saw
+  const int hi = count0 + Kc;                   // nodes at or beyond hi receive no gradient
+  const CT* cache = reinterpret_cast<const CT*>(a.cache) + (size_t)b * C * H1;
+  float* DZ = a.DZ + (size_t)b * C * H1;
+  float* sE = smem;
+  float* sG = smem + (size_t)a.kchunk * H1;
+  for (int k0 = 0; k0 < Kc || k0 == 0; k0 += a.kchunk) {
+    const int kc = max(0, min(a.kchunk, Kc - k0));
+    __syncthreads();
+    for (int i = tid; i < kc * tpr; i += 256) {
+      const int kk = i / tpr, v = i - kk * tpr;
+      const size_t g = (size_t)(k0 + kk) * a.sstride + (size_t)b * H1 + v * 4;
+      *reinterpret_cast<float4*>(sE + kk * H1 + v * 4) = *reinterpret_cast<const float4*>(a.wE + g);
+      *reinterpret_cast<float4*>(sG + kk * H1 + v * 4) = *reinterpret_cast<const float4*>(a.wdG + g);
+    }
+    __syncthreads();
+    if (rl < rpp) {
+      for (int j = rl; j < C; j += rpp) {
+        const int p = lo + j;
+        const int slot = p % C;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (p < hi) {
+          const int ka = max(k0, p - count0);
+          const int kb = min(k0 + kc - 1, p + N - count0 - 1);
+          if (ka <= kb) {
+            float q[4];
+            OnesCache<CT>::load4(cache + (size_t)slot * H1 + vl * 4, q);
+#pragma unroll 2
+            for (int k = ka; k <= kb; ++k) {
+              const float4 e4 = *reinterpret_cast<const float4*>(sE + (k - k0) * H1 + vl * 4);
+              const float4 g4 = *reinterpret_cast<const float4*>(sG + (k - k0) * H1 + vl * 4);
+              float d;
+              ones_eval<ACT>(e4.x, q[0], d); acc[0] = fmaf(g4.x, d, acc[0]);
+              ones_eval<ACT>(e4.y, q[1], d); acc[1] = fmaf(g4.y, d, acc[1]);
+              ones_eval<ACT>(e4.z, q[2], d); acc[2] = fmaf(g4.z, d, acc[2]);
+              ones_eval<ACT>(e4.w, q[3], d); acc[3] = fmaf(g4.w, d, acc[3]);
+            }
+          }
+          if (k0 == 0 && p >= count0) {
+            const float4 o4 = *reinterpret_cast<const float4*>(a.wdzo + (size_t)(p - count0) * a.sstride +
+                                                               (size_t)b * H1 + vl * 4);
+            acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w;
+          }
+        }
+        float4* out = reinterpret_cast<float4*>(DZ + (size_t)slot * H1 + vl * 4);
+        if (k0 == 0) {
+          *out = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        } else {
+          float4 o = *out;
+          o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
+          *out = o;
+        }
+      }
+    }
+  }
+}
+
+// DZ row of the node written at chain step k, over the steps k .. min(steps_used, k+N) - 1 that saw it (its own
+// step included: G_k sums over node k too), plus the lin_root2 term dzo_k of its own step.  CTA per graph, thread = channel.
+struct OnesNodeArgs {
+  gcm_dense_state st;
+  int H1;
+  const void* cache;
+  int steps_total, steps_used, k;
+  const float* wE; const float* wdG; const float* wdzo;
+  long long sstride;
+  float* dz;            // [B, H1] out
+};
+template <typename CT, int ACT>
+__global__ void __launch_bounds__(128) k_ones_node_bwd(const OnesNodeArgs a) {
   const int b = blockIdx.x, ch = threadIdx.x;
   const int H1 = a.H1, C = a.st.C, N = a.st.N;
   if (ch >= H1) return;
-  const int cnt = __ldcg(a.st.count + b) - a.back;    // nodes written up to and including this step
-  const int t = cnt - 1;                              // position of the step's own node
-  const int n = min(cnt, N);
-  const int first = cnt - n;
-  float* R = a.rcache + (size_t)b * C * H1;
-  const float cv = a.c[(size_t)b * H1 + ch];
-  const int act = a.act1;
-  // rows first .. t-1 live in slots slot0, slot0 + 1, ... (mod C): one division per graph, not per row
-  int slot = gcm_slot(first, C);
-  auto next_off = [&]() {
-    const size_t off = (size_t)slot * H1 + ch;
-    slot = slot + 1 == C ? 0 : slot + 1;
-    return off;
-  };
-  if (!BWD) {
-    const float rt = a.r_t[(size_t)b * H1 + ch];
-    R[(size_t)gcm_slot(t, C) * H1 + ch] = rt;
-    float g = 0.0f;
-    int l = 0;
-    for (; l + 8 <= n - 1; l += 8) {
-      float v[8];
+  const int count0 = __ldcg(a.st.count + b) - a.steps_total;
+  const int p = count0 + a.k;
+  const float q = OnesCache<CT>::load1(reinterpret_cast<const CT*>(a.cache) + ((size_t)b * C + p % C) * H1 + ch);
+  const size_t col = (size_t)b * H1 + ch;
+  float acc = a.wdzo[(size_t)a.k * a.sstride + col];
+  const int kb = min(a.steps_used, a.k + N) - 1;
+  int k = a.k;
+  for (; k + 3 <= kb; k += 4) {
+    float e[4], g[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcs(R + next_off());
+    for (int u = 0; u < 4; ++u) {
+      e[u] = a.wE[(size_t)(k + u) * a.sstride + col];
+      g[u] = a.wdG[(size_t)(k + u) * a.sstride + col];
+    }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) g += gcm_act_fast(cv + v[u], act);
+    for (int u = 0; u < 4; ++u) {
+      float d;
+      ones_eval<ACT>(e[u], q, d);
+      acc = fmaf(g[u], d, acc);
     }
-    for (; l < n - 1; ++l) g += gcm_act_fast(cv + __ldcs(R + next_off()), act);
-    const float ht = gcm_act_fast(cv + rt, act);
-    a.G[(size_t)b * H1 + ch] = g + ht;
-    a.h_t[(size_t)b * H1 + ch] = ht;
-  } else {
-    float* DZ = a.DZ + (size_t)b * C * H1;
-    const float dg = a.dG[(size_t)b * H1 + ch];
-    float dcs = 0.0f;
-    int l = 0;
-    for (; l + 8 <= n - 1; l += 8) {
-      float v[8], z[8];
-      size_t offs[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        offs[u] = next_off();
-        v[u] = __ldcs(R + offs[u]);
-        z[u] = __ldcs(DZ + offs[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float h = gcm_act_fast(cv + v[u], act);
-        const float d = dg * gcm_act_grad(h, act);
-        dcs += d;
-        DZ[offs[u]] = z[u] + d;
-      }
-    }
-    for (; l < n - 1; ++l) {
-      const size_t off = next_off();
-      const float h = gcm_act_fast(cv + __ldcs(R + off), act);
-      const float d = dg * gcm_act_grad(h, act);
-      dcs += d;
-      DZ[off] += d;
-    }
-    {   // the step's own node also feeds lin_root2
-      const size_t off = (size_t)gcm_slot(t, C) * H1 + ch;
-      const float h = gcm_act_fast(cv + R[off], act);
-      const float d = (dg + a.dh_t[(size_t)b * H1 + ch]) * gcm_act_grad(h, act);
-      dcs += d;
-      const float tot = DZ[off] + d;
-      DZ[off] = tot;
-      a.dz_t[(size_t)b * H1 + ch] = tot;
-    }
-    a.dc[(size_t)b * H1 + ch] = dcs;
   }
+  for (; k <= kb; ++k) {
+    float d;
+    ones_eval<ACT>(a.wE[(size_t)k * a.sstride + col], q, d);
+    acc = fmaf(a.wdG[(size_t)k * a.sstride + col], d, acc);
+  }
+  a.dz[col] = acc;
+}
+
+// per-step elementwise pieces of the backward:  do = d_belief * act2'(belief);
+// dzo = dh_t * act1'(h_t) (in place over dh_t);  dc = dG * P + dzo;  dcs = dc + dcs_next (suffix sum, optional)
+__global__ void __launch_bounds__(256) k_act_bwd(const float* d_out, const float* out, int act, long long n, float* res) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) res[i] = d_out[i] * gcm_act_grad(out[i], act);
+}
+__global__ void __launch_bounds__(256) k_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1,
+                                                 long long n, float* dc, const float* dcs_next, float* dcs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dzo = dht[i] * gcm_act_grad(h_t[i], act1);
+  const float v = fmaf(dG[i], P[i], dzo);
+  dht[i] = dzo;
+  dc[i] = v;
+  if (dcs) dcs[i] = v + (dcs_next ? dcs_next[i] : 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -337,12 +570,13 @@ static int ones_check_state(const gcm_dense_state* st, const char* what) {
   return GCM_OK;
 }
 
-extern "C" int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, float* xsum, void* stream) {
+extern "C" int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, const float* xsum_in, float* xsum,
+                                     void* stream) {
   if (int rc = ones_check_state(st, "dense_ones_update")) return rc;
-  GCM_REQUIRE(obs && xsum, "dense_ones_update: null pointer");
+  GCM_REQUIRE(obs && xsum_in && xsum, "dense_ones_update: null pointer");
   if (st->B == 0) return GCM_OK;
   const long long work = (long long)st->B * (st->F / 4);
-  k_ones_update<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, obs, xsum);
+  k_ones_update<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, obs, xsum_in, xsum);
   if (int rc = gcm_check_launch("k_ones_update")) return rc;
   k_ones_bump<<<(st->B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st->count, st->B);
   return gcm_check_launch("k_ones_bump");
@@ -388,29 +622,130 @@ extern "C" int gcm_outer_reduce(const float* A, long long lda, int Ho, const flo
   return gcm_check_launch("k_outer_reduce");
 }
 
-extern "C" int gcm_dense_ones_stream_fwd(const gcm_dense_state* st, int H1, int act1, float* rcache, const float* c,
-                                         const float* r_t, float* G, float* h_t, void* stream) {
-  if (int rc = ones_check_state(st, "dense_ones_stream_fwd")) return rc;
-  GCM_REQUIRE(H1 >= 1 && H1 <= 128 && rcache && c && r_t && G && h_t, "dense_ones_stream_fwd: bad arguments");
-  if (st->B == 0) return GCM_OK;
-  OnesStreamArgs a{};
-  a.st = *st; a.H1 = H1; a.act1 = act1; a.back = 0; a.rcache = rcache; a.c = c; a.r_t = r_t; a.G = G; a.h_t = h_t;
-  k_ones_stream<false><<<st->B, 128, 0, (cudaStream_t)stream>>>(a);
-  return gcm_check_launch("k_ones_stream_fwd");
+// ---- cache passes ---------------------------------------------------------------------------------
+static int ones_check_cache(int H1, int act1, int cache_type, const char* what) {
+  GCM_REQUIRE(act1 == GCM_ACT_NONE || act1 == GCM_ACT_TANH || act1 == GCM_ACT_RELU, "%s: bad activation", what);
+  GCM_REQUIRE(cache_type == GCM_CACHE_F32 || cache_type == GCM_CACHE_BF16, "%s: bad cache type", what);
+  GCM_REQUIRE(H1 >= 4 && H1 <= 128 && H1 % (cache_type == GCM_CACHE_BF16 ? 8 : 4) == 0,
+              "%s: H1 must be <= 128 and a multiple of %d", what, cache_type == GCM_CACHE_BF16 ? 8 : 4);
+  return GCM_OK;
 }
 
-extern "C" int gcm_dense_ones_stream_bwd(const gcm_dense_state* st, int steps_back, int H1, int act1, float* rcache,
-                                         const float* c, const float* dG, const float* dh_t, float* DZ, float* dc,
-                                         float* dz_t, void* stream) {
-  if (int rc = ones_check_state(st, "dense_ones_stream_bwd")) return rc;
-  GCM_REQUIRE(H1 >= 1 && H1 <= 128 && steps_back >= 0 && rcache && c && dG && dh_t && DZ && dc && dz_t,
-              "dense_ones_stream_bwd: bad arguments");
+// dispatch on (cache type, activation)
+#define ONES_DISPATCH(CT_EXPR, ACT_EXPR, CALL)                                                  \
+  do {                                                                                          \
+    if ((CT_EXPR) == GCM_CACHE_BF16) {                                                          \
+      using CT = __nv_bfloat16;                                                                 \
+      if ((ACT_EXPR) == GCM_ACT_TANH) { constexpr int ACT = GCM_ACT_TANH; CALL; }               \
+      else if ((ACT_EXPR) == GCM_ACT_RELU) { constexpr int ACT = GCM_ACT_RELU; CALL; }          \
+      else { constexpr int ACT = GCM_ACT_NONE; CALL; }                                          \
+    } else {                                                                                    \
+      using CT = float;                                                                         \
+      if ((ACT_EXPR) == GCM_ACT_TANH) { constexpr int ACT = GCM_ACT_TANH; CALL; }               \
+      else if ((ACT_EXPR) == GCM_ACT_RELU) { constexpr int ACT = GCM_ACT_RELU; CALL; }          \
+      else { constexpr int ACT = GCM_ACT_NONE; CALL; }                                          \
+    }                                                                                           \
+  } while (0)
+
+extern "C" int gcm_dense_ones_fwd(const gcm_dense_state* st, int H1, int act1, int cache_type, void* cache,
+                                  const float* e_c, const float* q_t, float* G, float* P, float* h_t, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_fwd")) return rc;
+  if (int rc = ones_check_cache(H1, act1, cache_type, "dense_ones_fwd")) return rc;
+  GCM_REQUIRE(cache && e_c && q_t && G && h_t, "dense_ones_fwd: null pointer");
   if (st->B == 0) return GCM_OK;
-  OnesStreamArgs a{};
-  a.st = *st; a.H1 = H1; a.act1 = act1; a.back = steps_back; a.rcache = rcache; a.c = c; a.dG = dG; a.dh_t = dh_t;
-  a.DZ = DZ; a.dc = dc; a.dz_t = dz_t;
-  k_ones_stream<true><<<st->B, 128, 0, (cudaStream_t)stream>>>(a);
-  return gcm_check_launch("k_ones_stream_bwd");
+  OnesFwdArgs a{*st, H1, cache, e_c, q_t, G, P, h_t};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (P) ONES_DISPATCH(cache_type, act1, (k_ones_fwd<CT, ACT, true><<<st->B, 128, 0, s>>>(a)));
+  else ONES_DISPATCH(cache_type, act1, (k_ones_fwd<CT, ACT, false><<<st->B, 128, 0, s>>>(a)));
+  return gcm_check_launch("k_ones_fwd");
+}
+
+template <typename CT, int ACT>
+static int ones_launch_window(const OnesWinArgs& a, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024) {
+    static bool done = false;   // per instantiation
+    if (!done) {
+      if (cudaFuncSetAttribute(k_ones_window_bwd<CT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+          cudaSuccess) {
+        gcm_set_error("k_ones_window_bwd: cannot raise the dynamic shared memory limit");
+        return GCM_ERR_CUDA;
+      }
+      done = true;
+    }
+  }
+  k_ones_window_bwd<CT, ACT><<<a.st.B, 256, smem, s>>>(a);
+  return GCM_OK;
+}
+
+extern "C" int gcm_dense_ones_window_bwd(const gcm_dense_state* st, int H1, int act1, int cache_type, const void* cache,
+                                         int steps_total, int steps_used, const float* wE, const float* wdG,
+                                         const float* wdzo, long long step_stride, float* DZ, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_window_bwd")) return rc;
+  if (int rc = ones_check_cache(H1, act1, cache_type, "dense_ones_window_bwd")) return rc;
+  GCM_REQUIRE(cache && wE && wdG && wdzo && DZ && steps_used >= 0 && steps_used <= steps_total &&
+                  steps_total <= st->C - st->N + 1 && step_stride >= (long long)st->B * H1,
+              "dense_ones_window_bwd: bad arguments (the chain must fit the spare rows of the node log)");
+  if (st->B == 0) return GCM_OK;
+  int kchunk = (192 * 1024) / (8 * H1);
+  if (kchunk > steps_used) kchunk = steps_used > 0 ? steps_used : 1;
+  OnesWinArgs a{*st, H1, cache, steps_total, steps_used, wE, wdG, wdzo, step_stride, DZ, kchunk};
+  const size_t smem = (size_t)kchunk * H1 * 8;
+  int rc = GCM_OK;
+  ONES_DISPATCH(cache_type, act1, (rc = ones_launch_window<CT, ACT>(a, smem, (cudaStream_t)stream)));
+  if (rc) return rc;
+  return gcm_check_launch("k_ones_window_bwd");
+}
+
+extern "C" int gcm_dense_ones_node_bwd(const gcm_dense_state* st, int H1, int act1, int cache_type, const void* cache,
+                                       int steps_total, int steps_used, int k, const float* wE, const float* wdG,
+                                       const float* wdzo, long long step_stride, float* dz, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_node_bwd")) return rc;
+  if (int rc = ones_check_cache(H1, act1, cache_type, "dense_ones_node_bwd")) return rc;
+  GCM_REQUIRE(cache && wE && wdG && wdzo && dz && k >= 0 && k < steps_used && steps_used <= steps_total &&
+                  steps_total <= st->C - st->N + 1,
+              "dense_ones_node_bwd: bad arguments");
+  if (st->B == 0) return GCM_OK;
+  OnesNodeArgs a{*st, H1, cache, steps_total, steps_used, k, wE, wdG, wdzo, step_stride, dz};
+  cudaStream_t s = (cudaStream_t)stream;
+  ONES_DISPATCH(cache_type, act1, (k_ones_node_bwd<CT, ACT><<<st->B, 128, 0, s>>>(a)));
+  return gcm_check_launch("k_ones_node_bwd");
+}
+
+extern "C" int gcm_act_backward(const float* d_out, const float* out, int act, long long n, float* res, void* stream) {
+  GCM_REQUIRE(d_out && out && res && n >= 0, "act_backward: bad arguments");
+  if (n == 0) return GCM_OK;
+  k_act_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, out, act, n, res);
+  return gcm_check_launch("k_act_bwd");
+}
+
+extern "C" int gcm_dense_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1, long long n,
+                                 float* dc, const float* dcs_next, float* dcs, void* stream) {
+  GCM_REQUIRE(dG && dht && P && h_t && dc && n >= 0, "dense_ones_dc: bad arguments");
+  if (n == 0) return GCM_OK;
+  k_ones_dc<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dG, dht, P, h_t, act1, n, dc, dcs_next, dcs);
+  return gcm_check_launch("k_ones_dc");
+}
+
+// float32 -> cache element type (cache refill after a weight update)
+__global__ void __launch_bounds__(256) k_to_bf16(const float* in, __nv_bfloat16* out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+extern "C" int gcm_to_bf16(const float* in, void* out, long long n, void* stream) {
+  GCM_REQUIRE(in && out && n >= 0, "to_bf16: bad arguments");
+  if (n == 0) return GCM_OK;
+  const long long thr = (n + 3) / 4;
+  k_to_bf16<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  return gcm_check_launch("k_to_bf16");
 }
 
 extern "C" int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream) {

@@ -28,6 +28,7 @@ FLAG_NOTDENSE = 32
 SEL_NONE, SEL_TEMPORAL, SEL_DENSE, SEL_EUCLIDEAN, SEL_COSINE, SEL_SPATIAL = range(6)
 DIR = {"forward": 0, "backward": 1, "both": 2}
 ACT = {"none": 0, "tanh": 1, "relu": 2}
+ACT_EXP2X = 3          # gcm_linear2 epilogue only: exp(2 clamp(z)), the tanh form of the ones path cache
 TK_AUTO, TK_HC, TK_TC, TK_WIN, TK_ROWS = range(5)
 EB_AUTO, EB_PAIRS, EB_HASH = range(3)
 STEP_PURE_TEMPORAL = 1
@@ -96,13 +97,21 @@ _SIGNATURES = {
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
                                     _P, _P, _L, _P]),
-    "gcm_dense_ones_update": (_I, [C.POINTER(DenseStateC), _P, _P, _P]),
+    "gcm_dense_ones_update": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P]),
     "gcm_dense_ones_xsum": (_I, [C.POINTER(DenseStateC), _P, _P]),
     "gcm_linear2": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P,
                          C.c_longlong, _P, _I, _P]),
     "gcm_outer_reduce": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P]),
-    "gcm_dense_ones_stream_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _P, _P, _P, _P, _P, _P]),
-    "gcm_dense_ones_stream_bwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gcm_dense_ones_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "gcm_dense_ones_window_bwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _I, _I, _P, _P, _P, C.c_longlong, _P, _P]),
+    "gcm_dense_ones_node_bwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, C.c_longlong, _P,
+                                     _P]),
+    "gcm_act_backward": (_I, [_P, _P, _I, C.c_longlong, _P, _P]),
+    "gcm_dense_ones_dc": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P, _P]),
+    "gcm_to_bf16": (_I, [_P, _P, C.c_longlong, _P]),
+    "gcm_linear_tc": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P, C.c_longlong, _I, _P]),
+    "gcm_outer_reduce_tc_workspace": (C.c_longlong, [C.c_longlong]),
+    "gcm_outer_reduce_tc": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),
     "gcm_dense_step_fwd_zc": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), C.POINTER(GnnC), _P, _P, _P, _P]),
     "gcm_set_edge_builder": (_I, [_I]),

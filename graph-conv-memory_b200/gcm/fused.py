@@ -374,7 +374,10 @@ def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tens
     with torch.no_grad():
         feats = module.gnn(nodes, adj, torch.zeros(0, device=state.device), nb, state.N)
         ref = feats[torch.arange(nb, device=state.device), nn - 1]
-    ok = ref.shape == belief[:nb].shape and torch.allclose(ref, belief[:nb].detach(), rtol=1e-3, atol=1e-4, equal_nan=True)
+    # a bfloat16 per-node cache (gcm.ones, DenseGCM.compute_dtype) is allowed BASELINE's 2e-2
+    rtol, atol = (5e-2, 2e-2) if (state.rc_bf16 and state.rcache is not None) else (1e-3, 1e-4)
+    ok = ref.shape == belief[:nb].shape and torch.allclose(ref, belief[:nb].detach(), rtol=rtol, atol=atol,
+                                                           equal_nan=True)
     if not ok:
         warnings.warn(
             "gcm: the GNN looked like a 2-layer DenseGraphConv stack but does not compute one; "

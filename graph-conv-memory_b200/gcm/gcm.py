@@ -138,6 +138,9 @@ class DenseGCM(torch.nn.Module):
         # extra log rows kept while autograd is recording, so that a BPTT window of up to this many
         # steps can be recomputed in backward without any per-step saved activations
         self.bptt_capacity = 128
+        # None (float32 everywhere, 1e-5 parity) or torch.bfloat16: DenseEdge-only states keep their per-node cache in
+        # bfloat16 (BASELINE cfg3's precision, 2e-2 parity); torch.autocast("cuda", dtype=torch.bfloat16) does the same
+        self.compute_dtype = None
 
     # ------------------------------------------------------------------ reference API
     def get_initial_hidden_state(self, x):
@@ -217,10 +220,10 @@ class DenseGCM(torch.nn.Module):
                 if state.C - state.N < 1:
                     state = fused.grow_state(state, state.N + max(int(self.bptt_capacity), 1))
                     token = None
-                belief, token = ones.step_grad(plan, state, xc, token)
+                belief, token = ones.step_grad(plan, state, xc, token, ones.want_bf16(self, plan))
                 token._gcm_ones = True
             else:
-                belief = ones.step_nograd(plan, state, xc.detach())
+                belief = ones.step_nograd(plan, state, xc.detach(), ones.want_bf16(self, plan))
                 token = None
         elif recording:
             belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)

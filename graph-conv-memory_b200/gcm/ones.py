@@ -3,10 +3,16 @@
 On a state whose adjacency is the all-ones block over the valid nodes (built from empty by DenseEdge alone, or
 ingested from a caller tuple that has exactly that adjacency) the reference's step (gcm.py:262-321 with the
 DenseGraphConv stack of README.md:52-62) reduces to a per-graph running sum, two small projections and ONE
-streaming pass over a per-node cache R_i = W_root1 x_i; see the header of the .cu file for the algebra.  This
-module owns the host side: the extra state buffers, the autograd functions (one node per step, newest-first
-through the token chain of gcm.fused) and the hand-over to the general kernels when a configuration leaves
-the path.  CUDA only; every product is a kernel behind the C ABI.
+streaming pass over a per-node cache (a function of R_i = W_root1 x_i); see the header of the .cu file for the
+algebra.  This module owns the host side: the extra state buffers, the per-step buffers of a BPTT window, the
+autograd functions and the hand-over to the general kernels when a configuration leaves the path.  CUDA only;
+every product is a kernel behind the C ABI.
+
+Autograd: GCM has no recurrence through the belief (the hidden state is the observation log), so once
+`backward()` runs, dL/dbelief of every step is known independently of the other steps.  A step's backward node
+therefore only does [B, H]-sized work (dG, dc, and dL/dx_k when the observation requires grad); the pass over the
+per-node cache and every weight gradient are done ONCE per window by the chain's root node, which autograd runs
+last (every step depends on it through the token chain of gcm.fused).
 """
 from __future__ import annotations
 
@@ -42,10 +48,36 @@ def _outer(a, x, dw, db=None):
                 "gcm_outer_reduce")
 
 
+_WS = {}
+
+
+def _outer_tc(a, x, dw, db=None):
+    """dw += a.T @ x, db += a.sum(0) on the bf16 tensor-core path (gcm_outer_reduce_tc; deterministic)."""
+    lib = _cabi.lib()
+    rows = a.shape[0]
+    need = int(lib.gcm_outer_reduce_tc_workspace(rows))
+    ws = _WS.get(a.device)
+    if ws is None or ws.numel() < need:
+        ws = _WS[a.device] = torch.empty(need, device=a.device, dtype=torch.float32)
+    _cabi.check(lib.gcm_outer_reduce_tc(a.data_ptr(), a.stride(0), a.shape[1], x.data_ptr(), x.stride(0), x.shape[1],
+                                        rows, ws.data_ptr(), dw.data_ptr(), None if db is None else db.data_ptr(),
+                                        _cabi.stream_ptr(a.device)), "gcm_outer_reduce_tc")
+
+
 def plan_supports(plan) -> bool:
     g = plan.gnn
     return (bool(plan.sels) and all(s.kind == _cabi.SEL_DENSE for s in plan.sels)
-            and max(g.F, g.H1, g.H2) <= 128 and g.F % 4 == 0)
+            and max(g.F, g.H1, g.H2) <= 128 and g.F % 4 == 0 and g.H1 % 4 == 0)
+
+
+def want_bf16(mod, plan) -> bool:
+    """bfloat16 per-node cache (BASELINE cfg3's precision: beliefs / gradients within 2e-2 instead of 1e-5):
+    `DenseGCM.compute_dtype = torch.bfloat16`, or a surrounding torch.autocast("cuda", dtype=torch.bfloat16)."""
+    if plan.gnn.H1 % 8:
+        return False
+    if getattr(mod, "compute_dtype", None) == torch.bfloat16:
+        return True
+    return torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
 
 
 def _weights(plan, dev):
@@ -53,13 +85,14 @@ def _weights(plan, dev):
     return plan.gnn._packed[1]
 
 
-def _root_key(plan):
-    w = plan.gnn.conv1.lin_root._parameters["weight"]
-    return (w.data_ptr(), w._version)
+def _cache_act(plan) -> int:
+    """epilogue that turns c / R into what the cache passes read: exp(2 clamp(.)) for tanh, identity otherwise"""
+    return _cabi.ACT_EXP2X if plan.gnn.act1 == "tanh" else 0
 
 
-def prepare(plan, state) -> None:
-    """Bring the extra buffers of the path up to date: S from the log, R for every row under the current W_root1."""
+def prepare(plan, state, bf16: bool = False) -> None:
+    """Bring the extra buffers of the path up to date: S from the log, the cache of every row under the current
+    W_root1 (and activation / element type)."""
     dev = state.device
     w = _weights(plan, dev)
     lib = _cabi.lib()
@@ -67,155 +100,259 @@ def prepare(plan, state) -> None:
         state.xsum = torch.empty(state.B, state.F, device=dev, dtype=torch.float32)
         _cabi.check(lib.gcm_dense_ones_xsum(state.c_ref(), state.xsum.data_ptr(), _cabi.stream_ptr(dev)),
                     "gcm_dense_ones_xsum")
-    key = _root_key(plan)
+    wr = plan.gnn.conv1.lin_root._parameters["weight"]
+    key = (wr.data_ptr(), wr._version, plan.gnn.act1, bool(bf16))
     if state.rcache is None or state.rc_key != key:
-        if state.rcache is None:
-            state.rcache = torch.empty(state.B, state.C, plan.gnn.H1, device=dev, dtype=torch.float32)
-        _lin2(state.nodes.view(state.B * state.C, state.F), w["w_root1"],
-              out=state.rcache.view(state.B * state.C, plan.gnn.H1))
+        H1 = plan.gnn.H1
+        rows = state.B * state.C
+        if bf16 and state.F % 16 == 0 and H1 % 16 == 0:
+            # bf16 tensor cores (tcgen05): the rounding of R_i is independent per node, like the cache's own
+            state.rcache = torch.empty(state.B, state.C, H1, device=dev, dtype=torch.bfloat16)
+            _cabi.check(lib.gcm_linear_tc(state.nodes.data_ptr(), state.F, state.F, w["w_root1"].data_ptr(), None,
+                                          _cache_act(plan), rows, H1, state.rcache.data_ptr(), H1, 1,
+                                          _cabi.stream_ptr(dev)), "gcm_linear_tc")
+        else:
+            full = _lin2(state.nodes.view(rows, state.F), w["w_root1"], act=_cache_act(plan))
+            if bf16:
+                state.rcache = torch.empty(state.B, state.C, H1, device=dev, dtype=torch.bfloat16)
+                _cabi.check(lib.gcm_to_bf16(full.data_ptr(), state.rcache.data_ptr(), rows * H1,
+                                            _cabi.stream_ptr(dev)), "gcm_to_bf16")
+            else:
+                state.rcache = full.view(state.B, state.C, H1)
         state.rc_key = key
+        state.rc_bf16 = bool(bf16)
+        state.ones_tmp = None
 
 
-def _forward_kernels(plan, state, x):
-    """One step on the in-place state.  Returns (belief, c, G, h_t)."""
+class _Window:
+    """Per-step buffers of one BPTT window, [K, B, .] float32 each, so that the window-level kernels address
+    step k at a fixed stride.  Forward: S_k, E_k (= exp(2 c_k) or c_k), G_k, P_k, h_t,k.  Backward: dL/dbelief
+    through act2 (do), dG, the own-node term (dzo), dc and - when observations require grad - its suffix sums."""
+
+    FWD = (("S", "F"), ("E", "H1"), ("G", "H1"), ("P", "H1"), ("ht", "H1"))
+    BWD = (("do", "H2"), ("dG", "H1"), ("dzo", "H1"), ("dc", "H1"))
+
+    def __init__(self, state, g):
+        self.B, self.dev = state.B, state.device
+        self.dims = {"F": g.F, "H1": g.H1, "H2": g.H2}
+        self.K = 0
+        self.Kb = 0
+        self.chain_id = 0
+        self.chain_start = 0
+        self.kmax = -1          # newest-first backward: steps kmax .. k have delivered gradients so far
+        self.need_dx = False
+        self.dcs = None
+
+    def _alloc(self, K, h):
+        return torch.empty(K, self.B, self.dims[h], device=self.dev, dtype=torch.float32)
+
+    def ensure_fwd(self, k, cap):
+        if k < self.K:
+            return
+        K = min(cap, max(16, 2 * self.K, k + 1))
+        for name, h in self.FWD:
+            new = self._alloc(K, h)
+            if self.K:
+                new[: self.K].copy_(getattr(self, name))
+            setattr(self, name, new)
+        self.K = K
+
+    def ensure_bwd(self):
+        if self.Kb < self.K:
+            for name, h in self.BWD:
+                setattr(self, name, self._alloc(self.K, h))
+            self.dcs = None
+            self.Kb = self.K
+        if self.need_dx and self.dcs is None:
+            self.dcs = self._alloc(self.K, "H1")
+
+
+def _tmp(state, g):
+    t = getattr(state, "ones_tmp", None)
+    if t is None:
+        mk = lambda h: torch.empty(state.B, h, device=state.device, dtype=torch.float32)
+        t = state.ones_tmp = {"E": mk(g.H1), "q": mk(g.H1), "G": mk(g.H1), "ht": mk(g.H1), "S": mk(g.F)}
+    return t
+
+
+def _forward_kernels(plan, state, x, k: Optional[int] = None):
+    """One step on the in-place state; k = index of the step in the recording window (None: not recording)."""
     dev = state.device
     lib = _cabi.lib()
     g = plan.gnn
     w = _weights(plan, dev)
     stream = _cabi.stream_ptr(dev)
-    _cabi.check(lib.gcm_dense_ones_update(state.c_ref(), x.data_ptr(), state.xsum.data_ptr(), stream),
+    tmp = _tmp(state, g)
+    win = state.win if k is not None else None
+    if win is not None:
+        S, E, G, P, ht = win.S[k], win.E[k], win.G[k], win.P[k], win.ht[k]
+    else:
+        S, E, G, P, ht = tmp["S"], tmp["E"], tmp["G"], None, tmp["ht"]
+    _cabi.check(lib.gcm_dense_ones_update(state.c_ref(), x.data_ptr(), state.xsum.data_ptr(), S.data_ptr(), stream),
                 "gcm_dense_ones_update")
-    c = _lin2(state.xsum, w["w_rel1"], bias=w["b1"])
-    r_t = _lin2(x, w["w_root1"])
-    G = torch.empty(state.B, g.H1, device=dev, dtype=torch.float32)
-    h_t = torch.empty(state.B, g.H1, device=dev, dtype=torch.float32)
-    _cabi.check(lib.gcm_dense_ones_stream_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], state.rcache.data_ptr(),
-                                              c.data_ptr(), r_t.data_ptr(), G.data_ptr(), h_t.data_ptr(), stream),
-                "gcm_dense_ones_stream_fwd")
-    belief = _lin2(G, w["w_rel2"], h_t, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
+    state.xsum = S
+    ca = _cache_act(plan)
+    _lin2(S, w["w_rel1"], bias=w["b1"], act=ca, out=E)
+    _lin2(x, w["w_root1"], act=ca, out=tmp["q"])
+    _cabi.check(lib.gcm_dense_ones_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
+                                       state.rcache.data_ptr(), E.data_ptr(), tmp["q"].data_ptr(), G.data_ptr(),
+                                       None if P is None else P.data_ptr(), ht.data_ptr(), stream),
+                "gcm_dense_ones_fwd")
+    belief = _lin2(G, w["w_rel2"], ht, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
     state.masks_stale = True
     state.version += 1
     state.steps += 1
     state.max_count += 1
     if state.host_count is not None:
         state.host_count += 1
-    return belief, c, G, h_t
+    return belief
 
 
-def step_nograd(plan, state, x):
-    prepare(plan, state)
-    return _forward_kernels(plan, state, x)[0]
+def step_nograd(plan, state, x, bf16: bool = False):
+    prepare(plan, state, bf16)
+    return _forward_kernels(plan, state, x)
+
+
+def _param_grads(g, grads):
+    """gradients in the order of GnnPlan.params()"""
+    out = []
+    for conv, wr, wo, bb in ((g.conv1, "w_rel1", "w_root1", "b1"), (g.conv2, "w_rel2", "w_root2", "b2")):
+        out.append(grads[wr])
+        if conv.lin_rel.bias is not None:
+            out.append(grads[bb])
+        out.append(grads[wo])
+        if conv.lin_root.bias is not None:
+            out.append(grads[bb])
+    return out
 
 
 class _OnesRootFn(torch.autograd.Function):
-    """Start of a recorded chain on the ones path.  Runs LAST in backward: the products of the accumulated
-    per-node dL/d(pre-activation) with the node rows are linear, so they are applied here once per chain:
-    dW_root1 = sum_{b,i} DZ_i x_i^T."""
+    """Start of a recorded chain on the ones path.  Runs LAST in backward, when every step of the window has
+    delivered dG_k / dzo_k / dc_k: ONE pass over the per-node cache gives DZ for all nodes
+    (gcm_dense_ones_window_bwd), and each weight gradient is one reduction over the window's buffers."""
 
     @staticmethod
-    def forward(ctx, anchor, w_root1, state):
-        ctx.state = state
+    def forward(ctx, anchor, plan, state, chain_id, *params):
+        ctx.plan, ctx.state, ctx.chain_id = plan, state, chain_id
+        ctx.pkey = plan.gnn.current_key(state.device)
         return anchor.clone()
 
     @staticmethod
     def backward(ctx, d_token):
-        st = ctx.state
-        dw = None
-        if st.DZ is not None:
-            H1 = st.DZ.shape[-1]
-            dw = torch.zeros(H1, st.F, device=st.device, dtype=torch.float32)
-            _outer(st.DZ.view(st.B * st.C, H1), st.nodes.view(st.B * st.C, st.F), dw)
-            st.DZ.zero_()
-            st.ds_run.zero_()
-            st.ds_snap.clear()
-        return torch.zeros_like(d_token), dw, None
+        plan, st = ctx.plan, ctx.state
+        g, win, dev = plan.gnn, st.win, st.device
+        if g.current_key(dev) != ctx.pkey:
+            raise RuntimeError("GNN parameters were modified in place between forward and backward")
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        Kc = win.kmax + 1
+        win.kmax = -1
+        grads = {
+            "w_rel1": torch.zeros(g.H1, g.F, device=dev), "w_root1": torch.zeros(g.H1, g.F, device=dev),
+            "b1": torch.zeros(g.H1, device=dev),
+            "w_rel2": torch.zeros(g.H2, g.H1, device=dev), "w_root2": torch.zeros(g.H2, g.H1, device=dev),
+            "b2": torch.zeros(g.H2, device=dev),
+        }
+        if Kc > 0:
+            steps_total = st.steps - win.chain_start
+            if steps_total > st.C - st.N + 1:
+                raise RuntimeError(
+                    f"BPTT window too long for the node log: {steps_total} steps since the chain started but the log "
+                    f"keeps {st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
+            if st.DZ is None:
+                st.DZ = torch.empty(st.B, st.C, g.H1, device=dev, dtype=torch.float32)
+            _cabi.check(_cabi.lib().gcm_dense_ones_window_bwd(
+                st.c_ref(), g.H1, _cabi.ACT[g.act1], int(st.rc_bf16), st.rcache.data_ptr(), steps_total, Kc,
+                win.E.data_ptr(), win.dG.data_ptr(), win.dzo.data_ptr(), st.B * g.H1, st.DZ.data_ptr(),
+                _cabi.stream_ptr(dev)), "gcm_dense_ones_window_bwd")
+            # weight gradients: reductions over (graph, node) and (step, graph) rows; on the bf16 path the products
+            # run on the tensor cores (independent rounding per row, fp32 accumulation)
+            tc_ok = st.rc_bf16 and g.F % 16 == 0 and g.H1 % 16 == 0
+            outer = _outer_tc if tc_ok else _outer
+            outer(st.DZ.view(st.B * st.C, g.H1), st.nodes.view(st.B * st.C, st.F), grads["w_root1"])
+            rows = Kc * st.B
+            do = win.do[:Kc].view(rows, g.H2)
+            outer(do, win.G[:Kc].view(rows, g.H1), grads["w_rel2"], grads["b2"])
+            outer(do, win.ht[:Kc].view(rows, g.H1), grads["w_root2"])
+            outer(win.dc[:Kc].view(rows, g.H1), win.S[:Kc].view(rows, g.F), grads["w_rel1"], grads["b1"])
+        return (torch.zeros_like(d_token), None, None, None, *_param_grads(g, grads))
 
 
 class _OnesStepFn(torch.autograd.Function):
-    """One step of the ones path.  Saved: S, c, G, h_t and the belief of the step ([B, F|H] each); the per-node
-    work of the backward is recomputed from the R cache."""
+    """One step of the ones path.  Saved: the belief ([B, H2]) and the step's index in the window buffers."""
 
     @staticmethod
-    def forward(ctx, x, token, plan, state, *params):
-        belief, c, G, h_t = _forward_kernels(plan, state, x.detach())
-        ctx.plan, ctx.state = plan, state
-        ctx.step_index = state.steps
-        ctx.pkey = plan.gnn._key
-        ctx.packed = plan.gnn._packed
-        ctx.save_for_backward(state.xsum.clone(), c, G, h_t, belief)
+    def forward(ctx, x, token, plan, state, k):
+        belief = _forward_kernels(plan, state, x.detach(), k)
+        ctx.plan, ctx.state, ctx.k = plan, state, k
+        ctx.chain_id = state.win.chain_id
+        ctx.save_for_backward(belief)
         return belief, torch.zeros(1, device=state.device)
 
     @staticmethod
     def backward(ctx, d_belief, d_token):
-        plan, st = ctx.plan, ctx.state
-        g = plan.gnn
-        dev = st.device
-        if g.current_key(dev) != ctx.pkey:
-            raise RuntimeError("GNN parameters were modified in place between forward and backward")
-        S, c, G, h_t, belief = ctx.saved_tensors
-        w = ctx.packed[1]
-        steps_back = st.steps - ctx.step_index
-        if steps_back > st.C - st.N:
-            raise RuntimeError(
-                f"BPTT window too long for the node log: this step is {steps_back} steps old but the log "
-                f"keeps {st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
-        if st.DZ is None:
-            st.DZ = torch.zeros(st.B, st.C, g.H1, device=dev, dtype=torch.float32)
-            st.ds_run = torch.zeros(st.B, st.F, device=dev, dtype=torch.float32)
-        tw = plan.gnn.transposed(dev)
+        plan, st, k = ctx.plan, ctx.state, ctx.k
+        g, win, dev = plan.gnn, st.win, st.device
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        (belief,) = ctx.saved_tensors
+        lib = _cabi.lib()
+        stream = _cabi.stream_ptr(dev)
+        tw = g.transposed(dev)
+        win.ensure_bwd()
+        n = st.B * g.H1
         db_ = d_belief.contiguous().float()
-        if g.act2 == "tanh":
-            do = db_ * (1.0 - belief * belief)
-        elif g.act2 == "relu":
-            do = db_ * (belief > 0).to(db_.dtype)
-        else:
-            do = db_
-        grads = {
-            "w_rel1": torch.zeros(g.H1, g.F, device=dev), "b1": torch.zeros(g.H1, device=dev),
-            "w_rel2": torch.zeros(g.H2, g.H1, device=dev), "w_root2": torch.zeros(g.H2, g.H1, device=dev),
-            "b2": torch.zeros(g.H2, device=dev),
-        }
-        _outer(do, G, grads["w_rel2"], grads["b2"])
-        _outer(do, h_t, grads["w_root2"])
-        dG = _lin2(do, tw["w_rel2_t"])                       # [B, H1] = do W_rel2
-        dh_t = _lin2(do, tw["w_root2_t"])
-        dc = torch.empty(st.B, g.H1, device=dev, dtype=torch.float32)
-        dz_t = torch.empty(st.B, g.H1, device=dev, dtype=torch.float32)
-        _cabi.check(_cabi.lib().gcm_dense_ones_stream_bwd(
-            st.c_ref(), steps_back, g.H1, _cabi.ACT[g.act1], st.rcache.data_ptr(), c.data_ptr(), dG.data_ptr(),
-            dh_t.data_ptr(), st.DZ.data_ptr(), dc.data_ptr(), dz_t.data_ptr(), _cabi.stream_ptr(dev)),
-            "gcm_dense_ones_stream_bwd")
-        _outer(dc, S, grads["w_rel1"], grads["b1"])
-        # dL/dS of this step reaches every node of its window: running sum over the later steps
-        _lin2(dc, tw["w_rel1_t"], out=st.ds_run, accumulate=True)
-        if st.max_count > st.N:
-            st.ds_snap[ctx.step_index] = st.ds_run.clone()
-        d_x = st.ds_run.clone()
-        gone = st.ds_snap.get(ctx.step_index + st.N)          # steps after this node left the window
-        if gone is not None:
-            d_x -= gone
-        _lin2(dz_t, tw["w_root1_t"], out=d_x, accumulate=True)
-        out = []
-        for conv, wr, wo, bb in ((g.conv1, "w_rel1", None, "b1"), (g.conv2, "w_rel2", "w_root2", "b2")):
-            out.append(grads[wr])
-            if conv.lin_rel.bias is not None:
-                out.append(grads[bb])
-            out.append(None if wo is None else grads[wo])     # dW_root1 is applied once, by _OnesRootFn
-            if conv.lin_root.bias is not None:
-                out.append(grads[bb])
-        return (d_x, torch.zeros(1, device=dev), None, None, *out)
+        _cabi.check(lib.gcm_act_backward(db_.data_ptr(), belief.data_ptr(), _cabi.ACT[g.act2], st.B * g.H2,
+                                         win.do[k].data_ptr(), stream), "gcm_act_backward")
+        _lin2(win.do[k], tw["w_rel2_t"], out=win.dG[k])                     # dL/dG = do W_rel2
+        _lin2(win.do[k], tw["w_root2_t"], out=win.dzo[k])                   # dL/dh_t through lin_root2
+        have_next = win.need_dx and k < win.kmax
+        _cabi.check(lib.gcm_dense_ones_dc(
+            win.dG[k].data_ptr(), win.dzo[k].data_ptr(), win.P[k].data_ptr(), win.ht[k].data_ptr(), _cabi.ACT[g.act1], n,
+            win.dc[k].data_ptr(), win.dcs[k + 1].data_ptr() if have_next else None,
+            win.dcs[k].data_ptr() if win.need_dx else None, stream), "gcm_dense_ones_dc")
+        win.kmax = max(win.kmax, k)
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            Kc = win.kmax + 1
+            steps_total = st.steps - win.chain_start
+            if steps_total > st.C - st.N + 1:
+                raise RuntimeError(
+                    f"BPTT window too long for the node log: {steps_total} steps since the chain started but the log "
+                    f"keeps {st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
+            dz = torch.empty(st.B, g.H1, device=dev, dtype=torch.float32)
+            _cabi.check(lib.gcm_dense_ones_node_bwd(
+                st.c_ref(), g.H1, _cabi.ACT[g.act1], int(st.rc_bf16), st.rcache.data_ptr(), steps_total, Kc, k,
+                win.E.data_ptr(), win.dG.data_ptr(), win.dzo.data_ptr(), st.B * g.H1, dz.data_ptr(), stream),
+                "gcm_dense_ones_node_bwd")
+            # dL/dS of a step reaches every node of its window: steps k .. k+N-1 saw node k
+            ds = win.dcs[k]
+            if k + st.N < Kc:
+                ds = ds - win.dcs[k + st.N]
+            d_x = _lin2(dz, tw["w_root1_t"], ds, tw["w_rel1_t"])
+        return d_x, torch.zeros(1, device=dev), None, None, None
 
 
-def step_grad(plan, state, x, token):
+def step_grad(plan, state, x, token, bf16: bool = False):
     """Recording step.  Returns (belief, token)."""
-    prepare(plan, state)
+    prepare(plan, state, bf16)
+    win = getattr(state, "win", None)
+    if win is None:
+        win = state.win = _Window(state, plan.gnn)
+    cap = state.C - state.N + 1
     if token is None:
+        win.chain_id += 1
+        win.chain_start = state.steps
+        win.kmax = -1
+        win.need_dx = False
         anchor = torch.zeros(1, device=state.device, requires_grad=True)
-        token = _OnesRootFn.apply(anchor, plan.gnn.conv1.lin_root.weight, state)
-        state.chain_start = state.steps
-    elif state.steps + 1 - getattr(state, "chain_start", 0) > state.C - state.N + 1:
+        token = _OnesRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
+    k = state.steps - win.chain_start
+    if k + 1 > cap:
         raise RuntimeError(
-            f"more than {state.C - state.N + 1} recorded steps on one hidden state; raise "
+            f"more than {cap} recorded steps on one hidden state; raise "
             "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
-    belief, token = _OnesStepFn.apply(x, token, plan, state, *plan.gnn.params())
+    win.ensure_fwd(k, cap)
+    win.need_dx = win.need_dx or x.requires_grad
+    belief, token = _OnesStepFn.apply(x, token, plan, state, k)
     return belief, token

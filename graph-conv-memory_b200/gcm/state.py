@@ -50,11 +50,12 @@ class DenseState:
         self.masks_stale = False    # steps were taken on the ones path: the bit masks must be rebuilt before use
         self.max_count = 0          # host-side upper bound of count[b]
         self.xsum: Optional[torch.Tensor] = None      # [B, F] sum of the window's rows
-        self.rcache: Optional[torch.Tensor] = None    # [B, C, H1] W_root1 x_i per node
-        self.rc_key = None
-        self.DZ: Optional[torch.Tensor] = None        # [B, C, H1] accumulated dL/d(pre-activation) (training)
-        self.ds_run: Optional[torch.Tensor] = None    # [B, F] running dL/dS over the later steps
-        self.ds_snap = {}
+        self.rcache: Optional[torch.Tensor] = None    # [B, C, H1] per-node cache: exp(2 W_root1 x_i) (tanh) or W_root1 x_i
+        self.rc_key = None          # (W_root1 identity/version, act1, element type) the cache was filled under
+        self.rc_bf16 = False        # cache element type: float32 or bfloat16
+        self.DZ: Optional[torch.Tensor] = None        # [B, C, H1] dL/d(pre-activation) per node of a BPTT window
+        self.win = None             # gcm.ones._Window: per-step buffers of the BPTT window being recorded
+        self.ones_tmp = None        # per-step scratch of non-recording steps
         # single distance selector (gcm.fused.zc_step): per-node pre-activation cache
         self.zc_ok = True           # every step so far went through the zc kernel (an empty state qualifies)
         self.zcache: Optional[torch.Tensor] = None    # [B, C, H1]

@@ -200,14 +200,15 @@ int gcm_select_dense(const float* nodes, float* adj, const int64_t* num_nodes, i
  * the valid nodes, so the 2-layer stack of gcm.py:308 reduces to
  *   c = W_rel1 S + b1 (S = sum of the window's rows),  h_i = act1(c + W_root1 x_i),
  *   belief = act2(W_rel2 sum_i h_i + b2 + W_root2 h_t).
- * The caller keeps, next to the node log: xsum [B,F] (= S), rcache [B,C,H1] (R_i = W_root1 x_i, slot = position
- * % C) and, while training, DZ [B,C,H1] (accumulated dL/d(pre-activation) per node).  The adjacency bit masks
+ * The caller keeps, next to the node log: xsum [B,F] (= S), the per-node cache [B,C,H1] (a function of R_i =
+ * W_root1 x_i, see below) and, while training, per-step [K,B,.] buffers of the BPTT window.  The adjacency bit masks
  * are NOT maintained on this path; gcm_dense_fill_masks writes them when they are needed.
  * GCM_FLAG_NOTDENSE is set by gcm_state_ingest when the valid block of a caller-supplied adjacency is not all
  * ones; status[1] receives max(num_nodes) (status must then have two words). */
 #define GCM_FLAG_NOTDENSE 32u
-/* node write (gcm.py:274) + overflow eviction (gcm.py:323-355) + S update + num_nodes + 1 */
-int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, float* xsum, void* stream);
+/* node write (gcm.py:274) + overflow eviction (gcm.py:323-355) + S update + num_nodes + 1.  xsum_in = S before the
+ * step, xsum = S after it (may alias; a recording caller keeps one S per step of the BPTT window). */
+int gcm_dense_ones_update(const gcm_dense_state* st, const float* obs, const float* xsum_in, float* xsum, void* stream);
 /* S recomputed from the log */
 int gcm_dense_ones_xsum(const gcm_dense_state* st, float* xsum, void* stream);
 /* out[r,:Ho] = act(A1[r,:K1] W1^T + A2[r,:K2] W2^T + bias); W row-major [Ho,K] (torch.nn.Linear.weight); A2/W2 and
@@ -219,15 +220,52 @@ int gcm_linear2(const float* A1, int K1, long long lda1, const float* W1, const 
 /* dW[o,i] += sum_r A[r,o] X[r,i];  db[o] += sum_r A[r,o] (db may be NULL).  Ho, Hi <= 128.  (weight gradients) */
 int gcm_outer_reduce(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
                      float* dW, float* db, void* stream);
-/* After gcm_dense_ones_update: stores r_t as the new node's cache row, G = sum_i act1(c + R_i) over the window,
- * h_t = act1(c + r_t).  c, r_t, G, h_t: [B,H1]. */
-int gcm_dense_ones_stream_fwd(const gcm_dense_state* st, int H1, int act1, float* rcache, const float* c,
-                              const float* r_t, float* G, float* h_t, void* stream);
-/* Backward of the step taken `steps_back` steps ago: DZ_i += (dG + [i==t] dh_t) * act1'(h_i) over that step's
- * window, dc = sum_i of the same, dz_t = the (now final) DZ row of that step's own node. */
-int gcm_dense_ones_stream_bwd(const gcm_dense_state* st, int steps_back, int H1, int act1, float* rcache,
-                              const float* c, const float* dG, const float* dh_t, float* DZ, float* dc, float* dz_t,
-                              void* stream);
+/* The per-node cache [B,C,H1] (slot = position % C).  Element type float32 or bfloat16; content for act1 = tanh:
+ * Q_i = exp(2 clamp(R_i, +-40)), so that tanh(c + R_i) = 1 - 2 / (E Q_i + 1) with E = exp(2 clamp(c, +-40)) costs one
+ * MUFU; for relu / none: R_i itself.  gcm_linear2 with act = GCM_ACT_EXP2X writes E and Q.  H1 <= 128, H1 % 4 == 0
+ * (bfloat16: H1 % 8 == 0). */
+#define GCM_CACHE_F32 0
+#define GCM_CACHE_BF16 1
+#define GCM_ACT_EXP2X 3
+/* After gcm_dense_ones_update: stores q_t (this step's node: Q or R, [B,H1] f32) as the new cache row, then
+ * G = sum_i act1(c + R_i) over the window, h_t = act1(c + r_t) and, if P != NULL, P = sum_i act1'(c + R_i).
+ * e_c [B,H1] = E (tanh) or c.  G, P, h_t: [B,H1] f32. */
+int gcm_dense_ones_fwd(const gcm_dense_state* st, int H1, int act1, int cache_type, void* cache, const float* e_c,
+                       const float* q_t, float* G, float* P, float* h_t, void* stream);
+/* Backward of a whole BPTT window (the autograd of gcm.py:308 for every step of the chain at once; GCM has no
+ * recurrence through the belief, so the steps' dL/dbelief are all known before any per-node work starts):
+ * DZ[b, slot(p), :] = sum over chain steps k < steps_used that had node p in their window of
+ * dG_k * act1'(c_k + R_p), plus dzo_k for the node written by step k; zero for every other slot.
+ * steps_total = steps applied to the state since the chain started (count0 = count - steps_total), wE / wdG / wdzo:
+ * [K, B, H1] f32 with `step_stride` floats between steps (E_k or c_k; dL/dG_k; own-node term times act1'(h_t)). */
+int gcm_dense_ones_window_bwd(const gcm_dense_state* st, int H1, int act1, int cache_type, const void* cache,
+                              int steps_total, int steps_used, const float* wE, const float* wdG, const float* wdzo,
+                              long long step_stride, float* DZ, void* stream);
+/* The DZ row of the node written by chain step k alone (dz [B,H1]): what dL/dx_k needs when observations require
+ * grad; valid once steps k .. steps_used-1 have delivered dG / dzo. */
+int gcm_dense_ones_node_bwd(const gcm_dense_state* st, int H1, int act1, int cache_type, const void* cache,
+                            int steps_total, int steps_used, int k, const float* wE, const float* wdG, const float* wdzo,
+                            long long step_stride, float* dz, void* stream);
+/* res = d_out * act'(out) elementwise (act' expressed through the activation's output) */
+int gcm_act_backward(const float* d_out, const float* out, int act, long long n, float* res, void* stream);
+/* per-step pieces of the backward, elementwise over n = B*H1: dht <- dzo = dht * act1'(h_t); dc = dG * P + dzo;
+ * dcs = dc + dcs_next (suffix sum over the later steps; dcs / dcs_next may be NULL) */
+int gcm_dense_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1, long long n, float* dc,
+                      const float* dcs_next, float* dcs, void* stream);
+/* float32 -> bfloat16 (cache refill) */
+int gcm_to_bf16(const float* in, void* out, long long n, void* stream);
+/* bf16 tensor-core (tcgen05) variants for callers that asked for bfloat16 compute (csrc/gcm_tc_gemm.cu); operands are
+ * rounded to bfloat16, accumulation is float32.
+ * gcm_linear_tc: out[r,:Ho] = epi(X[r,:K] W^T + bias), epi = none or GCM_ACT_EXP2X; out float32 or bfloat16 (out_bf16);
+ * K, Ho multiples of 16 in [16,128]; ldx % 4 == 0; ldo % 4 == 0 (bfloat16: % 8).  (lin_root of DenseGraphConv over the
+ * node log: the per-node cache fill.)
+ * gcm_outer_reduce_tc: as gcm_outer_reduce (dW += A^T X, db += column sums of A), deterministic; Hi a multiple of 16;
+ * workspace: gcm_outer_reduce_tc_workspace(rows) floats of device memory. */
+int gcm_linear_tc(const float* X, int K, long long ldx, const float* W, const float* bias, int act, long long rows,
+                  int Ho, void* out, long long ldo, int out_bf16, void* stream);
+long long gcm_outer_reduce_tc_workspace(long long rows);
+int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
+                        float* workspace, float* dW, float* db, void* stream);
 /* writes the bit masks of the all-ones valid block (every node of the window linked to every node, self loops) */
 int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream);
 

@@ -191,7 +191,7 @@ def test_ones_path_bptt_from_prefilled_dense_state(T, n0):
     x = obs.to(dev).requires_grad_(True)
     hidden = (nodes0.to(dev), adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
     outs, hidden = _bptt(mod, convs, x, w.to(dev), hidden)
-    assert _cabi.lib().gcm_last_kernel().decode() in ("k_outer_reduce", "k_linear2", "k_ones_stream_bwd")
+    assert _cabi.lib().gcm_last_kernel().decode() in ("k_outer_reduce", "k_linear2", "k_ones_window_bwd")
     ref64, ref32 = res[torch.float64], res[torch.float32]
     assert rel_err(outs, ref64[0]) < TOL + rel_err(ref32[0], ref64[0])
     assert rel_err(x.grad, ref64[1]) < TOL + rel_err(ref32[1], ref64[1])
@@ -217,3 +217,50 @@ def test_ones_path_bptt_from_prefilled_dense_state(T, n0):
     got = named_grads(convs)
     for k in got:
         assert rel_err(got[k], pp[k].grad) < 5 * TOL, k
+
+
+@pytest.mark.parametrize("acts,bf16", [(("tanh", "tanh"), False), (("tanh", "tanh"), True), (("relu", "none"), False)])
+def test_ones_path_window_backward_wide(acts, bf16):
+    """The ones path at a width where every vector lane of its kernels is used (H1 = 64: 16 / 8 threads per cache
+    row), ragged pre-filled counts, a chain that wraps, observations with and without grad.  float32 cache:
+    1e-5 against the fp64 oracle; bfloat16 cache (`DenseGCM.compute_dtype = torch.bfloat16`, BASELINE cfg3's
+    precision): 2e-2."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T = 6, 40, 32, 64, 12
+    spec = [("dense",)]
+    gen = torch.Generator().manual_seed(5)
+    p = oracle.make_params(F, H)
+    nn0 = torch.tensor([33, 0, 40, 17, 39, 5])
+    nodes0 = 0.5 * torch.randn(B, N, F, generator=gen)
+    adj0 = torch.zeros(B, N, N)
+    for b in range(B):
+        nodes0[b, int(nn0[b]):] = 0
+        adj0[b, : int(nn0[b]), : int(nn0[b])] = 1
+    obs = 0.5 * torch.randn(T, B, F, generator=gen)
+    w = torch.randn(T, B, H, generator=gen)
+    o = obs.double().clone().requires_grad_(True)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    outs, _ = oracle.dense_gcm_rollout(o, (nodes0.double(), adj0.double(), torch.zeros(0, dtype=torch.float64), nn0.clone()),
+                                       spec, pp, acts, graph_size=N)
+    (outs * w.double()).sum().backward()
+    tol = 2e-2 if bf16 else 5 * TOL
+    for x_grad in (True, False):
+        gnn, convs = make_dense_gnn(F, H, p, acts)
+        mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+        mod.bptt_capacity = T
+        if bf16:
+            mod.compute_dtype = torch.bfloat16
+        x = obs.to(dev).requires_grad_(x_grad)
+        hidden = (nodes0.to(dev), adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
+        got_outs, hidden = _bptt(mod, convs, x, w.to(dev), hidden)
+        assert _cabi.lib().gcm_last_kernel().decode() in ("k_outer_reduce", "k_linear2", "k_ones_window_bwd")
+        assert hidden.claim().rc_bf16 == bf16 and mod._plan is not None
+        assert rel_err(got_outs, outs.detach()) < tol
+        if x_grad:
+            assert rel_err(x.grad, o.grad) < tol
+        got = named_grads(convs)
+        for k in got:
+            assert rel_err(got[k], pp[k].grad) < tol, (k, x_grad)

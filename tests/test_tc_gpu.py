@@ -27,3 +27,50 @@ def test_tc_block_3xtf32_is_fp32_accurate(K, N):
     assert out[1] < 2e-3                       # plain tf32: layouts / descriptors are right
     assert out[3] < 2e-6                       # 3xTF32: fp32-class accuracy
     assert out[4] < 2e-6                       # lo term on the bf16 path (packed A in TMEM): same class
+
+
+@pytest.mark.parametrize("rows,K,Ho,act,out_bf16", [(1000, 128, 128, 3, 1), (257, 32, 64, 0, 0), (128 * 300 + 5, 64, 128, 0, 1)])
+def test_linear_tc_matches_bf16_rounded_reference(rows, K, Ho, act, out_bf16):
+    """gcm_linear_tc (tcgen05 bf16 MMA, fp32 accumulate): against a float64 product of the bf16-rounded operands."""
+    from gcm import _cabi
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(rows)
+    X = (0.5 * torch.randn(rows, K, generator=g)).to(dev)
+    W = (torch.randn(Ho, K, generator=g) / K ** 0.5).to(dev)
+    bias = torch.randn(Ho, generator=g).to(dev)
+    out = torch.empty(rows, Ho, device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    _cabi.check(_cabi.lib().gcm_linear_tc(X.data_ptr(), K, K, W.data_ptr(), bias.data_ptr(), act, rows, Ho, out.data_ptr(),
+                                          Ho, out_bf16, _cabi.stream_ptr(dev)), "gcm_linear_tc")
+    ref = X.bfloat16().double() @ W.bfloat16().double().t() + bias.double()
+    if act == 3:
+        ref = torch.exp(2 * ref.clamp(-40, 40))
+    tol = 1e-2 if out_bf16 else 1e-5
+    assert float(((out.double() - ref).abs() / ref.abs().clamp(min=1.0)).max()) < tol
+
+
+@pytest.mark.parametrize("rows,Ho,Hi,bias", [(5000, 128, 128, True), (64 * 700 + 13, 48, 32, False), (100, 128, 64, True)])
+def test_outer_reduce_tc_matches_bf16_rounded_reference(rows, Ho, Hi, bias):
+    """gcm_outer_reduce_tc: dW += A^T X with bf16 operands (exact products, fp32 accumulation), db += column sums
+    of A in fp32; accumulates into its outputs; deterministic (two runs are bit-identical)."""
+    from gcm import _cabi
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(rows)
+    A = torch.randn(rows, Ho, generator=g).to(dev)
+    X = torch.randn(rows, Hi, generator=g).to(dev)
+    ws = torch.empty(int(lib.gcm_outer_reduce_tc_workspace(rows)), device=dev)
+    outs = []
+    for _ in range(2):
+        dW = torch.ones(Ho, Hi, device=dev)
+        db = torch.ones(Ho, device=dev)
+        _cabi.check(lib.gcm_outer_reduce_tc(A.data_ptr(), Ho, Ho, X.data_ptr(), Hi, Hi, rows, ws.data_ptr(), dW.data_ptr(),
+                                            db.data_ptr() if bias else None, _cabi.stream_ptr(dev)), "gcm_outer_reduce_tc")
+        outs.append((dW, db))
+    ref = 1 + A.bfloat16().double().t() @ X.bfloat16().double()
+    scale = float(ref.abs().max())
+    assert float((outs[0][0].double() - ref).abs().max()) < 2e-5 * scale
+    if bias:
+        assert float((outs[0][1].double() - (1 + A.double().sum(0))).abs().max()) < 1e-4 * max(1.0, rows ** 0.5)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
