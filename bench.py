@@ -174,9 +174,9 @@ def algorithmic(workload, B, N, F, H, extra=None):
         per = N * F * 4 + 2 * F * 4 + N // 8 * 2 + H * 4 + 16
         return "hbm", per * B, "bytes"
     if workload == "cfg3":
-        # SURVEY.md 8(d), all-ones structure exploited: 66.8 KB per graph-step forward (bf16 node rows at n = N),
-        # forward + backward = 3x.  (The backward here is one pass per WINDOW, so the kernels move less than this.)
-        return "hbm", B * (N * F * 2 + 2 * F * 4 + N // 8 + H * 4 + 16) * 3, "bytes"
+        # SURVEY.md 8(d), all-ones structure exploited: 66.8 KB per graph-step of the forward (bf16 per-node rows at
+        # n = N); k_ones_fwd is that pass.  The backward is one pass per window, not 2x this per step.
+        return "hbm", B * (N * F * 2 + 2 * F * 4 + N // 8 + H * 4 + 16), "bytes"
     if workload == "cfg5":
         n, E = extra
         per_layer = n * F * 4 + E * 8 + (n + 1) * 8 + n * H * 4
@@ -420,8 +420,17 @@ def main():
         window(obs_dev)
         torch.cuda.synchronize()
         launches = int(_cabi.lib().gcm_launch_count() - n_l0) * K
-        kern_ms = total_ms / (K * T)
-        kernel_name = "k_ones_fwd per step + k_ones_window_bwd per window (+ k_linear2, k_outer_reduce, k_ones_update)"
+        # dominant kernel: the forward pass over the per-node cache (one launch per step), timed alone on the state
+        # the last window left behind (t = N - 1: the longest stream of the window)
+        from gcm import ones as _ones
+        with torch.no_grad():
+            _, hid = mod(obs_dev[0], (nodes0, adj0, torch.zeros(0, device=dev), nn0))
+            for t in range(1, T):
+                _, hid = mod(obs_dev[t], hid)
+        kern_ms = _ones.time_fwd_kernel(mod.fused_plan(), hid.claim())
+        extra = {"window_ms": total_ms / K, "fwd_kernel_share_of_window": kern_ms * T / (total_ms / K)}
+        kernel_name = ("k_ones_fwd (1 launch per step; the backward is ONE k_ones_window_bwd per window, "
+                       "see DESIGN.md section 3)")
     else:  # sparse, all-at-once
         mod = build_sparse(dev, N, F, H)
         x = torch.randn(B, N, F, generator=gen)
@@ -485,7 +494,9 @@ def main():
         else:
             line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": "device-resident only for this auxiliary workload"}
-        if extra is not None:
+        if isinstance(extra, dict):
+            line["roofline"].update(extra)
+        elif extra is not None:
             line["config"]["flat_nodes"], line["config"]["edges"] = extra
         if world == 1 and not args.no_cpu_baseline:
             cb = {"cfg2": args.cpu_batch, "cfg5": 8}.get(args.workload, 64)

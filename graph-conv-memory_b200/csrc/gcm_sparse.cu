@@ -49,6 +49,8 @@ struct EdgeGenArgs {
   const int64_t* edge_off;  // pass 2: [n_new + 1] exclusive cumsum of deg
   int64_t* edges;           // pass 2: [3, E]
   int64_t E;
+  const int64_t* flat_off;  // pass 2, optional: [B+1] exclusive cumsum of T + tau (the flat node numbering)
+  int64_t* flat_col;        // pass 2, optional: [E] flat id of every edge's source = flat_off[b] + source
 };
 
 __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
         a.edges[e] = b;
         a.edges[a.E + e] = s;
         a.edges[2 * a.E + e] = k;
+        if (a.flat_col) a.flat_col[e] = a.flat_off[b] + k;
       }
       base += __popc(bal);
       count += __popc(bal);
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
           a.edges[e] = b;
           a.edges[a.E + e] = s;
           a.edges[2 * a.E + e] = w * 32 + bit;
+          if (a.flat_col) a.flat_col[e] = a.flat_off[b] + w * 32 + bit;
           ++e;
         }
       }
@@ -299,6 +303,68 @@ struct GraphConvFwdArgs {
   float* out;             // [m, Fout]
 };
 
+// One row of phase 1 for Fin = 32 V: lane owns V contiguous features (one coalesced warp load per neighbour row).
+template <int V>
+__device__ __forceinline__ void gc_load_vec(const float* p, float (&v)[V]) {
+  if (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+  } else if (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1 % V] = t.y;
+  } else {
+    v[0] = *p;
+  }
+}
+template <int V>
+__device__ __forceinline__ void gc_gather_row(const GraphConvFwdArgs& a, int64_t i, int64_t li, int64_t e0, int64_t e1,
+                                              int lane, float* dst) {
+  const int Fin = 32 * V;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+  const float* xl = a.x + lane * V;
+  for (int64_t base = e0; base < e1; base += 32) {
+    const int cnt = (int)min((int64_t)32, e1 - base);
+    const int64_t my = lane < cnt ? a.col[base + lane] : 0;
+    const float myw = (a.ew && lane < cnt) ? a.ew[base + lane] : 1.0f;
+    int u = 0;
+    for (; u + 8 <= cnt; u += 8) {
+      float v[8][V];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u + q) * Fin, v[q]);
+      if (a.ew) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float w = __shfl_sync(GCM_FULL_MASK, myw, u + q);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[q][j] *= w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += v[q][j];
+    }
+    for (; u < cnt; ++u) {
+      float v[V];
+      gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u) * Fin, v);
+      const float w = a.ew ? __shfl_sync(GCM_FULL_MASK, myw, u) : 1.0f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += a.ew ? v[j] * w : v[j];
+    }
+  }
+  float own[V];
+  gc_load_vec<V>(xl + i * Fin, own);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const int f = lane * V + j;
+    dst[f] = acc[j];
+    dst[Fin + f] = own[j];
+    if (a.agg_out) a.agg_out[li * Fin + f] = acc[j];
+  }
+}
+
 // thread tile: 4 rows x (Fout / 16) columns, Fout in {16, 32, 64, 128} handled via NT = Fout / 16
 template <int NT>
 __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwdArgs a) {
@@ -310,12 +376,22 @@ __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwd
   const int64_t row0 = (int64_t)blockIdx.x * GC_TM;
 
   // ---- phase 1: [sum of in-neighbours | own features] for every row of the tile ----
+  // warp per row.  Fin in {32, 64, 128}: a lane owns Fin / 32 contiguous features, so one neighbour row is ONE
+  // coalesced 128 / 256 / 512-byte warp load; the column indices of up to 32 edges are fetched with one coalesced
+  // load and broadcast with shuffles; 8 gathers in flight; the sum runs in edge order (same order as a scalar loop).
+  const int V = (Fin == 32 || Fin == 64 || Fin == 128) ? Fin / 32 : 0;
   for (int r = warp; r < GC_TM; r += GC_THREADS / 32) {
     const int64_t li = row0 + r;
     float* dst = As + r * (K + 1);
     if (li < a.m) {
       const int64_t i = a.rows ? a.rows[li] : li;
       const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
+      if (V) {
+        if (V == 2) gc_gather_row<2>(a, i, li, e0, e1, lane, dst);
+        else if (V == 4) gc_gather_row<4>(a, i, li, e0, e1, lane, dst);
+        else gc_gather_row<1>(a, i, li, e0, e1, lane, dst);
+        continue;
+      }
       for (int f0 = 0; f0 < Fin; f0 += 32) {
         const int f = f0 + lane;
         float acc = 0.0f;
@@ -527,11 +603,12 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
                                       const int64_t* new_off, int B, int N, int F, int tmax, const int32_t* hops,
                                       int n_hops, int use_radius, int pos_start, int pos_step, int pos_len,
                                       float radius, int32_t* deg, const int64_t* edge_off, int64_t* edges,
-                                      int64_t E, void* stream) {
+                                      int64_t E, const int64_t* flat_off, int64_t* flat_col, void* stream) {
   GCM_REQUIRE(T && taus && new_off && B >= 0 && N >= 1 && F >= 1, "sparse_build_edges: bad arguments");
   GCM_REQUIRE(n_hops >= 0 && n_hops <= GCM_MAX_HOPS && (n_hops == 0 || hops), "sparse_build_edges: n_hops=%d", n_hops);
   GCM_REQUIRE((edges == nullptr) == (edge_off == nullptr), "sparse_build_edges: edges and edge_off go together");
   GCM_REQUIRE(edges || deg, "sparse_build_edges: pass 1 needs deg");
+  GCM_REQUIRE(!flat_col || (edges && flat_off), "sparse_build_edges: flat_col needs edges and flat_off");
   if (use_radius) {
     GCM_REQUIRE(nodes && pos_len >= 1 && pos_step >= 1 && pos_start >= 0 && pos_start + (pos_len - 1) * pos_step < F,
                 "sparse_build_edges: position slice outside [0,F)");
@@ -547,6 +624,7 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
   }
   a.use_radius = use_radius; a.pos_start = pos_start; a.pos_step = pos_step; a.pos_len = pos_len;
   a.radius = radius; a.deg = deg; a.edge_off = edge_off; a.edges = edges; a.E = E;
+  a.flat_off = flat_off; a.flat_col = flat_col;
   // radius selector on graphs large enough for the pair test to dominate: spatial hash
   const bool hash_fits = N <= 65535 && radius > 0.0f && radius < 1.0e30f && eh_smem_bytes(N, pos_len) <= 160 * 1024;
   if (use_radius && hash_fits && (g_edge_builder == GCM_EB_HASH || (g_edge_builder == GCM_EB_AUTO && N >= 256))) {

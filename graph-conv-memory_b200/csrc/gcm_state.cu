@@ -116,28 +116,72 @@ __global__ void __launch_bounds__(256) k_ingest(const gcm_dense_state st, const 
   if (tid == 0) st.count[b] = n;
   float* nodes_b = st.nodes + (size_t)b * C * F;
   const float* src = nodes_in + (size_t)b * N * F;
-  for (int idx = tid; idx < N * F; idx += blockDim.x) nodes_b[idx] = src[idx];  // slot l == row l
-  for (int idx = N * F + tid; idx < C * F; idx += blockDim.x) nodes_b[idx] = 0.0f;
+  if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(nodes_in) | reinterpret_cast<uintptr_t>(st.nodes)) & 15) == 0) {
+    // slot l == row l; 4 independent 16-byte loads in flight per thread
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(nodes_b);
+    const int n4 = N * F / 4, c4 = C * F / 4, bs = blockDim.x;
+    int idx = tid;
+    for (; idx + 3 * bs < n4; idx += 4 * bs) {
+      const float4 v0 = __ldcs(s4 + idx), v1 = __ldcs(s4 + idx + bs), v2 = __ldcs(s4 + idx + 2 * bs),
+                   v3 = __ldcs(s4 + idx + 3 * bs);
+      d4[idx] = v0; d4[idx + bs] = v1; d4[idx + 2 * bs] = v2; d4[idx + 3 * bs] = v3;
+    }
+    for (; idx < n4; idx += bs) d4[idx] = __ldcs(s4 + idx);
+    for (idx = n4 + tid; idx < c4; idx += bs) d4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int idx = tid; idx < N * F; idx += blockDim.x) nodes_b[idx] = src[idx];
+    for (int idx = N * F + tid; idx < C * F; idx += blockDim.x) nodes_b[idx] = 0.0f;
+  }
 
   uint32_t* masks_b = st.masks + (size_t)b * C * 2 * W;
   const float* adj_b = adj_in + (size_t)b * N * N;
-  // one warp per (row l, past|future, word w): lane i <-> offset e = 32 w + i
-  for (int item = warp; item < C * 2 * W; item += nwarps) {
-    const int l = item / (2 * W);
-    const int rem = item - l * 2 * W;
-    const int which = rem / W, w = rem - which * W;
-    uint32_t word = 0u;
-    if (l < N) {
-      const int e = w * 32 + lane;
-      const int m = which ? l + e : l - e;
-      const bool inb = which ? (e >= 1 && m < N) : (m >= 0);
-      const float v = inb ? adj_b[(size_t)l * N + m] : 0.0f;
-      const bool set = v == 1.0f;
-      if (inb && ((v != 0.0f && v != 1.0f) || (set && (l >= n || m >= n)))) flags |= GCM_FLAG_UNCLEAN;
-      if (inb && l < n && m < n && !set) flags |= GCM_FLAG_NOTDENSE;   // DenseEdge states are all ones here
-      word = __ballot_sync(GCM_FULL_MASK, set && l < n && m < n);
+  // one warp per row l: the row is read once with coalesced loads (8 in flight per lane) into a column bitmask
+  // (lane j keeps word j: bit i <-> column 32 j + i; W <= 32), which is then re-indexed by offset:
+  // past bit e <-> column l - e, future bit e <-> column l + e.
+  for (int l = warp; l < C; l += nwarps) {
+    uint32_t* row = masks_b + (size_t)l * 2 * W;
+    if (l >= N) {
+      for (int w = lane; w < 2 * W; w += 32) row[w] = 0u;
+      continue;
     }
-    if (lane == 0) masks_b[item] = word;
+    const float* arow = adj_b + (size_t)l * N;
+    uint32_t myword = 0u;
+    for (int j0 = 0; j0 < W; j0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = (j0 + u) * 32 + lane;
+        v[u] = (j0 + u < W && m < N) ? __ldcs(arow + m) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        if (j < W) {   // warp-uniform
+          const int m = j * 32 + lane;
+          const bool inb = m < N;
+          const bool set = v[u] == 1.0f;
+          if (inb && ((v[u] != 0.0f && v[u] != 1.0f) || (set && (l >= n || m >= n)))) flags |= GCM_FLAG_UNCLEAN;
+          if (inb && l < n && m < n && !set) flags |= GCM_FLAG_NOTDENSE;   // DenseEdge states are all ones here
+          const uint32_t wrd = __ballot_sync(GCM_FULL_MASK, set && l < n && m < n);
+          if (lane == j) myword = wrd;
+        }
+      }
+    }
+    for (int w = 0; w < W; ++w) {
+      const int e = w * 32 + lane;
+      const int mp = l - e;
+      const uint32_t sp = __shfl_sync(GCM_FULL_MASK, myword, (mp >= 0 ? mp : 0) >> 5);
+      const uint32_t pw = __ballot_sync(GCM_FULL_MASK, mp >= 0 && ((sp >> (mp & 31)) & 1u));
+      const int mf = l + e;
+      const bool okf = e >= 1 && mf < N;
+      const uint32_t sf = __shfl_sync(GCM_FULL_MASK, myword, (okf ? mf : 0) >> 5);
+      const uint32_t fw = __ballot_sync(GCM_FULL_MASK, okf && ((sf >> (mf & 31)) & 1u));
+      if (lane == 0) {
+        row[w] = pw;
+        row[W + w] = fw;
+      }
+    }
   }
   if (flags) atomicOr(reinterpret_cast<unsigned int*>(status), flags);
   if (tid == 0) atomicMax(status + 1, n);

@@ -149,7 +149,7 @@ class _Window:
     def ensure_fwd(self, k, cap):
         if k < self.K:
             return
-        K = min(cap, max(16, 2 * self.K, k + 1))
+        K = min(cap, max(64, 2 * self.K, k + 1))
         for name, h in self.FWD:
             new = self._alloc(K, h)
             if self.K:
@@ -193,7 +193,12 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
     state.xsum = S
     ca = _cache_act(plan)
     _lin2(S, w["w_rel1"], bias=w["b1"], act=ca, out=E)
-    _lin2(x, w["w_root1"], act=ca, out=tmp["q"])
+    if state.rc_bf16 and g.F % 16 == 0 and g.H1 % 16 == 0:
+        # the new node's cache row on the bf16 tensor cores, like the rows written by prepare()
+        _cabi.check(lib.gcm_linear_tc(x.data_ptr(), g.F, x.stride(0), w["w_root1"].data_ptr(), None, ca, state.B, g.H1,
+                                      tmp["q"].data_ptr(), g.H1, 0, stream), "gcm_linear_tc")
+    else:
+        _lin2(x, w["w_root1"], act=ca, out=tmp["q"])
     _cabi.check(lib.gcm_dense_ones_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
                                        state.rcache.data_ptr(), E.data_ptr(), tmp["q"].data_ptr(), G.data_ptr(),
                                        None if P is None else P.data_ptr(), ht.data_ptr(), stream),
@@ -206,6 +211,27 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
     if state.host_count is not None:
         state.host_count += 1
     return belief
+
+
+def time_fwd_kernel(plan, state, iters: int = 20) -> float:
+    """Average duration (ms, CUDA events on the current stream) of back-to-back k_ones_fwd launches on the state as it
+    is (the kernel re-derives everything from the counters, so repeating it changes nothing).  For bench.py."""
+    g = plan.gnn
+    tmp = _tmp(state, g)
+    lib = _cabi.lib()
+    stream = _cabi.stream_ptr(state.device)
+    P = torch.empty_like(tmp["G"])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(iters + 3):
+        if i == 3:
+            ev[0].record()
+        _cabi.check(lib.gcm_dense_ones_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
+                                           state.rcache.data_ptr(), tmp["E"].data_ptr(), tmp["q"].data_ptr(),
+                                           tmp["G"].data_ptr(), P.data_ptr(), tmp["ht"].data_ptr(), stream),
+                    "gcm_dense_ones_fwd")
+    ev[1].record()
+    ev[1].synchronize()
+    return ev[0].elapsed_time(ev[1]) / iters
 
 
 def step_nograd(plan, state, x, bf16: bool = False):
@@ -224,6 +250,36 @@ def _param_grads(g, grads):
         if conv.lin_root.bias is not None:
             out.append(grads[bb])
     return out
+
+
+def _lin_bwd(st, a, wt, out):
+    """out = a @ wt.T for the backward products dL/dG = do W_rel2, dL/dh_t = do W_root2 ([rows, H2] x [H2, H1]);
+    bf16 tensor cores when the state computes in bfloat16 (per-sample rounding, gradients only)."""
+    rows, k = a.shape
+    ho = wt.shape[0]
+    if st.rc_bf16 and k % 16 == 0 and ho % 16 == 0:
+        _cabi.check(_cabi.lib().gcm_linear_tc(a.data_ptr(), k, a.stride(0), wt.data_ptr(), None, 0, rows, ho,
+                                              out.data_ptr(), out.stride(0), 0, _cabi.stream_ptr(a.device)),
+                    "gcm_linear_tc")
+    else:
+        _lin2(a, wt, out=out)
+
+
+def _bwd_small(plan, st, k0, k1, have_next):
+    """The [B, H]-sized part of the backward of window steps k0 .. k1-1 (stacked rows): dG, dzo, dc (and the suffix
+    sums of dc when observations require grad; then k1 == k0 + 1)."""
+    g, win = plan.gnn, st.win
+    tw = g.transposed(st.device)
+    rows = (k1 - k0) * st.B
+    do = win.do[k0:k1].view(rows, g.H2)
+    dG = win.dG[k0:k1].view(rows, g.H1)
+    dzo = win.dzo[k0:k1].view(rows, g.H1)
+    _lin_bwd(st, do, tw["w_rel2_t"], dG)                        # dL/dG = do W_rel2
+    _lin_bwd(st, do, tw["w_root2_t"], dzo)                      # dL/dh_t through lin_root2
+    _cabi.check(_cabi.lib().gcm_dense_ones_dc(
+        dG.data_ptr(), dzo.data_ptr(), win.P[k0:k1].data_ptr(), win.ht[k0:k1].data_ptr(), _cabi.ACT[g.act1],
+        rows * g.H1, win.dc[k0:k1].data_ptr(), win.dcs[k0 + 1].data_ptr() if have_next else None,
+        win.dcs[k0].data_ptr() if win.need_dx else None, _cabi.stream_ptr(st.device)), "gcm_dense_ones_dc")
 
 
 class _OnesRootFn(torch.autograd.Function):
@@ -254,6 +310,8 @@ class _OnesRootFn(torch.autograd.Function):
             "b2": torch.zeros(g.H2, device=dev),
         }
         if Kc > 0:
+            if not win.need_dx:
+                _bwd_small(plan, st, 0, Kc, False)
             steps_total = st.steps - win.chain_start
             if steps_total > st.C - st.N + 1:
                 raise RuntimeError(
@@ -298,19 +356,14 @@ class _OnesStepFn(torch.autograd.Function):
         (belief,) = ctx.saved_tensors
         lib = _cabi.lib()
         stream = _cabi.stream_ptr(dev)
-        tw = g.transposed(dev)
         win.ensure_bwd()
-        n = st.B * g.H1
         db_ = d_belief.contiguous().float()
         _cabi.check(lib.gcm_act_backward(db_.data_ptr(), belief.data_ptr(), _cabi.ACT[g.act2], st.B * g.H2,
                                          win.do[k].data_ptr(), stream), "gcm_act_backward")
-        _lin2(win.do[k], tw["w_rel2_t"], out=win.dG[k])                     # dL/dG = do W_rel2
-        _lin2(win.do[k], tw["w_root2_t"], out=win.dzo[k])                   # dL/dh_t through lin_root2
-        have_next = win.need_dx and k < win.kmax
-        _cabi.check(lib.gcm_dense_ones_dc(
-            win.dG[k].data_ptr(), win.dzo[k].data_ptr(), win.P[k].data_ptr(), win.ht[k].data_ptr(), _cabi.ACT[g.act1], n,
-            win.dc[k].data_ptr(), win.dcs[k + 1].data_ptr() if have_next else None,
-            win.dcs[k].data_ptr() if win.need_dx else None, stream), "gcm_dense_ones_dc")
+        if win.need_dx:
+            # dL/dx_k is due now: finish this step's [B, H] work (otherwise the root does it for all steps at once)
+            _bwd_small(plan, st, k, k + 1, k < win.kmax)
+        tw = g.transposed(dev)
         win.kmax = max(win.kmax, k)
         d_x = None
         if ctx.needs_input_grad[0]:

@@ -171,7 +171,14 @@ class SparseGCM(torch.nn.Module):
 
         # edges: previous (sinks < T) + the new nodes' (sinks >= T), both sorted by (b, sink, source)
         old = adj.coalesce().indices() if adj._nnz() else torch.zeros(3, 0, dtype=torch.long, device=dev)
-        new = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, hops, radius)
+        csr = None
+        if old.shape[1] == 0 and n_new == n_flat:
+            # every row is new (hidden=None, all-at-once): the builder's per-sink offsets ARE the CSR row pointer
+            # and it writes the flat column ids in the same pass
+            new, edge_off, flat_col = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, hops, radius, offsets)
+            csr = sparse_ops.Csr(edge_off, flat_col, n_flat)
+        else:
+            new = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, hops, radius)
         if old.shape[1] == 0:
             edges = new
         elif new.shape[1] == 0:
@@ -186,8 +193,9 @@ class SparseGCM(torch.nn.Module):
             edges[:, torch.arange(new.shape[1], device=dev) + old_end[new[0]]] = new
         if old.shape[1]:
             assert bool((edges[2] < edges[1]).all()), "Causality violated"
-        base = offsets[edges[0]]
-        csr = sparse_ops.Csr.from_sorted_edges(edges[1] + base, edges[2] + base, n_flat)
+        if csr is None:
+            base = offsets[edges[0]]
+            csr = sparse_ops.Csr.from_sorted_edges(edges[1] + base, edges[2] + base, n_flat)
 
         # two GraphConv layers; the second only on the rows that are returned
         h = sparse_ops.graph_conv_csr(flat, csr, None, c1.lin_rel.weight, _one_bias(c1), c1.lin_root.weight, a1)

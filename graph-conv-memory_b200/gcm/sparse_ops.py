@@ -67,13 +67,19 @@ class _WriteFlattenFn(torch.autograd.Function):
 
 
 def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_off: torch.Tensor, n_new: int,
-                tmax: int, hops: Sequence[int], radius: Optional[Tuple[slice, float]]) -> torch.Tensor:
-    """Coalesced edges (batch, sink, source) int64 [3, E] of the new nodes (gcm_sparse_build_edges)."""
+                tmax: int, hops: Sequence[int], radius: Optional[Tuple[slice, float]],
+                flat_off: Optional[torch.Tensor] = None):
+    """Coalesced edges (batch, sink, source) int64 [3, E] of the new nodes (gcm_sparse_build_edges).
+    With flat_off ([B+1] exclusive cumsum of T + tau) also returns (edge_off [n_new+1], flat_col [E]): the CSR of
+    the new rows over the flat node numbering, written by the same kernel pass."""
     _cabi.require_cuda(nodes, "sparse edge selector")
     B, N, F = nodes.shape
     dev = nodes.device
     if n_new == 0 or (not hops and radius is None):
-        return torch.zeros(3, 0, dtype=torch.long, device=dev)
+        empty = torch.zeros(3, 0, dtype=torch.long, device=dev)
+        if flat_off is None:
+            return empty
+        return empty, torch.zeros(n_new + 1, dtype=torch.long, device=dev), empty[0]
     hops_t = torch.tensor(sorted(set(int(h) for h in hops)), dtype=torch.int32)
     hops_c = (_cabi.C.c_int32 * max(len(hops_t), 1))(*hops_t.tolist())
     use_r, p0, pst, pl, rad = 0, 0, 1, 0, 0.0
@@ -90,14 +96,19 @@ def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_of
     deg = torch.empty(n_new, dtype=torch.int32, device=dev)
     args = (nodes_c.data_ptr(), T.data_ptr(), taus.data_ptr(), new_off.data_ptr(), B, N, F, tmax, hops_c,
             len(hops_t), use_r, p0, pst, pl, float(rad))
-    _cabi.check(lib.gcm_sparse_build_edges(*args, deg.data_ptr(), None, None, 0, stream), "gcm_sparse_build_edges")
-    edge_off = _excl_cumsum(deg.long())
+    _cabi.check(lib.gcm_sparse_build_edges(*args, deg.data_ptr(), None, None, 0, None, None, stream),
+                "gcm_sparse_build_edges")
+    edge_off = _excl_cumsum(deg)
     E = int(edge_off[-1].item())
     edges = torch.empty(3, E, dtype=torch.long, device=dev)
+    flat_col = torch.empty(E, dtype=torch.long, device=dev) if flat_off is not None else None
     if E:
-        _cabi.check(lib.gcm_sparse_build_edges(*args, None, edge_off.data_ptr(), edges.data_ptr(), E, stream),
+        _cabi.check(lib.gcm_sparse_build_edges(*args, None, edge_off.data_ptr(), edges.data_ptr(), E,
+                                               _cabi.ptr(flat_off), _cabi.ptr(flat_col), stream),
                     "gcm_sparse_build_edges")
-    return edges
+    if flat_off is None:
+        return edges
+    return edges, edge_off, flat_col
 
 
 class Csr:

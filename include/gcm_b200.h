@@ -297,11 +297,12 @@ int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, con
  * from three COO coalesces (sparse_gcm.py:132-139,152).  Two passes: edges == NULL writes the
  * in-degree of every new node to deg [n_new] (ordered by b, then s; new_off = exclusive cumsum of
  * taus, [B+1]); with edge_off = exclusive cumsum of deg ([n_new+1]) the second call fills
- * edges int64 [3, E]. */
+ * edges int64 [3, E] and, if flat_col != NULL, flat_col[e] = flat_off[b] + source (flat_off [B+1] = exclusive cumsum
+ * of T + tau: the source's row in the flat node array of util.py:426-452, i.e. the CSR column of GraphConv). */
 int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* taus, const int64_t* new_off,
                            int B, int N, int F, int tmax, const int32_t* hops, int n_hops, int use_radius,
                            int pos_start, int pos_step, int pos_len, float radius, int32_t* deg,
-                           const int64_t* edge_off, int64_t* edges, int64_t E, void* stream);
+                           const int64_t* edge_off, int64_t* edges, int64_t E, const int64_t* flat_off, int64_t* flat_col, void* stream);
 
 /* Which kernel evaluates the radius selector (process-wide).  AUTO: all-pairs test for small graphs, spatial
  * hash (cells of side `radius`, 3 x 3 neighbourhood, same float comparison) from N = 256.  Both produce the
