@@ -28,6 +28,58 @@ __device__ __forceinline__ float tcg_exp2x(float z) {   // exp(2 clamp(z, +-40))
   return z == z ? e : z;
 }
 
+// W [Ho, K] row-major float32 (global) -> shared memory, canonical K-major no-swizzle layouts.  Four 16-byte loads
+// are in flight per thread (a one-load-per-iteration loop serialises ~100 L2 round trips per thread, which was the
+// whole duration of the small launches); 4 (tf32) / 8 (bf16) consecutive k are contiguous in the canonical layout.
+template <int NTHREADS>
+__device__ __forceinline__ void stage_w_tf32(const float* __restrict__ W, int Ho, int K, float* Whi, float* Wlo, int tid) {
+  const int n4 = Ho * K / 4;
+  for (int i0 = tid; i0 < n4; i0 += 4 * NTHREADS) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q * NTHREADS;
+      v[q] = i < n4 ? __ldg(reinterpret_cast<const float4*>(W) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q * NTHREADS;
+      if (i < n4) {
+        const int e = i * 4, n = e / K, k = e - n * K;
+        uint32_t h[4], l[4];
+        tc::split_tf32(v[q].x, h[0], l[0]); tc::split_tf32(v[q].y, h[1], l[1]);
+        tc::split_tf32(v[q].z, h[2], l[2]); tc::split_tf32(v[q].w, h[3], l[3]);
+        const int off = tc::kmajor_off(n, k, K);
+        *reinterpret_cast<uint4*>(Whi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(Wlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+template <int NTHREADS>
+__device__ __forceinline__ void stage_w_bf16(const float* __restrict__ W, int Ho, int K, __nv_bfloat16* Ws, int tid) {
+  const int n8 = Ho * K / 8;
+  for (int i0 = tid; i0 < n8; i0 += 2 * NTHREADS) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = i0 + q * NTHREADS;
+      v[2 * q] = i < n8 ? __ldg(reinterpret_cast<const float4*>(W) + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[2 * q + 1] = i < n8 ? __ldg(reinterpret_cast<const float4*>(W) + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = i0 + q * NTHREADS;
+      if (i < n8) {
+        const int e = i * 8, n = e / K, k = e - n * K;
+        *reinterpret_cast<uint4*>(Ws + tc::kmajor_off_bf16(n, k, K)) =
+            make_uint4(tc::pack_bf16(v[2 * q].x, v[2 * q].y), tc::pack_bf16(v[2 * q].z, v[2 * q].w),
+                       tc::pack_bf16(v[2 * q + 1].x, v[2 * q + 1].y), tc::pack_bf16(v[2 * q + 1].z, v[2 * q + 1].w));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[r, :Ho] = epi(X[r, :K] W^T + bias), W row-major [Ho, K] float32 (rounded to bf16 once per CTA).
 // Persistent; a tile = 128 rows, TMEM lane = row.  K, Ho multiples of 16, <= 128.
@@ -59,10 +111,7 @@ __global__ void __launch_bounds__(TCG_THREADS) k_linear_tc(const LinearTcArgs a)
     tc::mbar_fence_init();
   }
   if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < Ho * K; i += TCG_THREADS) {
-    const int n = i / K, k = i - n * K;
-    Ws[tc::kmajor_off_bf16(n, k, K)] = __float2bfloat16_rn(__ldg(a.W + i));
-  }
+  stage_w_bf16<TCG_THREADS>(a.W, Ho, K, Ws, tid);
   tc::fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -153,6 +202,163 @@ __global__ void __launch_bounds__(TCG_THREADS) k_linear_tc(const LinearTcArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// out[r, :Ho] = act(X1[r, :K1] W1^T  [3xTF32: fp32-accurate]  +  X2[r, :K2] W2^T  [bf16, optional]  + bias)
+// for the two products of a step whose error is common to every node of a graph (c = W_rel1 S + b1, and the G term of
+// the belief): every fp32 value is split hi + lo (hi exactly representable in tf32) and the product is issued as
+// lo*Bhi + hi*Blo + hi*Bhi (gcm_tc.cuh); the h_t W_root2^T term of the belief may ride along in bf16.
+// One 128-row tile per CTA (B graphs = B / 128 CTAs), TMEM: A1 hi | A1 lo | A2 | D.
+// ------------------------------------------------------------------------------------------------
+struct LinearTc32Args {
+  const float* X1; long long ldx1; int K1; const float* W1;
+  const float* X2; long long ldx2; int K2; const float* W2;   // optional bf16 part
+  const float* bias;
+  int act;              // GCM_ACT_* or GCM_ACT_EXP2X
+  long long rows;
+  int Ho;
+  float* out; long long ldo;
+  int32_t* status;
+};
+
+constexpr int TC32_THREADS = 288;   // warps 0-3: A rows -> TMEM, epilogue; warps 4-8: weight staging; warp 8 lane 0: MMA issue
+
+__global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int K1 = a.K1, K2 = a.X2 ? a.K2 : 0, Ho = a.Ho;
+  float* Whi = reinterpret_cast<float*>(smem_raw);                         // [Ho x K1] canonical K-major (tf32)
+  float* Wlo = Whi + (size_t)Ho * K1;
+  __nv_bfloat16* W2s = reinterpret_cast<__nv_bfloat16*>(Wlo + (size_t)Ho * K1);   // [Ho x K2] canonical (bf16)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W2s + (size_t)Ho * K2);
+  uint64_t* full = bars;         // A operands are in TMEM (128 arrivals)
+  uint64_t* wready = bars + 1;   // weights are in shared memory (160 arrivals)
+  uint64_t* done = bars + 2;     // all MMAs completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tc::mbar_init(full, 128);
+    tc::mbar_init(wready, TC32_THREADS - 128);
+    tc::mbar_init(done, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t col_hi = 0, col_lo = 128, col_a2 = 256, col_d = 320;   // K1 <= 128, K2 / 2 <= 64, Ho <= 128
+  if (warp < 4) {
+    // the tile's rows go to TMEM while the other warps stage the weights
+    const long long r = (long long)blockIdx.x * 128 + tid;
+    const bool ok = r < a.rows;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const float4* x1 = reinterpret_cast<const float4*>(a.X1 + (ok ? r : 0) * a.ldx1);
+    for (int k0 = 0; k0 < K1; k0 += 64) {        // 16 independent 16-byte loads in flight per thread
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = (ok && k0 + 4 * j < K1) ? __ldg(x1 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (k0 + 16 * c < K1) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tc::split_tf32(v[4 * c + j].x, hi[4 * j], lo[4 * j]);
+            tc::split_tf32(v[4 * c + j].y, hi[4 * j + 1], lo[4 * j + 1]);
+            tc::split_tf32(v[4 * c + j].z, hi[4 * j + 2], lo[4 * j + 2]);
+            tc::split_tf32(v[4 * c + j].w, hi[4 * j + 3], lo[4 * j + 3]);
+          }
+          tc::tmem_st16(lane_addr + col_hi + k0 + 16 * c, hi);
+          tc::tmem_st16(lane_addr + col_lo + k0 + 16 * c, lo);
+        }
+      }
+    }
+    if (K2) {
+      const float4* x2 = reinterpret_cast<const float4*>(a.X2 + (ok ? r : 0) * a.ldx2);
+      for (int k0 = 0; k0 < K2; k0 += 64) {
+        float4 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = (ok && k0 + 4 * j < K2) ? __ldg(x2 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (k0 + 16 * c < K2) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              pk[2 * j] = tc::pack_bf16(v[4 * c + j].x, v[4 * c + j].y);
+              pk[2 * j + 1] = tc::pack_bf16(v[4 * c + j].z, v[4 * c + j].w);
+            }
+            tc::tmem_st8(lane_addr + col_a2 + ((k0 + 16 * c) >> 1), pk);
+          }
+        }
+      }
+    }
+    tc::wait_st();
+    tc::fence_before_sync();
+    tc::mbar_arrive(full);
+    tc::mbar_wait(done, 0);
+    tc::fence_after_sync();
+    bool bad = false;
+    for (int n0 = 0; n0 < Ho; n0 += 16) {
+      uint32_t d[16];
+      tc::tmem_ld16(lane_addr + col_d + n0, d);
+      tc::wait_ld();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(d[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.0f);
+      if (a.act == GCM_ACT_EXP2X) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = tcg_exp2x(f[j]);
+      } else {
+        gcm_act_fast_vec(f, a.act);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bad |= !isfinite(f[j]);
+      if (ok) {
+        float4* o = reinterpret_cast<float4*>(a.out + r * a.ldo + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      }
+    }
+    if (a.status && bad && ok) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
+    tc::fence_before_sync();
+  } else {
+    stage_w_tf32<TC32_THREADS - 128>(a.W1, Ho, K1, Whi, Wlo, tid - 128);
+    if (K2) stage_w_bf16<TC32_THREADS - 128>(a.W2, Ho, K2, W2s, tid - 128);
+    tc::fence_proxy_async();
+    tc::mbar_arrive(wready);
+    if (warp == 8 && lane == 0) {
+      tc::mbar_wait(wready, 0);
+      tc::mbar_wait(full, 0);
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::idesc_tf32(128, Ho);
+      const uint32_t sbo = (uint32_t)(K1 / 4) * 128u;
+      bool acc = false;
+      for (int pass = 0; pass < 3; ++pass) {       // lo*Bhi, hi*Blo, hi*Bhi
+        const uint32_t a_col = pass == 0 ? col_lo : col_hi;
+        const float* bsrc = pass == 1 ? Wlo : Whi;
+        for (int ks = 0; ks < K1 / 8; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
+          tc::mma_tf32_ts(tbase + col_d, tbase + a_col + ks * 8, bdesc, idesc, acc);
+          acc = true;
+        }
+      }
+      if (K2) {
+        const uint32_t idesc16 = tc::idesc_bf16(128, Ho);
+        const uint32_t sbo16 = (uint32_t)(K2 / 8) * 128u;
+        for (int ks = 0; ks < K2 / 16; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(W2s) + ks * 256, 128, sbo16);
+          tc::mma_bf16_ts(tbase + col_d, tbase + col_a2 + ks * 8, bdesc, idesc16, true);
+        }
+      }
+      tc::mma_commit(done);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // part[cta][o][i] = sum over the CTA's rows of A[r, o] X[r, i]   (and the column sums of A); a second kernel
 // adds the partials into dW / db in a fixed order (deterministic, no atomics).
 // MMA view: D[M = o, N = i] += A^T[o, k = r] X^T[i, k = r]: TMEM lane = output channel o, the reduction runs over
@@ -206,15 +412,19 @@ __global__ void __launch_bounds__(TCG_THREADS, 2) k_outer_tc(const OuterTcArgs a
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float av[32], xv[32];
+        const long long rh = r0 + half * 32;
+        const float* pa = a.A + rh * a.lda + ch;
+        const float* px = a.X + rh * a.ldx + ch;
+        if (rh + 32 <= r_end) {   // whole half-chunk in range: no per-row guards, pointer increments only
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const long long r = r0 + half * 32 + u;
-          av[u] = (a_ok && r < r_end) ? __ldcs(a.A + r * a.lda + ch) : 0.0f;
-        }
+          for (int u = 0; u < 32; ++u) av[u] = a_ok ? __ldcs(pa + u * a.lda) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const long long r = r0 + half * 32 + u;
-          xv[u] = (x_ok && r < r_end) ? __ldcs(a.X + r * a.ldx + ch) : 0.0f;
+          for (int u = 0; u < 32; ++u) xv[u] = x_ok ? __ldcs(px + u * a.ldx) : 0.0f;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) av[u] = (a_ok && rh + u < r_end) ? __ldcs(pa + u * a.lda) : 0.0f;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) xv[u] = (x_ok && rh + u < r_end) ? __ldcs(px + u * a.ldx) : 0.0f;
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -304,12 +514,43 @@ extern "C" int gcm_linear_tc(const float* X, int K, long long ldx, const float* 
                   ldo % (out_bf16 ? 8 : 4) == 0,
               "linear_tc: K=%d and Ho=%d must be multiples of 16 in [16,128], rows 16-byte aligned", K, Ho);
   GCM_REQUIRE(act == GCM_ACT_NONE || act == GCM_ACT_EXP2X, "linear_tc: epilogue must be none or EXP2X");
+  GCM_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "linear_tc: X, W and out must be 16-byte aligned");
   if (rows == 0) return GCM_OK;
   LinearTcArgs a{X, ldx, K, W, bias, act, rows, Ho, out, ldo, out_bf16, (rows + 127) / 128};
   const size_t smem = (size_t)Ho * K * 2 + 64;
   long long grid = a.tiles < gcm_num_sms() ? a.tiles : gcm_num_sms();
   k_linear_tc<<<(unsigned)grid, TCG_THREADS, smem, (cudaStream_t)stream>>>(a);
   return gcm_check_launch("k_linear_tc");
+}
+
+extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const float* W1, const float* X2, int K2,
+                               long long ldx2, const float* W2, const float* bias, int act, long long rows, int Ho,
+                               float* out, long long ldo, int32_t* status, void* stream) {
+  GCM_REQUIRE(X1 && W1 && out && rows >= 0, "linear_tc32: null pointer");
+  GCM_REQUIRE((X2 == nullptr) == (W2 == nullptr), "linear_tc32: X2 and W2 go together");
+  GCM_REQUIRE(K1 >= 16 && K1 <= 128 && K1 % 16 == 0 && Ho >= 16 && Ho <= 128 && Ho % 16 == 0 && ldx1 % 4 == 0 && ldo % 4 == 0,
+              "linear_tc32: K1=%d and Ho=%d must be multiples of 16 in [16,128], rows 16-byte aligned", K1, Ho);
+  GCM_REQUIRE(!X2 || (K2 >= 16 && K2 <= 128 && K2 % 16 == 0 && ldx2 % 4 == 0), "linear_tc32: bad K2=%d", K2);
+  GCM_REQUIRE((act >= GCM_ACT_NONE && act <= GCM_ACT_RELU) || act == GCM_ACT_EXP2X, "linear_tc32: bad epilogue");
+  GCM_REQUIRE(((reinterpret_cast<uintptr_t>(X1) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(X2) |
+                reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              "linear_tc32: operands must be 16-byte aligned");
+  if (rows == 0) return GCM_OK;
+  LinearTc32Args a{X1, ldx1, K1, W1, X2, ldx2, X2 ? K2 : 0, W2, bias, act, rows, Ho, out, ldo, status};
+  const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_linear_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 10 + 64) != cudaSuccess) {
+      gcm_set_error("linear_tc32: cannot raise the dynamic shared memory limit");
+      return GCM_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const long long grid = (rows + 127) / 128;
+  GCM_REQUIRE(grid < 2147483647LL, "linear_tc32: too many rows");
+  k_linear_tc32<<<(unsigned)grid, TC32_THREADS, smem, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_linear_tc32");
 }
 
 extern "C" long long gcm_outer_reduce_tc_workspace(long long rows) {

@@ -110,6 +110,8 @@ _SIGNATURES = {
     "gcm_dense_ones_dc": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_to_bf16": (_I, [_P, _P, C.c_longlong, _P]),
     "gcm_linear_tc": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P, C.c_longlong, _I, _P]),
+    "gcm_linear_tc32": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P,
+                             C.c_longlong, _P, _P]),
     "gcm_outer_reduce_tc_workspace": (C.c_longlong, [C.c_longlong]),
     "gcm_outer_reduce_tc": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),

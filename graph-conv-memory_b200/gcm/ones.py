@@ -40,6 +40,21 @@ def _lin2(a1, w1, a2=None, w2=None, bias=None, act=0, out=None, status=None, acc
     return out
 
 
+def _lin_tc32(a1, w1, a2=None, w2=None, bias=None, act=0, out=None, status=None):
+    """out = act(a1 @ w1.T [3xTF32] + a2 @ w2.T [bf16] + bias) through gcm_linear_tc32 (tcgen05)."""
+    rows, k1 = a1.shape
+    ho = w1.shape[0]
+    if out is None:
+        out = torch.empty(rows, ho, device=a1.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().gcm_linear_tc32(
+        a1.data_ptr(), k1, a1.stride(0), w1.data_ptr(),
+        None if a2 is None else a2.data_ptr(), 0 if a2 is None else a2.shape[1], 0 if a2 is None else a2.stride(0),
+        None if w2 is None else w2.data_ptr(), None if bias is None else bias.data_ptr(), act, rows, ho,
+        out.data_ptr(), out.stride(0), None if status is None else status.data_ptr(),
+        _cabi.stream_ptr(a1.device)), "gcm_linear_tc32")
+    return out
+
+
 def _outer(a, x, dw, db=None):
     """dw += a.T @ x, db += a.sum(0) through gcm_outer_reduce."""
     _cabi.check(_cabi.lib().gcm_outer_reduce(a.data_ptr(), a.stride(0), a.shape[1], x.data_ptr(), x.stride(0),
@@ -192,7 +207,12 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
                 "gcm_dense_ones_update")
     state.xsum = S
     ca = _cache_act(plan)
-    _lin2(S, w["w_rel1"], bias=w["b1"], act=ca, out=E)
+    tc_dims = g.F % 16 == 0 and g.H1 % 16 == 0 and g.H2 % 16 == 0
+    if tc_dims:
+        # c = W_rel1 S + b1 is common to every node of the graph: 3xTF32 (fp32-accurate) on the tensor cores
+        _lin_tc32(S, w["w_rel1"], bias=w["b1"], act=ca, out=E)
+    else:
+        _lin2(S, w["w_rel1"], bias=w["b1"], act=ca, out=E)
     if state.rc_bf16 and g.F % 16 == 0 and g.H1 % 16 == 0:
         # the new node's cache row on the bf16 tensor cores, like the rows written by prepare()
         _cabi.check(lib.gcm_linear_tc(x.data_ptr(), g.F, x.stride(0), w["w_root1"].data_ptr(), None, ca, state.B, g.H1,
@@ -203,7 +223,11 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
                                        state.rcache.data_ptr(), E.data_ptr(), tmp["q"].data_ptr(), G.data_ptr(),
                                        None if P is None else P.data_ptr(), ht.data_ptr(), stream),
                 "gcm_dense_ones_fwd")
-    belief = _lin2(G, w["w_rel2"], ht, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
+    if tc_dims and state.rc_bf16:
+        # G W_rel2^T in 3xTF32 (G sums up to N rows), h_t W_root2^T in bf16 (|h_t| < 1, per-graph rounding only)
+        belief = _lin_tc32(G, w["w_rel2"], ht, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
+    else:
+        belief = _lin2(G, w["w_rel2"], ht, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
     state.masks_stale = True
     state.version += 1
     state.steps += 1

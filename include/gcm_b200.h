@@ -263,6 +263,13 @@ int gcm_to_bf16(const float* in, void* out, long long n, void* stream);
  * workspace: gcm_outer_reduce_tc_workspace(rows) floats of device memory. */
 int gcm_linear_tc(const float* X, int K, long long ldx, const float* W, const float* bias, int act, long long rows,
                   int Ho, void* out, long long ldo, int out_bf16, void* stream);
+/* out[r,:Ho] = act(X1[r,:K1] W1^T + X2[r,:K2] W2^T + bias): the X1 product in 3xTF32 (fp32-accurate: hi/lo split, three
+ * tcgen05 tf32 MMAs), the optional X2 product in bf16; act = GCM_ACT_* or GCM_ACT_EXP2X; status as gcm_linear2.
+ * (lin_rel of layer 1 on the window sum S, and lin_rel + lin_root of layer 2 on (G, h_t): the two products of the ones
+ * path whose rounding is common to every node of a graph.)  K1, K2, Ho multiples of 16 in [16,128]. */
+int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const float* W1, const float* X2, int K2, long long ldx2,
+                    const float* W2, const float* bias, int act, long long rows, int Ho, float* out, long long ldo,
+                    int32_t* status, void* stream);
 long long gcm_outer_reduce_tc_workspace(long long rows);
 int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
                         float* workspace, float* dW, float* db, void* stream);

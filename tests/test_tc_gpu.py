@@ -74,3 +74,37 @@ def test_outer_reduce_tc_matches_bf16_rounded_reference(rows, Ho, Hi, bias):
     if bias:
         assert float((outs[0][1].double() - (1 + A.double().sum(0))).abs().max()) < 1e-4 * max(1.0, rows ** 0.5)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("rows,K1,K2,Ho,act", [(16384, 128, 128, 128, 1), (300, 64, 0, 32, 3), (129, 16, 32, 128, 0)])
+def test_linear_tc32_is_fp32_accurate(rows, K1, K2, Ho, act):
+    """gcm_linear_tc32: the X1 product in 3xTF32 must be fp32-class (against fp64), the optional X2 product is bf16."""
+    from gcm import _cabi
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(rows + K1)
+    X1 = (8.0 * torch.randn(rows, K1, generator=g)).to(dev)           # large magnitudes, like the window sums S and G
+    W1 = (torch.randn(Ho, K1, generator=g) / K1 ** 0.5).to(dev)
+    X2 = torch.tanh(torch.randn(rows, max(K2, 1), generator=g)).to(dev)
+    W2 = (torch.randn(Ho, max(K2, 1), generator=g) / max(K2, 1) ** 0.5).to(dev)
+    bias = torch.randn(Ho, generator=g).to(dev)
+    out = torch.empty(rows, Ho, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    _cabi.check(_cabi.lib().gcm_linear_tc32(X1.data_ptr(), K1, K1, W1.data_ptr(), X2.data_ptr() if K2 else None, K2, K2,
+                                            W2.data_ptr() if K2 else None, bias.data_ptr(), act, rows, Ho, out.data_ptr(), Ho,
+                                            status.data_ptr(), _cabi.stream_ptr(dev)), "gcm_linear_tc32")
+    z = X1.double() @ W1.double().t() + bias.double()
+    if K2:
+        z = z + X2.bfloat16().double() @ W2.bfloat16().double().t()
+    z32 = (X1 @ W1.t()).double() + bias.double() + ((X2.bfloat16().float() @ W2.bfloat16().float().t()).double() if K2 else 0)
+    if act == 1:
+        ref, ref32 = torch.tanh(z), torch.tanh(z32)
+    elif act == 3:
+        ref, ref32 = torch.exp(2 * z.clamp(-40, 40)), torch.exp(2 * z32.clamp(-40, 40))
+    else:
+        ref, ref32 = z, z32
+    rel = lambda x: float(((x - ref).abs() / ref.abs().clamp(min=1.0)).max())
+    err, err32 = rel(out.double()), rel(ref32)
+    print(f"rows={rows} K1={K1} K2={K2} Ho={Ho} act={act}: 3xTF32 err {err:.2e}, fp32 matmul err {err32:.2e}")
+    assert err < (1e-4 if act == 3 else 1e-5) + 2 * err32      # exp(2z) multiplies a relative error of z by 2|z|
+    assert int(status[0]) == 0
