@@ -15,7 +15,7 @@ JSON line (rank 0):
                back-to-back launches), against MEASURED_PEAKS.json
   cpu_baseline the oracle port of the reference step on the host cores (bounded sample)
 
-Other workloads (`--workload cfg1|cfg3|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
+Other workloads (`--workload cfg1|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
 configs with the same line format; `--impl reference` times the oracle port of the reference on CPU.
 """
 import argparse
@@ -41,6 +41,8 @@ WORKLOADS = {
              65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "rollout"),
     "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, bf16 per-node cache, fp32 accumulate)",
              16384, 256, 128, 128, [("dense",)], "bptt"),
+    "cfg3-seq": ("cfg3 through DenseGCM.forward_sequence (SURVEY 8(f) rank 1): the T=64 steps of a window in one call, "
+                 "bf16 per-node cache, fwd+bwd", 16384, 256, 128, 128, [("dense",)], "bptt"),
     "cfg4-cosine": ("cfg4: DenseGCM CosineEdge(0.5) N=512 F=64 H=64 rollout fwd",
                     4096, 512, 64, 64, [("cosine", 0.5)], "rollout"),
     "cfg4-euclid": ("cfg4: DenseGCM EuclideanEdge(2.0) N=512 F=64 H=64 rollout fwd (cross-batch mean)",
@@ -173,7 +175,7 @@ def algorithmic(workload, B, N, F, H, extra=None):
             return "fp32", 2.0 * B * B * N * F, "flop"
         per = N * F * 4 + 2 * F * 4 + N // 8 * 2 + H * 4 + 16
         return "hbm", per * B, "bytes"
-    if workload == "cfg3":
+    if workload in ("cfg3", "cfg3-seq"):
         # SURVEY.md 8(d), all-ones structure exploited: 66.8 KB per graph-step of the forward (bf16 per-node rows at
         # n = N); k_ones_fwd is that pass.  The backward is one pass per window, not 2x this per step.
         return "hbm", B * (N * F * 2 + 2 * F * 4 + N // 8 + H * 4 + 16), "bytes"
@@ -390,13 +392,20 @@ def main():
         adj0 = torch.zeros(B, N, N, device=dev)
         adj0[:, : N - T, : N - T] = 1                                            # DenseEdge history: all ones
 
+        seq = args.workload == "cfg3-seq"
+        obs_bt = obs_dev.transpose(0, 1).contiguous() if seq else None         # [B, T, F] for the sequence entry
+
         def window(obs):
             hidden = (nodes0, adj0, torch.zeros(0, device=dev), nn0)
             opt.zero_grad(set_to_none=True)
-            tot = 0
-            for t in range(T):
-                belief, hidden = mod(obs[t], hidden)
-                tot = tot + belief.mean()
+            if seq:
+                beliefs, hidden = mod.forward_sequence(obs_bt, hidden)
+                tot = beliefs.mean() * T
+            else:
+                tot = 0
+                for t in range(T):
+                    belief, hidden = mod(obs[t], hidden)
+                    tot = tot + belief.mean()
             (tot / T).backward()
             gdist.allreduce_grads(mod.parameters(), average=True)               # the one NCCL collective
             opt.step()
@@ -431,6 +440,9 @@ def main():
         extra = {"window_ms": total_ms / K, "fwd_kernel_share_of_window": kern_ms * T / (total_ms / K)}
         kernel_name = ("k_ones_fwd (1 launch per step; the backward is ONE k_ones_window_bwd per window, "
                        "see DESIGN.md section 3)")
+        if seq:
+            extra["note"] = ("the sequence entry replaces the 64 k_ones_fwd launches by ONE k_ones_window_fwd (cache rows "
+                             "read once, MUFU-bound); kernel_ms / frac above are those of the per-step kernel for reference")
     else:  # sparse, all-at-once
         mod = build_sparse(dev, N, F, H)
         x = torch.randn(B, N, F, generator=gen)

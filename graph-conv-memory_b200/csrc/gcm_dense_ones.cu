@@ -400,6 +400,142 @@ __global__ void __launch_bounds__(128) k_ones_fwd(const OnesFwdArgs a) {
   }
 }
 
+// ---- T steps at once (the sequence entry: SURVEY 8(f) rank 1; caller = RayDenseGCM's `for t in range(T)` loop,
+// ray_gcm.py:200-202) ---------------------------------------------------------------------------------
+// With all T observations known, the forward has the structure of the window backward: the cache rows of a graph are
+// read from HBM ONCE (into shared memory) and every step's G_k = sum_i act1(c_k + R_i) is formed from there, so the
+// pass is MUFU-bound instead of T HBM streams.  k_ones_seq_update does the T node writes / evictions / running sums.
+__global__ void __launch_bounds__(256) k_ones_seq_update(const gcm_dense_state st, const float* x_seq, long long xs_b,
+                                                         long long xs_t, int T, const float* xsum_in, float* wS,
+                                                         long long sstride) {
+  const int F4 = st.F >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)st.B * F4) return;
+  const int b = (int)(i / F4), c = (int)(i - (long long)b * F4);
+  const int cnt = __ldcg(st.count + b);
+  float4* nodes_b = reinterpret_cast<float4*>(st.nodes + (size_t)b * st.C * st.F);
+  float4 s = reinterpret_cast<const float4*>(xsum_in)[(size_t)b * F4 + c];
+  for (int k = 0; k < T; ++k) {
+    const int p = cnt + k;
+    if (p >= st.N) {   // the oldest node leaves the window (gcm.py:323-355); read before its slot may be reused
+      const float4 old = nodes_b[(size_t)gcm_slot(p - st.N, st.C) * F4 + c];
+      s.x -= old.x; s.y -= old.y; s.z -= old.z; s.w -= old.w;
+    }
+    const float4 x = *reinterpret_cast<const float4*>(x_seq + (size_t)b * xs_b + (size_t)k * xs_t + c * 4);
+    s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    nodes_b[(size_t)gcm_slot(p, st.C) * F4 + c] = x;
+    reinterpret_cast<float4*>(wS + (size_t)k * sstride)[(size_t)b * F4 + c] = s;
+  }
+}
+__global__ void __launch_bounds__(256) k_ones_bump_n(int32_t* count, int B, int n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) count[b] += n;
+}
+
+struct OnesSeqArgs {
+  gcm_dense_state st;   // count already advanced by T
+  int H1, T;
+  void* cache;          // [B, C, H1]
+  const float* wE;      // [T, B, H1]  E_k (tanh) or c_k
+  const float* q_new;   // [B, T, H1]  cache rows of the T new nodes (float32; stored into the cache here)
+  float* wG;            // [T, B, H1]  out
+  float* wP;            // [T, B, H1]  out (REC)
+  float* wht;           // [T, B, H1]  out
+  long long sstride;    // floats between steps of wE / wG / wP / wht
+};
+
+constexpr int SEQ_THREADS = 256;
+template <typename CT, int ACT, bool REC>
+__global__ void __launch_bounds__(SEQ_THREADS) k_ones_window_fwd(const OnesSeqArgs a) {
+  extern __shared__ __align__(16) unsigned char seq_smem[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int H1 = a.H1, C = a.st.C, N = a.st.N, T = a.T;
+  const int tpr = H1 >> 2;                      // host: H1 % 4 == 0 (bf16: % 8), H1 <= 128
+  const int rpp = SEQ_THREADS / tpr;
+  const int rl = tid / tpr, vl = tid - rl * tpr;
+  const int count0 = __ldcg(a.st.count + b) - T;
+  const int lo = max(0, count0 + 1 - N);        // oldest node step 0 sees
+  const int n_old = count0 - lo;
+  CT* rows = reinterpret_cast<CT*>(seq_smem);   // [n_old + T][H1], row j = node lo + j
+  float* red = reinterpret_cast<float*>(seq_smem + (((size_t)(N + T) * H1 * sizeof(CT) + 15) & ~(size_t)15));  // [2][2][rpp][H1]
+  CT* cache = reinterpret_cast<CT*>(a.cache) + (size_t)b * C * H1;
+  // 1. rows that existed before the call: HBM -> shared memory (8-byte pieces; the only HBM stream of the kernel)
+  if (rl < rpp) {
+    for (int j = rl; j < n_old; j += rpp) {
+      const uint2* src = reinterpret_cast<const uint2*>(cache + (size_t)((lo + j) % C) * H1) + vl * (sizeof(CT) / 2);
+      uint2* dst = reinterpret_cast<uint2*>(rows + (size_t)j * H1) + vl * (sizeof(CT) / 2);
+      dst[0] = __ldcs(src);
+      if (sizeof(CT) == 4) dst[1] = __ldcs(src + 1);
+    }
+  }
+  __syncthreads();   // every old row is in shared memory before a recycled slot of the ring is overwritten
+  // 2. the T new rows: rounded to the cache type, into the cache and into shared memory
+  for (int i = tid; i < T * H1; i += SEQ_THREADS) {
+    const int k = i / H1, ch = i - k * H1;
+    const float q = a.q_new[((size_t)b * T + k) * H1 + ch];
+    OnesCache<CT>::store1(cache + (size_t)((count0 + k) % C) * H1 + ch, q);
+    OnesCache<CT>::store1(rows + (size_t)(n_old + k) * H1 + ch, q);
+  }
+  __syncthreads();
+  // 3. step k sees rows [cnt_k - n_k, cnt_k), cnt_k = count0 + k + 1
+  for (int k = 0; k < T; ++k) {
+    const int cnt = count0 + k + 1;
+    const int n = min(cnt, N);
+    const int j0 = cnt - n - lo, j1 = cnt - lo;          // row indices in shared memory
+    const size_t col = (size_t)k * a.sstride + (size_t)b * H1 + vl * 4;
+    float su[4] = {0.f, 0.f, 0.f, 0.f}, sp[4] = {0.f, 0.f, 0.f, 0.f};
+    float* rbuf = red + (size_t)(k & 1) * 2 * rpp * H1;
+    if (rl < rpp) {
+      const float4 e4 = *reinterpret_cast<const float4*>(a.wE + col);
+      const float ec[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll 4
+      for (int j = j0 + rl; j < j1; j += rpp) {
+        float q[4];
+        const CT* rp = rows + (size_t)j * H1 + vl * 4;
+        if (sizeof(CT) == 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(rp);
+          q[0] = t4.x; q[1] = t4.y; q[2] = t4.z; q[3] = t4.w;
+        } else {
+          const uint2 t2 = *reinterpret_cast<const uint2*>(rp);
+          q[0] = __uint_as_float(t2.x << 16); q[1] = __uint_as_float(t2.x & 0xffff0000u);
+          q[2] = __uint_as_float(t2.y << 16); q[3] = __uint_as_float(t2.y & 0xffff0000u);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float d;
+          su[c] += ones_eval<ACT>(ec[c], q[c], d);
+          if (REC) sp[c] += d;
+        }
+      }
+      *reinterpret_cast<float4*>(rbuf + (size_t)rl * H1 + vl * 4) = make_float4(su[0], su[1], su[2], su[3]);
+      if (REC) *reinterpret_cast<float4*>(rbuf + (size_t)(rpp + rl) * H1 + vl * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    __syncthreads();
+    if (rl == 0) {
+      float g[4] = {0.f, 0.f, 0.f, 0.f}, pp[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < rpp; ++r) {
+        const float4 u4 = *reinterpret_cast<const float4*>(rbuf + (size_t)r * H1 + vl * 4);
+        g[0] += u4.x; g[1] += u4.y; g[2] += u4.z; g[3] += u4.w;
+        if (REC) {
+          const float4 p4 = *reinterpret_cast<const float4*>(rbuf + (size_t)(rpp + r) * H1 + vl * 4);
+          pp[0] += p4.x; pp[1] += p4.y; pp[2] += p4.z; pp[3] += p4.w;
+        }
+      }
+      // h_t of the step's own node (row j1 - 1)
+      const float4 e4 = *reinterpret_cast<const float4*>(a.wE + col);
+      const CT* rp = rows + (size_t)(j1 - 1) * H1 + vl * 4;
+      float d;
+      const float4 ht = make_float4(ones_eval<ACT>(e4.x, OnesCache<CT>::load1(rp), d), ones_eval<ACT>(e4.y, OnesCache<CT>::load1(rp + 1), d),
+                                    ones_eval<ACT>(e4.z, OnesCache<CT>::load1(rp + 2), d), ones_eval<ACT>(e4.w, OnesCache<CT>::load1(rp + 3), d));
+      *reinterpret_cast<float4*>(a.wG + col) = make_float4(g[0], g[1], g[2], g[3]);
+      if (REC) *reinterpret_cast<float4*>(a.wP + col) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      *reinterpret_cast<float4*>(a.wht + col) = ht;
+    }
+    // red is double-buffered by k & 1: the next step's partial sums go to the other half, and the barrier of step
+    // k + 1 orders its reducers behind the writers of step k + 2
+  }
+}
+
 // ---- window-level backward -------------------------------------------------------------------------
 struct OnesWinArgs {
   gcm_dense_state st;
@@ -748,6 +884,69 @@ extern "C" int gcm_to_bf16(const float* in, void* out, long long n, void* stream
   const long long thr = (n + 3) / 4;
   k_to_bf16<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
   return gcm_check_launch("k_to_bf16");
+}
+
+// ---- sequence entry ---------------------------------------------------------------------------------
+extern "C" int gcm_dense_ones_seq_update(const gcm_dense_state* st, const float* x_seq, long long stride_b,
+                                         long long stride_t, int T, const float* xsum_in, float* wS,
+                                         long long step_stride, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_seq_update")) return rc;
+  GCM_REQUIRE(x_seq && xsum_in && wS && T >= 1 && stride_b % 4 == 0 && stride_t % 4 == 0 &&
+                  step_stride >= (long long)st->B * st->F,
+              "dense_ones_seq_update: bad arguments");
+  if (st->B == 0) return GCM_OK;
+  const long long work = (long long)st->B * (st->F / 4);
+  k_ones_seq_update<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, x_seq, stride_b, stride_t, T,
+                                                                                      xsum_in, wS, step_stride);
+  if (int rc = gcm_check_launch("k_ones_seq_update")) return rc;
+  k_ones_bump_n<<<(st->B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st->count, st->B, T);
+  return gcm_check_launch("k_ones_bump_n");
+}
+
+static size_t ones_seq_smem(int N, int T, int H1, int cache_type) {
+  const size_t rows = (((size_t)(N + T) * H1 * (cache_type == GCM_CACHE_BF16 ? 2 : 4)) + 15) & ~(size_t)15;
+  const int rpp = SEQ_THREADS / (H1 / 4);
+  return rows + (size_t)4 * rpp * H1 * 4;
+}
+
+extern "C" long long gcm_dense_ones_seq_smem(int N, int T, int H1, int cache_type) {
+  return (long long)ones_seq_smem(N, T, H1, cache_type);
+}
+
+template <typename CT, int ACT, bool REC>
+static int ones_launch_seq(const OnesSeqArgs& a, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024) {
+    static bool done = false;   // per instantiation
+    if (!done) {
+      if (cudaFuncSetAttribute(k_ones_window_fwd<CT, ACT, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+          cudaSuccess) {
+        gcm_set_error("k_ones_window_fwd: cannot raise the dynamic shared memory limit");
+        return GCM_ERR_CUDA;
+      }
+      done = true;
+    }
+  }
+  k_ones_window_fwd<CT, ACT, REC><<<a.st.B, SEQ_THREADS, smem, s>>>(a);
+  return GCM_OK;
+}
+
+extern "C" int gcm_dense_ones_window_fwd(const gcm_dense_state* st, int H1, int act1, int cache_type, void* cache, int T,
+                                         const float* wE, const float* q_new, float* wG, float* wP, float* wht,
+                                         long long step_stride, void* stream) {
+  if (int rc = ones_check_state(st, "dense_ones_window_fwd")) return rc;
+  if (int rc = ones_check_cache(H1, act1, cache_type, "dense_ones_window_fwd")) return rc;
+  GCM_REQUIRE(cache && wE && q_new && wG && wht && T >= 1 && step_stride >= (long long)st->B * H1,
+              "dense_ones_window_fwd: bad arguments");
+  const size_t smem = ones_seq_smem(st->N, T, H1, cache_type);
+  GCM_REQUIRE(smem <= 220 * 1024, "dense_ones_window_fwd: (N + T) * H1 rows do not fit in shared memory");
+  if (st->B == 0) return GCM_OK;
+  OnesSeqArgs a{*st, H1, T, cache, wE, q_new, wG, wP, wht, step_stride};
+  int rc = GCM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (wP) ONES_DISPATCH(cache_type, act1, (rc = ones_launch_seq<CT, ACT, true>(a, smem, s)));
+  else ONES_DISPATCH(cache_type, act1, (rc = ones_launch_seq<CT, ACT, false>(a, smem, s)));
+  if (rc) return rc;
+  return gcm_check_launch("k_ones_window_fwd");
 }
 
 extern "C" int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream) {

@@ -244,6 +244,57 @@ class DenseGCM(torch.nn.Module):
                 belief = feats[torch.arange(B, device=x.device), num_nodes - 1]
         return belief, DenseHidden(state, token)
 
+    def forward_sequence(self, x_seq, hidden):
+        """T steps at once: x_seq [B, T, F] -> (beliefs [B, T, H], hidden).  Same results as
+        `for t in range(T): belief_t, hidden = self(x_seq[:, t], hidden)` (the loop of RayDenseGCM.forward,
+        reference ray_gcm.py:200-202), which is also what runs for configurations without a fused sequence kernel.
+        DenseEdge-only states take the T steps in five launches (gcm.ones: the per-node cache is read once)."""
+        assert x_seq.dim() == 3, "x_seq must be [B, T, obs_size]"
+        T = x_seq.shape[1]
+
+        def loop(hidden):
+            outs = []
+            for t in range(T):
+                out, hidden = self(x_seq[:, t], hidden)
+                outs.append(out)
+            return torch.stack(outs, dim=1), hidden
+
+        plan = self.fused_plan()
+        if plan is None or not plan.ones or T < 2 or not x_seq.is_cuda or x_seq.dtype != torch.float32:
+            return loop(hidden)
+        recording = torch.is_grad_enabled() and (
+            x_seq.requires_grad or any(p.requires_grad for p in plan.gnn.params())
+            or (isinstance(hidden, DenseHidden) and hidden.token is not None))
+        if recording and T > int(self.bptt_capacity):
+            return loop(hidden)
+        # enter the state exactly as forward() does, by taking the first step through it
+        out0, hidden = self(x_seq[:, 0], hidden)
+        state = hidden.claim() if isinstance(hidden, DenseHidden) else None
+        token = hidden.token if state is not None else None
+        bf16 = ones.want_bf16(self, plan)
+        ok = (state is not None and state.dense_ok and state.rcache is not None and self._plan is plan
+              and (token is None) == (not recording) and (token is None or getattr(token, "_gcm_ones", False))
+              and ones.sequence_supported(plan, state, T - 1, bf16))
+        if ok and recording:
+            ok = state.steps - state.win.chain_start + (T - 1) <= state.C - state.N + 1
+        if not ok:
+            outs = [out0]
+            for t in range(1, T):
+                out, hidden = self(x_seq[:, t], hidden)
+                outs.append(out)
+            return torch.stack(outs, dim=1), hidden
+        rest = x_seq[:, 1:].contiguous()
+        if not DenseGCM.did_warn and state.host_count is not None and state.host_count + T - 1 > state.N:
+            print("Overflow detected, wrapping around. Will not warn again")
+            DenseGCM.did_warn = True
+        if recording:
+            beliefs, token = ones.sequence_grad(plan, state, rest, token, bf16)
+            token._gcm_ones = True
+        else:
+            beliefs = ones.sequence_nograd(plan, state, rest.detach(), bf16)
+            token = None
+        return torch.cat([out0.unsqueeze(1), beliefs.transpose(0, 1)], dim=1), DenseHidden(state, token)
+
     def _would_overflow(self, state: DenseState) -> bool:
         # host-side mirror only (no device sync): graphs started empty overflow after N steps
         return state.host_count is not None and state.host_count >= state.N

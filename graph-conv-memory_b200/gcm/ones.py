@@ -263,6 +263,65 @@ def step_nograd(plan, state, x, bf16: bool = False):
     return _forward_kernels(plan, state, x)
 
 
+def sequence_supported(plan, state, T: int, bf16: bool) -> bool:
+    """Can T steps be taken at once (gcm_dense_ones_window_fwd keeps N + T cache rows in shared memory)?"""
+    g = plan.gnn
+    if g.H1 % (8 if bf16 else 4):
+        return False
+    return int(_cabi.lib().gcm_dense_ones_seq_smem(state.N, T, g.H1, int(bool(bf16)))) <= 220 * 1024
+
+
+def _sequence_kernels(plan, state, x_seq, k0: Optional[int] = None):
+    """T steps on the in-place state from x_seq [B, T, F] (contiguous); k0 = index of the first step in the recording
+    window (None: not recording).  Returns beliefs [T, B, H2].  Same arithmetic per step as _forward_kernels."""
+    dev = state.device
+    lib = _cabi.lib()
+    g = plan.gnn
+    w = _weights(plan, dev)
+    stream = _cabi.stream_ptr(dev)
+    B, T, F = x_seq.shape
+    if k0 is not None:
+        win = state.win
+        S, E, G, P, ht = (getattr(win, n)[k0:k0 + T] for n in ("S", "E", "G", "P", "ht"))
+    else:
+        mk = lambda h: torch.empty(T, B, h, device=dev, dtype=torch.float32)
+        S, E, G, P, ht = mk(F), mk(g.H1), mk(g.H1), None, mk(g.H1)
+    _cabi.check(lib.gcm_dense_ones_seq_update(state.c_ref(), x_seq.data_ptr(), x_seq.stride(0), x_seq.stride(1), T,
+                                              state.xsum.data_ptr(), S.data_ptr(), B * F, stream),
+                "gcm_dense_ones_seq_update")
+    state.xsum = S[T - 1]
+    ca = _cache_act(plan)
+    tc_dims = g.F % 16 == 0 and g.H1 % 16 == 0 and g.H2 % 16 == 0
+    lin_c = _lin_tc32 if tc_dims else _lin2
+    lin_c(S.view(T * B, F), w["w_rel1"], bias=w["b1"], act=ca, out=E.view(T * B, g.H1))
+    q_new = torch.empty(B * T, g.H1, device=dev, dtype=torch.float32)
+    xf = x_seq.view(B * T, F)
+    if state.rc_bf16 and tc_dims:
+        _cabi.check(lib.gcm_linear_tc(xf.data_ptr(), F, F, w["w_root1"].data_ptr(), None, ca, B * T, g.H1,
+                                      q_new.data_ptr(), g.H1, 0, stream), "gcm_linear_tc")
+    else:
+        _lin2(xf, w["w_root1"], act=ca, out=q_new)
+    _cabi.check(lib.gcm_dense_ones_window_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
+                                              state.rcache.data_ptr(), T, E.data_ptr(), q_new.data_ptr(), G.data_ptr(),
+                                              None if P is None else P.data_ptr(), ht.data_ptr(), B * g.H1, stream),
+                "gcm_dense_ones_window_fwd")
+    lin_b = _lin_tc32 if (tc_dims and state.rc_bf16) else _lin2
+    beliefs = lin_b(G.view(T * B, g.H1), w["w_rel2"], ht.view(T * B, g.H1), w["w_root2"], bias=w["b2"],
+                    act=_cabi.ACT[g.act2], status=state.status)
+    state.masks_stale = True
+    state.version += 1
+    state.steps += T
+    state.max_count += T
+    if state.host_count is not None:
+        state.host_count += T
+    return beliefs.view(T, B, g.H2)
+
+
+def sequence_nograd(plan, state, x_seq, bf16: bool = False):
+    prepare(plan, state, bf16)
+    return _sequence_kernels(plan, state, x_seq)
+
+
 def _param_grads(g, grads):
     """gradients in the order of GnnPlan.params()"""
     out = []
@@ -410,9 +469,61 @@ class _OnesStepFn(torch.autograd.Function):
         return d_x, torch.zeros(1, device=dev), None, None, None
 
 
-def step_grad(plan, state, x, token, bf16: bool = False):
-    """Recording step.  Returns (belief, token)."""
-    prepare(plan, state, bf16)
+class _OnesSeqFn(torch.autograd.Function):
+    """T steps of the ones path taken at once: one node standing for the steps k0 .. k0+T-1 of the window."""
+
+    @staticmethod
+    def forward(ctx, x_seq, token, plan, state, k0):
+        beliefs = _sequence_kernels(plan, state, x_seq.detach(), k0)
+        ctx.plan, ctx.state, ctx.k0, ctx.T = plan, state, k0, x_seq.shape[1]
+        ctx.chain_id = state.win.chain_id
+        ctx.save_for_backward(beliefs)
+        return beliefs, torch.zeros(1, device=state.device)
+
+    @staticmethod
+    def backward(ctx, d_beliefs, d_token):
+        plan, st, k0, T = ctx.plan, ctx.state, ctx.k0, ctx.T
+        g, win, dev = plan.gnn, st.win, st.device
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        (beliefs,) = ctx.saved_tensors
+        lib = _cabi.lib()
+        stream = _cabi.stream_ptr(dev)
+        win.ensure_bwd()
+        db_ = d_beliefs.contiguous().float()
+        _cabi.check(lib.gcm_act_backward(db_.data_ptr(), beliefs.data_ptr(), _cabi.ACT[g.act2], T * st.B * g.H2,
+                                         win.do[k0:k0 + T].data_ptr(), stream), "gcm_act_backward")
+        d_x = None
+        if win.need_dx:
+            # observations require grad: finish the steps newest-first, like T single-step nodes would
+            tw = g.transposed(dev)
+            steps_total = st.steps - win.chain_start
+            if steps_total > st.C - st.N + 1:
+                raise RuntimeError(
+                    f"BPTT window too long for the node log: {steps_total} steps since the chain started but the log "
+                    f"keeps {st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
+            d_x = torch.empty(st.B, T, g.F, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+            dz = torch.empty(st.B, g.H1, device=dev, dtype=torch.float32)
+            for k in range(k0 + T - 1, k0 - 1, -1):
+                _bwd_small(plan, st, k, k + 1, k < win.kmax)
+                win.kmax = max(win.kmax, k)
+                if d_x is None:
+                    continue
+                Kc = win.kmax + 1
+                _cabi.check(lib.gcm_dense_ones_node_bwd(
+                    st.c_ref(), g.H1, _cabi.ACT[g.act1], int(st.rc_bf16), st.rcache.data_ptr(), steps_total, Kc, k,
+                    win.E.data_ptr(), win.dG.data_ptr(), win.dzo.data_ptr(), st.B * g.H1, dz.data_ptr(), stream),
+                    "gcm_dense_ones_node_bwd")
+                ds = win.dcs[k]
+                if k + st.N < Kc:
+                    ds = ds - win.dcs[k + st.N]
+                _lin2(dz, tw["w_root1_t"], ds, tw["w_rel1_t"], out=d_x[:, k - k0])
+        win.kmax = max(win.kmax, k0 + T - 1)
+        return d_x, torch.zeros(1, device=dev), None, None, None
+
+
+def _chain(plan, state, token, n_steps):
+    """Window bookkeeping shared by the recording entries: (token, index of the next step in the window)."""
     win = getattr(state, "win", None)
     if win is None:
         win = state.win = _Window(state, plan.gnn)
@@ -425,11 +536,27 @@ def step_grad(plan, state, x, token, bf16: bool = False):
         anchor = torch.zeros(1, device=state.device, requires_grad=True)
         token = _OnesRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
     k = state.steps - win.chain_start
-    if k + 1 > cap:
+    if k + n_steps > cap:
         raise RuntimeError(
             f"more than {cap} recorded steps on one hidden state; raise "
             "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
-    win.ensure_fwd(k, cap)
-    win.need_dx = win.need_dx or x.requires_grad
+    win.ensure_fwd(k + n_steps - 1, cap)
+    return token, k
+
+
+def sequence_grad(plan, state, x_seq, token, bf16: bool = False):
+    """Recording sequence entry.  Returns (beliefs [T, B, H2], token)."""
+    prepare(plan, state, bf16)
+    token, k0 = _chain(plan, state, token, x_seq.shape[1])
+    state.win.need_dx = state.win.need_dx or x_seq.requires_grad
+    beliefs, token = _OnesSeqFn.apply(x_seq, token, plan, state, k0)
+    return beliefs, token
+
+
+def step_grad(plan, state, x, token, bf16: bool = False):
+    """Recording step.  Returns (belief, token)."""
+    prepare(plan, state, bf16)
+    token, k = _chain(plan, state, token, 1)
+    state.win.need_dx = state.win.need_dx or x.requires_grad
     belief, token = _OnesStepFn.apply(x, token, plan, state, k)
     return belief, token

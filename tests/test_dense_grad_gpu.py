@@ -263,3 +263,87 @@ def test_ones_path_window_backward_wide(acts, bf16):
         got = named_grads(convs)
         for k in got:
             assert rel_err(got[k], pp[k].grad) < tol, (k, x_grad)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("x_grad", [True, False])
+def test_forward_sequence_matches_step_loop_and_oracle(bf16, x_grad):
+    """DenseGCM.forward_sequence (the caller is RayDenseGCM's loop over T, ray_gcm.py:200-202) on a
+    DenseEdge state: T steps at once must give what T forward() calls give -- beliefs, the hidden state, and every
+    gradient (fp64 oracle: 1e-5 class for the float32 cache, 2e-2 for bfloat16).  Ragged pre-filled counts; the
+    window wraps inside the sequence; a second sequence continues the same BPTT chain."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T1, T2 = 5, 40, 32, 64, 9, 7
+    T = T1 + T2
+    spec = [("dense",)]
+    acts = ("tanh", "tanh")
+    gen = torch.Generator().manual_seed(11)
+    p = oracle.make_params(F, H)
+    nn0 = torch.tensor([33, 0, 40, 17, 38])
+    nodes0 = 0.5 * torch.randn(B, N, F, generator=gen)
+    adj0 = torch.zeros(B, N, N)
+    for b in range(B):
+        nodes0[b, int(nn0[b]):] = 0
+        adj0[b, : int(nn0[b]), : int(nn0[b])] = 1
+    obs = 0.5 * torch.randn(T, B, F, generator=gen)
+    w = torch.randn(T, B, H, generator=gen)
+    o = obs.double().clone().requires_grad_(True)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    outs, o_hidden = oracle.dense_gcm_rollout(o, (nodes0.double(), adj0.double(), torch.zeros(0, dtype=torch.float64), nn0.clone()),
+                                              spec, pp, acts, graph_size=N)
+    (outs * w.double()).sum().backward()
+    tol = 2e-2 if bf16 else 5 * TOL
+    gnn, convs = make_dense_gnn(F, H, p, acts)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    mod.bptt_capacity = T
+    if bf16:
+        mod.compute_dtype = torch.bfloat16
+    x = obs.to(dev).transpose(0, 1).contiguous().requires_grad_(x_grad)            # [B, T, F]
+    hidden = (nodes0.to(dev), adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
+    b1, hidden = mod.forward_sequence(x[:, :T1], hidden)
+    assert hidden.claim().win is not None and hidden.claim().steps == T1
+    b2, hidden = mod.forward_sequence(x[:, T1:], hidden)
+    got = torch.cat([b1, b2], dim=1)                                                # [B, T, H]
+    assert got.shape == (B, T, H)
+    assert rel_err(got.transpose(0, 1), outs.detach()) < tol
+    (got.transpose(0, 1) * w.to(dev)).sum().backward()
+    if x_grad:
+        assert rel_err(x.grad.transpose(0, 1), o.grad) < tol
+    grads = named_grads(convs)
+    for k in grads:
+        assert rel_err(grads[k], pp[k].grad) < tol, k
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), o_hidden[0].float()) and torch.equal(adj.cpu(), o_hidden[1].float())
+    assert torch.equal(num_nodes.cpu(), o_hidden[3])
+
+
+def test_forward_sequence_rollout_ring_and_generic_fallback():
+    """No-grad sequences on an in-place ring (C == N): 3 x 30 steps from an empty 24-node DenseEdge graph (the window
+    wraps inside the second sequence) against the step loop of a second module; and a TemporalBackedge module, whose
+    forward_sequence is the plain loop."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T = 7, 24, 16, 32, 30
+    p = oracle.make_params(F, H)
+    gen = torch.Generator().manual_seed(3)
+    obs = (0.5 * torch.randn(B, 3 * T, F, generator=gen)).to(dev)
+    for spec in ([("dense",)], [("temporal", (1, 2), "forward")]):
+        mods = []
+        for _ in range(2):
+            gnn, _ = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+            mods.append(DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N))
+        with torch.no_grad():
+            h_seq, h_loop, seq_out, loop_out = None, None, [], []
+            for c in range(3):
+                out, h_seq = mods[0].forward_sequence(obs[:, c * T:(c + 1) * T], h_seq)
+                seq_out.append(out)
+            for t in range(3 * T):
+                out, h_loop = mods[1](obs[:, t], h_loop)
+                loop_out.append(out)
+        seq_out, loop_out = torch.cat(seq_out, dim=1), torch.stack(loop_out, dim=1)
+        assert rel_err(seq_out, loop_out) < TOL
+        for a, b in zip(tuple(h_seq), tuple(h_loop)):
+            assert torch.equal(a, b)

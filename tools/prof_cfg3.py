@@ -7,6 +7,7 @@ import bench
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 cache = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+seq = len(sys.argv) > 3 and sys.argv[3] == "seq"
 dev = torch.device("cuda:0")
 N, F, H, T = 256, 128, 128, 64
 mod = bench.build_dense(dev, N, F, H, [("dense",)])
@@ -15,6 +16,7 @@ mod.compute_dtype = torch.bfloat16 if cache == "bf16" else None
 opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
 gen = torch.Generator().manual_seed(1003)
 obs = (0.5 * torch.randn(T, B, F, generator=gen)).to(dev)
+obs_bt = obs.transpose(0, 1).contiguous()
 nn0 = torch.full((B,), N - T, dtype=torch.long, device=dev)
 nodes0 = 0.5 * torch.randn(B, N, F, device=dev)
 nodes0[:, N - T:] = 0
@@ -25,10 +27,14 @@ adj0[:, : N - T, : N - T] = 1
 def window():
     hidden = (nodes0, adj0, torch.zeros(0, device=dev), nn0)
     opt.zero_grad(set_to_none=True)
-    tot = 0
-    for t in range(T):
-        belief, hidden = mod(obs[t], hidden)
-        tot = tot + belief.mean()
+    if seq:
+        beliefs, hidden = mod.forward_sequence(obs_bt, hidden)
+        tot = beliefs.mean() * T
+    else:
+        tot = 0
+        for t in range(T):
+            belief, hidden = mod(obs[t], hidden)
+            tot = tot + belief.mean()
     (tot / T).backward()
     opt.step()
 
