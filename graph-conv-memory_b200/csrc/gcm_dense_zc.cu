@@ -10,7 +10,8 @@
 // which links t to the DISSIMILAR nodes (similarity < max_distance), that is ~n rows with ~n/2 neighbours each.
 // Here z lives in HBM next to the node log (zcache [B, C, H1]) and a step is two streaming passes per graph:
 //   pass 1 over the node rows  : distance + threshold -> mask row of t, and the aggregation of t's neighbours
-//                                (the rows are in registers anyway); then z_t, and u = W_rel1 x_e if a node leaves
+//                                (rows staged in shared memory tiles, one thread per row for the distance, one thread
+//                                per feature column for the sums); then z_t, and u = W_rel1 x_e if a node leaves
 //   pass 2 over the cached rows: z_i -= u for the rows that had e as in-neighbour (one mask bit each), and
 //                                G = sum_{i in N(t)} act1(z_i);  belief = act2(W_rel2 G + W_root2 act1(z_t) + b2)
 // = n (F + 2 H1) 4 bytes per graph-step instead of an n x n/2 gather plus a [n, 2F] x [2F, H1] product.
@@ -19,7 +20,6 @@
 #include "gcm_common.cuh"
 
 constexpr int ZC_THREADS = 256;
-constexpr int ZC_NW = ZC_THREADS / 32;
 
 struct ZcArgs {
   gcm_dense_state st;
@@ -29,6 +29,7 @@ struct ZcArgs {
   float* zcache;     // [B, C, H1]
   float* belief;
   int32_t* status;
+  int tile_rows;     // rows of the node log staged in shared memory at a time (<= ZC_THREADS)
 };
 
 template <int FR>
@@ -38,15 +39,17 @@ __global__ void __launch_bounds__(ZC_THREADS) k_step_dist_zc(const ZcArgs a) {
   float* cur = zs;                       // [F]   the observation
   float* xe = cur + F;                   // [F]   the node that leaves the window
   float* agg = xe + F;                   // [F]   sum of t's in-neighbours
-  float* part = agg + F;                 // [ZC_NW][F] / [8][H1] partial sums
-  const int pw = F > H1 ? F : H1;
-  float* u = part + ZC_NW * pw;          // [H1]  W_rel1 x_e
+  float* part = agg + F;                 // [ZC_THREADS]       column sums per row group (pass 1)
+  float* part2 = part + ZC_THREADS;      // [4 ZC_THREADS]     partial G per row lane (pass 2)
+  float* u = part2 + 4 * ZC_THREADS;     // [H1]  W_rel1 x_e
   float* zt = u + H1;                    // [H1]
   float* ht = zt + H1;                   // [H1]
   float* G = ht + H1;                    // [H1]
   uint32_t* rowmask = reinterpret_cast<uint32_t*>(G + H1);   // [W]
+  int* hitf = reinterpret_cast<int*>(rowmask + W);           // [tile_rows]
+  float* tile = reinterpret_cast<float*>(hitf + a.tile_rows);   // [tile_rows][F + 1]
 
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, tid = threadIdx.x;
   const int cnt = __ldcg(a.st.count + b);
   const int tpos = cnt;
   const int lt = min(cnt, N - 1);
@@ -66,106 +69,90 @@ __global__ void __launch_bounds__(ZC_THREADS) k_step_dist_zc(const ZcArgs a) {
   __syncthreads();
   for (int f = tid; f < F; f += ZC_THREADS) nodes_b[(size_t)tslot * F + f] = cur[f];   // node write (gcm.py:274)
 
-  // ---- pass 1: distance + threshold (same arithmetic as gcm_select_distance) fused with the aggregation ----
+  // ---- pass 1: distance + threshold fused with the aggregation of t's in-neighbours ----
+  // Rows are staged through shared memory in tiles (coalesced 16-byte loads); ONE THREAD PER ROW forms the distance
+  // (no shuffle reductions: the warp-per-row version spent ~100 warp instructions per row and the kernel was
+  // issue-bound, profiles/c4_step_dist_zc_r1.md), then thread = (feature column, row group) adds up the selected
+  // rows of the tile.
   {
     const bool learned = sel.dist_param != nullptr;
     const float thr = learned ? 1.0f : sel.max_distance;
     const float scale = learned ? 1.0f / fabsf(__ldg(sel.dist_param)) : 1.0f;
+    const int TR = a.tile_rows, FS = F + 1;                 // tile row stride: odd -> conflict-free column walks
     float cur_norm = 0.0f;
     if (sel.kind == GCM_SEL_COSINE) {
-      float s = 0.0f;
-      for (int f = lane; f < F; f += 32) s += cur[f] * cur[f];
-      cur_norm = fmaxf(sqrtf(gcm_warp_sum(s)), 1e-8f);
+      float sq = 0.0f;
+      for (int f = 0; f < F; ++f) sq = fmaf(cur[f], cur[f], sq);
+      cur_norm = fmaxf(sqrtf(sq), 1e-8f);
     }
-    float acc[FR];
-#pragma unroll
-    for (int k = 0; k < FR; ++k) acc[k] = 0.0f;
-    // 4 rows per warp iteration: their loads are issued together and the shuffle reductions interleave
-    constexpr int RU = 4;
-    for (int d0 = 1 + warp * RU; d0 <= lt; d0 += ZC_NW * RU) {
-      float v[RU][FR];
-      float dist[RU];
-      const float* rows[RU];
-      int slots[RU];
-#pragma unroll
-      for (int q = 0; q < RU; ++q) {
-        const int d = min(d0 + q, lt);                                 // clamped rows are recomputed, not used
-        slots[q] = tslot - d + (tslot - d < 0 ? C : 0);                // (tpos - d) mod C without a division
-        rows[q] = nodes_b + (size_t)slots[q] * F;
-#pragma unroll
-        for (int k = 0; k < FR; ++k) {
-          const int f = lane + 32 * k;
-          v[q][k] = f < F ? rows[q][f] : 0.0f;
+    const int F4 = F >> 2;                                  // host: F % 4 == 0 on this path
+    const int ngrp = ZC_THREADS / F, col = tid % F, grp = tid / F;   // column sums: ngrp row groups
+    const int rows_per_grp = (TR + ngrp - 1) / ngrp;
+    float acc = 0.0f;
+    const int half = tid & 1, prow = tid >> 1;              // two threads per row: each takes half of the features
+    const int fh = (F + 1) >> 1, f_lo = half * fh, f_hi = min(F, f_lo + fh);
+    for (int d0 = 1; d0 <= lt; d0 += TR) {
+      const int nr = min(TR, lt - d0 + 1);
+      // (fetching the next tile into registers during the work on this one cost a CTA of occupancy, 80+ registers, and
+      // was slower: 0.63 vs 0.49 ms at cfg4; four resident CTAs hide the load latency better)
+      for (int i = tid; i < nr * F4; i += ZC_THREADS) {
+        const int r = i / F4, c4 = i - r * F4;
+        const int d = d0 + r;
+        const int slot = tslot - d + (tslot - d < 0 ? C : 0);             // (tpos - d) mod C without a division
+        const float4 v = *reinterpret_cast<const float4*>(nodes_b + (size_t)slot * F + c4 * 4);
+        float* dst = tile + r * FS + c4 * 4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+      __syncthreads();
+      {
+        const bool rok = prow < nr;                        // warp-uniform up to the last partial warp; shuffles below
+        const float* row = tile + (rok ? prow : 0) * FS;   // are executed by all lanes
+        const int d = d0 + prow;
+        float dist = 0.0f;
+        if (sel.kind == GCM_SEL_EUCLIDEAN) {
+          const int slot = tslot - d + (tslot - d < 0 ? C : 0);
+          dist = rok ? __ldg(sel.dist + (size_t)b * C + slot) : 0.0f;
+        } else if (sel.kind == GCM_SEL_COSINE) {
+          float dot = 0.0f, nb = 0.0f;
+#pragma unroll 8
+          for (int f = f_lo; f < f_hi; ++f) {
+            const float v = row[f];
+            dot = fmaf(cur[f], v, dot);
+            nb = fmaf(v, v, nb);
+          }
+          dot += __shfl_xor_sync(GCM_FULL_MASK, dot, 1);
+          nb += __shfl_xor_sync(GCM_FULL_MASK, nb, 1);
+          dist = dot / (cur_norm * fmaxf(sqrtf(nb), 1e-8f));
+        } else {  // spatial
+          float sq = 0.0f;
+          for (int k = half; k < sel.slice_len; k += 2) {
+            const float df = cur[sel.a_start + k * sel.a_step] - row[sel.b_start + k * sel.b_step];
+            sq = fmaf(df, df, sq);
+          }
+          sq += __shfl_xor_sync(GCM_FULL_MASK, sq, 1);
+          dist = sqrtf(sq) * scale;
+        }
+        if (rok && half == 0) {
+          const bool hit = dist < thr;
+          hitf[prow] = hit ? 1 : 0;
+          if (hit) atomicOr(&rowmask[d >> 5], 1u << (d & 31));
         }
       }
-      if (sel.kind == GCM_SEL_EUCLIDEAN) {
-#pragma unroll
-        for (int q = 0; q < RU; ++q) dist[q] = __ldg(sel.dist + (size_t)b * C + slots[q]);
-      } else if (sel.kind == GCM_SEL_COSINE) {
-        float dot[RU], nb[RU];
-#pragma unroll
-        for (int q = 0; q < RU; ++q) {
-          dot[q] = 0.0f;
-          nb[q] = 0.0f;
-#pragma unroll
-          for (int k = 0; k < FR; ++k) {
-            const int f = lane + 32 * k;
-            if (f < F) {
-              dot[q] += cur[f] * v[q][k];
-              nb[q] += v[q][k] * v[q][k];
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int q = 0; q < RU; ++q) {
-            dot[q] += __shfl_xor_sync(GCM_FULL_MASK, dot[q], o);
-            nb[q] += __shfl_xor_sync(GCM_FULL_MASK, nb[q], o);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < RU; ++q) dist[q] = dot[q] / (cur_norm * fmaxf(sqrtf(nb[q]), 1e-8f));
-      } else {  // spatial
-        float sq[RU];
-#pragma unroll
-        for (int q = 0; q < RU; ++q) {
-          sq[q] = 0.0f;
-          for (int k = lane; k < sel.slice_len; k += 32) {
-            const float df = cur[sel.a_start + k * sel.a_step] - rows[q][sel.b_start + k * sel.b_step];
-            sq[q] += df * df;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int q = 0; q < RU; ++q) sq[q] += __shfl_xor_sync(GCM_FULL_MASK, sq[q], o);
-        }
-#pragma unroll
-        for (int q = 0; q < RU; ++q) dist[q] = sqrtf(sq[q]) * scale;
+      __syncthreads();
+      if (grp < ngrp) {
+        const int r1 = min(nr, (grp + 1) * rows_per_grp);
+        for (int r = grp * rows_per_grp; r < r1; ++r)
+          if (hitf[r]) acc += tile[r * FS + col];
       }
-#pragma unroll
-      for (int q = 0; q < RU; ++q) {
-        const int d = d0 + q;
-        if (d <= lt && dist[q] < thr) {          // warp-uniform: every lane holds the reduced value
-#pragma unroll
-          for (int k = 0; k < FR; ++k) acc[k] += v[q][k];
-          if (lane == 0) atomicOr(&rowmask[d >> 5], 1u << (d & 31));
-        }
-      }
+      __syncthreads();
     }
-#pragma unroll
-    for (int k = 0; k < FR; ++k) {
-      const int f = lane + 32 * k;
-      if (f < F) part[warp * F + f] = acc[k];
+    if (grp < ngrp) part[grp * F + col] = acc;
+    __syncthreads();
+    for (int f = tid; f < F; f += ZC_THREADS) {
+      float sum = 0.0f;
+      for (int g = 0; g < ngrp; ++g) sum += part[g * F + f];
+      agg[f] = sum;
     }
-  }
-  __syncthreads();
-  for (int f = tid; f < F; f += ZC_THREADS) {
-    float s = 0.0f;
-#pragma unroll
-    for (int w = 0; w < ZC_NW; ++w) s += part[w * F + f];
-    agg[f] = s;
   }
   // commit row t of the adjacency (a recycled slot is fully overwritten) and the counter
   for (int w = tid; w < W; w += ZC_THREADS) {
@@ -193,50 +180,54 @@ __global__ void __launch_bounds__(ZC_THREADS) k_step_dist_zc(const ZcArgs a) {
   __syncthreads();
 
   // ---- pass 2 over the cached rows: eviction correction + layer-2 aggregation ----
+  // thread = (row lane, 4 channels): one 16-byte load per cached row and thread, 4 rows in flight per thread
   {
-    const int hp = H1 <= 32 ? 32 : (H1 <= 64 ? 64 : 128);   // threads per row
-    const int rl = ZC_THREADS / hp, rr = tid / hp, ch = tid - rr * hp;
-    float g = 0.0f;
-    if (ch < H1) {
-      // 8 rows per iteration: all loads (cached row + the one mask word that says whether the leaving node was an
-      // in-neighbour) are issued before the first use, so a thread keeps 16 requests in flight
-      constexpr int U = 8;
+    const int tpr = H1 >> 2;                                  // host: H1 % 4 == 0 on this path
+    const int rpp = ZC_THREADS / tpr, rr = tid / tpr, vl = tid - rr * tpr;
+    float g4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rr < rpp) {
+      const float4 u4 = *reinterpret_cast<const float4*>(u + vl * 4);
       const int off_bit0 = N;    // offset of e in row (tpos - d)'s past mask is N - d
-      for (int d0 = 1 + rr; d0 <= lt; d0 += rl * U) {
-        float z[U];
+      constexpr int U = 4;
+      for (int d0 = 1 + rr; d0 <= lt; d0 += rpp * U) {
+        float4 z[U];
         uint32_t m[U];
         int slot[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-          const int d = d0 + q * rl;
-          z[q] = 0.0f;
+          const int d = d0 + q * rpp;
+          z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           m[q] = 0u;
           slot[q] = 0;
           if (d <= lt) {
             slot[q] = tslot - d + (tslot - d < 0 ? C : 0);       // (tpos - d) mod C without a division
-            z[q] = zc_b[(size_t)slot[q] * H1 + ch];
+            z[q] = *reinterpret_cast<const float4*>(zc_b + (size_t)slot[q] * H1 + vl * 4);
             if (evict) m[q] = gcm_ld_mask(masks_b + ((size_t)slot[q] * 2 + 0) * W + ((off_bit0 - d) >> 5));
           }
         }
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-          const int d = d0 + q * rl;
+          const int d = d0 + q * rpp;
           if (d <= lt) {
             if (evict && ((m[q] >> ((off_bit0 - d) & 31)) & 1u)) {
-              z[q] -= u[ch];
-              zc_b[(size_t)slot[q] * H1 + ch] = z[q];
+              z[q].x -= u4.x; z[q].y -= u4.y; z[q].z -= u4.z; z[q].w -= u4.w;
+              *reinterpret_cast<float4*>(zc_b + (size_t)slot[q] * H1 + vl * 4) = z[q];
             }
-            if ((rowmask[d >> 5] >> (d & 31)) & 1u) g += gcm_act_fast(z[q], a.gnn.act1);
+            if ((rowmask[d >> 5] >> (d & 31)) & 1u) {
+              float hv[4] = {z[q].x, z[q].y, z[q].z, z[q].w};
+              gcm_act_fast_vec(hv, a.gnn.act1);
+              g4[0] += hv[0]; g4[1] += hv[1]; g4[2] += hv[2]; g4[3] += hv[3];
+            }
           }
         }
       }
-      part[rr * H1 + ch] = g;
+      *reinterpret_cast<float4*>(part2 + (size_t)rr * H1 + vl * 4) = make_float4(g4[0], g4[1], g4[2], g4[3]);
     }
     __syncthreads();
     if (tid < H1) {
-      float s = 0.0f;
-      for (int r = 0; r < rl; ++r) s += part[r * H1 + tid];
-      G[tid] = s;
+      float sum = 0.0f;
+      for (int r = 0; r < rpp; ++r) sum += part2[r * H1 + tid];
+      G[tid] = sum;
     }
   }
   __syncthreads();
@@ -275,8 +266,9 @@ extern "C" int gcm_dense_step_fwd_zc(const gcm_dense_state* st, const float* obs
   ZcArgs a;
   a.st = *st; a.obs = obs; a.sel = *sel; a.gnn = *gnn; a.zcache = zcache; a.belief = belief; a.status = status;
   const int F = st->F, H1 = gnn->H1;
-  const int pw = F > H1 ? F : H1;
-  const size_t smem = ((size_t)3 * F + (size_t)ZC_NW * pw + 4 * H1 + st->W + 8) * 4;
+  GCM_REQUIRE(F % 4 == 0 && H1 % 4 == 0, "dense_step_fwd_zc: F and H1 must be multiples of 4");
+  a.tile_rows = F <= 64 ? 128 : 64;
+  const size_t smem = ((size_t)3 * F + 5 * ZC_THREADS + 4 * H1 + st->W + a.tile_rows + (size_t)a.tile_rows * (F + 1) + 8) * 4;
   const int fr = (F + 31) / 32;
   cudaStream_t s = (cudaStream_t)stream;
   switch (fr) {

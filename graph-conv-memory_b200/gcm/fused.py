@@ -204,7 +204,7 @@ class FusedPlan:
         self.ones = _ones.plan_supports(self)          # DenseEdge-only chain: the all-ones fast path (gcm.ones)
         # exactly one distance selector: per-node pre-activation cache (zc_step)
         self.zc = (len(sels) == 1 and sels[0].kind in (_cabi.SEL_EUCLIDEAN, _cabi.SEL_COSINE, _cabi.SEL_SPATIAL)
-                   and max(gnn.F, gnn.H1, gnn.H2) <= 128)
+                   and max(gnn.F, gnn.H1, gnn.H2) <= 128 and gnn.F % 4 == 0 and gnn.H1 % 4 == 0)
         # layer-1 row cache: forward-only temporal chains with 32 hidden channels (the library re-checks the shape)
         self.max_hop, self.hc_ring = 0, 0
         if (self.temporal_key is not None and gnn.H1 == 32 and gnn.H2 == 32
