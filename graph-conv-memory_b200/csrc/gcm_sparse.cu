@@ -51,6 +51,8 @@ struct EdgeGenArgs {
   int64_t E;
   const int64_t* flat_off;  // pass 2, optional: [B+1] exclusive cumsum of T + tau (the flat node numbering)
   int64_t* flat_col;        // pass 2, optional: [E] flat id of every edge's source = flat_off[b] + source
+  uint16_t* hits;           // pass 1, optional: [n_new, hit_cap] the first hit_cap sources of every new node, ascending
+  int hit_cap;              //   (gcm_sparse_expand_edges turns them into edges without a second search)
 };
 
 __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
   for (int s = s_begin + warp; s < s_end; s += nwarps) {
     const int64_t slot = a.new_off[b] + (s - t0);
     int64_t base = a.edges ? a.edge_off[slot] : 0;
+    if (a.edges && a.hit_cap > 0 && a.edge_off[slot + 1] - base <= a.hit_cap) continue;   // done by the expansion
     int count = 0;
     for (int k0 = 0; k0 < s; k0 += 32) {
       const int k = k0 + lane;
@@ -95,6 +98,9 @@ __global__ void __launch_bounds__(256) k_sparse_edges(const EdgeGenArgs a) {
         a.edges[a.E + e] = s;
         a.edges[2 * a.E + e] = k;
         if (a.flat_col) a.flat_col[e] = a.flat_off[b] + k;
+      } else if (a.hits && hit) {
+        const int at = count + __popc(bal & ((1u << lane) - 1u));
+        if (at < a.hit_cap) a.hits[slot * a.hit_cap + at] = (uint16_t)k;
       }
       base += __popc(bal);
       count += __popc(bal);
@@ -211,6 +217,10 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   uint32_t* my = bits + warp * W;
   const int wpl = (W + 31) / 32;                   // bitmask words per lane (contiguous chunk)
   for (int s = s_begin + warp; s < s_end; s += nwarps) {
+    if (a.edges && a.hit_cap > 0) {   // pass 2 after an expansion: only the nodes whose list overflowed are searched again
+      const int64_t sl = a.new_off[b] + (s - t0);
+      if (a.edge_off[sl + 1] - a.edge_off[sl] <= a.hit_cap) continue;
+    }
     for (int w = lane; w < W; w += 32) my[w] = 0u;
     __syncwarp();
     if (lane < a.n_hops) {
@@ -254,6 +264,19 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
     const int64_t slot = a.new_off[b] + (s - t0);
     if (!a.edges) {
       if (lane == 31) a.deg[slot] = incl;
+      if (a.hits) {
+        int at = incl - cnt;
+        for (int j = 0; j < wpl; ++j) {
+          const int w = lane * wpl + j;
+          uint32_t m = w < W ? my[w] : 0u;
+          while (m && at < a.hit_cap) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            a.hits[slot * a.hit_cap + at] = (uint16_t)(w * 32 + bit);
+            ++at;
+          }
+        }
+      }
     } else {
       int64_t e = a.edge_off[slot] + (incl - cnt);
       for (int j = 0; j < wpl; ++j) {
@@ -271,6 +294,37 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
       }
     }
     __syncwarp();
+  }
+}
+
+// Pass 2 without a search: the per-sink source lists written by pass 1 become the coalesced edge rows
+// (batch, sink, source) and the CSR columns.  One warp per new node; lanes write consecutive edges.
+struct EdgeExpandArgs {
+  const int64_t* T; const int64_t* taus; const int64_t* new_off;
+  const uint16_t* hits; int hit_cap;
+  const int64_t* edge_off; int64_t* edges; int64_t E;
+  const int64_t* flat_off; int64_t* flat_col;
+};
+constexpr int EX_SINKS = 256;
+__global__ void __launch_bounds__(256) k_sparse_edges_expand(const EdgeExpandArgs a) {
+  const int b = blockIdx.x;
+  const int t0 = (int)a.T[b], tau = (int)a.taus[b];
+  const int k_begin = blockIdx.y * EX_SINKS, k_end = min(tau, k_begin + EX_SINKS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t fo = a.flat_col ? a.flat_off[b] : 0;
+  for (int k = k_begin + warp; k < k_end; k += 8) {
+    const int64_t slot = a.new_off[b] + k;
+    const int64_t e0 = a.edge_off[slot];
+    const int deg = (int)(a.edge_off[slot + 1] - e0);
+    if (deg > a.hit_cap) continue;                       // list overflowed: left to the searching pass
+    const uint16_t* h = a.hits + slot * a.hit_cap;
+    for (int i = lane; i < deg; i += 32) {
+      const int64_t src = h[i];
+      a.edges[e0 + i] = b;
+      a.edges[a.E + e0 + i] = t0 + k;
+      a.edges[2 * a.E + e0 + i] = src;
+      if (a.flat_col) a.flat_col[e0 + i] = fo + src;
+    }
   }
 }
 
@@ -603,7 +657,8 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
                                       const int64_t* new_off, int B, int N, int F, int tmax, const int32_t* hops,
                                       int n_hops, int use_radius, int pos_start, int pos_step, int pos_len,
                                       float radius, int32_t* deg, const int64_t* edge_off, int64_t* edges,
-                                      int64_t E, const int64_t* flat_off, int64_t* flat_col, void* stream) {
+                                      int64_t E, const int64_t* flat_off, int64_t* flat_col, uint16_t* hits,
+                                      int hit_cap, void* stream) {
   GCM_REQUIRE(T && taus && new_off && B >= 0 && N >= 1 && F >= 1, "sparse_build_edges: bad arguments");
   GCM_REQUIRE(n_hops >= 0 && n_hops <= GCM_MAX_HOPS && (n_hops == 0 || hops), "sparse_build_edges: n_hops=%d", n_hops);
   GCM_REQUIRE((edges == nullptr) == (edge_off == nullptr), "sparse_build_edges: edges and edge_off go together");
@@ -625,6 +680,8 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
   a.use_radius = use_radius; a.pos_start = pos_start; a.pos_step = pos_step; a.pos_len = pos_len;
   a.radius = radius; a.deg = deg; a.edge_off = edge_off; a.edges = edges; a.E = E;
   a.flat_off = flat_off; a.flat_col = flat_col;
+  GCM_REQUIRE(!hits || (!edges && hit_cap >= 1 && N <= 65536), "sparse_build_edges: hits belong to pass 1 (N <= 65536)");
+  a.hits = hits; a.hit_cap = hit_cap;   // pass 2 with hit_cap > 0: nodes with at most hit_cap sources are skipped
   // radius selector on graphs large enough for the pair test to dominate: spatial hash
   const bool hash_fits = N <= 65535 && radius > 0.0f && radius < 1.0e30f && eh_smem_bytes(N, pos_len) <= 160 * 1024;
   if (use_radius && hash_fits && (g_edge_builder == GCM_EB_HASH || (g_edge_builder == GCM_EB_AUTO && N >= 256))) {
@@ -708,4 +765,17 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
   GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
   k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
   return gcm_check_launch("k_graphconv_bwd_gather");
+}
+
+extern "C" int gcm_sparse_expand_edges(const int64_t* T, const int64_t* taus, const int64_t* new_off, int B, int tmax,
+                                       const uint16_t* hits, int hit_cap, const int64_t* edge_off, int64_t* edges,
+                                       int64_t E, const int64_t* flat_off, int64_t* flat_col, void* stream) {
+  GCM_REQUIRE(T && taus && new_off && hits && edge_off && edges && hit_cap >= 1 && B >= 0 && tmax >= 0 && E >= 0,
+              "sparse_expand_edges: bad arguments");
+  GCM_REQUIRE(!flat_col || flat_off, "sparse_expand_edges: flat_col needs flat_off");
+  if (B == 0 || tmax == 0 || E == 0) return GCM_OK;
+  EdgeExpandArgs a{T, taus, new_off, hits, hit_cap, edge_off, edges, E, flat_off, flat_col};
+  dim3 grid(B, (tmax + EX_SINKS - 1) / EX_SINKS);
+  k_sparse_edges_expand<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  return gcm_check_launch("k_sparse_edges_expand");
 }

@@ -96,7 +96,8 @@ _SIGNATURES = {
     "gcm_select_dense": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(SelectorC), _P]),
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
-                                    _P, _P, _L, _P, _P, _P]),
+                                    _P, _P, _L, _P, _P, _P, _I, _P]),
+    "gcm_sparse_expand_edges": (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P, _L, _P, _P, _P]),
     "gcm_dense_ones_update": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P]),
     "gcm_dense_ones_xsum": (_I, [C.POINTER(DenseStateC), _P, _P]),
     "gcm_linear2": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P,

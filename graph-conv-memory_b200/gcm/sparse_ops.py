@@ -66,6 +66,9 @@ class _WriteFlattenFn(torch.autograd.Function):
         return d_nodes, d_x, None, None, None, None
 
 
+HIT_CAP = 64     # sources kept per new node by pass 1 of the edge builder (128 bytes per node)
+
+
 def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_off: torch.Tensor, n_new: int,
                 tmax: int, hops: Sequence[int], radius: Optional[Tuple[slice, float]],
                 flat_off: Optional[torch.Tensor] = None):
@@ -96,16 +99,25 @@ def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_of
     deg = torch.empty(n_new, dtype=torch.int32, device=dev)
     args = (nodes_c.data_ptr(), T.data_ptr(), taus.data_ptr(), new_off.data_ptr(), B, N, F, tmax, hops_c,
             len(hops_t), use_r, p0, pst, pl, float(rad))
-    _cabi.check(lib.gcm_sparse_build_edges(*args, deg.data_ptr(), None, None, 0, None, None, stream),
-                "gcm_sparse_build_edges")
+    # pass 1 also keeps every new node's sources as a short list (uint16, HIT_CAP per node): if no node has more,
+    # pass 2 is a plain expansion of those lists instead of a second search
+    hits = torch.empty(n_new, HIT_CAP, dtype=torch.int16, device=dev) if N <= 65536 else None
+    _cabi.check(lib.gcm_sparse_build_edges(*args, deg.data_ptr(), None, None, 0, None, None, _cabi.ptr(hits), HIT_CAP,
+                                           stream), "gcm_sparse_build_edges")
     edge_off = _excl_cumsum(deg)
-    E = int(edge_off[-1].item())
+    E, max_deg = (int(v) for v in torch.stack([edge_off[-1], deg.max().long()]).tolist())
     edges = torch.empty(3, E, dtype=torch.long, device=dev)
     flat_col = torch.empty(E, dtype=torch.long, device=dev) if flat_off is not None else None
-    if E:
+    if E and hits is not None:
+        _cabi.check(lib.gcm_sparse_expand_edges(T.data_ptr(), taus.data_ptr(), new_off.data_ptr(), B, tmax,
+                                                hits.data_ptr(), HIT_CAP, edge_off.data_ptr(), edges.data_ptr(), E,
+                                                _cabi.ptr(flat_off), _cabi.ptr(flat_col), stream),
+                    "gcm_sparse_expand_edges")
+    if E and (hits is None or max_deg > HIT_CAP):
+        # nodes with more than HIT_CAP sources (or all of them without lists) are searched a second time
         _cabi.check(lib.gcm_sparse_build_edges(*args, None, edge_off.data_ptr(), edges.data_ptr(), E,
-                                               _cabi.ptr(flat_off), _cabi.ptr(flat_col), stream),
-                    "gcm_sparse_build_edges")
+                                               _cabi.ptr(flat_off), _cabi.ptr(flat_col), None,
+                                               0 if hits is None else HIT_CAP, stream), "gcm_sparse_build_edges")
     if flat_off is None:
         return edges
     return edges, edge_off, flat_col

@@ -317,11 +317,19 @@ int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, con
  * in-degree of every new node to deg [n_new] (ordered by b, then s; new_off = exclusive cumsum of
  * taus, [B+1]); with edge_off = exclusive cumsum of deg ([n_new+1]) the second call fills
  * edges int64 [3, E] and, if flat_col != NULL, flat_col[e] = flat_off[b] + source (flat_off [B+1] = exclusive cumsum
- * of T + tau: the source's row in the flat node array of util.py:426-452, i.e. the CSR column of GraphConv). */
+ * of T + tau: the source's row in the flat node array of util.py:426-452, i.e. the CSR column of GraphConv).
+ * One-search variant: pass 1 with hits != NULL also stores the first hit_cap sources of every new node (uint16
+ * [n_new, hit_cap], ascending); gcm_sparse_expand_edges then writes edges / flat_col of every node with at most hit_cap
+ * sources from those lists and edge_off, and the second (searching) call, given the same hit_cap (hits = NULL), only
+ * handles the nodes whose list overflowed (not needed at all if max(deg) <= hit_cap). */
 int gcm_sparse_build_edges(const float* nodes, const int64_t* T, const int64_t* taus, const int64_t* new_off,
                            int B, int N, int F, int tmax, const int32_t* hops, int n_hops, int use_radius,
                            int pos_start, int pos_step, int pos_len, float radius, int32_t* deg,
-                           const int64_t* edge_off, int64_t* edges, int64_t E, const int64_t* flat_off, int64_t* flat_col, void* stream);
+                           const int64_t* edge_off, int64_t* edges, int64_t E, const int64_t* flat_off, int64_t* flat_col, uint16_t* hits,
+                           int hit_cap, void* stream);
+int gcm_sparse_expand_edges(const int64_t* T, const int64_t* taus, const int64_t* new_off, int B, int tmax,
+                            const uint16_t* hits, int hit_cap, const int64_t* edge_off, int64_t* edges, int64_t E,
+                            const int64_t* flat_off, int64_t* flat_col, void* stream);
 
 /* Which kernel evaluates the radius selector (process-wide).  AUTO: all-pairs test for small graphs, spatial
  * hash (cells of side `radius`, 3 x 3 neighbourhood, same float comparison) from N = 256.  Both produce the

@@ -190,10 +190,22 @@ def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
     try:
         for name, which in (("pairs", _cabi.EB_PAIRS), ("hash", _cabi.EB_HASH)):
             _cabi.check(lib.gcm_set_edge_builder(which), "gcm_set_edge_builder")
-            got[name] = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, (1, 3), (slice(1, 1 + PL), radius))
-            want_kernel = "k_sparse_edges_hash" if name == "hash" else "k_sparse_edges"
-            assert lib.gcm_last_kernel().decode() == want_kernel
+            # HIT_CAP = 1: some node has more sources than the per-node list holds -> pass 2 searches again (the
+            # original two-pass scheme); HIT_CAP = 4096: pass 2 only expands the lists written by pass 1
+            for cap in (1, 4096):
+                sparse_ops.HIT_CAP = cap
+                flat_off = sparse_ops._excl_cumsum(T + taus)
+                e, edge_off, flat_col = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, (1, 3),
+                                                               (slice(1, 1 + PL), radius), flat_off)
+                got[(name, cap)] = e
+                want_kernel = {1: "k_sparse_edges_hash" if name == "hash" else "k_sparse_edges",
+                               4096: "k_sparse_edges_expand"}[cap]
+                assert lib.gcm_last_kernel().decode() == want_kernel      # cap 1: expansion + a second search
+                assert torch.equal(flat_col, flat_off[e[0]] + e[2])                 # CSR columns over the flat numbering
+                assert int(edge_off[-1]) == e.shape[1]
     finally:
         lib.gcm_set_edge_builder(_cabi.EB_AUTO)
-    assert got["pairs"].shape[1] > 0
-    assert torch.equal(got["pairs"], got["hash"])
+        sparse_ops.HIT_CAP = 64
+    assert got[("pairs", 1)].shape[1] > 0
+    for k in got:
+        assert torch.equal(got[("pairs", 1)], got[k]), k
