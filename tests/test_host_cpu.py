@@ -211,3 +211,25 @@ def test_shard_bounds_partition_the_batch():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [hi - lo for lo, hi in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: one JSON line with the
+    contract's keys, timed on the oracle port."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for wl in ("cfg2", "cfg3"):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", wl,
+                              "--steps", "1", "--warmup", "1", "--cpu-batch", "4"], capture_output=True, text=True,
+                             timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+        for key in ("metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                    "config", "cpu_baseline", "e2e"):
+            assert key in line, key
+        assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
