@@ -122,6 +122,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T: both operands in shared memory (canonical K-major descriptors)
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // same with bf16 operands (K = 16 per instruction); a bf16 A operand in TMEM packs two K elements per column
 __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             bool accumulate) {

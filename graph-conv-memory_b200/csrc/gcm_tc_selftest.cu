@@ -12,7 +12,9 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
   float* Bhi = reinterpret_cast<float*>(st_raw);        // [N x K] canonical
   float* Blo = Bhi + N * K;
   __nv_bfloat16* Bbf = reinterpret_cast<__nv_bfloat16*>(Blo + N * K);   // [N x K] canonical, bf16 (passes == 4)
-  uint64_t* bar_a = reinterpret_cast<uint64_t*>(Bbf + N * K);
+  float* Ahi = reinterpret_cast<float*>(Bbf + N * K);   // [128 x K] canonical (passes == 5: A from shared memory)
+  float* Alo = Ahi + (passes == 5 ? 128 * K : 0);
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(Alo + (passes == 5 ? 128 * K : 0));
   uint64_t* bar_d = bar_a + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -45,6 +47,14 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) tc::split_tf32(A[(size_t)row * K + k0 + j], hi[j], lo[j]);
+      if (passes == 5) {   // SS form: the row-owning thread writes its row into the canonical shared-memory layout
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          Ahi[tc::kmajor_off(row, k0 + j, K)] = __uint_as_float(hi[j]);
+          Alo[tc::kmajor_off(row, k0 + j, K)] = __uint_as_float(lo[j]);
+        }
+        continue;
+      }
       tc::tmem_st16(lane_addr + col_ahi + k0, hi);
       if (passes == 4) {   // lo part as packed bf16: column c holds k = 2c (low half) and 2c + 1
         uint32_t pk[8];
@@ -56,6 +66,7 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
       }
     }
     tc::wait_st();
+    if (passes == 5) tc::fence_proxy_async();
     tc::fence_before_sync();
     tc::mbar_arrive(bar_a);
     tc::mbar_wait(bar_d, 0);
@@ -76,6 +87,18 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
       const uint32_t idesc = tc::idesc_tf32(128, N);
       const uint32_t sbo = (uint32_t)(K / 4) * 128u;
       bool acc = false;
+      if (passes == 5) {   // 3xTF32 with BOTH operands in shared memory: lo*Bhi, hi*Blo, hi*Bhi
+        for (int pass = 0; pass < 3; ++pass) {
+          const float* asrc = pass == 0 ? Alo : Ahi;
+          const float* bsrc = pass == 1 ? Blo : Bhi;
+          for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t adesc = tc::smem_desc_kmajor(tc::smem_u32(asrc) + ks * 256, 128, sbo);
+            const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
+            tc::mma_tf32_ss(tbase + col_d, adesc, bdesc, idesc, acc);
+            acc = true;
+          }
+        }
+      }
       if (passes == 4) {   // lo(bf16, TMEM) * B(bf16): 16 elements of K per instruction
         const uint32_t idesc16 = tc::idesc_bf16(128, N);
         const uint32_t sbo16 = (uint32_t)(K / 8) * 128u;
@@ -85,7 +108,7 @@ __global__ void __launch_bounds__(160) k_tc_selftest(const float* A, const float
           acc = true;
         }
       }
-      for (int pass = (passes == 4 ? 1 : 0); pass < (passes == 4 ? 3 : passes); ++pass) {
+      for (int pass = (passes == 4 ? 1 : 0); pass < (passes == 4 ? 3 : (passes == 5 ? 0 : passes)); ++pass) {
         // passes == 3: lo*Bhi, hi*Blo, hi*Bhi ; passes == 1: hi*Bhi only (plain tf32);
         // passes == 4: the lo*B term was issued above in bf16, then hi*Blo, hi*Bhi
         const int which = passes >= 3 ? pass : 2;
@@ -109,8 +132,9 @@ extern "C" int gcm_tc_selftest(const float* A, const float* B, float* D, int K, 
   GCM_REQUIRE(A && B && D, "tc_selftest: null pointer");
   GCM_REQUIRE(K % 16 == 0 && K >= 16 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 256,
               "tc_selftest: K=%d must be a multiple of 16 in [16,128], N=%d a multiple of 16 in [16,256]", K, N);
-  GCM_REQUIRE(passes == 1 || passes == 3 || passes == 4, "tc_selftest: passes must be 1, 3 or 4");
-  const size_t smem = (size_t)2 * N * K * 4 + (size_t)N * K * 2 + 64;
+  GCM_REQUIRE(passes == 1 || passes == 3 || passes == 4 || passes == 5, "tc_selftest: passes must be 1, 3, 4 or 5");
+  const size_t smem = (size_t)2 * N * K * 4 + (size_t)N * K * 2 + (passes == 5 ? (size_t)2 * 128 * K * 4 : 0) + 64;
+  GCM_REQUIRE(smem <= 220 * 1024, "tc_selftest: operands do not fit in shared memory");
   cudaError_t e = cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     gcm_set_error("cudaFuncSetAttribute(tc_selftest): %s", cudaGetErrorString(e));

@@ -108,3 +108,21 @@ def test_linear_tc32_is_fp32_accurate(rows, K1, K2, Ho, act):
     print(f"rows={rows} K1={K1} K2={K2} Ho={Ho} act={act}: 3xTF32 err {err:.2e}, fp32 matmul err {err32:.2e}")
     assert err < (1e-4 if act == 3 else 1e-5) + 2 * err32      # exp(2z) multiplies a relative error of z by 2|z|
     assert int(status[0]) == 0
+
+
+@pytest.mark.parametrize("K,N", [(64, 64), (128, 64), (32, 128)])
+def test_tc_block_ss_form_3xtf32(K, N):
+    """Same product with BOTH operands in shared memory (canonical K-major descriptors for A as for B): the form the
+    sparse GraphConv tile uses, where warps gather rows straight into the A tile."""
+    from gcm import _cabi
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(K * 7 + N)
+    A = torch.randn(128, K, generator=gen).to(dev)
+    B = (torch.randn(N, K, generator=gen) / K ** 0.5).to(dev)
+    D = torch.zeros(128, N, device=dev)
+    _cabi.check(_cabi.lib().gcm_tc_selftest(A.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, 5, _cabi.stream_ptr(dev)),
+                "gcm_tc_selftest")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    assert float((D.double() - ref).abs().max() / ref.abs().max()) < 2e-6
