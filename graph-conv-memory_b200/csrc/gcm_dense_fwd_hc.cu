@@ -606,12 +606,53 @@ static int launch_hc(const TemporalWinArgs& a, cudaStream_t stream) {
   cfg.blockDim = dim3(HC_THREADS);
   cfg.dynamicSmemBytes = L.total + 128;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool no_pdl = getenv("GCM_B200_NO_PDL") != nullptr;   // A/B switch for profiling
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  static const bool no_pdl = getenv("GCM_B200_NO_PDL") != nullptr;   // A/B switches for profiling
+  static const bool no_l2p = getenv("GCM_B200_NO_L2PERSIST") != nullptr;
+  if (!no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  // EXPERIMENT KNOB, off unless GCM_B200_L2PERSIST_MB is set.  The row cache is written once and read three times
+  // (hops 1, 2, 4 at cfg2) over the next steps and is L2-sized (67 MB against 126 MB), so a persisting access window
+  // looked like a way to stop 3 of the 7 rows of a graph-step from coming out of HBM.  Measured at cfg2 (B200, 82.9 MB
+  // maximum carve-out): 23.3 us without, 23.2 / 24.3 / 29.1 / 32.4 us with a 16 / 40 / 67 / 79 MB carve-out -- the
+  // carve-out takes L2 away from the streamed rows and costs more than the pinned lines give back.
+  static size_t l2_persist = 0, l2_window = 0;
+  static bool l2_init = false;
+  if (!l2_init && !no_l2p) {
+    l2_init = true;
+    int dev = 0;
+    cudaDeviceProp prop;
+    const char* mb = getenv("GCM_B200_L2PERSIST_MB");                 // size of the persisting carve-out (experiment knob)
+    if (mb && cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
+        prop.persistingL2CacheMaxSize > 0) {
+      size_t want = (size_t)atoll(mb) << 20;
+      if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+      if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        l2_persist = want;
+        l2_window = (size_t)prop.accessPolicyMaxWindowSize;
+      }
+      if (getenv("GCM_B200_L2PERSIST_VERBOSE"))
+        fprintf(stderr, "gcm: persisting L2 max %d B, window max %d B, carve-out %zu B\n", prop.persistingL2CacheMaxSize,
+                prop.accessPolicyMaxWindowSize, l2_persist);
+    }
+    cudaGetLastError();
+  }
+  const size_t hc_bytes = (size_t)a.st.B * a.hc_ring * HC_H * sizeof(float);
+  if (!no_l2p && l2_persist > 0 && hc_bytes > 0 && hc_bytes <= l2_window) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[na].val.accessPolicyWindow.base_ptr = const_cast<float*>(a.hcache);
+    attr[na].val.accessPolicyWindow.num_bytes = hc_bytes;
+    attr[na].val.accessPolicyWindow.hitRatio = hc_bytes <= l2_persist ? 1.0f : (float)((double)l2_persist / (double)hc_bytes);
+    attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = no_pdl ? 0 : 1;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k_step_temporal_hc<F>, a);
   if (e != cudaSuccess) {
     gcm_set_error("k_step_temporal_hc: launch failed: %s", cudaGetErrorString(e));

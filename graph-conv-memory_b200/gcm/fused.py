@@ -102,7 +102,21 @@ class GnnPlan:
         return None if b is None else b.detach()
 
     def current_key(self, device):
-        return tuple([(p.data_ptr(), p._version) for p in self.params()]) + (device,)
+        # once per step on the rollout path: one pass over the parameter dicts, no intermediate list
+        if self._lins is None:
+            self.params()
+        key = []
+        for lin in self._lins:
+            d = lin._parameters
+            w = d["weight"]
+            key.append(w.data_ptr())
+            key.append(w._version)
+            b = d.get("bias")
+            if b is not None:
+                key.append(b.data_ptr())
+                key.append(b._version)
+        key.append(device)
+        return tuple(key)
 
     def packed(self, device):
         """K-major weight packs (include/gcm_b200.h: gcm_gnn), rebuilt only when a parameter changed."""
