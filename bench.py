@@ -15,7 +15,7 @@ JSON line (rank 0):
                back-to-back launches), against MEASURED_PEAKS.json
   cpu_baseline the oracle port of the reference step on the host cores (bounded sample)
 
-Other workloads (`--workload cfg1|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
+Other workloads (`--workload cfg1|cfg2-pre|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
 configs with the same line format; `--impl reference` times the oracle port of the reference on CPU.
 """
 import argparse
@@ -39,6 +39,9 @@ WORKLOADS = {
              16, 128, 8, 32, [("temporal", (1,), "forward")], "rollout"),
     "cfg2": ("cfg2: DenseGCM N=128 F=32 H=32 TemporalBackedge([1,2,4]) rollout fwd",
              65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "rollout"),
+    "cfg2-pre": ("cfg2 with RayDenseGCM's Linear preprocessor (SURVEY 8(f) rank 2): DenseGCM(preprocessor=Linear(32,32)) "
+                 "N=128 H=32 TemporalBackedge([1,2,4]) rollout fwd", 65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")],
+                 "rollout"),
     "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, bf16 per-node cache, fp32 accumulate)",
              16384, 256, 128, 128, [("dense",)], "bptt"),
     "cfg3-seq": ("cfg3 through DenseGCM.forward_sequence (SURVEY 8(f) rank 1): the T=64 steps of a window in one call, "
@@ -113,7 +116,7 @@ def make_selector(spec):
     return EuclideanEdge(s[1])
 
 
-def build_dense(dev, N, F, H, spec):
+def build_dense(dev, N, F, H, spec, pre=False):
     from gcm.gcm import DenseGCM
     from gcm.nn import DenseGraphConv
 
@@ -129,7 +132,9 @@ def build_dense(dev, N, F, H, spec):
             return self.act(self.gc1(x, adj))
 
     torch.manual_seed(7)
-    return DenseGCM(GNN().to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    gnn = GNN().to(dev)
+    pre = torch.nn.Linear(F, F).to(dev) if pre else None     # RayDenseGCM's Linear pre-projection (ray_gcm.py:118)
+    return DenseGCM(gnn, preprocessor=pre, edge_selectors=make_selector(spec), graph_size=N)
 
 
 def build_sparse(dev, N, F, H):
@@ -165,7 +170,7 @@ def synth_obs(gen, n, B, F, spec):
 
 def algorithmic(workload, B, N, F, H, extra=None):
     """(bound, per-step algorithmic quantity, unit) — SURVEY.md §8(d)."""
-    if workload in ("cfg1", "cfg2"):
+    if workload in ("cfg1", "cfg2", "cfg2-pre"):
         hops = WORKLOADS[workload][5][0][1]
         r2 = len({0} | set(hops) | {a + b for a in hops for b in hops})
         per = r2 * F * 4 + F * 4 + F * 4 + N // 8 + H * 4 + 16
@@ -296,7 +301,7 @@ def main():
     unit_per_step = B
 
     if mode == "rollout":
-        mod = build_dense(dev, N, F, H, spec)
+        mod = build_dense(dev, N, F, H, spec, pre=args.workload == "cfg2-pre")
         n_obs = 16 if args.workload != "cfg4-euclid" else 4
         obs_host = synth_obs(gen, n_obs, B, F, spec).pin_memory()
         obs_dev = obs_host.to(dev)

@@ -336,6 +336,24 @@ extern "C" int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out
   return gcm_check_launch("k_materialize");
 }
 
+// nodes[b, (count[b] + offset) % C, :] = obs[b, :]: the node write of gcm.py:274 alone, on any log that shares the
+// counters of a state (the RAW observation log kept next to the preprocessed one when DenseGCM has a preprocessor,
+// gcm.py:290-291).  offset = 0 before the step that advances the counters, -1 after it.
+__global__ void __launch_bounds__(256) k_log_write(const gcm_dense_state st, const float* obs, int offset) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)st.B * st.F) return;
+  const int b = (int)(i / st.F), f = (int)(i - (long long)b * st.F);
+  st.nodes[((size_t)b * st.C + gcm_slot(__ldcg(st.count + b) + offset, st.C)) * st.F + f] = obs[i];
+}
+extern "C" int gcm_state_log_write(const gcm_dense_state* st, const float* obs, int offset, void* stream) {
+  GCM_REQUIRE(st && st->nodes && st->count && obs && st->B >= 0 && st->F >= 1 && st->C >= 1 && (offset == 0 || offset == -1),
+              "state_log_write: bad arguments");
+  if (st->B == 0) return GCM_OK;
+  const long long n = (long long)st->B * st->F;
+  k_log_write<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, obs, offset);
+  return gcm_check_launch("k_log_write");
+}
+
 extern "C" int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes,
                                           float* d_nodes_out, void* stream) {
   if (int rc = check_state(st)) return rc;

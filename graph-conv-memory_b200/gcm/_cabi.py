@@ -91,6 +91,7 @@ _SIGNATURES = {
                                 C.POINTER(GnnGradsC), _P]),
     "gcm_state_materialize": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P]),
     "gcm_state_materialize_grad": (_I, [C.POINTER(DenseStateC), _P, _P, _P]),
+    "gcm_state_log_write": (_I, [C.POINTER(DenseStateC), _P, _I, _P]),
     "gcm_state_ingest": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P, _P]),
     "gcm_euclid_batchmean": (_I, [C.POINTER(DenseStateC), _P, _I, _P, _P, _P]),
     "gcm_select_dense": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(SelectorC), _P]),

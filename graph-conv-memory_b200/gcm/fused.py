@@ -229,6 +229,7 @@ class FusedPlan:
                 self.hc_ring = 1 << max(self.max_hop, 1).bit_length()      # power of two > max_hop
         self.validated = False
         self._sel_cache = None
+        self.pre = False           # DenseGCM.preprocessor present (row-wise): see build_plan
 
     def selectors_c(self, F: int, dist: Optional[torch.Tensor]):
         n = len(self.sels)
@@ -243,9 +244,22 @@ class FusedPlan:
         return self._sel_cache[1], n
 
 
+_ROWWISE = (torch.nn.Linear, torch.nn.Tanh, torch.nn.ReLU, torch.nn.Sigmoid, torch.nn.Identity, torch.nn.LeakyReLU,
+            torch.nn.ELU, torch.nn.GELU, torch.nn.SiLU)
+
+
+def rowwise_preprocessor(pp) -> bool:
+    """Is `pp` a per-row map (Linear / activations / Sequential of those, what RayDenseGCM installs, ray_gcm.py:118,
+    133-136)?  The reference applies it to all N rows every step (gcm.py:290-291); a per-row map can be applied once, to
+    the new observation, and its result kept in the node log."""
+    if isinstance(pp, torch.nn.Sequential):
+        return len(pp) > 0 and all(rowwise_preprocessor(m) for m in pp)
+    return isinstance(pp, _ROWWISE)
+
+
 def build_plan(module) -> Optional[FusedPlan]:
     """DenseGCM -> FusedPlan, or None when the configuration is outside the fused hot path."""
-    if module.preprocessor is not None or module.aux_edge_selectors is not None:
+    if module.aux_edge_selectors is not None:
         return None
     if module.positional_encoder is not None or module.pooled:
         return None
@@ -255,7 +269,16 @@ def build_plan(module) -> Optional[FusedPlan]:
     sels = match_selectors(module.edge_selectors)
     if sels is None:
         return None
-    return FusedPlan(gnn, sels)
+    plan = FusedPlan(gnn, sels)
+    plan.pre = module.preprocessor is not None
+    if plan.pre:
+        # selectors see the RAW nodes (gcm.py:284-287), the GNN the preprocessed ones: fusable when no selector looks at
+        # node contents (TemporalBackedge / DenseEdge) and the preprocessor is a per-row map
+        if not rowwise_preprocessor(module.preprocessor):
+            return None
+        if any(s.kind not in (_cabi.SEL_TEMPORAL, _cabi.SEL_DENSE) for s in sels):
+            return None
+    return plan
 
 
 # ------------------------------------------------------------------------------------------------

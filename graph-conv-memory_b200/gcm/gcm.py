@@ -171,6 +171,66 @@ class DenseGCM(torch.nn.Module):
         plan = self.fused_plan()
         if plan is None:
             return self._forward_generic(x, hidden)
+        if plan.pre:
+            return self._forward_pre(plan, x, hidden)
+        return self._forward_fused(plan, x, hidden)
+
+    def _forward_pre(self, plan, x, hidden):
+        """Fused rollout step of a DenseGCM with a row-wise preprocessor (what RayDenseGCM installs, ray_gcm.py:118,
+        133-136).  The reference maps ALL N rows through the preprocessor every step (gcm.py:290-291); a per-row map only
+        has to be applied to the NEW observation, whose image goes into the node log the kernels read, while a second log
+        keeps the raw observations for the caller's view of m_t.  When the preprocessor's weights change the
+        preprocessed log is rebuilt from the raw one.  Anything that needs autograd takes the generic path (exact
+        reference semantics: gradients reach the preprocessor through every stored row)."""
+        pre = self.preprocessor
+        if torch.is_grad_enabled() and (
+                x.requires_grad or any(p.requires_grad for p in self.parameters())
+                or (isinstance(hidden, DenseHidden) and hidden.token is not None)
+                or (isinstance(hidden, (tuple, list)) and hidden[0].requires_grad)):
+            return self._forward_generic(x, hidden)
+        assert x.dtype == torch.float32
+        _cabi.require_cuda(x, "DenseGCM.forward(x)")
+        with torch.no_grad():
+            x_raw = x.contiguous()
+            plist = self.__dict__.get("_pre_params")
+            if plist is None:
+                plist = self.__dict__["_pre_params"] = list(pre.parameters())
+            pkey = tuple([v for p in plist for v in (p.data_ptr(), p._version)])
+            nodes_raw = None
+            if isinstance(hidden, DenseHidden):
+                state = hidden.claim()
+                if state.raw is None:
+                    return self._forward_generic(x, hidden)
+                if state.pre_key != pkey:
+                    # new preprocessor weights: every stored row gets its new image, every cache built on them goes
+                    state.nodes.copy_(pre(state.raw))
+                    state.pre_key = pkey
+                    state.xsum, state.rc_key, state.hc_key, state.hc_fresh = None, None, None, 0
+                inner = hidden
+            elif hidden is None:
+                inner = None
+            else:
+                nodes_raw, adj, weights, num_nodes = hidden
+                assert nodes_raw.dtype == torch.float
+                inner = (pre(nodes_raw), adj, weights, num_nodes)
+            belief, out = self._forward_fused(plan, pre(x_raw), inner, orig=(x, hidden))
+            if not isinstance(out, DenseHidden) or self._plan is not plan:
+                return belief, out
+            state = out.claim()
+            if state.raw is None:
+                state.raw = torch.zeros(state.B, state.C, x_raw.shape[1], device=x.device, dtype=torch.float32)
+                if nodes_raw is not None:
+                    state.raw[:, : state.N] = nodes_raw
+                state.pre_key = pkey
+            _cabi.check(_cabi.lib().gcm_state_log_write(state.raw_ref(), x_raw.data_ptr(), -1,
+                                                        _cabi.stream_ptr(x.device)), "gcm_state_log_write")
+        return belief, out
+
+    def _forward_fused(self, plan, x, hidden, orig=None):
+        """The fused step on GNN-input rows x.  `orig` = the caller's (x, hidden) when x is a preprocessed image: what
+        the generic path must be given if this configuration turns out not to be fusable."""
+        def generic():
+            return self._forward_generic(*(orig if orig is not None else (x, hidden)))
 
         assert x.dtype == torch.float32
         _cabi.require_cuda(x, "DenseGCM.forward(x)")
@@ -198,11 +258,11 @@ class DenseGCM(torch.nn.Module):
             N = nodes.shape[1]
             assert N == adj.shape[1] == adj.shape[2], "N must be equal for adj mat and node mat"
             if adj.requires_grad or (weights.numel() != 0 and weights.requires_grad):
-                return self._forward_generic(x, hidden)   # learned / weighted adjacency
+                return generic()   # learned / weighted adjacency
             state, flags = DenseState.ingest(nodes, adj, weights, num_nodes,
                                              N + (self.bptt_capacity if recording else 0))
             if flags & (_cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT):
-                return self._forward_generic(x, hidden)   # not a {0,1} graph over the valid block
+                return generic()   # not a {0,1} graph over the valid block
             token = None
             if recording and nodes.requires_grad:
                 ingest_grad = True

@@ -54,6 +54,11 @@ class DenseState:
         self.rc_key = None          # (W_root1 identity/version, act1, element type) the cache was filled under
         self.rc_bf16 = False        # cache element type: float32 or bfloat16
         self.DZ: Optional[torch.Tensor] = None        # [B, C, H1] dL/d(pre-activation) per node of a BPTT window
+        # DenseGCM with a row-wise preprocessor (gcm.py:290-291): `nodes` holds the PREPROCESSED rows the kernels read,
+        # `raw` [B, C, F_raw] the observations as the caller sees them in m_t; pre_key = preprocessor weights the rows
+        # were computed under
+        self.raw: Optional[torch.Tensor] = None
+        self.pre_key = None
         self.win = None             # gcm.ones._Window: per-step buffers of the BPTT window being recorded
         self.ones_tmp = None        # per-step scratch of non-recording steps
         # single distance selector (gcm.fused.zc_step): per-node pre-activation cache
@@ -110,8 +115,29 @@ class DenseState:
                         "gcm_dense_fill_masks")
             self.masks_stale = False
 
+    def raw_ref(self):
+        """C view of the raw-observation log (same masks and counters)."""
+        r = self.raw
+        c = self.__dict__.get("_raw_c")
+        if c is None or c.nodes != r.data_ptr():
+            c = self._raw_c = _cabi.DenseStateC(r.data_ptr(), self.masks.data_ptr(), self.count.data_ptr(), self.B,
+                                                self.N, self.C, r.shape[2], self.W)
+        return C.byref(c)
+
     def materialize(self, want_adj: bool = True):
         self.sync_masks()
+        if self.raw is not None:
+            # the caller's view of the nodes is the raw observations; adjacency and counters come from the state
+            lib = _cabi.lib()
+            nodes = torch.empty(self.B, self.N, self.raw.shape[2], device=self.device, dtype=torch.float32)
+            adj = torch.empty(self.B, self.N, self.N, device=self.device, dtype=torch.float32) if want_adj else None
+            num_nodes = torch.empty(self.B, device=self.device, dtype=torch.long)
+            _cabi.check(lib.gcm_state_materialize(self.raw_ref(), nodes.data_ptr(), None, num_nodes.data_ptr(),
+                                                  _cabi.stream_ptr(self.device)), "gcm_state_materialize")
+            if want_adj:
+                _cabi.check(lib.gcm_state_materialize(self.c_ref(), None, adj.data_ptr(), num_nodes.data_ptr(),
+                                                      _cabi.stream_ptr(self.device)), "gcm_state_materialize")
+            return nodes, adj, num_nodes
         nodes = torch.empty(self.B, self.N, self.F, device=self.device, dtype=torch.float32)
         adj = torch.empty(self.B, self.N, self.N, device=self.device, dtype=torch.float32) if want_adj else None
         num_nodes = torch.empty(self.B, device=self.device, dtype=torch.long)

@@ -174,6 +174,10 @@ int gcm_dense_step_bwd(const gcm_dense_state* st, int steps_back, const gcm_gnn*
  * Any of nodes_out / adj_out / num_nodes_out may be NULL. */
 int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out, float* adj_out,
                           int64_t* num_nodes_out, void* stream);
+/* nodes[b, (count[b] + offset) % C, :] = obs[b, :] -- the node write of gcm.py:274 on a log that shares the counters of
+ * a state (the raw-observation log kept beside the preprocessed one when DenseGCM has a preprocessor, gcm.py:290-291).
+ * offset = 0 before the step that advances the counters, -1 after it. */
+int gcm_state_log_write(const gcm_dense_state* st, const float* obs, int offset, void* stream);
 /* dL/dnodes in log layout -> [B,N,F] reference layout (rows >= num_nodes are zero) */
 int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes, float* d_nodes_out,
                                void* stream);

@@ -280,3 +280,58 @@ def test_distance_selector_cache_path_and_its_retirement(spec):
     assert all(n == "k_step_general" for n in names[100:])
     nodes, adj, weights, num_nodes = hidden
     assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
+
+
+@pytest.mark.parametrize("spec", [[("temporal", (1, 2, 4), "forward")], [("dense",)], [("temporal", (1,), "both")]])
+def test_rowwise_preprocessor_runs_fused_and_matches_the_reference_step(spec):
+    """DenseGCM(preprocessor=Linear) -- what RayDenseGCM builds (ray_gcm.py:118,133-136) -- on the fused rollout path
+    (SURVEY 8(f) rank 2): the reference preprocesses all N rows every step (gcm.py:290-291), here only the new
+    observation.  Beliefs every step and the caller's view of m_t (RAW nodes, adjacency, num_nodes) against the oracle
+    run on preprocessed observations; window wraps; a caller-supplied tuple; an in-place update of the preprocessor
+    weights in the middle (every stored row must get its new image)."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+    from gcm.state import DenseHidden
+
+    dev = torch.device("cuda:0")
+    B, N, F_raw, F, H, T = 6, 12, 10, 32, 32, 40
+    gen = torch.Generator().manual_seed(99)
+    p = oracle.make_params(F, H)
+    gnn, _ = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+    pre = torch.nn.Sequential(torch.nn.Linear(F_raw, F), torch.nn.Tanh())
+    mod = DenseGCM(gnn.to(dev), preprocessor=pre.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    assert mod.fused_plan() is not None and mod.fused_plan().pre
+    obs = torch.randn(T, B, F_raw, generator=gen)
+    hidden, o_hidden, raw_nodes = None, None, torch.zeros(B, N, F_raw)
+    names = []
+    with torch.no_grad():
+        for t in range(T):
+            if t == 25:
+                pre[0].weight.mul_(0.5)
+                pre[0].bias.add_(0.1)
+                # the oracle's stored rows are images under the OLD weights: rebuild them from the raw observations
+                o_hidden = (pre(raw_nodes.to(dev)).cpu() * (torch.arange(N).view(1, N, 1) < o_hidden[3].view(B, 1, 1)),
+                            o_hidden[1], o_hidden[2], o_hidden[3])
+            if t == 30:
+                hidden = tuple(hidden)                                  # a plain reference-layout tuple comes back in
+                assert torch.equal(hidden[0].cpu(), raw_nodes)
+            belief, hidden = mod(obs[t].to(dev), hidden)
+            names.append(_cabi.lib().gcm_last_kernel().decode())
+            assert isinstance(hidden, DenseHidden)
+            y = pre(obs[t].to(dev)).cpu()
+            ref, o_hidden = oracle.dense_gcm_step(y, o_hidden, spec, p, graph_size=N)
+            assert rel_err(belief, ref) < 5 * TOL, (t, names[-1])
+            # the reference's own bookkeeping of the raw rows (gcm.py:262-274, 323-355)
+            full = int(o_hidden[3][0]) == N and t >= N
+            if full:
+                raw_nodes = torch.cat([raw_nodes[:, 1:], obs[t].unsqueeze(1)], dim=1)
+            else:
+                raw_nodes[:, t] = obs[t]
+    assert names[-1] == "k_log_write"
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), raw_nodes) and torch.equal(adj.cpu(), o_hidden[1])
+    assert torch.equal(num_nodes.cpu(), o_hidden[3])
+    # anything that needs autograd takes the generic path and still agrees
+    x = obs[0].to(dev).requires_grad_(True)
+    belief, h2 = mod(x, hidden)
+    assert not isinstance(h2, DenseHidden) and belief.requires_grad

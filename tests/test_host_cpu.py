@@ -88,7 +88,13 @@ def test_plan_matching_rejects_what_is_outside_the_hot_path():
 
     p = oracle.make_params(4, 4)
     gnn, _ = make_dense_gnn(4, 4, p, ("tanh", "tanh"))
-    assert fused.build_plan(DenseGCM(gnn, preprocessor=torch.nn.Linear(4, 4))) is None
+    # a per-row preprocessor (what RayDenseGCM installs) is fusable with selectors that do not look at node contents ...
+    pre_plan = fused.build_plan(DenseGCM(gnn, preprocessor=torch.nn.Linear(6, 4), edge_selectors=make_selector([("dense",)])))
+    assert pre_plan is not None and pre_plan.pre
+    assert fused.build_plan(DenseGCM(gnn, preprocessor=torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh()))).pre
+    # ... but not with a distance selector (it reads the RAW rows, gcm.py:284-287) or a map that is not per-row
+    assert fused.build_plan(DenseGCM(gnn, preprocessor=torch.nn.Linear(6, 4), edge_selectors=make_selector([("cosine", 0.5)]))) is None
+    assert fused.build_plan(DenseGCM(gnn, preprocessor=torch.nn.LayerNorm(4))) is None
     assert fused.build_plan(DenseGCM(gnn, pooled=True)) is None
     assert fused.build_plan(DenseGCM(gnn, aux_edge_selectors=make_selector([("dense",)]))) is None
     assert fused.build_plan(DenseGCM(gnn, positional_encoder=PositionalEncoding())) is None
