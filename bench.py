@@ -15,7 +15,7 @@ JSON line (rank 0):
                back-to-back launches), against MEASURED_PEAKS.json
   cpu_baseline the oracle port of the reference step on the host cores (bounded sample)
 
-Other workloads (`--workload cfg1|cfg2-pre|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5`) report the remaining BASELINE
+Other workloads (`--workload cfg1|cfg2-pre|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the remaining BASELINE
 configs with the same line format; `--impl reference` times the oracle port of the reference on CPU.
 """
 import argparse
@@ -52,6 +52,8 @@ WORKLOADS = {
                     4096, 512, 64, 64, [("euclidean", 2.0)], "rollout"),
     "cfg5": ("cfg5: SparseGCM TemporalEdge([1]) + SpatialRadiusEdge(0.25) N=4096 F=H=64 all-at-once",
              1024, 4096, 64, 64, None, "sparse"),
+    "cfg5-train": ("cfg5 forward + backward (loss = mean of the outputs; gradients of the GraphConv weights and of x)",
+                   1024, 4096, 64, 64, None, "sparse"),
 }
 
 
@@ -70,9 +72,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # index: GPU index, a comma-separated list of indices (one sampler process for all ranks of the job: eight
+        # nvidia-smi pollers queue on the driver's locks and show up as launch hiccups on every rank), or None = idle
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if self.index is None:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -86,6 +92,8 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0=None, t1=None):
+        if self.index is None:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
@@ -184,10 +192,10 @@ def algorithmic(workload, B, N, F, H, extra=None):
         # SURVEY.md 8(d), all-ones structure exploited: 66.8 KB per graph-step of the forward (bf16 per-node rows at
         # n = N); k_ones_fwd is that pass.  The backward is one pass per window, not 2x this per step.
         return "hbm", B * (N * F * 2 + 2 * F * 4 + N // 8 + H * 4 + 16), "bytes"
-    if workload == "cfg5":
+    if workload in ("cfg5", "cfg5-train"):
         n, E = extra
         per_layer = n * F * 4 + E * 8 + (n + 1) * 8 + n * H * 4
-        return "hbm", 2 * per_layer, "bytes"
+        return "hbm", 2 * per_layer * (3 if workload == "cfg5-train" else 1), "bytes"
     raise ValueError(workload)
 
 
@@ -295,7 +303,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local)
+    # rank 0 samples the clocks of every GPU of the job (local ranks 0 .. world-1 of this node)
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None)
     sampler.start()
     extra, launches, e2e, kern_ms, kernel_name, host_us = None, K, None, None, None, None
     unit_per_step = B
@@ -305,16 +314,17 @@ def main():
         n_obs = 16 if args.workload != "cfg4-euclid" else 4
         obs_host = synth_obs(gen, n_obs, B, F, spec).pin_memory()
         obs_dev = obs_host.to(dev)
+        obs_steps = [obs_dev[i] for i in range(n_obs)]       # per-step views made once (2 us of host time per step)
         hidden = None
         with torch.no_grad():
             for i in range(W):
-                belief, hidden = mod(obs_dev[i % n_obs], hidden)
+                belief, hidden = mod(obs_steps[i % n_obs], hidden)
             barrier()
             t_lo = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(K):
-                belief, hidden = mod(obs_dev[i % n_obs], hidden)
+                belief, hidden = mod(obs_steps[i % n_obs], hidden)
             e1.record()
             barrier()
             total_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -327,7 +337,7 @@ def main():
             h0 = time.perf_counter()
             e0.record()
             for i in range(K):
-                belief, hidden = mod(obs_dev[i % n_obs], hidden)
+                belief, hidden = mod(obs_steps[i % n_obs], hidden)
             e1.record()
             host_us = (time.perf_counter() - h0) / K * 1e6
             torch.cuda.synchronize()
@@ -454,24 +464,38 @@ def main():
         x_host = x.pin_memory()
         x_dev = x_host.to(dev)
         taus = torch.full((B,), N, dtype=torch.long, device=dev)
-        with torch.no_grad():
-            for _ in range(W):
+        train = args.workload == "cfg5-train"
+        if train:
+            x_dev.requires_grad_(True)
+
+        def call():
+            if train:
+                for p_ in mod.parameters():
+                    p_.grad = None
+                x_dev.grad = None
                 out, hid = mod(x_dev, taus, None)
-            barrier()
-            t_lo = time.perf_counter()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(K):
-                out, hid = mod(x_dev, taus, None)
-            e1.record()
-            barrier()
-            total_ms = max_over_ranks(e0.elapsed_time(e1))
-            t_hi = time.perf_counter()
+                out.mean().backward()
+                return out, hid
+            with torch.no_grad():
+                return mod(x_dev, taus, None)
+
+        for _ in range(W):
+            out, hid = call()
+        barrier()
+        t_lo = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            out, hid = call()
+        e1.record()
+        barrier()
+        total_ms = max_over_ranks(e0.elapsed_time(e1))
+        t_hi = time.perf_counter()
         E = int(hid[1]._nnz())
         extra = (B * N, E)
         unit_per_step = B * N
         launches = K * 5
-        kernel_name = "k_graphconv_fwd x2 (+ edge build)"
+        kernel_name = "k_graphconv_fwd x2 (+ edge build)" + (" + backward (k_linear2, k_outer_reduce, k_graphconv_bwd_gather)" if train else "")
         kern_ms = total_ms / K
 
     value = unit_per_step * world * K / (total_ms * 1e-3)
@@ -489,7 +513,7 @@ def main():
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload)
         line = {
-            "metric": "GCM env-steps/sec (fwd)" if mode != "bptt" else "GCM env-steps/sec (fwd+bwd)",
+            "metric": "GCM env-steps/sec (fwd+bwd)" if (mode == "bptt" or args.workload == "cfg5-train") else "GCM env-steps/sec (fwd)",
             "value": value, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 cache / f32 accumulate" if (mode == "bptt" and args.cache == "bf16") else "f32",

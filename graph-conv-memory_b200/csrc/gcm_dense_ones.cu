@@ -185,51 +185,58 @@ struct OuterArgs {
   float* dW;   // [Ho, Hi]
   float* db;   // [Ho] or NULL
 };
+// P x Q register tile per thread (16 x 16 threads): P = ceil(Ho / 16), Q = ceil(Hi / 16) rounded up to 4 or 8, so that a
+// 64 x 64 gradient does not pay for a 128 x 128 tile.
+template <int P, int Q>
 __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(const OuterArgs a) {
-  __shared__ float As[OR_RC][128 + 1];
-  __shared__ float Xs[OR_RC][128 + 1];
+  __shared__ float As[OR_RC][16 * P + 1];
+  __shared__ float Xs[OR_RC][16 * Q + 1];
   const int tid = threadIdx.x;
   const int to = tid >> 4, ti = tid & 15;       // output rows to + 16 p, columns ti + 16 q
-  float acc[8][8];
-  float accb[8];
+  float acc[P][Q];
+  float accb[P];
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
+  for (int p = 0; p < P; ++p) {
     accb[p] = 0.0f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[p][q] = 0.0f;
+    for (int q = 0; q < Q; ++q) acc[p][q] = 0.0f;
   }
   const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
   const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
   for (long long r0 = r_begin; r0 < r_end; r0 += OR_RC) {
     __syncthreads();
-    for (int i = tid; i < OR_RC * 128; i += OR_THREADS) {
-      const int r = i >> 7, c = i & 127;
+    for (int i = tid; i < OR_RC * 16 * P; i += OR_THREADS) {
+      const int r = i / (16 * P), c = i - r * (16 * P);
       const long long gr = r0 + r;
       As[r][c] = (gr < r_end && c < a.Ho) ? a.A[gr * a.lda + c] : 0.0f;
+    }
+    for (int i = tid; i < OR_RC * 16 * Q; i += OR_THREADS) {
+      const int r = i / (16 * Q), c = i - r * (16 * Q);
+      const long long gr = r0 + r;
       Xs[r][c] = (gr < r_end && c < a.Hi) ? a.X[gr * a.ldx + c] : 0.0f;
     }
     __syncthreads();
 #pragma unroll 4
     for (int r = 0; r < OR_RC; ++r) {
-      float av[8], xv[8];
+      float av[P], xv[Q];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) av[p] = As[r][to + 16 * p];
+      for (int p = 0; p < P; ++p) av[p] = As[r][to + 16 * p];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) xv[q] = Xs[r][ti + 16 * q];
+      for (int q = 0; q < Q; ++q) xv[q] = Xs[r][ti + 16 * q];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
+      for (int p = 0; p < P; ++p) {
         accb[p] += av[p];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(av[p], xv[q], acc[p][q]);
+        for (int q = 0; q < Q; ++q) acc[p][q] = fmaf(av[p], xv[q], acc[p][q]);
       }
     }
   }
 #pragma unroll
-  for (int p = 0; p < 8; ++p) {
+  for (int p = 0; p < P; ++p) {
     const int o = to + 16 * p;
     if (o < a.Ho) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const int i = ti + 16 * q;
         if (i < a.Hi && acc[p][q] != 0.0f) atomicAdd(a.dW + (size_t)o * a.Hi + i, acc[p][q]);
       }
@@ -756,7 +763,11 @@ extern "C" int gcm_outer_reduce(const float* A, long long lda, int Ho, const flo
   per = (per + OR_RC - 1) / OR_RC * OR_RC;
   ctas = (rows + per - 1) / per;
   OuterArgs a{A, lda, Ho, X, ldx, Hi, rows, per, dW, db};
-  k_outer_reduce<<<(unsigned)ctas, OR_THREADS, 0, (cudaStream_t)stream>>>(a);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (Ho <= 64 && Hi <= 64) k_outer_reduce<4, 4><<<(unsigned)ctas, OR_THREADS, 0, s>>>(a);
+  else if (Ho <= 64) k_outer_reduce<4, 8><<<(unsigned)ctas, OR_THREADS, 0, s>>>(a);
+  else if (Hi <= 64) k_outer_reduce<8, 4><<<(unsigned)ctas, OR_THREADS, 0, s>>>(a);
+  else k_outer_reduce<8, 8><<<(unsigned)ctas, OR_THREADS, 0, s>>>(a);
   return gcm_check_launch("k_outer_reduce");
 }
 

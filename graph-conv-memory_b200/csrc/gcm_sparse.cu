@@ -612,6 +612,43 @@ __global__ void __launch_bounds__(256) k_graphconv_bwd_rows(const GraphConvBwdAr
 
 // transposed gather: t_rowptr/t_col group the edges by SOURCE node; t_col holds the LOCAL index (into
 // the m evaluated rows) of each edge's sink.  d_x[j] += sum w * d_agg[t_col[e]]
+template <int V>
+__device__ __forceinline__ void gc_bwd_gather_row(const float* d_agg, const int64_t* t_col, const float* t_ew, int64_t e0,
+                                                  int64_t e1, int lane, float* dst) {
+  // same scheme as gc_gather_row: lane owns V contiguous features, 32 column indices per coalesced load, 8 gathers in flight
+  const int Fin = 32 * V;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+  const float* xl = d_agg + lane * V;
+  for (int64_t base = e0; base < e1; base += 32) {
+    const int cnt = (int)min((int64_t)32, e1 - base);
+    const int64_t my = lane < cnt ? t_col[base + lane] : 0;
+    const float myw = (t_ew && lane < cnt) ? t_ew[base + lane] : 1.0f;
+    int u = 0;
+    for (; u + 8 <= cnt; u += 8) {
+      float v[8][V];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u + q) * Fin, v[q]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float w = t_ew ? __shfl_sync(GCM_FULL_MASK, myw, u + q) : 1.0f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += t_ew ? v[q][j] * w : v[q][j];
+      }
+    }
+    for (; u < cnt; ++u) {
+      float v[V];
+      gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u) * Fin, v);
+      const float w = t_ew ? __shfl_sync(GCM_FULL_MASK, myw, u) : 1.0f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += t_ew ? v[j] * w : v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) dst[lane * V + j] += acc[j];
+}
+
 __global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg, const int64_t* t_rowptr,
                                                              const int64_t* t_col, const float* t_ew,
                                                              int64_t n, int Fin, float* d_x) {
@@ -620,6 +657,9 @@ __global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg
   if (j >= n) return;
   const int64_t e0 = t_rowptr[j], e1 = t_rowptr[j + 1];
   if (e0 == e1) return;
+  if (Fin == 64) return gc_bwd_gather_row<2>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  if (Fin == 128) return gc_bwd_gather_row<4>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  if (Fin == 32) return gc_bwd_gather_row<1>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
   for (int f0 = 0; f0 < Fin; f0 += 32) {
     const int f = f0 + lane;
     if (f >= Fin) break;
@@ -743,12 +783,29 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
                                         const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
                                         const int64_t* t_col, const float* t_ew, int Fin, int Fout,
                                         const float* w_rel, const float* w_root, int act, float* d_agg, float* d_x,
-                                        float* d_w_rel, float* d_w_root, float* d_b, void* stream) {
+                                        float* d_w_rel, float* d_w_root, float* d_b, float* dz_scratch,
+                                        const float* w_rel_t, const float* w_root_t, void* stream) {
   GCM_REQUIRE(x && agg && out && d_out && t_rowptr && w_rel && w_root && d_agg && d_x && d_w_rel && d_w_root,
               "sparse_graphconv_bwd: null pointer");
   GCM_REQUIRE(Fin >= 1 && Fin <= 128 && Fout >= 1 && Fout <= 128 && m >= 0 && n >= 0,
               "sparse_graphconv_bwd: bad dims");
   if (m == 0 || n == 0) return GCM_OK;
+  if (!rows && dz_scratch && w_rel_t && w_root_t) {
+    // every row is evaluated (the all-at-once call): the per-row part is four plain products over m rows, done by the
+    // register-tiled kernels of the dense path instead of the element-owned tile kernel below (24.5 -> ~6 ms per layer
+    // at cfg5):  dz = d_out * act'(out);  d_agg = dz W_rel;  d_x = dz W_root;  dW_rel += dz^T agg;  dW_root += dz^T x
+    if (int rc = gcm_act_backward(d_out, out, act, (long long)m * Fout, dz_scratch, stream)) return rc;
+    if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_rel_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_agg,
+                             Fin, nullptr, 0, stream)) return rc;
+    if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_root_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_x,
+                             Fin, nullptr, 0, stream)) return rc;
+    if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, agg, Fin, Fin, m, d_w_rel, d_b, stream)) return rc;
+    if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, x, Fin, Fin, m, d_w_root, nullptr, stream)) return rc;
+    const int64_t g2 = (n + 7) / 8;
+    GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
+    k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+    return gcm_check_launch("k_graphconv_bwd_gather");
+  }
   GraphConvBwdArgs a{x, agg, out, d_out, rows, m, n, Fin, Fout, w_rel, w_root, act, d_agg, d_x, d_w_rel, d_w_root, d_b};
   const size_t smem = ((size_t)GB_TM * Fout + (size_t)GB_TM * 2 * Fin + (size_t)2 * Fin * Fout + Fout) * 4;
   cudaError_t e = cudaFuncSetAttribute(k_graphconv_bwd_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

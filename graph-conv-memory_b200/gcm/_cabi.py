@@ -124,7 +124,7 @@ _SIGNATURES = {
     "gcm_set_edge_builder": (_I, [_I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
-                                      _P, _P, _P, _P]),
+                                      _P, _P, _P, _P, _P, _P, _P]),
     "gcm_tc_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 

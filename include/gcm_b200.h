@@ -353,12 +353,15 @@ int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_
 
 /* Backward of the above.  t_rowptr [n+1] / t_col [E] / t_ew group the same edges by SOURCE node, with
  * t_col holding the position (in 0..m-1) of the edge's sink among the evaluated rows.  d_x [n, Fin]
- * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate. */
+ * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate.
+ * Optional (all three or none; used when rows == NULL): dz_scratch [m, Fout] and the transposed weights w_rel_t /
+ * w_root_t [Fin, Fout] let the per-row products run as plain register-tiled GEMMs over the m rows. */
 int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
                              const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
                              const int64_t* t_col, const float* t_ew, int Fin, int Fout, const float* w_rel,
                              const float* w_root, int act, float* d_agg, float* d_x, float* d_w_rel,
-                             float* d_w_root, float* d_b, void* stream);
+                             float* d_w_root, float* d_b, float* dz_scratch,
+                             const float* w_rel_t, const float* w_root_t, void* stream);
 
 /* Self-test of the tcgen05/TMEM building block of the tensor-core step kernels:
  * D[128,N] = A[128,K] B[N,K]^T, passes = 3 (3xTF32, fp32-accurate) or 1 (plain tf32).  Test hook only. */
