@@ -351,6 +351,43 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     state.steps += 1
     if state.host_count is not None:
         state.host_count += 1
+    # steady-state rollout on the row-cache kernel: the next step may take fast_temporal_step
+    state.fast_ok = bool(hcache is not None and (flags & _cabi.STEP_HCACHE_VALID) and state.hc_fresh > 0 and dist is None)
+
+
+def fast_temporal_step(plan: FusedPlan, state: DenseState, x: torch.Tensor):
+    """The steady-state rollout step (no autograd, forward-only temporal chain on the row-cache kernel) with the host
+    work cut to what can change between two steps: input checks, the weights key, the flags, the launch.  Returns None
+    whenever anything is unusual; DenseGCM.forward then takes the general route, which re-derives everything (and is the
+    only place that raises).  Same launch as _launch_fwd, argument for argument."""
+    if (x.dtype is not torch.float32 or not x.is_cuda or x.dim() != 2 or x.shape[0] != state.B or x.shape[1] != state.F
+            or not x.is_contiguous() or state.pure_key != plan.temporal_key or state.masks_stale
+            or torch.cuda.is_current_stream_capturing()):
+        return None
+    dev = state.device
+    gnn_c = plan.gnn.packed(dev)
+    if state.hc_key != plan.gnn._key or state.hc_fresh < plan.max_hop or state.hcache is None:
+        return None                              # weights changed / cache not warm: the general route handles it
+    flags = _cabi.STEP_PURE_TEMPORAL | _cabi.STEP_HCACHE_VALID | _cabi.STEP_WEIGHTS_STABLE
+    hc = state.host_count
+    if hc is not None:
+        if hc < plan.max_hop:
+            return None
+        flags |= _cabi.STEP_UNIFORM_COUNT | (hc << _cabi.STEP_COUNT_SHIFT)
+    sels, n = plan.selectors_c(state.F, None)
+    belief = torch.empty(state.B, plan.gnn.H2, device=dev, dtype=torch.float32)
+    written = C.c_int(0)
+    _cabi.check(_cabi.lib().gcm_dense_step_fwd_cached(
+        state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(), state.status.data_ptr(), flags,
+        state.hcache.data_ptr(), plan.hc_ring, C.byref(written), _cabi.stream_ptr(dev)), "gcm_dense_step_fwd")
+    state.hc_fresh = min(state.hc_fresh + 1, plan.max_hop) if written.value else 0
+    state.fast_ok = state.hc_fresh > 0
+    state.max_count += 1
+    state.version += 1
+    state.steps += 1
+    if hc is not None:
+        state.host_count = hc + 1
+    return belief
 
 
 def zc_step(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> Optional[torch.Tensor]:
@@ -382,6 +419,7 @@ def zc_step(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> Optional[tor
                 "gcm_dense_step_fwd_zc")
     state.pure_key = None
     state.dense_ok = False
+    state.fast_ok = False
     state.xsum, state.rc_key = None, None
     state.version += 1
     state.steps += 1
@@ -530,6 +568,7 @@ def grow_state(state: DenseState, capacity: int) -> DenseState:
 
 def fused_step_grad(plan: FusedPlan, state: DenseState, x: torch.Tensor, token, bptt_capacity: int):
     """Recording step.  Returns (belief, token, state) -- the state may have been re-homed."""
+    state.fast_ok = False
     if state.C - state.N < 1:
         state = grow_state(state, state.N + max(int(bptt_capacity), 1))
         token = None

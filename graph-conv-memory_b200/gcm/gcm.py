@@ -168,6 +168,18 @@ class DenseGCM(torch.nn.Module):
         hidden: None, the previous call's returned hidden, or a reference-style tuple
         (nodes[B,N,F], adj[B,N,N], weights [B,N,N] or empty, num_nodes[B] int64).
         Returns (belief [B,H], hidden)."""
+        if hidden.__class__ is DenseHidden and not torch.is_grad_enabled():
+            # steady-state rollout: skip everything that cannot have changed since the previous step
+            st = hidden._state
+            plan = self._plan
+            if (st.fast_ok and hidden._version == st.version and hidden.token is None and plan is not None
+                    and plan.validated and not plan.pre):
+                belief = fused.fast_temporal_step(plan, st, x)
+                if belief is not None:
+                    if not DenseGCM.did_warn and st.host_count is not None and st.host_count > st.N:
+                        print("Overflow detected, wrapping around. Will not warn again")
+                        DenseGCM.did_warn = True
+                    return belief, DenseHidden(st, None)
         plan = self.fused_plan()
         if plan is None:
             return self._forward_generic(x, hidden)

@@ -229,6 +229,7 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
     else:
         belief = _lin2(G, w["w_rel2"], ht, w["w_root2"], bias=w["b2"], act=_cabi.ACT[g.act2], status=state.status)
     state.masks_stale = True
+    state.fast_ok = False
     state.version += 1
     state.steps += 1
     state.max_count += 1
