@@ -674,6 +674,113 @@ __global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg
 }
 
 // ------------------------------------------------------------------------------------------------
+// Transposed CSR (edges grouped by SOURCE) of a block-diagonal graph whose per-graph edge ranges are contiguous:
+// what the backward gather needs, without a global sort.  One CTA per graph: histogram of the sources in shared
+// memory, exclusive scan, fill through atomic cursors, then every source row is sorted by sink (rows are short), so
+// the result does not depend on the order the atomics happened in (the gradient sums stay deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_MAXN = 8192;
+__global__ void __launch_bounds__(512) k_csr_transpose(const int64_t* rowptr, const int64_t* col, const int64_t* node_off,
+                                                       const int64_t* sink_local, int64_t* t_rowptr, int64_t* t_col,
+                                                       int64_t n_total) {
+  __shared__ int cnt[TC_MAXN + 1];
+  __shared__ int scan_tmp[16];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n0 = node_off[b], n1 = node_off[b + 1];
+  const int nb = (int)(n1 - n0);
+  const int64_t e0 = rowptr[n0], e1 = rowptr[n1];
+  for (int i = tid; i <= nb; i += 512) cnt[i] = 0;
+  __syncthreads();
+  for (int64_t e = e0 + tid; e < e1; e += 512) atomicAdd(&cnt[(int)(col[e] - n0) + 1], 1);
+  __syncthreads();
+  // inclusive scan of cnt[1..nb] in place (cnt[0] = 0): 16 values per thread, then a block scan of the thread totals
+  const int per = (nb + 511) / 512;
+  const int base = 1 + tid * per;
+  int sum = 0;
+  for (int i = 0; i < per; ++i)
+    if (base + i <= nb) sum += cnt[base + i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(GCM_FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) scan_tmp[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
+  int run = woff + incl - sum;
+  for (int i = 0; i < per; ++i)
+    if (base + i <= nb) {
+      run += cnt[base + i];
+      cnt[base + i] = run;                      // cnt[j + 1] = end of source j's row (local), cnt[j] = its start
+    }
+  __syncthreads();
+  for (int i = tid; i < nb; i += 512) t_rowptr[n0 + i] = e0 + cnt[i];
+  if (b == gridDim.x - 1 && tid == 0) t_rowptr[n_total] = e1;
+  __syncthreads();
+  // fill: cursor of source j = cnt[j] (start), advanced atomically; afterwards cnt[j] = end of row j
+  if (sink_local) {   // the builder's edge list names every edge's sink: coalesced walk over the edges
+    for (int64_t e = e0 + tid; e < e1; e += 512) {
+      const int j = (int)(col[e] - n0);
+      const int at = atomicAdd(&cnt[j], 1);
+      t_col[e0 + at] = n0 + sink_local[e];      // the sink's flat id (= its position among the evaluated rows)
+    }
+  } else {
+    for (int64_t i = n0 + tid; i < n1; i += 512) {
+      for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+        const int j = (int)(col[e] - n0);
+        const int at = atomicAdd(&cnt[j], 1);
+        t_col[e0 + at] = i;
+      }
+    }
+  }
+  __syncthreads();
+  // cnt[j] is now the END of row j; its start is the end of row j - 1 (0 for j = 0).  Every row is sorted by sink in a
+  // thread-local buffer (one read and one write of the row; sorting in place in global memory cost a read-modify-write
+  // per shifted element and 6 of the kernel's 7.9 ms at cfg5); rows longer than the buffer are sorted in place.
+  constexpr int TB = 96;
+  for (int j = tid; j < nb; j += 512) {
+    const int r0 = j ? cnt[j - 1] : 0, r1 = cnt[j];
+    int64_t* row = t_col + e0;
+    const int len = r1 - r0;
+    if (len <= 1) continue;
+    if (len <= TB) {
+      int buf[TB];
+      for (int a = 0; a < len; ++a) {
+        const int v = (int)(row[r0 + a] - n0);
+        int p = a - 1;
+        while (p >= 0 && buf[p] > v) {
+          buf[p + 1] = buf[p];
+          --p;
+        }
+        buf[p + 1] = v;
+      }
+      for (int a = 0; a < len; ++a) row[r0 + a] = n0 + buf[a];
+    } else {
+      for (int a = r0 + 1; a < r1; ++a) {
+        const int64_t v = row[a];
+        int p = a - 1;
+        while (p >= r0 && row[p] > v) {
+          row[p + 1] = row[p];
+          --p;
+        }
+        row[p + 1] = v;
+      }
+    }
+  }
+}
+
+extern "C" int gcm_sparse_csr_transpose(const int64_t* rowptr, const int64_t* col, const int64_t* node_off,
+                                        const int64_t* sink_local, int B, int64_t n_total, int64_t* t_rowptr,
+                                        int64_t* t_col, void* stream) {
+  GCM_REQUIRE(rowptr && col && node_off && t_rowptr && t_col && B >= 0 && n_total >= 0, "sparse_csr_transpose: bad arguments");
+  if (B == 0) return GCM_OK;
+  k_csr_transpose<<<B, 512, 0, (cudaStream_t)stream>>>(rowptr, col, node_off, sink_local, t_rowptr, t_col, n_total);
+  return gcm_check_launch("k_csr_transpose");
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, const int64_t* taus,

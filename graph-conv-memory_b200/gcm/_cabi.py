@@ -123,6 +123,7 @@ _SIGNATURES = {
     "gcm_dense_step_fwd_zc": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), C.POINTER(GnnC), _P, _P, _P, _P]),
     "gcm_set_edge_builder": (_I, [_I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "gcm_sparse_csr_transpose": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
                                       _P, _P, _P, _P, _P, _P, _P]),
     "gcm_tc_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),

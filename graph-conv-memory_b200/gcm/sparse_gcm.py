@@ -176,7 +176,8 @@ class SparseGCM(torch.nn.Module):
             # every row is new (hidden=None, all-at-once): the builder's per-sink offsets ARE the CSR row pointer
             # and it writes the flat column ids in the same pass
             new, edge_off, flat_col = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, hops, radius, offsets)
-            csr = sparse_ops.Csr(edge_off, flat_col, n_flat)
+            csr = sparse_ops.Csr(edge_off, flat_col, n_flat, node_off=offsets, max_nodes=max_count,
+                                 sink_local=new[1])        # n_new == n_flat: T == 0, so sink index == row in graph
         else:
             new = sparse_ops.build_edges(nodes, T, taus, new_off, n_new, tmax, hops, radius)
         if old.shape[1] == 0:
@@ -207,9 +208,12 @@ class SparseGCM(torch.nn.Module):
         mx = sparse_ops.graph_conv_csr(h, csr, rows, c2.lin_rel.weight, _one_bias(c2), c2.lin_root.weight, a2)
         assert torch.all(torch.isfinite(mx)), "Got NaN in returned memory, try using tanh activation"
 
-        db, dk = sparse_ops.ragged_arange(taus, n_new)
-        mx_dense = torch.zeros((B, tmax, mx.shape[-1]), device=dev)
-        mx_dense[db, dk] = mx
+        if n_new == B * tmax:
+            mx_dense = mx.view(B, tmax, mx.shape[-1])       # no padding anywhere: the flat rows ARE the padded layout
+        else:
+            db, dk = sparse_ops.ragged_arange(taus, n_new)
+            mx_dense = torch.zeros((B, tmax, mx.shape[-1]), device=dev)
+            mx_dense[db, dk] = mx
         adj_out = torch.sparse_coo_tensor(indices=edges, values=torch.ones(edges.shape[1], device=dev),
                                           size=adj.shape, is_coalesced=True)
         return mx_dense, (nodes, adj_out, counts)

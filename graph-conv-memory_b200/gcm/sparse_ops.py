@@ -126,8 +126,13 @@ def build_edges(nodes: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, new_of
 class Csr:
     """Edges grouped by sink over the flat node numbering, plus (lazily) the transposed grouping."""
 
-    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n: int):
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, n: int, node_off: Optional[torch.Tensor] = None,
+                 max_nodes: int = 0, sink_local: Optional[torch.Tensor] = None):
         self.rowptr, self.col, self.n = rowptr, col, n
+        self.sink_local = sink_local    # [E] every edge's sink as an index inside its graph (optional, speeds transposed())
+        # node_off [B+1]: first flat node of every graph, when the graph is block-diagonal with contiguous per-graph
+        # edge ranges (what SparseGCM builds); lets transposed() run gcm_sparse_csr_transpose instead of a global sort
+        self.node_off, self.max_nodes = node_off, max_nodes
         self._t = {}
 
     @classmethod
@@ -140,6 +145,14 @@ class Csr:
         """(t_rowptr [n+1], t_col [E']) grouping by SOURCE the edges whose sink is an evaluated row;
         t_col = position of that sink among the evaluated rows."""
         key = None if rows is None else rows.data_ptr()
+        if key not in self._t and rows is None and self.node_off is not None and 0 < self.max_nodes <= 8192:
+            t_rowptr = torch.empty_like(self.rowptr)
+            t_col = torch.empty_like(self.col)
+            _cabi.check(_cabi.lib().gcm_sparse_csr_transpose(
+                self.rowptr.data_ptr(), self.col.data_ptr(), self.node_off.data_ptr(), _cabi.ptr(self.sink_local),
+                self.node_off.numel() - 1, self.n,
+                t_rowptr.data_ptr(), t_col.data_ptr(), _cabi.stream_ptr(self.col.device)), "gcm_sparse_csr_transpose")
+            self._t[key] = (t_rowptr, t_col)
         if key not in self._t:
             dev = self.col.device
             if rows is None:

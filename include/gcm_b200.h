@@ -351,6 +351,16 @@ int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_
                              const int64_t* rows, int64_t m, int Fin, int Fout, const float* wt,
                              const float* bias, int act, float* agg_out, float* out, void* stream);
 
+/* The transposed grouping the backward needs, for a block-diagonal graph: rowptr [n+1] / col [E] = CSR by sink over
+ * the flat numbering, node_off [B+1] = first flat node of every graph (each graph has at most 8192 nodes and its
+ * edges are contiguous); sink_local [E] (optional) = every edge's sink as an index inside its graph (row 1 of the
+ * builder's edge list).  Writes t_rowptr [n+1] / t_col [E]: edges grouped by source, sinks ascending within a
+ * source (deterministic).  Replaces a global argsort of the sources (the scatter backward of torch_geometric's
+ * GraphConv, sparse_gcm.py:178,199). */
+int gcm_sparse_csr_transpose(const int64_t* rowptr, const int64_t* col, const int64_t* node_off,
+                             const int64_t* sink_local, int B, int64_t n_total, int64_t* t_rowptr, int64_t* t_col,
+                             void* stream);
+
 /* Backward of the above.  t_rowptr [n+1] / t_col [E] / t_ew group the same edges by SOURCE node, with
  * t_col holding the position (in 0..m-1) of the edge's sink among the evaluated rows.  d_x [n, Fin]
  * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate.

@@ -209,3 +209,29 @@ def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
     assert got[("pairs", 1)].shape[1] > 0
     for k in got:
         assert torch.equal(got[("pairs", 1)], got[k]), k
+
+
+def test_csr_transpose_kernel_equals_the_global_sort():
+    """gcm_sparse_csr_transpose (per-graph counting sort + per-row sort of the sinks) must give exactly the grouping the
+    stable global argsort gives: same row pointers, sinks ascending within every source.  Ragged graphs, one empty."""
+    from gcm import sparse_ops
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    B, N, F = 7, 300, 8
+    nodes = torch.randn(B, N, F, generator=gen)
+    nodes[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, N, 2, generator=gen), dim=1)
+    T = torch.zeros(B, dtype=torch.long)
+    taus = torch.tensor([300, 1, 257, 0, 64, 299, 128])
+    nodes, T, taus = nodes.to(dev), T.to(dev), taus.to(dev)
+    new_off = sparse_ops._excl_cumsum(taus)
+    offsets = sparse_ops._excl_cumsum(T + taus)
+    n = int(taus.sum())
+    edges, edge_off, flat_col = sparse_ops.build_edges(nodes, T, taus, new_off, n, int(taus.max()), (1, 2),
+                                                       (slice(0, 2), 0.3), offsets)
+    fast = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N).transposed(None)
+    fast2 = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N, sink_local=edges[1].contiguous()).transposed(None)
+    slow = sparse_ops.Csr(edge_off, flat_col, n).transposed(None)
+    assert edges.shape[1] > 1000
+    for got in (fast, fast2):
+        assert torch.equal(got[0], slow[0]) and torch.equal(got[1], slow[1])
