@@ -341,6 +341,7 @@ static size_t eh_smem_bytes(int N, int pos_len) {
 constexpr int GC_TM = 64;      // rows per CTA tile
 constexpr int GC_THREADS = 256;
 constexpr int GC_KC = 32;      // K chunk of the weight pack staged in smem
+constexpr int GC_AS = GC_TM + 4;   // row stride of the transposed A tile (16-byte aligned, off the 32-bank period)
 
 struct GraphConvFwdArgs {
   const float* x;         // [n, Fin]
@@ -413,8 +414,8 @@ __device__ __forceinline__ void gc_gather_row(const GraphConvFwdArgs& a, int64_t
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const int f = lane * V + j;
-    dst[f] = acc[j];
-    dst[Fin + f] = own[j];
+    dst[f * GC_AS] = acc[j];
+    dst[(Fin + f) * GC_AS] = own[j];
     if (a.agg_out) a.agg_out[li * Fin + f] = acc[j];
   }
 }
@@ -424,8 +425,8 @@ template <int NT>
 __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwdArgs a) {
   extern __shared__ __align__(16) float gc_smem[];
   const int Fin = a.Fin, Fout = a.Fout, K = 2 * Fin;
-  float* As = gc_smem;                     // [GC_TM][K + 1]
-  float* Ws = As + GC_TM * (K + 1);        // [GC_KC][Fout]
+  float* As = gc_smem;                     // [K][GC_AS]: element (row r, k) at As[k * GC_AS + r]
+  float* Ws = As + K * GC_AS;              // [GC_KC][16 NT]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row0 = (int64_t)blockIdx.x * GC_TM;
 
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwd
   const int V = (Fin == 32 || Fin == 64 || Fin == 128) ? Fin / 32 : 0;
   for (int r = warp; r < GC_TM; r += GC_THREADS / 32) {
     const int64_t li = row0 + r;
-    float* dst = As + r * (K + 1);
+    float* dst = As + r;                   // row r of the transposed tile: feature k at dst[k * GC_AS]
     if (li < a.m) {
       const int64_t i = a.rows ? a.rows[li] : li;
       const int64_t e0 = a.rowptr[i], e1 = a.rowptr[i + 1];
@@ -464,18 +465,22 @@ __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwd
             if (a.ew) v *= a.ew[e];
             acc += v;
           }
-          dst[f] = acc;
-          dst[Fin + f] = a.x[i * Fin + f];
+          dst[f * GC_AS] = acc;
+          dst[(Fin + f) * GC_AS] = a.x[i * Fin + f];
           if (a.agg_out) a.agg_out[li * Fin + f] = acc;
         }
       }
     } else {
-      for (int f = lane; f < K; f += 32) dst[f] = 0.0f;
+      for (int f = lane; f < K; f += 32) dst[f * GC_AS] = 0.0f;
     }
   }
 
   // ---- phase 2: out = act(A W + b), 4 x NT register tile per thread ----
-  const int tr = tid >> 4, tc = tid & 15;   // 16 row groups x 16 column groups
+  // A tile stored transposed ([k][row], stride GC_AS) and the weight chunk padded to 16 NT columns, so that a thread's
+  // 4 rows and its groups of 4 columns are one 128-bit shared load each (2-3 loads per 16-32 FMAs instead of 8 scalar
+  // ones: ncu had the kernel issue-bound with this product as half of its instructions).
+  constexpr int NV = NT < 4 ? NT : 4, NG = NT / NV, WS = 16 * NT;
+  const int tr = tid >> 4, tc = tid & 15;   // 16 row groups x 16 column groups; columns g*16*NV + tc*NV + v
   float acc[4][NT];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -484,19 +489,32 @@ __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwd
   for (int k0 = 0; k0 < K; k0 += GC_KC) {
     __syncthreads();
     const int kc = min(GC_KC, K - k0);
-    for (int i = tid; i < kc * Fout; i += GC_THREADS) Ws[i] = __ldg(a.wt + (size_t)k0 * Fout + i);
+    for (int i = tid; i < kc * WS; i += GC_THREADS) {
+      const int kk = i / WS, c = i - kk * WS;
+      Ws[i] = c < Fout ? __ldg(a.wt + (size_t)(k0 + kk) * Fout + c) : 0.0f;
+    }
     __syncthreads();
+#pragma unroll 4
     for (int kk = 0; kk < kc; ++kk) {
-      float av[4];
+      const float4 a4 = *reinterpret_cast<const float4*>(As + (k0 + kk) * GC_AS + tr * 4);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      float wv[NT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[(tr * 4 + i) * (K + 1) + k0 + kk];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int c = tc + 16 * j;
-        const float wv = c < Fout ? Ws[kk * Fout + c] : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(av[i], wv, acc[i][j]);
+      for (int g = 0; g < NG; ++g) {
+        if (NV == 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(Ws + kk * WS + g * 64 + tc * 4);
+          wv[g * 4] = w4.x; wv[g * 4 + 1] = w4.y; wv[g * 4 + 2] = w4.z; wv[g * 4 + 3] = w4.w;
+        } else if (NV == 2) {
+          const float2 w2 = *reinterpret_cast<const float2*>(Ws + kk * WS + tc * 2);
+          wv[0] = w2.x; wv[1] = w2.y;
+        } else {
+          wv[0] = Ws[kk * WS + tc];
+        }
       }
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
   }
 #pragma unroll
@@ -505,10 +523,10 @@ __global__ void __launch_bounds__(GC_THREADS) k_graphconv_fwd(const GraphConvFwd
     if (li < a.m) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const int c = tc + 16 * j;
+        const int c = (j / NV) * (16 * NV) + tc * NV + (j % NV);
         if (c < Fout) {
           const float z = acc[i][j] + (a.bias ? __ldg(a.bias + c) : 0.0f);
-          a.out[li * Fout + c] = gcm_act_fwd(z, a.act);
+          a.out[li * Fout + c] = gcm_act_fast(z, a.act);
         }
       }
     }
@@ -863,7 +881,7 @@ extern "C" int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, c
               Fin, Fout);
   if (m == 0) return GCM_OK;
   GraphConvFwdArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out};
-  const size_t smem = ((size_t)GC_TM * (2 * Fin + 1) + (size_t)GC_KC * Fout) * 4;
+  const size_t smem = ((size_t)2 * Fin * GC_AS + (size_t)GC_KC * 16 * ((Fout + 15) / 16 <= 1 ? 1 : ((Fout + 15) / 16 <= 2 ? 2 : ((Fout + 15) / 16 <= 4 ? 4 : 8)))) * 4;
   const int64_t grid = (m + GC_TM - 1) / GC_TM;
   GCM_REQUIRE(grid < 2147483647LL, "sparse_graphconv_fwd: too many rows");
   const int nt = (Fout + 15) / 16;
