@@ -185,7 +185,9 @@ def algorithmic(workload, B, N, F, H, extra=None):
         return "hbm", per * B, "bytes"
     if workload.startswith("cfg4"):
         if workload == "cfg4-euclid":
-            return "fp32", 2.0 * B * B * N * F, "flop"
+            # the cross-batch mean distance: 2 B^2 N F useful flops per step, issued as THREE tf32 MMAs per product
+            # (3xTF32: fp32-accurate) by k_euclid_tc -> the tensor-pipe work is 3x the useful figure
+            return "tensor", 3 * 2.0 * B * B * N * F, "flop"
         per = N * F * 4 + 2 * F * 4 + N // 8 * 2 + H * 4 + 16
         return "hbm", per * B, "bytes"
     if workload in ("cfg3", "cfg3-seq"):
@@ -344,6 +346,8 @@ def main():
             kern_ms = e0.elapsed_time(e1) / K
             launches = int(lib.gcm_launch_count() - n_l0)
             kernel_name = lib.gcm_last_kernel().decode()
+            if args.workload == "cfg4-euclid":
+                kernel_name = "k_euclid_tc (cross-batch mean distance, 3xTF32 tcgen05) + " + kernel_name
             # end to end through the public API from HOST buffers: every step copies its observation from pinned
             # host memory and reads its belief back; the copies run on their own streams (PCIe is full duplex)
             # and overlap the neighbouring steps' kernels, ordered by events
@@ -507,7 +511,8 @@ def main():
         if algo_unit == "bytes":
             achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
         else:
-            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e12, 72.0, "TFLOP/s"
+            # tf32 dense peak = half of the measured bf16 peak (MEASURED_PEAKS.json has no tf32 entry of its own)
+            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e12, pk["bf16_tflops"] / 2.0, "TFLOP/s"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -526,7 +531,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
                          "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind if unit == "GB/s"
-                         else "fp32 FMA nominal (CUDA cores)", "kernel": kernel_name, "kernel_ms": kern_ms,
+                         else pk_kind + " bf16 dense / 2 = tf32 dense; achieved counts the 3 tf32 MMAs of every 3xTF32 product", "kernel": kernel_name, "kernel_ms": kern_ms,
                          "algorithmic_per_launch": algo, "host_us_per_call": host_us},
         }
         if e2e is not None:

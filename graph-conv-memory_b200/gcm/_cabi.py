@@ -94,6 +94,8 @@ _SIGNATURES = {
     "gcm_state_log_write": (_I, [C.POINTER(DenseStateC), _P, _I, _P]),
     "gcm_state_ingest": (_I, [C.POINTER(DenseStateC), _P, _P, _P, _P, _P]),
     "gcm_euclid_batchmean": (_I, [C.POINTER(DenseStateC), _P, _I, _P, _P, _P]),
+    "gcm_euclid_tc_scratch": (C.c_longlong, [_I, _I]),
+    "gcm_euclid_batchmean_tc": (_I, [C.POINTER(DenseStateC), _P, _I, _P, _P, _P, _P]),
     "gcm_select_dense": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(SelectorC), _P]),
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,

@@ -284,6 +284,26 @@ def build_plan(module) -> Optional[FusedPlan]:
 # ------------------------------------------------------------------------------------------------
 # execution
 # ------------------------------------------------------------------------------------------------
+EUCLID_TC = True     # tensor-core batch-mean distances (csrc/gcm_euclid_tc.cu); False: the CUDA-core kernel (tests compare both)
+
+
+def euclid_batchmean(state: DenseState, cur: torch.Tensor, dist_param, dist: torch.Tensor) -> None:
+    """dist[b, slot] = mean_p ||cur_p - nodes[b, slot]||_2 (distance.py:48-49) for every slot of the node log."""
+    lib = _cabi.lib()
+    stream = _cabi.stream_ptr(state.device)
+    F = state.F
+    if EUCLID_TC and F % 16 == 0 and F <= 64 and 128 <= cur.shape[0] <= 16384:
+        need = int(lib.gcm_euclid_tc_scratch(cur.shape[0], F))
+        scratch = state.__dict__.get("_euclid_scratch")
+        if scratch is None or scratch.numel() < need:
+            scratch = state.__dict__["_euclid_scratch"] = torch.empty(need, device=state.device, dtype=torch.float32)
+        _cabi.check(lib.gcm_euclid_batchmean_tc(state.c_ref(), cur.data_ptr(), cur.shape[0], _cabi.ptr(dist_param),
+                                                scratch.data_ptr(), dist.data_ptr(), stream), "gcm_euclid_batchmean_tc")
+    else:
+        _cabi.check(lib.gcm_euclid_batchmean(state.c_ref(), cur.data_ptr(), cur.shape[0], _cabi.ptr(dist_param),
+                                             dist.data_ptr(), stream), "gcm_euclid_batchmean")
+
+
 def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: torch.Tensor) -> None:
     lib = _cabi.lib()
     dev = state.device
@@ -301,9 +321,7 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
         euc = next(s for s in plan.sels if s.kind == _cabi.SEL_EUCLIDEAN)
         cur = state.__dict__.get("_euclid_cur_all")
         cur = x if cur is None else cur
-        _cabi.check(lib.gcm_euclid_batchmean(state.c_ref(), cur.data_ptr(), cur.shape[0],
-                                             _cabi.ptr(euc.dist_param), dist.data_ptr(), stream),
-                    "gcm_euclid_batchmean")
+        euclid_batchmean(state, cur.contiguous(), euc.dist_param, dist)
     sels, n = plan.selectors_c(state.F, dist)
     flags = 0
     gnn_c = plan.gnn.packed(dev)
@@ -409,9 +427,7 @@ def zc_step(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> Optional[tor
         dist = state.__dict__.setdefault("_euclid_dist", torch.empty(state.B, state.C, device=dev))
         cur = state.__dict__.get("_euclid_cur_all")
         cur = x if cur is None else cur
-        _cabi.check(lib.gcm_euclid_batchmean(state.c_ref(), cur.data_ptr(), cur.shape[0],
-                                             _cabi.ptr(plan.sels[0].dist_param), dist.data_ptr(), stream),
-                    "gcm_euclid_batchmean")
+        euclid_batchmean(state, cur.contiguous(), plan.sels[0].dist_param, dist)
     sels, _ = plan.selectors_c(state.F, dist)
     belief = torch.empty(state.B, plan.gnn.H2, device=dev, dtype=torch.float32)
     _cabi.check(lib.gcm_dense_step_fwd_zc(state.c_ref(), x.data_ptr(), sels, C.byref(gnn_c), state.zcache.data_ptr(),

@@ -192,6 +192,12 @@ int gcm_state_ingest(const gcm_dense_state* st, const float* nodes_in, const flo
  * slots of the nodes currently in the window.  Runs BEFORE gcm_dense_step_fwd of the same step. */
 int gcm_euclid_batchmean(const gcm_dense_state* st, const float* cur, int n_cur,
                          const float* dist_param, float* dist, void* stream);
+/* The same distances through the tensor cores: ||c - n||^2 = |n|^2 + |c|^2 - 2 n.c with n.c in 3xTF32 (tcgen05; the
+ * matmul form torch.cdist itself uses at these sizes).  F a multiple of 16, <= 64; scratch: gcm_euclid_tc_scratch(n_cur,
+ * F) floats of device memory (the observations pre-split into K-major tiles). */
+long long gcm_euclid_tc_scratch(int n_cur, int F);
+int gcm_euclid_batchmean_tc(const gcm_dense_state* st, const float* cur, int n_cur, const float* dist_param,
+                            float* scratch, float* dist, void* stream);
 
 /* The selectors' own forward(nodes, adj_mats, edge_weights, num_nodes, B) on the reference's DENSE
  * tensors (edge_selectors/{temporal,dense,distance}.py): ORs 1s into adj [B,N,N] f32 in place.

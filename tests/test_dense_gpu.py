@@ -335,3 +335,33 @@ def test_rowwise_preprocessor_runs_fused_and_matches_the_reference_step(spec):
     x = obs[0].to(dev).requires_grad_(True)
     belief, h2 = mod(x, hidden)
     assert not isinstance(h2, DenseHidden) and belief.requires_grad
+
+
+@pytest.mark.parametrize("B,C,F,learned", [(300, 9, 64, False), (129, 5, 32, True), (1024, 6, 16, False)])
+def test_euclid_batchmean_tensor_core_kernel_matches_the_cuda_core_kernel(B, C, F, learned):
+    """EuclideanEdge's cross-batch mean distance (distance.py:48-49) through tcgen05 (|n|^2 + |c|^2 - 2 n.c in 3xTF32)
+    against the difference-squared CUDA-core kernel and against float64: clustered rows (small distances, where the
+    matmul form cancels), a batch that is not a multiple of the 128-observation tile, the learned scale."""
+    from gcm import fused
+    from gcm.state import DenseState
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(B + F)
+    centres = 2.0 * torch.randn(5, F, generator=gen)
+    st = DenseState(B, C, F, dev)
+    st.nodes.copy_((centres[torch.randint(0, 5, (B, C), generator=gen)] + 0.05 * torch.randn(B, C, F, generator=gen)).to(dev))
+    cur = (centres[torch.randint(0, 5, (B,), generator=gen)] + 0.05 * torch.randn(B, F, generator=gen)).to(dev)
+    param = torch.tensor([-1.7], device=dev) if learned else None
+    out = {}
+    try:
+        for tc_on in (False, True):
+            fused.EUCLID_TC = tc_on
+            d = torch.empty(B, C, device=dev)
+            fused.euclid_batchmean(st, cur, param, d)
+            out[tc_on] = d
+    finally:
+        fused.EUCLID_TC = True
+    ref = torch.cdist(st.nodes.double().view(1, B * C, F), cur.double().view(1, B, F), compute_mode="donot_use_mm_for_euclid_dist")
+    ref = ref.mean(-1).view(B, C) / (1.7 if learned else 1.0)
+    for k, d in out.items():
+        assert rel_err(d, ref) < 2e-5, k
