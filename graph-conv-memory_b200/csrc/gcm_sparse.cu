@@ -920,10 +920,21 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
     // register-tiled kernels of the dense path instead of the element-owned tile kernel below (24.5 -> ~6 ms per layer
     // at cfg5):  dz = d_out * act'(out);  d_agg = dz W_rel;  d_x = dz W_root;  dW_rel += dz^T agg;  dW_root += dz^T x
     if (int rc = gcm_act_backward(d_out, out, act, (long long)m * Fout, dz_scratch, stream)) return rc;
-    if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_rel_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_agg,
-                             Fin, nullptr, 0, stream)) return rc;
-    if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_root_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_x,
-                             Fin, nullptr, 0, stream)) return rc;
+    const bool tc_ok = Fin % 16 == 0 && Fout % 16 == 0 && Fin >= 16 && Fout >= 16 &&
+                       ((reinterpret_cast<uintptr_t>(dz_scratch) | reinterpret_cast<uintptr_t>(w_rel_t) |
+                         reinterpret_cast<uintptr_t>(w_root_t) | reinterpret_cast<uintptr_t>(d_agg) |
+                         reinterpret_cast<uintptr_t>(d_x)) & 15) == 0;
+    if (tc_ok) {   // 3xTF32 on the tensor cores (fp32-accurate), persistent over the row tiles
+      if (int rc = gcm_linear_tc32(dz_scratch, Fout, Fout, w_rel_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin,
+                                   d_agg, Fin, nullptr, stream)) return rc;
+      if (int rc = gcm_linear_tc32(dz_scratch, Fout, Fout, w_root_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin,
+                                   d_x, Fin, nullptr, stream)) return rc;
+    } else {
+      if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_rel_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_agg,
+                               Fin, nullptr, 0, stream)) return rc;
+      if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_root_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_x,
+                               Fin, nullptr, 0, stream)) return rc;
+    }
     if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, agg, Fin, Fin, m, d_w_rel, d_b, stream)) return rc;
     if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, x, Fin, Fin, m, d_w_root, nullptr, stream)) return rc;
     const int64_t g2 = (n + 7) / 8;

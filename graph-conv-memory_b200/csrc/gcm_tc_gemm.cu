@@ -217,6 +217,8 @@ struct LinearTc32Args {
   int Ho;
   float* out; long long ldo;
   int32_t* status;
+  long long tiles;
+  uint32_t tmem_cols;   // power of two >= 2 K1 + K2 / 2 + Ho
 };
 
 constexpr int TC32_THREADS = 288;   // warps 0-3: A rows -> TMEM, epilogue; warps 4-8: weight staging; warp 8 lane 0: MMA issue
@@ -228,9 +230,9 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
   float* Wlo = Whi + (size_t)Ho * K1;
   __nv_bfloat16* W2s = reinterpret_cast<__nv_bfloat16*>(Wlo + (size_t)Ho * K1);   // [Ho x K2] canonical (bf16)
   uint64_t* bars = reinterpret_cast<uint64_t*>(W2s + (size_t)Ho * K2);
-  uint64_t* full = bars;         // A operands are in TMEM (128 arrivals)
-  uint64_t* wready = bars + 1;   // weights are in shared memory (160 arrivals)
-  uint64_t* done = bars + 2;     // all MMAs completed
+  uint64_t* full = bars;         // A operands of the current tile are in TMEM (128 arrivals)
+  uint64_t* wready = bars + 1;   // weights are in shared memory (160 arrivals, once)
+  uint64_t* done = bars + 2;     // all MMAs of the current tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -239,89 +241,92 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
     tc::mbar_init(done, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 4) tc::tmem_alloc(tmem_slot, a.tmem_cols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t col_hi = 0, col_lo = 128, col_a2 = 256, col_d = 320;   // K1 <= 128, K2 / 2 <= 64, Ho <= 128
+  const uint32_t col_hi = 0, col_lo = K1, col_a2 = 2 * K1, col_d = 2 * K1 + K2 / 2;
+  const long long n_it = (a.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // persistent: tiles of this CTA
   if (warp < 4) {
-    // the tile's rows go to TMEM while the other warps stage the weights
-    const long long r = (long long)blockIdx.x * 128 + tid;
-    const bool ok = r < a.rows;
+    // the tile's rows go to TMEM while the other warps stage the weights (first tile) / idle (later tiles)
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
-    const float4* x1 = reinterpret_cast<const float4*>(a.X1 + (ok ? r : 0) * a.ldx1);
-    for (int k0 = 0; k0 < K1; k0 += 64) {        // 16 independent 16-byte loads in flight per thread
-      float4 v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        v[j] = (ok && k0 + 4 * j < K1) ? __ldg(x1 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (k0 + 16 * c < K1) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            tc::split_tf32(v[4 * c + j].x, hi[4 * j], lo[4 * j]);
-            tc::split_tf32(v[4 * c + j].y, hi[4 * j + 1], lo[4 * j + 1]);
-            tc::split_tf32(v[4 * c + j].z, hi[4 * j + 2], lo[4 * j + 2]);
-            tc::split_tf32(v[4 * c + j].w, hi[4 * j + 3], lo[4 * j + 3]);
-          }
-          tc::tmem_st16(lane_addr + col_hi + k0 + 16 * c, hi);
-          tc::tmem_st16(lane_addr + col_lo + k0 + 16 * c, lo);
-        }
-      }
-    }
-    if (K2) {
-      const float4* x2 = reinterpret_cast<const float4*>(a.X2 + (ok ? r : 0) * a.ldx2);
-      for (int k0 = 0; k0 < K2; k0 += 64) {
+    bool bad = false;
+    for (long long it = 0; it < n_it; ++it) {
+      const long long r = (blockIdx.x + it * gridDim.x) * 128 + tid;
+      const bool ok = r < a.rows;
+      const float4* x1 = reinterpret_cast<const float4*>(a.X1 + (ok ? r : 0) * a.ldx1);
+      for (int k0 = 0; k0 < K1; k0 += 64) {        // 16 independent 16-byte loads in flight per thread
         float4 v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          v[j] = (ok && k0 + 4 * j < K2) ? __ldg(x2 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[j] = (ok && k0 + 4 * j < K1) ? __ldg(x1 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (k0 + 16 * c < K2) {
-            uint32_t pk[8];
+          if (k0 + 16 * c < K1) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              pk[2 * j] = tc::pack_bf16(v[4 * c + j].x, v[4 * c + j].y);
-              pk[2 * j + 1] = tc::pack_bf16(v[4 * c + j].z, v[4 * c + j].w);
+              tc::split_tf32(v[4 * c + j].x, hi[4 * j], lo[4 * j]);
+              tc::split_tf32(v[4 * c + j].y, hi[4 * j + 1], lo[4 * j + 1]);
+              tc::split_tf32(v[4 * c + j].z, hi[4 * j + 2], lo[4 * j + 2]);
+              tc::split_tf32(v[4 * c + j].w, hi[4 * j + 3], lo[4 * j + 3]);
             }
-            tc::tmem_st8(lane_addr + col_a2 + ((k0 + 16 * c) >> 1), pk);
+            tc::tmem_st16(lane_addr + col_hi + k0 + 16 * c, hi);
+            tc::tmem_st16(lane_addr + col_lo + k0 + 16 * c, lo);
           }
         }
       }
-    }
-    tc::wait_st();
-    tc::fence_before_sync();
-    tc::mbar_arrive(full);
-    tc::mbar_wait(done, 0);
-    tc::fence_after_sync();
-    bool bad = false;
-    for (int n0 = 0; n0 < Ho; n0 += 16) {
-      uint32_t d[16];
-      tc::tmem_ld16(lane_addr + col_d + n0, d);
-      tc::wait_ld();
-      float f[16];
+      if (K2) {
+        const float4* x2 = reinterpret_cast<const float4*>(a.X2 + (ok ? r : 0) * a.ldx2);
+        for (int k0 = 0; k0 < K2; k0 += 64) {
+          float4 v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(d[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.0f);
-      if (a.act == GCM_ACT_EXP2X) {
+          for (int j = 0; j < 16; ++j)
+            v[j] = (ok && k0 + 4 * j < K2) ? __ldg(x2 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = tcg_exp2x(f[j]);
-      } else {
-        gcm_act_fast_vec(f, a.act);
+          for (int c = 0; c < 4; ++c) {
+            if (k0 + 16 * c < K2) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                pk[2 * j] = tc::pack_bf16(v[4 * c + j].x, v[4 * c + j].y);
+                pk[2 * j + 1] = tc::pack_bf16(v[4 * c + j].z, v[4 * c + j].w);
+              }
+              tc::tmem_st8(lane_addr + col_a2 + ((k0 + 16 * c) >> 1), pk);
+            }
+          }
+        }
       }
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(full);
+      tc::mbar_wait(done, (uint32_t)(it & 1));
+      tc::fence_after_sync();
+      for (int n0 = 0; n0 < Ho; n0 += 16) {
+        uint32_t d[16];
+        tc::tmem_ld16(lane_addr + col_d + n0, d);
+        tc::wait_ld();
+        float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bad |= !isfinite(f[j]);
-      if (ok) {
-        float4* o = reinterpret_cast<float4*>(a.out + r * a.ldo + n0);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(d[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.0f);
+        if (a.act == GCM_ACT_EXP2X) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) f[j] = tcg_exp2x(f[j]);
+        } else {
+          gcm_act_fast_vec(f, a.act);
+        }
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bad |= !isfinite(f[j]);
+          float4* o = reinterpret_cast<float4*>(a.out + r * a.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
       }
+      tc::fence_before_sync();   // the accumulator and the A columns are free again: the next tile may overwrite them
     }
-    if (a.status && bad && ok) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
-    tc::fence_before_sync();
+    if (a.status && bad) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
   } else {
     stage_w_tf32<TC32_THREADS - 128>(a.W1, Ho, K1, Whi, Wlo, tid - 128);
     if (K2) stage_w_bf16<TC32_THREADS - 128>(a.W2, Ho, K2, W2s, tid - 128);
@@ -329,33 +334,33 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
     tc::mbar_arrive(wready);
     if (warp == 8 && lane == 0) {
       tc::mbar_wait(wready, 0);
-      tc::mbar_wait(full, 0);
-      tc::fence_after_sync();
       const uint32_t idesc = tc::idesc_tf32(128, Ho);
       const uint32_t sbo = (uint32_t)(K1 / 4) * 128u;
-      bool acc = false;
-      for (int pass = 0; pass < 3; ++pass) {       // lo*Bhi, hi*Blo, hi*Bhi
-        const uint32_t a_col = pass == 0 ? col_lo : col_hi;
-        const float* bsrc = pass == 1 ? Wlo : Whi;
-        for (int ks = 0; ks < K1 / 8; ++ks) {
-          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
-          tc::mma_tf32_ts(tbase + col_d, tbase + a_col + ks * 8, bdesc, idesc, acc);
-          acc = true;
+      const uint32_t idesc16 = tc::idesc_bf16(128, Ho);
+      const uint32_t sbo16 = (uint32_t)(K2 ? K2 / 8 : 1) * 128u;
+      for (long long it = 0; it < n_it; ++it) {
+        tc::mbar_wait(full, (uint32_t)(it & 1));
+        tc::fence_after_sync();
+        bool acc = false;
+        for (int pass = 0; pass < 3; ++pass) {       // lo*Bhi, hi*Blo, hi*Bhi
+          const uint32_t a_col = pass == 0 ? col_lo : col_hi;
+          const float* bsrc = pass == 1 ? Wlo : Whi;
+          for (int ks = 0; ks < K1 / 8; ++ks) {
+            const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
+            tc::mma_tf32_ts(tbase + col_d, tbase + a_col + ks * 8, bdesc, idesc, acc);
+            acc = true;
+          }
         }
-      }
-      if (K2) {
-        const uint32_t idesc16 = tc::idesc_bf16(128, Ho);
-        const uint32_t sbo16 = (uint32_t)(K2 / 8) * 128u;
         for (int ks = 0; ks < K2 / 16; ++ks) {
           const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(W2s) + ks * 256, 128, sbo16);
           tc::mma_bf16_ts(tbase + col_d, tbase + col_a2 + ks * 8, bdesc, idesc16, true);
         }
+        tc::mma_commit(done);
       }
-      tc::mma_commit(done);
     }
   }
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tbase, 512);
+  if (warp == 4) tc::tmem_dealloc(tbase, a.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -537,7 +542,9 @@ extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const fl
                 reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
               "linear_tc32: operands must be 16-byte aligned");
   if (rows == 0) return GCM_OK;
-  LinearTc32Args a{X1, ldx1, K1, W1, X2, ldx2, X2 ? K2 : 0, W2, bias, act, rows, Ho, out, ldo, status};
+  LinearTc32Args a{X1, ldx1, K1, W1, X2, ldx2, X2 ? K2 : 0, W2, bias, act, rows, Ho, out, ldo, status, (rows + 127) / 128, 32};
+  const uint32_t need_cols = (uint32_t)(2 * K1 + a.K2 / 2 + Ho);
+  while (a.tmem_cols < need_cols) a.tmem_cols <<= 1;
   const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64;
   static bool attr_done = false;
   if (!attr_done) {
@@ -547,8 +554,14 @@ extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const fl
     }
     attr_done = true;
   }
-  const long long grid = (rows + 127) / 128;
-  GCM_REQUIRE(grid < 2147483647LL, "linear_tc32: too many rows");
+  // persistent: as many CTAs as fit at once (TMEM columns and shared memory decide), each walks its tiles
+  int per_sm = (int)(512 / a.tmem_cols);
+  const int by_smem = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > 2) per_sm = 2;   // 104 registers x 288 threads: two CTAs per SM
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)per_sm * gcm_num_sms();
+  if (grid > a.tiles) grid = a.tiles;
   k_linear_tc32<<<(unsigned)grid, TC32_THREADS, smem, (cudaStream_t)stream>>>(a);
   return gcm_check_launch("k_linear_tc32");
 }
