@@ -909,7 +909,7 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
                                         const int64_t* t_col, const float* t_ew, int Fin, int Fout,
                                         const float* w_rel, const float* w_root, int act, float* d_agg, float* d_x,
                                         float* d_w_rel, float* d_w_root, float* d_b, float* dz_scratch,
-                                        const float* w_rel_t, const float* w_root_t, void* stream) {
+                                        const float* w_rel_t, const float* w_root_t, float* outer_ws, void* stream) {
   GCM_REQUIRE(x && agg && out && d_out && t_rowptr && w_rel && w_root && d_agg && d_x && d_w_rel && d_w_root,
               "sparse_graphconv_bwd: null pointer");
   GCM_REQUIRE(Fin >= 1 && Fin <= 128 && Fout >= 1 && Fout <= 128 && m >= 0 && n >= 0,
@@ -935,8 +935,15 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
       if (int rc = gcm_linear2(dz_scratch, Fout, Fout, w_root_t, nullptr, 0, 0, nullptr, nullptr, GCM_ACT_NONE, m, Fin, d_x,
                                Fin, nullptr, 0, stream)) return rc;
     }
-    if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, agg, Fin, Fin, m, d_w_rel, d_b, stream)) return rc;
-    if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, x, Fin, Fin, m, d_w_root, nullptr, stream)) return rc;
+    // weight gradients: 3xTF32 reductions over the m rows on the tensor cores for wide layers; at 64 x 64 half of that
+    // kernel's row-owning threads would idle and the CUDA-core tile (1.67 ms per reduction at cfg5) beats it (2.10 ms)
+    if (outer_ws && tc_ok && (Fin > 64 || Fout > 64)) {
+      if (int rc = gcm_outer_reduce_tc32(dz_scratch, Fout, Fout, agg, Fin, Fin, m, outer_ws, d_w_rel, d_b, stream)) return rc;
+      if (int rc = gcm_outer_reduce_tc32(dz_scratch, Fout, Fout, x, Fin, Fin, m, outer_ws, d_w_root, nullptr, stream)) return rc;
+    } else {
+      if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, agg, Fin, Fin, m, d_w_rel, d_b, stream)) return rc;
+      if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, x, Fin, Fin, m, d_w_root, nullptr, stream)) return rc;
+    }
     const int64_t g2 = (n + 7) / 8;
     GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
     k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);

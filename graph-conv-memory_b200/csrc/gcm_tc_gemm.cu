@@ -493,6 +493,129 @@ __global__ void __launch_bounds__(TCG_THREADS, 2) k_outer_tc(const OuterTcArgs a
   if (warp == 8) tc::tmem_dealloc(tbase, 256);
 }
 
+// The same reduction in 3xTF32 (fp32-accurate: hi/lo split of both operands, lo*Bhi + hi*Blo + hi*Bhi), for callers that
+// stay in float32 (the sparse GraphConv backward, DenseEdge states with a float32 cache).  A^T hi | lo take 64 + 64 TMEM
+// columns per group, the X chunk hi | lo 2 x 32 KB of shared memory per group.
+__global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs a) {
+  extern __shared__ __align__(128) unsigned char o32_smem[];
+  float* Bs = reinterpret_cast<float*>(o32_smem);                 // [group][hi, lo][128 x 64] canonical K-major
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 4 * 128 * OT_KC);
+  uint64_t* full = bars;      // [2]
+  uint64_t* done = bars + 2;  // [2]
+  uint64_t* fin = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Ho = a.Ho, Hi = a.Hi;
+  if (tid == 0) {
+    tc::mbar_init(&full[0], 128); tc::mbar_init(&full[1], 128);
+    tc::mbar_init(&done[0], 1);   tc::mbar_init(&done[1], 1);
+    tc::mbar_init(fin, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
+  const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
+  const long long nchunks = r_end > r_begin ? (r_end - r_begin + OT_KC - 1) / OT_KC : 0;
+
+  if (warp < 8) {
+    const int g = warp >> 2;
+    const int ch = tid & 127;                                      // output channel o (A) / input channel i (X)
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t col_a = 128 + g * 128;                          // hi at +0 .. 63, lo at +64 .. 127
+    const bool a_ok = ch < Ho, x_ok = ch < Hi;
+    float colsum = 0.0f;
+    float* bhi = Bs + (size_t)g * 2 * 128 * OT_KC + ((ch >> 3) * (OT_KC >> 2)) * 32 + (ch & 7) * 4;
+    float* blo = bhi + 128 * OT_KC;
+    for (long long j = g; j < nchunks; j += 2) {
+      const long long it = j >> 1;
+      const long long r0 = r_begin + j * OT_KC;
+      if (it > 0) {
+        tc::mbar_wait(&done[g], (uint32_t)((it - 1) & 1));
+        tc::fence_after_sync();
+      }
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {                                // 16 rows (k) at a time
+        const long long rq = r0 + q * 16;
+        const float* pa = a.A + rq * a.lda + ch;
+        const float* px = a.X + rq * a.ldx + ch;
+        float av[16], xv[16];
+        const bool whole = rq + 16 <= r_end;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) av[u] = (a_ok && (whole || rq + u < r_end)) ? __ldcs(pa + u * a.lda) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) xv[u] = (x_ok && (whole || rq + u < r_end)) ? __ldcs(px + u * a.ldx) : 0.0f;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          colsum += av[u];
+          tc::split_tf32(av[u], hi[u], lo[u]);
+        }
+        tc::tmem_st16(lane_addr + col_a + q * 16, hi);
+        tc::tmem_st16(lane_addr + col_a + 64 + q * 16, lo);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {   // 4 rows (k) of channel ch -> one 16-byte core-matrix row, hi and lo
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tc::split_tf32(xv[s4 * 4 + u], h[u], l[u]);
+          *reinterpret_cast<uint4*>(bhi + (q * 4 + s4) * 32) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(blo + (q * 4 + s4) * 32) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      tc::wait_st();
+      tc::fence_proxy_async();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&full[g]);
+    }
+    if (a.part_b && a_ok) atomicAdd(a.part_b + (size_t)blockIdx.x * 128 + ch, colsum);
+    if (g == 0) {
+      float* out = a.part + ((size_t)blockIdx.x * 128 + ch) * Hi;
+      if (nchunks > 0) {
+        tc::mbar_wait(fin, 0);
+        tc::fence_after_sync();
+        for (int n0 = 0; n0 < Hi; n0 += 16) {
+          uint32_t d[16];
+          tc::tmem_ld16(lane_addr + n0, d);
+          tc::wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<float4*>(out + n0)[q] = make_float4(__uint_as_float(d[4 * q]), __uint_as_float(d[4 * q + 1]),
+                                                                 __uint_as_float(d[4 * q + 2]), __uint_as_float(d[4 * q + 3]));
+        }
+        tc::fence_before_sync();
+      } else {
+        for (int n0 = 0; n0 < Hi; ++n0) out[n0] = 0.0f;
+      }
+    }
+  } else if (lane == 0) {
+    const uint32_t idesc = tc::idesc_tf32(128, Hi);
+    const uint32_t sbo = (uint32_t)(OT_KC / 4) * 128u;
+    for (long long j = 0; j < nchunks; ++j) {
+      const int g = (int)(j & 1);
+      tc::mbar_wait(&full[g], (uint32_t)((j >> 1) & 1));
+      tc::fence_after_sync();
+      const float* bh = Bs + (size_t)g * 2 * 128 * OT_KC;
+      const float* bl = bh + 128 * OT_KC;
+      for (int pass = 0; pass < 3; ++pass) {                      // lo*Bhi, hi*Blo, hi*Bhi
+        const uint32_t a_col = 128 + g * 128 + (pass == 0 ? 64 : 0);
+        const float* bsrc = pass == 1 ? bl : bh;
+#pragma unroll
+        for (int ks = 0; ks < OT_KC / 8; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_kmajor(tc::smem_u32(bsrc) + ks * 256, 128, sbo);
+          tc::mma_tf32_ts(tbase, tbase + a_col + ks * 8, bdesc, idesc, j > 0 || pass > 0 || ks > 0);
+        }
+      }
+      tc::mma_commit(&done[g]);
+    }
+    if (nchunks > 0) tc::mma_commit(fin);
+  }
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tbase, 512);
+}
+
 // dW[o, i] += sum_c part[c][o][i];  db[o] += sum_c part_b[c][o]
 __global__ void __launch_bounds__(256) k_outer_tc_reduce(const float* part, const float* part_b, int ctas, int Ho, int Hi,
                                                          float* dW, float* db) {
@@ -574,13 +697,14 @@ extern "C" long long gcm_outer_reduce_tc_workspace(long long rows) {
   return ctas * 128 * 129;   // floats: [ctas,128,<=128] partial products + [ctas,128] column sums
 }
 
-extern "C" int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi,
-                                   long long rows, float* workspace, float* dW, float* db, void* stream) {
+static int outer_reduce_tc_impl(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
+                                float* workspace, float* dW, float* db, bool tf32x3, void* stream) {
   GCM_REQUIRE(A && X && dW && workspace && rows >= 0, "outer_reduce_tc: null pointer");
   GCM_REQUIRE(Ho >= 1 && Ho <= 128 && Hi >= 16 && Hi <= 128 && Hi % 16 == 0,
               "outer_reduce_tc: Ho=%d must be <= 128, Hi=%d a multiple of 16 in [16,128]", Ho, Hi);
   if (rows == 0) return GCM_OK;
   long long ctas = gcm_outer_reduce_tc_workspace(rows) / (128 * 129);
+  if (tf32x3 && ctas > gcm_num_sms()) ctas = gcm_num_sms();       // 512 TMEM columns: one CTA per SM
   long long per = (rows + ctas - 1) / ctas;
   per = (per + OT_KC - 1) / OT_KC * OT_KC;
   ctas = (rows + per - 1) / per;
@@ -592,8 +716,32 @@ extern "C" int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const 
     return GCM_ERR_CUDA;
   }
   OuterTcArgs a{A, lda, Ho, X, ldx, Hi, rows, per, part, db ? part_b : nullptr};
-  k_outer_tc<<<(unsigned)ctas, TCG_THREADS, 0, s>>>(a);
-  if (int rc = gcm_check_launch("k_outer_tc")) return rc;
+  if (tf32x3) {
+    const size_t smem = (size_t)4 * 128 * OT_KC * sizeof(float) + 128;
+    static bool attr_done = false;
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(k_outer_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        gcm_set_error("outer_reduce_tc32: cannot raise the dynamic shared memory limit");
+        return GCM_ERR_CUDA;
+      }
+      attr_done = true;
+    }
+    k_outer_tc32<<<(unsigned)ctas, TCG_THREADS, smem, s>>>(a);
+    if (int rc = gcm_check_launch("k_outer_tc32")) return rc;
+  } else {
+    k_outer_tc<<<(unsigned)ctas, TCG_THREADS, 0, s>>>(a);
+    if (int rc = gcm_check_launch("k_outer_tc")) return rc;
+  }
   k_outer_tc_reduce<<<(Ho * Hi + 255) / 256, 256, 0, s>>>(part, part_b, (int)ctas, Ho, Hi, dW, db);
   return gcm_check_launch("k_outer_tc_reduce");
+}
+
+extern "C" int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi,
+                                   long long rows, float* workspace, float* dW, float* db, void* stream) {
+  return outer_reduce_tc_impl(A, lda, Ho, X, ldx, Hi, rows, workspace, dW, db, false, stream);
+}
+
+extern "C" int gcm_outer_reduce_tc32(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi,
+                                     long long rows, float* workspace, float* dW, float* db, void* stream) {
+  return outer_reduce_tc_impl(A, lda, Ho, X, ldx, Hi, rows, workspace, dW, db, true, stream);
 }

@@ -121,13 +121,14 @@ _SIGNATURES = {
                              C.c_longlong, _P, _P]),
     "gcm_outer_reduce_tc_workspace": (C.c_longlong, [C.c_longlong]),
     "gcm_outer_reduce_tc": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
+    "gcm_outer_reduce_tc32": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),
     "gcm_dense_step_fwd_zc": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), C.POINTER(GnnC), _P, _P, _P, _P]),
     "gcm_set_edge_builder": (_I, [_I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_csr_transpose": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
-                                      _P, _P, _P, _P, _P, _P, _P]),
+                                      _P, _P, _P, _P, _P, _P, _P, _P]),
     "gcm_tc_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 

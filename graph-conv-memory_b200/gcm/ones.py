@@ -66,7 +66,12 @@ def _outer(a, x, dw, db=None):
 _WS = {}
 
 
-def _outer_tc(a, x, dw, db=None):
+def _outer_tc32(a, x, dw, db=None):
+    """dw += a.T @ x, db += a.sum(0) in 3xTF32 on the tensor cores (fp32-accurate, deterministic)."""
+    return _outer_tc(a, x, dw, db, fn="gcm_outer_reduce_tc32")
+
+
+def _outer_tc(a, x, dw, db=None, fn="gcm_outer_reduce_tc"):
     """dw += a.T @ x, db += a.sum(0) on the bf16 tensor-core path (gcm_outer_reduce_tc; deterministic)."""
     lib = _cabi.lib()
     rows = a.shape[0]
@@ -74,9 +79,9 @@ def _outer_tc(a, x, dw, db=None):
     ws = _WS.get(a.device)
     if ws is None or ws.numel() < need:
         ws = _WS[a.device] = torch.empty(need, device=a.device, dtype=torch.float32)
-    _cabi.check(lib.gcm_outer_reduce_tc(a.data_ptr(), a.stride(0), a.shape[1], x.data_ptr(), x.stride(0), x.shape[1],
-                                        rows, ws.data_ptr(), dw.data_ptr(), None if db is None else db.data_ptr(),
-                                        _cabi.stream_ptr(a.device)), "gcm_outer_reduce_tc")
+    _cabi.check(getattr(lib, fn)(a.data_ptr(), a.stride(0), a.shape[1], x.data_ptr(), x.stride(0), x.shape[1],
+                                 rows, ws.data_ptr(), dw.data_ptr(), None if db is None else db.data_ptr(),
+                                 _cabi.stream_ptr(a.device)), fn)
 
 
 def plan_supports(plan) -> bool:
@@ -127,7 +132,8 @@ def prepare(plan, state, bf16: bool = False) -> None:
                                           _cache_act(plan), rows, H1, state.rcache.data_ptr(), H1, 1,
                                           _cabi.stream_ptr(dev)), "gcm_linear_tc")
         else:
-            full = _lin2(state.nodes.view(rows, state.F), w["w_root1"], act=_cache_act(plan))
+            lin = _lin_tc32 if (state.F % 16 == 0 and H1 % 16 == 0) else _lin2      # float32 cache: 3xTF32
+            full = lin(state.nodes.view(rows, state.F), w["w_root1"], act=_cache_act(plan))
             if bf16:
                 state.rcache = torch.empty(state.B, state.C, H1, device=dev, dtype=torch.bfloat16)
                 _cabi.check(lib.gcm_to_bf16(full.data_ptr(), state.rcache.data_ptr(), rows * H1,
@@ -217,6 +223,8 @@ def _forward_kernels(plan, state, x, k: Optional[int] = None):
         # the new node's cache row on the bf16 tensor cores, like the rows written by prepare()
         _cabi.check(lib.gcm_linear_tc(x.data_ptr(), g.F, x.stride(0), w["w_root1"].data_ptr(), None, ca, state.B, g.H1,
                                       tmp["q"].data_ptr(), g.H1, 0, stream), "gcm_linear_tc")
+    elif tc_dims:
+        _lin_tc32(x, w["w_root1"], act=ca, out=tmp["q"])
     else:
         _lin2(x, w["w_root1"], act=ca, out=tmp["q"])
     _cabi.check(lib.gcm_dense_ones_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
@@ -345,6 +353,8 @@ def _lin_bwd(st, a, wt, out):
         _cabi.check(_cabi.lib().gcm_linear_tc(a.data_ptr(), k, a.stride(0), wt.data_ptr(), None, 0, rows, ho,
                                               out.data_ptr(), out.stride(0), 0, _cabi.stream_ptr(a.device)),
                     "gcm_linear_tc")
+    elif k % 16 == 0 and ho % 16 == 0:
+        _lin_tc32(a, wt, out=out)
     else:
         _lin2(a, wt, out=out)
 
@@ -409,8 +419,8 @@ class _OnesRootFn(torch.autograd.Function):
                 _cabi.stream_ptr(dev)), "gcm_dense_ones_window_bwd")
             # weight gradients: reductions over (graph, node) and (step, graph) rows; on the bf16 path the products
             # run on the tensor cores (independent rounding per row, fp32 accumulation)
-            tc_ok = st.rc_bf16 and g.F % 16 == 0 and g.H1 % 16 == 0
-            outer = _outer_tc if tc_ok else _outer
+            tc_ok = g.F % 16 == 0 and g.H1 % 16 == 0 and g.H2 % 16 == 0
+            outer = (_outer_tc if st.rc_bf16 else _outer_tc32) if tc_ok else _outer
             outer(st.DZ.view(st.B * st.C, g.H1), st.nodes.view(st.B * st.C, st.F), grads["w_root1"])
             rows = Kc * st.B
             do = win.do[:Kc].view(rows, g.H2)

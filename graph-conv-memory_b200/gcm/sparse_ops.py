@@ -210,17 +210,19 @@ class _GraphConvFn(torch.autograd.Function):
         d_w_rel = torch.zeros_like(w_rel)
         d_w_root = torch.zeros_like(w_root)
         d_b = torch.zeros(Fout, device=dev) if ctx.has_bias else None
-        dz = w_rel_t = w_root_t = None
+        dz = w_rel_t = w_root_t = ws = None
         if rows is None:
             dz = torch.empty(m, Fout, device=dev)
             w_rel_t = w_rel.detach().t().contiguous()
             w_root_t = w_root.detach().t().contiguous()
+            if Fin % 16 == 0 and Fout % 16 == 0:
+                ws = torch.empty(int(_cabi.lib().gcm_outer_reduce_tc_workspace(m)), device=dev)
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_bwd(
             x.data_ptr(), agg.data_ptr(), out.data_ptr(), d_out.contiguous().data_ptr(), _cabi.ptr(rows), m, n,
             t_rowptr.data_ptr(), t_col.data_ptr(), None, Fin, Fout, w_rel.detach().contiguous().data_ptr(),
             w_root.detach().contiguous().data_ptr(), ctx.act, d_agg.data_ptr(), d_x.data_ptr(),
             d_w_rel.data_ptr(), d_w_root.data_ptr(), _cabi.ptr(d_b), _cabi.ptr(dz), _cabi.ptr(w_rel_t),
-            _cabi.ptr(w_root_t), _cabi.stream_ptr(dev)),
+            _cabi.ptr(w_root_t), _cabi.ptr(ws), _cabi.stream_ptr(dev)),
             "gcm_sparse_graphconv_bwd")
         return d_x, d_w_rel, d_b, d_w_root, None, None, None
 

@@ -295,6 +295,9 @@ int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const float* W1, co
 long long gcm_outer_reduce_tc_workspace(long long rows);
 int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
                         float* workspace, float* dW, float* db, void* stream);
+/* the same in 3xTF32 (fp32-accurate), same workspace */
+int gcm_outer_reduce_tc32(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
+                          float* workspace, float* dW, float* db, void* stream);
 /* writes the bit masks of the all-ones valid block (every node of the window linked to every node, self loops) */
 int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream);
 
@@ -371,13 +374,15 @@ int gcm_sparse_csr_transpose(const int64_t* rowptr, const int64_t* col, const in
  * t_col holding the position (in 0..m-1) of the edge's sink among the evaluated rows.  d_x [n, Fin]
  * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate.
  * Optional (all three or none; used when rows == NULL): dz_scratch [m, Fout] and the transposed weights w_rel_t /
- * w_root_t [Fin, Fout] let the per-row products run as plain register-tiled GEMMs over the m rows. */
+ * w_root_t [Fin, Fout] let the per-row products run as plain GEMMs over the m rows (3xTF32 on the tensor cores when
+ * Fin and Fout are multiples of 16); outer_ws (optional, gcm_outer_reduce_tc_workspace(m) floats) moves the two weight
+ * gradient reductions there as well. */
 int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
                              const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
                              const int64_t* t_col, const float* t_ew, int Fin, int Fout, const float* w_rel,
                              const float* w_root, int act, float* d_agg, float* d_x, float* d_w_rel,
                              float* d_w_root, float* d_b, float* dz_scratch,
-                             const float* w_rel_t, const float* w_root_t, void* stream);
+                             const float* w_rel_t, const float* w_root_t, float* outer_ws, void* stream);
 
 /* Self-test of the tcgen05/TMEM building block of the tensor-core step kernels:
  * D[128,N] = A[128,K] B[N,K]^T, passes = 3 (3xTF32, fp32-accurate) or 1 (plain tf32).  Test hook only. */

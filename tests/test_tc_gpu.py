@@ -126,3 +126,27 @@ def test_tc_block_ss_form_3xtf32(K, N):
     torch.cuda.synchronize()
     ref = A.double() @ B.double().t()
     assert float((D.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("rows,Ho,Hi", [(64 * 900 + 7, 64, 64), (5000, 128, 128), (200, 48, 32)])
+def test_outer_reduce_tc32_is_fp32_accurate(rows, Ho, Hi):
+    """gcm_outer_reduce_tc32 (3xTF32): dW += A^T X against float64, with the error of a plain fp32 matmul as the budget."""
+    from gcm import _cabi
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    g = torch.Generator().manual_seed(rows + Ho)
+    A = torch.randn(rows, Ho, generator=g).to(dev)
+    X = torch.randn(rows, Hi, generator=g).to(dev)
+    ws = torch.empty(int(lib.gcm_outer_reduce_tc_workspace(rows)), device=dev)
+    dW = torch.zeros(Ho, Hi, device=dev)
+    db = torch.zeros(Ho, device=dev)
+    _cabi.check(lib.gcm_outer_reduce_tc32(A.data_ptr(), Ho, Ho, X.data_ptr(), Hi, Hi, rows, ws.data_ptr(), dW.data_ptr(),
+                                          db.data_ptr(), _cabi.stream_ptr(dev)), "gcm_outer_reduce_tc32")
+    ref = A.double().t() @ X.double()
+    scale = float(ref.abs().max())
+    err = float((dW.double() - ref).abs().max()) / scale
+    err32 = float(((A.t() @ X).double() - ref).abs().max()) / scale
+    print(f"rows={rows}: 3xTF32 err {err:.2e}, fp32 matmul err {err32:.2e}")
+    assert err < 2e-6 + 2 * err32
+    assert float((db.double() - A.double().sum(0)).abs().max()) < 1e-4 * max(1.0, rows ** 0.5)
