@@ -265,15 +265,24 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
     if (!a.edges) {
       if (lane == 31) a.deg[slot] = incl;
       if (a.hits) {
-        int at = incl - cnt;
-        for (int j = 0; j < wpl; ++j) {
-          const int w = lane * wpl + j;
-          uint32_t m = w < W ? my[w] : 0u;
-          while (m && at < a.hit_cap) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            a.hits[slot * a.hit_cap + at] = (uint16_t)(w * 32 + bit);
-            ++at;
+        // walk the NON-EMPTY mask words in ascending order, the whole warp on one word at a time (lane = bit): the
+        // sources of a sink sit in a handful of words, and a per-lane bit loop serialised on the lane that owned most
+        // of them (16.6 divergent iterations per sink, 19 % of the kernel's instructions)
+        uint32_t lanes = __ballot_sync(GCM_FULL_MASK, cnt != 0);   // lanes whose chunk of words has any bit
+        int base = 0;
+        while (lanes) {
+          const int L = __ffs(lanes) - 1;
+          lanes &= lanes - 1;
+          for (int j = 0; j < wpl; ++j) {
+            const int w = L * wpl + j;
+            if (w >= W) break;
+            const uint32_t word = my[w];                              // shared memory: the same word for every lane
+            if (!word) continue;
+            if ((word >> lane) & 1u) {
+              const int at = base + __popc(word & ((1u << lane) - 1u));
+              if (at < a.hit_cap) a.hits[slot * a.hit_cap + at] = (uint16_t)(w * 32 + lane);
+            }
+            base += __popc(word);
           }
         }
       }
