@@ -239,3 +239,44 @@ def test_bench_reference_arm_prints_the_contract_line():
                     "config", "cpu_baseline", "e2e"):
             assert key in line, key
         assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_workload_table_and_roofline_accounting_are_consistent():
+    """Every bench workload has its SURVEY 8(d) accounting (no GPU needed): the bound, a positive per-step quantity
+    and a unit, for the shapes in the table."""
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    for name, (desc, B, N, F, H, spec, mode) in bench.WORKLOADS.items():
+        extra = (B * N, 20 * B * N) if mode == "sparse" else None
+        bound, qty, unit = bench.algorithmic(name, B, N, F, H, extra)
+        assert bound in ("hbm", "tensor") and qty > 0 and unit in ("bytes", "flop"), name
+        assert mode in ("rollout", "bptt", "sparse") and isinstance(desc, str)
+    # cfg2's figure is SURVEY's 1 440 B per graph-step
+    assert bench.algorithmic("cfg2", 65536, 128, 32, 32)[1] == 65536 * 1440
+
+
+def test_ones_window_buffers_grow_without_losing_recorded_steps():
+    """gcm.ones._Window: the per-step buffers of a BPTT window grow geometrically up to the log's capacity and keep what
+    was recorded (host logic only; runs on CPU tensors)."""
+    from types import SimpleNamespace
+
+    from gcm import ones
+
+    st = SimpleNamespace(B=3, device=torch.device("cpu"))
+    g = SimpleNamespace(F=4, H1=8, H2=8)
+    win = ones._Window(st, g)
+    win.ensure_fwd(0, cap=200)
+    assert win.K == 64 and win.S.shape == (64, 3, 4) and win.E.shape == (64, 3, 8)
+    win.G[5].fill_(7.0)
+    win.ensure_fwd(64, cap=200)
+    assert win.K == 128 and float(win.G[5].min()) == 7.0
+    win.ensure_fwd(150, cap=200)
+    assert win.K == 200
+    win.need_dx = True
+    win.ensure_bwd()
+    assert win.do.shape == (200, 3, 8) and win.dcs.shape == (200, 3, 8)
