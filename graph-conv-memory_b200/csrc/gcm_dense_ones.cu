@@ -440,8 +440,9 @@ __global__ void __launch_bounds__(256) k_ones_bump_n(int32_t* count, int B, int 
 }
 
 struct OnesSeqArgs {
-  gcm_dense_state st;   // count already advanced by T
-  int H1, T;
+  gcm_dense_state st;   // count already advanced by T + after
+  int H1, T, after;     // this launch covers T steps; `after` more steps follow them (chunked windows)
+  long long q_stride_b; // floats between graphs in q_new
   void* cache;          // [B, C, H1]
   const float* wE;      // [T, B, H1]  E_k (tanh) or c_k
   const float* q_new;   // [B, T, H1]  cache rows of the T new nodes (float32; stored into the cache here)
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_ones_window_fwd(const OnesSeqAr
   const int tpr = H1 >> 2;                      // host: H1 % 4 == 0 (bf16: % 8), H1 <= 128
   const int rpp = SEQ_THREADS / tpr;
   const int rl = tid / tpr, vl = tid - rl * tpr;
-  const int count0 = __ldcg(a.st.count + b) - T;
+  const int count0 = __ldcg(a.st.count + b) - T - a.after;
   const int lo = max(0, count0 + 1 - N);        // oldest node step 0 sees
   const int n_old = count0 - lo;
   CT* rows = reinterpret_cast<CT*>(seq_smem);   // [n_old + T][H1], row j = node lo + j
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_ones_window_fwd(const OnesSeqAr
   // 2. the T new rows: rounded to the cache type, into the cache and into shared memory
   for (int i = tid; i < T * H1; i += SEQ_THREADS) {
     const int k = i / H1, ch = i - k * H1;
-    const float q = a.q_new[((size_t)b * T + k) * H1 + ch];
+    const float q = a.q_new[(size_t)b * a.q_stride_b + (size_t)k * H1 + ch];
     OnesCache<CT>::store1(cache + (size_t)((count0 + k) % C) * H1 + ch, q);
     OnesCache<CT>::store1(rows + (size_t)(n_old + k) * H1 + ch, q);
   }
@@ -921,16 +922,17 @@ static int ones_launch_seq(const OnesSeqArgs& a, size_t smem, cudaStream_t s) {
 }
 
 extern "C" int gcm_dense_ones_window_fwd(const gcm_dense_state* st, int H1, int act1, int cache_type, void* cache, int T,
-                                         const float* wE, const float* q_new, float* wG, float* wP, float* wht,
-                                         long long step_stride, void* stream) {
+                                         int steps_after, const float* wE, const float* q_new, long long q_stride_b,
+                                         float* wG, float* wP, float* wht, long long step_stride, void* stream) {
   if (int rc = ones_check_state(st, "dense_ones_window_fwd")) return rc;
   if (int rc = ones_check_cache(H1, act1, cache_type, "dense_ones_window_fwd")) return rc;
-  GCM_REQUIRE(cache && wE && q_new && wG && wht && T >= 1 && step_stride >= (long long)st->B * H1,
+  GCM_REQUIRE(cache && wE && q_new && wG && wht && T >= 1 && steps_after >= 0 && q_stride_b >= (long long)T * H1 &&
+                  step_stride >= (long long)st->B * H1,
               "dense_ones_window_fwd: bad arguments");
   const size_t smem = ones_seq_smem(st->N, T, H1, cache_type);
   GCM_REQUIRE(smem <= 220 * 1024, "dense_ones_window_fwd: (N + T) * H1 rows do not fit in shared memory");
   if (st->B == 0) return GCM_OK;
-  OnesSeqArgs a{*st, H1, T, cache, wE, q_new, wG, wP, wht, step_stride};
+  OnesSeqArgs a{*st, H1, T, steps_after, q_stride_b, cache, wE, q_new, wG, wP, wht, step_stride};
   int rc = GCM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (wP) ONES_DISPATCH(cache_type, act1, (rc = ones_launch_seq<CT, ACT, true>(a, smem, s)));

@@ -112,7 +112,8 @@ _SIGNATURES = {
                                      _P]),
     "gcm_dense_ones_seq_update": (_I, [C.POINTER(DenseStateC), _P, C.c_longlong, C.c_longlong, _I, _P, _P, C.c_longlong, _P]),
     "gcm_dense_ones_seq_smem": (C.c_longlong, [_I, _I, _I, _I]),
-    "gcm_dense_ones_window_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, C.c_longlong, _P]),
+    "gcm_dense_ones_window_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _I, _I, _P, _P, C.c_longlong, _P, _P, _P,
+                                       C.c_longlong, _P]),
     "gcm_act_backward": (_I, [_P, _P, _I, C.c_longlong, _P, _P]),
     "gcm_dense_ones_dc": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_to_bf16": (_I, [_P, _P, C.c_longlong, _P]),

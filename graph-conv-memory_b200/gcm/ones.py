@@ -310,10 +310,22 @@ def _sequence_kernels(plan, state, x_seq, k0: Optional[int] = None):
                                       q_new.data_ptr(), g.H1, 0, stream), "gcm_linear_tc")
     else:
         _lin2(xf, w["w_root1"], act=ca, out=q_new)
-    _cabi.check(lib.gcm_dense_ones_window_fwd(state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16),
-                                              state.rcache.data_ptr(), T, E.data_ptr(), q_new.data_ptr(), G.data_ptr(),
-                                              None if P is None else P.data_ptr(), ht.data_ptr(), B * g.H1, stream),
-                "gcm_dense_ones_window_fwd")
+    # chunks of the window small enough for three resident CTAs per SM (cache rows of N + chunk nodes in shared memory),
+    # when that is possible; steps are independent given the cache, so the chunks are just consecutive launches
+    chunk = T
+    smem = lambda t: int(lib.gcm_dense_ones_seq_smem(state.N, t, g.H1, int(state.rc_bf16)))
+    if smem(T) > 74 * 1024:
+        fit = [t for t in range(min(T - 1, 64), 7, -8) if smem(t) <= 74 * 1024]
+        if fit:
+            n_chunks = -(-T // fit[0])
+            chunk = -(-T // n_chunks)            # balanced: 63 steps -> 32 + 31, not 48 + 15
+    for k_start in range(0, T, chunk):
+        tc_ = min(chunk, T - k_start)
+        _cabi.check(lib.gcm_dense_ones_window_fwd(
+            state.c_ref(), g.H1, _cabi.ACT[g.act1], int(state.rc_bf16), state.rcache.data_ptr(), tc_, T - k_start - tc_,
+            E[k_start].data_ptr(), q_new.data_ptr() + 4 * k_start * g.H1, T * g.H1, G[k_start].data_ptr(),
+            None if P is None else P[k_start].data_ptr(), ht[k_start].data_ptr(), B * g.H1, stream),
+            "gcm_dense_ones_window_fwd")
     lin_b = _lin_tc32 if (tc_dims and state.rc_bf16) else _lin2
     beliefs = lin_b(G.view(T * B, g.H1), w["w_rel2"], ht.view(T * B, g.H1), w["w_root2"], bias=w["b2"],
                     act=_cabi.ACT[g.act2], status=state.status)

@@ -260,14 +260,16 @@ int gcm_dense_ones_node_bwd(const gcm_dense_state* st, int H1, int act1, int cac
  * observations).  gcm_dense_ones_seq_update = T x gcm_dense_ones_update: x_seq[b, k, :] at b * stride_b + k * stride_t
  * floats; wS [T, B, F] receives S after every step (step_stride floats between steps), count += T.
  * gcm_dense_ones_window_fwd = T x gcm_dense_ones_fwd with the graph's cache rows read from HBM once: wE [T,B,H1]
- * (E_k or c_k), q_new [B,T,H1] (cache rows of the new nodes, float32), outputs wG / wP (NULL ok) / wht [T,B,H1].
+ * (E_k or c_k), q_new (cache rows of the new nodes, float32: graph b, step k at b * q_stride_b + k * H1), outputs wG / wP
+ * (NULL ok) / wht [T,B,H1].  A window may be taken in chunks (fewer rows in shared memory -> more resident CTAs):
+ * steps_after = steps of the same gcm_dense_ones_seq_update call that come after this chunk.
  * Needs gcm_dense_ones_seq_smem(N, T, H1, cache_type) <= 220 KB of shared memory. */
 int gcm_dense_ones_seq_update(const gcm_dense_state* st, const float* x_seq, long long stride_b, long long stride_t, int T,
                               const float* xsum_in, float* wS, long long step_stride, void* stream);
 long long gcm_dense_ones_seq_smem(int N, int T, int H1, int cache_type);
 int gcm_dense_ones_window_fwd(const gcm_dense_state* st, int H1, int act1, int cache_type, void* cache, int T,
-                              const float* wE, const float* q_new, float* wG, float* wP, float* wht, long long step_stride,
-                              void* stream);
+                              int steps_after, const float* wE, const float* q_new, long long q_stride_b, float* wG,
+                              float* wP, float* wht, long long step_stride, void* stream);
 /* res = d_out * act'(out) elementwise (act' expressed through the activation's output) */
 int gcm_act_backward(const float* d_out, const float* out, int act, long long n, float* res, void* stream);
 /* per-step pieces of the backward, elementwise over n = B*H1: dht <- dzo = dht * act1'(h_t); dc = dG * P + dzo;
