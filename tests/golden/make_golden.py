@@ -160,6 +160,35 @@ def dense_case(name, B, N, F, H, T, spec, acts=("tanh", "tanh"), seed=0, obs=Non
     print("wrote", name, "adj nnz", int(hidden[1].sum()))
 
 
+def preproc_case(name, B, N, F_raw, F, H, T, spec, seed=0, pre_act=None):
+    """The reference DenseGCM WITH a preprocessor (what RayDenseGCM builds, ray_gcm.py:118,133-136): a Linear (+ optional
+    activation) applied by the reference to all N rows every step (gcm.py:290-291).  Also pins the equivalence the fused
+    path relies on: for a per-row preprocessor the beliefs equal those of the plain step fed the PREPROCESSED
+    observations, while the hidden state keeps the RAW ones."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    obs = torch.randn(T, B, F_raw, generator=g)
+    p = oracle.make_params(F, H, seed=7 + seed)
+    lin = torch.nn.Linear(F_raw, F)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(F, F_raw, generator=g) / F_raw ** 0.5)
+        lin.bias.copy_(0.1 * torch.randn(F, generator=g))
+    pre = lin if pre_act is None else torch.nn.Sequential(lin, ACT[pre_act]())
+    mod = DenseGCM(RefDenseGNN(F, H, p, ("tanh", "tanh")), preprocessor=pre, edge_selectors=ref_selector(spec), graph_size=N)
+    hidden, o_hidden, beliefs = None, None, []
+    with torch.no_grad():
+        for t in range(T):
+            mx, hidden = mod(obs[t], hidden)
+            omx, o_hidden = oracle.dense_gcm_step(pre(obs[t]), o_hidden, spec, p, ("tanh", "tanh"), graph_size=N)
+            assert torch.allclose(mx, omx, rtol=1e-5, atol=1e-6), (name, t, (mx - omx).abs().max())
+            assert torch.equal(hidden[1].float(), o_hidden[1].float()) and torch.equal(hidden[3], o_hidden[3]), (name, t)
+            beliefs.append(mx)
+    out = {"name": name, "B": B, "N": N, "F_raw": F_raw, "F": F, "H": H, "T": T, "spec": spec, "pre_act": pre_act,
+           "obs": obs, "params": p, "pre_weight": lin.weight.detach().clone(), "pre_bias": lin.bias.detach().clone(),
+           "beliefs": torch.stack(beliefs).clone(), "final": tuple(h.detach().clone() for h in hidden)}
+    torch.save(out, os.path.join(HERE, name + ".pt"))
+    print("wrote", name, "adj nnz", int(hidden[1].sum()))
+
+
 def coo_to_idx(adj):
     return adj.coalesce().indices()
 
@@ -281,6 +310,9 @@ def main():
     dense_case("dense_grad_denseedge", B=2, N=8, F=3, H=4, T=7, spec=[("dense",)], seed=15, grads=True)
     dense_case("dense_grad_relu", B=2, N=5, F=3, H=4, T=8, spec=[("temporal", (1,), "forward")],
                acts=("relu", "none"), seed=16, grads=True)
+    # preprocessor (RayDenseGCM's configuration), window wraps
+    preproc_case("dense_preproc_temporal", B=4, N=8, F_raw=6, F=8, H=8, T=20, spec=[("temporal", (1, 2), "forward")], seed=17)
+    preproc_case("dense_preproc_denseedge", B=3, N=6, F_raw=5, F=4, H=8, T=14, spec=[("dense",)], seed=18, pre_act="tanh")
     # ---- sparse ------------------------------------------------------------
     sparse_case("sparse_temporal12_once", B=3, N=8, F=3, H=4, calls=[[8, 5, 7]],
                 spec=[("temporal", (1, 2))], grads=True)

@@ -12,7 +12,21 @@ def load_golden(name):
 
 
 def dense_cases():
-    return sorted(f[:-3] for f in os.listdir(GOLDEN) if f.startswith("dense_") and f.endswith(".pt"))
+    return sorted(f[:-3] for f in os.listdir(GOLDEN) if f.startswith("dense_") and f.endswith(".pt")
+                  and not f.startswith("dense_preproc"))
+
+
+def preproc_cases():
+    """fixtures of the reference DenseGCM WITH a preprocessor (tests/golden/make_golden.py: preproc_case)"""
+    return sorted(f[:-3] for f in os.listdir(GOLDEN) if f.startswith("dense_preproc") and f.endswith(".pt"))
+
+
+def make_preprocessor(g):
+    lin = torch.nn.Linear(g["F_raw"], g["F"])
+    with torch.no_grad():
+        lin.weight.copy_(g["pre_weight"])
+        lin.bias.copy_(g["pre_bias"])
+    return lin if g["pre_act"] is None else torch.nn.Sequential(lin, ACT[g["pre_act"]]())
 
 
 def sparse_cases():

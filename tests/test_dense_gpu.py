@@ -5,7 +5,8 @@ import pytest
 import torch
 
 import gcm_oracle as oracle
-from helpers import dense_cases, load_golden, make_dense_gnn, make_selector, rel_err
+from helpers import (dense_cases, load_golden, make_dense_gnn, make_preprocessor, make_selector, preproc_cases,
+                     rel_err)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -365,3 +366,25 @@ def test_euclid_batchmean_tensor_core_kernel_matches_the_cuda_core_kernel(B, C, 
     ref = ref.mean(-1).view(B, C) / (1.7 if learned else 1.0)
     for k, d in out.items():
         assert rel_err(d, ref) < 2e-5, k
+
+
+@pytest.mark.parametrize("name", preproc_cases())
+def test_preprocessor_path_matches_reference_golden(name):
+    """The fused preprocessor path against golden vectors of the unmodified reference DenseGCM(preprocessor=...)."""
+    from gcm.gcm import DenseGCM
+    from gcm.state import DenseHidden
+
+    g = load_golden(name)
+    dev = torch.device("cuda:0")
+    gnn, _ = make_dense_gnn(g["F"], g["H"], g["params"], ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), preprocessor=make_preprocessor(g).to(dev), edge_selectors=make_selector(g["spec"]),
+                   graph_size=g["N"])
+    hidden = None
+    with torch.no_grad():
+        for t in range(g["T"]):
+            belief, hidden = mod(g["obs"][t].to(dev), hidden)
+            assert isinstance(hidden, DenseHidden)
+            assert rel_err(belief, g["beliefs"][t]) < 5 * TOL, (name, t)
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(nodes.cpu(), g["final"][0]) and torch.equal(adj.cpu(), g["final"][1].float())
+    assert torch.equal(num_nodes.cpu(), g["final"][3])

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import gcm_oracle as oracle
+import helpers
 from helpers import dense_cases, load_golden, sparse_cases
 
 
@@ -179,3 +180,25 @@ def test_kat_double_edge_chain():
     for i in range(2, 4):
         want[:, i, i - 2] = 1
     assert torch.equal(h[1], want)
+
+
+@pytest.mark.parametrize("name", helpers.preproc_cases())
+def test_oracle_on_preprocessed_observations_reproduces_the_reference_with_a_preprocessor(name):
+    """Golden vectors of the UNMODIFIED reference DenseGCM(preprocessor=Linear[, act]) (gcm.py:290-291; what RayDenseGCM
+    builds): for a per-row preprocessor the beliefs are those of the plain step fed the preprocessed observations, and
+    the hidden state keeps the raw observations -- the equivalence the fused preprocessor path is built on."""
+    g = helpers.load_golden(name)
+    pre = helpers.make_preprocessor(g)
+    hidden = None
+    raw = torch.zeros(g["B"], g["N"], g["F_raw"])
+    with torch.no_grad():
+        for t in range(g["T"]):
+            mx, hidden = oracle.dense_gcm_step(pre(g["obs"][t]), hidden, g["spec"], g["params"], ("tanh", "tanh"),
+                                               graph_size=g["N"])
+            assert torch.allclose(mx, g["beliefs"][t], rtol=1e-5, atol=1e-6), (name, t)
+            if t >= g["N"]:
+                raw = torch.cat([raw[:, 1:], g["obs"][t].unsqueeze(1)], dim=1)
+            else:
+                raw[:, t] = g["obs"][t]
+    assert torch.equal(raw, g["final"][0])                       # the reference's m_t holds RAW observations
+    assert torch.equal(hidden[1].float(), g["final"][1].float()) and torch.equal(hidden[3], g["final"][3])
