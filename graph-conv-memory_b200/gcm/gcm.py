@@ -218,6 +218,20 @@ class DenseGCM(torch.nn.Module):
                     state.nodes.copy_(pre(state.raw))
                     state.pre_key = pkey
                     state.xsum, state.rc_key, state.hc_key, state.hc_fresh = None, None, None, 0
+                    state.fast_ok = False
+                elif state.fast_ok and hidden.token is None and plan.validated and self._plan is plan:
+                    # steady-state rollout: the preprocessor on the new observation (our own Linear kernel when it is
+                    # a plain Linear <= 128 wide), the trimmed step (gcm.fused.fast_temporal_step), the raw-log write
+                    if (type(pre) is torch.nn.Linear and pre.out_features <= 128 and pre.weight.dtype == torch.float32
+                            and pre.weight.is_cuda):
+                        y = ones._lin2(x_raw, pre.weight, bias=pre.bias)
+                    else:
+                        y = pre(x_raw)
+                    belief = fused.fast_temporal_step(plan, state, y)
+                    if belief is not None:
+                        _cabi.check(_cabi.lib().gcm_state_log_write(state.raw_ref(), x_raw.data_ptr(), -1,
+                                                                    _cabi.stream_ptr(x.device)), "gcm_state_log_write")
+                        return belief, DenseHidden(state, None)
                 inner = hidden
             elif hidden is None:
                 inner = None
