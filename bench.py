@@ -2,21 +2,27 @@
 """bench.py — GCM env-steps/s on B200 (BASELINE.json metric), one process per GPU.
 
 Default workload = BASELINE.json configs[1] ("cfg2"): DenseGCM graph_size 128, hidden 32,
-TemporalBackedge([1,2,4]), 65536 graphs per GPU, forward rollout in steady state (graphs full, the
-oldest node is dropped every step).  A "step" is one DenseGCM.forward over the whole batch = ONE launch
+TemporalBackedge([1,2,4]), 65536 graphs per GPU, forward pass in steady state (graphs full, the
+oldest node is dropped every step).  A "step" is one DenseGCM step over the whole batch = ONE launch
 of the fused step kernel.  Graphs are independent, so the batch shards across ranks with no data-path
 collective (weak scaling: every rank owns --batch graphs).
 
 JSON line (rank 0):
-  value        env-steps/s, observations already resident in HBM (CUDA events, max over ranks)
+  value        env-steps/s, observations already resident in HBM (CUDA events, max over ranks).  For temporal
+               chains the K timed steps are ONE `DenseGCM.forward_sequence(x[B,K,F], m_t)` call -- the loop of
+               RayDenseGCM.forward (reference ray_gcm.py:200-202) enqueued from C; `per_call` holds the same K steps
+               as K `DenseGCM.forward` calls (one Python round trip per step).
   e2e          same metric through the public API from HOST buffers: every step copies its [B,F]
                observation from pinned host memory and reads the [B,H] belief back
   roofline     algorithmic bytes per launch / kernel duration (CUDA events around
                back-to-back launches), against MEASURED_PEAKS.json
-  cpu_baseline the oracle port of the reference step on the host cores (bounded sample)
+  cpu_baseline the reference step on the host cores (bounded sample)
+  also         fwd+bwd records of the same run: cfg2-bptt (BPTT over T=64 steps of the cfg2 chain) and cfg3 (DenseEdge
+               N=256 H=128 T=64 with the NCCL gradient all-reduce), each with its own roofline / clocks / e2e
 
-Other workloads (`--workload cfg1|cfg2-pre|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the remaining BASELINE
-configs with the same line format; `--impl reference` times the oracle port of the reference on CPU.
+Other workloads (`--workload cfg1|cfg2-pre|cfg2-bptt|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the
+remaining BASELINE configs with the same line format; `--impl reference` times the reference on CPU (the unmodified
+reference package from baseline/_ref when it is installed, else the oracle port).
 """
 import argparse
 import json
@@ -27,11 +33,9 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.join(ROOT, "graph-conv-memory_b200"), os.path.join(ROOT, "oracle")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
-
-import torch  # noqa: E402
+PKG_PATHS = (os.path.join(ROOT, "graph-conv-memory_b200"), os.path.join(ROOT, "oracle"))
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+STANDIN = os.path.join(ROOT, "tests", "golden", "standin")
 
 # name -> (description, B, N, F, H, selector spec, mode)
 WORKLOADS = {
@@ -42,6 +46,8 @@ WORKLOADS = {
     "cfg2-pre": ("cfg2 with RayDenseGCM's Linear preprocessor (SURVEY 8(f) rank 2): DenseGCM(preprocessor=Linear(32,32)) "
                  "N=128 H=32 TemporalBackedge([1,2,4]) rollout fwd", 65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")],
                  "rollout"),
+    "cfg2-bptt": ("cfg2 chain, BPTT T=64 fwd+bwd on full graphs (truncated BPTT on a running rollout: m_t.detach() per "
+                  "window), SGD step, gradient all-reduce", 65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "bptt"),
     "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, bf16 per-node cache, fp32 accumulate)",
              16384, 256, 128, 128, [("dense",)], "bptt"),
     "cfg3-seq": ("cfg3 through DenseGCM.forward_sequence (SURVEY 8(f) rank 1): the T=64 steps of a window in one call, "
@@ -55,6 +61,13 @@ WORKLOADS = {
     "cfg5-train": ("cfg5 forward + backward (loss = mean of the outputs; gradients of the GraphConv weights and of x)",
                    1024, 4096, 64, 64, None, "sparse"),
 }
+BPTT_T = 64
+
+
+def _product_paths():
+    for p in PKG_PATHS:
+        if p not in sys.path:
+            sys.path.insert(0, p)
 
 
 def peaks():
@@ -91,13 +104,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0=None, t1=None):
+    def window(self, t0=None, t1=None):
+        """clocks summary of the samples taken between two perf_counter stamps (the sampler keeps running)"""
         if self.index is None:
             return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
         rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.1)]
         if not rows:
             rows = [r for _, r in self.rows]
@@ -107,6 +120,10 @@ class ClockSampler:
         reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
 
 def make_selector(spec):
@@ -125,6 +142,7 @@ def make_selector(spec):
 
 
 def build_dense(dev, N, F, H, spec, pre=False):
+    import torch
     from gcm.gcm import DenseGCM
     from gcm.nn import DenseGraphConv
 
@@ -146,6 +164,7 @@ def build_dense(dev, N, F, H, spec, pre=False):
 
 
 def build_sparse(dev, N, F, H):
+    import torch
     from gcm.nn import GraphConv
     from gcm.sparse_edge_selectors.spatial import SpatialRadiusEdge
     from gcm.sparse_edge_selectors.temporal import TemporalEdge
@@ -169,6 +188,8 @@ def build_sparse(dev, N, F, H):
 
 def synth_obs(gen, n, B, F, spec):
     """N(0,1) observations; clustered (K=16 centres, shared schedule) for distance edges."""
+    import torch
+
     if spec and spec[0][0] in ("cosine", "euclidean"):
         centres = torch.randn(16, F, generator=gen)
         sched = torch.randint(0, 16, (n,), generator=gen)
@@ -183,6 +204,14 @@ def algorithmic(workload, B, N, F, H, extra=None):
         r2 = len({0} | set(hops) | {a + b for a in hops for b in hops})
         per = r2 * F * 4 + F * 4 + F * 4 + N // 8 + H * 4 + 16
         return "hbm", per * B, "bytes"
+    if workload == "cfg2-bptt":
+        # per graph-step of a BPTT window: the forward's 1 440 B (SURVEY 8(d) k-hop figure) + the
+        # backward's streams: dL/dbelief and the belief (act2'), h_t and its act1', the node row, dL/dx written
+        hops = WORKLOADS[workload][5][0][1]
+        r2 = len({0} | set(hops) | {a + b for a in hops for b in hops})
+        fwd = r2 * F * 4 + F * 4 + F * 4 + N // 8 + H * 4 + 16
+        bwd = 2 * H * 4 + H * 4 + F * 4 + F * 4
+        return "hbm", (fwd + bwd) * B, "bytes"
     if workload.startswith("cfg4"):
         if workload == "cfg4-euclid":
             # the cross-batch mean distance: 2 B^2 N F useful flops per step, issued as THREE tf32 MMAs per product
@@ -201,8 +230,90 @@ def algorithmic(workload, B, N, F, H, extra=None):
     raise ValueError(workload)
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------
+def reference_installed():
+    return os.path.exists(os.path.join(REF_DIR, "gcm", "gcm.py"))
+
+
+def cpu_reference_rate_real(workload, batch, steps, warm):
+    """The UNMODIFIED reference package (pip-installed from /root/reference into baseline/_ref by
+    __graft_entry__.build()) on the host cores.  Its torch_geometric dependency is not installable here; the stand-in
+    under tests/golden/standin restates DenseGraphConv / Sequential per PyG's published definitions in plain torch.
+    Must run in a process that has NOT imported this repository's own `gcm` package (same top-level name)."""
+    assert "gcm" not in sys.modules, "the reference arm needs a process of its own"
+    sys.path.insert(0, STANDIN)
+    sys.path.insert(0, REF_DIR)
+    import torch
+    import torch_geometric
+    from gcm.edge_selectors.dense import DenseEdge
+    from gcm.edge_selectors.distance import CosineEdge, EuclideanEdge
+    from gcm.edge_selectors.temporal import TemporalBackedge
+    from gcm.gcm import DenseGCM
+
+    desc, _, N, F, H, spec, mode = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    class GNN(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gc0 = torch_geometric.nn.DenseGraphConv(F, H)
+            self.gc1 = torch_geometric.nn.DenseGraphConv(H, H)
+            self.act = torch.nn.Tanh()
+
+        def forward(self, x, adj, weights, B, N):
+            x = self.act(self.gc0(x, adj))
+            return self.act(self.gc1(x, adj))
+
+    s = spec[0]
+    sel = (TemporalBackedge(list(s[1]), direction=s[2]) if s[0] == "temporal" else DenseEdge() if s[0] == "dense"
+           else CosineEdge(s[1]) if s[0] == "cosine" else EuclideanEdge(s[1]))
+    torch.manual_seed(7)
+    mod = DenseGCM(GNN(), edge_selectors=sel, graph_size=N)
+    gen = torch.Generator().manual_seed(1002)
+    DenseGCM.did_warn = True
+    hidden = (torch.randn(batch, N, F, generator=gen), torch.zeros(batch, N, N), torch.zeros(0),
+              torch.full((batch,), N, dtype=torch.long))
+    obs = synth_obs(gen, 4, batch, F, spec)
+    if mode == "bptt":
+        opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
+        T = min(BPTT_T, 8)
+
+        def window(hidden):
+            opt.zero_grad(set_to_none=True)
+            hidden = tuple(h.detach() for h in hidden)
+            tot = 0
+            for t in range(T):
+                belief, hidden = mod(obs[t % 4], hidden)
+                tot = tot + belief.mean()
+            (tot / T).backward()
+            opt.step()
+            return hidden
+
+        for _ in range(min(warm, 1)):
+            hidden = window(hidden)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hidden = window(hidden)
+        dt = time.perf_counter() - t0
+        return batch * T * steps / dt, dt / steps, cores, f"B={batch} full graphs, windows of T={T} fwd+bwd+SGD"
+    with torch.no_grad():
+        for i in range(warm):
+            _, hidden = mod(obs[i % 4], hidden)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            _, hidden = mod(obs[i % 4], hidden)
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores, f"B={batch} full graphs (wrap every step)"
+
+
 def cpu_reference_rate(workload, batch, steps, warm):
     """The oracle port of the reference (oracle/gcm_oracle.py) on the host cores."""
+    _product_paths()
+    import torch
+
     import gcm_oracle as oracle
 
     desc, _, N, F, H, spec, mode = WORKLOADS[workload]
@@ -237,103 +348,151 @@ def cpu_reference_rate(workload, batch, steps, warm):
     return batch * steps / dt, dt / steps, cores, f"B={batch} full graphs (wrap every step)"
 
 
+def cpu_arm(workload, batch, steps, warm):
+    """(rate, seconds per step, cores, sample text, kind): the real reference when it is installed and covers the
+    workload's mode, else the oracle port."""
+    mode = WORKLOADS[workload][6]
+    if reference_installed() and mode != "sparse" and "gcm" not in sys.modules:
+        rate, per, cores, what = cpu_reference_rate_real(workload, batch, steps, warm)
+        return rate, per, cores, ("unmodified reference package (baseline/_ref) + torch_geometric stand-in "
+                                  "(tests/golden/standin), " + what), "reference"
+    rate, per, cores, what = cpu_reference_rate(workload, batch, steps, warm)
+    return rate, per, cores, "oracle port of the reference, " + what, "port"
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     desc = WORKLOADS[args.workload][0]
-    rate, per, cores, what = cpu_reference_rate(args.workload, args.cpu_batch, args.steps, min(args.warmup, 4))
-    sample = f"oracle port of the reference ({what}; GPU arm runs {args.batch or WORKLOADS[args.workload][1]} graphs per GPU)"
+    mode = WORKLOADS[args.workload][6]
+    rate, per, cores, what, kind = cpu_arm(args.workload, args.cpu_batch, args.steps, min(args.warmup, 4))
+    sample = f"{what}; GPU arm runs {args.batch or WORKLOADS[args.workload][1]} graphs per GPU"
     print(json.dumps({
-        "impl": "reference", "metric": "GCM env-steps/sec (fwd)", "value": rate, "unit": "env-steps/s",
+        "impl": "reference", "metric": "GCM env-steps/sec (fwd+bwd)" if mode == "bptt" else "GCM env-steps/sec (fwd)",
+        "value": rate, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "batch_per_step": args.cpu_batch, "timing": "host wall clock, CPU only"},
-        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU (default: the workload's)")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=1024)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cache", default="bf16", choices=["bf16", "f32"],
-                    help="cfg3: element type of the per-node cache (bf16 = the config's stated precision)")
-    args = ap.parse_args()
+def cpu_baseline_subprocess(workload, batch, steps, warm):
+    """The CPU baseline of the default run, in a process of its own (the reference package shares its top-level name
+    with this repository's)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                              "--steps", str(steps), "--warmup", str(warm), "--cpu-batch", str(batch)],
+                             capture_output=True, text=True, timeout=600)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        cb = line["cpu_baseline"]
+        cb["sample"] += f", {line['ms_per_step']:.1f} ms/step"
+        cb["unit"] = line["unit"]
+        return cb
+    except Exception as e:  # noqa: BLE001 - the baseline is context, never fatal
+        return {"value": None, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port",
+                "sample": f"unavailable: {type(e).__name__}: {e}"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    desc, B0, N, F, H, spec, mode = WORKLOADS[args.workload]
-    if args.warmup is None:
-        args.warmup = N + 8 if mode == "rollout" else 3   # fill the graphs, then steady state
-    args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        if args.workload == "cfg5":
-            args.cpu_batch = min(args.cpu_batch, 16)
-        elif args.workload != "cfg2":
-            args.cpu_batch = min(args.cpu_batch, 64)
-        run_reference(args, rank)
-        return
 
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, dev, rank, world, dist, sampler):
+        self.dev, self.rank, self.world, self.dist, self.sampler = dev, rank, world, dist, sampler
 
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or B0
-    K, W = args.steps, args.warmup
-    gen = torch.Generator().manual_seed(1002 + rank)
+    def barrier(self):
+        import torch
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+        if self.dist is not None:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, ms):
+        import torch
+
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # rank 0 samples the clocks of every GPU of the job (local ranks 0 .. world-1 of this node)
-    sampler = ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None)
-    sampler.start()
-    extra, launches, e2e, kern_ms, kernel_name, host_us = None, K, None, None, None, None
-    unit_per_step = B
 
-    if mode == "rollout":
-        mod = build_dense(dev, N, F, H, spec, pre=args.workload == "cfg2-pre")
-        n_obs = 16 if args.workload != "cfg4-euclid" else 4
-        obs_host = synth_obs(gen, n_obs, B, F, spec).pin_memory()
-        obs_dev = obs_host.to(dev)
-        obs_steps = [obs_dev[i] for i in range(n_obs)]       # per-step views made once (2 us of host time per step)
-        hidden = None
-        with torch.no_grad():
-            for i in range(W):
+def run_rollout(ctx, workload, B, K, W, args):
+    import torch
+    from gcm import _cabi
+
+    desc, _, N, F, H, spec, mode = WORKLOADS[workload]
+    dev, world = ctx.dev, ctx.world
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(1002 + ctx.rank)
+    mod = build_dense(dev, N, F, H, spec, pre=workload == "cfg2-pre")
+    n_obs = 16 if workload != "cfg4-euclid" else 4
+    obs_host = synth_obs(gen, n_obs, B, F, spec).pin_memory()
+    obs_dev = obs_host.to(dev)
+    obs_steps = [obs_dev[i] for i in range(n_obs)]       # per-step views made once (2 us of host time per step)
+    seq = spec[0][0] == "temporal"                       # temporal chains have the C rollout entry behind forward_sequence
+    fill = max(0, N + 8 - W)                             # untimed: the graphs are FULL before the warm-up starts
+    out = {}
+    hidden = None
+    with torch.no_grad():
+        if seq:
+            def xs(n, off=0):                            # [B, n, F]: step k of the call reads observation (off + k) % n_obs
+                return torch.stack([obs_steps[(off + k) % n_obs] for k in range(n)], dim=1).contiguous()
+
+            if fill:
+                _, hidden = mod.forward_sequence(xs(fill), hidden)
+            x_warm, x_seq = xs(max(W, 2), fill), xs(K, fill + W)
+            _, hidden = mod.forward_sequence(x_warm, hidden)
+            _, hidden = mod.forward_sequence(x_seq, hidden)           # same call shape as the timed one (allocator warm)
+            ctx.barrier()
+            t_lo = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            beliefs, hidden = mod.forward_sequence(x_seq, hidden)
+            e1.record()
+            ctx.barrier()
+            total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+            # kernel-only duration: the same call queued behind a spinning blocker kernel
+            n_l0 = lib.gcm_launch_count()
+            torch.cuda._sleep(int(1.0e7))
+            e0.record()
+            beliefs, hidden = mod.forward_sequence(x_seq, hidden)
+            e1.record()
+            torch.cuda.synchronize()
+            kern_ms = e0.elapsed_time(e1) / K
+            launches = int(lib.gcm_launch_count() - n_l0)
+            kernel_name = lib.gcm_last_kernel().decode()
+            if workload == "cfg2-pre":
+                kernel_name = "k_step_temporal_hc"       # (the call ends with the raw-log write)
+            # the same K steps as K DenseGCM.forward calls (one Python round trip per step)
+            for i in range(max(W, 3)):
                 belief, hidden = mod(obs_steps[i % n_obs], hidden)
-            barrier()
+            ctx.barrier()
+            h0 = time.perf_counter()
+            e0.record()
+            for i in range(K):
+                belief, hidden = mod(obs_steps[i % n_obs], hidden)
+            e1.record()
+            host_us = (time.perf_counter() - h0) / K * 1e6
+            ctx.barrier()
+            pc_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+            out["per_call"] = {"value": B * world * K / (pc_ms * 1e-3), "ms_per_step": pc_ms / K,
+                               "host_us_per_call": host_us,
+                               "what": "the same K steps as K DenseGCM.forward(x[B,F], m_t) calls (Python per step)"}
+        else:
+            for i in range(fill + W):
+                belief, hidden = mod(obs_steps[i % n_obs], hidden)
+            ctx.barrier()
             t_lo = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(K):
                 belief, hidden = mod(obs_steps[i % n_obs], hidden)
             e1.record()
-            barrier()
-            total_ms = max_over_ranks(e0.elapsed_time(e1))
-            # kernel-only duration: the SAME public-API calls, queued behind a spinning blocker kernel so the
-            # host runs ahead and the K step kernels execute back to back; CUDA events on the launching stream
-            from gcm import _cabi
-            lib = _cabi.lib()
+            ctx.barrier()
+            total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
             n_l0 = lib.gcm_launch_count()
             torch.cuda._sleep(int(2.0e7))                      # ~10 ms at 1.9 GHz: covers K host-side launches
             h0 = time.perf_counter()
@@ -346,208 +505,372 @@ def main():
             kern_ms = e0.elapsed_time(e1) / K
             launches = int(lib.gcm_launch_count() - n_l0)
             kernel_name = lib.gcm_last_kernel().decode()
-            if args.workload == "cfg4-euclid":
+            if workload == "cfg4-euclid":
                 kernel_name = "k_euclid_tc (cross-batch mean distance, 3xTF32 tcgen05) + " + kernel_name
-            # end to end through the public API from HOST buffers: every step copies its observation from pinned
-            # host memory and reads its belief back; the copies run on their own streams (PCIe is full duplex)
-            # and overlap the neighbouring steps' kernels, ordered by events
-            R = 4
-            main = torch.cuda.current_stream()
-            h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
-            ring = [torch.empty(B, F, device=dev) for _ in range(R)]
-            belief_host = [torch.empty(B, H).pin_memory() for _ in range(R)]
-            ev_in = [torch.cuda.Event() for _ in range(R)]
-            ev_done = [torch.cuda.Event() for _ in range(R)]
+            out["host_us_per_call"] = host_us
+        # end to end through the public API from HOST buffers: every step copies its observation from pinned
+        # host memory and reads its belief back; the copies run on their own streams (PCIe is full duplex)
+        # and overlap the neighbouring steps' kernels, ordered by events
+        R = 4
+        main = torch.cuda.current_stream()
+        h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        ring = [torch.empty(B, F, device=dev) for _ in range(R)]
+        belief_host = [torch.empty(B, H).pin_memory() for _ in range(R)]
+        ev_in = [torch.cuda.Event() for _ in range(R)]
+        ev_done = [torch.cuda.Event() for _ in range(R)]
 
-            def e2e_steps(n, hidden):
-                for i in range(n):
-                    j = i % R
-                    with torch.cuda.stream(h2d):
-                        if i >= R:
-                            h2d.wait_event(ev_done[j])
-                        ring[j].copy_(obs_host[i % n_obs], non_blocking=True)
-                        ev_in[j].record(h2d)
-                    main.wait_event(ev_in[j])
-                    belief, hidden = mod(ring[j], hidden)
-                    ev_done[j].record(main)
-                    with torch.cuda.stream(d2h):
-                        d2h.wait_event(ev_done[j])
-                        belief_host[j].copy_(belief, non_blocking=True)
-                        belief.record_stream(d2h)
-                main.wait_stream(d2h)
-                main.wait_stream(h2d)
-                return hidden
+        def e2e_steps(n, hidden):
+            for i in range(n):
+                j = i % R
+                with torch.cuda.stream(h2d):
+                    if i >= R:
+                        h2d.wait_event(ev_done[j])
+                    ring[j].copy_(obs_host[i % n_obs], non_blocking=True)
+                    ev_in[j].record(h2d)
+                main.wait_event(ev_in[j])
+                belief, hidden = mod(ring[j], hidden)
+                ev_done[j].record(main)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev_done[j])
+                    belief_host[j].copy_(belief, non_blocking=True)
+                    belief.record_stream(d2h)
+            main.wait_stream(d2h)
+            main.wait_stream(h2d)
+            return hidden
 
-            hidden = e2e_steps(2 * R, hidden)
-            e2e_runs = []
-            for _ in range(3):                      # PCIe / host jitter: median of three timed passes of K steps
-                barrier()
-                e0.record()
-                hidden = e2e_steps(K, hidden)
-                e1.record()
-                barrier()
-                e2e_runs.append(max_over_ranks(e0.elapsed_time(e1)))
-            e2e_ms = sorted(e2e_runs)[1]
-            t_hi = time.perf_counter()
-        e2e = {"value": B * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
-               "d2h_bytes_per_step": B * H * 4, "ms_per_step": e2e_ms / K,
-               "ms_per_step_runs": [r / K for r in e2e_runs],
-               "how": "H2D / step kernel / D2H on three streams, 4-deep buffer ring, pinned host memory"}
-        hidden.claim().check_flags()
-    elif mode == "bptt":
-        from gcm import dist as gdist
+        hidden = e2e_steps(2 * R, hidden)
+        e2e_runs = []
+        for _ in range(3):                      # PCIe / host jitter: median of three timed passes of K steps
+            ctx.barrier()
+            e0.record()
+            hidden = e2e_steps(K, hidden)
+            e1.record()
+            ctx.barrier()
+            e2e_runs.append(ctx.max_over_ranks(e0.elapsed_time(e1)))
+        e2e_ms = sorted(e2e_runs)[1]
+        t_hi = time.perf_counter()
+    hidden.claim().check_flags()
+    out.update({
+        "total_ms": total_ms, "kern_ms": kern_ms, "launches": launches, "kernel_name": kernel_name, "unit_per_step": B,
+        "t_lo": t_lo, "t_hi": t_hi, "extra": None,
+        "state": ("in-place node log + bit-packed adjacency; steady state: graphs full before the warm-up "
+                  f"({fill} untimed fill steps + {W} warm-up steps), the oldest node is dropped every step"),
+        "timed_call": (f"ONE DenseGCM.forward_sequence(x[B,{K},F], m_t) call (C rollout entry, {K} kernel launches)"
+                       if seq else f"{K} DenseGCM.forward calls"),
+        "e2e": {"value": B * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
+                "d2h_bytes_per_step": B * H * 4, "ms_per_step": e2e_ms / K,
+                "ms_per_step_runs": [r / K for r in e2e_runs],
+                "how": "per-step DenseGCM.forward; H2D / step kernel / D2H on three streams, 4-deep buffer ring, "
+                       "pinned host memory"}})
+    return out
 
-        T = 64
-        mod = build_dense(dev, N, F, H, spec)
-        mod.bptt_capacity = T
+
+def run_bptt(ctx, workload, B, K, W, args):
+    import torch
+    from gcm import _cabi
+    from gcm import dist as gdist
+
+    desc, _, N, F, H, spec, mode = WORKLOADS[workload]
+    dev, world = ctx.dev, ctx.world
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(1002 + ctx.rank)
+    T = BPTT_T
+    temporal = spec[0][0] == "temporal"
+    mod = build_dense(dev, N, F, H, spec)
+    mod.bptt_capacity = T
+    if not temporal:
         mod.compute_dtype = torch.bfloat16 if args.cache == "bf16" else None
-        opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
-        obs_host = (0.5 * torch.randn(T, B, F, generator=gen)).pin_memory()
-        obs_dev = obs_host.to(dev)
+    opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
+    obs_host = ((1.0 if temporal else 0.5) * torch.randn(T, B, F, generator=gen)).pin_memory()
+    obs_dev = obs_host.to(dev)
+    obs_stage = torch.empty_like(obs_dev)
+    seq = workload == "cfg3-seq" or temporal
+    obs_bt = obs_dev.transpose(0, 1).contiguous() if seq else None         # [B, T, F] for the sequence entry
+    loss_host = torch.empty(1).pin_memory()
+    if temporal:
+        # truncated BPTT on a running rollout: fill the graphs without autograd, then one window per optimiser step
+        with torch.no_grad():
+            _, carry = mod.forward_sequence(torch.randn(B, N + 8, F, device=dev), None)
+        carry = [carry]
+
+        def window(obs, obs_seq):
+            opt.zero_grad(set_to_none=True)
+            hidden = carry[0].detach()
+            beliefs, hidden = mod.forward_sequence(obs_seq, hidden)
+            loss = beliefs.mean()
+            loss.backward()
+            gdist.allreduce_grads(mod.parameters(), average=True)
+            opt.step()
+            carry[0] = hidden
+            return loss
+    else:
         nn0 = torch.full((B,), N - T, dtype=torch.long, device=dev)            # pre-filled with N - T nodes
         nodes0 = 0.5 * torch.randn(B, N, F, device=dev)
         nodes0[:, N - T:] = 0
         adj0 = torch.zeros(B, N, N, device=dev)
         adj0[:, : N - T, : N - T] = 1                                            # DenseEdge history: all ones
 
-        seq = args.workload == "cfg3-seq"
-        obs_bt = obs_dev.transpose(0, 1).contiguous() if seq else None         # [B, T, F] for the sequence entry
-
-        def window(obs):
+        def window(obs, obs_seq):
             hidden = (nodes0, adj0, torch.zeros(0, device=dev), nn0)
             opt.zero_grad(set_to_none=True)
             if seq:
-                beliefs, hidden = mod.forward_sequence(obs_bt, hidden)
+                beliefs, hidden = mod.forward_sequence(obs_seq, hidden)
                 tot = beliefs.mean() * T
             else:
                 tot = 0
                 for t in range(T):
                     belief, hidden = mod(obs[t], hidden)
                     tot = tot + belief.mean()
-            (tot / T).backward()
+            loss = tot / T
+            loss.backward()
             gdist.allreduce_grads(mod.parameters(), average=True)               # the one NCCL collective
             opt.step()
-            return tot
+            return loss
 
-        for _ in range(min(W, 2)):
-            window(obs_dev)
-        barrier()
-        t_lo = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            window(obs_dev)
-        e1.record()
-        barrier()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
-        t_hi = time.perf_counter()
-        unit_per_step = B * T
-        from gcm import _cabi
-        n_l0 = _cabi.lib().gcm_launch_count()
-        window(obs_dev)
-        torch.cuda.synchronize()
-        launches = int(_cabi.lib().gcm_launch_count() - n_l0) * K
-        # dominant kernel: the forward pass over the per-node cache (one launch per step), timed alone on the state
-        # the last window left behind (t = N - 1: the longest stream of the window)
+    for _ in range(min(W, 2)):
+        window(obs_dev, obs_bt)
+    ctx.barrier()
+    t_lo = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        window(obs_dev, obs_bt)
+    e1.record()
+    ctx.barrier()
+    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    n_l0 = lib.gcm_launch_count()
+    window(obs_dev, obs_bt)
+    torch.cuda.synchronize()
+    launches = int(lib.gcm_launch_count() - n_l0) * K
+    # end to end from HOST buffers: the window's observations come from pinned host memory, the loss is read back
+    def e2e_window():
+        obs_stage.copy_(obs_host, non_blocking=True)
+        ob = obs_stage.transpose(0, 1).contiguous() if seq else None
+        loss = window(obs_stage, ob)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    e2e_window()
+    ctx.barrier()
+    Ke = max(1, min(K, 3))
+    e0.record()
+    for _ in range(Ke):
+        e2e_window()
+    e1.record()
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / Ke
+    t_hi = time.perf_counter()
+    window_ms = total_ms / K
+    extra = {"window_ms": window_ms, "window_T": T}
+    if temporal:
+        # whole-window roofline: (forward + backward algorithmic bytes of the T steps) / window time; dominant kernel =
+        # the forward step kernel, timed alone on a no-grad sequence call
+        with torch.no_grad():
+            hid = carry[0].detach()
+            _, hid = mod.forward_sequence(obs_bt, hid)
+            torch.cuda._sleep(int(1.0e7))
+            e0.record()
+            _, hid = mod.forward_sequence(obs_bt, hid)
+            e1.record()
+            torch.cuda.synchronize()
+            carry[0] = hid
+        step_kernel_ms = e0.elapsed_time(e1) / T
+        kern_ms = window_ms / T
+        kernel_name = ("whole window: T x k_step_temporal_hc forward + the window-level backward "
+                       "(gcm.temporal_bwd), per graph-step")
+        extra.update({"fwd_step_kernel_ms": step_kernel_ms, "fwd_kernel_share_of_window": step_kernel_ms * T / window_ms})
+    else:
         from gcm import ones as _ones
         with torch.no_grad():
             _, hid = mod(obs_dev[0], (nodes0, adj0, torch.zeros(0, device=dev), nn0))
             for t in range(1, T):
                 _, hid = mod(obs_dev[t], hid)
         kern_ms = _ones.time_fwd_kernel(mod.fused_plan(), hid.claim())
-        extra = {"window_ms": total_ms / K, "fwd_kernel_share_of_window": kern_ms * T / (total_ms / K)}
+        _, algo, _ = algorithmic(workload, B, N, F, H)
+        pk, _ = peaks()
+        extra.update({"fwd_kernel_share_of_window": kern_ms * T / window_ms,
+                      "window_fwd_bytes_frac": algo * T / (window_ms * 1e-3) / 1e9 / pk["hbm_gbs"]})
         kernel_name = ("k_ones_fwd (1 launch per step; the backward is ONE k_ones_window_bwd per window, "
                        "see DESIGN.md section 3)")
         if seq:
             extra["note"] = ("the sequence entry replaces the 64 k_ones_fwd launches by ONE k_ones_window_fwd (cache rows "
                              "read once, MUFU-bound); kernel_ms / frac above are those of the per-step kernel for reference")
-    else:  # sparse, all-at-once
-        mod = build_sparse(dev, N, F, H)
-        x = torch.randn(B, N, F, generator=gen)
-        x[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, N, 2, generator=gen), dim=1)
-        x_host = x.pin_memory()
-        x_dev = x_host.to(dev)
-        taus = torch.full((B,), N, dtype=torch.long, device=dev)
-        train = args.workload == "cfg5-train"
+    return {"total_ms": total_ms, "kern_ms": kern_ms, "launches": launches, "kernel_name": kernel_name,
+            "unit_per_step": B * T, "t_lo": t_lo, "t_hi": t_hi, "extra": extra, "state": mode,
+            "timed_call": f"{K} windows of T={T}: forward, backward, gradient all-reduce, SGD step",
+            "e2e": {"value": B * T * world / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": T * B * F * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                    "how": "per window: the [T,B,F] observations copied from pinned host memory, the loss read back"}}
+
+
+def run_sparse(ctx, workload, B, K, W, args):
+    import torch
+
+    desc, _, N, F, H, spec, mode = WORKLOADS[workload]
+    dev = ctx.dev
+    gen = torch.Generator().manual_seed(1002 + ctx.rank)
+    mod = build_sparse(dev, N, F, H)
+    x = torch.randn(B, N, F, generator=gen)
+    x[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, N, 2, generator=gen), dim=1)
+    x_host = x.pin_memory()
+    x_dev = x_host.to(dev)
+    taus = torch.full((B,), N, dtype=torch.long, device=dev)
+    train = workload == "cfg5-train"
+    if train:
+        x_dev.requires_grad_(True)
+
+    def call():
         if train:
-            x_dev.requires_grad_(True)
+            for p_ in mod.parameters():
+                p_.grad = None
+            x_dev.grad = None
+            out, hid = mod(x_dev, taus, None)
+            out.mean().backward()
+            return out, hid
+        with torch.no_grad():
+            return mod(x_dev, taus, None)
 
-        def call():
-            if train:
-                for p_ in mod.parameters():
-                    p_.grad = None
-                x_dev.grad = None
-                out, hid = mod(x_dev, taus, None)
-                out.mean().backward()
-                return out, hid
-            with torch.no_grad():
-                return mod(x_dev, taus, None)
+    for _ in range(W):
+        out, hid = call()
+    ctx.barrier()
+    t_lo = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out, hid = call()
+    e1.record()
+    ctx.barrier()
+    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    t_hi = time.perf_counter()
+    E = int(hid[1]._nnz())
+    kernel_name = "k_graphconv_fwd x2 (+ edge build)" + (
+        " + backward (k_linear2, k_outer_reduce, k_graphconv_bwd_gather)" if train else "")
+    return {"total_ms": total_ms, "kern_ms": total_ms / K, "launches": K * 5, "kernel_name": kernel_name,
+            "unit_per_step": B * N, "t_lo": t_lo, "t_hi": t_hi, "extra": (B * N, E), "state": mode,
+            "timed_call": f"{K} SparseGCM.forward calls (all {N} observations of every graph at once)", "e2e": None}
 
-        for _ in range(W):
-            out, hid = call()
-        barrier()
-        t_lo = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            out, hid = call()
-        e1.record()
-        barrier()
-        total_ms = max_over_ranks(e0.elapsed_time(e1))
-        t_hi = time.perf_counter()
-        E = int(hid[1]._nnz())
-        extra = (B * N, E)
-        unit_per_step = B * N
-        launches = K * 5
-        kernel_name = "k_graphconv_fwd x2 (+ edge build)" + (" + backward (k_linear2, k_outer_reduce, k_graphconv_bwd_gather)" if train else "")
-        kern_ms = total_ms / K
 
-    value = unit_per_step * world * K / (total_ms * 1e-3)
-    clocks = sampler.stop(t_lo, t_hi)
+def run_workload(ctx, workload, K, W, args, batch=None):
+    """One workload -> the JSON line's dictionary (without cpu_baseline)."""
+    import torch
 
+    desc, B0, N, F, H, spec, mode = WORKLOADS[workload]
+    B = batch or B0
+    r = {"rollout": run_rollout, "bptt": run_bptt, "sparse": run_sparse}[mode](ctx, workload, B, K, W, args)
+    total_ms, kern_ms, extra = r["total_ms"], r["kern_ms"], r["extra"]
+    value = r["unit_per_step"] * ctx.world * K / (total_ms * 1e-3)
+    clocks = ctx.sampler.window(r["t_lo"], r["t_hi"])
+    torch.cuda.empty_cache()
+    if ctx.rank != 0:
+        return None
+    pk, pk_kind = peaks()
+    bound, algo, algo_unit = algorithmic(workload, B, N, F, H, extra if isinstance(extra, tuple) else None)
+    if algo_unit == "bytes":
+        achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+    else:
+        # tf32 dense peak = half of the measured bf16 peak (MEASURED_PEAKS.json has no tf32 entry of its own)
+        achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e12, pk["bf16_tflops"] / 2.0, "TFLOP/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(workload)
+    fwdbwd = mode == "bptt" or workload == "cfg5-train"
+    line = {
+        "metric": "GCM env-steps/sec (fwd+bwd)" if fwdbwd else "GCM env-steps/sec (fwd)",
+        "value": value, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s", "n_gpus": ctx.world,
+        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16 cache / f32 accumulate" if (mode == "bptt" and spec[0][0] == "dense" and args.cache == "bf16") else "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": B, "graph_size": N, "obs_size": F, "hidden": H,
+                   "state": r["state"], "timed_call": r["timed_call"],
+                   "l2": f"per-GPU state {B * N * F * 4 / 1e6:.0f} MB vs 126 MB L2; fresh observations every step",
+                   "parallelism": f"batch-sharded x{ctx.world}, no data-path collective"
+                   + (" (one NCCL all-reduce of the weight gradients per window)" if mode == "bptt" else "")},
+        "clocks": clocks, "gpu_launches": r["launches"],
+        "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind if unit == "GB/s"
+                     else pk_kind + " bf16 dense / 2 = tf32 dense; achieved counts the 3 tf32 MMAs of every 3xTF32 product",
+                     "kernel": r["kernel_name"], "kernel_ms": kern_ms, "algorithmic_per_launch": algo},
+    }
+    for k in ("per_call", "host_us_per_call"):
+        if k in r:
+            (line if k == "per_call" else line["roofline"])[k] = r[k]
+    if r["e2e"] is not None:
+        line["e2e"] = r["e2e"]
+    else:
+        line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "device-resident only for this auxiliary workload"}
+    if isinstance(extra, dict):
+        line["roofline"].update(extra)
+    elif extra is not None:
+        line["config"]["flat_nodes"], line["config"]["edges"] = extra
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="graphs per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="cfg2 only: skip the fwd+bwd records (cfg2-bptt, cfg3)")
+    ap.add_argument("--cache", default="bf16", choices=["bf16", "f32"],
+                    help="cfg3: element type of the per-node cache (bf16 = the config's stated precision)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    desc, B0, N, F, H, spec, mode = WORKLOADS[args.workload]
+    if args.warmup is None:
+        args.warmup = 8 if mode == "rollout" else 3
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if args.workload == "cfg5":
+            args.cpu_batch = min(args.cpu_batch, 16)
+        elif args.workload != "cfg2":
+            args.cpu_batch = min(args.cpu_batch, 64)
+        run_reference(args, rank)
+        return
+
+    _product_paths()
+    import torch
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    # rank 0 samples the clocks of every GPU of the job (local ranks 0 .. world-1 of this node)
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None)
+    sampler.start()
+    ctx = Ctx(dev, rank, world, dist, sampler)
+    line = run_workload(ctx, args.workload, args.steps, args.warmup, args, args.batch)
+    also = []
+    if args.workload == "cfg2" and not args.no_also and args.batch is None:
+        # the fwd+bwd half of BASELINE.json's metric, measured in the same run
+        for wl, k in (("cfg2-bptt", 4), ("cfg3", 3)):
+            rec = run_workload(ctx, wl, k, 3, args)
+            if rec is not None:
+                rec = {key: rec[key] for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                                                 "dtype", "config", "clocks", "gpu_launches", "roofline", "e2e")}
+                rec["workload"] = wl
+                also.append(rec)
+    sampler.stop()
     if rank == 0:
-        pk, pk_kind = peaks()
-        bound, algo, algo_unit = algorithmic(args.workload, B, N, F, H, extra)
-        if algo_unit == "bytes":
-            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
-        else:
-            # tf32 dense peak = half of the measured bf16 peak (MEASURED_PEAKS.json has no tf32 entry of its own)
-            achieved, peak, unit = algo / (kern_ms * 1e-3) / 1e12, pk["bf16_tflops"] / 2.0, "TFLOP/s"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload)
-        line = {
-            "metric": "GCM env-steps/sec (fwd+bwd)" if (mode == "bptt" or args.workload == "cfg5-train") else "GCM env-steps/sec (fwd)",
-            "value": value, "unit": "env-steps/s" if mode != "sparse" else "node-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 cache / f32 accumulate" if (mode == "bptt" and args.cache == "bf16") else "f32",
-            "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "graph_size": N, "obs_size": F, "hidden": H,
-                       "state": "in-place node log + bit-packed adjacency; steady state (graphs full)"
-                       if mode == "rollout" else mode,
-                       "l2": f"per-GPU state {B * N * F * 4 / 1e6:.0f} MB vs 126 MB L2; fresh observations every step",
-                       "parallelism": f"batch-sharded x{world}, no data-path collective"},
-            "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind if unit == "GB/s"
-                         else pk_kind + " bf16 dense / 2 = tf32 dense; achieved counts the 3 tf32 MMAs of every 3xTF32 product", "kernel": kernel_name, "kernel_ms": kern_ms,
-                         "algorithmic_per_launch": algo, "host_us_per_call": host_us},
-        }
-        if e2e is not None:
-            line["e2e"] = e2e
-        else:
-            line["e2e"] = {"value": value, "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                           "note": "device-resident only for this auxiliary workload"}
-        if isinstance(extra, dict):
-            line["roofline"].update(extra)
-        elif extra is not None:
-            line["config"]["flat_nodes"], line["config"]["edges"] = extra
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
             cb = {"cfg2": args.cpu_batch, "cfg5": 8}.get(args.workload, 64)
-            rate, per, cores, what = cpu_reference_rate(args.workload, cb, 6 if mode != "sparse" else 1, 2)
-            line["cpu_baseline"] = {"value": rate, "unit": line["unit"], "cores": cores, "kind": "port",
-                                    "sample": f"oracle port of the reference, {what}, {per * 1e3:.1f} ms/step"}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, cb, 6 if mode != "sparse" else 1, 2)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -833,6 +833,11 @@ extern "C" int gcm_set_temporal_kernel(int which) {
   return GCM_OK;
 }
 
+static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
+                         int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
+                         int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
+                         void* stream_);
+
 extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                                   int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
                                   int flags, void* stream_) {
@@ -843,6 +848,25 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
                                          int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
                                          int flags, float* hcache, int hc_ring, int* cache_written,
                                          void* stream_) {
+  // legacy packing of the uniform count into bits 8.. of `flags` (23 bits); gcm_dense_step_fwd_ex takes it as its own
+  // argument and is what the host code of this repository calls
+  const int uc = (flags & GCM_STEP_UNIFORM_COUNT) ? (int)((unsigned)flags >> GCM_STEP_COUNT_SHIFT) : -1;
+  return step_fwd_impl(st, obs, 0, sels, n_sels, gnn, belief, 0, status, flags & 0xff, uc, hcache, hc_ring,
+                       cache_written, stream_);
+}
+
+extern "C" int gcm_dense_step_fwd_ex(const gcm_dense_state* st, const float* obs, long long obs_ld,
+                                     const gcm_selector* sels, int n_sels, const gcm_gnn* gnn, float* belief,
+                                     long long belief_ld, int32_t* status, int flags, int uniform_count, float* hcache,
+                                     int hc_ring, int* cache_written, void* stream_) {
+  return step_fwd_impl(st, obs, obs_ld, sels, n_sels, gnn, belief, belief_ld, status, flags & 0xff,
+                       (flags & GCM_STEP_UNIFORM_COUNT) ? uniform_count : -1, hcache, hc_ring, cache_written, stream_);
+}
+
+static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
+                         int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
+                         int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
+                         void* stream_) {
   if (cache_written) *cache_written = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = validate_state(st)) return rc;
@@ -869,6 +893,11 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
     }
   }
   if (st->B == 0) return GCM_OK;
+  if (obs_ld <= 0) obs_ld = st->F;
+  if (belief_ld <= 0) belief_ld = gnn->H2;
+  // only the cached-row kernel takes strided observation / belief rows (the sequence entry's [B, T, .] views)
+  const bool strided = obs_ld != st->F || belief_ld != gnn->H2;
+  GCM_REQUIRE(!(flags & GCM_STEP_UNIFORM_COUNT) || uniform_count >= 0, "dense_step_fwd: negative uniform count");
 
   if ((flags & GCM_STEP_PURE_TEMPORAL) && gnn->H1 == 32 && gnn->H2 == 32 &&
       (st->F == 8 || st->F == 16 || st->F == 32)) {
@@ -890,7 +919,9 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
         wa.status = status;
         wa.prog = ta.prog;
         wa.win = win;
-        wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? (flags >> GCM_STEP_COUNT_SHIFT) : -1;
+        wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? uniform_count : -1;
+        wa.obs_ld = obs_ld;
+        wa.belief_ld = belief_ld;
         wa.hcache = hcache;
         wa.hc_ring = hc_ring;
         wa.weights_stable = (flags & GCM_STEP_WEIGHTS_STABLE) ? 1 : 0;
@@ -907,6 +938,10 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
             return rc;
           }
         }
+        if (strided) {
+          gcm_set_error("dense_step_fwd: strided rows need the cached-row kernel");
+          return GCM_ERR_UNSUPPORTED;
+        }
         if (want == GCM_TK_AUTO || want == GCM_TK_TC || want == GCM_TK_HC) {
           const int rc = gcm_launch_temporal_tc(wa, stream);
           if (rc != GCM_ERR_UNSUPPORTED) {
@@ -921,6 +956,10 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
           default: return launch_temporal_win<32>(wa, stream);
         }
       }
+      if (strided) {
+        gcm_set_error("dense_step_fwd: strided rows need the cached-row kernel");
+        return GCM_ERR_UNSUPPORTED;
+      }
       ta.st = *st;
       ta.obs = obs;
       ta.gnn = *gnn;
@@ -934,6 +973,10 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
     }
   }
 
+  if (strided) {
+    gcm_set_error("dense_step_fwd: strided rows need the cached-row kernel");
+    return GCM_ERR_UNSUPPORTED;
+  }
   DenseStepArgs a;
   a.st = *st;
   a.obs = obs;
@@ -952,4 +995,73 @@ extern "C" int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float*
     case 4: return launch_general_h<4>(a, hr, stream);
     default: return launch_general_h<8>(a, hr, stream);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rollout entry: T steps enqueued back to back from C (the loop of ray_gcm.py:200-202 without a Python round trip
+// per step).  Each step is the same launch gcm_dense_step_fwd_ex would make; the bookkeeping the host keeps
+// between steps (uniform count, freshness of the layer-1 row cache) lives in the gcm_rollout descriptor.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_copy_rows(const float* __restrict__ src, long long src_ld, float* __restrict__ dst,
+                                                   long long dst_ld, long long rows, int width) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * width) return;
+  const long long r = i / width;
+  const int c = (int)(i - r * width);
+  dst[r * dst_ld + c] = src[r * src_ld + c];
+}
+
+static int copy_rows(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows, int width,
+                     cudaStream_t stream) {
+  const long long n = rows * width;
+  if (n == 0) return GCM_OK;
+  k_copy_rows<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, src_ld, dst, dst_ld, rows, width);
+  return gcm_check_launch("k_copy_rows");
+}
+
+extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long obs_ld, long long obs_stride_t,
+                                     float* belief, long long belief_ld, long long belief_stride_t, int T,
+                                     void* stream_) {
+  GCM_REQUIRE(r && obs && belief && T >= 0, "dense_rollout_fwd: bad arguments");
+  GCM_REQUIRE(r->n_sels >= 1 && r->n_sels <= GCM_MAX_SELECTORS && r->max_hop >= 1, "dense_rollout_fwd: bad selector chain");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int F = r->st.F, H2 = r->gnn.H2;
+  if (obs_ld <= 0) obs_ld = F;
+  if (belief_ld <= 0) belief_ld = H2;
+  const bool strided = obs_ld != F || belief_ld != H2;
+  const long long l0 = gcm_launch_count();
+  for (int k = 0; k < T; ++k) {
+    const float* ob = obs + (long long)k * obs_stride_t;
+    float* be = belief + (long long)k * belief_stride_t;
+    int flags = GCM_STEP_PURE_TEMPORAL;
+    if (r->uniform_count >= 0) flags |= GCM_STEP_UNIFORM_COUNT;
+    const int need = r->uniform_count >= 0 && r->uniform_count < r->max_hop ? r->uniform_count : r->max_hop;
+    if (r->hcache && r->hc_fresh >= need) flags |= GCM_STEP_HCACHE_VALID;
+    if (r->weights_stable && r->hc_fresh >= 1) flags |= GCM_STEP_WEIGHTS_STABLE;
+    int written = 0;
+    int rc = step_fwd_impl(&r->st, ob, obs_ld, r->sels, r->n_sels, &r->gnn, be, belief_ld, r->status, flags,
+                           r->uniform_count, r->hcache, r->hc_ring, &written, stream_);
+    if (rc == GCM_ERR_UNSUPPORTED && strided) {
+      // a step the cached-row kernel cannot take (cache being filled, shape): contiguous copies of the rows
+      GCM_REQUIRE(r->scratch_obs && r->scratch_belief, "dense_rollout_fwd: strided rows need the scratch buffers");
+      if ((rc = copy_rows(ob, obs_ld, r->scratch_obs, F, r->st.B, F, stream))) return rc;
+      rc = step_fwd_impl(&r->st, r->scratch_obs, F, r->sels, r->n_sels, &r->gnn, r->scratch_belief, H2, r->status,
+                         flags, r->uniform_count, r->hcache, r->hc_ring, &written, stream_);
+      if (rc) return rc;
+      rc = copy_rows(r->scratch_belief, H2, be, belief_ld, r->st.B, H2, stream);
+    }
+    if (rc) return rc;
+    if (r->hcache) {
+      if (!written) r->hc_fresh = 0;
+      else if (r->hc_fresh < r->max_hop) ++r->hc_fresh;
+    }
+    if (r->uniform_count >= 0) ++r->uniform_count;
+    r->weights_stable = 1;   // nothing but this loop touches the stream between the steps of one call
+  }
+  r->launches = gcm_launch_count() - l0;
+  return GCM_OK;
+}
+
+extern "C" int gcm_dense_rollout_step(gcm_rollout* r, const float* obs, float* belief, void* stream_) {
+  return gcm_dense_rollout_fwd(r, obs, 0, 0, belief, 0, 0, 1, stream_);
 }

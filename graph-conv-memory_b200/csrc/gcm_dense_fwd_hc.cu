@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
             src = a.hcache + ((size_t)g0 * R + ((cnt - hop) & (R - 1))) * HC_H + col * 4;
             stride = (size_t)R * HC_H;
           } else if (kind == 2) {
-            src = a.obs + (size_t)g0 * F + col * 4;
-            stride = F;
+            src = a.obs + (size_t)g0 * a.obs_ld + col * 4;
+            stride = (size_t)a.obs_ld;
           }
           if (src) {
             float* dst = st_base + dst_off;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
             else if (kind == 1 && hop <= lt)
               src = a.hcache + ((size_t)(g0 + gi) * R + ((cnt - hop) & (R - 1))) * HC_H + col * 4;
             else if (kind == 2)
-              src = a.obs + (size_t)(g0 + gi) * F + col * 4;
+              src = a.obs + (size_t)(g0 + gi) * a.obs_ld + col * 4;
             if (src) hc_cp16(st_base + (size_t)gi * gs + dst_off, src);
           }
         }
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           const int gi = i * (32 / CPR) + lane / CPR, col = lane % CPR;
           const int ts = __shfl_sync(GCM_FULL_MASK, tslot, gi);
           if (gi < gt) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)(g0 + gi) * F + col * 4));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)(g0 + gi) * a.obs_ld + col * 4));
             *reinterpret_cast<float4*>(a.st.nodes + ((size_t)(g0 + gi) * C + ts) * F + col * 4) = v;
           }
         }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           bool bad = false;
 #pragma unroll
           for (int k = 0; k < 16; ++k) bad |= !isfinite(o0[k]) | !isfinite(o1[k]);
-          float4* dst = reinterpret_cast<float4*>(a.belief + (size_t)(g0 + lane) * HC_H);
+          float4* dst = reinterpret_cast<float4*>(a.belief + (size_t)(g0 + lane) * a.belief_ld);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             dst[k] = make_float4(o0[4 * k], o0[4 * k + 1], o0[4 * k + 2], o0[4 * k + 3]);
@@ -675,7 +675,9 @@ bool gcm_temporal_hc_shape_ok(const TemporalWinArgs& a) {
 }
 
 int gcm_launch_temporal_hc(const TemporalWinArgs& a, cudaStream_t stream) {
-  if (!a.hcache || !gcm_temporal_hc_shape_ok(a) || (reinterpret_cast<uintptr_t>(a.hcache) & 15) != 0)
+  if (!a.hcache || !gcm_temporal_hc_shape_ok(a) || (reinterpret_cast<uintptr_t>(a.hcache) & 15) != 0 ||
+      (a.obs_ld & 3) != 0 || (a.belief_ld & 3) != 0 || a.obs_ld < a.st.F || a.belief_ld < HC_H ||
+      (reinterpret_cast<uintptr_t>(a.belief) & 15) != 0)
     return GCM_ERR_UNSUPPORTED;
   switch (a.st.F) {
     case 8: return launch_hc<8>(a, stream);

@@ -354,6 +354,31 @@ extern "C" int gcm_state_log_write(const gcm_dense_state* st, const float* obs, 
   return gcm_check_launch("k_log_write");
 }
 
+// T node writes at once, AFTER the T steps that advanced the counters: nodes[b, (count[b] - T + k) % C, :] = x_seq[b, k, :]
+// (graph b, step k at b * stride_b + k * stride_t floats).  The raw-observation log of a sequence call (ray_gcm.py:200-202
+// with the Linear preprocessor of ray_gcm.py:118).
+__global__ void __launch_bounds__(256) k_log_write_seq(const gcm_dense_state st, const float* x_seq, long long stride_b,
+                                                       long long stride_t, int T, int k0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_b = (long long)(T - k0) * st.F;
+  if (i >= (long long)st.B * per_b) return;
+  const int b = (int)(i / per_b);
+  const long long rem = i - (long long)b * per_b;
+  const int k = k0 + (int)(rem / st.F), f = (int)(rem % st.F);
+  const int pos = __ldcg(st.count + b) - T + k;
+  st.nodes[((size_t)b * st.C + gcm_slot(pos, st.C)) * st.F + f] = x_seq[b * stride_b + k * stride_t + f];
+}
+extern "C" int gcm_state_log_write_seq(const gcm_dense_state* st, const float* x_seq, long long stride_b,
+                                       long long stride_t, int T, void* stream) {
+  GCM_REQUIRE(st && st->nodes && st->count && x_seq && st->B >= 0 && st->F >= 1 && st->C >= 1 && T >= 0,
+              "state_log_write_seq: bad arguments");
+  if (st->B == 0 || T == 0) return GCM_OK;
+  const int k0 = T > st->C ? T - st->C : 0;      // older rows would be overwritten by the later ones anyway
+  const long long n = (long long)st->B * (T - k0) * st->F;
+  k_log_write_seq<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, x_seq, stride_b, stride_t, T, k0);
+  return gcm_check_launch("k_log_write_seq");
+}
+
 extern "C" int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes,
                                           float* d_nodes_out, void* stream) {
   if (int rc = check_state(st)) return rc;

@@ -41,6 +41,8 @@ struct TemporalWinArgs {
   float* hcache;      // [B, hc_ring, 32] layer-1 output of the last hc_ring nodes (slot = position % hc_ring), or NULL
   int hc_ring;        // power of two
   int weights_stable; // GCM_STEP_WEIGHTS_STABLE: the weights were not written since the previous step of this state
+  long long obs_ld;    // floats between the observation rows of consecutive graphs (F when contiguous); hc kernel only
+  long long belief_ld; // floats between consecutive belief rows (H2 when contiguous); hc kernel only
 };
 
 

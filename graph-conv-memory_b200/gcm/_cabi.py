@@ -67,6 +67,18 @@ class GnnC(C.Structure):
     ]
 
 
+class RolloutC(C.Structure):
+    """gcm_rollout (include/gcm_b200.h): what the host keeps between the steps of a temporal rollout."""
+    _fields_ = [
+        ("st", DenseStateC), ("gnn", GnnC), ("sels", SelectorC * GCM_MAX_SELECTORS),
+        ("n_sels", C.c_int32), ("max_hop", C.c_int32),
+        ("hcache", C.c_void_p), ("hc_ring", C.c_int32),
+        ("uniform_count", C.c_int32), ("hc_fresh", C.c_int32), ("weights_stable", C.c_int32),
+        ("status", C.c_void_p), ("scratch_obs", C.c_void_p), ("scratch_belief", C.c_void_p),
+        ("launches", C.c_longlong),
+    ]
+
+
 class GnnGradsC(C.Structure):
     _fields_ = [
         ("d_w_rel1", C.c_void_p), ("d_w_root1", C.c_void_p), ("d_b1", C.c_void_p),
@@ -86,6 +98,11 @@ _SIGNATURES = {
                                 _P, _P, _I, _P]),
     "gcm_dense_step_fwd_cached": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), _I, C.POINTER(GnnC),
                                        _P, _P, _I, _P, _I, C.POINTER(C.c_int), _P]),
+    "gcm_dense_step_fwd_ex": (_I, [C.POINTER(DenseStateC), _P, _L, C.POINTER(SelectorC), _I, C.POINTER(GnnC),
+                                   _P, _L, _P, _I, _I, _P, _I, C.POINTER(C.c_int), _P]),
+    "gcm_dense_rollout_fwd": (_I, [C.POINTER(RolloutC), _P, _L, _L, _P, _L, _L, _I, _P]),
+    "gcm_dense_rollout_step": (_I, [C.POINTER(RolloutC), _P, _P, _P]),
+    "gcm_state_log_write_seq": (_I, [C.POINTER(DenseStateC), _P, _L, _L, _I, _P]),
     "gcm_set_temporal_kernel": (_I, [_I]),
     "gcm_dense_step_bwd": (_I, [C.POINTER(DenseStateC), _I, C.POINTER(GnnC), _P, _P, _P,
                                 C.POINTER(GnnGradsC), _P]),

@@ -336,7 +336,7 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
             state.hc_fresh = -(1 << 30)
         if state.host_count is not None:
             # every graph has the same count and the host knows it: spare the kernel the dependent load
-            flags |= _cabi.STEP_UNIFORM_COUNT | (state.host_count << _cabi.STEP_COUNT_SHIFT)
+            flags |= _cabi.STEP_UNIFORM_COUNT
         if plan.hc_ring:
             # layer-1 row cache (include/gcm_b200.h: gcm_dense_step_fwd_cached).  hc_fresh counts the newest
             # nodes whose cached row was written under the current weights; the cached-row kernel may run once
@@ -357,9 +357,10 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
     else:
         state.pure_key = None
     written = C.c_int(0)
-    _cabi.check(lib.gcm_dense_step_fwd_cached(state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(),
-                                              state.status.data_ptr(), flags, hcache, ring, C.byref(written),
-                                              stream), "gcm_dense_step_fwd")
+    _cabi.check(lib.gcm_dense_step_fwd_ex(state.c_ref(), x.data_ptr(), 0, sels, n, C.byref(gnn_c), belief.data_ptr(), 0,
+                                          state.status.data_ptr(), flags,
+                                          state.host_count if (flags & _cabi.STEP_UNIFORM_COUNT) else -1, hcache, ring,
+                                          C.byref(written), stream), "gcm_dense_step_fwd")
     if hcache is not None:
         if state.hc_fresh < 0:           # captured launch: replays run without the host, start over afterwards
             state.hc_fresh = 0
@@ -371,41 +372,16 @@ def _launch_fwd(plan: FusedPlan, state: DenseState, x: torch.Tensor, belief: tor
         state.host_count += 1
     # steady-state rollout on the row-cache kernel: the next step may take fast_temporal_step
     state.fast_ok = bool(hcache is not None and (flags & _cabi.STEP_HCACHE_VALID) and state.hc_fresh > 0 and dist is None)
+    if state.fast_ok:
+        from gcm import temporal as _temporal
+        state.fast_ok = _temporal.ready(plan, state) is not None     # the descriptor the fast path calls through
 
 
 def fast_temporal_step(plan: FusedPlan, state: DenseState, x: torch.Tensor):
-    """The steady-state rollout step (no autograd, forward-only temporal chain on the row-cache kernel) with the host
-    work cut to what can change between two steps: input checks, the weights key, the flags, the launch.  Returns None
-    whenever anything is unusual; DenseGCM.forward then takes the general route, which re-derives everything (and is the
-    only place that raises).  Same launch as _launch_fwd, argument for argument."""
-    if (x.dtype is not torch.float32 or not x.is_cuda or x.dim() != 2 or x.shape[0] != state.B or x.shape[1] != state.F
-            or not x.is_contiguous() or state.pure_key != plan.temporal_key or state.masks_stale
-            or torch.cuda.is_current_stream_capturing()):
-        return None
-    dev = state.device
-    gnn_c = plan.gnn.packed(dev)
-    if state.hc_key != plan.gnn._key or state.hc_fresh < plan.max_hop or state.hcache is None:
-        return None                              # weights changed / cache not warm: the general route handles it
-    flags = _cabi.STEP_PURE_TEMPORAL | _cabi.STEP_HCACHE_VALID | _cabi.STEP_WEIGHTS_STABLE
-    hc = state.host_count
-    if hc is not None:
-        if hc < plan.max_hop:
-            return None
-        flags |= _cabi.STEP_UNIFORM_COUNT | (hc << _cabi.STEP_COUNT_SHIFT)
-    sels, n = plan.selectors_c(state.F, None)
-    belief = torch.empty(state.B, plan.gnn.H2, device=dev, dtype=torch.float32)
-    written = C.c_int(0)
-    _cabi.check(_cabi.lib().gcm_dense_step_fwd_cached(
-        state.c_ref(), x.data_ptr(), sels, n, C.byref(gnn_c), belief.data_ptr(), state.status.data_ptr(), flags,
-        state.hcache.data_ptr(), plan.hc_ring, C.byref(written), _cabi.stream_ptr(dev)), "gcm_dense_step_fwd")
-    state.hc_fresh = min(state.hc_fresh + 1, plan.max_hop) if written.value else 0
-    state.fast_ok = state.hc_fresh > 0
-    state.max_count += 1
-    state.version += 1
-    state.steps += 1
-    if hc is not None:
-        state.host_count = hc + 1
-    return belief
+    """The steady-state rollout step (no autograd, forward-only temporal chain on the row-cache kernel): see
+    gcm.temporal.fast_step.  Returns None whenever anything is unusual; DenseGCM.forward then takes the general route."""
+    from gcm import temporal as _temporal
+    return _temporal.fast_step(plan, state, x)
 
 
 def zc_step(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> Optional[torch.Tensor]:

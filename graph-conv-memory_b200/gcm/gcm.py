@@ -18,7 +18,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 import gcm.util
-from gcm import _cabi, fused, ones
+from gcm import _cabi, fused, ones, temporal
 from gcm.state import DenseHidden, DenseState
 
 
@@ -174,7 +174,7 @@ class DenseGCM(torch.nn.Module):
             plan = self._plan
             if (st.fast_ok and hidden._version == st.version and hidden.token is None and plan is not None
                     and plan.validated and not plan.pre):
-                belief = fused.fast_temporal_step(plan, st, x)
+                belief = temporal.fast_step(plan, st, x)
                 if belief is not None:
                     if not DenseGCM.did_warn and st.host_count is not None and st.host_count > st.N:
                         print("Overflow detected, wrapping around. Will not warn again")
@@ -227,7 +227,7 @@ class DenseGCM(torch.nn.Module):
                         y = ones._lin2(x_raw, pre.weight, bias=pre.bias)
                     else:
                         y = pre(x_raw)
-                    belief = fused.fast_temporal_step(plan, state, y)
+                    belief = temporal.fast_step(plan, state, y)
                     if belief is not None:
                         _cabi.check(_cabi.lib().gcm_state_log_write(state.raw_ref(), x_raw.data_ptr(), -1,
                                                                     _cabi.stream_ptr(x.device)), "gcm_state_log_write")
@@ -346,7 +346,12 @@ class DenseGCM(torch.nn.Module):
             return torch.stack(outs, dim=1), hidden
 
         plan = self.fused_plan()
-        if plan is None or not plan.ones or T < 2 or not x_seq.is_cuda or x_seq.dtype != torch.float32:
+        if plan is None or T < 2 or not x_seq.is_cuda or x_seq.dtype != torch.float32:
+            return loop(hidden)
+        if plan.temporal_key is not None and plan.hc_ring:
+            return self._sequence_temporal(plan, x_seq, hidden, loop)
+        if not plan.ones or plan.pre:
+            # (a DenseEdge state behind a preprocessor keeps two logs; its sequence kernels only know one)
             return loop(hidden)
         recording = torch.is_grad_enabled() and (
             x_seq.requires_grad or any(p.requires_grad for p in plan.gnn.params())
@@ -380,6 +385,56 @@ class DenseGCM(torch.nn.Module):
             beliefs = ones.sequence_nograd(plan, state, rest.detach(), bf16)
             token = None
         return torch.cat([out0.unsqueeze(1), beliefs.transpose(0, 1)], dim=1), DenseHidden(state, token)
+
+    def _sequence_temporal(self, plan, x_seq, hidden, loop):
+        """forward_sequence for forward-only TemporalBackedge chains (with or without a row-wise preprocessor): the T
+        steps are enqueued by ONE C call (gcm.temporal.sequence_nograd -> gcm_dense_rollout_fwd), which reads x_seq
+        [B, T, F] and writes the [B, T, H] result in place.  Anything that records autograd, and any state that is not a
+        pure temporal state of this chain, takes the step loop."""
+        T = x_seq.shape[1]
+        pre = self.preprocessor if plan.pre else None
+        if torch.is_grad_enabled() and (
+                x_seq.requires_grad or any(p.requires_grad for p in self.parameters())
+                or (isinstance(hidden, DenseHidden) and hidden.token is not None)
+                or (isinstance(hidden, (tuple, list)) and hidden[0].requires_grad)):
+            return loop(hidden)
+        with torch.no_grad():
+            start = 0
+            out0 = None
+            state = hidden._state if (hidden.__class__ is DenseHidden and hidden.live() and hidden.token is None) else None
+            if state is None or not plan.validated or self._plan is not plan or state.rollout is None:
+                # enter the state exactly as forward() does, by taking the first step through it
+                out0, hidden = self(x_seq[:, 0], hidden)
+                start = 1
+                state = hidden._state if (hidden.__class__ is DenseHidden and hidden.live()) else None
+            if pre is not None and state is not None:
+                plist = self.__dict__.get("_pre_params")
+                if plist is None:
+                    plist = self.__dict__["_pre_params"] = list(pre.parameters())
+                pkey = tuple([v for p in plist for v in (p.data_ptr(), p._version)])
+                if state.raw is None or state.pre_key != pkey:
+                    state = None                 # forward() rebuilds the preprocessed log under the new weights
+            rest_raw = x_seq[:, start:]
+            rest = rest_raw if pre is None else (pre(rest_raw) if state is not None else None)
+            if (state is None or self._plan is not plan or rest.dtype != torch.float32
+                    or not temporal.sequence_supported(plan, state, rest)):
+                outs = [] if out0 is None else [out0]
+                for t in range(start, T):
+                    out, hidden = self(x_seq[:, t], hidden)
+                    outs.append(out)
+                return torch.stack(outs, dim=1), hidden
+            beliefs = torch.empty(state.B, T, plan.gnn.H2, device=x_seq.device, dtype=torch.float32)
+            if out0 is not None:
+                beliefs[:, 0] = out0
+            if not DenseGCM.did_warn and state.host_count is not None and state.host_count + (T - start) > state.N:
+                print("Overflow detected, wrapping around. Will not warn again")
+                DenseGCM.did_warn = True
+            temporal.sequence_nograd(plan, state, rest, beliefs[:, start:])
+            if pre is not None:
+                _cabi.check(_cabi.lib().gcm_state_log_write_seq(
+                    state.raw_ref(), rest_raw.data_ptr(), rest_raw.stride(0), rest_raw.stride(1), T - start,
+                    _cabi.stream_ptr(x_seq.device)), "gcm_state_log_write_seq")
+            return beliefs, DenseHidden(state, None)
 
     def _would_overflow(self, state: DenseState) -> bool:
         # host-side mirror only (no device sync): graphs started empty overflow after N steps

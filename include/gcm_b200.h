@@ -149,6 +149,41 @@ int gcm_dense_step_fwd_cached(const gcm_dense_state* st, const float* obs, const
                               int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status, int flags,
                               float* hcache, int hc_ring, int* cache_written, void* stream);
 
+/* The same step with the uniform count as its own argument (any int32; the packed form above holds 23 bits) and
+ * strided rows: observation of graph b at obs + b * obs_ld floats, belief row b at belief + b * belief_ld (0 = contiguous;
+ * multiples of 4).  Strided rows are what a caller holding [B, T, .] tensors passes for one t (ray_gcm.py:200-202); only
+ * the cached-row kernel takes them, any other kernel choice returns GCM_ERR_UNSUPPORTED without launching. */
+int gcm_dense_step_fwd_ex(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
+                          int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status, int flags,
+                          int uniform_count, float* hcache, int hc_ring, int* cache_written, void* stream);
+
+/* Rollout entry for TEMPORAL-only selector chains (edge_selectors/temporal.py:72-88): T consecutive DenseGCM.forward
+ * steps (gcm.py:213-321) enqueued back to back from C, i.e. the loop `for t in range(T): out, hidden = self.gcm(flat[:,
+ * t, :], hidden)` of ray_gcm.py:200-202 without a host round trip per step.  The descriptor carries what the host
+ * otherwise keeps between steps; the library updates the in/out fields.  Step k reads obs + k * obs_stride_t (graph b at
+ * + b * obs_ld) and writes belief + k * belief_stride_t (row b at + b * belief_ld); scratch_obs [B,F] / scratch_belief
+ * [B,H2] are needed when rows are strided (steps that cannot run on the cached-row kernel are staged through them). */
+typedef struct gcm_rollout {
+  gcm_dense_state st;
+  gcm_gnn gnn;
+  gcm_selector sels[GCM_MAX_SELECTORS];
+  int32_t n_sels;
+  int32_t max_hop;        /* largest hop of the chain                                                         */
+  float* hcache;          /* layer-1 row cache [B, hc_ring, H1] (see gcm_dense_step_fwd_cached) or NULL        */
+  int32_t hc_ring;
+  int32_t uniform_count;  /* in/out: every graph's count when they are all equal (host mirror), else -1        */
+  int32_t hc_fresh;       /* in/out: newest nodes whose cached row was written under the current weights       */
+  int32_t weights_stable; /* in: the weights were not written since the previous step of this state            */
+  int32_t* status;        /* device status word                                                                */
+  float* scratch_obs;
+  float* scratch_belief;
+  long long launches;     /* out: kernels launched by the last call                                            */
+} gcm_rollout;
+int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long obs_ld, long long obs_stride_t, float* belief,
+                          long long belief_ld, long long belief_stride_t, int T, void* stream);
+/* one contiguous step: gcm_dense_rollout_fwd(r, obs, 0, 0, belief, 0, 0, 1, stream) */
+int gcm_dense_rollout_step(gcm_rollout* r, const float* obs, float* belief, void* stream);
+
 /* Which kernel serves GCM_STEP_PURE_TEMPORAL steps (process-wide; default AUTO = fastest that fits the
  * shape).  All variants compute the same step; the switch exists for parity tests and A/B profiling. */
 typedef enum gcm_temporal_kernel {
@@ -178,6 +213,10 @@ int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out, float* ad
  * a state (the raw-observation log kept beside the preprocessed one when DenseGCM has a preprocessor, gcm.py:290-291).
  * offset = 0 before the step that advances the counters, -1 after it. */
 int gcm_state_log_write(const gcm_dense_state* st, const float* obs, int offset, void* stream);
+/* T node writes at once, after the T steps that advanced the counters: nodes[b, (count[b] - T + k) % C, :] = x_seq[b, k, :]
+ * with x_seq[b, k, :] at b * stride_b + k * stride_t floats (the raw-observation log of a sequence call). */
+int gcm_state_log_write_seq(const gcm_dense_state* st, const float* x_seq, long long stride_b, long long stride_t, int T,
+                            void* stream);
 /* dL/dnodes in log layout -> [B,N,F] reference layout (rows >= num_nodes are zero) */
 int gcm_state_materialize_grad(const gcm_dense_state* st, const float* d_nodes, float* d_nodes_out,
                                void* stream);

@@ -35,15 +35,17 @@ def test_abi_struct_layout_matches_header(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "gcm_b200.h"\n'
-        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(gcm_dense_state), sizeof(gcm_selector),"
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(gcm_dense_state), sizeof(gcm_selector),"
         " sizeof(gcm_gnn), sizeof(gcm_gnn_grads), offsetof(gcm_selector, max_distance), offsetof(gcm_selector, dist_param),"
-        " offsetof(gcm_gnn, F), offsetof(gcm_dense_state, B));return 0;}\n")
+        " offsetof(gcm_gnn, F), offsetof(gcm_dense_state, B), sizeof(gcm_rollout), offsetof(gcm_rollout, sels),"
+        " offsetof(gcm_rollout, hcache), offsetof(gcm_rollout, status), offsetof(gcm_rollout, launches));return 0;}\n")
     exe = tmp_path / "abi"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(_cabi.DenseStateC), ctypes.sizeof(_cabi.SelectorC), ctypes.sizeof(_cabi.GnnC),
             ctypes.sizeof(_cabi.GnnGradsC), _cabi.SelectorC.max_distance.offset, _cabi.SelectorC.dist_param.offset,
-            _cabi.GnnC.F.offset, _cabi.DenseStateC.B.offset]
+            _cabi.GnnC.F.offset, _cabi.DenseStateC.B.offset, ctypes.sizeof(_cabi.RolloutC), _cabi.RolloutC.sels.offset,
+            _cabi.RolloutC.hcache.offset, _cabi.RolloutC.status.offset, _cabi.RolloutC.launches.offset]
     assert got == want
 
 
@@ -238,7 +240,7 @@ def test_bench_reference_arm_prints_the_contract_line():
         for key in ("metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
                     "config", "cpu_baseline", "e2e"):
             assert key in line, key
-        assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+        assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_bench_workload_table_and_roofline_accounting_are_consistent():
