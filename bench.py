@@ -64,6 +64,12 @@ WORKLOADS = {
 BPTT_T = 64
 
 
+def progress(msg):
+    """stage markers on stderr (GCM_BENCH_VERBOSE=1): a killed run still shows how far it got"""
+    if os.environ.get("GCM_BENCH_VERBOSE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def _product_paths():
     for p in PKG_PATHS:
         if p not in sys.path:
@@ -443,6 +449,7 @@ def run_rollout(ctx, workload, B, K, W, args):
 
             if fill:
                 _, hidden = mod.forward_sequence(xs(fill), hidden)
+            progress(f"{workload}: filled")
             x_warm, x_seq = xs(max(W, 2), fill), xs(K, fill + W)
             _, hidden = mod.forward_sequence(x_warm, hidden)
             _, hidden = mod.forward_sequence(x_seq, hidden)           # same call shape as the timed one (allocator warm)
@@ -538,6 +545,7 @@ def run_rollout(ctx, workload, B, K, W, args):
             main.wait_stream(h2d)
             return hidden
 
+        progress(f"{workload}: device-resident timing done, e2e next")
         hidden = e2e_steps(2 * R, hidden)
         e2e_runs = []
         for _ in range(3):                      # PCIe / host jitter: median of three timed passes of K steps
@@ -629,6 +637,7 @@ def run_bptt(ctx, workload, B, K, W, args):
 
     for _ in range(min(W, 2)):
         window(obs_dev, obs_bt)
+        progress(f"{workload}: warm-up window done")
     ctx.barrier()
     t_lo = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -641,6 +650,7 @@ def run_bptt(ctx, workload, B, K, W, args):
     n_l0 = lib.gcm_launch_count()
     window(obs_dev, obs_bt)
     torch.cuda.synchronize()
+    progress(f"{workload}: timed windows done")
     launches = int(lib.gcm_launch_count() - n_l0) * K
     # end to end from HOST buffers: the window's observations come from pinned host memory, the loss is read back
     def e2e_window():
@@ -757,7 +767,9 @@ def run_workload(ctx, workload, K, W, args, batch=None):
 
     desc, B0, N, F, H, spec, mode = WORKLOADS[workload]
     B = batch or B0
+    progress(f"{workload}: start (B={B}, K={K}, W={W})")
     r = {"rollout": run_rollout, "bptt": run_bptt, "sparse": run_sparse}[mode](ctx, workload, B, K, W, args)
+    progress(f"{workload}: timed region done, {r['total_ms'] / K:.4f} ms per step")
     total_ms, kern_ms, extra = r["total_ms"], r["kern_ms"], r["extra"]
     value = r["unit_per_step"] * ctx.world * K / (total_ms * 1e-3)
     clocks = ctx.sampler.window(r["t_lo"], r["t_hi"])
@@ -870,6 +882,7 @@ def main():
             line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
             cb = {"cfg2": args.cpu_batch, "cfg5": 8}.get(args.workload, 64)
+            progress("cpu baseline: start")
             line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, cb, 6 if mode != "sparse" else 1, 2)
         print(json.dumps(line))
     if dist is not None:

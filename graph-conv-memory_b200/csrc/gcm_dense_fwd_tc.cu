@@ -7,7 +7,7 @@
 // tcgen05 the FMAs disappear from the instruction stream.  fp32 accuracy is kept with the 3xTF32 split
 // (gcm_tc.cuh; 5e-7 relative on B200, tests/test_tc_gpu.py).
 //
-// One persistent CTA per SM, 14 warps:
+// One persistent CTA per SM, 15 warps:
 //   warps 0-11       three consumer groups of 4 warps, each owns a 32-graph tile: warp r of a group holds
 //                    row r of R1 for all 32 graphs (lane = graph), so TMEM lane = 32 r + graph and the
 //                    neighbour program is warp-uniform.  They build [agg | x] (hi, lo) straight into TMEM
@@ -16,7 +16,7 @@
 //                    Warp 3 of a group also issues the group's MMAs (one elected lane) once the other
 //                    three have arrived on a named barrier; warps 0-2 carry one state-update duty each
 //                    (node rows / adjacency rows / counters) while the tensor core works.
-//   warps 12-13      producers: 16-byte cp.async (coalesced, 512 B per instruction) of each graph's
+//   warps 12-14      producers (one per group's stage): 16-byte cp.async (coalesced, 512 B per instruction) of each graph's
 //                    history window + the observation tile into the group's shared-memory stage, completion
 //                    signalled with cp.async.mbarrier.arrive.  (Round-1 profile: one warp issuing 96
 //                    lane-serialised bulk copies per tile was the throughput limiter, profiles/.)  A stage
@@ -29,7 +29,7 @@
 
 constexpr int TC_G = 32;                  // graphs per tile
 constexpr int TC_GROUPS = 3;
-constexpr int TC_NPROD = 2;               // producer warps
+constexpr int TC_NPROD = TC_GROUPS;       // producer warps: ONE PER STAGE (see the producer loop)
 constexpr int TC_CONS_THREADS = 4 * TC_GROUPS * 32;
 constexpr int TC_THREADS = TC_CONS_THREADS + TC_NPROD * 32;
 constexpr int TC_MAXNB = 6;               // in-neighbours per row held in registers
@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_step_temporal_tc(const Tempor
   if (warp >= PROD_WARP0) {
     // =============================== producers ===============================
     // 16-byte cp.async per lane: consecutive lanes cover consecutive chunks of one graph's history window
-    // (coalesced 512 B per instruction); tiles alternate between the producer warps.
+    // (coalesced 512 B per instruction).  Producer p only ever fills stage p (tiles j = p, p + 3, ...): the one-bit
+    // phase parity of a stage's mbarriers is unambiguous only if its fills are issued in order by one warp -- with two
+    // producers alternating over three stages a producer could run a whole tile ahead of a slow consumer group,
+    // see a stale parity on `empty` and refill a stage that was still being read (hang at B = 65536 on full graphs).
+    static_assert(TC_NPROD == TC_GROUPS, "one producer warp per stage");
     for (int j = warp - PROD_WARP0; j < my_tiles; j += TC_NPROD) {
       const int grp = j % TC_GROUPS, it = j / TC_GROUPS;
       const int tile = blockIdx.x + j * gridDim.x;

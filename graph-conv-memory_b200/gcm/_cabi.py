@@ -103,6 +103,8 @@ _SIGNATURES = {
     "gcm_dense_rollout_fwd": (_I, [C.POINTER(RolloutC), _P, _L, _L, _P, _L, _L, _I, _P]),
     "gcm_dense_rollout_step": (_I, [C.POINTER(RolloutC), _P, _P, _P]),
     "gcm_state_log_write_seq": (_I, [C.POINTER(DenseStateC), _P, _L, _L, _I, _P]),
+    "gcm_temporal_gather": (_I, [C.POINTER(DenseStateC), _P, _I, _L, _I, _P, _P]),
+    "gcm_temporal_shift_sum": (_I, [_P, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _P]),
     "gcm_set_temporal_kernel": (_I, [_I]),
     "gcm_dense_step_bwd": (_I, [C.POINTER(DenseStateC), _I, C.POINTER(GnnC), _P, _P, _P,
                                 C.POINTER(GnnGradsC), _P]),
@@ -189,7 +191,20 @@ def lib() -> C.CDLL:
     return handle
 
 
+_TRACE = bool(os.environ.get("GCM_B200_TRACE"))
+_trace_t = [0.0]
+
+
 def check(rc: int, what: str) -> None:
+    if _TRACE:
+        # debugging aid: synchronise after every library call and print what ran and how long it took
+        import sys
+        import time
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        print(f"[gcm trace] {what}: {lib().gcm_last_kernel().decode()} +{(now - _trace_t[0]) * 1e3:.2f} ms",
+              file=sys.stderr, flush=True)
+        _trace_t[0] = now
     if rc != 0:
         msg = lib().gcm_last_error().decode("utf-8", "replace")
         raise GcmLibraryError(f"{what} failed (status {rc}): {msg}")

@@ -312,7 +312,12 @@ class DenseGCM(torch.nn.Module):
                 belief = ones.step_nograd(plan, state, xc.detach(), ones.want_bf16(self, plan))
                 token = None
         elif recording:
-            belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
+            if (not ingest_grad and (token is None or getattr(token, "_gcm_tw", False))
+                    and temporal.grad_supported(plan, state)):
+                # forward-only temporal chain on a state it built itself: window-level backward (gcm.temporal)
+                belief, token, state = temporal.step_grad(plan, state, xc, token, self.bptt_capacity)
+            else:
+                belief, token, state = fused.fused_step_grad(plan, state, xc, token, self.bptt_capacity)
         else:
             belief = None
             if plan.zc and state.zc_ok:
@@ -397,7 +402,32 @@ class DenseGCM(torch.nn.Module):
                 x_seq.requires_grad or any(p.requires_grad for p in self.parameters())
                 or (isinstance(hidden, DenseHidden) and hidden.token is not None)
                 or (isinstance(hidden, (tuple, list)) and hidden[0].requires_grad)):
-            return loop(hidden)
+            if pre is not None or T > int(self.bptt_capacity):
+                return loop(hidden)
+            # recording: one autograd node for the T steps, window-level backward (gcm.temporal)
+            out0, start = None, 0
+            if not (hidden.__class__ is DenseHidden and hidden.live()):
+                out0, hidden = self(x_seq[:, 0], hidden)     # enter the state exactly as forward() does
+                start = 1
+            state = hidden._state if (hidden.__class__ is DenseHidden and hidden.live()) else None
+            token = hidden.token if state is not None else None
+            ok = (state is not None and self._plan is plan and temporal.grad_supported(plan, state)
+                  and (token is None or getattr(token, "_gcm_tw", False)) and x_seq.dtype == torch.float32)
+            if ok and token is not None:
+                ok = state.steps - state.twin.chain_start + (T - start) <= state.C - state.N + 1
+            if not ok:
+                outs = [] if out0 is None else [out0]
+                for t in range(start, T):
+                    out, hidden = self(x_seq[:, t], hidden)
+                    outs.append(out)
+                return torch.stack(outs, dim=1), hidden
+            if not DenseGCM.did_warn and state.host_count + (T - start) > state.N:
+                print("Overflow detected, wrapping around. Will not warn again")
+                DenseGCM.did_warn = True
+            beliefs, token, state = temporal.sequence_grad(plan, state, x_seq[:, start:], token, self.bptt_capacity)
+            if out0 is not None:
+                beliefs = torch.cat([out0.unsqueeze(1), beliefs], dim=1)
+            return beliefs, DenseHidden(state, token)
         with torch.no_grad():
             start = 0
             out0 = None

@@ -69,6 +69,7 @@ class DenseState:
         self.hc_key = None          # weights key the cached rows were computed under
         self.hc_fresh = 0           # newest nodes whose cached row is valid under hc_key
         self.fast_ok = False        # last step was a steady-state row-cache step (gcm.fused.fast_temporal_step may run)
+        self.twin = None            # gcm.temporal._TWindow: the BPTT window being recorded on a temporal chain
         self.rollout = None         # gcm.temporal.Rollout: the gcm_rollout descriptor of this state (temporal chains)
         self._c = _cabi.DenseStateC(self.nodes.data_ptr(), self.masks.data_ptr(), self.count.data_ptr(),
                                     B, N, self.C, F, self.W)

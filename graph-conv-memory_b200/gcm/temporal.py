@@ -154,3 +154,303 @@ def sequence_nograd(plan, state, x_seq: torch.Tensor, beliefs: torch.Tensor) -> 
         _cabi.check(rc, "gcm_dense_rollout_fwd")
     _sync_out(ro, state, T)
     return int(c.launches)
+
+
+# ------------------------------------------------------------------------------------------------
+# BPTT: window-level backward (csrc/gcm_temporal_bwd.cu + the 3xTF32 products of csrc/gcm_tc_gemm.cu)
+# ------------------------------------------------------------------------------------------------
+# Autograd through gcm.py:262-321 over the steps of a BPTT window (the reference's training loop:
+# tests/test_gcm.py:412-439).  GCM has no recurrence through the belief, so when backward() runs every step's
+# dL/dbelief is known; each recorded step (or sequence call) only delivers dz2 = dL/dbelief * act2'(belief) into the
+# window buffer, and the chain's root node -- which autograd runs last, every step depends on it through the token
+# chain -- does the whole window's work as a few row-parallel products over [rows, graphs] (see the .cu header for
+# the algebra).  Nothing but the beliefs is saved: layer 1 is recomputed from the node log, which keeps every row
+# the window needs because the log has spare capacity while gradients are being recorded (DenseState.C > N).
+def grad_supported(plan, state) -> bool:
+    """Forward-only hops on the cached-row shape, state built from empty by this chain (so an edge p-s -> p exists iff
+    p - s >= 0 and every graph has the same count, mirrored on the host)."""
+    return bool(plan.hc_ring and plan.temporal_key is not None and state.pure_key in ((), plan.temporal_key)
+                and state.host_count is not None and state.F % 4 == 0 and state.N - 1 >= 2 * plan.max_hop
+                and not state.masks_stale)
+
+
+class _TWindow:
+    """Bookkeeping of the BPTT window being recorded on a state (one chain of steps at a time)."""
+
+    def __init__(self):
+        self.chain_id = 0
+        self.chain_start = 0      # state.steps when the chain started
+        self.P0 = 0               # absolute position of the node written by the chain's first step
+        self.kmax = -1            # newest-first backward: steps kmax .. k have delivered dz2 so far
+        self.dz2 = None           # [K, B, H2] float32, time-major; zero rows = steps whose belief got no gradient
+        self.cache = None         # (A1, h, dz1) over the whole window, left by a sequence node for the root
+
+
+def _hops(plan, dev):
+    """the chain's hop list as a HOST int32 array (the C entry points read it on the host)"""
+    t = plan.__dict__.get("_hops_host")
+    if t is None:
+        hops = sorted({h for s in plan.sels for h in s.hops})
+        t = plan.__dict__["_hops_host"] = (torch.tensor(hops, dtype=torch.int32, device="cpu"), len(hops))
+    return t
+
+
+def _wcat(plan, dev):
+    """[W_rel | W_root] packs for the window products, rebuilt when a parameter changed."""
+    g = plan.gnn
+    g.packed(dev)
+    if g.__dict__.get("_wcat_key") != g._key:
+        w = g._packed[1]
+        g._wcat = {
+            "w1": torch.cat([w["w_rel1"], w["w_root1"]], dim=1).contiguous(),               # [H1, 2F]   h  = A1 w1^T
+            "w2t": torch.cat([w["w_rel2"].t(), w["w_root2"].t()], dim=1).contiguous(),      # [H1, 2H2]  dh = D2 w2t^T
+            "w1t": torch.cat([w["w_rel1"].t(), w["w_root1"].t()], dim=1).contiguous(),      # [F, 2H1]   dx = D1 w1t^T
+            "b1": w["b1"],
+        }
+        g._wcat_key = g._key
+    return g._wcat
+
+
+def _lin(a, w, bias=None, act=0, out=None):
+    from gcm import ones
+    rows, k = a.shape
+    if k % 16 == 0 and w.shape[0] % 16 == 0:
+        return ones._lin_tc32(a, w, bias=bias, act=act, out=out)
+    return ones._lin2(a, w, bias=bias, act=act, out=out)
+
+
+def _outer(a, x, dw, db):
+    from gcm import ones
+    if x.shape[1] % 16 == 0:
+        ones._outer_tc32(a, x, dw, db)
+    else:
+        ones._outer(a, x, dw, db)
+
+
+def _shift_sum(plan, src, src_pos0, sign, out, out_pos0):
+    hops, nh = _hops(plan, src.device)
+    n_src, B, H = src.shape
+    _cabi.check(_cabi.lib().gcm_temporal_shift_sum(src.data_ptr(), src_pos0, n_src, 0, hops.data_ptr(), nh, sign,
+                                                   out.data_ptr(), out_pos0, out.shape[0], B, H,
+                                                   _cabi.stream_ptr(src.device)), "gcm_temporal_shift_sum")
+
+
+def _rows(plan, st, win, p_lo, p_hi, Kc):
+    """Layer-1 operand rows A1 = [sum_s x_{p-s} | x_p], h_p and dz1_p = dL/d(pre-activation of layer 1) for the node
+    positions p_lo .. p_hi-1, given the dz2 delivered so far (chain steps 0 .. Kc-1 = positions P0 .. P0+Kc-1)."""
+    g, dev = plan.gnn, st.device
+    n, B = p_hi - p_lo, st.B
+    hops, nh = _hops(plan, dev)
+    wc = _wcat(plan, dev)
+    lib = _cabi.lib()
+    A1 = torch.empty(n, B, 2 * st.F, device=dev, dtype=torch.float32)
+    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), _cabi.stream_ptr(dev)),
+                "gcm_temporal_gather")
+    h = _lin(A1.view(n * B, 2 * st.F), wc["w1"], bias=wc["b1"], act=_cabi.ACT[g.act1]).view(n, B, g.H1)
+    D2 = torch.empty(n, B, 2 * g.H2, device=dev, dtype=torch.float32)
+    _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo)
+    dz1 = _lin(D2.view(n * B, 2 * g.H2), wc["w2t"]).view(n, B, g.H1)
+    del D2
+    _cabi.check(lib.gcm_act_backward(dz1.data_ptr(), h.data_ptr(), _cabi.ACT[g.act1], n * B * g.H1, dz1.data_ptr(),
+                                     _cabi.stream_ptr(dev)), "gcm_act_backward")
+    return A1, h, dz1
+
+
+def _check_log(st, win, plan):
+    steps_total = st.steps - win.chain_start
+    if steps_total + 2 * plan.max_hop > st.C:
+        raise RuntimeError(
+            f"BPTT window too long for the node log: {steps_total} steps since the chain started but the log keeps "
+            f"{st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
+
+
+def _dx(plan, st, win, k_lo, k_hi, Kc, rows=None):
+    """dL/dx of chain steps k_lo .. k_hi-1 ([n, B, F], time-major); valid once steps k_lo .. Kc-1 delivered dz2."""
+    g = plan.gnn
+    mh = plan.max_hop
+    q_lo, q_hi = win.P0 + k_lo, win.P0 + k_hi
+    if rows is None:
+        z_lo, z_hi = q_lo, min(q_hi + mh, win.P0 + Kc)
+        _, _, dz1 = _rows(plan, st, win, z_lo, z_hi, Kc)
+    else:
+        z_lo, dz1 = rows
+    D1 = torch.empty(k_hi - k_lo, st.B, 2 * g.H1, device=st.device, dtype=torch.float32)
+    _shift_sum(plan, dz1, z_lo, +1, D1, q_lo)
+    return _lin(D1.view(-1, 2 * g.H1), _wcat(plan, st.device)["w1t"]).view(k_hi - k_lo, st.B, st.F)
+
+
+def _deliver(plan, st, win, k0, n, d_beliefs_tm, beliefs_tm):
+    """dz2 of chain steps k0 .. k0+n-1 from dL/dbelief and the beliefs (both [n, B, H2], time-major, contiguous)."""
+    g = plan.gnn
+    K = st.steps - win.chain_start
+    if win.dz2 is None or win.dz2.shape[0] < K:
+        win.dz2 = torch.zeros(K, st.B, g.H2, device=st.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().gcm_act_backward(d_beliefs_tm.data_ptr(), beliefs_tm.data_ptr(), _cabi.ACT[g.act2],
+                                             n * st.B * g.H2, win.dz2[k0:k0 + n].data_ptr(),
+                                             _cabi.stream_ptr(st.device)), "gcm_act_backward")
+    win.kmax = max(win.kmax, k0 + n - 1)
+
+
+class _TRootFn(torch.autograd.Function):
+    """Start of a recorded chain of temporal steps.  Runs LAST in backward: every weight gradient of the window."""
+
+    @staticmethod
+    def forward(ctx, anchor, plan, state, chain_id, *params):
+        ctx.plan, ctx.state, ctx.chain_id = plan, state, chain_id
+        ctx.pkey = plan.gnn.current_key(state.device)
+        return anchor.clone()
+
+    @staticmethod
+    def backward(ctx, d_token):
+        from gcm import ones
+        plan, st = ctx.plan, ctx.state
+        g, win, dev = plan.gnn, st.twin, st.device
+        if g.current_key(dev) != ctx.pkey:
+            raise RuntimeError("GNN parameters were modified in place between forward and backward")
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        Kc = win.kmax + 1
+        F, H1, H2, B, mh = st.F, g.H1, g.H2, st.B, plan.max_hop
+        dW1 = torch.zeros(H1, 2 * F, device=dev)
+        dW2 = torch.zeros(H2, 2 * H1, device=dev)
+        db1, db2 = torch.zeros(H1, device=dev), torch.zeros(H2, device=dev)
+        if Kc > 0:
+            _check_log(st, win, plan)
+            p_lo, p_hi = win.P0 - mh, win.P0 + Kc
+            if win.cache is not None:
+                A1, h, dz1 = win.cache
+            else:
+                A1, h, dz1 = _rows(plan, st, win, p_lo, p_hi, Kc)
+            n = p_hi - p_lo
+            _outer(dz1.view(n * B, H1), A1.view(n * B, 2 * F), dW1, db1)
+            del A1, dz1
+            A2 = torch.empty(Kc, B, 2 * H1, device=dev, dtype=torch.float32)
+            _shift_sum(plan, h, p_lo, -1, A2, win.P0)
+            _outer(win.dz2[:Kc].view(Kc * B, H2), A2.view(Kc * B, 2 * H1), dW2, db2)
+        win.kmax, win.dz2, win.cache = -1, None, None
+        grads = {"w_rel1": dW1[:, :F].contiguous(), "w_root1": dW1[:, F:].contiguous(), "b1": db1,
+                 "w_rel2": dW2[:, :H1].contiguous(), "w_root2": dW2[:, H1:].contiguous(), "b2": db2}
+        return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, grads))
+
+
+class _TStepFn(torch.autograd.Function):
+    """One recorded step.  Saved: the belief [B, H2]."""
+
+    @staticmethod
+    def forward(ctx, x, token, plan, state, k):
+        from gcm import fused
+        belief = torch.empty(state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)
+        fused._launch_fwd(plan, state, x.detach(), belief)
+        ctx.plan, ctx.state, ctx.k = plan, state, k
+        ctx.chain_id = state.twin.chain_id
+        ctx.save_for_backward(belief)
+        return belief, torch.zeros(1, device=state.device)
+
+    @staticmethod
+    def backward(ctx, d_belief, d_token):
+        plan, st, k = ctx.plan, ctx.state, ctx.k
+        win = st.twin
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        (belief,) = ctx.saved_tensors
+        _deliver(plan, st, win, k, 1, d_belief.contiguous().float(), belief)
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            _check_log(st, win, plan)
+            d_x = _dx(plan, st, win, k, k + 1, win.kmax + 1)[0]
+        return d_x, torch.zeros(1, device=st.device), None, None, None
+
+
+class _TSeqFn(torch.autograd.Function):
+    """T recorded steps taken at once (DenseGCM.forward_sequence): one node for the steps k0 .. k0+T-1."""
+
+    @staticmethod
+    def forward(ctx, x_seq, token, plan, state, k0):
+        from gcm import fused
+        T = x_seq.shape[1]
+        buf = torch.empty(T, state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)   # time-major
+        xs = x_seq.detach()
+        if sequence_supported(plan, state, xs):
+            sequence_nograd(plan, state, xs, buf.transpose(0, 1))
+        else:
+            for t in range(T):
+                fused._launch_fwd(plan, state, xs[:, t].contiguous(), buf[t])
+        ctx.plan, ctx.state, ctx.k0, ctx.T = plan, state, k0, T
+        ctx.chain_id = state.twin.chain_id
+        ctx.buf = buf
+        return buf.transpose(0, 1), torch.zeros(1, device=state.device)
+
+    @staticmethod
+    def backward(ctx, d_beliefs, d_token):
+        plan, st, k0, T = ctx.plan, ctx.state, ctx.k0, ctx.T
+        win = st.twin
+        if win.chain_id != ctx.chain_id:
+            raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
+        _deliver(plan, st, win, k0, T, d_beliefs.transpose(0, 1).contiguous().float(), ctx.buf)
+        ctx.buf = None
+        d_x = None
+        if ctx.needs_input_grad[0]:
+            _check_log(st, win, plan)
+            Kc, mh = win.kmax + 1, plan.max_hop
+            if k0 == 0 and Kc == T:
+                # the node covers the whole window: one evaluation serves dL/dx here and the weight gradients at the root
+                rows = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
+                win.cache = rows
+                d_x = _dx(plan, st, win, 0, T, Kc, rows=(win.P0, rows[2][mh:]))
+            else:
+                d_x = _dx(plan, st, win, k0, k0 + T, Kc)
+            d_x = d_x.transpose(0, 1)
+        return d_x, torch.zeros(1, device=st.device), None, None, None
+
+
+def _chain(plan, state, token, n_steps):
+    win = state.twin
+    if win is None:
+        win = state.twin = _TWindow()
+    cap = state.C - state.N + 1
+    if token is None:
+        win.chain_id += 1
+        win.chain_start = state.steps
+        win.P0 = state.host_count
+        win.kmax, win.dz2, win.cache = -1, None, None
+        anchor = torch.zeros(1, device=state.device, requires_grad=True)
+        token = _TRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
+    k = state.steps - win.chain_start
+    if k + n_steps > cap:
+        raise RuntimeError(
+            f"more than {cap} recorded steps on one hidden state; raise "
+            "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+    return token, k
+
+
+def _room(plan, state, token, n_steps, bptt_capacity):
+    """A state without spare log rows is re-homed before the first recorded step (chain start only)."""
+    from gcm import fused
+    if state.C - state.N + 1 < n_steps or state.C - state.N < 1:
+        if token is not None:
+            raise RuntimeError(
+                f"more than {state.C - state.N + 1} recorded steps on one hidden state; raise "
+                "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+        state = fused.grow_state(state, state.N + max(int(bptt_capacity), n_steps, 1))
+    return state
+
+
+def step_grad(plan, state, x, token, bptt_capacity):
+    """Recording step.  Returns (belief, token, state) -- the state may have been re-homed."""
+    state.fast_ok = False
+    state = _room(plan, state, token, 1, bptt_capacity)
+    token, k = _chain(plan, state, token, 1)
+    belief, token = _TStepFn.apply(x, token, plan, state, k)
+    token._gcm_tw = True
+    return belief, token, state
+
+
+def sequence_grad(plan, state, x_seq, token, bptt_capacity):
+    """Recording sequence entry.  Returns (beliefs [B, T, H2], token, state)."""
+    state.fast_ok = False
+    T = x_seq.shape[1]
+    state = _room(plan, state, token, T, bptt_capacity)
+    token, k0 = _chain(plan, state, token, T)
+    beliefs, token = _TSeqFn.apply(x_seq, token, plan, state, k0)
+    token._gcm_tw = True
+    return beliefs, token, state

@@ -205,6 +205,23 @@ int gcm_dense_step_bwd(const gcm_dense_state* st, int steps_back, const gcm_gnn*
                        const float* d_belief, float* d_nodes, float* d_obs,
                        const gcm_gnn_grads* grads, void* stream);
 
+/* ---- window-level backward of forward-only TemporalBackedge chains (csrc/gcm_temporal_bwd.cu) ----------------
+ * Autograd through gcm.py:262-321 over the T steps of a BPTT window (reference training loop: tests/test_gcm.py:412-439)
+ * for a state built from empty by a chain of forward hops (edge_selectors/temporal.py:72-88): every product of the
+ * backward is a row-parallel GEMM over TIME-MAJOR rows [row, graph, feature] (row <-> absolute node position p; edge
+ * p-s -> p exists iff p - s >= 0), run by gcm_linear_tc32 / gcm_outer_reduce_tc32; these two entries build the operands.
+ * gcm_temporal_gather: out[i, b, :] = [ sum_{s in hops, p-s >= 0} x_{p-s} | x_p ] (2F floats), p = p0 + i, from the node
+ * log (rows with p < 0 are zero).  The caller guarantees that positions p0 - max_hop .. p0 + n_rows - 1 are still in
+ * the log (count - C <= p0 - max_hop) and already written (p0 + n_rows <= count).  F % 4 == 0.
+ * gcm_temporal_shift_sum: out[i, b, :] = [ sum_s src[pos + sign * s] | src[pos] ] (2H floats), pos = out_pos0 + i, with
+ * src [n_src, B, H] holding positions src_pos0 .. src_pos0 + n_src - 1 (anything outside is zero); positions below
+ * valid_lo are nodes that never existed: they contribute nothing and their own output rows are zero.  sign = -1: sums
+ * over in-neighbours (layer inputs), +1: over out-neighbours (gradients).  H % 4 == 0. */
+int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hops, int n_hops, long long p0, int n_rows, float* out,
+                        void* stream);
+int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo, const int32_t* hops,
+                           int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H, void* stream);
+
 /* ring/log + bitmasks -> the reference's hidden-state tensors (gcm.py:194-211 layout).
  * Any of nodes_out / adj_out / num_nodes_out may be NULL. */
 int gcm_state_materialize(const gcm_dense_state* st, float* nodes_out, float* adj_out,

@@ -1,0 +1,167 @@
+"""GPU tier: window-level backward of forward-only TemporalBackedge chains (gcm.temporal, csrc/gcm_temporal_bwd.cu)
+against the fp64 oracle's autograd (the reference's BPTT, tests/test_gcm.py:412-439): gradients of the six GNN weight
+tensors and of every observation, per-step recording, sequence recording and mixtures, windows that wrap, truncated
+BPTT over several windows with weight updates in between.  Tolerance: BASELINE.json's 1e-5 relative on top of the fp32
+oracle's own distance from fp64."""
+import pytest
+import torch
+
+import gcm_oracle as oracle
+from helpers import make_dense_gnn, make_selector, named_grads, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _oracle_grads(obs, w, p, spec, N, hidden=None):
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        o = obs.to(dt).clone().requires_grad_(True)
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in p.items()}
+        hid = None if hidden is None else tuple(h.to(dt) if h.is_floating_point() else h for h in hidden[dt])
+        outs, hid = oracle.dense_gcm_rollout(o, hid, spec, pp, ("tanh", "tanh"), graph_size=N)
+        (outs * w.to(dt)).sum().backward()
+        res[dt] = (o.grad, {k: v.grad for k, v in pp.items()}, outs.detach(), tuple(h.detach() for h in hid))
+    return res
+
+
+@pytest.mark.parametrize("mode", ["step", "seq", "mixed"])
+@pytest.mark.parametrize("x_grad", [True, False])
+@pytest.mark.parametrize("B,N,F,T,hops", [(9, 16, 32, 24, (1, 2, 4)), (5, 128, 32, 40, (1, 2, 4)), (7, 12, 8, 30, (1,)),
+                                          (3, 20, 16, 26, (1, 3))])
+def test_temporal_window_backward_matches_fp64_oracle(mode, x_grad, B, N, F, T, hops):
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(100 + N + F)
+    obs = torch.randn(T, B, F, generator=gen) * 0.5
+    w = torch.randn(T, B, 32, generator=gen)
+    p = oracle.make_params(F, 32)
+    res = _oracle_grads(obs, w, p, spec, N)
+    gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    x = obs.to(dev).requires_grad_(x_grad)
+    xb = x.transpose(0, 1)                       # [B, T, F] view for the sequence entry
+    hidden = None
+    if mode == "step":
+        outs = []
+        for t in range(T):
+            o, hidden = mod(x[t], hidden)
+            outs.append(o)
+        outs = torch.stack(outs)
+    elif mode == "seq":
+        outs, hidden = mod.forward_sequence(xb, hidden)
+        outs = outs.transpose(0, 1)
+    else:
+        a, hidden = mod.forward_sequence(xb[:, :7], hidden)
+        b, hidden = mod(x[7], hidden)
+        c, hidden = mod.forward_sequence(xb[:, 8:], hidden)
+        outs = torch.cat([a.transpose(0, 1), b.unsqueeze(0), c.transpose(0, 1)])
+    assert getattr(hidden.token, "_gcm_tw", False), "the window-level backward should have been recorded"
+    ref64, ref32 = res[torch.float64], res[torch.float32]
+    assert rel_err(outs, ref64[2]) < TOL + rel_err(ref32[2], ref64[2])
+    (outs * w.to(dev)).sum().backward()
+    if x_grad:
+        assert rel_err(x.grad, ref64[0]) < TOL + rel_err(ref32[0], ref64[0])
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], ref64[1][k]) < TOL + rel_err(ref32[1][k], ref64[1][k]), k
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(adj.cpu(), ref32[3][1]) and torch.equal(num_nodes.cpu(), ref32[3][3])
+    assert torch.equal(nodes.detach().cpu(), ref32[3][0])
+
+
+def test_truncated_bptt_over_windows_with_weight_updates():
+    """A running rollout trained window by window (m_t.detach(), SGD step in between): fill without autograd, then three
+    windows; every window's gradients against the fp64 oracle doing the same."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, T, hops = 6, 16, 32, 10, (1, 2, 4)
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(9)
+    fill = torch.randn(N + 3, B, F, generator=gen) * 0.5
+    p = oracle.make_params(F, 32)
+    gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    mod.bptt_capacity = T
+    opt = torch.optim.SGD(mod.parameters(), lr=0.05)
+    with torch.no_grad():
+        _, hidden = mod.forward_sequence(fill.to(dev).transpose(0, 1), None)
+        o_hid = {}
+        for dt in (torch.float64, torch.float32):
+            _, o_hid[dt] = oracle.dense_gcm_rollout(fill.to(dt), None, spec, {k: v.to(dt) for k, v in p.items()},
+                                                    ("tanh", "tanh"), graph_size=N)
+    for wi in range(3):
+        obs = torch.randn(T, B, F, generator=gen) * 0.5
+        w = torch.randn(T, B, 32, generator=gen)
+        res = _oracle_grads(obs, w, p, spec, N, hidden=o_hid)
+        opt.zero_grad(set_to_none=True)
+        hidden = hidden.detach()
+        if wi == 1:
+            outs = []
+            for t in range(T):
+                o, hidden = mod(obs[t].to(dev), hidden)
+                outs.append(o)
+            outs = torch.stack(outs)
+        else:
+            outs, hidden = mod.forward_sequence(obs.to(dev).transpose(0, 1), hidden)
+            outs = outs.transpose(0, 1)
+        assert getattr(hidden.token, "_gcm_tw", False)
+        (outs * w.to(dev)).sum().backward()
+        ref64, ref32 = res[torch.float64], res[torch.float32]
+        assert rel_err(outs, ref64[2]) < TOL + rel_err(ref32[2], ref64[2]), wi
+        got = named_grads(convs)
+        for k in got:
+            assert rel_err(got[k], ref64[1][k]) < TOL + rel_err(ref32[1][k], ref64[1][k]), (wi, k)
+        opt.step()
+        # the oracle takes the same SGD step (with ITS fp64 gradients) and carries its own hidden state on
+        p = {k: (v.double() - 0.05 * ref64[1][k]).float() for k, v in p.items()}
+        with torch.no_grad():
+            for k, v in named_params(convs).items():
+                v.copy_(p[k])
+        o_hid = {dt: res[dt][3] for dt in res}
+    nodes, adj, _, num_nodes = hidden
+    assert torch.equal(adj.cpu(), o_hid[torch.float32][1]) and torch.equal(nodes.detach().cpu(), o_hid[torch.float32][0])
+
+
+def named_params(convs):
+    return {"w_rel1": convs[0].lin_rel.weight, "b1": convs[0].lin_rel.bias, "w_root1": convs[0].lin_root.weight,
+            "w_rel2": convs[1].lin_rel.weight, "b2": convs[1].lin_rel.bias, "w_root2": convs[1].lin_root.weight}
+
+
+def test_window_capacity_error_and_unused_beliefs():
+    """More recorded steps than the log keeps -> the documented RuntimeError; steps whose belief does not reach the loss
+    deliver nothing and cost nothing."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, T = 4, 16, 32, 12
+    spec = [("temporal", (1, 2), "forward")]
+    p = oracle.make_params(F, 32)
+    gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    mod.bptt_capacity = 8
+    gen = torch.Generator().manual_seed(1)
+    obs = torch.randn(T, B, F, generator=gen) * 0.5
+    hidden = None
+    outs = []
+    with pytest.raises(RuntimeError, match="recorded steps"):
+        for t in range(T):
+            o, hidden = mod(obs[t].to(dev), hidden)
+            outs.append(o)
+    # only step 5's belief is used
+    o = obs.clone().requires_grad_(True)
+    pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ref, _ = oracle.dense_gcm_rollout(o[:8], None, spec, pp, ("tanh", "tanh"), graph_size=N)
+    ref[5].sum().backward()
+    mod.zero_grad(set_to_none=True)
+    hidden, outs = None, []
+    for t in range(8):
+        b, hidden = mod(obs[t].to(dev), hidden)
+        outs.append(b)
+    outs[5].sum().backward()
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], pp[k].grad) < 5 * TOL, k
