@@ -836,7 +836,7 @@ extern "C" int gcm_set_temporal_kernel(int which) {
 static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
                          int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
                          int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
-                         void* stream_);
+                         void* stream_, int n_steps = 1, long long obs_stride_t = 0, long long belief_stride_t = 0);
 
 extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                                   int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
@@ -863,10 +863,12 @@ extern "C" int gcm_dense_step_fwd_ex(const gcm_dense_state* st, const float* obs
                        (flags & GCM_STEP_UNIFORM_COUNT) ? uniform_count : -1, hcache, hc_ring, cache_written, stream_);
 }
 
+// n_steps > 1: that many consecutive steps in ONE launch of the cached-row kernel (step k at obs + k * obs_stride_t /
+// belief + k * belief_stride_t); any other kernel choice returns GCM_ERR_UNSUPPORTED without launching.
 static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
                          int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
                          int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
-                         void* stream_) {
+                         void* stream_, int n_steps, long long obs_stride_t, long long belief_stride_t) {
   if (cache_written) *cache_written = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = validate_state(st)) return rc;
@@ -896,7 +898,7 @@ static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long 
   if (obs_ld <= 0) obs_ld = st->F;
   if (belief_ld <= 0) belief_ld = gnn->H2;
   // only the cached-row kernel takes strided observation / belief rows (the sequence entry's [B, T, .] views)
-  const bool strided = obs_ld != st->F || belief_ld != gnn->H2;
+  const bool strided = obs_ld != st->F || belief_ld != gnn->H2 || n_steps > 1;
   GCM_REQUIRE(!(flags & GCM_STEP_UNIFORM_COUNT) || uniform_count >= 0, "dense_step_fwd: negative uniform count");
 
   if ((flags & GCM_STEP_PURE_TEMPORAL) && gnn->H1 == 32 && gnn->H2 == 32 &&
@@ -922,6 +924,9 @@ static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long 
         wa.uniform_count = (flags & GCM_STEP_UNIFORM_COUNT) ? uniform_count : -1;
         wa.obs_ld = obs_ld;
         wa.belief_ld = belief_ld;
+        wa.n_steps = n_steps;
+        wa.obs_stride_t = obs_stride_t;
+        wa.belief_stride_t = belief_stride_t;
         wa.hcache = hcache;
         wa.hc_ring = hc_ring;
         wa.weights_stable = (flags & GCM_STEP_WEIGHTS_STABLE) ? 1 : 0;
@@ -1030,7 +1035,8 @@ extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long
   if (belief_ld <= 0) belief_ld = H2;
   const bool strided = obs_ld != F || belief_ld != H2;
   const long long l0 = gcm_launch_count();
-  for (int k = 0; k < T; ++k) {
+  static const bool no_multi = getenv("GCM_B200_NO_MULTISTEP") != nullptr;     // A/B switch: one launch per step
+  for (int k = 0; k < T;) {
     const float* ob = obs + (long long)k * obs_stride_t;
     float* be = belief + (long long)k * belief_stride_t;
     int flags = GCM_STEP_PURE_TEMPORAL;
@@ -1039,8 +1045,23 @@ extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long
     if (r->hcache && r->hc_fresh >= need) flags |= GCM_STEP_HCACHE_VALID;
     if (r->weights_stable && r->hc_fresh >= 1) flags |= GCM_STEP_WEIGHTS_STABLE;
     int written = 0;
-    int rc = step_fwd_impl(&r->st, ob, obs_ld, r->sels, r->n_sels, &r->gnn, be, belief_ld, r->status, flags,
-                           r->uniform_count, r->hcache, r->hc_ring, &written, stream_);
+    int rc;
+    if ((flags & GCM_STEP_HCACHE_VALID) && r->hc_fresh >= r->max_hop && T - k > 1 && !no_multi) {
+      // every remaining step runs on the cached-row kernel (the weights cannot change inside this call): ONE launch
+      // walks all of them, consecutive steps overlapping inside the kernel (csrc/gcm_dense_fwd_hc.cu)
+      rc = step_fwd_impl(&r->st, ob, obs_ld, r->sels, r->n_sels, &r->gnn, be, belief_ld, r->status, flags,
+                         r->uniform_count, r->hcache, r->hc_ring, &written, stream_, T - k, obs_stride_t,
+                         belief_stride_t);
+      if (rc == GCM_OK && written) {
+        if (r->uniform_count >= 0) r->uniform_count += T - k;
+        r->weights_stable = 1;
+        k = T;
+        continue;
+      }
+      if (rc != GCM_ERR_UNSUPPORTED) return rc ? rc : GCM_ERR_INVALID;
+    }
+    rc = step_fwd_impl(&r->st, ob, obs_ld, r->sels, r->n_sels, &r->gnn, be, belief_ld, r->status, flags,
+                       r->uniform_count, r->hcache, r->hc_ring, &written, stream_);
     if (rc == GCM_ERR_UNSUPPORTED && strided) {
       // a step the cached-row kernel cannot take (cache being filled, shape): contiguous copies of the rows
       GCM_REQUIRE(r->scratch_obs && r->scratch_belief, "dense_rollout_fwd: strided rows need the scratch buffers");
@@ -1057,6 +1078,7 @@ extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long
     }
     if (r->uniform_count >= 0) ++r->uniform_count;
     r->weights_stable = 1;   // nothing but this loop touches the stream between the steps of one call
+    ++k;
   }
   r->launches = gcm_launch_count() - l0;
   return GCM_OK;

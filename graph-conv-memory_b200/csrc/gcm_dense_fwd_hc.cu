@@ -47,13 +47,14 @@ constexpr uint32_t HC_COL_A1HI = 0, HC_COL_A1LO = 64, HC_COL_D1 = 128, HC_COL_SH
 constexpr int HC_BAR_A1 = 1, HC_BAR_A2 = 3, HC_BAR_W = 5;   // named barriers (A1/A2: + group)
 
 struct HcSmem {   // byte offsets into dynamic shared memory
-  uint32_t b1hi, b1lo, b2hi, b2lo, zero, bias, bars, tmem_slot, stage, total;
+  uint32_t b1hi, b1lo, b2hi, b2lo, zero, bias, bars, tmem_slot, flags, stage, total;
   uint32_t gs_floats;   // per-graph stride inside a stage
   uint32_t slot_bytes;
   int ns;               // quarter-tile stages in the ring
 };
 
-__host__ __device__ inline HcSmem hc_smem_layout(int F, int np) {
+// nflags: quarter tiles per CTA (multi-step launches keep one "steps completed" word per quarter tile)
+__host__ __device__ inline HcSmem hc_smem_layout(int F, int np, int nflags) {
   HcSmem L;
   const uint32_t K1 = 2 * F;
   uint32_t o = 0;
@@ -65,6 +66,7 @@ __host__ __device__ inline HcSmem hc_smem_layout(int F, int np) {
   L.bias = o; o += 2 * HC_H * 4;
   L.bars = o; o += (2 * HC_MAXSTAGES + 2 * HC_GROUPS) * 8;
   L.tmem_slot = o; o += 16;
+  L.flags = o; o += (uint32_t)(nflags > HC_MAXSTAGES ? nflags : HC_MAXSTAGES) * 4;
   o = (o + 127u) & ~127u;
   // [np node rows | np cached h rows | observation] + 4 floats so that the 16-byte stride is odd (no bank
   // conflicts when the 32 lanes of a warp read the same column of their own graphs)
@@ -112,8 +114,12 @@ __device__ __forceinline__ void hc_cta_stamp(int which) {
   }
 }
 #define HC_CTA_STAMP(w) hc_cta_stamp(w)
+#ifndef HC_TRACE_FROM
+#define HC_TRACE_FROM 0
+#endif
 __device__ __forceinline__ void hc_stamp(int warp, int it, int phase) {
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it < 8) {
+  it -= HC_TRACE_FROM;
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && it >= 0 && it < 8) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_hc_trace[warp][it][phase] = t;
@@ -159,7 +165,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
   constexpr int CPR = F / 4;                 // 16-byte chunks per node row
   const int np = a.prog.n_past;
   extern __shared__ __align__(128) unsigned char sm[];
-  const HcSmem L = hc_smem_layout(F, np);
+  // this CTA's contiguous range of quarter tiles; every CTA walks the same padded sequence of nqp quarter slots per step
+  const int nq_total = (a.st.B + HC_Q - 1) / HC_Q;
+  const int nq_max = (nq_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const HcSmem L = hc_smem_layout(F, np, nq_max);
   float* B1hi = reinterpret_cast<float*>(sm + L.b1hi);
   float* B1lo = reinterpret_cast<float*>(sm + L.b1lo);
   float* B2hi = reinterpret_cast<float*>(sm + L.b2hi);
@@ -168,6 +177,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
   float* bias_s = reinterpret_cast<float*>(sm + L.bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.tmem_slot);
+  int* done_step = reinterpret_cast<int*>(sm + L.flags);        // [quarter tile of this CTA] steps completed so far
   float* stages = reinterpret_cast<float*>(sm + L.stage);
   uint64_t* full = bars;                         // [slot]
   uint64_t* empty = bars + HC_MAXSTAGES;         // [slot]
@@ -180,12 +190,18 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
   const int gs = (int)L.gs_floats, NS = L.ns;
   const int R = a.hc_ring;                       // power of two
   const bool uni = a.uniform_count >= 0;
-  // this CTA's contiguous range of quarter tiles
-  const int nq_total = (B + HC_Q - 1) / HC_Q;
   const int q_begin = (int)(((long long)nq_total * blockIdx.x) / gridDim.x);
   const int q_end = (int)(((long long)nq_total * (blockIdx.x + 1)) / gridDim.x);
   const int nq = q_end - q_begin;
-  const int my_tiles = (nq + (L.ns >> 1) - 1) / (L.ns >> 1);
+  // The work of a launch is ONE sequence of quarter slots: S = t * nqp + s (step t, quarter tile s of this CTA; slots
+  // s >= nq are bubbles).  Stage = S % NS, so over the steps of a sequence call every builder warp gets the same
+  // share of quarter tiles (a single step leaves ceil(nq / builders) rounds to some warps and one less to others),
+  // and consecutive steps overlap: there is no ramp / drain between them.  nqp >= NS keeps step t + 1 of a quarter
+  // tile out of the MMA tile that holds its step t.
+  const int T = a.n_steps > 1 ? a.n_steps : 1;
+  const int nqp = nq_max > NS ? nq_max : NS;
+  const int total = T * nqp;
+  const int my_tiles = (total + (L.ns >> 1) - 1) / (L.ns >> 1);
 
   HC_CTA_STAMP(0);
   pdl_launch_dependents();
@@ -201,6 +217,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
     tc::mbar_fence_init();
   }
   if (tid < 32) zero_row[tid] = 0.0f;
+  for (int i = tid; i < (nq_max > HC_MAXSTAGES ? nq_max : HC_MAXSTAGES); i += HC_THREADS) done_step[i] = 0;
   if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
@@ -216,17 +233,28 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
     const int nprod = (NS % 3 == 0) ? 3 : 4;
     pdl_wait();                                  // the state and the observations come from earlier kernels
     const int xch = np * CPR, hch = np * 8, tch = xch + hch + CPR;    // 16-byte chunks per graph
-    for (int s = p; s < nq && p < nprod; s += nprod) {
-      const int slot = s % NS, use = s / NS;
+    for (int S = p; S < total && p < nprod; S += nprod) {
+      const int slot = S % NS, use = S / NS;
+      const int t = S / nqp, s = S - t * nqp;
       const int g0 = (q_begin + s) * HC_Q;
-      const int gt = min(HC_Q, B - g0);
+      const int gt = s < nq ? min(HC_Q, B - g0) : 0;          // 0: a bubble (nothing to fetch, the stage still cycles)
       float* st_base = stages + (size_t)slot * HC_Q * gs;
+      const float* obs_t = a.obs + (long long)t * a.obs_stride_t;
+      HC_STAMP(S / nprod, 0);
+      HC_WAIT(empty + slot, (use & 1) ^ 1, 100 + S);
+      if (t > 0 && gt > 0) {
+        // rows and counters of step t were written by the builder warp that ran step t - 1 of this quarter tile
+        if (lane == 0) {
+          volatile int* f = done_step + s;
+          while (*f < t) {}
+          __threadfence();
+        }
+        __syncwarp();
+      }
       int cnt_l = 0;
-      if (uni) cnt_l = a.uniform_count;
+      if (uni) cnt_l = a.uniform_count + t;
       else if (lane < gt) cnt_l = __ldcg(a.st.count + g0 + lane);
-      HC_STAMP(s / nprod, 0);
-      HC_WAIT(empty + slot, (use & 1) ^ 1, 100 + s);
-      HC_STAMP(s / nprod, 1);
+      HC_STAMP(S / nprod, 1);
       for (int c0 = 0; c0 < tch; c0 += 32) {
         const int c = c0 + lane;
         // decode the chunk: which row of which array, and its offset inside the per-graph stage
@@ -251,7 +279,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
             src = a.hcache + ((size_t)g0 * R + ((cnt - hop) & (R - 1))) * HC_H + col * 4;
             stride = (size_t)R * HC_H;
           } else if (kind == 2) {
-            src = a.obs + (size_t)g0 * a.obs_ld + col * 4;
+            src = obs_t + (size_t)g0 * a.obs_ld + col * 4;
             stride = (size_t)a.obs_ld;
           }
           if (src) {
@@ -269,13 +297,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
             else if (kind == 1 && hop <= lt)
               src = a.hcache + ((size_t)(g0 + gi) * R + ((cnt - hop) & (R - 1))) * HC_H + col * 4;
             else if (kind == 2)
-              src = a.obs + (size_t)(g0 + gi) * a.obs_ld + col * 4;
+              src = obs_t + (size_t)(g0 + gi) * a.obs_ld + col * 4;
             if (src) hc_cp16(st_base + (size_t)gi * gs + dst_off, src);
           }
         }
       }
       hc_cp_arrive(full + slot);
-      HC_STAMP(s / nprod, 2);
+      HC_STAMP(S / nprod, 2);
     }
   } else {
     // =============================== consumers ===============================
@@ -342,23 +370,26 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
     int it = 0;
     for (int j = grp; j < my_tiles; j += HC_GROUPS, ++it) {
       const uint32_t ph = it & 1;
-      const int s = QPG * j + q;               // quarter sequence number; slot = grp * QPG + q, use = it
-      const bool has = builder && s < nq;
-      const int slot = s % NS, use = s / NS;
+      const int S = QPG * j + q;               // position in the launch's sequence; slot = grp * QPG + q, use = it
+      const bool has = builder && S < total;
+      const int slot = S % NS, use = S / NS;
+      const int t = has ? S / nqp : 0, s = has ? S - t * nqp : 0;
       const int g0 = (q_begin + s) * HC_Q;
-      const int gt = has ? min(HC_Q, B - g0) : 0;
+      const int gt = (has && s < nq) ? min(HC_Q, B - g0) : 0;
       const bool live = lane < gt;
-      int cnt = 0;
-      if (uni) cnt = a.uniform_count;
-      else if (live) cnt = __ldcg(a.st.count + g0 + lane);
-      const int lt = min(cnt, N - 1);
       float* st_base = stages + (size_t)slot * HC_Q * gs;
       const float* mine = st_base + (size_t)lane * gs;
+      const float* obs_t = a.obs + (long long)t * a.obs_stride_t;
+      int cnt = 0, lt = 0;
 
       if (has) {
         HC_STAMP(it, 0);
-        HC_WAIT(full + slot, use & 1, 200 + s);
+        HC_WAIT(full + slot, use & 1, 200 + S);
         HC_STAMP(it, 1);
+        // (after the wait: in a multi-step launch the counter was written by the previous step's builder warp)
+        if (uni) cnt = a.uniform_count + t;
+        else if (live) cnt = __ldcg(a.st.count + g0 + lane);
+        lt = min(cnt, N - 1);
         const float* xp[HC_MAXP];
         const float* hp[HC_MAXP];
 #pragma unroll
@@ -407,6 +438,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           }
           hc_store_split16(taddr + HC_COL_SHI + c0, taddr + HC_COL_SLO + c0, v);
         }
+        // node write (gcm.py:274) straight from the stage's observation tile, before the stage is released: 32 / CPR
+        // graphs per instruction, 128-bit coalesced stores (re-reading the tile from global after the release put an
+        // L2 round trip of ~1 us on every tile's critical path, tools/hc_trace_seq.py)
+        if (gt > 0) {
+          const int tslot_w = gcm_slot(cnt, C);
+#pragma unroll
+          for (int i = 0; i < CPR; ++i) {
+            const int gi = i * (32 / CPR) + lane / CPR, col = lane % CPR;
+            const int ts = __shfl_sync(GCM_FULL_MASK, tslot_w, gi);
+            if (gi < gt) {
+              const float4 v = *reinterpret_cast<const float4*>(st_base + (size_t)gi * gs + np * F + np * HC_H + col * 4);
+              *reinterpret_cast<float4*>(a.st.nodes + ((size_t)(g0 + gi) * C + ts) * F + col * 4) = v;
+            }
+          }
+        }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(empty + slot);        // everything was read: the stage can be refilled
         tc::wait_st();
@@ -436,19 +482,8 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       }
 
       // ---- state update of this warp's quarter while the tensor core works ----
-      if (has) {
+      if (gt > 0) {
         const int tslot = gcm_slot(cnt, C);
-        // node write (gcm.py:274): the stage is already released, so the observation tile (contiguous, L2-hot)
-        // is read again: 32 / CPR graphs per instruction, 128-bit coalesced loads and stores
-#pragma unroll
-        for (int i = 0; i < CPR; ++i) {
-          const int gi = i * (32 / CPR) + lane / CPR, col = lane % CPR;
-          const int ts = __shfl_sync(GCM_FULL_MASK, tslot, gi);
-          if (gi < gt) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs + (size_t)(g0 + gi) * a.obs_ld + col * 4));
-            *reinterpret_cast<float4*>(a.st.nodes + ((size_t)(g0 + gi) * C + ts) * F + col * 4) = v;
-          }
-        }
         if (live) {
           // adjacency row of the new node: past mask, cleared future mask (contiguous 2W words per graph)
           uint32_t* mrow = a.st.masks + ((size_t)(g0 + lane) * C + tslot) * 2 * W;
@@ -514,6 +549,14 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       }
       tc::wait_st();
       }
+      if (T > 1 && gt > 0) {
+        // this quarter tile's node rows, cached rows and counters of step t are written: step t + 1 may fetch them
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          *reinterpret_cast<volatile int*>(done_step + s) = t + 1;
+        }
+      }
       tc::fence_before_sync();
       if (!issuer) {
         hc_bar_arrive(HC_BAR_A2 + grp, 128);
@@ -562,7 +605,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           bool bad = false;
 #pragma unroll
           for (int k = 0; k < 16; ++k) bad |= !isfinite(o0[k]) | !isfinite(o1[k]);
-          float4* dst = reinterpret_cast<float4*>(a.belief + (size_t)(g0 + lane) * a.belief_ld);
+          float4* dst = reinterpret_cast<float4*>(a.belief + (long long)t * a.belief_stride_t + (size_t)(g0 + lane) * a.belief_ld);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             dst[k] = make_float4(o0[4 * k], o0[4 * k + 1], o0[4 * k + 2], o0[4 * k + 3]);
@@ -586,8 +629,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
 
 template <int F>
 static int launch_hc(const TemporalWinArgs& a, cudaStream_t stream) {
-  const HcSmem L = hc_smem_layout(F, a.prog.n_past);
+  const int nq = (a.st.B + HC_Q - 1) / HC_Q;
+  int grid = gcm_num_sms();
+  if (grid > nq) grid = nq;
+  const int nq_max = (nq + grid - 1) / grid;
+  const HcSmem L = hc_smem_layout(F, a.prog.n_past, nq_max);
   if (L.ns < 6) return GCM_ERR_UNSUPPORTED;
+  if ((long long)(a.n_steps > 1 ? a.n_steps : 1) * (nq_max > L.ns ? nq_max : L.ns) >= (1ll << 30)) return GCM_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_step_temporal_hc<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -598,9 +646,6 @@ static int launch_hc(const TemporalWinArgs& a, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const int nq = (a.st.B + HC_Q - 1) / HC_Q;
-  int grid = gcm_num_sms();
-  if (grid > nq) grid = nq;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(HC_THREADS);

@@ -43,6 +43,10 @@ struct TemporalWinArgs {
   int weights_stable; // GCM_STEP_WEIGHTS_STABLE: the weights were not written since the previous step of this state
   long long obs_ld;    // floats between the observation rows of consecutive graphs (F when contiguous); hc kernel only
   long long belief_ld; // floats between consecutive belief rows (H2 when contiguous); hc kernel only
+  // hc kernel only: n_steps consecutive steps in ONE launch (the sequence entry); step k reads obs + k * obs_stride_t,
+  // writes belief + k * belief_stride_t and sees uniform_count + k.  0 or 1 = a single step.
+  int n_steps;
+  long long obs_stride_t, belief_stride_t;
 };
 
 

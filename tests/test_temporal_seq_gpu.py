@@ -67,8 +67,8 @@ def test_temporal_sequence_equals_step_loop(B, N, F, hops, chunks):
                 assert rel_err(o, ref) < TOL, (ci, t)
             assert torch.equal(out_seq, torch.stack(outs, dim=1)), (ci, n)
             if ci >= 2 and n >= 2:
-                # warm state: one launch per step, every one the cached-row kernel, no staging copies
-                assert launched == n, (launched, n)
+                # warm state: every step on the cached-row kernel (one launch walks consecutive steps), no staging copies
+                assert 1 <= launched <= n, (launched, n)
                 assert lib.gcm_last_kernel().decode() == "k_step_temporal_hc"
             t0 += n
         for a, b in zip(h_seq, h_loop):
