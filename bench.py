@@ -444,20 +444,20 @@ def run_rollout(ctx, workload, B, K, W, args):
     hidden = None
     with torch.no_grad():
         if seq:
-            def xs(n, off=0):                            # [B, n, F]: step k of the call reads observation (off + k) % n_obs
-                return torch.stack([obs_steps[(off + k) % n_obs] for k in range(n)], dim=1).contiguous()
+            def xs(n, off=0):                            # [n, B, F]: step k of the call reads observation (off + k) % n_obs
+                return torch.stack([obs_steps[(off + k) % n_obs] for k in range(n)], dim=0).contiguous()
 
             if fill:
-                _, hidden = mod.forward_sequence(xs(fill), hidden)
+                _, hidden = mod.forward_sequence(xs(fill), hidden, time_major=True)
             progress(f"{workload}: filled")
             x_warm, x_seq = xs(max(W, 2), fill), xs(K, fill + W)
-            _, hidden = mod.forward_sequence(x_warm, hidden)
-            _, hidden = mod.forward_sequence(x_seq, hidden)           # same call shape as the timed one (allocator warm)
+            _, hidden = mod.forward_sequence(x_warm, hidden, time_major=True)
+            _, hidden = mod.forward_sequence(x_seq, hidden, time_major=True)   # same call shape as the timed one
             ctx.barrier()
             t_lo = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            beliefs, hidden = mod.forward_sequence(x_seq, hidden)
+            beliefs, hidden = mod.forward_sequence(x_seq, hidden, time_major=True)
             e1.record()
             ctx.barrier()
             total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
@@ -465,7 +465,7 @@ def run_rollout(ctx, workload, B, K, W, args):
             n_l0 = lib.gcm_launch_count()
             torch.cuda._sleep(int(1.0e7))
             e0.record()
-            beliefs, hidden = mod.forward_sequence(x_seq, hidden)
+            beliefs, hidden = mod.forward_sequence(x_seq, hidden, time_major=True)
             e1.record()
             torch.cuda.synchronize()
             kern_ms = e0.elapsed_time(e1) / K
@@ -563,7 +563,8 @@ def run_rollout(ctx, workload, B, K, W, args):
         "t_lo": t_lo, "t_hi": t_hi, "extra": None,
         "state": ("in-place node log + bit-packed adjacency; steady state: graphs full before the warm-up "
                   f"({fill} untimed fill steps + {W} warm-up steps), the oldest node is dropped every step"),
-        "timed_call": (f"ONE DenseGCM.forward_sequence(x[B,{K},F], m_t) call (C rollout entry, {K} kernel launches)"
+        "timed_call": (f"ONE DenseGCM.forward_sequence(x[{K},B,F], m_t, time_major=True) call: the C rollout entry walks "
+                       f"the {K} steps in {launches} launch(es) of the step kernel"
                        if seq else f"{K} DenseGCM.forward calls"),
         "e2e": {"value": B * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
                 "d2h_bytes_per_step": B * H * 4, "ms_per_step": e2e_ms / K,
@@ -592,19 +593,19 @@ def run_bptt(ctx, workload, B, K, W, args):
     obs_host = ((1.0 if temporal else 0.5) * torch.randn(T, B, F, generator=gen)).pin_memory()
     obs_dev = obs_host.to(dev)
     obs_stage = torch.empty_like(obs_dev)
-    seq = workload == "cfg3-seq" or temporal
+    seq = workload == "cfg3-seq"
     obs_bt = obs_dev.transpose(0, 1).contiguous() if seq else None         # [B, T, F] for the sequence entry
     loss_host = torch.empty(1).pin_memory()
     if temporal:
         # truncated BPTT on a running rollout: fill the graphs without autograd, then one window per optimiser step
         with torch.no_grad():
-            _, carry = mod.forward_sequence(torch.randn(B, N + 8, F, device=dev), None)
+            _, carry = mod.forward_sequence(torch.randn(N + 8, B, F, device=dev), None, time_major=True)
         carry = [carry]
 
         def window(obs, obs_seq):
             opt.zero_grad(set_to_none=True)
             hidden = carry[0].detach()
-            beliefs, hidden = mod.forward_sequence(obs_seq, hidden)
+            beliefs, hidden = mod.forward_sequence(obs, hidden, time_major=True)
             loss = beliefs.mean()
             loss.backward()
             gdist.allreduce_grads(mod.parameters(), average=True)
@@ -678,10 +679,10 @@ def run_bptt(ctx, workload, B, K, W, args):
         # the forward step kernel, timed alone on a no-grad sequence call
         with torch.no_grad():
             hid = carry[0].detach()
-            _, hid = mod.forward_sequence(obs_bt, hid)
+            _, hid = mod.forward_sequence(obs_dev, hid, time_major=True)
             torch.cuda._sleep(int(1.0e7))
             e0.record()
-            _, hid = mod.forward_sequence(obs_bt, hid)
+            _, hid = mod.forward_sequence(obs_dev, hid, time_major=True)
             e1.record()
             torch.cuda.synchronize()
             carry[0] = hid

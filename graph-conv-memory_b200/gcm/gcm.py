@@ -335,11 +335,22 @@ class DenseGCM(torch.nn.Module):
                 belief = feats[torch.arange(B, device=x.device), num_nodes - 1]
         return belief, DenseHidden(state, token)
 
-    def forward_sequence(self, x_seq, hidden):
+    def forward_sequence(self, x_seq, hidden, time_major: bool = False):
         """T steps at once: x_seq [B, T, F] -> (beliefs [B, T, H], hidden).  Same results as
         `for t in range(T): belief_t, hidden = self(x_seq[:, t], hidden)` (the loop of RayDenseGCM.forward,
         reference ray_gcm.py:200-202), which is also what runs for configurations without a fused sequence kernel.
-        DenseEdge-only states take the T steps in five launches (gcm.ones: the per-node cache is read once)."""
+        Forward-only TemporalBackedge chains take the T steps in ONE C call (gcm.temporal: the step kernels are enqueued
+        from C, consecutive cached-row steps in a single multi-step launch); DenseEdge-only states in five launches
+        (gcm.ones: the per-node cache is read once).
+        time_major=True: x_seq is [T, B, F] and the beliefs come back as [T, B, H] (every step's rows contiguous, like
+        torch.nn.RNN's batch_first=False)."""
+        if time_major:
+            assert x_seq.dim() == 3, "x_seq must be [T, B, obs_size]"
+            beliefs, hidden = self._forward_sequence(x_seq.transpose(0, 1), hidden, True)
+            return beliefs.transpose(0, 1), hidden
+        return self._forward_sequence(x_seq, hidden, False)
+
+    def _forward_sequence(self, x_seq, hidden, tm_out):
         assert x_seq.dim() == 3, "x_seq must be [B, T, obs_size]"
         T = x_seq.shape[1]
 
@@ -354,7 +365,7 @@ class DenseGCM(torch.nn.Module):
         if plan is None or T < 2 or not x_seq.is_cuda or x_seq.dtype != torch.float32:
             return loop(hidden)
         if plan.temporal_key is not None and plan.hc_ring:
-            return self._sequence_temporal(plan, x_seq, hidden, loop)
+            return self._sequence_temporal(plan, x_seq, hidden, loop, tm_out)
         if not plan.ones or plan.pre:
             # (a DenseEdge state behind a preprocessor keeps two logs; its sequence kernels only know one)
             return loop(hidden)
@@ -391,7 +402,7 @@ class DenseGCM(torch.nn.Module):
             token = None
         return torch.cat([out0.unsqueeze(1), beliefs.transpose(0, 1)], dim=1), DenseHidden(state, token)
 
-    def _sequence_temporal(self, plan, x_seq, hidden, loop):
+    def _sequence_temporal(self, plan, x_seq, hidden, loop, tm_out=False):
         """forward_sequence for forward-only TemporalBackedge chains (with or without a row-wise preprocessor): the T
         steps are enqueued by ONE C call (gcm.temporal.sequence_nograd -> gcm_dense_rollout_fwd), which reads x_seq
         [B, T, F] and writes the [B, T, H] result in place.  Anything that records autograd, and any state that is not a
@@ -453,7 +464,10 @@ class DenseGCM(torch.nn.Module):
                     out, hidden = self(x_seq[:, t], hidden)
                     outs.append(out)
                 return torch.stack(outs, dim=1), hidden
-            beliefs = torch.empty(state.B, T, plan.gnn.H2, device=x_seq.device, dtype=torch.float32)
+            if tm_out:      # the caller wants [T, B, H]: every step's belief rows contiguous
+                beliefs = torch.empty(T, state.B, plan.gnn.H2, device=x_seq.device, dtype=torch.float32).transpose(0, 1)
+            else:
+                beliefs = torch.empty(state.B, T, plan.gnn.H2, device=x_seq.device, dtype=torch.float32)
             if out0 is not None:
                 beliefs[:, 0] = out0
             if not DenseGCM.did_warn and state.host_count is not None and state.host_count + (T - start) > state.N:

@@ -76,6 +76,11 @@ def test_temporal_sequence_equals_step_loop(B, N, F, hops, chunks):
         nodes, adj, _, num_nodes = h_seq
         assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
         assert torch.equal(num_nodes.cpu(), o_hidden[3])
+        # time-major layout: [T, B, F] in, [T, B, H] out, same numbers
+        xt = obs[:, :6].transpose(0, 1).contiguous()
+        o_tm, h_seq = m_seq.forward_sequence(xt, h_seq, time_major=True)
+        o_bm, h_loop = m_loop.forward_sequence(obs[:, :6], h_loop)
+        assert o_tm.shape == (6, B, 32) and o_tm.is_contiguous() and torch.equal(o_tm.transpose(0, 1), o_bm)
         # the handle returned by a sequence call feeds the per-step fast path and the other way round
         o1, h_seq = m_seq(obs[:, 0].contiguous(), h_seq)
         o2, h_loop = m_loop(obs[:, 0].contiguous(), h_loop)

@@ -13,15 +13,15 @@ mod = bench.build_dense(dev, N, F, H, [("temporal", (1, 2, 4), "forward")])
 mod.bptt_capacity = T
 opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
 gen = torch.Generator().manual_seed(1003)
-obs_bt = torch.randn(B, T, F, generator=gen).to(dev)
+obs_tb = torch.randn(T, B, F, generator=gen).to(dev)
 with torch.no_grad():
-    _, carry = mod.forward_sequence(torch.randn(B, N + 8, F, device=dev), None)
+    _, carry = mod.forward_sequence(torch.randn(N + 8, B, F, device=dev), None, time_major=True)
 carry = [carry]
 
 
 def window():
     opt.zero_grad(set_to_none=True)
-    beliefs, hidden = mod.forward_sequence(obs_bt, carry[0].detach())
+    beliefs, hidden = mod.forward_sequence(obs_tb, carry[0].detach(), time_major=True)
     beliefs.mean().backward()
     opt.step()
     carry[0] = hidden
