@@ -220,8 +220,26 @@ def _lin(a, w, bias=None, act=0, out=None):
 
 
 def _outer(a, x, dw, db):
+    """dw += a^T x, db += column sums of a, for NARROW operands (a [rows, 32], x [rows, 16..64]).
+    gcm_outer_reduce_tc32 maps channels to threads (128 per group), so a 32 x 64 product would leave most of its threads
+    idle; viewing s consecutive rows as one (x as [rows / s, s * Hx] in the kernel's wide A role, a as [rows / s, s * Ha])
+    makes it a 128 x (s * Ha) product whose s diagonal [Hx, Ha] blocks sum to (a^T x)^T -- same bytes read, s^2 / s of
+    the MMA work wasted on the off-diagonal blocks, all threads loading."""
     from gcm import ones
-    if x.shape[1] % 16 == 0:
+    rows, ha = a.shape
+    hx = x.shape[1]
+    s = min(128 // hx, 128 // ha)
+    while s > 1 and rows % s:
+        s //= 2
+    if s > 1 and hx % 16 == 0 and (s * ha) % 16 == 0 and a.is_contiguous() and x.is_contiguous():
+        tmp = torch.zeros(s * hx, s * ha, device=a.device, dtype=torch.float32)
+        ones._outer_tc32(x.view(rows // s, s * hx), a.view(rows // s, s * ha), tmp, None)
+        acc = tmp[:hx, :ha]
+        for i in range(1, s):
+            acc = acc + tmp[i * hx:(i + 1) * hx, i * ha:(i + 1) * ha]
+        dw += acc.t()
+        db += a.sum(0)
+    elif hx % 16 == 0:
         ones._outer_tc32(a, x, dw, db)
     else:
         ones._outer(a, x, dw, db)
