@@ -62,6 +62,10 @@ SEEDED = [
     (2, 256, 128, 128, 12, [("dense",)]),                              # BASELINE cfg 3 shape (fp32 path)
     (6, 96, 64, 64, 100, [("cosine", 0.5)]),                           # BASELINE cfg 4 shape, reduced N
     (6, 96, 64, 64, 100, [("euclidean", 2.0)]),
+    # B >= 128: the cross-batch mean distance runs on the tensor cores (k_euclid_tc, gcm/fused.py: euclid_batchmean);
+    # edge set -> belief end to end through DenseGCM, window wraps, threshold margin asserted below
+    (256, 24, 32, 32, 40, [("euclidean", 2.0)]),
+    (384, 20, 64, 64, 30, [("euclidean", 2.0)]),
     (4, 70, 12, 16, 80, [("spatial", 1.0, slice(0, 2), None)]),
     (3, 1024, 8, 8, 5, [("temporal", (1, 512), "forward")]),           # maximum graph_size
     (2, 20, 256, 256, 4, [("dense",)]),                                # maximum feature width
@@ -88,6 +92,18 @@ def test_fused_matches_oracle_seeded(B, N, F, H, T, spec):
     mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
     hidden, o_hidden, o64 = None, None, None
     p64 = {k: v.double() for k, v in p.items()}
+    tc_euclid = bool(spec) and spec[0][0] == "euclidean" and B >= 128
+    seen = set()
+    if tc_euclid:
+        # spy on the library call that computes the distances: the tensor-core entry must be the one that runs
+        from gcm import _cabi, fused
+        assert fused.EUCLID_TC and F % 16 == 0 and F <= 64
+        real = _cabi.lib().gcm_euclid_batchmean_tc
+
+        def spy(*a):
+            seen.add("tc")
+            return real(*a)
+        _cabi.lib().gcm_euclid_batchmean_tc = spy
     with torch.no_grad():
         for t in range(T):
             belief, hidden = mod(obs[t].to(dev), hidden)
@@ -96,6 +112,9 @@ def test_fused_matches_oracle_seeded(B, N, F, H, T, spec):
             # 1e-5 relative to the reference, budgeted against fp64: the fp32
             # reference's own rounding distance from the exact result is not charged to the kernel
             assert rel_err(belief, ref64) < TOL + rel_err(ref, ref64), (t, rel_err(belief, ref))
+    if tc_euclid:
+        _cabi.lib().gcm_euclid_batchmean_tc = real
+        assert seen == {"tc"}, "the tensor-core distance kernel should have served this batch size"
     if distance:
         # the edge set depends on a float comparison: the inputs must keep a margin
         kind = spec[0][0]

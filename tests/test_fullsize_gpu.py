@@ -55,6 +55,55 @@ def test_cfg2_full_size_rollout_matches_oracle_on_probe_graphs():
     assert torch.equal(num_nodes[idx].cpu(), o_hidden[3]) and int(num_nodes.min()) == N
 
 
+def test_cfg2_full_size_bptt_window_gradients_of_probe_graphs_match_fp64_oracle():
+    """cfg2 chain at full size (65536 graphs, N=128, F=H=32, hops 1/2/4): the graphs are filled by a no-grad sequence
+    call (136 steps, wrapping), then a BPTT window of T=64 is recorded through forward_sequence (multi-step cached-row
+    kernel forward, window-level backward of gcm.temporal).  The loss only looks at probe graphs, so the full-batch
+    weight gradients and dL/dobs must equal the fp64 oracle's autograd on those graphs alone (1e-5 relative, budgeted
+    against the fp32 oracle's own distance from fp64)."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T, T0 = 65536, 128, 32, 32, 64, 136
+    spec = [("temporal", (1, 2, 4), "forward")]
+    acts = ("tanh", "tanh")
+    p = oracle.make_params(F, H)
+    gen = torch.Generator(device=dev).manual_seed(1005)
+    fill = torch.randn(T0, B, F, device=dev, generator=gen) * 0.5
+    obs = (torch.randn(T, B, F, device=dev, generator=gen) * 0.5).requires_grad_(True)
+    probe = _probe(B)
+    w = torch.zeros(T, B, H, device=dev)
+    w[:, probe] = torch.randn(T, len(probe), H, device=dev, generator=gen)
+    gnn, convs = make_dense_gnn(F, H, p, acts)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    mod.bptt_capacity = T
+    with torch.no_grad():
+        _, hidden = mod.forward_sequence(fill, None, time_major=True)
+    beliefs, hidden = mod.forward_sequence(obs, hidden.detach(), time_major=True)
+    assert getattr(hidden.token, "_gcm_tw", False)
+    (beliefs * w).sum().backward()
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in p.items()}
+        with torch.no_grad():
+            _, hid = oracle.dense_gcm_rollout(fill[:, probe].to(dt).cpu(), None, spec, {k: v.detach() for k, v in pp.items()},
+                                              acts, graph_size=N)
+        o = obs[:, probe].detach().to(dt).cpu().requires_grad_(True)
+        ref, _ = oracle.dense_gcm_rollout(o, hid, spec, pp, acts, graph_size=N)
+        (ref * w[:, probe].to(dt).cpu()).sum().backward()
+        res[dt] = (ref.detach(), o.grad, {k: v.grad for k, v in pp.items()})
+    r64, r32 = res[torch.float64], res[torch.float32]
+    assert rel_err(beliefs[:, probe], r64[0]) < TOL + rel_err(r32[0], r64[0])
+    assert rel_err(obs.grad[:, probe], r64[1]) < TOL + rel_err(r32[1], r64[1])
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], r64[2][k]) < TOL + rel_err(r32[2][k], r64[2][k]), (k, rel_err(got[k], r64[2][k]))
+        assert float(got[k].abs().max()) > 0
+    rest = torch.ones(B, dtype=torch.bool, device=dev)
+    rest[probe] = False
+    assert float(obs.grad[:, rest].abs().max()) == 0.0
+
+
 def test_cfg3_full_size_bptt_window_probe_graphs_and_gradient_additivity():
     """cfg3: DenseEdge N=256 F=H=128, 16384 graphs, BPTT over T=64 from a state pre-filled with 192 nodes, bfloat16
     per-node cache (2e-2): beliefs of probe graphs against the fp64 oracle, and the six weight gradients of the full
@@ -103,6 +152,56 @@ def test_cfg3_full_size_bptt_window_probe_graphs_and_gradient_additivity():
                                                                     torch.zeros(0, dtype=torch.float64), nn0[probe].cpu()),
                                       spec, {k: v.double() for k, v in p.items()}, acts, graph_size=N)
     assert rel_err(outs[:, probe], ref) < 2e-2
+
+
+def test_cfg3_full_size_bf16_gradients_of_probe_graphs_match_fp64_oracle():
+    """cfg3 at full size (16384 graphs, N=256, F=H=128, T=64, bfloat16 per-node cache): the loss only looks at the beliefs
+    of a few probe graphs, so the six weight gradients and dL/dobs of the FULL-batch run (every kernel of the window at
+    its full grid; the other graphs contribute exact zeros) must equal the fp64 oracle's autograd on those graphs alone
+    -- within BASELINE.json's 2e-2 for the bf16 configuration."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T = 16384, 256, 128, 128, 64
+    spec = [("dense",)]
+    acts = ("tanh", "tanh")
+    p = oracle.make_params(F, H)
+    gen = torch.Generator(device=dev).manual_seed(1004)
+    obs = (0.5 * torch.randn(T, B, F, device=dev, generator=gen)).requires_grad_(True)
+    nodes0 = 0.5 * torch.randn(B, N, F, device=dev, generator=gen)
+    nodes0[:, N - T:] = 0
+    nn0 = torch.full((B,), N - T, dtype=torch.long, device=dev)
+    probe = [0, 127, 128, B // 2, B - 1]
+    w = torch.zeros(T, B, H, device=dev)
+    w[:, probe] = torch.randn(T, len(probe), H, device=dev, generator=gen)
+    gnn, convs = make_dense_gnn(F, H, p, acts)
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    mod.bptt_capacity = T
+    mod.compute_dtype = torch.bfloat16
+    adj0 = torch.zeros(B, N, N, device=dev)
+    adj0[:, : N - T, : N - T] = 1
+    hidden = (nodes0, adj0, torch.zeros(0, device=dev), nn0)
+    outs = []
+    for t in range(T):
+        belief, hidden = mod(obs[t], hidden)
+        outs.append(belief)
+    (torch.stack(outs) * w).sum().backward()
+    # fp64 oracle on the probe graphs alone
+    o = obs[:, probe].detach().double().cpu().requires_grad_(True)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in p.items()}
+    a0 = torch.zeros(len(probe), N, N, dtype=torch.float64)
+    a0[:, : N - T, : N - T] = 1
+    ref, _ = oracle.dense_gcm_rollout(o, (nodes0[probe].double().cpu(), a0, torch.zeros(0, dtype=torch.float64),
+                                          nn0[probe].cpu()), spec, pp, acts, graph_size=N)
+    (ref * w[:, probe].double().cpu()).sum().backward()
+    got = named_grads(convs)
+    for k in got:
+        assert rel_err(got[k], pp[k].grad) < 2e-2, (k, rel_err(got[k], pp[k].grad))
+        assert float(got[k].abs().max()) > 0
+    assert rel_err(obs.grad[:, probe], o.grad) < 2e-2
+    rest = torch.ones(B, dtype=torch.bool, device=dev)
+    rest[probe] = False
+    assert float(obs.grad[:, rest].abs().max()) == 0.0          # graphs are independent: no gradient leaks across them
 
 
 def test_cfg4_full_size_cosine_rollout_matches_oracle_on_probe_graphs():
