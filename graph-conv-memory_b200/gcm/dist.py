@@ -46,17 +46,31 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, average: b
     return flat.numel()
 
 
-def gather_current_obs(x: torch.Tensor, group=None) -> torch.Tensor:
-    """All ranks' current observations [sum_r B_r, F] (EuclideanEdge under batch sharding)."""
+def gather_current_obs(x: torch.Tensor, group=None, sizes=None) -> torch.Tensor:
+    """All ranks' current observations [sum_r B_r, F] in batch order (EuclideanEdge under batch sharding).
+    sizes: the per-rank batch sizes when the caller already knows them (DenseGCM caches them: a rollout's shards do not
+    change size), which spares the size exchange and its host sync; equal shards take a single all_gather into one
+    buffer."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return x
     world = dist.get_world_size(group)
-    sizes = [torch.zeros(1, dtype=torch.long, device=x.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([x.shape[0]], dtype=torch.long, device=x.device), group=group)
-    sizes = [int(s) for s in sizes]
+    if sizes is None:
+        sizes = shard_sizes(x.shape[0], x.device, group)
+    if len(set(sizes)) == 1:
+        out = x.new_empty(world * x.shape[0], x.shape[1])
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out
     cap = max(sizes)                                   # all_gather needs equal shapes: pad, then trim
     mine = x.new_zeros(cap, x.shape[1])
     mine[: x.shape[0]] = x
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+def shard_sizes(local_batch: int, device, group=None):
+    """Every rank's local batch size (one small all_gather + host read; callers cache the result)."""
+    world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.long, device=device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([local_batch], dtype=torch.long, device=device), group=group)
+    return [int(s) for s in sizes]

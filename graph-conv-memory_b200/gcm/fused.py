@@ -427,9 +427,43 @@ def fused_step_nograd(plan: FusedPlan, state: DenseState, x: torch.Tensor) -> to
     return belief
 
 
+def _validate_structure(plan: FusedPlan, module, device) -> bool:
+    """Does `module.gnn(x, adj, weights, B, N)` compute the plain two-layer DenseGraphConv stack the fused kernels
+    implement?  Checked on a SYNTHETIC state: a few nodes with a random 0/1 adjacency (self loops, asymmetric), every row
+    compared -- a user forward() that transposes, normalises or masks the adjacency differs here, whereas the first live
+    step of a rollout has one node and no edges and would let it through."""
+    g = plan.gnn
+    gen = torch.Generator().manual_seed(20240229)
+    nb, n = 2, 6
+    x = torch.randn(nb, n, g.F, generator=gen).to(device)
+    adj = (torch.rand(nb, n, n, generator=gen) < 0.4).float().to(device)
+    act = {"tanh": torch.tanh, "relu": torch.relu, "none": lambda t: t}
+    with torch.no_grad():
+        def bias(conv):
+            b = 0
+            for lin in (conv.lin_rel, conv.lin_root):
+                if lin.bias is not None:
+                    b = b + lin.bias
+            return b
+        h = act[g.act1]((adj @ x) @ g.conv1.lin_rel.weight.t() + x @ g.conv1.lin_root.weight.t() + bias(g.conv1))
+        want = act[g.act2]((adj @ h) @ g.conv2.lin_rel.weight.t() + h @ g.conv2.lin_root.weight.t() + bias(g.conv2))
+        try:
+            got = module.gnn(x, adj, torch.zeros(0, device=device), nb, n)
+        except Exception:
+            return False
+    return (isinstance(got, torch.Tensor) and got.shape == want.shape
+            and torch.allclose(got.float(), want, rtol=1e-4, atol=1e-5))
+
+
 def validate_plan(plan: FusedPlan, module, state: DenseState, belief: torch.Tensor) -> bool:
-    """One-time check that the matched structure computes what the user's GNN module computes:
-    run the module itself on the materialised state of a few graphs and compare beliefs."""
+    """One-time check that the matched structure computes what the user's GNN module computes: the module itself on a
+    synthetic state with edges (_validate_structure), then on the materialised live state of a few graphs against the
+    belief the kernels just produced."""
+    if not _validate_structure(plan, module, state.device):
+        warnings.warn(
+            "gcm: the GNN looked like a 2-layer DenseGraphConv stack but does not compute one; "
+            "falling back to the generic (unfused) path for this module")
+        return False
     nb = min(state.B, 8)
     state.sync_masks()
     nodes = torch.empty(nb, state.N, state.F, device=state.device)
@@ -544,6 +578,19 @@ class _StepFn(torch.autograd.Function):
         return (d_obs, torch.zeros(1, device=dev) if ctx.has_token else None, None, None, *out)
 
 
+_warned_truncated = [False]
+
+
+def warn_truncated(cap: int) -> None:
+    if not _warned_truncated[0]:
+        _warned_truncated[0] = True
+        warnings.warn(
+            f"gcm: more than {cap} steps were recorded on one hidden state; the autograd history is cut here (as if "
+            "m_t.detach() had been called) and recording continues.  backward() through the earlier steps will raise; "
+            "pass a larger bptt_capacity to DenseGCM, detach per BPTT window, or run rollouts under torch.no_grad(). "
+            "Will not warn again")
+
+
 def grow_state(state: DenseState, capacity: int) -> DenseState:
     """Re-home a state in a log with more spare rows (needed before gradients can be recorded on a
     state that was built without spare capacity)."""
@@ -569,9 +616,14 @@ def fused_step_grad(plan: FusedPlan, state: DenseState, x: torch.Tensor, token, 
         token = _RootFn.apply(anchor, state)
         state.chain_start = state.steps
     elif state.steps + 1 - getattr(state, "chain_start", 0) > state.C - state.N + 1:
-        raise RuntimeError(
-            f"more than {state.C - state.N + 1} recorded steps on one hidden state; raise "
-            "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+        # The log keeps C - N spare rows: older steps can no longer be recomputed.  The reference records arbitrarily
+        # long grad-mode rollouts (an eval loop without torch.no_grad() is legal there), so the forward keeps going on
+        # a fresh chain; a backward() that reaches the steps left behind raises ("BPTT window too long for the node
+        # log"), it never returns wrong gradients.
+        warn_truncated(state.C - state.N + 1)
+        anchor = torch.zeros(1, device=state.device, requires_grad=True)
+        token = _RootFn.apply(anchor, state)
+        state.chain_start = state.steps
     belief, token = _StepFn.apply(x, token, plan, state, *plan.gnn.params())
     return belief, token, state
 

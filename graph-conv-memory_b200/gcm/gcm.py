@@ -123,7 +123,10 @@ class DenseGCM(torch.nn.Module):
         pooled: bool = False,
         positional_encoder: torch.nn.Module = None,
         edge_weights: bool = False,
+        bptt_capacity: int = 128,
     ):
+        """Arguments and defaults as the reference's (gcm.py:156-182).  bptt_capacity (extension, keyword only in
+        practice): the longest BPTT window, in steps, whose backward the fused paths can recompute from the node log."""
         super().__init__()
         self.preprocessor = preprocessor
         self.gnn = gnn
@@ -137,10 +140,17 @@ class DenseGCM(torch.nn.Module):
         self._plan_built = False
         # extra log rows kept while autograd is recording, so that a BPTT window of up to this many
         # steps can be recomputed in backward without any per-step saved activations
-        self.bptt_capacity = 128
+        self.bptt_capacity = int(bptt_capacity)
         # None (float32 everywhere, 1e-5 parity) or torch.bfloat16: DenseEdge-only states keep their per-node cache in
         # bfloat16 (BASELINE cfg3's precision, 2e-2 parity); torch.autocast("cuda", dtype=torch.bfloat16) does the same
         self.compute_dtype = None
+        # Batch sharding (one process per GPU, every rank owns a slice of the graphs): the hot path needs no exchange
+        # EXCEPT for EuclideanEdge, whose distance averages over the current observation of every graph of the batch
+        # (reference edge_selectors/distance.py:48-49).  Set batch_group to the torch.distributed group the batch is
+        # sharded over (True = the default group) and every step all-gathers the ranks' observations first, so that
+        # sharded results equal the unsharded reference's.  None: this process holds the whole batch.
+        self.batch_group = None
+        self._shard_sizes = None
 
     # ------------------------------------------------------------------ reference API
     def get_initial_hidden_state(self, x):
@@ -300,6 +310,8 @@ class DenseGCM(torch.nn.Module):
             DenseGCM.did_warn = True
 
         xc = x.contiguous()
+        if plan.needs_euclid:
+            state.__dict__["_euclid_cur_all"] = self._all_current_obs(xc)
         if plan.ones and state.dense_ok and not ingest_grad and (token is None or getattr(token, "_gcm_ones", False)):
             # DenseEdge-only state: implicit all-ones adjacency, per-node cache (gcm.ones)
             if recording:
@@ -479,6 +491,20 @@ class DenseGCM(torch.nn.Module):
                     state.raw_ref(), rest_raw.data_ptr(), rest_raw.stride(0), rest_raw.stride(1), T - start,
                     _cabi.stream_ptr(x_seq.device)), "gcm_state_log_write_seq")
             return beliefs, DenseHidden(state, None)
+
+    def _all_current_obs(self, x):
+        """EuclideanEdge under batch sharding: the current observations of EVERY rank's graphs, in batch order (None when
+        this process holds the whole batch)."""
+        if self.batch_group is None:
+            return None
+        import torch.distributed as tdist
+        from gcm import dist as gdist
+        if not tdist.is_initialized():
+            return None
+        group = None if self.batch_group is True else self.batch_group
+        if self._shard_sizes is None or self._shard_sizes[0] != x.shape[0]:
+            self._shard_sizes = (x.shape[0], gdist.shard_sizes(x.shape[0], x.device, group))
+        return gdist.gather_current_obs(x.detach(), group, self._shard_sizes[1])
 
     def _would_overflow(self, state: DenseState) -> bool:
         # host-side mirror only (no device sync): graphs started empty overflow after N steps

@@ -560,9 +560,15 @@ def _chain(plan, state, token, n_steps):
         token = _OnesRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
     k = state.steps - win.chain_start
     if k + n_steps > cap:
-        raise RuntimeError(
-            f"more than {cap} recorded steps on one hidden state; raise "
-            "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+        if n_steps > cap:
+            raise RuntimeError(
+                f"a sequence of {n_steps} recorded steps does not fit the node log ({cap} steps); raise "
+                "DenseGCM.bptt_capacity")
+        # the log cannot keep more recorded steps: the forward goes on on a fresh chain (see gcm.fused.warn_truncated);
+        # backward() through the steps left behind raises
+        from gcm import fused
+        fused.warn_truncated(cap)
+        return _chain(plan, state, None, n_steps)
     win.ensure_fwd(k + n_steps - 1, cap)
     return token, k
 

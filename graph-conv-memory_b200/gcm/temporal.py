@@ -435,28 +435,33 @@ def _chain(plan, state, token, n_steps):
         token = _TRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
     k = state.steps - win.chain_start
     if k + n_steps > cap:
-        raise RuntimeError(
-            f"more than {cap} recorded steps on one hidden state; raise "
-            "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+        if n_steps > cap:
+            raise RuntimeError(
+                f"a sequence of {n_steps} recorded steps does not fit the node log ({cap} steps); raise "
+                "DenseGCM.bptt_capacity")
+        # the log cannot keep more recorded steps: the forward goes on on a fresh chain (see gcm.fused.warn_truncated);
+        # backward() through the steps left behind raises
+        from gcm import fused
+        fused.warn_truncated(cap)
+        return _chain(plan, state, None, n_steps)
     return token, k
 
 
 def _room(plan, state, token, n_steps, bptt_capacity):
-    """A state without spare log rows is re-homed before the first recorded step (chain start only)."""
+    """A state without enough spare log rows is re-homed (-> a new chain) before the recorded step(s)."""
     from gcm import fused
     if state.C - state.N + 1 < n_steps or state.C - state.N < 1:
         if token is not None:
-            raise RuntimeError(
-                f"more than {state.C - state.N + 1} recorded steps on one hidden state; raise "
-                "DenseGCM.bptt_capacity or cut the graph with m_t.detach()")
+            fused.warn_truncated(state.C - state.N + 1)
         state = fused.grow_state(state, state.N + max(int(bptt_capacity), n_steps, 1))
-    return state
+        token = None                  # a re-homed log starts a new chain
+    return state, token
 
 
 def step_grad(plan, state, x, token, bptt_capacity):
     """Recording step.  Returns (belief, token, state) -- the state may have been re-homed."""
     state.fast_ok = False
-    state = _room(plan, state, token, 1, bptt_capacity)
+    state, token = _room(plan, state, token, 1, bptt_capacity)
     token, k = _chain(plan, state, token, 1)
     belief, token = _TStepFn.apply(x, token, plan, state, k)
     token._gcm_tw = True
@@ -467,7 +472,7 @@ def sequence_grad(plan, state, x_seq, token, bptt_capacity):
     """Recording sequence entry.  Returns (beliefs [B, T, H2], token, state)."""
     state.fast_ok = False
     T = x_seq.shape[1]
-    state = _room(plan, state, token, T, bptt_capacity)
+    state, token = _room(plan, state, token, T, bptt_capacity)
     token, k0 = _chain(plan, state, token, T)
     beliefs, token = _TSeqFn.apply(x_seq, token, plan, state, k0)
     token._gcm_tw = True

@@ -407,3 +407,45 @@ def test_preprocessor_path_matches_reference_golden(name):
     nodes, adj, _, num_nodes = hidden
     assert torch.equal(nodes.cpu(), g["final"][0]) and torch.equal(adj.cpu(), g["final"][1].float())
     assert torch.equal(num_nodes.cpu(), g["final"][3])
+
+
+def test_user_gnn_with_a_different_forward_is_not_fused():
+    """A user module whose children look like the README GNN (two DenseGraphConv + one activation) but whose forward()
+    uses the adjacency differently (here: transposed) must NOT be replaced by the fused two-layer formula: the one-time
+    validation runs the module on a synthetic state WITH edges (the first live step of a rollout has none), the plan is
+    dropped with a warning and every step goes through the module itself."""
+    import warnings
+
+    from gcm.gcm import DenseGCM
+    from gcm.nn import DenseGraphConv
+
+    dev = torch.device("cuda:0")
+    F, H, N, B, T = 8, 16, 10, 3, 14
+
+    class Odd(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gc0 = DenseGraphConv(F, H)
+            self.gc1 = DenseGraphConv(H, H)
+            self.act = torch.nn.Tanh()
+
+        def forward(self, x, adj, weights, B, N):
+            x = self.act(self.gc0(x, adj.transpose(1, 2)))
+            return self.act(self.gc1(x, adj.transpose(1, 2)))
+
+    torch.manual_seed(3)
+    gnn = Odd().to(dev)
+    mod = DenseGCM(gnn, edge_selectors=make_selector([("temporal", (1, 2), "forward")]), graph_size=N)
+    assert mod.fused_plan() is not None                       # the structure matches ...
+    gen = torch.Generator().manual_seed(8)
+    obs = torch.randn(T, B, F, generator=gen).to(dev)
+    hidden = None
+    with torch.no_grad(), warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        for t in range(T):
+            belief, hidden = mod(obs[t], hidden)
+            # ... but the semantics are the module's: recompute with torch on the materialised state
+            nodes, adj, _, nn = tuple(hidden)
+            want = gnn(nodes, adj, torch.zeros(0, device=dev), B, N)[torch.arange(B, device=dev), nn - 1]
+            assert rel_err(belief, want) < 1e-5, t
+    assert mod._plan is None and any("does not compute one" in str(w.message) for w in caught)

@@ -28,6 +28,10 @@ def _worker(rank, world, port, q):
         # 2. EuclideanEdge's cross-batch term: every rank sees all current observations, in batch order
         allx = gdist.gather_current_obs(mine)
         assert torch.equal(allx, full)
+        assert gdist.shard_sizes(mine.shape[0], mine.device) == [6, 5]
+        assert torch.equal(gdist.gather_current_obs(mine, None, [6, 5]), full)      # cached sizes: no size exchange
+        even = gdist.shard(full[:10], rank, world)                                   # equal shards: one all_gather_into_tensor
+        assert torch.equal(gdist.gather_current_obs(even, None, [5, 5]), full[:10])
         # 3. one flattened all-reduce of the weight gradients == gradient of the unsharded loss
         lin = torch.nn.Linear(4, 3)
         with torch.no_grad():

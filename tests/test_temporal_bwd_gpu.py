@@ -131,26 +131,39 @@ def named_params(convs):
             "w_rel2": convs[1].lin_rel.weight, "b2": convs[1].lin_rel.bias, "w_root2": convs[1].lin_root.weight}
 
 
-def test_window_capacity_error_and_unused_beliefs():
-    """More recorded steps than the log keeps -> the documented RuntimeError; steps whose belief does not reach the loss
-    deliver nothing and cost nothing."""
+def test_window_capacity_truncation_and_unused_beliefs():
+    """More recorded steps than the log keeps: the forward keeps going (the reference records arbitrarily long grad-mode
+    rollouts; an eval loop without torch.no_grad() is legal) on a fresh chain with a one-time warning, beliefs stay
+    right, and backward() through the steps left behind raises instead of returning wrong gradients.  Steps whose
+    belief does not reach the loss deliver nothing and cost nothing."""
+    import warnings
+
+    from gcm import fused
     from gcm.gcm import DenseGCM
 
     dev = torch.device("cuda:0")
-    B, N, F, T = 4, 16, 32, 12
+    B, N, F, T = 4, 16, 32, 30
     spec = [("temporal", (1, 2), "forward")]
     p = oracle.make_params(F, 32)
     gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
-    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
-    mod.bptt_capacity = 8
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N, bptt_capacity=8)
     gen = torch.Generator().manual_seed(1)
     obs = torch.randn(T, B, F, generator=gen) * 0.5
-    hidden = None
+    hidden, o_hidden = None, None
     outs = []
-    with pytest.raises(RuntimeError, match="recorded steps"):
+    fused._warned_truncated[0] = False
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
         for t in range(T):
             o, hidden = mod(obs[t].to(dev), hidden)
             outs.append(o)
+            ref, o_hidden = oracle.dense_gcm_step(obs[t], o_hidden, spec, p, graph_size=N)
+            assert rel_err(o, ref) < TOL, t
+    assert sum("autograd history is cut" in str(w.message) for w in caught) == 1
+    with pytest.raises(RuntimeError):
+        outs[2].sum().backward()                       # recorded before the cut: its window is gone
+    outs[-1].sum().backward()                          # the current chain still works
+    assert convs[0].lin_rel.weight.grad is not None
     # only step 5's belief is used
     o = obs.clone().requires_grad_(True)
     pp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
