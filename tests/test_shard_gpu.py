@@ -31,7 +31,9 @@ def test_euclidean_shards_with_gathered_observations_equal_the_unsharded_batch()
     spec = [("euclidean", 2.0)]
     gen = torch.Generator().manual_seed(77)
     obs = _clustered(gen, T, B, F)
-    obs[:, B // 2:] += 0.8 * torch.randn(T, 1, F, generator=gen)     # the two halves see different observations
+    # on odd steps the first half's observations sit far away: the batch-mean distance of the second half's nodes then
+    # exceeds the threshold (no edge), while a shard that only saw its own observations would still link them
+    obs[1::2, : B // 2] += 6.0 / F ** 0.5
     p = oracle.make_params(F, H)
     mods = []
     for _ in range(2):
