@@ -121,7 +121,7 @@ class SparseGCM(torch.nn.Module):
             self._plan_built = True
             self._plan = None
             if self.preprocessor is None and self.positional_encoder is None and (
-                    self.max_hops is None or self.max_hops >= 2):
+                    self.max_hops is None or self.max_hops >= 0):
                 g = _match_sparse_gnn(self.gnn)
                 hops: List[int] = []
                 radius = None
@@ -147,6 +147,13 @@ class SparseGCM(torch.nn.Module):
         """Add tau_b observations to every graph b and query the memory for each of them."""
         plan = self.fused_plan()
         if plan is None:
+            return self._forward_generic(x, taus, hidden)
+        small_k = self.max_hops is not None and self.max_hops < 2
+        if small_k and torch.is_grad_enabled() and (
+                x.requires_grad or any(p.requires_grad for p in self.parameters())
+                or (hidden is not None and hidden[0].requires_grad)):
+            # a subgraph SMALLER than the two layers' receptive field changes the result (sparse_gcm.py:182-199); its
+            # masked aggregation has no backward kernel
             return self._forward_generic(x, taus, hidden)
         _cabi.require_cuda(x, "SparseGCM.forward(x)")
         (c1, c2, a1, a2), hops, radius = plan
@@ -198,14 +205,45 @@ class SparseGCM(torch.nn.Module):
             base = offsets[edges[0]]
             csr = sparse_ops.Csr.from_sorted_edges(edges[1] + base, edges[2] + base, n_flat)
 
-        # two GraphConv layers; the second only on the rows that are returned
-        h = sparse_ops.graph_conv_csr(flat, csr, None, c1.lin_rel.weight, _one_bias(c1), c1.lin_root.weight, a1)
+        # two GraphConv layers; the second only on the rows that are returned, the first only on the rows the second
+        # reads: the returned rows and their in-neighbours (the k-hop subgraph of sparse_gcm.py:182-199 for the two
+        # layers' receptive field -- max_hops >= 2 and max_hops = None give the same numbers).  In a
+        # step-wise rollout (tau = 1) that is 1 + in-degree rows per graph instead of all T_b + 1.
         if n_new == n_flat:
             rows = None
         else:
             ob, ok_ = sparse_ops.ragged_arange(taus, n_new)
             rows = (offsets[ob] + T[ob] + ok_).contiguous()
-        mx = sparse_ops.graph_conv_csr(h, csr, rows, c2.lin_rel.weight, _one_bias(c2), c2.lin_root.weight, a2)
+        mask = None
+        if small_k:
+            # max_hops in {0, 1}: only edges whose source is inside the subgraph count, in BOTH layers
+            keep = torch.zeros(n_flat, dtype=torch.bool, device=dev)
+            if rows is None:
+                keep.fill_(True)
+            else:
+                keep[rows] = True
+                if self.max_hops == 1 and new.shape[1]:
+                    keep[offsets[new[0]] + new[2]] = True
+            mask = keep[csr.col].to(torch.float32).contiguous()
+        if rows is None:
+            h = sparse_ops.graph_conv_csr(flat, csr, None, c1.lin_rel.weight, _one_bias(c1), c1.lin_root.weight, a1,
+                                          edge_mask=mask)
+        else:
+            rows1 = rows
+            if new.shape[1] and not (small_k and self.max_hops == 0):
+                rows1 = torch.cat([rows, offsets[new[0]] + new[2]])     # the new nodes' in-neighbours (duplicates possible)
+            recording = torch.is_grad_enabled() and (flat.requires_grad or any(p.requires_grad for p in self.parameters()))
+            if recording:
+                rows1 = torch.unique(rows1)                                # autograd must see every row once
+            h_sub = sparse_ops.graph_conv_csr(flat, csr, rows1.contiguous(), c1.lin_rel.weight, _one_bias(c1),
+                                              c1.lin_root.weight, a1, edge_mask=mask)
+            if recording:
+                h = torch.zeros(n_flat, h_sub.shape[1], device=dev).index_copy(0, rows1, h_sub)
+            else:
+                h = (torch.zeros if small_k else torch.empty)(n_flat, h_sub.shape[1], device=dev)
+                h[rows1] = h_sub                                            # rows nobody reads stay unwritten
+        mx = sparse_ops.graph_conv_csr(h, csr, rows, c2.lin_rel.weight, _one_bias(c2), c2.lin_root.weight, a2,
+                                       edge_mask=mask)
         assert torch.all(torch.isfinite(mx)), "Got NaN in returned memory, try using tanh activation"
 
         if n_new == B * tmax:

@@ -227,7 +227,21 @@ class _GraphConvFn(torch.autograd.Function):
         return d_x, d_w_rel, d_b, d_w_root, None, None, None
 
 
-def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none"):
+def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none", edge_mask=None):
+    """edge_mask float32 [E] in CSR order (0 / 1): the k-hop subgraph restriction of sparse_gcm.py:182-199 (an edge counts
+    only while its source belongs to the subgraph).  Forward only: a masked call must not record autograd."""
+    if edge_mask is not None:
+        assert not (torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, w_rel, bias, w_root)))
+        x = x.contiguous()
+        m = x.shape[0] if rows is None else rows.numel()
+        out = torch.empty(m, w_rel.shape[0], device=x.device)
+        wt = _kmajor(w_rel, w_root)
+        b = None if bias is None else bias.detach().contiguous()
+        _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
+            x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), edge_mask.data_ptr(), _cabi.ptr(rows), m, x.shape[1],
+            w_rel.shape[0], wt.data_ptr(), _cabi.ptr(b), _cabi.ACT[act], None, out.data_ptr(),
+            _cabi.stream_ptr(x.device)), "gcm_sparse_graphconv_fwd")
+        return out
     return _GraphConvFn.apply(x, w_rel, bias, w_root, csr, rows, _cabi.ACT[act])
 
 

@@ -119,10 +119,25 @@ def unflatten_adj(edges, weights, batch_idx, T, taus, B, max_edges):
 
 
 def pack_hidden(hidden, B, max_edges: int, edge_fill: int = -1, weight_fill: float = 1.0):
-    """COO adjacency -> fixed-size [B, 2, max_edges] edge list for RLlib (reference util.py:323-353)."""
+    """COO adjacency -> fixed-size [B, 2, max_edges] edge list for RLlib (reference util.py:323-353).  CUDA tensors: one
+    kernel (gcm_pack_edges, csrc/gcm_pack.cu); CPU tensors: the same thing with torch indexing (helper API, not the hot
+    path)."""
     nodes, adj, T = hidden
     adj = adj.coalesce()
     idx, val = adj.indices(), adj.values()
+    if adj.is_cuda:
+        from gcm import _cabi
+        dense_edges = torch.empty((B, 2, max_edges), device=adj.device, dtype=torch.long)
+        dense_weights = torch.empty((B, 1, max_edges), device=adj.device, dtype=torch.float)
+        counts = torch.empty(B, device=adj.device, dtype=torch.int32)
+        idx_c, val_c = idx.contiguous(), val.to(torch.float32).contiguous()
+        _cabi.check(_cabi.lib().gcm_pack_edges(idx_c.data_ptr(), val_c.data_ptr(), idx_c.shape[1], B, max_edges,
+                                               int(edge_fill), float(weight_fill), dense_edges.data_ptr(),
+                                               dense_weights.data_ptr(), counts.data_ptr(),
+                                               _cabi.stream_ptr(adj.device)), "gcm_pack_edges")
+        most = int(counts.max()) if B else 0
+        assert most < max_edges or idx_c.shape[1] == 0, f"Cannot pack {most} edges into {max_edges}, increase max edges"
+        return nodes, dense_edges, dense_weights, T
     dense_edges = torch.full((B, 2, max_edges), edge_fill, device=adj.device, dtype=torch.long)
     dense_weights = torch.full((B, 1, max_edges), weight_fill, device=adj.device, dtype=torch.float)
     counts = torch.bincount(idx[0], minlength=B)
@@ -137,8 +152,27 @@ def pack_hidden(hidden, B, max_edges: int, edge_fill: int = -1, weight_fill: flo
 
 
 def unpack_hidden(hidden, B):
-    """Fixed-size edge list -> COO adjacency (reference util.py:355-382)."""
+    """Fixed-size edge list -> COO adjacency (reference util.py:355-382).  CUDA tensors: gcm_count_valid_edges +
+    gcm_unpack_edges (one host read of the edge total, as the reference's nonzero() has)."""
     nodes, edges, weights, T = hidden
+    if edges.is_cuda:
+        from gcm import _cabi
+        lib = _cabi.lib()
+        stream = _cabi.stream_ptr(edges.device)
+        Bn, _, M = edges.shape
+        e_c = edges.to(torch.long).contiguous()
+        w_c = weights.to(torch.float32).contiguous()
+        offsets = torch.zeros(Bn + 1, device=edges.device, dtype=torch.long)
+        _cabi.check(lib.gcm_count_valid_edges(e_c.data_ptr(), Bn, M, offsets[1:].data_ptr(), stream),
+                    "gcm_count_valid_edges")
+        torch.cumsum(offsets[1:], 0, out=offsets[1:])
+        E = int(offsets[-1])
+        coo = torch.empty(3, E, device=edges.device, dtype=torch.long)
+        vals = torch.empty(E, device=edges.device, dtype=torch.float32)
+        _cabi.check(lib.gcm_unpack_edges(e_c.data_ptr(), w_c.data_ptr(), Bn, M, offsets.data_ptr(), E, coo.data_ptr(),
+                                         vals.data_ptr(), stream), "gcm_unpack_edges")
+        adj = torch.sparse_coo_tensor(indices=coo, values=vals, size=(B, nodes.shape[1], nodes.shape[1]))
+        return nodes, adj, T
     batch_idx, edge_idx = (edges[:, 0] >= 0).nonzero().T.unbind()
     adj_idx = torch.stack([batch_idx, edges[batch_idx, 0, edge_idx], edges[batch_idx, 1, edge_idx]])
     adj = torch.sparse_coo_tensor(indices=adj_idx, values=weights[batch_idx, 0, edge_idx],

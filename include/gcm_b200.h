@@ -442,6 +442,20 @@ int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out,
                              float* d_w_root, float* d_b, float* dz_scratch,
                              const float* w_rel_t, const float* w_root_t, float* outer_ws, void* stream);
 
+/* ---- RLlib state wire format of the sparse path (util.py:323-382; RaySparseGCM.forward, ray_sparse_gcm.py:195-213) ----
+ * gcm_pack_edges = util.pack_hidden's adjacency part: coo int64 [3, E] (rows: batch, index 1, index 2) COALESCED (sorted
+ * by batch), vals [E] -> dense_edges int64 [B, 2, max_edges] (rows = coo rows 1 and 2 of the graph's edges in order,
+ * rest = edge_fill) and dense_weights [B, 1, max_edges] (rest = weight_fill); counts int32 [B] = edges per graph (the
+ * caller asserts counts < max_edges like util.py:343-346).
+ * gcm_unpack_edges = util.unpack_hidden's: the slots with dense_edges[b, 0, s] >= 0 (util.py:367) of every graph, in
+ * (graph, slot) order, back to coo [3, E] / vals [E]; offsets int64 [B+1] = exclusive cumsum of the per-graph valid counts
+ * (gcm_count_valid_edges), E = offsets[B]. */
+int gcm_pack_edges(const int64_t* coo, const float* vals, long long E, int B, int max_edges, long long edge_fill,
+                   float weight_fill, int64_t* dense_edges, float* dense_weights, int32_t* counts, void* stream);
+int gcm_count_valid_edges(const int64_t* dense_edges, int B, int max_edges, int64_t* counts, void* stream);
+int gcm_unpack_edges(const int64_t* dense_edges, const float* dense_weights, int B, int max_edges, const int64_t* offsets,
+                     long long E, int64_t* coo, float* vals, void* stream);
+
 /* Self-test of the tcgen05/TMEM building block of the tensor-core step kernels:
  * D[128,N] = A[128,K] B[N,K]^T, passes = 3 (3xTF32, fp32-accurate) or 1 (plain tf32).  Test hook only. */
 int gcm_tc_selftest(const float* A, const float* B, float* D, int K, int N, int passes, void* stream);

@@ -437,3 +437,38 @@ def sparse_gcm_forward(x: Tensor, taus: Tensor, hidden, selectors, params,
         dense[b, :k] = mx[pos: pos + k]
         pos += k
     return dense, (nodes, edges, T + taus)
+
+
+# --------------------------------------------------------------------------- #
+# RLlib state wire format (util.py:323-382)                                    #
+# --------------------------------------------------------------------------- #
+def pack_hidden(hidden, B: int, max_edges: int, edge_fill: int = -1, weight_fill: float = 1.0):
+    """util.py:323-353 -- COO adjacency -> [B, 2, max_edges] edge list + [B, 1, max_edges] weights, one graph at a time:
+    the graph's edges (rows 1 and 2 of the coalesced indices, in coalesced order) first, fill values after."""
+    nodes, adj, T = hidden
+    adj = adj.coalesce()
+    idx, val = adj.indices(), adj.values()
+    dense_edges = torch.full((B, 2, max_edges), edge_fill, dtype=torch.long)
+    dense_weights = torch.full((B, 1, max_edges), weight_fill, dtype=torch.float)
+    for b in range(B):
+        sel = torch.nonzero(idx[0] == b).reshape(-1)
+        assert sel.shape[-1] < max_edges, f"Cannot pack {sel.shape[-1]} edges into {max_edges}, increase max edges"
+        for s, e in enumerate(sel.tolist()):
+            dense_edges[b, 0, s] = idx[1, e]
+            dense_edges[b, 1, s] = idx[2, e]
+            dense_weights[b, 0, s] = val[e]
+    return nodes, dense_edges, dense_weights, T
+
+
+def unpack_hidden(hidden, B: int):
+    """util.py:355-382 -- the slots whose first row is >= 0, in (graph, slot) order, back to a COO adjacency."""
+    nodes, edges, weights, T = hidden
+    bs, i1, i2, vs = [], [], [], []
+    for b in range(edges.shape[0]):
+        for s in range(edges.shape[2]):
+            if int(edges[b, 0, s]) >= 0:
+                bs.append(b); i1.append(int(edges[b, 0, s])); i2.append(int(edges[b, 1, s])); vs.append(float(weights[b, 0, s]))
+    idx = torch.tensor([bs, i1, i2], dtype=torch.long).reshape(3, -1)
+    adj = torch.sparse_coo_tensor(indices=idx, values=torch.tensor(vs, dtype=torch.float),
+                                  size=(B, nodes.shape[1], nodes.shape[1]))
+    return nodes, adj, T

@@ -329,7 +329,51 @@ def main():
                 seed=4, walk=True)
     sparse_case("sparse_temporal12_maxhops2", B=3, N=8, F=3, H=4, calls=[[2, 1, 2], [3, 3, 1], [1, 2, 2]],
                 spec=[("temporal", (1, 2))], seed=5, max_hops=2)
+    # subgraphs smaller than the two layers' receptive field change the numbers (k_hop_subgraph, sparse_gcm.py:182-199)
+    sparse_case("sparse_temporal12_maxhops1", B=3, N=8, F=3, H=4, calls=[[2, 1, 2], [3, 3, 1], [1, 2, 2]],
+                spec=[("temporal", (1, 2))], seed=6, max_hops=1)
+    sparse_case("sparse_temporal12_maxhops0", B=3, N=8, F=3, H=4, calls=[[2, 1, 2], [3, 3, 1], [1, 2, 2]],
+                spec=[("temporal", (1, 2))], seed=7, max_hops=0)
+    sparse_case("sparse_radius_steps_maxhops1", B=2, N=16, F=6, H=5, calls=[[4, 2], [1, 1], [1, 1], [3, 6], [1, 1]],
+                spec=[("temporal", (1,))], aux=[("spatial_radius", slice(0, 2), 0.3)], seed=8, walk=True, max_hops=1)
+    sparse_case("sparse_radius_rollout_maxhops3", B=2, N=16, F=6, H=5, calls=[[1, 1]] * 12,
+                spec=[("temporal", (1,))], aux=[("spatial_radius", slice(0, 2), 0.3)], seed=9, walk=True, max_hops=3)
+
+
+def pack_case(name, B, N, max_edges, seed):
+    """util.pack_hidden / util.unpack_hidden of the UNMODIFIED reference (util.py:323-382) on a random ragged COO
+    adjacency with non-unit weights, one empty graph included; the oracle's restatement is checked on the way."""
+    from gcm import util as ref_util
+
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(B):
+        n_e = 0 if b == 1 else int(torch.randint(1, max_edges - 1, (1,), generator=g))
+        pairs = torch.randperm(N * N, generator=g)[:n_e]
+        rows.append(torch.stack([torch.full((n_e,), b), pairs // N, pairs % N]))
+    idx = torch.cat(rows, dim=1).long()
+    vals = torch.rand(idx.shape[1], generator=g) + 0.5
+    adj = torch.sparse_coo_tensor(idx, vals, size=(B, N, N)).coalesce()
+    nodes = torch.randn(B, N, 3, generator=g)
+    T = torch.randint(0, N, (B,), generator=g)
+    _, edges, weights, _ = ref_util.pack_hidden((nodes, adj, T), B, max_edges)
+    _, adj2, _ = ref_util.unpack_hidden((nodes, edges, weights, T), B)
+    o = oracle.pack_hidden((nodes, adj, T), B, max_edges)
+    assert torch.equal(o[1], edges) and torch.equal(o[2], weights)
+    o2 = oracle.unpack_hidden((nodes, edges, weights, T), B)[1]
+    assert torch.equal(o2._indices(), adj2._indices()) and torch.equal(o2._values(), adj2._values())
+    torch.save({"name": name, "B": B, "N": N, "max_edges": max_edges, "indices": adj.indices(), "values": adj.values(),
+                "nodes": nodes, "T": T, "edges": edges, "weights": weights,
+                "unpacked_indices": adj2._indices(), "unpacked_values": adj2._values()},
+               os.path.join(HERE, name + ".pt"))
+    print("wrote", name)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pack":
+        pack_case("pack_ragged", B=5, N=12, max_edges=20, seed=21)
+        pack_case("pack_wide", B=9, N=40, max_edges=70, seed=22)
+    else:
+        main()
+        pack_case("pack_ragged", B=5, N=12, max_edges=20, seed=21)
+        pack_case("pack_wide", B=9, N=40, max_edges=70, seed=22)

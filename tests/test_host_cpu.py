@@ -145,7 +145,7 @@ def test_sparse_plan_matching():
                       aux_edge_selectors=make_sparse_selector([("spatial_radius", slice(0, 2), 0.25)]))
         (c1, c2, a1, a2), hops, radius = m.fused_plan()
         assert (a1, a2, hops, radius[1]) == ("tanh", "tanh", (1, 3), 0.25)
-        assert SparseGCM(gnn, max_hops=1).fused_plan() is None
+        assert SparseGCM(gnn, max_hops=1).fused_plan() is not None      # masked aggregation (forward only)
         assert SparseGCM(gnn, max_hops=2).fused_plan() is not None
         assert SparseGCM(gnn, preprocessor=torch.nn.Linear(6, 6)).fused_plan() is None
 

@@ -202,3 +202,20 @@ def test_oracle_on_preprocessed_observations_reproduces_the_reference_with_a_pre
                 raw[:, t] = g["obs"][t]
     assert torch.equal(raw, g["final"][0])                       # the reference's m_t holds RAW observations
     assert torch.equal(hidden[1].float(), g["final"][1].float()) and torch.equal(hidden[3], g["final"][3])
+
+
+@pytest.mark.parametrize("name", ["pack_ragged", "pack_wide"])
+def test_pack_unpack_oracle_and_cpu_helpers_match_reference_golden(name):
+    """util.pack_hidden / unpack_hidden (reference util.py:323-382): the oracle's restatement and the product package's
+    torch path for CPU tensors against the fixtures written by the unmodified reference."""
+    from gcm import util
+
+    g = load_golden(name)
+    adj = torch.sparse_coo_tensor(g["indices"], g["values"], size=(g["B"], g["N"], g["N"]))
+    for impl in (oracle, util):
+        _, edges, weights, _ = impl.pack_hidden((g["nodes"], adj, g["T"]), g["B"], g["max_edges"])
+        assert torch.equal(edges, g["edges"]) and torch.equal(weights, g["weights"]), impl.__name__
+        _, adj2, _ = impl.unpack_hidden((g["nodes"], g["edges"], g["weights"], g["T"]), g["B"])
+        assert torch.equal(adj2._indices(), g["unpacked_indices"]) and torch.equal(adj2._values(), g["unpacked_values"])
+    with pytest.raises(AssertionError, match="Cannot pack"):
+        oracle.pack_hidden((g["nodes"], adj, g["T"]), g["B"], 3)

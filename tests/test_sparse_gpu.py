@@ -235,3 +235,70 @@ def test_csr_transpose_kernel_equals_the_global_sort():
     assert edges.shape[1] > 1000
     for got in (fast, fast2):
         assert torch.equal(got[0], slow[0]) and torch.equal(got[1], slow[1])
+
+
+@pytest.mark.parametrize("name", ["pack_ragged", "pack_wide"])
+def test_pack_unpack_kernels_match_reference_golden(name):
+    """RLlib state wire format: gcm_pack_edges / gcm_unpack_edges behind util.pack_hidden /
+    util.unpack_hidden against the fixtures written by the unmodified reference (util.py:323-382), bit for bit."""
+    from helpers import load_golden
+    from gcm import _cabi, util
+
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    adj = torch.sparse_coo_tensor(g["indices"], g["values"], size=(g["B"], g["N"], g["N"])).to(dev)
+    _, edges, weights, _ = util.pack_hidden((g["nodes"].to(dev), adj, g["T"].to(dev)), g["B"], g["max_edges"])
+    assert _cabi.lib().gcm_last_kernel().decode() == "k_pack_edges"
+    assert edges.dtype == torch.long and torch.equal(edges.cpu(), g["edges"]) and torch.equal(weights.cpu(), g["weights"])
+    _, adj2, _ = util.unpack_hidden((g["nodes"].to(dev), edges, weights, g["T"].to(dev)), g["B"])
+    assert _cabi.lib().gcm_last_kernel().decode() == "k_unpack_edges"
+    assert torch.equal(adj2._indices().cpu(), g["unpacked_indices"]) and torch.equal(adj2._values().cpu(), g["unpacked_values"])
+    with pytest.raises(AssertionError, match="Cannot pack"):
+        util.pack_hidden((g["nodes"].to(dev), adj, g["T"].to(dev)), g["B"], 3)
+
+
+def test_pack_unpack_round_trip_at_scale_and_through_sparse_gcm():
+    """B = 1024 graphs, ragged edge counts up to 200: pack -> unpack is the identity on the coalesced COO, agrees with the
+    oracle's per-graph loops on a sample of graphs, and a SparseGCM hidden state survives the trip RaySparseGCM.forward
+    makes around every call (ray_sparse_gcm.py:195-213): the next step's output is unchanged."""
+    import gcm_oracle as oracle
+    from gcm import util
+
+    dev = torch.device("cuda:0")
+    B, N, M = 1024, 64, 256
+    gen = torch.Generator().manual_seed(12)
+    n_e = torch.randint(0, 200, (B,), generator=gen)
+    b_idx = torch.repeat_interleave(torch.arange(B), n_e)
+    flat = torch.cat([torch.randperm(N * N, generator=gen)[:int(k)] for k in n_e])
+    idx = torch.stack([b_idx, flat // N, flat % N])
+    vals = torch.rand(idx.shape[1], generator=gen)
+    adj = torch.sparse_coo_tensor(idx, vals, size=(B, N, N)).coalesce()
+    nodes, T = torch.zeros(B, N, 2), torch.zeros(B, dtype=torch.long)
+    _, edges, weights, _ = util.pack_hidden((nodes.to(dev), adj.to(dev), T.to(dev)), B, M)
+    _, back, _ = util.unpack_hidden((nodes.to(dev), edges, weights, T.to(dev)), B)
+    assert torch.equal(back._indices().cpu(), adj.indices()) and torch.equal(back._values().cpu(), adj.values())
+    sample = [0, 1, 511, 1023]
+    sub = torch.sparse_coo_tensor(torch.cat([torch.stack([torch.full_like(adj.indices()[0][adj.indices()[0] == b], i),
+                                                          adj.indices()[1][adj.indices()[0] == b],
+                                                          adj.indices()[2][adj.indices()[0] == b]]) for i, b in enumerate(sample)], 1),
+                                  torch.cat([adj.values()[adj.indices()[0] == b] for b in sample]), size=(len(sample), N, N))
+    _, e_o, w_o, _ = oracle.pack_hidden((nodes[sample], sub, T[sample]), len(sample), M)
+    assert torch.equal(edges[sample].cpu(), e_o) and torch.equal(weights[sample].cpu(), w_o)
+    # through SparseGCM: step, pack + unpack the hidden state, step again == stepping without the trip
+    from helpers import make_sparse_gnn, make_sparse_selector
+    from gcm.sparse_gcm import SparseGCM
+    p = oracle.make_params(6, 8)
+    outs = []
+    for trip in (False, True):
+        gnn, _ = make_sparse_gnn(6, 8, p, ("tanh", "tanh"))
+        mod = SparseGCM(gnn.to(dev), edge_selectors=make_sparse_selector([("temporal", (1, 2))]), graph_size=16)
+        g2 = torch.Generator().manual_seed(3)
+        x1, x2 = torch.randn(5, 4, 6, generator=g2).to(dev), torch.randn(5, 3, 6, generator=g2).to(dev)
+        taus1, taus2 = torch.tensor([4, 2, 3, 4, 1], device=dev), torch.tensor([3, 3, 1, 2, 3], device=dev)
+        with torch.no_grad():
+            _, hid = mod(x1, taus1, None)
+            if trip:
+                hid = util.unpack_hidden(util.pack_hidden(hid, 5, 64), 5)
+            o, hid2 = mod(x2, taus2, hid)
+        outs.append((o, hid2[1].coalesce().indices()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
