@@ -110,6 +110,25 @@ class DenseState:
             st.weights0 = weights
         return st, flags
 
+    def clone(self) -> "DenseState":
+        """An independent copy of the graphs (device copies of the node log, the adjacency masks when they are current,
+        the counters): a checkpoint several rollouts / BPTT windows can restart from without going back through the
+        reference-layout tensors (materialise + ingest moves the [B,N,N] float adjacency; this moves the log only).
+        Caches that depend on the layer weights (per-node caches, cached layer-1 rows) are rebuilt on first use."""
+        new = DenseState(self.B, self.N, self.F, self.device, self.C)
+        new.nodes.copy_(self.nodes)
+        new.count.copy_(self.count)
+        if not self.masks_stale:
+            new.masks.copy_(self.masks)
+        new.masks_stale = self.masks_stale
+        new.status = self.status
+        new.pure_key, new.host_count, new.dense_ok = self.pure_key, self.host_count, self.dense_ok
+        new.max_count, new.weights0 = self.max_count, self.weights0
+        new.zc_ok = False
+        if self.raw is not None:
+            new.raw, new.pre_key = self.raw.clone(), self.pre_key
+        return new
+
     # -- materialisation ------------------------------------------------------------------------
     def sync_masks(self) -> None:
         """The ones path does not maintain the adjacency bit masks; write them before anything reads them."""
@@ -219,6 +238,11 @@ class DenseHidden:
     def detach(self) -> "DenseHidden":
         """Same graph state, cut from the autograd history (truncated BPTT)."""
         return DenseHidden(self.claim(), None)
+
+    def clone(self) -> "DenseHidden":
+        """An independent copy of the memory (detached): later steps on either handle do not affect the other.  Use it to
+        restart several episodes / BPTT windows from one prepared state."""
+        return DenseHidden(self.claim().clone(), None)
 
     @property
     def num_nodes(self) -> torch.Tensor:

@@ -449,3 +449,41 @@ def test_user_gnn_with_a_different_forward_is_not_fused():
             want = gnn(nodes, adj, torch.zeros(0, device=dev), B, N)[torch.arange(B, device=dev), nn - 1]
             assert rel_err(belief, want) < 1e-5, t
     assert mod._plan is None and any("does not compute one" in str(w.message) for w in caught)
+
+
+@pytest.mark.parametrize("spec", [[("temporal", (1, 2, 4), "forward")], [("dense",)], [("cosine", 0.5)]])
+def test_hidden_clone_is_an_independent_checkpoint(spec):
+    """m_t.clone(): two rollouts restarted from the same prepared memory give the same beliefs as one rollout from the
+    reference-layout tuple, and stepping one copy leaves the other (and the original) untouched."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, H, T0, T1 = 6, 12, 16, 32, 9, 8
+    gen = torch.Generator().manual_seed(55)
+    obs = _clustered(gen, T0 + T1, B, F).to(dev)
+    p = oracle.make_params(F, H)
+    gnn, _ = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+    with torch.no_grad():
+        hidden = None
+        for t in range(T0):
+            _, hidden = mod(obs[t], hidden)
+        base = tuple(t.clone() for t in hidden)               # the checkpoint in the reference's layout
+        runs = []
+        for _ in range(2):
+            h = hidden.clone()
+            outs = []
+            for t in range(T0, T0 + T1):
+                o, h = mod(obs[t], h)
+                outs.append(o)
+            runs.append((torch.stack(outs), tuple(h)))
+        for a, b in zip(tuple(hidden), base):
+            assert torch.equal(a, b)                          # the original never moved
+        h, outs = base, []
+        for t in range(T0, T0 + T1):
+            o, h = mod(obs[t], h)
+            outs.append(o)
+        want = torch.stack(outs)
+    assert torch.equal(runs[0][0], runs[1][0]) and rel_err(runs[0][0], want) < TOL
+    for a, b in zip(runs[0][1], tuple(h)):
+        assert torch.equal(a, b)
