@@ -405,6 +405,33 @@ def cpu_baseline_subprocess(workload, batch, steps, warm):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank to the CPUs of its GPU's NUMA node (before any pinned host buffer is allocated, so that first touch
+    puts the pages there): with all ranks on node 0 the per-step H2D / D2H copies of 8 ranks share one memory controller
+    and one PCIe root (round 1: e2e 1.76x at 8 GPUs).  Best effort: silently does nothing when sysfs / affinity say no."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{pci}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": True, "cpus": len(allowed)}
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class Ctx:
     def __init__(self, dev, rank, world, dist, sampler):
         self.dev, self.rank, self.world, self.dist, self.sampler = dev, rank, world, dist, sampler
@@ -456,6 +483,11 @@ def run_rollout(ctx, workload, B, K, W, args):
             ctx.barrier()
             t_lo = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # The K steps are ONE call, so its host-side latency (Python + the first launch, ~50 us; more with N ranks
+            # sharing the host) would sit in front of ~450 us of device work and be charged to every step.  A short
+            # spinning kernel queued BEFORE the start event keeps the stream busy while the host makes the call -- the
+            # state any step but the first of a rollout is in -- so the events bracket exactly the K steps on the device.
+            torch.cuda._sleep(int(4.0e5))                      # ~200 us at 1.9 GHz, outside the timed region
             e0.record()
             beliefs, hidden = mod.forward_sequence(x_seq, hidden, time_major=True)
             e1.record()
@@ -564,7 +596,8 @@ def run_rollout(ctx, workload, B, K, W, args):
         "state": ("in-place node log + bit-packed adjacency; steady state: graphs full before the warm-up "
                   f"({fill} untimed fill steps + {W} warm-up steps), the oldest node is dropped every step"),
         "timed_call": (f"ONE DenseGCM.forward_sequence(x[{K},B,F], m_t, time_major=True) call: the C rollout entry walks "
-                       f"the {K} steps in {launches} launch(es) of the step kernel"
+                       f"the {K} steps in {launches} launch(es) of the step kernel; CUDA events around the call, the "
+                       "stream kept busy by a spin kernel queued before the start event while the host makes the call"
                        if seq else f"{K} DenseGCM.forward calls"),
         "e2e": {"value": B * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * F * 4,
                 "d2h_bytes_per_step": B * H * 4, "ms_per_step": e2e_ms / K,
@@ -877,6 +910,7 @@ def main():
 
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -890,7 +924,7 @@ def main():
     also = []
     if args.workload == "cfg2" and not args.no_also and args.batch is None:
         # the fwd+bwd half of BASELINE.json's metric, measured in the same run
-        for wl, k in (("cfg2-bptt", 4), ("cfg3", 3)):
+        for wl, k in (("cfg2-bptt", 4), ("cfg3", 3), ("cfg3-seq", 3)):
             rec = run_workload(ctx, wl, k, 3, args)
             if rec is not None:
                 rec = {key: rec[key] for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
@@ -901,6 +935,8 @@ def main():
     if rank == 0:
         if also:
             line["also"] = also
+        if numa is not None:
+            line["config"]["host_binding"] = numa
         if world == 1 and not args.no_cpu_baseline:
             cb = {"cfg2": args.cpu_batch, "cfg5": 8}.get(args.workload, 64)
             progress("cpu baseline: start")
