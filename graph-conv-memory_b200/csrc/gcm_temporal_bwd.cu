@@ -24,63 +24,61 @@ struct HopList {
 };
 
 // out[i, b, 0:F] = sum_{s: p-s >= 0} x[b, slot(p-s), :],  out[i, b, F:2F] = x[b, slot(p), :],  p = p0 + i (zero row if p < 0)
-__global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state st, const HopList hops, long long p0,
-                                                         int n_rows, float* __restrict__ out) {
+// grid: (chunks of B * F/4, rows); 32-bit index arithmetic (node positions are int32 counters on the device): the first
+// version spent a fifth of its issue slots in emulated 64-bit divisions (profiles/c2_bptt_kernels_r2.md).
+__global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state st, const HopList hops, int p0,
+                                                         float* __restrict__ out) {
   const int F4 = st.F >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n_rows * st.B * F4;
-  if (idx >= total) return;
-  const int c = (int)(idx % F4);
-  const long long ib = idx / F4;
-  const int b = (int)(ib % st.B);
-  const long long p = p0 + ib / st.B;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk)
+  if (j >= st.B * F4) return;
+  const int b = j / F4, c = j - b * F4;
+  const int i = blockIdx.y;
+  const int p = p0 + i;
   float4 self = make_float4(0.f, 0.f, 0.f, 0.f), sum = self;
   if (p >= 0) {
     const float4* rows = reinterpret_cast<const float4*>(st.nodes + (size_t)b * st.C * st.F) + c;
     self = __ldg(rows + (size_t)(p % st.C) * F4);
-    for (int j = 0; j < hops.n; ++j) {
-      const long long q = p - hops.h[j];
+    for (int k = 0; k < hops.n; ++k) {
+      const int q = p - hops.h[k];
       if (q >= 0) {
         const float4 v = __ldg(rows + (size_t)(q % st.C) * F4);
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
     }
   }
-  float4* o = reinterpret_cast<float4*>(out + (size_t)ib * 2 * st.F) + c;
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)i * st.B + b) * 2 * st.F) + c;
   __stcs(o, sum);
   __stcs(o + F4, self);
 }
 
 // out[i, b, 0:H] = sum_s src[pos + sign * s, b, :],  out[i, b, H:2H] = src[pos, b, :],  pos = out_pos0 + i;
 // src rows cover positions [src_pos0, src_pos0 + n_src); a position below valid_lo (a node that never existed)
-// contributes nothing, and an output row whose own position is below valid_lo is zero.
-__global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src, long long src_pos0, int n_src,
-                                                   long long valid_lo, const HopList hops, int sign,
-                                                   float* __restrict__ out, long long out_pos0, int n_out, int B, int H) {
+// contributes nothing, and an output row whose own position is below valid_lo is zero.  Same grid as above.
+__global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src, int src_pos0, int n_src, int valid_lo,
+                                                   const HopList hops, int sign, float* __restrict__ out, int out_pos0,
+                                                   int B, int H) {
   const int H4 = H >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n_out * B * H4;
-  if (idx >= total) return;
-  const int c = (int)(idx % H4);
-  const long long ib = idx / H4;
-  const int b = (int)(ib % B);
-  const long long pos = out_pos0 + ib / B;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk): row-major inside a row block
+  if (j >= B * H4) return;
+  const int i = blockIdx.y;
+  const int pos = out_pos0 + i;
   float4 self = make_float4(0.f, 0.f, 0.f, 0.f), sum = self;
   if (pos >= valid_lo) {
-    const float4* s4 = reinterpret_cast<const float4*>(src) + (size_t)b * H4 + c;
+    const float4* s4 = reinterpret_cast<const float4*>(src) + j;
     const size_t row = (size_t)B * H4;
-    const long long j0 = pos - src_pos0;
+    const int j0 = pos - src_pos0;
     if (j0 >= 0 && j0 < n_src) self = __ldg(s4 + (size_t)j0 * row);
-    for (int j = 0; j < hops.n; ++j) {
-      const long long q = pos + (long long)sign * hops.h[j];
-      const long long jq = q - src_pos0;
+    for (int k = 0; k < hops.n; ++k) {
+      const int q = pos + sign * hops.h[k];
+      const int jq = q - src_pos0;
       if (q >= valid_lo && jq >= 0 && jq < n_src) {
         const float4 v = __ldg(s4 + (size_t)jq * row);
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
     }
   }
-  float4* o = reinterpret_cast<float4*>(out + (size_t)ib * 2 * H) + c;
+  const int b = j / H4, c = j - b * H4;
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)i * B + b) * 2 * H) + c;
   __stcs(o, sum);
   __stcs(o + H4, self);
 }
@@ -105,9 +103,11 @@ extern "C" int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hop
               "temporal_gather: pointers must be 16-byte aligned");
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_gather: bad hop list");
-  const long long total = (long long)n_rows * st->B * (st->F >> 2);
-  if (total == 0) return GCM_OK;
-  k_temporal_gather<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*st, hl, p0, n_rows, out);
+  GCM_REQUIRE(p0 > -(1ll << 30) && p0 + n_rows < (1ll << 31) && n_rows <= 65535 && (long long)st->B * (st->F >> 2) < (1ll << 31),
+              "temporal_gather: position / size out of range");
+  if (n_rows == 0 || st->B == 0) return GCM_OK;
+  const dim3 grid((unsigned)(((long long)st->B * (st->F >> 2) + 255) / 256), (unsigned)n_rows);
+  k_temporal_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, hl, (int)p0, out);
   return gcm_check_launch("k_temporal_gather");
 }
 
@@ -120,9 +120,13 @@ extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int 
               "temporal_shift_sum: pointers must be 16-byte aligned");
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_shift_sum: bad hop list");
-  const long long total = (long long)n_out * B * (H >> 2);
-  if (total == 0) return GCM_OK;
-  k_shift_sum<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_pos0, n_src, valid_lo, hl, sign,
-                                                                                out, out_pos0, n_out, B, H);
+  GCM_REQUIRE(src_pos0 > -(1ll << 30) && out_pos0 > -(1ll << 30) && src_pos0 + n_src < (1ll << 31) &&
+                  out_pos0 + n_out < (1ll << 31) && valid_lo > -(1ll << 31) && valid_lo < (1ll << 31) && n_out <= 65535 &&
+                  (long long)B * (H >> 2) < (1ll << 31),
+              "temporal_shift_sum: position / size out of range");
+  if (n_out == 0 || B == 0) return GCM_OK;
+  const dim3 grid((unsigned)(((long long)B * (H >> 2) + 255) / 256), (unsigned)n_out);
+  k_shift_sum<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hl, sign, out,
+                                                      (int)out_pos0, B, H);
   return gcm_check_launch("k_shift_sum");
 }
