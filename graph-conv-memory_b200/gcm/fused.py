@@ -628,6 +628,36 @@ def fused_step_grad(plan: FusedPlan, state: DenseState, x: torch.Tensor, token, 
     return belief, token, state
 
 
+_PATTERNS = {}
+
+
+def recognise_pure_temporal(plan: FusedPlan, state: DenseState, adj: torch.Tensor, num_nodes: torch.Tensor) -> bool:
+    """Is a caller-supplied adjacency exactly what THIS forward-only TemporalBackedge chain builds (reference
+    edge_selectors/temporal.py:72-88 followed by the shifts of gcm.py:323-355): adj[i, i - s] = 1 for every hop s and
+    s <= i < num_nodes, zeros elsewhere?  Then the ingested state is as good as one the chain built itself ("pure
+    temporal": implicit adjacency, cached-row kernel, window-level backward).  This is what keeps RLlib round trips on
+    the fast path: RayDenseGCM hands the memory back as plain tensors on every call (ray_gcm.py:194-211)."""
+    if plan.temporal_key is None or any(s.direction != _cabi.DIR["forward"] for s in plan.sels):
+        return False
+    N = state.N
+    hops = sorted({h for s in plan.sels for h in s.hops if 0 < h < N})
+    key = (N, tuple(hops), adj.device)
+    pat = _PATTERNS.get(key)
+    if pat is None:
+        pat = torch.zeros(N, N, device=adj.device)
+        for h in hops:
+            pat += torch.diag(torch.ones(N - h, device=adj.device), -h)
+        _PATTERNS[key] = pat
+    n = num_nodes.to(adj.device)
+    sink_ok = torch.arange(N, device=adj.device).view(1, N, 1) < n.view(-1, 1, 1)
+    if not bool((adj == pat.unsqueeze(0) * sink_ok).all()):
+        return False
+    state.pure_key = plan.temporal_key
+    lo, hi = int(n.min()), int(n.max())
+    state.host_count = lo if lo == hi else None
+    return True
+
+
 def ingest_token(state: DenseState, nodes: torch.Tensor):
     state.chain_start = state.steps
     return _IngestFn.apply(nodes, state)

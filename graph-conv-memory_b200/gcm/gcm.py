@@ -299,6 +299,7 @@ class DenseGCM(torch.nn.Module):
                                              N + (self.bptt_capacity if recording else 0))
             if flags & (_cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT):
                 return generic()   # not a {0,1} graph over the valid block
+            fused.recognise_pure_temporal(plan, state, adj, num_nodes)     # a memory this chain built keeps its fast path
             token = None
             if recording and nodes.requires_grad:
                 ingest_grad = True

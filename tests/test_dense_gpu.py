@@ -225,8 +225,10 @@ def test_every_temporal_kernel_variant_matches_oracle(variant, B, N, F, T, hops)
 def test_row_cache_follows_weight_updates_and_reingest():
     """The layer-1 row cache is only read while every row it would use was written under the current weights:
     after an in-place weight update the recomputing kernel runs for max_hop steps, then the cached-row kernel
-    resumes; a state that went through materialise -> ingest is no longer 'pure temporal' and takes the general
-    kernel.  Every step is checked against the oracle evaluated with the weights of that step."""
+    resumes; a state that went through materialise -> ingest (what RayDenseGCM does on every call) is recognised as this
+    chain's own adjacency and keeps the fast kernels (cache refilled first); an ingested adjacency that is NOT the chain's
+    pattern takes the general kernel.  Every step is checked against the oracle evaluated with the weights of that
+    step."""
     from gcm import _cabi
     from gcm.gcm import DenseGCM
 
@@ -259,9 +261,18 @@ def test_row_cache_follows_weight_updates_and_reingest():
     assert names[:10] == ["k_step_temporal_hc"] * 10
     assert names[10:14] == ["k_step_temporal_tc"] * 4 and names[14] == "k_step_temporal_hc"
     assert names[40:44] == ["k_step_temporal_tc"] * 4 and names[44] == "k_step_temporal_hc"
-    assert all(n == "k_step_general" for n in names[50:])
+    assert names[50:54] == ["k_step_temporal_tc"] * 4 and all(n == "k_step_temporal_hc" for n in names[54:])
     nodes, adj, weights, num_nodes = hidden
     assert torch.equal(nodes.cpu(), o_hidden[0]) and torch.equal(adj.cpu(), o_hidden[1])
+    # one extra edge that the chain would not have written: no longer the chain's pattern -> the general kernel
+    adj2 = adj.clone()
+    adj2[:, 5, 0] = 1.0
+    o_hidden = (o_hidden[0], adj2.cpu(), o_hidden[2], o_hidden[3])
+    with torch.no_grad():
+        belief, hidden = mod(obs[0].to(dev), (nodes, adj2, weights, num_nodes))
+        ref, o_hidden = oracle.dense_gcm_step(obs[0], o_hidden, spec, p, graph_size=N)
+    assert lib.gcm_last_kernel().decode() == "k_step_general" and rel_err(belief, ref) < 2e-5
+    assert torch.equal(tuple(hidden)[1].cpu(), o_hidden[1])
 
 
 @pytest.mark.parametrize("spec", [[("cosine", 0.5)], [("spatial", 1.0, slice(0, 2), None)], [("euclidean", 2.0)]])
