@@ -209,6 +209,9 @@ class DenseGCM(torch.nn.Module):
                 x.requires_grad or any(p.requires_grad for p in self.parameters())
                 or (isinstance(hidden, DenseHidden) and hidden.token is not None)
                 or (isinstance(hidden, (tuple, list)) and hidden[0].requires_grad)):
+            res = self._sequence_pre_grad(plan, x.unsqueeze(1), hidden) if x.dim() == 2 else None
+            if res is not None:
+                return res[0][:, 0], res[1]
             return self._forward_generic(x, hidden)
         assert x.dtype == torch.float32
         _cabi.require_cuda(x, "DenseGCM.forward(x)")
@@ -426,7 +429,10 @@ class DenseGCM(torch.nn.Module):
                 x_seq.requires_grad or any(p.requires_grad for p in self.parameters())
                 or (isinstance(hidden, DenseHidden) and hidden.token is not None)
                 or (isinstance(hidden, (tuple, list)) and hidden[0].requires_grad)):
-            if pre is not None or T > int(self.bptt_capacity):
+            if pre is not None:
+                res = self._sequence_pre_grad(plan, x_seq, hidden)
+                return res if res is not None else loop(hidden)
+            if T > int(self.bptt_capacity):
                 return loop(hidden)
             # recording: one autograd node for the T steps, window-level backward (gcm.temporal)
             out0, start = None, 0
@@ -506,6 +512,96 @@ class DenseGCM(torch.nn.Module):
         if self._shard_sizes is None or self._shard_sizes[0] != x.shape[0]:
             self._shard_sizes = (x.shape[0], gdist.shard_sizes(x.shape[0], x.device, group))
         return gdist.gather_current_obs(x.detach(), group, self._shard_sizes[1])
+
+    def _sequence_pre_grad(self, plan, x_seq, hidden):
+        """Recorded steps of a forward-only TemporalBackedge chain behind a row-wise preprocessor (RayDenseGCM's
+        configuration in training) on the window-level backward.  The reference maps ALL stored rows through the
+        preprocessor at every step (gcm.py:290-291); a per-row map only has to be applied to the new observations
+        (y = pre(x), with autograd: dL/dy comes back from the window's backward) and -- for its parameters' gradient
+        through the rows written BEFORE the window -- to the 2 max_hop newest stored raw rows, which enter the autograd
+        graph as the `hist` input of gcm.temporal._TSeqFn.  Returns None when the situation is not covered (the caller
+        then takes the generic path)."""
+        pre = self.preprocessor
+        if (not plan.hc_ring or plan.temporal_key is None or x_seq.dtype != torch.float32 or not x_seq.is_cuda
+                or x_seq.dim() != 3 or self._plan is not plan):
+            return None
+        B, T, F_raw = x_seq.shape
+        dev = x_seq.device
+        mh, N = plan.max_hop, self.graph_size
+        cap = max(int(self.bptt_capacity), T)
+        plist = self.__dict__.get("_pre_params")
+        if plist is None:
+            plist = self.__dict__["_pre_params"] = list(pre.parameters())
+        pkey = tuple([v for p in plist for v in (p.data_ptr(), p._version)])
+        token = None
+        with torch.no_grad():
+            if hidden is None:
+                state = DenseState(B, N, plan.gnn.F, dev, N + cap)
+                state.raw = torch.zeros(B, state.C, F_raw, device=dev, dtype=torch.float32)
+                state.pre_key = pkey
+            elif isinstance(hidden, DenseHidden):
+                state, token = hidden.claim(), hidden.token
+                if state.raw is None or state.B != B or state.raw.shape[2] != F_raw:
+                    return None
+                if state.pre_key != pkey:
+                    if token is not None:
+                        raise RuntimeError("preprocessor parameters were modified in place inside a recorded window")
+                    state.nodes.copy_(pre(state.raw))          # new weights: every stored row gets its new image
+                    state.pre_key = pkey
+                    state.xsum, state.rc_key, state.hc_key, state.hc_fresh, state.fast_ok = None, None, None, 0, False
+                if token is None and (state.C - state.N + 1 < T or state.C - state.N < 1):
+                    state = self._rehome_pre(plan, state, state.N + cap, pkey)
+            else:
+                nodes_raw, adj, weights, num_nodes = hidden
+                if nodes_raw.requires_grad or adj.requires_grad or nodes_raw.dtype != torch.float32 or not nodes_raw.is_cuda:
+                    return None
+                N = nodes_raw.shape[1]
+                state, flags = DenseState.ingest(pre(nodes_raw), adj, weights, num_nodes, N + cap)
+                if flags & (_cabi.FLAG_UNCLEAN | _cabi.FLAG_BADCOUNT):
+                    return None
+                fused.recognise_pure_temporal(plan, state, adj, num_nodes)
+                state.raw = torch.zeros(B, state.C, F_raw, device=dev, dtype=torch.float32)
+                state.raw[:, :N] = nodes_raw
+                state.pre_key = pkey
+            if (state is None or not temporal.grad_supported(plan, state)
+                    or (token is not None and not getattr(token, "_gcm_tw", False))):
+                return None
+            if token is not None and state.steps - state.twin.chain_start + T > state.C - state.N + 1:
+                return None
+        hist = None
+        if token is None and any(p.requires_grad for p in plist):
+            # GNN-input rows of the 2 max_hop nodes written before this window, as a function of the preprocessor
+            P0 = state.host_count
+            pos = torch.arange(P0 - 2 * mh, P0, device=dev)
+            raw_hist = state.raw[:, pos.clamp(min=0) % state.C]
+            hist = pre(raw_hist) * (pos >= 0).view(1, -1, 1).to(raw_hist.dtype)
+        if not DenseGCM.did_warn and state.host_count + T > state.N:
+            print("Overflow detected, wrapping around. Will not warn again")
+            DenseGCM.did_warn = True
+        y_seq = pre(x_seq)
+        beliefs, token, state = temporal.sequence_grad(plan, state, y_seq, token, cap, hist=hist)
+        if not plan.validated:
+            plan.validated = True
+            if not fused._validate_structure(plan, self, dev):
+                raise RuntimeError("gcm: the GNN looked like a 2-layer DenseGraphConv stack but does not compute one")
+        with torch.no_grad():
+            xr = x_seq.detach()
+            _cabi.check(_cabi.lib().gcm_state_log_write_seq(state.raw_ref(), xr.data_ptr(), xr.stride(0), xr.stride(1), T,
+                                                            _cabi.stream_ptr(dev)), "gcm_state_log_write_seq")
+        return beliefs, DenseHidden(state, token)
+
+    def _rehome_pre(self, plan, state, capacity, pkey):
+        """A preprocessed state in a log with more spare rows (before the first recorded step of a window)."""
+        nodes_raw, adj, num_nodes = state.materialize()
+        w = torch.zeros(0, device=state.device) if state.weights0 is None else state.materialize_weights()
+        new, _ = DenseState.ingest(self.preprocessor(nodes_raw), adj, w, num_nodes, capacity)
+        new.pure_key = state.pure_key
+        new.host_count = None if state.host_count is None else min(state.host_count, state.N)
+        new.status = state.status
+        new.raw = torch.zeros(state.B, new.C, nodes_raw.shape[2], device=state.device, dtype=torch.float32)
+        new.raw[:, : state.N] = nodes_raw
+        new.pre_key = pkey
+        return new
 
     def _would_overflow(self, state: DenseState) -> bool:
         # host-side mirror only (no device sync): graphs started empty overflow after N steps

@@ -274,9 +274,9 @@ def _rows(plan, st, win, p_lo, p_hi, Kc):
     return A1, h, dz1
 
 
-def _check_log(st, win, plan):
+def _check_log(st, win, plan, margin=2):
     steps_total = st.steps - win.chain_start
-    if steps_total + 2 * plan.max_hop > st.C:
+    if steps_total + margin * plan.max_hop > st.C:
         raise RuntimeError(
             f"BPTT window too long for the node log: {steps_total} steps since the chain started but the log keeps "
             f"{st.C - st.N} spare rows; raise DenseGCM.bptt_capacity")
@@ -380,10 +380,15 @@ class _TStepFn(torch.autograd.Function):
 
 
 class _TSeqFn(torch.autograd.Function):
-    """T recorded steps taken at once (DenseGCM.forward_sequence): one node for the steps k0 .. k0+T-1."""
+    """T recorded steps taken at once (DenseGCM.forward_sequence): one node for the steps k0 .. k0+T-1.
+    hist (optional, first node of a chain only): the GNN-input rows of the 2 max_hop nodes written BEFORE the chain,
+    [B, 2 max_hop, F], as a function of something that requires grad -- a preprocessor's image of the stored raw
+    observations (the reference maps every stored row through the preprocessor at every step, gcm.py:290-291, so its
+    parameters also collect gradient through rows older than the window).  Forward ignores its values (the node log
+    already holds them); backward returns dL/dhist."""
 
     @staticmethod
-    def forward(ctx, x_seq, token, plan, state, k0):
+    def forward(ctx, x_seq, token, plan, state, k0, hist):
         from gcm import fused
         T = x_seq.shape[1]
         buf = torch.empty(T, state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)   # time-major
@@ -396,6 +401,7 @@ class _TSeqFn(torch.autograd.Function):
         ctx.plan, ctx.state, ctx.k0, ctx.T = plan, state, k0, T
         ctx.chain_id = state.twin.chain_id
         ctx.buf = buf
+        ctx.has_hist = hist is not None
         return buf.transpose(0, 1), torch.zeros(1, device=state.device)
 
     @staticmethod
@@ -406,19 +412,29 @@ class _TSeqFn(torch.autograd.Function):
             raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
         _deliver(plan, st, win, k0, T, d_beliefs.transpose(0, 1).contiguous().float(), ctx.buf)
         ctx.buf = None
-        d_x = None
-        if ctx.needs_input_grad[0]:
-            _check_log(st, win, plan)
+        d_x = d_hist = None
+        want_hist = ctx.has_hist and ctx.needs_input_grad[5]
+        if ctx.needs_input_grad[0] or want_hist:
             Kc, mh = win.kmax + 1, plan.max_hop
-            if k0 == 0 and Kc == T:
-                # the node covers the whole window: one evaluation serves dL/dx here and the weight gradients at the root
-                rows = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
-                win.cache = rows
-                d_x = _dx(plan, st, win, 0, T, Kc, rows=(win.P0, rows[2][mh:]))
-            else:
-                d_x = _dx(plan, st, win, k0, k0 + T, Kc)
-            d_x = d_x.transpose(0, 1)
-        return d_x, torch.zeros(1, device=st.device), None, None, None
+            _check_log(st, win, plan)
+            rows = None
+            if k0 == 0:
+                # the chain's first node runs last: every step has delivered.  One evaluation of the window serves dL/dx
+                # here, dL/dhist, and the weight gradients at the root
+                full = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
+                win.cache = full
+                rows = (win.P0 - mh, full[2])
+            if ctx.needs_input_grad[0]:
+                if rows is not None:
+                    d_x = _dx(plan, st, win, 0, T, Kc, rows=(win.P0, rows[1][mh:]))
+                else:
+                    d_x = _dx(plan, st, win, k0, k0 + T, Kc)
+                d_x = d_x.transpose(0, 1)
+            if want_hist:
+                assert k0 == 0
+                # rows P0 - 2 max_hop .. P0 - 1: dz1 vanishes below P0 - max_hop, so the cached rows are all that is needed
+                d_hist = _dx(plan, st, win, -2 * mh, 0, Kc, rows=rows).transpose(0, 1)
+        return d_x, torch.zeros(1, device=st.device), None, None, None, d_hist
 
 
 def _chain(plan, state, token, n_steps):
@@ -468,12 +484,13 @@ def step_grad(plan, state, x, token, bptt_capacity):
     return belief, token, state
 
 
-def sequence_grad(plan, state, x_seq, token, bptt_capacity):
-    """Recording sequence entry.  Returns (beliefs [B, T, H2], token, state)."""
+def sequence_grad(plan, state, x_seq, token, bptt_capacity, hist=None):
+    """Recording sequence entry.  Returns (beliefs [B, T, H2], token, state).  hist: see _TSeqFn (chain start only)."""
     state.fast_ok = False
     T = x_seq.shape[1]
     state, token = _room(plan, state, token, T, bptt_capacity)
     token, k0 = _chain(plan, state, token, T)
-    beliefs, token = _TSeqFn.apply(x_seq, token, plan, state, k0)
+    assert hist is None or k0 == 0
+    beliefs, token = _TSeqFn.apply(x_seq, token, plan, state, k0, hist)
     token._gcm_tw = True
     return beliefs, token, state

@@ -189,6 +189,47 @@ def preproc_case(name, B, N, F_raw, F, H, T, spec, seed=0, pre_act=None):
     print("wrote", name, "adj nnz", int(hidden[1].sum()))
 
 
+def preproc_grad_case(name, B, N, F_raw, F, H, T0, T1, spec, seed=0):
+    """Training through the reference DenseGCM WITH a preprocessor (RayDenseGCM's configuration): T0 steps without
+    autograd (the window wraps), the hidden state handed on as plain detached tensors, then a BPTT window of T1 steps.
+    The reference maps ALL stored rows through the preprocessor at every step (gcm.py:290-291), so the preprocessor's
+    gradients also collect contributions through the rows written BEFORE the window.  Stored: beliefs, dL/dobs of the
+    window, gradients of the six GNN tensors and of the preprocessor."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    obs = torch.randn(T0 + T1, B, F_raw, generator=g)
+    w = torch.randn(T1, B, H, generator=g)
+    p = oracle.make_params(F, H, seed=7 + seed)
+    lin = torch.nn.Linear(F_raw, F)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(F, F_raw, generator=g) / F_raw ** 0.5)
+        lin.bias.copy_(0.1 * torch.randn(F, generator=g))
+    gnn = RefDenseGNN(F, H, p, ("tanh", "tanh"))
+    mod = DenseGCM(gnn, preprocessor=lin, edge_selectors=ref_selector(spec), graph_size=N)
+    hidden = None
+    with torch.no_grad():
+        for t in range(T0):
+            _, hidden = mod(obs[t], hidden)
+    hidden = tuple(h.detach().clone() for h in hidden)
+    start = tuple(h.clone() for h in hidden)
+    x = obs[T0:].clone().requires_grad_(True)
+    outs = []
+    for t in range(T1):
+        mx, hidden = mod(x[t], hidden)
+        outs.append(mx)
+    outs = torch.stack(outs)
+    (outs * w).sum().backward()
+    d_params = {"w_rel1": gnn.gc0.lin_rel.weight.grad, "b1": gnn.gc0.lin_rel.bias.grad, "w_root1": gnn.gc0.lin_root.weight.grad,
+                "w_rel2": gnn.gc1.lin_rel.weight.grad, "b2": gnn.gc1.lin_rel.bias.grad, "w_root2": gnn.gc1.lin_root.weight.grad}
+    out = {"name": name, "B": B, "N": N, "F_raw": F_raw, "F": F, "H": H, "T0": T0, "T1": T1, "spec": spec, "obs": obs,
+           "loss_w": w, "params": p, "pre_weight": lin.weight.detach().clone(), "pre_bias": lin.bias.detach().clone(),
+           "start": start, "beliefs": outs.detach().clone(), "d_obs": x.grad.clone(),
+           "d_params": {k: v.clone() for k, v in d_params.items()},
+           "d_pre_weight": lin.weight.grad.clone(), "d_pre_bias": lin.bias.grad.clone(),
+           "final": tuple(h.detach().clone() for h in hidden)}
+    torch.save(out, os.path.join(HERE, name + ".pt"))
+    print("wrote", name)
+
+
 def coo_to_idx(adj):
     return adj.coalesce().indices()
 
@@ -370,10 +411,16 @@ def pack_case(name, B, N, max_edges, seed):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "pack":
+    def extras():
         pack_case("pack_ragged", B=5, N=12, max_edges=20, seed=21)
         pack_case("pack_wide", B=9, N=40, max_edges=70, seed=22)
+        preproc_grad_case("train_preproc_temporal", B=4, N=12, F_raw=6, F=32, H=32, T0=15, T1=9,
+                          spec=[("temporal", (1, 2, 4), "forward")], seed=31)
+        preproc_grad_case("train_preproc_temporal_young", B=3, N=16, F_raw=5, F=8, H=32, T0=2, T1=7,
+                          spec=[("temporal", (1, 3), "forward")], seed=32)
+
+    if len(sys.argv) > 1 and sys.argv[1] == "extras":
+        extras()
     else:
         main()
-        pack_case("pack_ragged", B=5, N=12, max_edges=20, seed=21)
-        pack_case("pack_wide", B=9, N=40, max_edges=70, seed=22)
+        extras()

@@ -362,10 +362,14 @@ def test_rowwise_preprocessor_runs_fused_and_matches_the_reference_step(spec):
     nodes, adj, _, num_nodes = hidden
     assert torch.equal(nodes.cpu(), raw_nodes) and torch.equal(adj.cpu(), o_hidden[1])
     assert torch.equal(num_nodes.cpu(), o_hidden[3])
-    # anything that needs autograd takes the generic path and still agrees
+    # autograd: a forward-only temporal chain records on the window-level backward (tests/test_temporal_bwd_gpu.py pins its
+    # gradients to the reference), anything else takes the generic path; either way the belief carries a graph
     x = obs[0].to(dev).requires_grad_(True)
     belief, h2 = mod(x, hidden)
-    assert not isinstance(h2, DenseHidden) and belief.requires_grad
+    fused_grad = spec[0][0] == "temporal" and spec[0][2] == "forward"
+    assert isinstance(h2, DenseHidden) == fused_grad and belief.requires_grad
+    belief.sum().backward()
+    assert x.grad is not None and pre[0].weight.grad is not None
 
 
 @pytest.mark.parametrize("B,C,F,learned", [(300, 9, 64, False), (129, 5, 32, True), (1024, 6, 16, False)])

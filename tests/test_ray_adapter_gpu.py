@@ -59,3 +59,10 @@ def test_reference_ray_adapter_runs_on_this_package(selector):
             window = torch.stack(raw[max(0, n_seen - N):], dim=1)
             assert torch.equal(state[0][:, : window.shape[1]].cpu(), window)
             assert torch.equal(state[1].cpu(), o_hidden[1]) and torch.equal(state[3].cpu(), o_hidden[3])
+    # a training forward of the adapter (autograd on): gradients reach the heads, the GNN and the Linear preprocessor
+    obs = torch.randn(B, T, obs_dim, generator=gen)
+    logits, state2 = model.forward({"obs_flat": obs.reshape(B * T, obs_dim).to(dev)}, state, torch.full((B,), T))
+    (logits.pow(2).sum() + model.value_function().sum()).backward()
+    for prm in list(model.gcm.preprocessor.parameters()) + list(model.gcm.gnn.parameters()) + list(model.logit_branch.parameters()):
+        assert prm.grad is not None and bool(torch.isfinite(prm.grad).all()) and float(prm.grad.abs().max()) > 0
+    assert all(isinstance(s, torch.Tensor) for s in state2) and state2[3].dtype == torch.long

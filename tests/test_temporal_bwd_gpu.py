@@ -178,3 +178,51 @@ def test_window_capacity_truncation_and_unused_beliefs():
     got = named_grads(convs)
     for k in got:
         assert rel_err(got[k], pp[k].grad) < 5 * TOL, k
+
+
+@pytest.mark.parametrize("mode", ["step", "seq", "handle"])
+@pytest.mark.parametrize("name", ["train_preproc_temporal", "train_preproc_temporal_young"])
+def test_training_with_preprocessor_matches_reference_golden(name, mode):
+    """RayDenseGCM's configuration in TRAINING (Linear preprocessor + TemporalBackedge): a BPTT window recorded on the
+    window-level backward, started from the plain tensors RLlib hands back ("step" / "seq") or from a live handle after
+    a no-grad rollout ("handle").  Beliefs, dL/dobs, the six GNN gradients and the preprocessor's gradients -- which
+    include the contributions through rows written before the window (gcm.py:290-291) -- against the fixtures written
+    by the unmodified reference."""
+    from helpers import load_golden
+    from gcm.gcm import DenseGCM
+
+    g = load_golden(name)
+    dev = torch.device("cuda:0")
+    gnn, convs = make_dense_gnn(g["F"], g["H"], g["params"], ("tanh", "tanh"))
+    pre = torch.nn.Linear(g["F_raw"], g["F"])
+    with torch.no_grad():
+        pre.weight.copy_(g["pre_weight"])
+        pre.bias.copy_(g["pre_bias"])
+    mod = DenseGCM(gnn.to(dev), preprocessor=pre.to(dev), edge_selectors=make_selector(g["spec"]), graph_size=g["N"])
+    T0, T1 = g["T0"], g["T1"]
+    if mode == "handle":
+        with torch.no_grad():
+            _, hidden = mod.forward_sequence(g["obs"][:T0].to(dev), None, time_major=True)
+        hidden = hidden.detach()
+    else:
+        hidden = tuple(t.to(dev) for t in g["start"])
+    x = g["obs"][T0:].to(dev).requires_grad_(True)
+    if mode == "step":
+        outs = []
+        for t in range(T1):
+            o, hidden = mod(x[t], hidden)
+            outs.append(o)
+        outs = torch.stack(outs)
+    else:
+        outs, hidden = mod.forward_sequence(x, hidden, time_major=True)
+    assert getattr(hidden.token, "_gcm_tw", False), "the window-level backward should have been recorded"
+    assert rel_err(outs, g["beliefs"]) < 5 * TOL
+    (outs * g["loss_w"].to(dev)).sum().backward()
+    assert rel_err(x.grad, g["d_obs"]) < 5 * TOL
+    got = named_grads(convs)
+    for k, v in g["d_params"].items():
+        assert rel_err(got[k], v) < 5 * TOL, k
+    assert rel_err(pre.weight.grad, g["d_pre_weight"]) < 5 * TOL and rel_err(pre.bias.grad, g["d_pre_bias"]) < 5 * TOL
+    final = tuple(hidden)
+    assert torch.equal(final[0].cpu(), g["final"][0]) and torch.equal(final[1].cpu(), g["final"][1].float())
+    assert torch.equal(final[3].cpu(), g["final"][3])
