@@ -858,7 +858,10 @@ def run_workload(ctx, workload, K, W, args, batch=None):
         "roofline": {"bound": "hbm" if bound == "hbm" else "tensor", "achieved": achieved, "peak": peak, "unit": unit,
                      "frac": achieved / peak, "traffic": traffic, "peak_source": pk_kind if unit == "GB/s"
                      else pk_kind + " bf16 dense / 2 = tf32 dense; achieved counts the 3 tf32 MMAs of every 3xTF32 product",
-                     "kernel": r["kernel_name"], "kernel_ms": kern_ms, "algorithmic_per_launch": algo},
+                     "kernel": r["kernel_name"], "kernel_ms": kern_ms, "algorithmic_per_launch": algo,
+                     "note": "achieved = algorithmic bytes of ONE step / kernel_ms, kernel_ms = duration of the timed launch(es) / "
+                             "steps (a multi-step launch walks all K steps: per-launch figures are these times K); traffic "
+                             "is per step as well"},
     }
     for k in ("per_call", "host_us_per_call"):
         if k in r:

@@ -475,7 +475,14 @@ class DenseGCM(torch.nn.Module):
                 if state.raw is None or state.pre_key != pkey:
                     state = None                 # forward() rebuilds the preprocessed log under the new weights
             rest_raw = x_seq[:, start:]
-            rest = rest_raw if pre is None else (pre(rest_raw) if state is not None else None)
+            rest = rest_raw
+            if pre is not None:
+                rest = None
+                if state is not None:
+                    # map the observations in the layout they came in: a time-major caller ([T, B, F] behind this
+                    # transposed view) gets time-major images, i.e. contiguous rows per step for the kernels
+                    tm = rest_raw.transpose(0, 1)
+                    rest = pre(tm).transpose(0, 1) if tm.is_contiguous() else pre(rest_raw)
             if (state is None or self._plan is not plan or rest.dtype != torch.float32
                     or not temporal.sequence_supported(plan, state, rest)):
                 outs = [] if out0 is None else [out0]
