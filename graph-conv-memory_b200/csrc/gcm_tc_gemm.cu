@@ -13,6 +13,7 @@
 // accumulator is read back with tcgen05.ld.  Two groups of four warps alternate tiles / row chunks so that the
 // loads of one overlap the MMA + epilogue of the other; a ninth warp only issues MMAs.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "gcm_common.cuh"
 #include "gcm_tc.cuh"
@@ -219,6 +220,7 @@ struct LinearTc32Args {
   int32_t* status;
   long long tiles;
   uint32_t tmem_cols;   // power of two >= 2 K1 + K2 / 2 + Ho
+  int stage;            // 1: the 128 x K1 row tile and the 128 x Ho result tile go through shared memory (K1 <= 64, no X2)
 };
 
 constexpr int TC32_THREADS = 288;   // warps 0-3: A rows -> TMEM, epilogue; warps 4-8: weight staging; warp 8 lane 0: MMA issue
@@ -234,6 +236,9 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
   uint64_t* wready = bars + 1;   // weights are in shared memory (160 arrivals, once)
   uint64_t* done = bars + 2;     // all MMAs of the current tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  // staging tile (a.stage): rows padded by 4 floats so that a thread reading ITS row with 16-byte loads is conflict-free
+  float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 64);
+  const int tile_ld = (K1 > Ho ? K1 : Ho) + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     tc::mbar_init(full, 128);
@@ -256,11 +261,38 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
       const long long r = (blockIdx.x + it * gridDim.x) * 128 + tid;
       const bool ok = r < a.rows;
       const float4* x1 = reinterpret_cast<const float4*>(a.X1 + (ok ? r : 0) * a.ldx1);
+      if (a.stage) {
+        // Coalesced staging: consecutive threads copy consecutive 16-byte chunks of the tile's rows (a warp instruction
+        // covers whole rows) with cp.async, then every thread reads ITS row from shared memory.  The row-per-thread
+        // global loads of the other branch touch 32 different lines per warp instruction and were the limiter of the
+        // narrow products (K1 = 64 -> Ho = 32: 1.7 TB/s, profiles/c2_bptt_kernels_r2.md).
+        const long long r0 = (blockIdx.x + it * gridDim.x) * 128;
+        const int cpr = K1 >> 2;                     // 16-byte chunks per row
+        for (int c = tid; c < 128 * cpr; c += 128) {
+          const int row = c / cpr, c4 = c - row * cpr;
+          float* dst = tile + row * tile_ld + c4 * 4;
+          if (r0 + row < a.rows) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst)),
+                         "l"(a.X1 + (r0 + row) * a.ldx1 + c4 * 4) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       for (int k0 = 0; k0 < K1; k0 += 64) {        // 16 independent 16-byte loads in flight per thread
         float4 v[16];
+        if (a.stage) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = (ok && k0 + 4 * j < K1) ? __ldg(x1 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 16; ++j)
+            v[j] = (k0 + 4 * j < K1) ? *reinterpret_cast<const float4*>(tile + tid * tile_ld + k0 + 4 * j)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = (ok && k0 + 4 * j < K1) ? __ldg(x1 + (k0 >> 2) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (k0 + 16 * c < K1) {
@@ -319,10 +351,29 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) bad |= !isfinite(f[j]);
+        }
+        if (a.stage) {
+          // (every thread has read its input row long ago: the MMAs that consumed it have completed)
+          float4* o = reinterpret_cast<float4*>(tile + tid * tile_ld + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else if (ok) {
           float4* o = reinterpret_cast<float4*>(a.out + r * a.ldo + n0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
+      }
+      if (a.stage) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const long long r0 = (blockIdx.x + it * gridDim.x) * 128;
+        const int cpr = Ho >> 2;
+        for (int c = tid; c < 128 * cpr; c += 128) {     // coalesced 16-byte stores of the result tile
+          const int row = c / cpr, c4 = c - row * cpr;
+          if (r0 + row < a.rows)
+            *reinterpret_cast<float4*>(a.out + (r0 + row) * a.ldo + c4 * 4) =
+                *reinterpret_cast<const float4*>(tile + row * tile_ld + c4 * 4);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the tile buffer is reused by the next tile's staging
       }
       tc::fence_before_sync();   // the accumulator and the A columns are free again: the next tile may overwrite them
     }
@@ -538,31 +589,35 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
         tc::fence_after_sync();
       }
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {                                // 16 rows (k) at a time
-        const long long rq = r0 + q * 16;
+      for (int q2 = 0; q2 < 2; ++q2) {                             // 32 rows (k) at a time: 64 loads in flight per thread
+        const long long rq = r0 + q2 * 32;
         const float* pa = a.A + rq * a.lda + ch;
         const float* px = a.X + rq * a.ldx + ch;
-        float av[16], xv[16];
-        const bool whole = rq + 16 <= r_end;
+        float av[32], xv[32];
+        const bool whole = rq + 32 <= r_end;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) av[u] = (a_ok && (whole || rq + u < r_end)) ? __ldcs(pa + u * a.lda) : 0.0f;
+        for (int u = 0; u < 32; ++u) av[u] = (a_ok && (whole || rq + u < r_end)) ? __ldcs(pa + u * a.lda) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) xv[u] = (x_ok && (whole || rq + u < r_end)) ? __ldcs(px + u * a.ldx) : 0.0f;
-        uint32_t hi[16], lo[16];
+        for (int u = 0; u < 32; ++u) xv[u] = (x_ok && (whole || rq + u < r_end)) ? __ldcs(px + u * a.ldx) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          colsum += av[u];
-          tc::split_tf32(av[u], hi[u], lo[u]);
-        }
-        tc::tmem_st16(lane_addr + col_a + q * 16, hi);
-        tc::tmem_st16(lane_addr + col_a + 64 + q * 16, lo);
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int q = q2 * 2 + h2;
+          uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {   // 4 rows (k) of channel ch -> one 16-byte core-matrix row, hi and lo
-          uint32_t h[4], l[4];
+          for (int u = 0; u < 16; ++u) {
+            colsum += av[h2 * 16 + u];
+            tc::split_tf32(av[h2 * 16 + u], hi[u], lo[u]);
+          }
+          tc::tmem_st16(lane_addr + col_a + q * 16, hi);
+          tc::tmem_st16(lane_addr + col_a + 64 + q * 16, lo);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) tc::split_tf32(xv[s4 * 4 + u], h[u], l[u]);
-          *reinterpret_cast<uint4*>(bhi + (q * 4 + s4) * 32) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(blo + (q * 4 + s4) * 32) = make_uint4(l[0], l[1], l[2], l[3]);
+          for (int s4 = 0; s4 < 4; ++s4) {   // 4 rows (k) of channel ch -> one 16-byte core-matrix row, hi and lo
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) tc::split_tf32(xv[h2 * 16 + s4 * 4 + u], h[u], l[u]);
+            *reinterpret_cast<uint4*>(bhi + (q * 4 + s4) * 32) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(blo + (q * 4 + s4) * 32) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       tc::wait_st();
@@ -665,13 +720,17 @@ extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const fl
                 reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
               "linear_tc32: operands must be 16-byte aligned");
   if (rows == 0) return GCM_OK;
-  LinearTc32Args a{X1, ldx1, K1, W1, X2, ldx2, X2 ? K2 : 0, W2, bias, act, rows, Ho, out, ldo, status, (rows + 127) / 128, 32};
+  LinearTc32Args a{X1, ldx1, K1, W1, X2, ldx2, X2 ? K2 : 0, W2, bias, act, rows, Ho, out, ldo, status, (rows + 127) / 128, 32, 0};
   const uint32_t need_cols = (uint32_t)(2 * K1 + a.K2 / 2 + Ho);
   while (a.tmem_cols < need_cols) a.tmem_cols <<= 1;
-  const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64;
+  // narrow streaming products (many rows, K1 <= 64, Ho <= 64): row / result tiles staged through shared memory
+  static const bool no_stage = getenv("GCM_B200_NO_LINEAR_STAGE") != nullptr;
+  a.stage = (!X2 && K1 <= 64 && Ho <= 64 && rows >= 4096 && !no_stage) ? 1 : 0;
+  const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64 + 64 +
+                      (a.stage ? (size_t)128 * ((K1 > Ho ? K1 : Ho) + 4) * 4 : 0);
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(k_linear_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 10 + 64) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_linear_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 10 + 256) != cudaSuccess) {
       gcm_set_error("linear_tc32: cannot raise the dynamic shared memory limit");
       return GCM_ERR_CUDA;
     }
