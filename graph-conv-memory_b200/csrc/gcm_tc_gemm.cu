@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
         // global loads of the other branch touch 32 different lines per warp instruction and were the limiter of the
         // narrow products (K1 = 64 -> Ho = 32: 1.7 TB/s, profiles/c2_bptt_kernels_r2.md).
         const long long r0 = (blockIdx.x + it * gridDim.x) * 128;
-        const int cpr = K1 >> 2;                     // 16-byte chunks per row
+        const int cpr = K1 >> 2, csh = __ffs(cpr) - 1;   // 16-byte chunks per row (a power of two on this path)
         for (int c = tid; c < 128 * cpr; c += 128) {
-          const int row = c / cpr, c4 = c - row * cpr;
+          const int row = c >> csh, c4 = c & (cpr - 1);
           float* dst = tile + row * tile_ld + c4 * 4;
           if (r0 + row < a.rows) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(dst)),
@@ -366,9 +366,9 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
       if (a.stage) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const long long r0 = (blockIdx.x + it * gridDim.x) * 128;
-        const int cpr = Ho >> 2;
+        const int cpr = Ho >> 2, csh = __ffs(cpr) - 1;
         for (int c = tid; c < 128 * cpr; c += 128) {     // coalesced 16-byte stores of the result tile
-          const int row = c / cpr, c4 = c - row * cpr;
+          const int row = c >> csh, c4 = c & (cpr - 1);
           if (r0 + row < a.rows)
             *reinterpret_cast<float4*>(a.out + (r0 + row) * a.ldo + c4 * 4) =
                 *reinterpret_cast<const float4*>(tile + row * tile_ld + c4 * 4);
@@ -725,7 +725,7 @@ extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const fl
   while (a.tmem_cols < need_cols) a.tmem_cols <<= 1;
   // narrow streaming products (many rows, K1 <= 64, Ho <= 64): row / result tiles staged through shared memory
   static const bool no_stage = getenv("GCM_B200_NO_LINEAR_STAGE") != nullptr;
-  a.stage = (!X2 && K1 <= 64 && Ho <= 64 && rows >= 4096 && !no_stage) ? 1 : 0;
+  a.stage = (!X2 && K1 <= 64 && Ho <= 64 && (K1 & (K1 - 1)) == 0 && (Ho & (Ho - 1)) == 0 && rows >= 4096 && !no_stage) ? 1 : 0;
   const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64 + 64 +
                       (a.stage ? (size_t)128 * ((K1 > Ho ? K1 : Ho) + 4) * 4 : 0);
   static bool attr_done = false;
