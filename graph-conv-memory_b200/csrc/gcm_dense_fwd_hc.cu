@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
       const bool live = lane < gt;
       float* st_base = stages + (size_t)slot * HC_Q * gs;
       const float* mine = st_base + (size_t)lane * gs;
-      const float* obs_t = a.obs + (long long)t * a.obs_stride_t;
       int cnt = 0, lt = 0;
 
       if (has) {

@@ -314,7 +314,7 @@ class DenseGCM(torch.nn.Module):
             DenseGCM.did_warn = True
 
         xc = x.contiguous()
-        if plan.needs_euclid:
+        if plan.needs_euclid and not (plan.ones and state.dense_ok):
             state.__dict__["_euclid_cur_all"] = self._all_current_obs(xc)
         if plan.ones and state.dense_ok and not ingest_grad and (token is None or getattr(token, "_gcm_ones", False)):
             # DenseEdge-only state: implicit all-ones adjacency, per-node cache (gcm.ones)

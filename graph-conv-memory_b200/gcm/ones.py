@@ -85,8 +85,15 @@ def _outer_tc(a, x, dw, db=None, fn="gcm_outer_reduce_tc"):
 
 
 def plan_supports(plan) -> bool:
+    """A selector chain that CONTAINS a DenseEdge builds the all-ones valid block whatever else is chained with it:
+    DenseEdge links every new node to every node of the window in both directions, with self loops
+    (edge_selectors/dense.py:16-21), and the other selectors only ever OR in edges between valid nodes (SURVEY.md
+    checklist item 8), so their edges are already there.  Such chains take this path too (the distance selectors of the
+    chain are not even evaluated: they cannot change the adjacency)."""
     g = plan.gnn
-    return (bool(plan.sels) and all(s.kind == _cabi.SEL_DENSE for s in plan.sels)
+    known = (_cabi.SEL_TEMPORAL, _cabi.SEL_DENSE, _cabi.SEL_EUCLIDEAN, _cabi.SEL_COSINE, _cabi.SEL_SPATIAL)
+    return (bool(plan.sels) and any(s.kind == _cabi.SEL_DENSE for s in plan.sels)
+            and all(s.kind in known for s in plan.sels)
             and max(g.F, g.H1, g.H2) <= 128 and g.F % 4 == 0 and g.H1 % 4 == 0)
 
 

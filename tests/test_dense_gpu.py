@@ -59,6 +59,9 @@ SEEDED = [
     (5, 40, 16, 32, 50, [("temporal", (1, 3), "both")]),
     (4, 33, 20, 24, 70, [("temporal", (2, 5), "backward"), ("temporal", (1,), "forward")]),
     (3, 64, 48, 40, 70, [("dense",)]),
+    # DenseEdge chained with other selectors is still the all-ones block: the DenseEdge kernels serve it
+    (3, 24, 16, 32, 40, [("temporal", (1, 2), "forward"), ("dense",)]),
+    (3, 20, 16, 16, 30, [("dense",), ("temporal", (1, 3), "both"), ("cosine", 0.5)]),
     (2, 256, 128, 128, 12, [("dense",)]),                              # BASELINE cfg 3 shape (fp32 path)
     (6, 96, 64, 64, 100, [("cosine", 0.5)]),                           # BASELINE cfg 4 shape, reduced N
     (6, 96, 64, 64, 100, [("euclidean", 2.0)]),
@@ -115,6 +118,9 @@ def test_fused_matches_oracle_seeded(B, N, F, H, T, spec):
     if tc_euclid:
         _cabi.lib().gcm_euclid_batchmean_tc = real
         assert seen == {"tc"}, "the tensor-core distance kernel should have served this batch size"
+    if len(spec) > 1 and any(s[0] == "dense" for s in spec):
+        assert mod.fused_plan().ones and hidden.claim().dense_ok and hidden.claim().masks_stale, \
+            "a chain that contains DenseEdge should run on the DenseEdge (implicit all-ones) kernels"
     if distance:
         # the edge set depends on a float comparison: the inputs must keep a margin
         kind = spec[0][0]

@@ -43,6 +43,7 @@ SEEDED = [
     (3, 10, 20, 12, 14, [("dense",)], ("tanh", "relu")),                           # wraps, complement trick off
     (2, 40, 16, 24, 30, [("dense",)], ("tanh", "tanh")),                           # nR > 16: complement trick on
     (3, 24, 12, 10, 30, [("cosine", 0.5)], ("tanh", "tanh")),
+    (3, 12, 16, 16, 18, [("temporal", (1, 2), "forward"), ("dense",)], ("tanh", "tanh")),   # chain with DenseEdge: ones path
     (3, 9, 70, 40, 6, [("temporal", (2,), "backward"), ("temporal", (1,), "forward")], ("relu", "none")),
 ]
 
