@@ -882,6 +882,17 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
   return gcm_check_launch("k_sparse_edges");
 }
 
+int gcm_graphconv_fwd_tc(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew, const int64_t* rows,
+                         int64_t m, int Fin, int Fout, const float* wt, const float* bias, int act, float* agg_out,
+                         float* out, cudaStream_t stream, int64_t x_rows);
+static int64_t g_graphconv_x_rows = 0;
+// Rows of x for the next gcm_sparse_graphconv_fwd call of this thread that evaluates a row SUBSET (the tensor-core kernel
+// addresses x with 32-bit offsets and must know that column * Fin fits); 0 = unknown.
+extern "C" int gcm_sparse_graphconv_hint_rows(long long n) {
+  g_graphconv_x_rows = n;
+  return GCM_OK;
+}
+
 extern "C" int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew,
                                         const int64_t* rows, int64_t m, int Fin, int Fout, const float* wt,
                                         const float* bias, int act, float* agg_out, float* out, void* stream) {
@@ -889,6 +900,14 @@ extern "C" int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, c
   GCM_REQUIRE(Fin >= 1 && Fin <= 128 && Fout >= 1 && Fout <= 128, "sparse_graphconv_fwd: Fin=%d Fout=%d outside [1,128]",
               Fin, Fout);
   if (m == 0) return GCM_OK;
+  {
+    // the per-tile product on the tensor cores (3xTF32) for Fin in {32, 64} (gcm_sparse_tc.cu); same gathers, same sums
+    const int64_t hint = g_graphconv_x_rows;
+    g_graphconv_x_rows = 0;
+    const int rc = gcm_graphconv_fwd_tc(x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out,
+                                        (cudaStream_t)stream, hint);
+    if (rc != GCM_ERR_UNSUPPORTED) return rc;
+  }
   GraphConvFwdArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out};
   const size_t smem = ((size_t)2 * Fin * GC_AS + (size_t)GC_KC * 16 * ((Fout + 15) / 16 <= 1 ? 1 : ((Fout + 15) / 16 <= 2 ? 2 : ((Fout + 15) / 16 <= 4 ? 4 : 8)))) * 4;
   const int64_t grid = (m + GC_TM - 1) / GC_TM;

@@ -1,0 +1,326 @@
+// GraphConv forward with the per-tile product on the tensor cores (tcgen05 + TMEM, 3xTF32), sm_100a.
+//
+// torch_geometric.nn.GraphConv (call sites ray_sparse_gcm.py:37-40, invoked at sparse_gcm.py:178,199):
+//   out_i = act(W_rel (sum_{(j->i) in E} w_ji x_j) + b + W_root x_i)
+// k_graphconv_fwd (gcm_sparse.cu) gathers a 64-row tile into shared memory and multiplies it by the weight pack on the
+// CUDA cores; ncu had it issue-bound with that [64 x 2Fin] x [2Fin x Fout] product as half of its instructions
+// (profiles/c4_c5_kernels_r1.md).  Here the product leaves the instruction stream:
+//   warps 0-23  gather: warp per row, a lane owns Fin/32 contiguous features (one coalesced warp load per neighbour row),
+//               32-bit column indices fetched 32 at a time and broadcast by shuffle, 8 gathers in flight per warp, summed
+//               in edge order (the SAME order as the CUDA-core kernel), then write [agg | x_i] of the row, split hi / lo
+//               (3xTF32), into the
+//               A tile [128 x 2Fin] in shared memory in the canonical K-major core-matrix layout, with the leading-byte
+//               offset padded to 144 B so that the per-row stores do not pile onto four banks
+//   warp 28     one lane issues, per 128-row tile, lo*Whi + hi*Wlo + hi*Whi as SS-form tcgen05.mma.kind::tf32 (A and the
+//               weight pack both in shared memory) into one of two accumulators in TMEM
+//   warps 24-27 epilogue of the PREVIOUS tile (tcgen05.ld, bias, activation, row stores) while the gather warps already
+//               fill the A tile of the next one (the A tile is free as soon as the tile's MMAs have completed)
+// Persistent: one CTA per SM walks the tiles.  fp32-accurate (tests/test_sparse_gpu.py compares with the CUDA-core kernel).
+#include <stdlib.h>
+
+#include "gcm_common.cuh"
+#include "gcm_tc.cuh"
+
+namespace {
+
+constexpr int GT_TM = 128;                 // rows per tile (M of the MMA)
+constexpr int GT_GATHER_WARPS = 24;             // memory-level parallelism of the gathers: 8 warps per SM ran at half the speed of the CUDA-core kernel (5 CTAs x 8 warps)
+constexpr int GT_THREADS = (GT_GATHER_WARPS + 4 + 1) * 32;
+constexpr int GT_LBO = 144;                // bytes between core matrices along K in the A tile (128 + 16 padding)
+
+struct GcTcArgs {
+  const float* x;
+  const int64_t* rowptr;
+  const int64_t* col;
+  const float* ew;
+  const int64_t* rows;
+  int64_t m;
+  int Fin, Fout;
+  const float* wt;      // [2 Fin, Fout] K-major pack: wt[k * Fout + n]
+  const float* bias;
+  int act;
+  float* agg_out;
+  float* out;
+  int64_t tiles;
+};
+
+// Warp per row, a lane owns V = Fin / 32 contiguous features (one coalesced warp load per neighbour row).  Column indices
+// come 32 at a time (one coalesced load) and are narrowed to 32 bits: the shuffle that broadcasts one is a single
+// instruction and the row address is ONE IMAD.WIDE (the int64 version spent 2 shuffles + an emulated 64-bit multiply per
+// gather; ncu: 1.8 G warp instructions per layer at cfg5, 22 per edge).  Every batch of 8 gathers is issued in full with
+// out-of-range slots predicated off, so there is no serial tail.  Sums run in edge order, like the CUDA-core kernel's.
+// (Tried and measured slower: half-warp per row, two rows per warp, float4 per lane: 5.4 ms per layer against 4.8.)
+template <int V>
+__device__ __forceinline__ void gt_ld(const float* p, float (&v)[V]) {
+  if (V == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1 % V] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void gt_gather(const GcTcArgs& a, int64_t i, int64_t e0, int64_t e1, int lane, float (&acc)[V],
+                                          float (&own)[V]) {
+  constexpr int Fin = 32 * V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+  const float* xl = a.x + lane * V;
+  gt_ld<V>(xl + i * Fin, own);
+  for (int64_t base = e0; base < e1; base += 32) {
+    const int cnt = (int)min((int64_t)32, e1 - base);
+    const unsigned my = lane < cnt ? (unsigned)a.col[base + lane] : 0u;     // host: every column * Fin fits 32 bits
+    const float myw = (a.ew && lane < cnt) ? a.ew[base + lane] : 1.0f;
+    int u = 0;
+    for (; u + 8 <= cnt; u += 8) {
+      float v[8][V];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) gt_ld<V>(xl + (size_t)(__shfl_sync(GCM_FULL_MASK, my, u + q) * (unsigned)Fin), v[q]);
+      if (a.ew) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float w = __shfl_sync(GCM_FULL_MASK, myw, u + q);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[q][j] *= w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += v[q][j];
+    }
+    if (u < cnt) {
+      // the last cnt % 8 edges of the batch: all loads first (no-ops beyond cnt), then the sums in edge order
+      float v[7][V];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[q][j] = 0.0f;
+        const unsigned c = __shfl_sync(GCM_FULL_MASK, my, (u + q) & 31);
+        if (u + q < cnt) gt_ld<V>(xl + (size_t)(c * (unsigned)Fin), v[q]);
+      }
+      if (a.ew) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const float w = __shfl_sync(GCM_FULL_MASK, myw, (u + q) & 31);
+#pragma unroll
+          for (int j = 0; j < V; ++j) v[q][j] *= w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 7; ++q)
+        if (u + q < cnt) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += v[q][j];
+        }
+    }
+  }
+}
+
+// float offset of element (row r, k) of the padded K-major A tile with K columns
+__device__ __forceinline__ int gt_a_off(int r, int k, int K) {
+  return (r >> 3) * ((K >> 2) * (GT_LBO / 4)) + (k >> 2) * (GT_LBO / 4) + (r & 7) * 4 + (k & 3);
+}
+
+template <int V>
+__global__ void __launch_bounds__(GT_THREADS, 1) k_graphconv_fwd_tc(const GcTcArgs a) {
+  constexpr int Fin = 32 * V, K = 2 * Fin;
+  extern __shared__ __align__(128) unsigned char gt_smem[];
+  const int Fout = a.Fout;
+  const int a_floats = (GT_TM / 8) * (K / 4) * (GT_LBO / 4);
+  float* Ahi = reinterpret_cast<float*>(gt_smem);
+  float* Alo = Ahi + a_floats;
+  float* Whi = Alo + a_floats;                       // [Fout x K] canonical K-major (unpadded)
+  float* Wlo = Whi + (size_t)Fout * K;
+  float* bias_s = Wlo + (size_t)Fout * K;            // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 128);
+  uint64_t* a_full = bars;            // gather warps -> MMA warp (one arrival per gather warp)
+  uint64_t* mma_done = bars + 1;      // [2]  MMA warp -> epilogue warps and gather warps (A tile free)
+  uint64_t* d_free = bars + 3;        // [2]  epilogue warps -> MMA warp (accumulator free)
+  uint64_t* w_ready = bars + 5;       // weights staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t d_cols = Fout <= 32 ? 32u : (Fout <= 64 ? 64u : 128u);
+  const uint32_t tmem_cols = 2 * d_cols < 32 ? 32u : 2 * d_cols;
+
+  if (tid == 0) {
+    tc::mbar_init(a_full, GT_GATHER_WARPS);
+    tc::mbar_init(mma_done + 0, 1);
+    tc::mbar_init(mma_done + 1, 1);
+    tc::mbar_init(d_free + 0, 128);
+    tc::mbar_init(d_free + 1, 128);
+    tc::mbar_init(w_ready, 5 * 32);
+    tc::mbar_fence_init();
+  }
+  if (warp == GT_GATHER_WARPS + 4) tc::tmem_alloc(tmem_slot, tmem_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int64_t n_it = (a.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp < GT_GATHER_WARPS) {
+    // =============================== gather ===============================
+    for (int64_t it = 0; it < n_it; ++it) {
+      const int64_t row0 = (blockIdx.x + it * gridDim.x) * GT_TM;
+      if (it > 0) {
+        // the MMAs that read the A tile of the previous tile have completed
+        tc::mbar_wait(mma_done + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
+      }
+      for (int r = warp; r < GT_TM; r += GT_GATHER_WARPS) {
+        const int64_t li = row0 + r;
+        float acc[V], own[V];
+        if (li < a.m) {
+          const int64_t i = a.rows ? a.rows[li] : li;
+          gt_gather<V>(a, i, a.rowptr[i], a.rowptr[i + 1], lane, acc, own);
+          if (a.agg_out) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) a.agg_out[li * Fin + lane * V + j] = acc[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] = own[j] = 0.0f;
+        }
+        uint32_t ah[V], al[V], oh[V], ol[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          tc::split_tf32(acc[j], ah[j], al[j]);
+          tc::split_tf32(own[j], oh[j], ol[j]);
+        }
+        const int o_agg = gt_a_off(r, lane * V, K), o_own = gt_a_off(r, Fin + lane * V, K);
+        if (V == 2) {
+          *reinterpret_cast<uint2*>(Ahi + o_agg) = make_uint2(ah[0], ah[1 % V]);
+          *reinterpret_cast<uint2*>(Alo + o_agg) = make_uint2(al[0], al[1 % V]);
+          *reinterpret_cast<uint2*>(Ahi + o_own) = make_uint2(oh[0], oh[1 % V]);
+          *reinterpret_cast<uint2*>(Alo + o_own) = make_uint2(ol[0], ol[1 % V]);
+        } else {
+          Ahi[o_agg] = __uint_as_float(ah[0]); Alo[o_agg] = __uint_as_float(al[0]);
+          Ahi[o_own] = __uint_as_float(oh[0]); Alo[o_own] = __uint_as_float(ol[0]);
+        }
+      }
+      tc::fence_proxy_async();          // the tensor core reads the tile through the async proxy
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a_full);
+    }
+  } else {
+    // ---- weight pack -> canonical K-major B operand, split hi / lo (warps 8-12, once) ----
+    const int t5 = tid - GT_GATHER_WARPS * 32;
+    for (int i = t5; i < Fout * K; i += 5 * 32) {
+      const int k = i / Fout, n = i - k * Fout;            // wt[k * Fout + n]: coalesced reads
+      uint32_t hi, lo;
+      tc::split_tf32(__ldg(a.wt + i), hi, lo);
+      Whi[tc::kmajor_off(n, k, K)] = __uint_as_float(hi);
+      Wlo[tc::kmajor_off(n, k, K)] = __uint_as_float(lo);
+    }
+    for (int i = t5; i < 128; i += 5 * 32) bias_s[i] = (a.bias && i < Fout) ? __ldg(a.bias + i) : 0.0f;
+    tc::fence_proxy_async();
+    tc::mbar_arrive(w_ready);
+    tc::mbar_wait(w_ready, 0);
+
+    if (warp == GT_GATHER_WARPS + 4) {
+      // =============================== MMA issue ===============================
+      if (lane == 0) {
+        const uint32_t idesc = tc::idesc_tf32(GT_TM, Fout);
+        const uint32_t a_sbo = (uint32_t)(K / 4) * GT_LBO, b_sbo = (uint32_t)(K / 4) * 128u;
+        const uint32_t ahi = tc::smem_u32(Ahi), alo = tc::smem_u32(Alo), whi = tc::smem_u32(Whi), wlo = tc::smem_u32(Wlo);
+        for (int64_t it = 0; it < n_it; ++it) {
+          const int buf = (int)(it & 1);
+          tc::mbar_wait(a_full, (uint32_t)(it & 1));
+          tc::mbar_wait(d_free + buf, (uint32_t)(((it >> 1) & 1) ^ 1));     // the epilogue of tile it - 2 has read it
+          tc::fence_after_sync();
+          const uint32_t d = tbase + buf * d_cols;
+          bool accum = false;
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {           // lo*Whi, hi*Wlo, hi*Whi
+            const uint32_t asm_ = pass == 0 ? alo : ahi;
+            const uint32_t bsm = pass == 1 ? wlo : whi;
+            for (int ks = 0; ks < K / 8; ++ks) {
+              tc::mma_tf32_ss(d, tc::smem_desc_kmajor(asm_ + ks * 2 * GT_LBO, GT_LBO, a_sbo),
+                              tc::smem_desc_kmajor(bsm + ks * 256, 128, b_sbo), idesc, accum);
+              accum = true;
+            }
+          }
+          tc::mma_commit(mma_done + buf);
+        }
+      }
+    } else {
+      // =============================== epilogue ===============================
+      const int q = warp - GT_GATHER_WARPS;                 // TMEM lane quadrant
+      const int r = q * 32 + lane;
+      const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
+      const int act = a.act;
+      for (int64_t it = 0; it < n_it; ++it) {
+        const int buf = (int)(it & 1);
+        const int64_t li = (blockIdx.x + it * gridDim.x) * GT_TM + r;
+        tc::mbar_wait(mma_done + buf, (uint32_t)((it >> 1) & 1));
+        tc::fence_after_sync();
+        for (int n0 = 0; n0 < Fout; n0 += 16) {
+          uint32_t dv[16];
+          tc::tmem_ld16(lane_addr + buf * d_cols + n0, dv);
+          tc::wait_ld();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(dv[j]) + bias_s[n0 + j];
+          gcm_act_fast_vec(f, act);
+          if (li < a.m) {
+            float4* o = reinterpret_cast<float4*>(a.out + li * Fout + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        }
+        tc::fence_before_sync();
+        tc::mbar_arrive(d_free + buf);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == GT_GATHER_WARPS + 4) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tbase, tmem_cols);
+  }
+}
+
+}  // namespace
+
+static int g_graphconv_kernel = GCM_GC_AUTO;
+extern "C" int gcm_set_graphconv_kernel(int which) {
+  GCM_REQUIRE(which >= GCM_GC_AUTO && which <= GCM_GC_TC, "set_graphconv_kernel: bad variant %d", which);
+  g_graphconv_kernel = which;
+  return GCM_OK;
+}
+
+// returns GCM_ERR_UNSUPPORTED (nothing launched) when the shape is not covered: the caller then runs k_graphconv_fwd
+int gcm_graphconv_fwd_tc(const float* x, const int64_t* rowptr, const int64_t* col, const float* ew, const int64_t* rows,
+                         int64_t m, int Fin, int Fout, const float* wt, const float* bias, int act, float* agg_out,
+                         float* out, cudaStream_t stream, int64_t x_rows) {
+  static const bool off = getenv("GCM_B200_GRAPHCONV_CUDA_CORES") != nullptr;     // A/B switch
+  if (off || g_graphconv_kernel == GCM_GC_CUDA_CORES) return GCM_ERR_UNSUPPORTED;
+  if (!(Fin == 32 || Fin == 64) || Fout < 16 || Fout > 128 || (Fout & 15) != 0) return GCM_ERR_UNSUPPORTED;
+  if (m < 4 * GT_TM && g_graphconv_kernel != GCM_GC_TC) return GCM_ERR_UNSUPPORTED;     // small calls: not worth a persistent CTA
+  // the gathers address x with 32-bit element offsets (column * Fin): the number of rows of x is only known here when
+  // every row is evaluated (rows == NULL: m == n); a row subset goes to the CUDA-core kernel unless the caller vouches
+  if (x_rows <= 0) x_rows = rows ? 0 : m;
+  if (x_rows <= 0 || (unsigned long long)x_rows * (unsigned long long)Fin >= (1ull << 32)) return GCM_ERR_UNSUPPORTED;
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return GCM_ERR_UNSUPPORTED;
+  const int K = 2 * Fin;
+  const size_t a_bytes = (size_t)(GT_TM / 8) * (K / 4) * GT_LBO;
+  const size_t smem = 2 * a_bytes + (size_t)2 * Fout * K * 4 + 128 * 4 + 64 + 128;
+  if (smem > 227 * 1024) return GCM_ERR_UNSUPPORTED;
+  GcTcArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out, (m + GT_TM - 1) / GT_TM};
+  long long grid = gcm_num_sms();
+  if (grid > a.tiles) grid = a.tiles;
+  cudaError_t e;
+  if (Fin == 64) {
+    e = cudaFuncSetAttribute(k_graphconv_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_graphconv_fwd_tc<2><<<(unsigned)grid, GT_THREADS, smem, stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_graphconv_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) k_graphconv_fwd_tc<1><<<(unsigned)grid, GT_THREADS, smem, stream>>>(a);
+  }
+  if (e != cudaSuccess) {
+    gcm_set_error("cudaFuncSetAttribute(graphconv_fwd_tc): %s", cudaGetErrorString(e));
+    return GCM_ERR_CUDA;
+  }
+  return gcm_check_launch("k_graphconv_fwd_tc");
+}

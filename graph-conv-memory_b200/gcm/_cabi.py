@@ -31,6 +31,7 @@ ACT = {"none": 0, "tanh": 1, "relu": 2}
 ACT_EXP2X = 3          # gcm_linear2 epilogue only: exp(2 clamp(z)), the tanh form of the ones path cache
 TK_AUTO, TK_HC, TK_TC, TK_WIN, TK_ROWS = range(5)
 EB_AUTO, EB_PAIRS, EB_HASH = range(3)
+GC_AUTO, GC_CUDA_CORES, GC_TC = range(3)
 STEP_PURE_TEMPORAL = 1
 STEP_UNIFORM_COUNT = 2
 STEP_HCACHE_VALID = 4
@@ -145,6 +146,8 @@ _SIGNATURES = {
     "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),
     "gcm_dense_step_fwd_zc": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), C.POINTER(GnnC), _P, _P, _P, _P]),
     "gcm_set_edge_builder": (_I, [_I]),
+    "gcm_set_graphconv_kernel": (_I, [_I]),
+    "gcm_sparse_graphconv_hint_rows": (_I, [C.c_longlong]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_csr_transpose": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,

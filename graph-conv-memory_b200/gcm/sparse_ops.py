@@ -188,6 +188,7 @@ class _GraphConvFn(torch.autograd.Function):
         out = torch.empty(m, Fout, device=dev)
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
+        _cabi.lib().gcm_sparse_graphconv_hint_rows(n)
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
             x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), None, _cabi.ptr(rows), m, Fin, Fout,
             wt.data_ptr(), _cabi.ptr(b), act, _cabi.ptr(agg), out.data_ptr(), _cabi.stream_ptr(dev)),
@@ -237,6 +238,7 @@ def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none", ed
         out = torch.empty(m, w_rel.shape[0], device=x.device)
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
+        _cabi.lib().gcm_sparse_graphconv_hint_rows(x.shape[0])
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
             x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), edge_mask.data_ptr(), _cabi.ptr(rows), m, x.shape[1],
             w_rel.shape[0], wt.data_ptr(), _cabi.ptr(b), _cabi.ACT[act], None, out.data_ptr(),

@@ -418,6 +418,15 @@ int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, const int64_
                              const int64_t* rows, int64_t m, int Fin, int Fout, const float* wt,
                              const float* bias, int act, float* agg_out, float* out, void* stream);
 
+/* Which kernel runs the GraphConv forward (process-wide).  AUTO: the tensor-core kernel (csrc/gcm_sparse_tc.cu: same
+ * gathers, the [128 x 2 Fin] x [2 Fin x Fout] product of a tile in 3xTF32 on tcgen05) for Fin in {32, 64}, Fout a multiple
+ * of 16 and at least 512 rows, else the CUDA-core kernel.  The switch exists for parity tests and A/B profiling. */
+typedef enum gcm_graphconv_kernel { GCM_GC_AUTO = 0, GCM_GC_CUDA_CORES = 1, GCM_GC_TC = 2 } gcm_graphconv_kernel;
+int gcm_set_graphconv_kernel(int which);
+/* number of rows of x for the NEXT gcm_sparse_graphconv_fwd call that evaluates a row subset (`rows` != NULL): lets the
+ * tensor-core kernel, which addresses x with 32-bit offsets, take that call too; 0 / not called: unknown. */
+int gcm_sparse_graphconv_hint_rows(long long n);
+
 /* The transposed grouping the backward needs, for a block-diagonal graph: rowptr [n+1] / col [E] = CSR by sink over
  * the flat numbering, node_off [B+1] = first flat node of every graph (each graph has at most 8192 nodes and its
  * edges are contiguous); sink_local [E] (optional) = every edge's sink as an index inside its graph (row 1 of the

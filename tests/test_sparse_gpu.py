@@ -302,3 +302,66 @@ def test_pack_unpack_round_trip_at_scale_and_through_sparse_gcm():
             o, hid2 = mod(x2, taus2, hid)
         outs.append((o, hid2[1].coalesce().indices()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("F,H,act,use_rows,masked", [(64, 64, "tanh", False, False), (32, 32, "relu", False, False),
+                                                      (64, 32, "none", True, False), (32, 64, "tanh", True, True)])
+def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_rows, masked):
+    """k_graphconv_fwd_tc (tcgen05, 3xTF32, SS-form MMAs on a padded K-major tile) against k_graphconv_fwd (CUDA cores) and
+    the definition out = act(W_rel sum_j w_j x_j + b + W_root x_i), on a random block-diagonal causal graph: all rows /
+    a row subset, unit weights / a 0-1 edge mask, a ragged tail tile."""
+    from gcm import _cabi, sparse_ops
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(F + H)
+    n = 128 * 9 + 37
+    deg = torch.randint(0, 40, (n,), generator=gen)
+    deg[0] = 0
+    sink = torch.repeat_interleave(torch.arange(n), deg)
+    src = (torch.rand(sink.numel(), generator=gen) * sink.float()).long().clamp(max=n - 1)     # source < sink
+    order = torch.argsort(sink * n + src)
+    sink, src = sink[order], src[order]
+    csr = sparse_ops.Csr.from_sorted_edges(sink.to(dev), src.to(dev), n)
+    x = torch.randn(n, F, generator=gen).to(dev)
+    w_rel = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    w_root = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    bias = torch.randn(H, generator=gen).to(dev)
+    rows = torch.randperm(n, generator=gen)[: 128 * 5 + 11].sort().values.to(dev) if use_rows else None
+    mask = (torch.rand(sink.numel(), generator=gen) < 0.7).float().to(dev) if masked else None
+    outs = {}
+    try:
+        for which in (_cabi.GC_CUDA_CORES, _cabi.GC_TC):
+            lib.gcm_set_graphconv_kernel(which)
+            with torch.no_grad():
+                outs[which] = sparse_ops.graph_conv_csr(x, csr, rows, w_rel, bias, w_root, act, edge_mask=mask)
+            want = "k_graphconv_fwd_tc" if which == _cabi.GC_TC else "k_graphconv_fwd"
+            assert lib.gcm_last_kernel().decode() == want
+    finally:
+        lib.gcm_set_graphconv_kernel(_cabi.GC_AUTO)
+    w = torch.ones(sink.numel(), device=dev) if mask is None else mask
+    agg = torch.zeros(n, F, device=dev, dtype=torch.float64).index_add_(0, sink.to(dev), (x[src.to(dev)] * w[:, None]).double())
+    ref = agg @ w_rel.double().t() + bias.double() + x.double() @ w_root.double().t()
+    ref = {"tanh": torch.tanh, "relu": torch.relu, "none": lambda t: t}[act](ref)
+    if rows is not None:
+        ref = ref[rows]
+    a, b = outs[_cabi.GC_CUDA_CORES], outs[_cabi.GC_TC]
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((b.double() - ref).abs().max()) / scale < 2e-5
+    assert float((a - b).abs().max()) / scale < 1e-5
+    if mask is None:
+        # recording: the tensor-core forward also hands the aggregation to the backward; same gradients from both kernels
+        grads = {}
+        try:
+            for which in (_cabi.GC_CUDA_CORES, _cabi.GC_TC):
+                lib.gcm_set_graphconv_kernel(which)
+                xg = x.clone().requires_grad_(True)
+                wr, wo, bb = (t.clone().requires_grad_(True) for t in (w_rel, w_root, bias))
+                out = sparse_ops.graph_conv_csr(xg, csr, rows, wr, bb, wo, act)
+                (out * torch.linspace(-1, 1, out.numel(), device=dev).view_as(out)).sum().backward()
+                grads[which] = (xg.grad, wr.grad, wo.grad, bb.grad)
+        finally:
+            lib.gcm_set_graphconv_kernel(_cabi.GC_AUTO)
+        for ga, gb in zip(grads[_cabi.GC_CUDA_CORES], grads[_cabi.GC_TC]):
+            # sums of ~1200 signed terms of size ~1: the two forwards differ by ~1e-6, which the cancellation amplifies
+            assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
