@@ -106,6 +106,8 @@ _SIGNATURES = {
     "gcm_state_log_write_seq": (_I, [C.POINTER(DenseStateC), _P, _L, _L, _I, _P]),
     "gcm_temporal_gather": (_I, [C.POINTER(DenseStateC), _P, _I, _L, _I, _P, _P]),
     "gcm_temporal_shift_sum": (_I, [_P, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _P]),
+    "gcm_temporal_window_bwd_workspace": (_L, []),
+    "gcm_temporal_window_bwd": (_I, [_P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "gcm_set_temporal_kernel": (_I, [_I]),
     "gcm_dense_step_bwd": (_I, [C.POINTER(DenseStateC), _I, C.POINTER(GnnC), _P, _P, _P,
                                 C.POINTER(GnnGradsC), _P]),
@@ -196,6 +198,8 @@ def lib() -> C.CDLL:
     _lib = handle
     return handle
 
+
+ERR_UNSUPPORTED = -3
 
 _TRACE = bool(os.environ.get("GCM_B200_TRACE"))
 _trace_t = [0.0]

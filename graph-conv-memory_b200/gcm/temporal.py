@@ -16,6 +16,7 @@ Results are those of the step loop, launch for launch (tests/test_dense_gpu.py::
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -274,6 +275,44 @@ def _rows(plan, st, win, p_lo, p_hi, Kc):
     return A1, h, dz1
 
 
+_WB_WS = {}
+
+
+def _window_fused(plan, st, win, Kc, want_dz1=False):
+    """Both layers' row products and both weight-gradient reductions of the window in ONE kernel
+    (csrc/gcm_temporal_bwd_tc.cu) over the operand rows [sum x | x] and [sum dz2 | dz2] of the positions
+    P0 - max_hop .. P0 + Kc - 1.  Returns (grads dict, (first position, dz1 rows) or None), or None when the shape is not
+    the kernel's (F = H1 = H2 = 32) -- the caller then runs the separate products."""
+    g, dev = plan.gnn, st.device
+    if os.environ.get("GCM_B200_NO_WINDOW_BWD_TC") or st.F != 32 or g.H1 != 32 or g.H2 != 32:
+        return None
+    lib = _cabi.lib()
+    hops, nh = _hops(plan, dev)
+    wc = _wcat(plan, dev)
+    p_lo, p_hi = win.P0 - plan.max_hop, win.P0 + Kc
+    n, B = p_hi - p_lo, st.B
+    A1 = torch.empty(n, B, 64, device=dev, dtype=torch.float32)
+    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), _cabi.stream_ptr(dev)),
+                "gcm_temporal_gather")
+    D2 = torch.empty(n, B, 64, device=dev, dtype=torch.float32)
+    _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo)
+    ws = _WB_WS.get(dev)
+    if ws is None:
+        ws = _WB_WS[dev] = torch.empty(int(lib.gcm_temporal_window_bwd_workspace()), device=dev, dtype=torch.float32)
+    acc = torch.zeros(2 * 64 * 32 + 64, device=dev, dtype=torch.float32)
+    g1, g2 = acc[:2048].view(64, 32), acc[2048:4096].view(64, 32)
+    db1, db2 = acc[4096:4128], acc[4128:4160]
+    dz1 = torch.empty(n, B, 32, device=dev, dtype=torch.float32) if want_dz1 else None
+    _cabi.check(lib.gcm_temporal_window_bwd(A1.data_ptr(), D2.data_ptr(), n * B, wc["w1"].data_ptr(), wc["b1"].data_ptr(),
+                                            wc["w2t"].data_ptr(), _cabi.ACT[g.act1], ws.data_ptr(), g1.data_ptr(),
+                                            g2.data_ptr(), db1.data_ptr(), db2.data_ptr(),
+                                            None if dz1 is None else dz1.data_ptr(), _cabi.stream_ptr(dev)),
+                "gcm_temporal_window_bwd")
+    grads = {"w_rel1": g1[:32].t().contiguous(), "w_root1": g1[32:].t().contiguous(), "b1": db1,
+             "w_rel2": g2[:32].contiguous(), "w_root2": g2[32:].contiguous(), "b2": db2}
+    return grads, (None if dz1 is None else (p_lo, dz1))
+
+
 def _check_log(st, win, plan, margin=2):
     steps_total = st.steps - win.chain_start
     if steps_total + margin * plan.max_hop > st.C:
@@ -332,8 +371,15 @@ class _TRootFn(torch.autograd.Function):
         dW1 = torch.zeros(H1, 2 * F, device=dev)
         dW2 = torch.zeros(H2, 2 * H1, device=dev)
         db1, db2 = torch.zeros(H1, device=dev), torch.zeros(H2, device=dev)
+        fused = None
         if Kc > 0:
             _check_log(st, win, plan)
+            if win.cache is None:
+                fused = _window_fused(plan, st, win, Kc)
+        if fused is not None:
+            win.kmax, win.dz2, win.cache = -1, None, None
+            return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, fused[0]))
+        if Kc > 0:
             p_lo, p_hi = win.P0 - mh, win.P0 + Kc
             if win.cache is not None:
                 A1, h, dz1 = win.cache

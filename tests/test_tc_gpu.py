@@ -150,3 +150,4 @@ def test_outer_reduce_tc32_is_fp32_accurate(rows, Ho, Hi):
     print(f"rows={rows}: 3xTF32 err {err:.2e}, fp32 matmul err {err32:.2e}")
     assert err < 2e-6 + 2 * err32
     assert float((db.double() - A.double().sum(0)).abs().max()) < 1e-4 * max(1.0, rows ** 0.5)
+
