@@ -26,8 +26,14 @@ struct HopList {
 // out[i, b, 0:F] = sum_{s: p-s >= 0} x[b, slot(p-s), :],  out[i, b, F:2F] = x[b, slot(p), :],  p = p0 + i (zero row if p < 0)
 // grid: (chunks of B * F/4, rows); 32-bit index arithmetic (node positions are int32 counters on the device): the first
 // version spent a fifth of its issue slots in emulated 64-bit divisions (profiles/c2_bptt_kernels_r2.md).
+// tiled = 1 (F = 32 only): out is [tile of 128 rows][16-byte chunk 0 .. 15][row of the tile][4 floats] over the flattened
+// rows r = i * B + b, the layout the fused window-backward kernel loads with fully coalesced warps (gcm_temporal_bwd_tc.cu)
+__device__ __forceinline__ float4* tiled_slot(float* out, long long r, int chunk) {
+  return reinterpret_cast<float4*>(out) + (r >> 7) * (16 * 128) + chunk * 128 + (r & 127);
+}
+
 __global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state st, const HopList hops, int p0,
-                                                         float* __restrict__ out) {
+                                                         float* __restrict__ out, int tiled) {
   const int F4 = st.F >> 2;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk)
   if (j >= st.B * F4) return;
@@ -46,6 +52,12 @@ __global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state s
       }
     }
   }
+  if (tiled) {
+    const long long r = (long long)i * st.B + b;
+    __stcs(tiled_slot(out, r, c), sum);
+    __stcs(tiled_slot(out, r, F4 + c), self);
+    return;
+  }
   float4* o = reinterpret_cast<float4*>(out + ((size_t)i * st.B + b) * 2 * st.F) + c;
   __stcs(o, sum);
   __stcs(o + F4, self);
@@ -56,7 +68,7 @@ __global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state s
 // contributes nothing, and an output row whose own position is below valid_lo is zero.  Same grid as above.
 __global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src, int src_pos0, int n_src, int valid_lo,
                                                    const HopList hops, int sign, float* __restrict__ out, int out_pos0,
-                                                   int B, int H) {
+                                                   int B, int H, int tiled) {
   const int H4 = H >> 2;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk): row-major inside a row block
   if (j >= B * H4) return;
@@ -78,6 +90,12 @@ __global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src
     }
   }
   const int b = j / H4, c = j - b * H4;
+  if (tiled) {
+    const long long r = (long long)i * B + b;
+    __stcs(tiled_slot(out, r, c), sum);
+    __stcs(tiled_slot(out, r, H4 + c), self);
+    return;
+  }
   float4* o = reinterpret_cast<float4*>(out + ((size_t)i * B + b) * 2 * H) + c;
   __stcs(o, sum);
   __stcs(o + H4, self);
@@ -96,30 +114,32 @@ bool hop_list(const int32_t* hops, int n_hops, HopList& hl) {
 }  // namespace
 
 extern "C" int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hops, int n_hops, long long p0, int n_rows,
-                                   float* out, void* stream) {
+                                   float* out, int tiled, void* stream) {
   GCM_REQUIRE(st && st->nodes && out && n_rows >= 0 && st->F >= 4 && (st->F & 3) == 0 && st->C >= 1,
               "temporal_gather: bad arguments (F must be a multiple of 4)");
   GCM_REQUIRE(((reinterpret_cast<uintptr_t>(st->nodes) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
               "temporal_gather: pointers must be 16-byte aligned");
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_gather: bad hop list");
+  GCM_REQUIRE(!tiled || st->F == 32, "temporal_gather: the tiled layout needs F = 32");
   GCM_REQUIRE(p0 > -(1ll << 30) && p0 + n_rows < (1ll << 31) && n_rows <= 65535 && (long long)st->B * (st->F >> 2) < (1ll << 31),
               "temporal_gather: position / size out of range");
   if (n_rows == 0 || st->B == 0) return GCM_OK;
   const dim3 grid((unsigned)(((long long)st->B * (st->F >> 2) + 255) / 256), (unsigned)n_rows);
-  k_temporal_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, hl, (int)p0, out);
+  k_temporal_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, hl, (int)p0, out, tiled);
   return gcm_check_launch("k_temporal_gather");
 }
 
 extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo,
                                       const int32_t* hops, int n_hops, int sign, float* out, long long out_pos0,
-                                      int n_out, int B, int H, void* stream) {
+                                      int n_out, int B, int H, int tiled, void* stream) {
   GCM_REQUIRE(src && out && n_src >= 0 && n_out >= 0 && B >= 0 && H >= 4 && (H & 3) == 0 && (sign == 1 || sign == -1),
               "temporal_shift_sum: bad arguments (H must be a multiple of 4)");
   GCM_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
               "temporal_shift_sum: pointers must be 16-byte aligned");
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_shift_sum: bad hop list");
+  GCM_REQUIRE(!tiled || H == 32, "temporal_shift_sum: the tiled layout needs H = 32");
   GCM_REQUIRE(src_pos0 > -(1ll << 30) && out_pos0 > -(1ll << 30) && src_pos0 + n_src < (1ll << 31) &&
                   out_pos0 + n_out < (1ll << 31) && valid_lo > -(1ll << 31) && valid_lo < (1ll << 31) && n_out <= 65535 &&
                   (long long)B * (H >> 2) < (1ll << 31),
@@ -127,6 +147,6 @@ extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int 
   if (n_out == 0 || B == 0) return GCM_OK;
   const dim3 grid((unsigned)(((long long)B * (H >> 2) + 255) / 256), (unsigned)n_out);
   k_shift_sum<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hl, sign, out,
-                                                      (int)out_pos0, B, H);
+                                                      (int)out_pos0, B, H, tiled);
   return gcm_check_launch("k_shift_sum");
 }

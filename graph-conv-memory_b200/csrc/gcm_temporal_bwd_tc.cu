@@ -11,45 +11,50 @@
 //   G2 += U_r^T h_r     ([2H2, H1] = [dW_rel2 ; dW_root2]:  sum_p dz2_p (sum_s h_{p-s})^T = sum_q (sum_s dz2_{q+s}) h_q^T)
 // The separate-launch version (gcm_linear_tc32 x 2, gcm_act_backward, gcm_temporal_shift_sum, gcm_outer_reduce_tc32 x 2)
 // streams seven [rows, 32..64] operands through HBM; this kernel reads X and U once (512 B per row) and writes nothing
-// but per-CTA partials.  A CTA takes tiles of 128 rows (TMEM lane = row, 4 threads per row with 8 features each):
+// but per-CTA partials.  A CTA takes tiles of 128 rows (TMEM lane = row, 4 threads per row):
+//   * X and U come in TILED layout ([tile][16-byte chunk][row of the tile][4 floats], written that way by the two
+//     operand kernels): a warp's load of one chunk for its 32 rows is 512 contiguous bytes.  With row-major operands every
+//     lane touches its own 128-byte line and the loads alone took 4300 of a tile's 13900 cycles (tools/wb_trace.py);
 //   * the row products are TS-form MMAs: the row-owning threads write X and U (hi / lo split) into TMEM with tcgen05.st;
 //   * the weight-gradient products contract over the 128 ROWS of the tile, so their operands are [feature][row] matrices:
 //     the same threads scatter X, U, dz1, h into shared memory in the canonical K-major core-matrix layout with the row
 //     index as K (one float per store; a warp's 32 rows of one feature land in 32 different banks because the distance
 //     between K-adjacent core matrices is padded by 16 bytes);
-//   * the accumulator G = [X | U]^T [dz1 | h] ([128, 64]; its two diagonal blocks are G1 and G2) stays in TMEM for the
-//     whole launch and is flushed once per CTA; a second kernel adds the per-CTA partials in a fixed order.
+//   * 3xTF32 with STACKED operands: hi and lo parts sit next to each other along M (weight gradients: [X_hi ; X_lo]) or N
+//     ([dz1_hi | dz1_lo], [W_hi ; W_lo]), so one pass over K yields the hi*hi, lo*hi and hi*lo blocks side by side in the
+//     accumulator and every operand byte is read once instead of three times (64 MMAs per tile instead of 144); the
+//     blocks are added in the epilogue (row products) or by the reduce kernel (weight gradients);
+//   * the weight-gradient accumulators stay in TMEM for the whole launch and are flushed once per CTA; a second kernel
+//     adds the per-CTA partials in a fixed order (deterministic).
 #include "gcm_common.cuh"
 #include "gcm_tc.cuh"
 
 namespace {
 
 constexpr int WB_TILE = 128;          // rows per tile = TMEM lanes
-constexpr int WB_THREADS = 512;       // 4 threads per row: 8 of the 32 features each; warp 0's lane 0 also issues the MMAs
+constexpr int WB_THREADS = 512;       // 4 threads per row; lane 0 of warps 0 and 4 also issue the MMAs
 constexpr int WB_F = 32;              // F = H1 = H2 = 32 (the cached-row kernel's shape)
-constexpr int WB_AW = 4 * WB_F;       // features of the wide A block: [Xsum | Xself | Usum | Uself]
-constexpr int WB_BW = 2 * WB_F;       // [dz1 | h]
-// TMEM columns: accumulators, then the TS-form A operands (hi / lo) of the two row products
-constexpr uint32_t WB_COL_Z1 = 0, WB_COL_DH = 32, WB_COL_G = 64, WB_COL_XHI = 128, WB_COL_XLO = 192, WB_COL_UHI = 256,
-                   WB_COL_ULO = 320;
-constexpr int WB_PART = WB_AW * WB_F + 2 * WB_F;   // floats per CTA partial: G rows [128][32] + db1 + db2
+// TMEM columns: row-product accumulators [hi*hi + lo*hi | hi*lo] (64 each), weight-gradient accumulators (64 each), then
+// the TS-form A operands
+constexpr uint32_t WB_COL_Z1 = 0, WB_COL_DH = 64, WB_COL_G1 = 128, WB_COL_G2 = 192, WB_COL_XHI = 256, WB_COL_XLO = 320,
+                   WB_COL_UHI = 384, WB_COL_ULO = 448;
+constexpr int WB_GBLK = 128 * 64;                    // floats of one raw weight-gradient accumulator
+constexpr int WB_PART = 2 * WB_GBLK + 2 * WB_F;      // floats per CTA partial: raw G1, raw G2, db1, db2
 // [feature][row] operand blocks, K = row: core matrix (8 features x 4 rows) = 128 B; feature groups adjacent (SBO = 128),
 // row chunks LBO apart, LBO = (#feature groups) * 128 + 16: the pad makes LBO / 4 = 4 (mod 32), so the 32 rows a warp
 // stores for one feature hit 32 different banks
-constexpr int WB_A_LBO = (WB_AW / 8) * 128 + 16;   // 2064
-constexpr int WB_B_LBO = (WB_BW / 8) * 128 + 16;   // 1040
+constexpr int WB_A_LBO = 16 * 128 + 16;              // [X_hi (64 features) ; X_lo (64)]: 16 groups
+constexpr int WB_B_LBO = 8 * 128 + 16;               // [dz1_hi (32) | dz1_lo (32)]: 8 groups
 constexpr int WB_A_BYTES = (WB_TILE / 4) * WB_A_LBO;   // 66 048
 constexpr int WB_B_BYTES = (WB_TILE / 4) * WB_B_LBO;   // 33 280
 
 struct WbSmem {
-  unsigned char a_hi[WB_A_BYTES];
-  unsigned char a_lo[WB_A_BYTES];
-  unsigned char b_hi[WB_B_BYTES];
-  unsigned char b_lo[WB_B_BYTES];
-  float w1_hi[WB_F * 2 * WB_F];  // [H1][2F] canonical K-major, 8 KB each
-  float w1_lo[WB_F * 2 * WB_F];
-  float w2_hi[WB_F * 2 * WB_F];  // [H1][2H2]: dh = U w2t^T
-  float w2_lo[WB_F * 2 * WB_F];
+  unsigned char ax[WB_A_BYTES];  // [X_hi ; X_lo]^T  (features x rows)
+  unsigned char au[WB_A_BYTES];  // [U_hi ; U_lo]
+  unsigned char bd[WB_B_BYTES];  // [dz1_hi | dz1_lo]
+  unsigned char bh[WB_B_BYTES];  // [h_hi | h_lo]
+  float w1[2 * WB_F * 2 * WB_F];  // [W1_hi ; W1_lo]: [64][2F] canonical K-major, 16 KB
+  float w2[2 * WB_F * 2 * WB_F];  // [W2t_hi ; W2t_lo]
   float b1[WB_F];
   uint64_t bar_ops, bar_ab, bar_hd, bar_g;
   uint32_t tmem_slot;
@@ -57,15 +62,17 @@ struct WbSmem {
 static_assert(sizeof(WbSmem) <= 227 * 1024, "window backward: shared memory");
 
 struct WbArgs {
-  const float* X;       // [rows, 64]
-  const float* U;       // [rows, 64]
+  const float* X;       // tiled [rows / 128][16][128][4]
+  const float* U;
   const float* w1;      // [32, 64] = [W_rel1 | W_root1]
   const float* b1;      // [32]
   const float* w2t;     // [32, 64] = [W_rel2^T | W_root2^T]
   float* part;          // [grid, WB_PART]
-  float* dz1_out;       // optional [rows, 32]
+  float* dz1_out;       // optional [rows, 32] (row-major)
   long long rows;
   int n_tiles, act1;
+  long long* trace;     // debugging: per-tile phase clocks of warp `trace_warp` of CTA 0 ([tile][10])
+  int trace_warp;
 };
 
 // byte offset of (feature f, row g) in a [feature][row] block with row-chunk distance LBO
@@ -81,9 +88,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_temporal_window_bwd(const WbA
 
   if (tid == 0) {
     tc::mbar_init(&sm.bar_ops, WB_THREADS / 32);
-    tc::mbar_init(&sm.bar_ab, 1);
+    tc::mbar_init(&sm.bar_ab, 2);
     tc::mbar_init(&sm.bar_hd, WB_THREADS / 32);
-    tc::mbar_init(&sm.bar_g, 1);
+    tc::mbar_init(&sm.bar_g, 2);
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(&sm.tmem_slot, 512);
@@ -91,11 +98,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_temporal_window_bwd(const WbA
     const int n = i >> 6, k = i & 63;
     uint32_t hi, lo;
     tc::split_tf32(a.w1[i], hi, lo);
-    sm.w1_hi[tc::kmajor_off(n, k, 64)] = __uint_as_float(hi);
-    sm.w1_lo[tc::kmajor_off(n, k, 64)] = __uint_as_float(lo);
+    sm.w1[tc::kmajor_off(n, k, 64)] = __uint_as_float(hi);
+    sm.w1[tc::kmajor_off(32 + n, k, 64)] = __uint_as_float(lo);
     tc::split_tf32(a.w2t[i], hi, lo);
-    sm.w2_hi[tc::kmajor_off(n, k, 64)] = __uint_as_float(hi);
-    sm.w2_lo[tc::kmajor_off(n, k, 64)] = __uint_as_float(lo);
+    sm.w2[tc::kmajor_off(n, k, 64)] = __uint_as_float(hi);
+    sm.w2[tc::kmajor_off(32 + n, k, 64)] = __uint_as_float(lo);
   }
   if (tid < WB_F) sm.b1[tid] = a.b1[tid];
   tc::fence_proxy_async();
@@ -104,154 +111,174 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_temporal_window_bwd(const WbA
   tc::fence_after_sync();
   const uint32_t tbase = sm.tmem_slot;
 
-  // ---------------- MMA issue (warp 0, lane 0) ----------------
-  const uint32_t idesc_row = tc::idesc_tf32(128, 32);
-  const uint32_t idesc_g = tc::idesc_tf32(128, 64);
-  const uint32_t a_hi = tc::smem_u32(sm.a_hi), a_lo = tc::smem_u32(sm.a_lo);
-  const uint32_t b_hi = tc::smem_u32(sm.b_hi), b_lo = tc::smem_u32(sm.b_lo);
-  const uint32_t w1_hi = tc::smem_u32(sm.w1_hi), w1_lo = tc::smem_u32(sm.w1_lo);
-  const uint32_t w2_hi = tc::smem_u32(sm.w2_hi), w2_lo = tc::smem_u32(sm.w2_lo);
-  auto issue_rows = [&]() {        // z1 = X W1^T, dh = U W2t^T: A from TMEM
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {          // lo*Whi, hi*Wlo, hi*Whi
-      const uint32_t xc = pass == 0 ? WB_COL_XLO : WB_COL_XHI;
-      const uint32_t uc = pass == 0 ? WB_COL_ULO : WB_COL_UHI;
-      const uint32_t w1s = pass == 1 ? w1_lo : w1_hi;
-      const uint32_t w2s = pass == 1 ? w2_lo : w2_hi;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {              // K = 64 = 8 steps of 8
-        tc::mma_tf32_ts(tbase + WB_COL_Z1, tbase + xc + ks * 8, tc::smem_desc_kmajor(w1s + ks * 256, 128, 2048),
-                        idesc_row, pass > 0 || ks > 0);
-        tc::mma_tf32_ts(tbase + WB_COL_DH, tbase + uc + ks * 8, tc::smem_desc_kmajor(w2s + ks * 256, 128, 2048),
-                        idesc_row, pass > 0 || ks > 0);
-      }
-    }
+  // ---------------- MMA issue: lane 0 of warp 0 (layer-1 side: z1, G1) and of warp 4 (layer-2 side: dh, G2) ----------------
+  const int side = warp >> 2;                          // 0: X / W1 / dz1, 1: U / W2t / h   (warps 0 and 4 issue)
+  auto issue_rows = [&]() {
+    // [z1 | .] = X_hi [W_hi ; W_lo]^T (N = 64: hi*hi and hi*lo side by side), then X_lo W_hi^T on top of the first half
+    const uint64_t wd0 = tc::smem_desc_kmajor(tc::smem_u32(side ? sm.w2 : sm.w1), 128, 2048);
+    const uint32_t a_hi = tbase + (side ? WB_COL_UHI : WB_COL_XHI);
+    const uint32_t d = tbase + (side ? WB_COL_DH : WB_COL_Z1);
+    uint64_t wd = wd0;
+    uint32_t ac = a_hi;
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks, ac += 8, wd += 16)   // K = 64 = 8 steps of 8 (2 chunks of 128 B in the weight pack)
+      tc::mma_tf32_ts(d, ac, wd, tc::idesc_tf32(128, 64), ks > 0);
+    wd = wd0;
+    ac = a_hi + 64;
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks, ac += 8, wd += 16)
+      tc::mma_tf32_ts(d, ac, wd, tc::idesc_tf32(128, 32), true);
     tc::mma_commit(&sm.bar_ab);
   };
-  auto issue_grads = [&](bool first) {   // G (+)= [X | U]^T [dz1 | h]: K = the 128 rows of the tile
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t as = pass == 0 ? a_lo : a_hi;
-      const uint32_t bs = pass == 1 ? b_lo : b_hi;
-#pragma unroll
-      for (int ks = 0; ks < 16; ++ks) {             // 8 rows = 2 row chunks per instruction
-        tc::mma_tf32_ss(tbase + WB_COL_G, tc::smem_desc_kmajor(as + ks * 2 * WB_A_LBO, WB_A_LBO, 128),
-                        tc::smem_desc_kmajor(bs + ks * 2 * WB_B_LBO, WB_B_LBO, 128), idesc_g,
-                        !first || pass > 0 || ks > 0);
-      }
-    }
+  auto issue_grads = [&](bool first) {
+    // raw G1 (+)= [X_hi ; X_lo]^T [dz1_hi | dz1_lo]  (side 0),  raw G2 (+)= [U_hi ; U_lo]^T [h_hi | h_lo]  (side 1):
+    // M = 128, N = 64, K = the tile's 128 rows, 8 (= 2 row chunks) per instruction
+    uint64_t ad = tc::smem_desc_kmajor(tc::smem_u32(side ? sm.au : sm.ax), WB_A_LBO, 128);
+    uint64_t bd = tc::smem_desc_kmajor(tc::smem_u32(side ? sm.bh : sm.bd), WB_B_LBO, 128);
+    const uint32_t d = tbase + (side ? WB_COL_G2 : WB_COL_G1);
+#pragma unroll 2
+    for (int ks = 0; ks < 16; ++ks, ad += 2 * WB_A_LBO / 16, bd += 2 * WB_B_LBO / 16)
+      tc::mma_tf32_ss(d, ad, bd, tc::idesc_tf32(128, 64), !first || ks > 0);
     tc::mma_commit(&sm.bar_g);
   };
+  const bool issuer = (warp & 3) == 0 && warp < 8;     // warps 0 and 4
 
-  // ---------------- thread = (row of the tile, 8-feature block) ----------------
+  // ---------------- thread = (row of the tile, quarter of the operand columns / 8 of the 32 output features) ----------------
   const int quarter = warp & 3, fb = warp >> 2;
   const int g = quarter * 32 + lane;
   const int fcol = fb * 8;
   const uint32_t lane_base = tbase + ((uint32_t)(quarter * 32) << 16);
   const int act1 = a.act1;
-  float db1[8], db2[8];
+  float db1[8], db2[16];    // db2: columns 16 fb .. of U, i.e. dz2 features 16 (fb - 2) .. for fb >= 2
 #pragma unroll
-  for (int j = 0; j < 8; ++j) db1[j] = db2[j] = 0.f;
+  for (int j = 0; j < 8; ++j) db1[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) db2[j] = 0.f;
 
-  float4 v[8];    // this tile's [Xsum | Xself | Usum | Uself] slices (2 x float4 each), loaded one tile ahead
+  float4 v[8];    // chunks 4 fb .. 4 fb + 3 of this row's X (v[0..3]) and U (v[4..7]), loaded one tile ahead
   auto load_tile = [&](int tile) {
-    const long long r = (long long)tile * WB_TILE + g;
-    if (r < a.rows) {
-      const float4* x = reinterpret_cast<const float4*>(a.X + r * 64 + fcol);
-      const float4* u = reinterpret_cast<const float4*>(a.U + r * 64 + fcol);
-      v[0] = __ldcs(x);
-      v[1] = __ldcs(x + 1);
-      v[2] = __ldcs(x + 8);
-      v[3] = __ldcs(x + 9);
-      v[4] = __ldcs(u);
-      v[5] = __ldcs(u + 1);
-      v[6] = __ldcs(u + 8);
-      v[7] = __ldcs(u + 9);
-    } else {
+    const float4* x = reinterpret_cast<const float4*>(a.X) + (size_t)tile * (16 * WB_TILE) + (4 * fb) * WB_TILE + g;
+    const float4* u = reinterpret_cast<const float4*>(a.U) + (size_t)tile * (16 * WB_TILE) + (4 * fb) * WB_TILE + g;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i) {
+      v[i] = __ldcs(x + i * WB_TILE);
+      v[4 + i] = __ldcs(u + i * WB_TILE);
     }
   };
 
   int it = 0;
   int tile = blockIdx.x;
+#define WB_T(k)                                                                                   \
+  if (a.trace && blockIdx.x == 0 && warp == a.trace_warp && lane == 0 && it < 64) a.trace[it * 10 + (k)] = clock64();
   if (tile < a.n_tiles) load_tile(tile);
   for (; tile < a.n_tiles; tile += gridDim.x, ++it) {
-    // ---- split; TS-form A operands -> TMEM ----
-    uint32_t hi[4][8], lo[4][8];
+    WB_T(0)
+    // ---- split; TS-form A operands -> TMEM (the split is redone for the shared-memory copy below: keeping hi / lo of
+    //      all 32 values alive across the barrier waits spilled the prefetched rows) ----
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float f[8] = {v[2 * i].x, v[2 * i].y, v[2 * i].z, v[2 * i].w, v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 1].z,
-                          v[2 * i + 1].w};
+    for (int t = 0; t < 2; ++t) {
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tc::split_tf32(f[j], hi[i][j], lo[i][j]);
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = v[4 * t + i];
+        tc::split_tf32(q.x, hi[4 * i], lo[4 * i]);
+        tc::split_tf32(q.y, hi[4 * i + 1], lo[4 * i + 1]);
+        tc::split_tf32(q.z, hi[4 * i + 2], lo[4 * i + 2]);
+        tc::split_tf32(q.w, hi[4 * i + 3], lo[4 * i + 3]);
+        if (t == 1) {
+          db2[4 * i] += q.x;
+          db2[4 * i + 1] += q.y;
+          db2[4 * i + 2] += q.z;
+          db2[4 * i + 3] += q.w;
+        }
+      }
+      const uint32_t c_hi = (t == 0 ? WB_COL_XHI : WB_COL_UHI) + 16 * fb;
+      tc::tmem_st16(lane_base + c_hi, hi);
+      tc::tmem_st16(lane_base + c_hi + 64, lo);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) db2[j] += __uint_as_float(hi[3][j]) + __uint_as_float(lo[3][j]);
-    tc::tmem_st8(lane_base + WB_COL_XHI + fcol, hi[0]);
-    tc::tmem_st8(lane_base + WB_COL_XHI + 32 + fcol, hi[1]);
-    tc::tmem_st8(lane_base + WB_COL_XLO + fcol, lo[0]);
-    tc::tmem_st8(lane_base + WB_COL_XLO + 32 + fcol, lo[1]);
-    tc::tmem_st8(lane_base + WB_COL_UHI + fcol, hi[2]);
-    tc::tmem_st8(lane_base + WB_COL_UHI + 32 + fcol, hi[3]);
-    tc::tmem_st8(lane_base + WB_COL_ULO + fcol, lo[2]);
-    tc::tmem_st8(lane_base + WB_COL_ULO + 32 + fcol, lo[3]);
     tc::wait_st();
     tc::fence_before_sync();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&sm.bar_ops);
-    if (warp == 0) {
+    WB_T(1)
+    if (issuer) {
       tc::mbar_wait(&sm.bar_ops, it & 1);
       tc::fence_after_sync();
       if (lane == 0) issue_rows();
       __syncwarp();
     }
     // ---- the same values as [feature][row] operands of the weight-gradient product (previous tile's must be done) ----
+    WB_T(2)
     tc::mbar_wait(&sm.bar_g, (it & 1) ^ 1);
+    WB_T(3)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int t = 0; t < 2; ++t) {
+      // feature 16 fb + 4 i + j: group 2 fb + i / 2, row-in-group 4 (i & 1) + j; the lo copy sits 8 groups further
+      unsigned char* p = (t == 0 ? sm.ax : sm.au) + fr_off<WB_A_LBO>(16 * fb, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t o = fr_off<WB_A_LBO>(i * 32 + fcol + j, g);
-        *reinterpret_cast<uint32_t*>(sm.a_hi + o) = hi[i][j];
-        *reinterpret_cast<uint32_t*>(sm.a_lo + o) = lo[i][j];
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = v[4 * t + i];
+        const float f[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hi, lo;
+          tc::split_tf32(f[j], hi, lo);
+          *reinterpret_cast<uint32_t*>(p + (i >> 1) * 128 + ((i & 1) * 4 + j) * 16) = hi;
+          *reinterpret_cast<uint32_t*>(p + 1024 + (i >> 1) * 128 + ((i & 1) * 4 + j) * 16) = lo;
+        }
       }
+    }
+    WB_T(4)
     // ---- next tile's rows (in flight while the MMAs run) ----
     if (tile + (int)gridDim.x < a.n_tiles) load_tile(tile + gridDim.x);
     // ---- h, dz1 ----
+    WB_T(5)
     tc::mbar_wait(&sm.bar_ab, it & 1);
     tc::fence_after_sync();
+    WB_T(6)
     float hq[8], d1[8];
     {
-      uint32_t z[8], dh[8];
-      tc::tmem_ld8(lane_base + WB_COL_Z1 + fcol, z);
-      tc::tmem_ld8(lane_base + WB_COL_DH + fcol, dh);
+      uint32_t z0[8], z1[8], e0[8], e1[8];
+      tc::tmem_ld8(lane_base + WB_COL_Z1 + fcol, z0);
+      tc::tmem_ld8(lane_base + WB_COL_Z1 + 32 + fcol, z1);
+      tc::tmem_ld8(lane_base + WB_COL_DH + fcol, e0);
+      tc::tmem_ld8(lane_base + WB_COL_DH + 32 + fcol, e1);
       tc::wait_ld();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hq[j] = __uint_as_float(z[j]) + sm.b1[fcol + j];
+      for (int j = 0; j < 8; ++j) hq[j] = (__uint_as_float(z0[j]) + __uint_as_float(z1[j])) + sm.b1[fcol + j];
       gcm_act_fast_vec<8>(hq, act1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d1[j] = __uint_as_float(dh[j]) * gcm_act_grad(hq[j], act1);
-        db1[j] += d1[j];
-      }
-    }
+      for (int j = 0; j < 8; ++j) d1[j] = __uint_as_float(e0[j]) + __uint_as_float(e1[j]);
+      if (act1 == GCM_ACT_TANH) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t h, l;
-      tc::split_tf32(d1[j], h, l);
-      uint32_t o = fr_off<WB_B_LBO>(fcol + j, g);
-      *reinterpret_cast<uint32_t*>(sm.b_hi + o) = h;
-      *reinterpret_cast<uint32_t*>(sm.b_lo + o) = l;
-      tc::split_tf32(hq[j], h, l);
-      o = fr_off<WB_B_LBO>(32 + fcol + j, g);
-      *reinterpret_cast<uint32_t*>(sm.b_hi + o) = h;
-      *reinterpret_cast<uint32_t*>(sm.b_lo + o) = l;
+        for (int j = 0; j < 8; ++j) d1[j] *= 1.0f - hq[j] * hq[j];
+      } else if (act1 == GCM_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d1[j] = hq[j] > 0.0f ? d1[j] : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) db1[j] += d1[j];
+    }
+    {
+      // feature fcol + j: group fb, row-in-group j; lo copy 4 groups further
+      unsigned char* pd = sm.bd + fr_off<WB_B_LBO>(fcol, g);
+      unsigned char* ph = sm.bh + fr_off<WB_B_LBO>(fcol, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t h, l;
+        tc::split_tf32(d1[j], h, l);
+        *reinterpret_cast<uint32_t*>(pd + j * 16) = h;
+        *reinterpret_cast<uint32_t*>(pd + 512 + j * 16) = l;
+        tc::split_tf32(hq[j], h, l);
+        *reinterpret_cast<uint32_t*>(ph + j * 16) = h;
+        *reinterpret_cast<uint32_t*>(ph + 512 + j * 16) = l;
+      }
     }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&sm.bar_hd);
+    WB_T(7)
     if (a.dz1_out) {
       const long long r = (long long)tile * WB_TILE + g;
       if (r < a.rows) {
@@ -260,62 +287,83 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_temporal_window_bwd(const WbA
         __stcs(o + 1, make_float4(d1[4], d1[5], d1[6], d1[7]));
       }
     }
-    if (warp == 0) {
+    if (issuer) {
       tc::mbar_wait(&sm.bar_hd, it & 1);
       tc::fence_after_sync();
       if (lane == 0) issue_grads(it == 0);
       __syncwarp();
     }
+    WB_T(8)
   }
-  // ---- flush: G rows and the bias sums of this CTA ----
+  // ---- flush: the raw accumulators (row m of G1 / G2 = feature m of [hi ; lo]) and the bias sums of this CTA ----
   tc::mbar_wait(&sm.bar_g, (it & 1) ^ 1);
   tc::fence_after_sync();
   float* part = a.part + (size_t)blockIdx.x * WB_PART;
-  {
-    uint32_t w[8];
-    const int m = g;                                     // G row = feature index of [Xsum | Xself | Usum | Uself]
-    tc::tmem_ld8(lane_base + WB_COL_G + (m < 64 ? 0 : 32) + fcol, w);
-    tc::wait_ld();
-    float4* o = reinterpret_cast<float4*>(part + m * WB_F + fcol);
-    if (it > 0) {
-      o[0] = make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3]));
-      o[1] = make_float4(__uint_as_float(w[4]), __uint_as_float(w[5]), __uint_as_float(w[6]), __uint_as_float(w[7]));
-    } else {
-      o[0] = o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t w[8];
+      tc::tmem_ld8(lane_base + (which ? WB_COL_G2 : WB_COL_G1) + half * 32 + fcol, w);
+      tc::wait_ld();
+      float4* o = reinterpret_cast<float4*>(part + which * WB_GBLK + g * 64 + half * 32 + fcol);
+      if (it > 0) {
+        o[0] = make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3]));
+        o[1] = make_float4(__uint_as_float(w[4]), __uint_as_float(w[5]), __uint_as_float(w[6]), __uint_as_float(w[7]));
+      } else {
+        o[0] = o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
-  // bias sums: [which][feature][row] in the (now idle) A block, then one thread per (which, feature) adds 128 values
-  float* red = reinterpret_cast<float*>(sm.a_hi);
+  // bias sums: [feature][row] in the (now idle) A block, then one thread per feature adds 128 values
+  float* red = reinterpret_cast<float*>(sm.ax);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    red[(fcol + j) * WB_TILE + g] = db1[j];
-    red[(WB_F + fcol + j) * WB_TILE + g] = db2[j];
+  for (int j = 0; j < 8; ++j) red[(fcol + j) * WB_TILE + g] = db1[j];
+  if (fb >= 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) red[(WB_F + 16 * (fb - 2) + j) * WB_TILE + g] = db2[j];
   }
   tc::fence_before_sync();
   __syncthreads();
   if (tid < 2 * WB_F) {
     float s = 0.f;
     for (int i = 0; i < WB_TILE; ++i) s += red[tid * WB_TILE + ((i + tid) & (WB_TILE - 1))];
-    part[WB_AW * WB_F + tid] = s;
+    part[2 * WB_GBLK + tid] = s;
   }
   if (warp == 1) tc::tmem_dealloc(tbase, 512);
 }
 
-// out[i] += sum over CTAs (fixed order) of part[cta][i]; i < 128 * 32: G rows, then db1, db2
+// g1 / g2 [64, 32] += sum over CTAs (fixed order) of the three useful blocks of the raw accumulators
+//   raw[m][n]: m < 64 hi feature m, m >= 64 lo feature m - 64; n < 32 hi column n, n >= 32 lo column n - 32
 __global__ void __launch_bounds__(256) k_temporal_window_bwd_reduce(const float* __restrict__ part, int n_cta,
                                                                     float* __restrict__ g1, float* __restrict__ g2,
                                                                     float* __restrict__ db1, float* __restrict__ db2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= WB_PART) return;
+  if (i >= 2 * 64 * WB_F + 2 * WB_F) return;
   float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += part[(size_t)c * WB_PART + i];
-  if (i < 64 * WB_F) g1[i] += s;
-  else if (i < 128 * WB_F) g2[i - 64 * WB_F] += s;
-  else if (i < 128 * WB_F + WB_F) db1[i - 128 * WB_F] += s;
-  else db2[i - 128 * WB_F - WB_F] += s;
+  if (i < 2 * 64 * WB_F) {
+    const int which = i / (64 * WB_F), f = (i / WB_F) % 64, k = i % WB_F;
+    const float* p = part + which * WB_GBLK;
+    for (int c = 0; c < n_cta; ++c, p += WB_PART) s += (p[f * 64 + k] + p[(64 + f) * 64 + k]) + p[f * 64 + 32 + k];
+    (which ? g2 : g1)[f * WB_F + k] += s;
+  } else {
+    const int j = i - 2 * 64 * WB_F;
+    const float* p = part + 2 * WB_GBLK + j;
+    for (int c = 0; c < n_cta; ++c, p += WB_PART) s += *p;
+    (j < WB_F ? db1 : db2)[j & (WB_F - 1)] += s;
+  }
 }
 
 }  // namespace
+
+static long long* g_wb_trace = nullptr;
+static int g_wb_trace_warp = 0;
+/* debugging hook (tools/wb_trace.py): device buffer [64][10] of int64 that the next launches fill with phase clocks */
+extern "C" int gcm_temporal_window_bwd_set_trace(long long* buf, int warp) {
+  g_wb_trace = buf;
+  g_wb_trace_warp = warp;
+  return GCM_OK;
+}
 
 extern "C" long long gcm_temporal_window_bwd_workspace(void) { return (long long)gcm_num_sms() * WB_PART; }
 
@@ -339,6 +387,8 @@ extern "C" int gcm_temporal_window_bwd(const float* X, const float* U, long long
   a.dz1_out = dz1_out;
   a.rows = rows;
   a.act1 = act1;
+  a.trace = g_wb_trace;
+  a.trace_warp = g_wb_trace_warp;
   a.n_tiles = (int)((rows + WB_TILE - 1) / WB_TILE);
   const int sms = gcm_num_sms();
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
@@ -355,6 +405,7 @@ extern "C" int gcm_temporal_window_bwd(const float* X, const float* U, long long
   k_temporal_window_bwd<<<grid, WB_THREADS, sizeof(WbSmem), (cudaStream_t)stream>>>(a);
   int rc = gcm_check_launch("k_temporal_window_bwd");
   if (rc != GCM_OK) return rc;
-  k_temporal_window_bwd_reduce<<<(WB_PART + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grid, g1, g2, db1, db2);
+  k_temporal_window_bwd_reduce<<<(2 * 64 * WB_F + 2 * WB_F + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, grid, g1,
+                                                                                                          g2, db1, db2);
   return gcm_check_launch("k_temporal_window_bwd_reduce");
 }

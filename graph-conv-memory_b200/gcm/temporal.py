@@ -246,12 +246,14 @@ def _outer(a, x, dw, db):
         ones._outer(a, x, dw, db)
 
 
-def _shift_sum(plan, src, src_pos0, sign, out, out_pos0):
+def _shift_sum(plan, src, src_pos0, sign, out, out_pos0, n_out=None):
+    """n_out given: `out` is a flat buffer in the tiled layout of the fused window kernel (see include/gcm_b200.h)"""
     hops, nh = _hops(plan, src.device)
     n_src, B, H = src.shape
     _cabi.check(_cabi.lib().gcm_temporal_shift_sum(src.data_ptr(), src_pos0, n_src, 0, hops.data_ptr(), nh, sign,
-                                                   out.data_ptr(), out_pos0, out.shape[0], B, H,
-                                                   _cabi.stream_ptr(src.device)), "gcm_temporal_shift_sum")
+                                                   out.data_ptr(), out_pos0, out.shape[0] if n_out is None else n_out, B, H,
+                                                   0 if n_out is None else 1, _cabi.stream_ptr(src.device)),
+                "gcm_temporal_shift_sum")
 
 
 def _rows(plan, st, win, p_lo, p_hi, Kc):
@@ -263,7 +265,7 @@ def _rows(plan, st, win, p_lo, p_hi, Kc):
     wc = _wcat(plan, dev)
     lib = _cabi.lib()
     A1 = torch.empty(n, B, 2 * st.F, device=dev, dtype=torch.float32)
-    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), _cabi.stream_ptr(dev)),
+    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), 0, _cabi.stream_ptr(dev)),
                 "gcm_temporal_gather")
     h = _lin(A1.view(n * B, 2 * st.F), wc["w1"], bias=wc["b1"], act=_cabi.ACT[g.act1]).view(n, B, g.H1)
     D2 = torch.empty(n, B, 2 * g.H2, device=dev, dtype=torch.float32)
@@ -291,11 +293,14 @@ def _window_fused(plan, st, win, Kc, want_dz1=False):
     wc = _wcat(plan, dev)
     p_lo, p_hi = win.P0 - plan.max_hop, win.P0 + Kc
     n, B = p_hi - p_lo, st.B
-    A1 = torch.empty(n, B, 64, device=dev, dtype=torch.float32)
-    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), _cabi.stream_ptr(dev)),
+    rows = n * B
+    padded = (rows + 127) // 128 * 128          # the kernel reads whole tiles of 128 rows; rows past the end are zero
+    alloc = torch.empty if padded == rows else torch.zeros
+    A1 = alloc(padded * 64, device=dev, dtype=torch.float32)
+    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), 1, _cabi.stream_ptr(dev)),
                 "gcm_temporal_gather")
-    D2 = torch.empty(n, B, 64, device=dev, dtype=torch.float32)
-    _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo)
+    D2 = alloc(padded * 64, device=dev, dtype=torch.float32)
+    _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo, n_out=n)
     ws = _WB_WS.get(dev)
     if ws is None:
         ws = _WB_WS[dev] = torch.empty(int(lib.gcm_temporal_window_bwd_workspace()), device=dev, dtype=torch.float32)

@@ -216,23 +216,29 @@ int gcm_dense_step_bwd(const gcm_dense_state* st, int steps_back, const gcm_gnn*
  * gcm_temporal_shift_sum: out[i, b, :] = [ sum_s src[pos + sign * s] | src[pos] ] (2H floats), pos = out_pos0 + i, with
  * src [n_src, B, H] holding positions src_pos0 .. src_pos0 + n_src - 1 (anything outside is zero); positions below
  * valid_lo are nodes that never existed: they contribute nothing and their own output rows are zero.  sign = -1: sums
- * over in-neighbours (layer inputs), +1: over out-neighbours (gradients).  H % 4 == 0. */
+ * over in-neighbours (layer inputs), +1: over out-neighbours (gradients).  H % 4 == 0.
+ * tiled = 1 (32 features only): out is written as [tile of 128 rows][16-byte chunk 0 .. 15][row of the tile][4 floats] over
+ * the flattened rows r = i * B + b, the operand layout of gcm_temporal_window_bwd; the buffer must cover whole tiles. */
 int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hops, int n_hops, long long p0, int n_rows, float* out,
-                        void* stream);
+                        int tiled, void* stream);
 int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo, const int32_t* hops,
-                           int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H, void* stream);
+                           int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H, int tiled,
+                           void* stream);
 
 /* ---- the row products and weight-gradient reductions of that backward as ONE kernel (csrc/gcm_temporal_bwd_tc.cu) ----
  * Replaces gcm_linear_tc32 x 2 + gcm_act_backward + gcm_temporal_shift_sum + gcm_outer_reduce_tc32 x 2 of the window
  * backward (autograd through gcm.py:262-321, tests/test_gcm.py:412-439) for F = H1 = H2 = 32: tcgen05 / TMEM, 3xTF32,
  * one pass over the two operand streams.
- *   X [rows, 64] = [sum_s x_{q-s} | x_q]      (gcm_temporal_gather)         row = (position q, graph b), any order
- *   U [rows, 64] = [sum_s dz2_{q+s} | dz2_q]  (gcm_temporal_shift_sum, sign = +1)
+ *   X = rows [sum_s x_{q-s} | x_q]      (gcm_temporal_gather, tiled = 1)         row = (position q, graph b), any order
+ *   U = rows [sum_s dz2_{q+s} | dz2_q]  (gcm_temporal_shift_sum, sign = +1, tiled = 1); both cover ceil(rows / 128) whole
+ *       tiles, rows past `rows` zero
  *   w1cat [32, 64] = [W_rel1 | W_root1],  w2tcat [32, 64] = [W_rel2^T | W_root2^T],  b1 [32],  act1 = GCM_ACT_*
  *   g1 [64, 32] += [dW_rel1^T ; dW_root1^T],  g2 [64, 32] += [dW_rel2 ; dW_root2],  db1 [32] +=,  db2 [32] +=
  *   dz1_out (optional) [rows, 32]: dL/d(pre-activation of layer 1) of every row
  *   workspace: gcm_temporal_window_bwd_workspace() floats.  Deterministic (per-CTA partials added in a fixed order). */
 long long gcm_temporal_window_bwd_workspace(void);
+/* debugging hook: device buffer [64][10] of int64 that later launches fill with per-tile phase clocks (NULL: off) */
+int gcm_temporal_window_bwd_set_trace(long long* buf, int warp);
 int gcm_temporal_window_bwd(const float* X, const float* U, long long rows, const float* w1cat, const float* b1,
                             const float* w2tcat, int act1, float* workspace, float* g1, float* g2, float* db1, float* db2,
                             float* dz1_out, void* stream);
