@@ -836,7 +836,8 @@ extern "C" int gcm_set_temporal_kernel(int which) {
 static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
                          int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
                          int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
-                         void* stream_, int n_steps = 1, long long obs_stride_t = 0, long long belief_stride_t = 0);
+                         void* stream_, int n_steps = 1, long long obs_stride_t = 0, long long belief_stride_t = 0,
+                         float* xrec = nullptr, long long xrec_row0 = 0);
 
 extern "C" int gcm_dense_step_fwd(const gcm_dense_state* st, const float* obs, const gcm_selector* sels,
                                   int n_sels, const gcm_gnn* gnn, float* belief, int32_t* status,
@@ -868,7 +869,8 @@ extern "C" int gcm_dense_step_fwd_ex(const gcm_dense_state* st, const float* obs
 static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long obs_ld, const gcm_selector* sels,
                          int n_sels, const gcm_gnn* gnn, float* belief, long long belief_ld, int32_t* status,
                          int flags, int uniform_count, float* hcache, int hc_ring, int* cache_written,
-                         void* stream_, int n_steps, long long obs_stride_t, long long belief_stride_t) {
+                         void* stream_, int n_steps, long long obs_stride_t, long long belief_stride_t, float* xrec,
+                         long long xrec_row0) {
   if (cache_written) *cache_written = 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = validate_state(st)) return rc;
@@ -927,6 +929,8 @@ static int step_fwd_impl(const gcm_dense_state* st, const float* obs, long long 
         wa.n_steps = n_steps;
         wa.obs_stride_t = obs_stride_t;
         wa.belief_stride_t = belief_stride_t;
+        wa.xrec = xrec;
+        wa.xrec_row0 = xrec_row0;
         wa.hcache = hcache;
         wa.hc_ring = hc_ring;
         wa.weights_stable = (flags & GCM_STEP_WEIGHTS_STABLE) ? 1 : 0;
@@ -1035,6 +1039,7 @@ extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long
   if (belief_ld <= 0) belief_ld = H2;
   const bool strided = obs_ld != F || belief_ld != H2;
   const long long l0 = gcm_launch_count();
+  r->xrec_from = T;
   static const bool no_multi = getenv("GCM_B200_NO_MULTISTEP") != nullptr;     // A/B switch: one launch per step
   for (int k = 0; k < T;) {
     const float* ob = obs + (long long)k * obs_stride_t;
@@ -1051,8 +1056,9 @@ extern "C" int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long
       // walks all of them, consecutive steps overlapping inside the kernel (csrc/gcm_dense_fwd_hc.cu)
       rc = step_fwd_impl(&r->st, ob, obs_ld, r->sels, r->n_sels, &r->gnn, be, belief_ld, r->status, flags,
                          r->uniform_count, r->hcache, r->hc_ring, &written, stream_, T - k, obs_stride_t,
-                         belief_stride_t);
+                         belief_stride_t, r->xrec, r->xrec_row0 + (long long)k * r->st.B);
       if (rc == GCM_OK && written) {
+        if (r->xrec && r->st.F == 32) r->xrec_from = k;
         if (r->uniform_count >= 0) r->uniform_count += T - k;
         r->weights_stable = 1;
         k = T;

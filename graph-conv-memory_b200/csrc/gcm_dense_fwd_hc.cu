@@ -398,6 +398,12 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
           hp[i] = ok ? mine + np * F + i * HC_H : zero_row;
         }
         const float* x_ptr = live ? mine + np * F + np * HC_H : zero_row;
+        // recording (F = 32): the same operand row also goes to the tiled buffer of the fused window backward
+        float4* xrec4 = nullptr;
+        if (F == 32 && a.xrec && live) {
+          const long long r = a.xrec_row0 + (long long)t * a.st.B + g0 + lane;
+          xrec4 = reinterpret_cast<float4*>(a.xrec) + (r >> 7) * (16 * 128) + (r & 127);
+        }
         // ---- layer-1 operand [sum of in-neighbour rows | own row] -> TMEM (hi | lo) ----
 #pragma unroll
         for (int c0 = 0; c0 < K1; c0 += 16) {
@@ -419,6 +425,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) k_step_temporal_hc(const Tempor
             v[q4 * 4 + 0] = sv.x; v[q4 * 4 + 1] = sv.y; v[q4 * 4 + 2] = sv.z; v[q4 * 4 + 3] = sv.w;
           }
           hc_store_split16(taddr + HC_COL_A1HI + c0, taddr + HC_COL_A1LO + c0, v);
+          if (F == 32 && xrec4) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              __stcs(xrec4 + (c0 / 4 + q4) * 128, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+          }
         }
         // ---- second half of the layer-2 operand: sum of the in-neighbours' cached h rows ----
 #pragma unroll

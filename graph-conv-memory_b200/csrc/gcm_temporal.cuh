@@ -47,6 +47,10 @@ struct TemporalWinArgs {
   // writes belief + k * belief_stride_t and sees uniform_count + k.  0 or 1 = a single step.
   int n_steps;
   long long obs_stride_t, belief_stride_t;
+  // hc kernel only, F = 32: also write the layer-1 operand rows [sum of in-neighbour rows | own row] of every step into the
+  // TILED operand buffer of the fused window backward (gcm_temporal_bwd_tc.cu), row index xrec_row0 + step * B + graph
+  float* xrec;
+  long long xrec_row0;
 };
 
 

@@ -66,9 +66,11 @@ __global__ void __launch_bounds__(256) k_temporal_gather(const gcm_dense_state s
 // out[i, b, 0:H] = sum_s src[pos + sign * s, b, :],  out[i, b, H:2H] = src[pos, b, :],  pos = out_pos0 + i;
 // src rows cover positions [src_pos0, src_pos0 + n_src); a position below valid_lo (a node that never existed)
 // contributes nothing, and an output row whose own position is below valid_lo is zero.  Same grid as above.
+// act_out != nullptr: the source rows are src * act'(act_out) (dL/dbelief and the beliefs of a window: dz2 is formed on the
+// fly instead of being written and re-read)
 __global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src, int src_pos0, int n_src, int valid_lo,
                                                    const HopList hops, int sign, float* __restrict__ out, int out_pos0,
-                                                   int B, int H, int tiled) {
+                                                   int B, int H, int tiled, const float* __restrict__ act_out, int act) {
   const int H4 = H >> 2;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk): row-major inside a row block
   if (j >= B * H4) return;
@@ -77,14 +79,26 @@ __global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src
   float4 self = make_float4(0.f, 0.f, 0.f, 0.f), sum = self;
   if (pos >= valid_lo) {
     const float4* s4 = reinterpret_cast<const float4*>(src) + j;
+    const float4* a4 = reinterpret_cast<const float4*>(act_out) + j;
     const size_t row = (size_t)B * H4;
+    auto fetch = [&](int jq) {
+      float4 v = __ldg(s4 + (size_t)jq * row);
+      if (act_out) {
+        const float4 o = __ldg(a4 + (size_t)jq * row);
+        v.x *= gcm_act_grad(o.x, act);
+        v.y *= gcm_act_grad(o.y, act);
+        v.z *= gcm_act_grad(o.z, act);
+        v.w *= gcm_act_grad(o.w, act);
+      }
+      return v;
+    };
     const int j0 = pos - src_pos0;
-    if (j0 >= 0 && j0 < n_src) self = __ldg(s4 + (size_t)j0 * row);
+    if (j0 >= 0 && j0 < n_src) self = fetch(j0);
     for (int k = 0; k < hops.n; ++k) {
       const int q = pos + sign * hops.h[k];
       const int jq = q - src_pos0;
       if (q >= valid_lo && jq >= 0 && jq < n_src) {
-        const float4 v = __ldg(s4 + (size_t)jq * row);
+        const float4 v = fetch(jq);
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
     }
@@ -132,7 +146,7 @@ extern "C" int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hop
 
 extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo,
                                       const int32_t* hops, int n_hops, int sign, float* out, long long out_pos0,
-                                      int n_out, int B, int H, int tiled, void* stream) {
+                                      int n_out, int B, int H, int tiled, const float* act_out, int act, void* stream) {
   GCM_REQUIRE(src && out && n_src >= 0 && n_out >= 0 && B >= 0 && H >= 4 && (H & 3) == 0 && (sign == 1 || sign == -1),
               "temporal_shift_sum: bad arguments (H must be a multiple of 4)");
   GCM_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
@@ -140,6 +154,9 @@ extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int 
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_shift_sum: bad hop list");
   GCM_REQUIRE(!tiled || H == 32, "temporal_shift_sum: the tiled layout needs H = 32");
+  GCM_REQUIRE((reinterpret_cast<uintptr_t>(act_out) & 15) == 0 &&
+                  (!act_out || act == GCM_ACT_NONE || act == GCM_ACT_TANH || act == GCM_ACT_RELU),
+              "temporal_shift_sum: bad activation operand");
   GCM_REQUIRE(src_pos0 > -(1ll << 30) && out_pos0 > -(1ll << 30) && src_pos0 + n_src < (1ll << 31) &&
                   out_pos0 + n_out < (1ll << 31) && valid_lo > -(1ll << 31) && valid_lo < (1ll << 31) && n_out <= 65535 &&
                   (long long)B * (H >> 2) < (1ll << 31),
@@ -147,6 +164,6 @@ extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int 
   if (n_out == 0 || B == 0) return GCM_OK;
   const dim3 grid((unsigned)(((long long)B * (H >> 2) + 255) / 256), (unsigned)n_out);
   k_shift_sum<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hl, sign, out,
-                                                      (int)out_pos0, B, H, tiled);
+                                                      (int)out_pos0, B, H, tiled, act_out, act);
   return gcm_check_launch("k_shift_sum");
 }

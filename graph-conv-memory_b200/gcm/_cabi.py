@@ -77,6 +77,7 @@ class RolloutC(C.Structure):
         ("uniform_count", C.c_int32), ("hc_fresh", C.c_int32), ("weights_stable", C.c_int32),
         ("status", C.c_void_p), ("scratch_obs", C.c_void_p), ("scratch_belief", C.c_void_p),
         ("launches", C.c_longlong),
+        ("xrec", C.c_void_p), ("xrec_row0", C.c_longlong), ("xrec_from", C.c_int32),
     ]
 
 
@@ -105,7 +106,7 @@ _SIGNATURES = {
     "gcm_dense_rollout_step": (_I, [C.POINTER(RolloutC), _P, _P, _P]),
     "gcm_state_log_write_seq": (_I, [C.POINTER(DenseStateC), _P, _L, _L, _I, _P]),
     "gcm_temporal_gather": (_I, [C.POINTER(DenseStateC), _P, _I, _L, _I, _P, _I, _P]),
-    "gcm_temporal_shift_sum": (_I, [_P, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _I, _P]),
+    "gcm_temporal_shift_sum": (_I, [_P, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _I, _P, _I, _P]),
     "gcm_temporal_window_bwd_workspace": (_L, []),
     "gcm_temporal_window_bwd_set_trace": (_I, [_P, _I]),
     "gcm_temporal_window_bwd": (_I, [_P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -132,9 +132,11 @@ def sequence_supported(plan, state, x_seq: torch.Tensor) -> bool:
             and not torch.cuda.is_current_stream_capturing())
 
 
-def sequence_nograd(plan, state, x_seq: torch.Tensor, beliefs: torch.Tensor) -> int:
+def sequence_nograd(plan, state, x_seq: torch.Tensor, beliefs: torch.Tensor, rec=None) -> int:
     """T in-place steps from x_seq [B, T, F] (inner stride 1) into beliefs [B, T, H2] (inner stride 1): the step loop of
-    ray_gcm.py:200-202 as ONE C call.  Returns the number of kernels launched.  Caller checked sequence_supported."""
+    ray_gcm.py:200-202 as ONE C call.  Returns the number of kernels launched.  Caller checked sequence_supported.
+    rec = [tiled operand buffer, row of the first step, None]: the cached-row kernel also writes the layer-1 operand rows
+    of its steps there (gcm_rollout.xrec); rec[2] becomes the index of the first step it wrote."""
     ro = ready(plan, state)
     dev = state.device
     T = x_seq.shape[1]
@@ -148,8 +150,12 @@ def sequence_nograd(plan, state, x_seq: torch.Tensor, beliefs: torch.Tensor) -> 
                 torch.empty(state.B, plan.gnn.H2, device=dev, dtype=torch.float32))
         c.scratch_obs, c.scratch_belief = scr[0].data_ptr(), scr[1].data_ptr()
     _sync_in(ro, state)
+    if rec is not None:
+        c.xrec, c.xrec_row0 = rec[0].data_ptr(), rec[1]
     rc = ro.seq_fn(ro.ref, x_seq.data_ptr(), x_seq.stride(0), x_seq.stride(1), beliefs.data_ptr(), beliefs.stride(0),
                    beliefs.stride(1), T, _cabi.stream_ptr(dev))
+    if rec is not None:
+        c.xrec, rec[2] = None, (T if rc else int(c.xrec_from))
     if rc:
         _failed(state)
         _cabi.check(rc, "gcm_dense_rollout_fwd")
@@ -185,6 +191,8 @@ class _TWindow:
         self.kmax = -1            # newest-first backward: steps kmax .. k have delivered dz2 so far
         self.dz2 = None           # [K, B, H2] float32, time-major; zero rows = steps whose belief got no gradient
         self.cache = None         # (A1, h, dz1) over the whole window, left by a sequence node for the root
+        self.lazy = None          # (dL/dbelief, beliefs), both [K, B, H2] time-major: dz2 of the WHOLE window not yet formed
+        self.xrec = None          # [tiled X buffer, row of step 0, first step the forward kernel wrote] of the WHOLE window
 
 
 def _hops(plan, dev):
@@ -246,13 +254,16 @@ def _outer(a, x, dw, db):
         ones._outer(a, x, dw, db)
 
 
-def _shift_sum(plan, src, src_pos0, sign, out, out_pos0, n_out=None):
-    """n_out given: `out` is a flat buffer in the tiled layout of the fused window kernel (see include/gcm_b200.h)"""
+def _shift_sum(plan, src, src_pos0, sign, out, out_pos0, n_out=None, act_out=None, act=0):
+    """n_out given: `out` is a flat buffer in the tiled layout of the fused window kernel (see include/gcm_b200.h);
+    act_out given: the source rows are src * act'(act_out)"""
     hops, nh = _hops(plan, src.device)
     n_src, B, H = src.shape
     _cabi.check(_cabi.lib().gcm_temporal_shift_sum(src.data_ptr(), src_pos0, n_src, 0, hops.data_ptr(), nh, sign,
                                                    out.data_ptr(), out_pos0, out.shape[0] if n_out is None else n_out, B, H,
-                                                   0 if n_out is None else 1, _cabi.stream_ptr(src.device)),
+                                                   0 if n_out is None else 1,
+                                                   None if act_out is None else act_out.data_ptr(), act,
+                                                   _cabi.stream_ptr(src.device)),
                 "gcm_temporal_shift_sum")
 
 
@@ -280,13 +291,18 @@ def _rows(plan, st, win, p_lo, p_hi, Kc):
 _WB_WS = {}
 
 
+def _fused_shape(plan, st) -> bool:
+    g = plan.gnn
+    return not os.environ.get("GCM_B200_NO_WINDOW_BWD_TC") and st.F == 32 and g.H1 == 32 and g.H2 == 32
+
+
 def _window_fused(plan, st, win, Kc, want_dz1=False):
     """Both layers' row products and both weight-gradient reductions of the window in ONE kernel
     (csrc/gcm_temporal_bwd_tc.cu) over the operand rows [sum x | x] and [sum dz2 | dz2] of the positions
     P0 - max_hop .. P0 + Kc - 1.  Returns (grads dict, (first position, dz1 rows) or None), or None when the shape is not
     the kernel's (F = H1 = H2 = 32) -- the caller then runs the separate products."""
     g, dev = plan.gnn, st.device
-    if os.environ.get("GCM_B200_NO_WINDOW_BWD_TC") or st.F != 32 or g.H1 != 32 or g.H2 != 32:
+    if not _fused_shape(plan, st):
         return None
     lib = _cabi.lib()
     hops, nh = _hops(plan, dev)
@@ -296,11 +312,19 @@ def _window_fused(plan, st, win, Kc, want_dz1=False):
     rows = n * B
     padded = (rows + 127) // 128 * 128          # the kernel reads whole tiles of 128 rows; rows past the end are zero
     alloc = torch.empty if padded == rows else torch.zeros
-    A1 = alloc(padded * 64, device=dev, dtype=torch.float32)
-    _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n, A1.data_ptr(), 1, _cabi.stream_ptr(dev)),
-                "gcm_temporal_gather")
+    n_gather = n
+    if win.xrec is not None and win.xrec[0].numel() == padded * 64 and win.xrec[1] == plan.max_hop * B:
+        A1, n_gather = win.xrec[0], plan.max_hop + win.xrec[2]      # the rest was written by the forward kernel
+    else:
+        A1 = alloc(padded * 64, device=dev, dtype=torch.float32)
+    if n_gather > 0:
+        _cabi.check(lib.gcm_temporal_gather(st.c_ref(), hops.data_ptr(), nh, p_lo, n_gather, A1.data_ptr(), 1,
+                                            _cabi.stream_ptr(dev)), "gcm_temporal_gather")
     D2 = alloc(padded * 64, device=dev, dtype=torch.float32)
-    _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo, n_out=n)
+    if win.lazy is not None:
+        _shift_sum(plan, win.lazy[0], win.P0, +1, D2, p_lo, n_out=n, act_out=win.lazy[1], act=_cabi.ACT[g.act2])
+    else:
+        _shift_sum(plan, win.dz2[:Kc], win.P0, +1, D2, p_lo, n_out=n)
     ws = _WB_WS.get(dev)
     if ws is None:
         ws = _WB_WS[dev] = torch.empty(int(lib.gcm_temporal_window_bwd_workspace()), device=dev, dtype=torch.float32)
@@ -382,8 +406,11 @@ class _TRootFn(torch.autograd.Function):
             if win.cache is None:
                 fused = _window_fused(plan, st, win, Kc)
         if fused is not None:
-            win.kmax, win.dz2, win.cache = -1, None, None
+            win.kmax, win.dz2, win.cache, win.lazy, win.xrec = -1, None, None, None, None
             return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, fused[0]))
+        if win.lazy is not None:
+            _deliver(plan, st, win, 0, Kc, *win.lazy)
+            win.lazy = None
         if Kc > 0:
             p_lo, p_hi = win.P0 - mh, win.P0 + Kc
             if win.cache is not None:
@@ -396,7 +423,7 @@ class _TRootFn(torch.autograd.Function):
             A2 = torch.empty(Kc, B, 2 * H1, device=dev, dtype=torch.float32)
             _shift_sum(plan, h, p_lo, -1, A2, win.P0)
             _outer(win.dz2[:Kc].view(Kc * B, H2), A2.view(Kc * B, 2 * H1), dW2, db2)
-        win.kmax, win.dz2, win.cache = -1, None, None
+        win.kmax, win.dz2, win.cache, win.lazy, win.xrec = -1, None, None, None, None
         grads = {"w_rel1": dW1[:, :F].contiguous(), "w_root1": dW1[:, F:].contiguous(), "b1": db1,
                  "w_rel2": dW2[:, :H1].contiguous(), "w_root2": dW2[:, H1:].contiguous(), "b2": db2}
         return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, grads))
@@ -444,14 +471,22 @@ class _TSeqFn(torch.autograd.Function):
         T = x_seq.shape[1]
         buf = torch.empty(T, state.B, plan.gnn.H2, device=state.device, dtype=torch.float32)   # time-major
         xs = x_seq.detach()
+        rec = None
         if sequence_supported(plan, state, xs):
-            sequence_nograd(plan, state, xs, buf.transpose(0, 1))
+            if k0 == 0 and hist is None and not x_seq.requires_grad and _fused_shape(plan, state):
+                # the forward kernel leaves the layer-1 operand rows of its steps for the fused window backward
+                rows = (plan.max_hop + T) * state.B
+                padded = (rows + 127) // 128 * 128
+                rec = [(torch.empty if padded == rows else torch.zeros)(padded * 64, device=state.device), plan.max_hop * state.B,
+                       None]
+            sequence_nograd(plan, state, xs, buf.transpose(0, 1), rec)
         else:
             for t in range(T):
                 fused._launch_fwd(plan, state, xs[:, t].contiguous(), buf[t])
         ctx.plan, ctx.state, ctx.k0, ctx.T = plan, state, k0, T
         ctx.chain_id = state.twin.chain_id
         ctx.buf = buf
+        ctx.xrec = rec
         ctx.has_hist = hist is not None
         return buf.transpose(0, 1), torch.zeros(1, device=state.device)
 
@@ -461,10 +496,16 @@ class _TSeqFn(torch.autograd.Function):
         win = st.twin
         if win.chain_id != ctx.chain_id:
             raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
-        _deliver(plan, st, win, k0, T, d_beliefs.transpose(0, 1).contiguous().float(), ctx.buf)
-        ctx.buf = None
         d_x = d_hist = None
         want_hist = ctx.has_hist and ctx.needs_input_grad[5]
+        d_tm = d_beliefs.transpose(0, 1).contiguous().float()
+        if (k0 == 0 and T == st.steps - win.chain_start and win.kmax < 0 and _fused_shape(plan, st)
+                and not ctx.needs_input_grad[0] and not want_hist):
+            # this node is the whole window and nothing but the weights wants a gradient: the root forms dz2 on the fly
+            win.lazy, win.kmax, win.xrec = (d_tm, ctx.buf), T - 1, ctx.xrec
+        else:
+            _deliver(plan, st, win, k0, T, d_tm, ctx.buf)
+        ctx.buf = ctx.xrec = None
         if ctx.needs_input_grad[0] or want_hist:
             Kc, mh = win.kmax + 1, plan.max_hop
             _check_log(st, win, plan)
@@ -497,7 +538,7 @@ def _chain(plan, state, token, n_steps):
         win.chain_id += 1
         win.chain_start = state.steps
         win.P0 = state.host_count
-        win.kmax, win.dz2, win.cache = -1, None, None
+        win.kmax, win.dz2, win.cache, win.lazy, win.xrec = -1, None, None, None, None
         anchor = torch.zeros(1, device=state.device, requires_grad=True)
         token = _TRootFn.apply(anchor, plan, state, win.chain_id, *plan.gnn.params())
     k = state.steps - win.chain_start

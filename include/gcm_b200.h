@@ -178,6 +178,13 @@ typedef struct gcm_rollout {
   float* scratch_obs;
   float* scratch_belief;
   long long launches;     /* out: kernels launched by the last call                                            */
+  /* recording for the fused window backward (gcm_temporal_window_bwd), F = 32: xrec = its TILED operand buffer X or NULL;
+   * step k of a call writes the rows xrec_row0 + k * B + graph.  Only the multi-step launch of the cached-row kernel
+   * writes them: on return xrec_from = index of the first step whose rows were written (T if none); the caller fills
+   * the earlier rows with gcm_temporal_gather. */
+  float* xrec;
+  long long xrec_row0;
+  int32_t xrec_from;
 } gcm_rollout;
 int gcm_dense_rollout_fwd(gcm_rollout* r, const float* obs, long long obs_ld, long long obs_stride_t, float* belief,
                           long long belief_ld, long long belief_stride_t, int T, void* stream);
@@ -217,13 +224,15 @@ int gcm_dense_step_bwd(const gcm_dense_state* st, int steps_back, const gcm_gnn*
  * src [n_src, B, H] holding positions src_pos0 .. src_pos0 + n_src - 1 (anything outside is zero); positions below
  * valid_lo are nodes that never existed: they contribute nothing and their own output rows are zero.  sign = -1: sums
  * over in-neighbours (layer inputs), +1: over out-neighbours (gradients).  H % 4 == 0.
+ * act_out (optional, same shape as src): the source rows are src * act'(act_out) with act = GCM_ACT_* -- dL/dbelief and
+ * the beliefs of a window, so that dz2 is formed on the fly.
  * tiled = 1 (32 features only): out is written as [tile of 128 rows][16-byte chunk 0 .. 15][row of the tile][4 floats] over
  * the flattened rows r = i * B + b, the operand layout of gcm_temporal_window_bwd; the buffer must cover whole tiles. */
 int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hops, int n_hops, long long p0, int n_rows, float* out,
                         int tiled, void* stream);
 int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo, const int32_t* hops,
                            int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H, int tiled,
-                           void* stream);
+                           const float* act_out, int act, void* stream);
 
 /* ---- the row products and weight-gradient reductions of that backward as ONE kernel (csrc/gcm_temporal_bwd_tc.cu) ----
  * Replaces gcm_linear_tc32 x 2 + gcm_act_backward + gcm_temporal_shift_sum + gcm_outer_reduce_tc32 x 2 of the window

@@ -35,17 +35,18 @@ def test_abi_struct_layout_matches_header(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "gcm_b200.h"\n'
-        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(gcm_dense_state), sizeof(gcm_selector),"
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(gcm_dense_state), sizeof(gcm_selector),"
         " sizeof(gcm_gnn), sizeof(gcm_gnn_grads), offsetof(gcm_selector, max_distance), offsetof(gcm_selector, dist_param),"
         " offsetof(gcm_gnn, F), offsetof(gcm_dense_state, B), sizeof(gcm_rollout), offsetof(gcm_rollout, sels),"
-        " offsetof(gcm_rollout, hcache), offsetof(gcm_rollout, status), offsetof(gcm_rollout, launches));return 0;}\n")
+        " offsetof(gcm_rollout, hcache), offsetof(gcm_rollout, status), offsetof(gcm_rollout, launches), offsetof(gcm_rollout, xrec_from));return 0;}\n")
     exe = tmp_path / "abi"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [ctypes.sizeof(_cabi.DenseStateC), ctypes.sizeof(_cabi.SelectorC), ctypes.sizeof(_cabi.GnnC),
             ctypes.sizeof(_cabi.GnnGradsC), _cabi.SelectorC.max_distance.offset, _cabi.SelectorC.dist_param.offset,
             _cabi.GnnC.F.offset, _cabi.DenseStateC.B.offset, ctypes.sizeof(_cabi.RolloutC), _cabi.RolloutC.sels.offset,
-            _cabi.RolloutC.hcache.offset, _cabi.RolloutC.status.offset, _cabi.RolloutC.launches.offset]
+            _cabi.RolloutC.hcache.offset, _cabi.RolloutC.status.offset, _cabi.RolloutC.launches.offset,
+            _cabi.RolloutC.xrec_from.offset]
     assert got == want
 
 

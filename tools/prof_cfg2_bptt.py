@@ -33,6 +33,22 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); window(); e1.record(); torch.cuda.synchronize()
 print(f"window: {e0.elapsed_time(e1):.2f} ms")
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+e0.record()
+for _ in range(5):
+    window()
+e1.record()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"5 windows back to back: {e0.elapsed_time(e1) / 5:.2f} ms per window on the device, host issue time {(t1 - t0) * 200:.2f} ms per window")
+if os.environ.get("GCM_TRACE_JSON"):
+    from torch.profiler import profile as _p, ProfilerActivity as _A
+    with _p(activities=[_A.CUDA, _A.CPU]) as pr:
+        window(); window()
+        torch.cuda.synchronize()
+    pr.export_chrome_trace(os.environ["GCM_TRACE_JSON"])
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     window()
