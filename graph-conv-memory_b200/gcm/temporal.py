@@ -403,8 +403,10 @@ class _TRootFn(torch.autograd.Function):
         fused = None
         if Kc > 0:
             _check_log(st, win, plan)
-            if win.cache is None:
-                fused = _window_fused(plan, st, win, Kc)
+        if Kc > 0 and win.cache is None:
+            fused = _window_fused(plan, st, win, Kc)
+        elif Kc > 0 and isinstance(win.cache[0], str):
+            fused = (win.cache[1], None)                 # a sequence node already ran the fused kernel
         if fused is not None:
             win.kmax, win.dz2, win.cache, win.lazy, win.xrec = -1, None, None, None, None
             return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, fused[0]))
@@ -473,7 +475,7 @@ class _TSeqFn(torch.autograd.Function):
         xs = x_seq.detach()
         rec = None
         if sequence_supported(plan, state, xs):
-            if k0 == 0 and hist is None and not x_seq.requires_grad and _fused_shape(plan, state):
+            if k0 == 0 and _fused_shape(plan, state):
                 # the forward kernel leaves the layer-1 operand rows of its steps for the fused window backward
                 rows = (plan.max_hop + T) * state.B
                 padded = (rows + 127) // 128 * 128
@@ -499,9 +501,8 @@ class _TSeqFn(torch.autograd.Function):
         d_x = d_hist = None
         want_hist = ctx.has_hist and ctx.needs_input_grad[5]
         d_tm = d_beliefs.transpose(0, 1).contiguous().float()
-        if (k0 == 0 and T == st.steps - win.chain_start and win.kmax < 0 and _fused_shape(plan, st)
-                and not ctx.needs_input_grad[0] and not want_hist):
-            # this node is the whole window and nothing but the weights wants a gradient: the root forms dz2 on the fly
+        if k0 == 0 and T == st.steps - win.chain_start and win.kmax < 0 and _fused_shape(plan, st):
+            # this node is the whole window: the fused kernel's shift-sum forms dz2 on the fly
             win.lazy, win.kmax, win.xrec = (d_tm, ctx.buf), T - 1, ctx.xrec
         else:
             _deliver(plan, st, win, k0, T, d_tm, ctx.buf)
@@ -513,9 +514,16 @@ class _TSeqFn(torch.autograd.Function):
             if k0 == 0:
                 # the chain's first node runs last: every step has delivered.  One evaluation of the window serves dL/dx
                 # here, dL/dhist, and the weight gradients at the root
-                full = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
-                win.cache = full
-                rows = (win.P0 - mh, full[2])
+                fz = _window_fused(plan, st, win, Kc, want_dz1=True)
+                if fz is not None:
+                    win.cache, rows = ("fused", fz[0]), fz[1]     # the weight gradients are done: the root returns them
+                else:
+                    if win.lazy is not None:
+                        _deliver(plan, st, win, 0, Kc, *win.lazy)
+                        win.lazy = None
+                    full = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
+                    win.cache = full
+                    rows = (win.P0 - mh, full[2])
             if ctx.needs_input_grad[0]:
                 if rows is not None:
                     d_x = _dx(plan, st, win, 0, T, Kc, rows=(win.P0, rows[1][mh:]))

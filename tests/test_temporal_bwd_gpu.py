@@ -72,6 +72,50 @@ def test_temporal_window_backward_matches_fp64_oracle(mode, x_grad, B, N, F, T, 
     assert torch.equal(nodes.detach().cpu(), ref32[3][0])
 
 
+@pytest.mark.parametrize("x_grad", [False, True])
+def test_fused_window_kernel_serves_f32_shapes_and_matches_the_separate_products(x_grad, monkeypatch):
+    """F = H = 32: the root runs ONE fused kernel (gcm_temporal_window_bwd; with dz2 formed inside the shift-sum and the
+    operand rows left by the forward kernel when the sequence node is the whole window); GCM_B200_NO_WINDOW_BWD_TC=1
+    switches back to the separate products.  Same gradients either way."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, T, hops = 260, 16, 32, 19, (1, 2, 4)
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(5)
+    obs = (torch.randn(T, B, F, generator=gen) * 0.5).to(dev)
+    w = torch.randn(T, B, 32, generator=gen).to(dev)
+    p = oracle.make_params(F, 32)
+    res = {}
+    lib = _cabi.lib()
+    real, calls = lib.gcm_temporal_window_bwd, []
+
+    def spy(*a):
+        calls.append(a[2])
+        return real(*a)
+    monkeypatch.setattr(lib, "gcm_temporal_window_bwd", spy)
+    for fused in (True, False):
+        calls.clear()
+        if fused:
+            monkeypatch.delenv("GCM_B200_NO_WINDOW_BWD_TC", raising=False)
+        else:
+            monkeypatch.setenv("GCM_B200_NO_WINDOW_BWD_TC", "1")
+        gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+        mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+        with torch.no_grad():                                   # a running rollout first: the window starts mid-log
+            _, hidden = mod.forward_sequence(obs[:7].transpose(0, 1), None)
+        x = obs.clone().requires_grad_(x_grad)
+        outs, hidden = mod.forward_sequence(x.transpose(0, 1), hidden)
+        (outs.transpose(0, 1) * w).sum().backward()
+        assert calls == ([(T + 4) * B] if fused else []), calls      # one launch over the window's rows + max_hop planes
+        res[fused] = (named_grads(convs), None if not x_grad else x.grad.clone())
+    for k in res[True][0]:
+        assert rel_err(res[True][0][k], res[False][0][k]) < 2e-5, k
+    if x_grad:
+        assert rel_err(res[True][1], res[False][1]) < 2e-5
+
+
 def test_truncated_bptt_over_windows_with_weight_updates():
     """A running rollout trained window by window (m_t.detach(), SGD step in between): fill without autograd, then three
     windows; every window's gradients against the fp64 oracle doing the same."""
