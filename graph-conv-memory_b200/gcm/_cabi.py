@@ -152,6 +152,7 @@ _SIGNATURES = {
     "gcm_set_edge_builder": (_I, [_I]),
     "gcm_set_graphconv_kernel": (_I, [_I]),
     "gcm_sparse_graphconv_hint_rows": (_I, [C.c_longlong]),
+    "gcm_sparse_graphconv_hint_blocks": (_I, [_P, _I, _I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_csr_transpose": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,

@@ -171,6 +171,13 @@ class Csr:
         return self._t[key]
 
 
+def _hint_blocks(csr: Csr, rows) -> None:
+    """SparseGCM's CSR is block-diagonal over graphs whose rows are contiguous: tell the next forward call, which can then
+    stage a graph's rows in shared memory (gcm_sparse_graphconv_hint_blocks)."""
+    if rows is None and csr.node_off is not None and csr.max_nodes > 0:
+        _cabi.lib().gcm_sparse_graphconv_hint_blocks(csr.node_off.data_ptr(), csr.node_off.numel() - 1, int(csr.max_nodes))
+
+
 def _kmajor(w_rel: torch.Tensor, w_root: torch.Tensor) -> torch.Tensor:
     return torch.cat([w_rel.detach().t(), w_root.detach().t()], dim=0).contiguous()
 
@@ -189,6 +196,7 @@ class _GraphConvFn(torch.autograd.Function):
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
         _cabi.lib().gcm_sparse_graphconv_hint_rows(n)
+        _hint_blocks(csr, rows)
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
             x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), None, _cabi.ptr(rows), m, Fin, Fout,
             wt.data_ptr(), _cabi.ptr(b), act, _cabi.ptr(agg), out.data_ptr(), _cabi.stream_ptr(dev)),
@@ -239,6 +247,7 @@ def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none", ed
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
         _cabi.lib().gcm_sparse_graphconv_hint_rows(x.shape[0])
+        _hint_blocks(csr, rows)
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
             x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), edge_mask.data_ptr(), _cabi.ptr(rows), m, x.shape[1],
             w_rel.shape[0], wt.data_ptr(), _cabi.ptr(b), _cabi.ACT[act], None, out.data_ptr(),

@@ -456,6 +456,12 @@ int gcm_set_graphconv_kernel(int which);
 /* number of rows of x for the NEXT gcm_sparse_graphconv_fwd call that evaluates a row subset (`rows` != NULL): lets the
  * tensor-core kernel, which addresses x with 32-bit offsets, take that call too; 0 / not called: unknown. */
 int gcm_sparse_graphconv_hint_rows(long long n);
+/* block structure of x for the NEXT gcm_sparse_graphconv_fwd call that evaluates every row (`rows` == NULL): the rows of
+ * graph g are node_off[g] .. node_off[g + 1] - 1 (device array of the n_graphs first rows, the last graph ends at m), no
+ * graph has more than max_nodes rows and every edge stays inside its graph -- what util.flatten_adj (util.py) produces
+ * from the per-batch-element adjacency.  Lets the call take the block-local kernel (a graph's rows staged in shared
+ * memory by one bulk copy, gathers from shared memory). */
+int gcm_sparse_graphconv_hint_blocks(const int64_t* node_off, int n_graphs, int max_nodes);
 
 /* The transposed grouping the backward needs, for a block-diagonal graph: rowptr [n+1] / col [E] = CSR by sink over
  * the flat numbering, node_off [B+1] = first flat node of every graph (each graph has at most 8192 nodes and its

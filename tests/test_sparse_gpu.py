@@ -365,3 +365,60 @@ def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_ro
         for ga, gb in zip(grads[_cabi.GC_CUDA_CORES], grads[_cabi.GC_TC]):
             # sums of ~1200 signed terms of size ~1: the two forwards differ by ~1e-6, which the cancellation amplifies
             assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
+
+
+@pytest.mark.parametrize("F,H,act,masked", [(64, 64, "tanh", False), (32, 48, "relu", True)])
+def test_graphconv_block_local_kernel_matches_the_others(F, H, act, masked):
+    """k_graphconv_fwd_blk (a graph's rows staged in shared memory by one bulk copy, gathers from shared memory, M = 64
+    tiles) on a block-diagonal graph with ragged blocks -- an empty graph, one row, sizes that are not multiples of the
+    tile -- against the CUDA-core kernel and the definition; forward values, the aggregation handed to the backward (via
+    the gradients)."""
+    from gcm import _cabi, sparse_ops
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(3 * F + H)
+    sizes = torch.tensor([200, 0, 1, 64, 65, 256, 130, 17, 255, 128] * 4)
+    node_off = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(sizes, 0)])
+    n = int(node_off[-1])
+    gid = torch.repeat_interleave(torch.arange(sizes.numel()), sizes)
+    local = torch.arange(n) - node_off[gid]
+    deg = torch.minimum(torch.randint(0, 45, (n,), generator=gen), local)          # at most `local` distinct earlier rows
+    sink = torch.repeat_interleave(torch.arange(n), deg)
+    src = node_off[gid[sink]] + (torch.rand(sink.numel(), generator=gen) * local[sink].float()).long()   # same graph, earlier
+    order = torch.argsort(sink * n + src)
+    sink, src = sink[order], src[order]
+    csr = sparse_ops.Csr.from_sorted_edges(sink.to(dev), src.to(dev), n)
+    csr.node_off, csr.max_nodes = node_off.to(dev), int(sizes.max())
+    x = torch.randn(n, F, generator=gen).to(dev)
+    w_rel = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    w_root = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    bias = torch.randn(H, generator=gen).to(dev)
+    mask = (torch.rand(sink.numel(), generator=gen) < 0.7).float().to(dev) if masked else None
+    outs, grads = {}, {}
+    try:
+        for which in (_cabi.GC_CUDA_CORES, _cabi.GC_TC):
+            lib.gcm_set_graphconv_kernel(which)
+            with torch.no_grad():
+                outs[which] = sparse_ops.graph_conv_csr(x, csr, None, w_rel, bias, w_root, act, edge_mask=mask)
+            want = "k_graphconv_fwd_blk" if which == _cabi.GC_TC else "k_graphconv_fwd"
+            assert lib.gcm_last_kernel().decode() == want
+            if mask is None:
+                xg = x.clone().requires_grad_(True)
+                wr, wo, bb = (t.clone().requires_grad_(True) for t in (w_rel, w_root, bias))
+                out = sparse_ops.graph_conv_csr(xg, csr, None, wr, bb, wo, act)
+                (out * torch.linspace(-1, 1, out.numel(), device=dev).view_as(out)).sum().backward()
+                grads[which] = (xg.grad, wr.grad, wo.grad, bb.grad)
+    finally:
+        lib.gcm_set_graphconv_kernel(_cabi.GC_AUTO)
+    w = torch.ones(sink.numel(), device=dev) if mask is None else mask
+    agg = torch.zeros(n, F, device=dev, dtype=torch.float64).index_add_(0, sink.to(dev), (x[src.to(dev)] * w[:, None]).double())
+    ref = agg @ w_rel.double().t() + bias.double() + x.double() @ w_root.double().t()
+    ref = {"tanh": torch.tanh, "relu": torch.relu, "none": lambda t: t}[act](ref)
+    a, b = outs[_cabi.GC_CUDA_CORES], outs[_cabi.GC_TC]
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((b.double() - ref).abs().max()) / scale < 2e-5
+    assert float((a - b).abs().max()) / scale < 1e-5
+    if mask is None:
+        for ga, gb in zip(grads[_cabi.GC_CUDA_CORES], grads[_cabi.GC_TC]):
+            assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
