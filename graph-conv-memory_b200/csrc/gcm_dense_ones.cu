@@ -315,6 +315,20 @@ __device__ __forceinline__ float ones_eval(float e, float q, float& d) {
   }
 }
 
+// u = 1 / (E Q + 1) for TWO (step, node, channel) triples with ONE MUFU:  r = rcp(a b),  1/a = r b,  1/b = r a.
+// The window kernels are bound by the MUFU pipe (one rcp per evaluation: XU 80 %, profiles/c3_ones_kernels_r1.md) while
+// the FP32 pipes have room for the three extra multiplies.  a, b are cut at 1e18 so that the product stays finite (E and Q
+// are exponentials clamped at e^80 each; beyond 1e18 u < 2^-59, i.e. tanh = 1 and tanh' = 0 exactly in fp32 either way);
+// min.NaN keeps a NaN a NaN (the finite check of gcm.py:318 must still fire).
+__device__ __forceinline__ void ones_u2(float e0, float q0, float e1, float q1, float& u0, float& u1) {
+  float a = fmaf(e0, q0, 1.0f), b = fmaf(e1, q1, 1.0f);
+  asm("min.NaN.f32 %0, %0, 0f5D5E0B6B;" : "+f"(a));      // 1e18
+  asm("min.NaN.f32 %0, %0, 0f5D5E0B6B;" : "+f"(b));
+  const float r = ones_rcp(a * b);
+  u0 = r * b;
+  u1 = r * a;
+}
+
 struct OnesFwdArgs {
   gcm_dense_state st;
   int H1;
@@ -509,12 +523,43 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_ones_window_fwd(const OnesSeqAr
           q[0] = __uint_as_float(t2.x << 16); q[1] = __uint_as_float(t2.x & 0xffff0000u);
           q[2] = __uint_as_float(t2.y << 16); q[3] = __uint_as_float(t2.y & 0xffff0000u);
         }
+        if (ACT == GCM_ACT_TANH) {
+          // two evaluations per MUFU (ones_u2).  bf16 cache (2e-2 tolerance): only sum u and u^2 per evaluation and
+          // recover  sum h = n - 2 sum u,  sum h' = 4 (sum u - sum u^2)  after the loop (2 FP32 instructions instead of 4;
+          // the partial sums stay near n / 2, which costs ~1e-4 absolute on G: too much for the float32 cache mode)
+          float u[4];
+          ones_u2(ec[0], q[0], ec[1], q[1], u[0], u[1]);
+          ones_u2(ec[2], q[2], ec[3], q[3], u[2], u[3]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            hl[c] = u[c];
+            if (sizeof(CT) == 2) {
+              su[c] += u[c];
+              if (REC) sp[c] = fmaf(u[c], u[c], sp[c]);
+            } else {
+              su[c] += fmaf(-2.0f, u[c], 1.0f);
+              if (REC) sp[c] += 4.0f * fmaf(-u[c], u[c], u[c]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float d;
+            hl[c] = ones_eval<ACT>(ec[c], q[c], d);          // after the loop: h of the last row = the step's own node
+            su[c] += hl[c];
+            if (REC) sp[c] += d;
+          }
+        }
+      }
+      if (ACT == GCM_ACT_TANH) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float d;
-          hl[c] = ones_eval<ACT>(ec[c], q[c], d);          // after the loop: h of the last row = the step's own node
-          su[c] += hl[c];
-          if (REC) sp[c] += d;
+          hl[c] = fmaf(-2.0f, hl[c], 1.0f);                  // u of the last row -> h of the step's own node
+          if (sizeof(CT) == 2) {
+            const float sum_u = su[c];
+            su[c] = fmaf(-2.0f, sum_u, (float)(j1 - j0));
+            if (REC) sp[c] = 4.0f * (sum_u - sp[c]);
+          }
         }
       }
       *reinterpret_cast<float4*>(a.wG + col) = make_float4(su[0], su[1], su[2], su[3]);
@@ -562,44 +607,80 @@ __global__ void __launch_bounds__(256) k_ones_window_bwd(const OnesWinArgs a) {
       const int kk = i / tpr, v = i - kk * tpr;
       const size_t g = (size_t)(k0 + kk) * a.sstride + (size_t)b * H1 + v * 4;
       *reinterpret_cast<float4*>(sE + kk * H1 + v * 4) = *reinterpret_cast<const float4*>(a.wE + g);
-      *reinterpret_cast<float4*>(sG + kk * H1 + v * 4) = *reinterpret_cast<const float4*>(a.wdG + g);
+      float4 g4 = *reinterpret_cast<const float4*>(a.wdG + g);
+      if (ACT == GCM_ACT_TANH) { g4.x *= 4.0f; g4.y *= 4.0f; g4.z *= 4.0f; g4.w *= 4.0f; }   // tanh' = 4 (u - u^2)
+      *reinterpret_cast<float4*>(sG + kk * H1 + v * 4) = g4;
     }
     __syncthreads();
     if (rl < rpp) {
-      for (int j = rl; j < C; j += rpp) {
-        const int p = lo + j;
-        const int slot = p % C;
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (p < hi) {
-          const int ka = max(k0, p - count0);
-          const int kb = min(k0 + kc - 1, p + N - count0 - 1);
-          if (ka <= kb) {
-            float q[4];
-            OnesCache<CT>::load4(cache + (size_t)slot * H1 + vl * 4, q);
-#pragma unroll 2
-            for (int k = ka; k <= kb; ++k) {
-              const float4 e4 = *reinterpret_cast<const float4*>(sE + (k - k0) * H1 + vl * 4);
-              const float4 g4 = *reinterpret_cast<const float4*>(sG + (k - k0) * H1 + vl * 4);
-              float d;
-              ones_eval<ACT>(e4.x, q[0], d); acc[0] = fmaf(g4.x, d, acc[0]);
-              ones_eval<ACT>(e4.y, q[1], d); acc[1] = fmaf(g4.y, d, acc[1]);
-              ones_eval<ACT>(e4.z, q[2], d); acc[2] = fmaf(g4.z, d, acc[2]);
-              ones_eval<ACT>(e4.w, q[3], d); acc[3] = fmaf(g4.w, d, acc[3]);
+      // a thread takes RB consecutive nodes at a time: the step's E / dG vectors are read from shared memory once for
+      // all of them (one node per thread moved 8 bytes of shared memory per evaluation: 240 GB per cfg3 window, the
+      // kernel ran at the shared-memory bandwidth, not at the MUFU rate)
+      constexpr int RB = 4;
+      for (int jb = rl * RB; jb < C; jb += rpp * RB) {
+        float acc[RB][4], q[RB][4];
+        int ka[RB], kb[RB];
+        int kmin = 0x7fffffff, kmax = -1;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int p = lo + jb + r;
+          acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+          q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0.0f;
+          ka[r] = 1;
+          kb[r] = 0;
+          if (jb + r < C && p < hi) {
+            const int a0 = max(k0, p - count0), b0 = min(k0 + kc - 1, p + N - count0 - 1);
+            if (a0 <= b0) {
+              ka[r] = a0;
+              kb[r] = b0;
+              kmin = min(kmin, a0);
+              kmax = max(kmax, b0);
+              OnesCache<CT>::load4(cache + (size_t)(p % C) * H1 + vl * 4, q[r]);
             }
           }
-          if (k0 == 0 && p >= count0) {
-            const float4 o4 = *reinterpret_cast<const float4*>(a.wdzo + (size_t)(p - count0) * a.sstride +
-                                                               (size_t)b * H1 + vl * 4);
-            acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w;
+        }
+#pragma unroll 2
+        for (int k = kmin; k <= kmax; ++k) {
+          const float4 e4 = *reinterpret_cast<const float4*>(sE + (k - k0) * H1 + vl * 4);
+          const float4 g4 = *reinterpret_cast<const float4*>(sG + (k - k0) * H1 + vl * 4);
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            if (k < ka[r] || k > kb[r]) continue;
+            if (ACT == GCM_ACT_TANH) {
+              // two evaluations per MUFU; g4 was staged times 4:  acc += 4 g (u - u^2)
+              float u0, u1, u2, u3;
+              ones_u2(e4.x, q[r][0], e4.y, q[r][1], u0, u1);
+              ones_u2(e4.z, q[r][2], e4.w, q[r][3], u2, u3);
+              acc[r][0] = fmaf(g4.x, fmaf(-u0, u0, u0), acc[r][0]);
+              acc[r][1] = fmaf(g4.y, fmaf(-u1, u1, u1), acc[r][1]);
+              acc[r][2] = fmaf(g4.z, fmaf(-u2, u2, u2), acc[r][2]);
+              acc[r][3] = fmaf(g4.w, fmaf(-u3, u3, u3), acc[r][3]);
+            } else {
+              float d;
+              ones_eval<ACT>(e4.x, q[r][0], d); acc[r][0] = fmaf(g4.x, d, acc[r][0]);
+              ones_eval<ACT>(e4.y, q[r][1], d); acc[r][1] = fmaf(g4.y, d, acc[r][1]);
+              ones_eval<ACT>(e4.z, q[r][2], d); acc[r][2] = fmaf(g4.z, d, acc[r][2]);
+              ones_eval<ACT>(e4.w, q[r][3], d); acc[r][3] = fmaf(g4.w, d, acc[r][3]);
+            }
           }
         }
-        float4* out = reinterpret_cast<float4*>(DZ + (size_t)slot * H1 + vl * 4);
-        if (k0 == 0) {
-          *out = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        } else {
-          float4 o = *out;
-          o.x += acc[0]; o.y += acc[1]; o.z += acc[2]; o.w += acc[3];
-          *out = o;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (jb + r >= C) continue;
+          const int p = lo + jb + r;
+          if (p < hi && k0 == 0 && p >= count0) {
+            const float4 o4 = *reinterpret_cast<const float4*>(a.wdzo + (size_t)(p - count0) * a.sstride +
+                                                               (size_t)b * H1 + vl * 4);
+            acc[r][0] += o4.x; acc[r][1] += o4.y; acc[r][2] += o4.z; acc[r][3] += o4.w;
+          }
+          float4* out = reinterpret_cast<float4*>(DZ + (size_t)(p % C) * H1 + vl * 4);
+          if (k0 == 0) {
+            *out = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          } else {
+            float4 o = *out;
+            o.x += acc[r][0]; o.y += acc[r][1]; o.z += acc[r][2]; o.w += acc[r][3];
+            *out = o;
+          }
         }
       }
     }

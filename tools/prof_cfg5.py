@@ -8,7 +8,7 @@ import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 grad = len(sys.argv) > 2 and sys.argv[2] == "grad"
 dev = torch.device("cuda:0")
-N, F, H = 4096, 64, 64
+N, F, H = int(os.environ.get("GCM_PROF_N", "4096")), 64, 64      # GCM_PROF_N=256 with B=16384: small graphs, same node count
 mod = bench.build_sparse(dev, N, F, H)
 gen = torch.Generator().manual_seed(1005)
 x = torch.randn(B, N, F, generator=gen)
