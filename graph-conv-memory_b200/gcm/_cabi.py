@@ -160,6 +160,7 @@ _SIGNATURES = {
     "gcm_pack_edges": (_I, [_P, _P, _L, _I, _I, _L, C.c_float, _P, _P, _P, _P]),
     "gcm_count_valid_edges": (_I, [_P, _I, _I, _P, _P]),
     "gcm_unpack_edges": (_I, [_P, _P, _I, _I, _P, _L, _P, _P, _P]),
+    "gcm_any_nonfinite": (_I, [_P, _L, _P, _P]),
     "gcm_tc_selftest": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 

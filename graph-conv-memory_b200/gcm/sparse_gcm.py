@@ -79,6 +79,17 @@ def _one_bias(conv):
     return b_rel if b_rel is not None else b_root
 
 
+def _all_finite(t: torch.Tensor) -> bool:
+    """torch.all(torch.isfinite(t)) as ONE pass (gcm_any_nonfinite) -- the check of sparse_gcm.py:203."""
+    t = t.detach()
+    if not (t.is_cuda and t.dtype is torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0):
+        return bool(torch.all(torch.isfinite(t)))
+    flag = torch.zeros(1, dtype=torch.int32, device=t.device)
+    _cabi.check(_cabi.lib().gcm_any_nonfinite(t.data_ptr(), t.numel(), flag.data_ptr(), _cabi.stream_ptr(t.device)),
+                "gcm_any_nonfinite")
+    return int(flag.item()) == 0
+
+
 class SparseGCM(torch.nn.Module):
     """Graph Associative Memory using sparse-graph representations"""
 
@@ -244,7 +255,7 @@ class SparseGCM(torch.nn.Module):
                 h[rows1] = h_sub                                            # rows nobody reads stay unwritten
         mx = sparse_ops.graph_conv_csr(h, csr, rows, c2.lin_rel.weight, _one_bias(c2), c2.lin_root.weight, a2,
                                        edge_mask=mask)
-        assert torch.all(torch.isfinite(mx)), "Got NaN in returned memory, try using tanh activation"
+        assert _all_finite(mx), "Got NaN in returned memory, try using tanh activation"
 
         if n_new == B * tmax:
             mx_dense = mx.view(B, tmax, mx.shape[-1])       # no padding anywhere: the flat rows ARE the padded layout

@@ -500,6 +500,9 @@ int gcm_pack_edges(const int64_t* coo, const float* vals, long long E, int B, in
 int gcm_count_valid_edges(const int64_t* dense_edges, int B, int max_edges, int64_t* counts, void* stream);
 int gcm_unpack_edges(const int64_t* dense_edges, const float* dense_weights, int B, int max_edges, const int64_t* offsets,
                      long long E, int64_t* coo, float* vals, void* stream);
+/* sets *flag (device int32, |= 1) when any of the n floats is NaN or +-inf: the finite check of SparseGCM.forward
+ * (sparse_gcm.py:203) as one pass.  x 16-byte aligned. */
+int gcm_any_nonfinite(const float* x, long long n, int32_t* flag, void* stream);
 
 /* Self-test of the tcgen05/TMEM building block of the tensor-core step kernels:
  * D[128,N] = A[128,K] B[N,K]^T, passes = 3 (3xTF32, fp32-accurate) or 1 (plain tf32).  Test hook only. */

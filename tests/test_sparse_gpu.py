@@ -422,3 +422,19 @@ def test_graphconv_block_local_kernel_matches_the_others(F, H, act, masked):
     if mask is None:
         for ga, gb in zip(grads[_cabi.GC_CUDA_CORES], grads[_cabi.GC_TC]):
             assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
+
+
+def test_finite_check_kernel_finds_nan_and_inf_anywhere():
+    """gcm_any_nonfinite (the one-pass form of sparse_gcm.py:203's assert) against torch.isfinite: clean data, one NaN /
+    +inf / -inf at the start, in the middle, in the unaligned tail."""
+    from gcm.sparse_gcm import _all_finite
+
+    dev = torch.device("cuda:0")
+    for n in (1, 3, 4, 1027, 1 << 20, (1 << 20) + 3):
+        x = torch.randn(n, device=dev)
+        assert _all_finite(x)
+        for pos in {0, n // 2, n - 1}:
+            for bad in (float("nan"), float("inf"), float("-inf")):
+                y = x.clone()
+                y[pos] = bad
+                assert not _all_finite(y), (n, pos, bad)
