@@ -187,6 +187,7 @@ def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
     new_off = sparse_ops._excl_cumsum(taus)
     n_new, tmax = int(taus.sum()), int(taus.max())
     got = {}
+    saved_cap = sparse_ops.HIT_CAP
     try:
         for name, which in (("pairs", _cabi.EB_PAIRS), ("hash", _cabi.EB_HASH)):
             _cabi.check(lib.gcm_set_edge_builder(which), "gcm_set_edge_builder")
@@ -205,7 +206,7 @@ def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
                 assert int(edge_off[-1]) == e.shape[1]
     finally:
         lib.gcm_set_edge_builder(_cabi.EB_AUTO)
-        sparse_ops.HIT_CAP = 64
+        sparse_ops.HIT_CAP = saved_cap
     assert got[("pairs", 1)].shape[1] > 0
     for k in got:
         assert torch.equal(got[("pairs", 1)], got[k]), k
