@@ -108,22 +108,78 @@ def overflow(num_nodes: torch.Tensor, N: int):
     return torch.any(num_nodes + 1 > N)
 
 
-def _apply_pre(pre, t: torch.Tensor) -> torch.Tensor:
+def _apply_pre(pre, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The row-wise preprocessor on a block of observations (no autograd).  A plain float32 Linear -- RayDenseGCM's,
     ray_gcm.py:118 -- runs on the library's own product kernel (3xTF32 on the tensor cores when both widths are
     multiples of 16): cuBLAS picked a SIMT sgemm plus a separate bias kernel for these narrow shapes, 16 us per cfg2-pre
-    step against 4."""
+    step against 4.  out: a contiguous float32 tensor of the result's shape to write into."""
     if (type(pre) is torch.nn.Linear and t.is_cuda and t.dtype is torch.float32 and t.is_contiguous()
             and pre.weight.dtype is torch.float32 and pre.weight.is_cuda and pre.out_features <= 128
             and pre.in_features <= 128 and t.numel() > 0):
-        a = t.reshape(-1, pre.in_features)
+        a = t.detach().reshape(-1, pre.in_features)
         w = pre.weight.detach()
         bias = None if pre.bias is None else pre.bias.detach()
+        o2 = None
+        if out is not None and out.is_contiguous() and out.dtype is torch.float32 and out.numel() == a.shape[0] * pre.out_features:
+            o2 = out.view(-1, pre.out_features)
         if pre.in_features % 16 == 0 and pre.out_features % 16 == 0:
-            y = ones._lin_tc32(a, w, bias=bias)
+            y = ones._lin_tc32(a, w, bias=bias, out=o2)
         else:
-            y = ones._lin2(a, w, bias=bias)
-        return y.view(*t.shape[:-1], pre.out_features)
+            y = ones._lin2(a, w, bias=bias, out=o2)
+        return out if o2 is not None else y.view(*t.shape[:-1], pre.out_features)
+    y = pre(t)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+class _PreLinearFn(torch.autograd.Function):
+    """y = x W^T + b for a row-wise Linear preprocessor, with autograd, on the library's 3xTF32 kernels (forward and
+    dL/dx: gcm_linear_tc32, dL/dW and dL/db: gcm_outer_reduce_tc32).  The training window of RayDenseGCM spent 5 of its 12
+    ms in cuBLAS' SIMT sgemm + bias kernels for these 32-wide products.  A [B, T, F] view of time-major data is
+    processed (and returned) in its memory order."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        tm = x.dim() == 3 and not x.is_contiguous() and x.transpose(0, 1).is_contiguous()
+        xc = (x.transpose(0, 1) if tm else x.contiguous()).detach()
+        a = xc.reshape(-1, weight.shape[1])
+        y = ones._lin_tc32(a, weight.detach(), bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(a, weight)
+        ctx.tm, ctx.shape, ctx.has_bias = tm, xc.shape, bias is not None
+        y = y.view(*xc.shape[:-1], weight.shape[0])
+        return y.transpose(0, 1) if tm else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight = ctx.saved_tensors
+        dyc = (dy.transpose(0, 1) if ctx.tm else dy).contiguous().float()
+        d2 = dyc.reshape(-1, weight.shape[0])
+        dx = dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(weight)
+            db = torch.zeros(weight.shape[0], device=weight.device, dtype=torch.float32)
+            temporal._outer(d2, a, dw, db)
+            if not ctx.has_bias:
+                db = None
+        if ctx.needs_input_grad[0]:
+            dx = ones._lin_tc32(d2, weight.detach().t().contiguous()).view(ctx.shape)
+            if ctx.tm:
+                dx = dx.transpose(0, 1)
+        return dx, dw, db
+
+
+def _pre_own_kernels(pre, t: torch.Tensor) -> bool:
+    return (type(pre) is torch.nn.Linear and t.is_cuda and t.dtype is torch.float32 and pre.weight.dtype is torch.float32
+            and pre.weight.is_cuda and pre.in_features % 16 == 0 and pre.out_features % 16 == 0
+            and pre.in_features <= 128 and pre.out_features <= 128 and t.numel() > 0)
+
+
+def _apply_pre_grad(pre, t: torch.Tensor) -> torch.Tensor:
+    """The preprocessor with autograd (training windows)."""
+    if _pre_own_kernels(pre, t) and torch.is_grad_enabled():
+        return _PreLinearFn.apply(t, pre.weight, pre.bias)
     return pre(t)
 
 
@@ -572,7 +628,8 @@ class DenseGCM(torch.nn.Module):
                 if state.pre_key != pkey:
                     if token is not None:
                         raise RuntimeError("preprocessor parameters were modified in place inside a recorded window")
-                    state.nodes.copy_(pre(state.raw))          # new weights: every stored row gets its new image
+                    with torch.no_grad():
+                        _apply_pre(pre, state.raw, out=state.nodes)   # new weights: every stored row gets its new image
                     state.pre_key = pkey
                     state.xsum, state.rc_key, state.hc_key, state.hc_fresh, state.fast_ok = None, None, None, 0, False
                 if token is None and (state.C - state.N + 1 < T or state.C - state.N < 1):
@@ -600,11 +657,11 @@ class DenseGCM(torch.nn.Module):
             P0 = state.host_count
             pos = torch.arange(P0 - 2 * mh, P0, device=dev)
             raw_hist = state.raw[:, pos.clamp(min=0) % state.C]
-            hist = pre(raw_hist) * (pos >= 0).view(1, -1, 1).to(raw_hist.dtype)
+            hist = _apply_pre_grad(pre, raw_hist) * (pos >= 0).view(1, -1, 1).to(raw_hist.dtype)
         if not DenseGCM.did_warn and state.host_count + T > state.N:
             print("Overflow detected, wrapping around. Will not warn again")
             DenseGCM.did_warn = True
-        y_seq = pre(x_seq)
+        y_seq = _apply_pre_grad(pre, x_seq)
         beliefs, token, state = temporal.sequence_grad(plan, state, y_seq, token, cap, hist=hist)
         if not plan.validated:
             plan.validated = True

@@ -9,7 +9,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 dev = torch.device("cuda:0")
 N, F, H = 128, 32, 32
-mod = bench.build_dense(dev, N, F, H, [("temporal", (1, 2, 4), "forward")])
+mod = bench.build_dense(dev, N, F, H, [("temporal", (1, 2, 4), "forward")], pre=bool(os.environ.get("GCM_PROF_PRE")))   # GCM_PROF_PRE=1: with RayDenseGCM's Linear preprocessor (its parameters train too)
 mod.bptt_capacity = T
 opt = torch.optim.SGD(mod.parameters(), lr=1e-3)
 gen = torch.Generator().manual_seed(1003)
