@@ -20,7 +20,7 @@ JSON line (rank 0):
   also         fwd+bwd records of the same run: cfg2-bptt (BPTT over T=64 steps of the cfg2 chain) and cfg3 (DenseEdge
                N=256 H=128 T=64 with the NCCL gradient all-reduce), each with its own roofline / clocks / e2e
 
-Other workloads (`--workload cfg1|cfg2-pre|cfg2-bptt|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the
+Other workloads (`--workload cfg1|cfg2-pre|cfg2-bptt|cfg2-pre-bptt|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the
 remaining BASELINE configs with the same line format; `--impl reference` times the reference on CPU (the unmodified
 reference package from baseline/_ref when it is installed, else the oracle port).
 """
@@ -48,6 +48,9 @@ WORKLOADS = {
                  "rollout"),
     "cfg2-bptt": ("cfg2 chain, BPTT T=64 fwd+bwd on full graphs (truncated BPTT on a running rollout: m_t.detach() per "
                   "window), SGD step, gradient all-reduce", 65536, 128, 32, 32, [("temporal", (1, 2, 4), "forward")], "bptt"),
+    "cfg2-pre-bptt": ("cfg2-bptt with RayDenseGCM's Linear(32,32) preprocessor, whose parameters train too (SURVEY 8(f) rank 2: "
+                      "gradients reach it through every stored row, gcm.py:290-291)", 65536, 128, 32, 32,
+                      [("temporal", (1, 2, 4), "forward")], "bptt"),
     "cfg3": ("cfg3: DenseGCM DenseEdge N=256 F=H=128 BPTT T=64 fwd+bwd (DenseEdge-only kernels, bf16 per-node cache, fp32 accumulate)",
              16384, 256, 128, 128, [("dense",)], "bptt"),
     "cfg3-seq": ("cfg3 through DenseGCM.forward_sequence (SURVEY 8(f) rank 1): the T=64 steps of a window in one call, "
@@ -210,7 +213,8 @@ def algorithmic(workload, B, N, F, H, extra=None):
         r2 = len({0} | set(hops) | {a + b for a in hops for b in hops})
         per = r2 * F * 4 + F * 4 + F * 4 + N // 8 + H * 4 + 16
         return "hbm", per * B, "bytes"
-    if workload == "cfg2-bptt":
+    if workload in ("cfg2-bptt", "cfg2-pre-bptt"):
+        # (cfg2-pre-bptt: the preprocessor's own rows are NOT counted, so its fraction is a lower bound)
         # per graph-step of a BPTT window: the forward's 1 440 B (SURVEY 8(d) k-hop figure) + the
         # backward's streams: dL/dbelief and the belief (act2'), h_t and its act1', the node row, dL/dx written
         hops = WORKLOADS[workload][5][0][1]
@@ -619,7 +623,7 @@ def run_bptt(ctx, workload, B, K, W, args):
     gen = torch.Generator().manual_seed(1002 + ctx.rank)
     T = BPTT_T
     temporal = spec[0][0] == "temporal"
-    mod = build_dense(dev, N, F, H, spec)
+    mod = build_dense(dev, N, F, H, spec, pre=workload == "cfg2-pre-bptt")
     mod.bptt_capacity = T
     if not temporal:
         mod.compute_dtype = torch.bfloat16 if args.cache == "bf16" else None
