@@ -270,3 +270,63 @@ def test_training_with_preprocessor_matches_reference_golden(name, mode):
     final = tuple(hidden)
     assert torch.equal(final[0].cpu(), g["final"][0]) and torch.equal(final[1].cpu(), g["final"][1].float())
     assert torch.equal(final[3].cpu(), g["final"][3])
+
+
+def test_training_windows_with_preprocessor_updates_match_the_generic_path():
+    """Truncated BPTT over several windows with SGD updates of the GNN AND of the Linear preprocessor in between: the fused
+    route (own product kernels for the preprocessor, only the last 2 max_hop stored rows re-imaged after an update, fused
+    window backward) against the same module on the generic torch route (reference statement order, gcm.py:241-321, every
+    stored row through the preprocessor at every step).  Beliefs of every window and the parameters after every update."""
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F_raw, F, H, T = 37, 12, 16, 32, 32, 7
+    spec = [("temporal", (1, 2, 4), "forward")]
+    gen = torch.Generator().manual_seed(11)
+    obs = (torch.randn(5, T, B, F_raw, generator=gen) * 0.7).to(dev)
+    w = torch.randn(5, T, B, H, generator=gen).to(dev)
+    p = oracle.make_params(F, H)
+    mods = []
+    for fused_route in (True, False):
+        gnn, convs = make_dense_gnn(F, H, p, ("tanh", "tanh"))
+        pre = torch.nn.Linear(F_raw, F)
+        with torch.no_grad():
+            g2 = torch.Generator().manual_seed(12)
+            pre.weight.copy_(torch.randn(F, F_raw, generator=g2) / F_raw ** 0.5)
+            pre.bias.copy_(0.1 * torch.randn(F, generator=g2))
+        mod = DenseGCM(gnn.to(dev), preprocessor=pre.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+        if not fused_route:
+            mod._plan, mod._plan_built = None, True            # no fused plan: DenseGCM._forward_generic
+        mods.append((mod, torch.optim.SGD(mod.parameters(), lr=0.01)))
+    hidden = [None, None]
+    pre0 = [q.detach().clone() for q in mods[0][0].preprocessor.parameters()]
+    for win in range(4):
+        outs = []
+        for i, (mod, opt) in enumerate(mods):
+            opt.zero_grad(set_to_none=True)
+            h = hidden[i]
+            if h is not None:
+                h = h.detach() if hasattr(h, "detach") else tuple(t.detach() for t in h)
+            if i == 0:
+                o, h = mod.forward_sequence(obs[win], h, time_major=True)
+            else:
+                steps = []
+                for t in range(T):
+                    ot, h = mod(obs[win, t], h)
+                    steps.append(ot)
+                o = torch.stack(steps)
+            (o * w[win]).sum().backward()
+            opt.step()
+            hidden[i] = h
+            outs.append(o.detach())
+        # the updates are large (lr 0.01 on a sum loss: the preprocessor's weights move by > 1e-2 per window), so a stale
+        # image of a stored row would show at the 1e-2 level; fp32 rounding of two different evaluation orders, amplified
+        # through the updates, stays below 1e-3
+        tol = 2e-5 if win == 0 else 1e-3
+        assert rel_err(outs[0], outs[1]) < tol, f"beliefs of window {win}"
+        for (n0, p0), (n1, p1) in zip(mods[0][0].named_parameters(), mods[1][0].named_parameters()):
+            assert n0 == n1 and rel_err(p0.detach(), p1.detach()) < (5e-5 if win == 0 else 1e-3), f"{n0} after window {win}"
+        if win == 0:
+            moved = max(float((p0.detach() - q0).abs().max()) for p0, q0 in zip(mods[0][0].preprocessor.parameters(), pre0))
+            assert moved > 1e-2, "the test needs updates that matter"
+    assert getattr(hidden[0].token, "_gcm_tw", False)
