@@ -491,7 +491,9 @@ def run_rollout(ctx, workload, B, K, W, args):
             # sharing the host) would sit in front of ~450 us of device work and be charged to every step.  A short
             # spinning kernel queued BEFORE the start event keeps the stream busy while the host makes the call -- the
             # state any step but the first of a rollout is in -- so the events bracket exactly the K steps on the device.
-            torch.cuda._sleep(int(4.0e5))                      # ~200 us at 1.9 GHz, outside the timed region
+            torch.cuda._sleep(int(2.0e6))                      # ~1 ms at 1.9 GHz, outside the timed region (200 us was not
+                                                               # always enough with several ranks sharing the host: 22.9
+                                                               # instead of 20.6 us per step at N = 2)
             e0.record()
             beliefs, hidden = mod.forward_sequence(x_seq, hidden, time_major=True)
             e1.record()
