@@ -131,8 +131,27 @@ __device__ __forceinline__ int eh_cell(float x, float inv_side) {
   const float c = floorf(x * inv_side);
   return c != c ? 0 : (c > 1.0e9f ? 1000000000 : (c < -1.0e9f ? -1000000000 : (int)c));
 }
-__device__ __forceinline__ int eh_bucket(int cx, int cy) {
-  return (int)(((uint32_t)cx * 73856093u) ^ ((uint32_t)cy * 19349663u)) & (EH_BUCKETS - 1);
+// Bucket of cell (cx, cy): a hashed ROW of the table per cy, the column is cx modulo the row length -- so the three cells
+// cx - 1 .. cx + 1 of one cy are ONE contiguous run of buckets (two runs when the column wraps), and a sink scans three
+// runs of the bucket-sorted node list instead of nine separate buckets.  colbits = 6 (128 rows x 64 columns) for 2-D cells,
+// 13 (one row) for 1-D positions.  Cells that share a bucket only add candidates.
+__device__ __forceinline__ int eh_row(int cy, int colbits) {
+  return colbits >= 13 ? 0 : (int)(((uint32_t)cy * 2654435761u) >> (19 + colbits)) << colbits;
+}
+__device__ __forceinline__ int eh_bucket(int cx, int cy, int colbits) {
+  return eh_row(cy, colbits) + (cx & ((1 << colbits) - 1));
+}
+// smallest float t with sqrtf(t) >= r: sqrtf is correctly rounded and monotone, so  sqrtf(d2) < r  <=>  d2 < t  for every
+// d2 (NaN and +inf fail both) -- the pair test of k_sparse_edges without the square root
+__device__ __forceinline__ float eh_sq_threshold(float r) {
+  float c = r * r;
+  while (c > 0.0f && sqrtf(c) >= r) c = __uint_as_float(__float_as_uint(c) - 1u);        // now sqrtf(c) < r (or c == 0)
+  if (!(sqrtf(c) < r)) return c;                                                          // r <= 0: nothing passes
+  for (;;) {
+    const float up = __uint_as_float(__float_as_uint(c) + 1u);
+    if (!(sqrtf(up) < r)) return up;
+    c = up;
+  }
 }
 
 __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenArgs a) {
@@ -145,6 +164,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   const int n = s_end;                       // sources of these sinks are < s_end
   const int W = (a.N + 31) >> 5;
   const int PL = a.pos_len;
+  const int colbits = PL > 1 ? 6 : 13;
   float* pos = reinterpret_cast<float*>(eh_smem);                        // [n][PL]
   uint32_t* bits = reinterpret_cast<uint32_t*>(pos + (size_t)a.N * PL);  // [warps][W]
   uint16_t* bstart = reinterpret_cast<uint16_t*>(bits + (EH_THREADS / 32) * W);   // [EH_BUCKETS + 1]
@@ -155,6 +175,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = EH_THREADS / 32;
   const float* nodes_b = a.nodes + (size_t)b * a.N * a.F;
   const float inv_side = 1.0f / (a.radius * 1.0009765625f);
+  const float t2 = eh_sq_threshold(a.radius);
 
   for (int i = tid; i < n * PL; i += EH_THREADS) {
     const int k = i / PL, c = i - k * PL;
@@ -167,7 +188,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   for (int k = tid; k < n; k += EH_THREADS) {
     const int cx = eh_cell(pos[k * PL], inv_side);
     const int cy = PL > 1 ? eh_cell(pos[k * PL + 1], inv_side) : 0;
-    const int bk = eh_bucket(cx, cy);
+    const int bk = eh_bucket(cx, cy, colbits);
     bkt[k] = (uint16_t)bk;
     // two buckets share one 32-bit word of bstart (offset by one so that the scan is exclusive)
     atomicAdd(reinterpret_cast<unsigned int*>(bstart) + ((bk + 1) >> 1), ((bk + 1) & 1) ? 0x10000u : 1u);
@@ -215,11 +236,24 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   __syncthreads();
 
   uint32_t* my = bits + warp * W;
-  const int wpl = (W + 31) / 32;                   // bitmask words per lane (contiguous chunk)
+  const int ncols = 1 << colbits;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // one candidate of the bucket-sorted list: causal filter, the pair test of k_sparse_edges, hit -> bit of the source
+  auto test = [&](int idx, int s) {
+    const int k = sorted[idx];
+    if (k < s) {
+      float d2 = 0.0f;
+      for (int cc = 0; cc < PL; ++cc) {
+        const float df = pos[s * PL + cc] - pos[k * PL + cc];
+        d2 += df * df;
+      }
+      if (d2 < t2) atomicOr(my + (k >> 5), 1u << (k & 31));
+    }
+  };
   for (int s = s_begin + warp; s < s_end; s += nwarps) {
+    const int64_t slot = a.new_off[b] + (s - t0);
     if (a.edges && a.hit_cap > 0) {   // pass 2 after an expansion: only the nodes whose list overflowed are searched again
-      const int64_t sl = a.new_off[b] + (s - t0);
-      if (a.edge_off[sl + 1] - a.edge_off[sl] <= a.hit_cap) continue;
+      if (a.edge_off[slot + 1] - a.edge_off[slot] <= a.hit_cap) continue;
     }
     for (int w = lane; w < W; w += 32) my[w] = 0u;
     __syncwarp();
@@ -230,78 +264,67 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
     if (s > 0) {
       const int cx = eh_cell(pos[s * PL], inv_side);
       const int cy = PL > 1 ? eh_cell(pos[s * PL + 1], inv_side) : 0;
-      const int ncell = PL > 1 ? 9 : 3;
-      for (int c = 0; c < ncell; ++c) {
-        const int dx = c % 3 - 1, dy = PL > 1 ? c / 3 - 1 : 0;
-        const int bk = eh_bucket(cx + dx, cy + dy);
-        const int i0 = bstart[bk], i1 = bstart[bk + 1];
-        for (int i = i0 + lane; i < i1; i += 32) {
-          const int k = sorted[i];
-          if (k < s) {
-            float d2 = 0.0f;
-            for (int cc = 0; cc < PL; ++cc) {
-              const float df = pos[s * PL + cc] - pos[k * PL + cc];
-              d2 += df * df;
-            }
-            if (sqrtf(d2) < a.radius) atomicOr(my + (k >> 5), 1u << (k & 31));
-          }
+      const int col0 = (cx - 1) & (ncols - 1);
+      const int cend = min(col0 + 3, ncols);
+      // the runs of the three cell rows, walked as one list: candidate c sits at c + off of its run
+      int e0, e1, tot, o0, o1, o2;
+      {
+        const int r0 = eh_row(PL > 1 ? cy - 1 : cy, colbits);
+        const int b0 = bstart[r0 + col0];
+        e0 = bstart[r0 + cend] - b0;
+        o0 = b0;
+        e1 = e0;
+        tot = e0;
+        o1 = o2 = 0;
+        if (PL > 1) {
+          const int r1 = eh_row(cy, colbits), r2 = eh_row(cy + 1, colbits);
+          const int b1 = bstart[r1 + col0], b2 = bstart[r2 + col0];
+          e1 = e0 + (bstart[r1 + cend] - b1);
+          tot = e1 + (bstart[r2 + cend] - b2);
+          o1 = b1 - e0;
+          o2 = b2 - e1;
+        }
+      }
+      for (int c = lane; c < tot; c += 32) test(c + (c < e0 ? o0 : (c < e1 ? o1 : o2)), s);
+      if (col0 + 3 > ncols) {
+        // the column wrapped: the rest of each row's run starts at the row's first bucket
+        const int wl = col0 + 3 - ncols;
+        for (int dy = (PL > 1 ? -1 : 0); dy <= (PL > 1 ? 1 : 0); ++dy) {
+          const int r = eh_row(cy + dy, colbits);
+          const int i0 = bstart[r], i1 = bstart[r + wl];
+          for (int i = i0 + lane; i < i1; i += 32) test(i, s);
         }
       }
     }
     __syncwarp();
-    // count / emit in ascending source order
-    int cnt = 0;
-    for (int j = 0; j < wpl; ++j) {
-      const int w = lane * wpl + j;
-      if (w < W) cnt += __popc(my[w]);
-    }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(GCM_FULL_MASK, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int64_t slot = a.new_off[b] + (s - t0);
-    if (!a.edges) {
-      if (lane == 31) a.deg[slot] = incl;
-      if (a.hits) {
-        // walk the NON-EMPTY mask words in ascending order, the whole warp on one word at a time (lane = bit): the
-        // sources of a sink sit in a handful of words, and a per-lane bit loop serialised on the lane that owned most
-        // of them (16.6 divergent iterations per sink, 19 % of the kernel's instructions)
-        uint32_t lanes = __ballot_sync(GCM_FULL_MASK, cnt != 0);   // lanes whose chunk of words has any bit
-        int base = 0;
-        while (lanes) {
-          const int L = __ffs(lanes) - 1;
-          lanes &= lanes - 1;
-          for (int j = 0; j < wpl; ++j) {
-            const int w = L * wpl + j;
-            if (w >= W) break;
-            const uint32_t word = my[w];                              // shared memory: the same word for every lane
-            if (!word) continue;
-            if ((word >> lane) & 1u) {
-              const int at = base + __popc(word & ((1u << lane) - 1u));
-              if (at < a.hit_cap) a.hits[slot * a.hit_cap + at] = (uint16_t)(w * 32 + lane);
-            }
-            base += __popc(word);
+    // emit in ascending source order: word w of the mask belongs to lane w % 32; the warp walks the NON-EMPTY words in
+    // ascending order, all lanes on one word at a time (lane = bit)
+    const int64_t e_base = a.edges ? a.edge_off[slot] : 0;
+    int base = 0;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+      const uint32_t mine = (w0 + lane < W) ? my[w0 + lane] : 0u;
+      uint32_t nz = __ballot_sync(GCM_FULL_MASK, mine != 0u);
+      while (nz) {
+        const int L = __ffs(nz) - 1;
+        nz &= nz - 1;
+        const uint32_t word = __shfl_sync(GCM_FULL_MASK, mine, L);
+        if ((word >> lane) & 1u) {
+          const int at = base + __popc(word & lt_mask);
+          const int src = (w0 + L) * 32 + lane;
+          if (!a.edges) {
+            if (a.hits && at < a.hit_cap) a.hits[slot * a.hit_cap + at] = (uint16_t)src;
+          } else {
+            const int64_t e = e_base + at;
+            a.edges[e] = b;
+            a.edges[a.E + e] = s;
+            a.edges[2 * a.E + e] = src;
+            if (a.flat_col) a.flat_col[e] = a.flat_off[b] + src;
           }
         }
-      }
-    } else {
-      int64_t e = a.edge_off[slot] + (incl - cnt);
-      for (int j = 0; j < wpl; ++j) {
-        const int w = lane * wpl + j;
-        uint32_t m = w < W ? my[w] : 0u;
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          a.edges[e] = b;
-          a.edges[a.E + e] = s;
-          a.edges[2 * a.E + e] = w * 32 + bit;
-          if (a.flat_col) a.flat_col[e] = a.flat_off[b] + w * 32 + bit;
-          ++e;
-        }
+        base += __popc(word);
       }
     }
+    if (!a.edges && lane == 0) a.deg[slot] = base;
     __syncwarp();
   }
 }
