@@ -154,6 +154,8 @@ __device__ __forceinline__ float eh_sq_threshold(float r) {
   }
 }
 
+// PLT: compile-time pos_len (2: positions as float2, the sink's position in registers), 0 = run-time a.pos_len
+template <int PLT>
 __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenArgs a) {
   extern __shared__ __align__(16) unsigned char eh_smem[];
   const int b = blockIdx.x;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   if (s_begin >= s_end) return;
   const int n = s_end;                       // sources of these sinks are < s_end
   const int W = (a.N + 31) >> 5;
-  const int PL = a.pos_len;
+  const int PL = PLT ? PLT : a.pos_len;
   const int colbits = PL > 1 ? 6 : 13;
   float* pos = reinterpret_cast<float*>(eh_smem);                        // [n][PL]
   uint32_t* bits = reinterpret_cast<uint32_t*>(pos + (size_t)a.N * PL);  // [warps][W]
@@ -239,31 +241,47 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
   const int ncols = 1 << colbits;
   const uint32_t lt_mask = (1u << lane) - 1u;
   // one candidate of the bucket-sorted list: causal filter, the pair test of k_sparse_edges, hit -> bit of the source
+  float sx = 0.0f, sy = 0.0f;                       // PLT == 2: the sink's position
   auto test = [&](int idx, int s) {
     const int k = sorted[idx];
     if (k < s) {
       float d2 = 0.0f;
-      for (int cc = 0; cc < PL; ++cc) {
-        const float df = pos[s * PL + cc] - pos[k * PL + cc];
-        d2 += df * df;
+      if (PLT == 2) {
+        const float2 pk = reinterpret_cast<const float2*>(pos)[k];
+        const float dx = sx - pk.x, dy = sy - pk.y;
+        d2 += dx * dx;
+        d2 += dy * dy;
+      } else {
+        for (int cc = 0; cc < PL; ++cc) {
+          const float df = pos[s * PL + cc] - pos[k * PL + cc];
+          d2 += df * df;
+        }
       }
       if (d2 < t2) atomicOr(my + (k >> 5), 1u << (k & 31));
     }
   };
+  for (int w = lane; w < W; w += 32) my[w] = 0u;       // the emission walk leaves the mask clear again
+  __syncwarp();
   for (int s = s_begin + warp; s < s_end; s += nwarps) {
     const int64_t slot = a.new_off[b] + (s - t0);
     if (a.edges && a.hit_cap > 0) {   // pass 2 after an expansion: only the nodes whose list overflowed are searched again
       if (a.edge_off[slot + 1] - a.edge_off[slot] <= a.hit_cap) continue;
     }
-    for (int w = lane; w < W; w += 32) my[w] = 0u;
-    __syncwarp();
     if (lane < a.n_hops) {
       const int k = s - a.hops[lane];
       if (k >= 0) atomicOr(my + (k >> 5), 1u << (k & 31));
     }
     if (s > 0) {
-      const int cx = eh_cell(pos[s * PL], inv_side);
-      const int cy = PL > 1 ? eh_cell(pos[s * PL + 1], inv_side) : 0;
+      if (PLT == 2) {
+        const float2 ps = reinterpret_cast<const float2*>(pos)[s];
+        sx = ps.x;
+        sy = ps.y;
+      } else {
+        sx = pos[s * PL];
+        sy = PL > 1 ? pos[s * PL + 1] : 0.0f;
+      }
+      const int cx = eh_cell(sx, inv_side);
+      const int cy = PL > 1 ? eh_cell(sy, inv_side) : 0;
       const int col0 = (cx - 1) & (ncols - 1);
       const int cend = min(col0 + 3, ncols);
       // the runs of the three cell rows, walked as one list: candidate c sits at c + off of its run
@@ -300,9 +318,12 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
     // emit in ascending source order: word w of the mask belongs to lane w % 32; the warp walks the NON-EMPTY words in
     // ascending order, all lanes on one word at a time (lane = bit)
     const int64_t e_base = a.edges ? a.edge_off[slot] : 0;
+    uint16_t* hrow = a.hits ? a.hits + slot * a.hit_cap : nullptr;
+    const int hcap = hrow ? a.hit_cap : 0;
     int base = 0;
     for (int w0 = 0; w0 < W; w0 += 32) {
       const uint32_t mine = (w0 + lane < W) ? my[w0 + lane] : 0u;
+      if (mine) my[w0 + lane] = 0u;
       uint32_t nz = __ballot_sync(GCM_FULL_MASK, mine != 0u);
       while (nz) {
         const int L = __ffs(nz) - 1;
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(EH_THREADS) k_sparse_edges_hash(const EdgeGenA
           const int at = base + __popc(word & lt_mask);
           const int src = (w0 + L) * 32 + lane;
           if (!a.edges) {
-            if (a.hits && at < a.hit_cap) a.hits[slot * a.hit_cap + at] = (uint16_t)src;
+            if (at < hcap) hrow[at] = (uint16_t)src;
           } else {
             const int64_t e = e_base + at;
             a.edges[e] = b;
@@ -883,13 +904,14 @@ extern "C" int gcm_sparse_build_edges(const float* nodes, const int64_t* T, cons
   const bool hash_fits = N <= 65535 && radius > 0.0f && radius < 1.0e30f && eh_smem_bytes(N, pos_len) <= 160 * 1024;
   if (use_radius && hash_fits && (g_edge_builder == GCM_EB_HASH || (g_edge_builder == GCM_EB_AUTO && N >= 256))) {
     const size_t hsmem = eh_smem_bytes(N, pos_len);
-    cudaError_t e = cudaFuncSetAttribute(k_sparse_edges_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+    auto kern = pos_len == 2 ? k_sparse_edges_hash<2> : k_sparse_edges_hash<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
     if (e != cudaSuccess) {
       gcm_set_error("cudaFuncSetAttribute(edges_hash): %s", cudaGetErrorString(e));
       return GCM_ERR_CUDA;
     }
     dim3 hgrid(B, (tmax + EH_SINKS - 1) / EH_SINKS);
-    k_sparse_edges_hash<<<hgrid, EH_THREADS, hsmem, (cudaStream_t)stream>>>(a);
+    kern<<<hgrid, EH_THREADS, hsmem, (cudaStream_t)stream>>>(a);
     return gcm_check_launch("k_sparse_edges_hash");
   }
   const size_t smem = use_radius ? (size_t)N * pos_len * 4 : 0;

@@ -42,6 +42,7 @@ struct GcTcArgs {
   float* agg_out;
   float* out;
   int64_t tiles;
+  const float* agg_in;  // two-pass form: the sums were made by k_csr_gather, the row warps only load [agg_in | x] rows
 };
 
 // Warp per row, a lane owns V = Fin / 32 contiguous features (one coalesced warp load per neighbour row).  Column indices
@@ -60,14 +61,14 @@ __device__ __forceinline__ void gt_ld(const float* p, float (&v)[V]) {
   }
 }
 
-template <int V>
+template <int V, bool OWN = true>
 __device__ __forceinline__ void gt_gather(const GcTcArgs& a, int64_t i, int64_t e0, int64_t e1, int lane, float (&acc)[V],
                                           float (&own)[V]) {
   constexpr int Fin = 32 * V;
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.0f;
   const float* xl = a.x + lane * V;
-  gt_ld<V>(xl + i * Fin, own);
+  if (OWN) gt_ld<V>(xl + i * Fin, own);
   for (int64_t base = e0; base < e1; base += 32) {
     const int cnt = (int)min((int64_t)32, e1 - base);
     const unsigned my = lane < cnt ? (unsigned)a.col[base + lane] : 0u;     // host: every column * Fin fits 32 bits
@@ -118,12 +119,36 @@ __device__ __forceinline__ void gt_gather(const GcTcArgs& a, int64_t i, int64_t 
   }
 }
 
+// Pass 1 of the two-pass form: agg_i = sum_{(j->i)} w_ji x_j alone, a warp per row with nothing else on the SM -- no A
+// tile, no weight pack, no TMEM -- so 48 warps per SM keep gathers in flight instead of the fused kernel's 24 (whose
+// 214 KB of shared memory also leave the gathers ~30 KB of L1).  ncu (profiles/c5_graphconv_r2.md) has this pass bound by
+// the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 77 %): a 256-byte row costs 4 wavefronts whichever load width brings
+// it, and every SHFL that broadcasts a column index is one more wavefront on the same pipe.  Measured and rejected here:
+// LDG.128 with two rows per warp instruction (2.80 ms per layer at cfg5 against 2.22), broadcasting the index with a warp
+// reduction instead of the shuffle (REDUX of `lane == src ? index : 0`: 2.76 against 2.44 for the same loop shape), one
+// loop of predicated 8-slot batches instead of full batches + a tail (2.44 against 2.22).  Same loads and the same sums in
+// the same order as the fused kernel: bit-identical aggregation.
+template <int V>
+__global__ void __launch_bounds__(256, 6) k_csr_gather(const GcTcArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t li = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (li >= a.m) return;
+  const int64_t i = a.rows ? a.rows[li] : li;
+  float acc[V], own[V];
+  gt_gather<V, false>(a, i, a.rowptr[i], a.rowptr[i + 1], lane, acc, own);
+  float* o = a.agg_out + li * (32 * V) + lane * V;
+  if (V == 2) *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1 % V]);
+  else o[0] = acc[0];
+}
+
 // float offset of element (row r, k) of the padded K-major A tile with K columns
 __device__ __forceinline__ int gt_a_off(int r, int k, int K) {
   return (r >> 3) * ((K >> 2) * (GT_LBO / 4)) + (k >> 2) * (GT_LBO / 4) + (r & 7) * 4 + (k & 3);
 }
 
-template <int V>
+// STREAM: pass 2 of the two-pass form (a.agg_in set): the row warps only load [agg_in | x] rows, and they load the rows of
+// tile it + 1 into registers right after handing tile it to the MMA warp, so the loads fly during the MMAs
+template <int V, bool STREAM>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_graphconv_fwd_tc(const GcTcArgs a) {
   constexpr int Fin = 32 * V, K = 2 * Fin;
   extern __shared__ __align__(128) unsigned char gt_smem[];
@@ -162,6 +187,55 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_graphconv_fwd_tc(const GcTcAr
 
   if (warp < GT_GATHER_WARPS) {
     // =============================== gather ===============================
+    if (STREAM) {
+      constexpr int RP = (GT_TM + GT_GATHER_WARPS - 1) / GT_GATHER_WARPS;     // rows of a tile per warp
+      float pa[RP][V], po[RP][V];
+      auto load_tile = [&](int64_t it) {
+        const int64_t row0 = (blockIdx.x + it * gridDim.x) * GT_TM;
+#pragma unroll
+        for (int k = 0; k < RP; ++k) {
+          const int r = warp + k * GT_GATHER_WARPS;
+          const int64_t li = row0 + r;
+#pragma unroll
+          for (int j = 0; j < V; ++j) pa[k][j] = po[k][j] = 0.0f;
+          if (r < GT_TM && li < a.m) {
+            const int64_t i = a.rows ? a.rows[li] : li;
+            gt_ld<V>(a.agg_in + li * Fin + lane * V, pa[k]);
+            gt_ld<V>(a.x + i * Fin + lane * V, po[k]);
+          }
+        }
+      };
+      if (n_it > 0) load_tile(0);
+      for (int64_t it = 0; it < n_it; ++it) {
+        if (it > 0) tc::mbar_wait(mma_done + ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
+#pragma unroll
+        for (int k = 0; k < RP; ++k) {
+          const int r = warp + k * GT_GATHER_WARPS;
+          if (r < GT_TM) {
+            uint32_t ah[V], al[V], oh[V], ol[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              tc::split_tf32(pa[k][j], ah[j], al[j]);
+              tc::split_tf32(po[k][j], oh[j], ol[j]);
+            }
+            const int o_agg = gt_a_off(r, lane * V, K), o_own = gt_a_off(r, Fin + lane * V, K);
+            if (V == 2) {
+              *reinterpret_cast<uint2*>(Ahi + o_agg) = make_uint2(ah[0], ah[1 % V]);
+              *reinterpret_cast<uint2*>(Alo + o_agg) = make_uint2(al[0], al[1 % V]);
+              *reinterpret_cast<uint2*>(Ahi + o_own) = make_uint2(oh[0], oh[1 % V]);
+              *reinterpret_cast<uint2*>(Alo + o_own) = make_uint2(ol[0], ol[1 % V]);
+            } else {
+              Ahi[o_agg] = __uint_as_float(ah[0]); Alo[o_agg] = __uint_as_float(al[0]);
+              Ahi[o_own] = __uint_as_float(oh[0]); Alo[o_own] = __uint_as_float(ol[0]);
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_full);
+        if (it + 1 < n_it) load_tile(it + 1);
+      }
+    } else
     for (int64_t it = 0; it < n_it; ++it) {
       const int64_t row0 = (blockIdx.x + it * gridDim.x) * GT_TM;
       if (it > 0) {
@@ -630,7 +704,24 @@ int gcm_graphconv_fwd_tc(const float* x, const int64_t* rowptr, const int64_t* c
   const size_t a_bytes = (size_t)(GT_TM / 8) * (K / 4) * GT_LBO;
   const size_t smem = 2 * a_bytes + (size_t)2 * Fout * K * 4 + 128 * 4 + 64 + 128;
   if (smem > 227 * 1024) return GCM_ERR_UNSUPPORTED;
-  GcTcArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out, (m + GT_TM - 1) / GT_TM};
+  GcTcArgs a{x, rowptr, col, ew, rows, m, Fin, Fout, wt, bias, act, agg_out, out, (m + GT_TM - 1) / GT_TM, nullptr};
+  {
+    // two-pass form when the caller provides room for the sums (always while recording; gcm.sparse_ops also hands a
+    // scratch buffer to large no-grad calls): k_csr_gather at full occupancy, then the product kernel streams [agg | x]
+    static const bool one_pass = getenv("GCM_B200_GRAPHCONV_ONE_PASS") != nullptr;     // A/B switch
+    if (agg_out && !one_pass && m >= 64 * GT_TM && (reinterpret_cast<uintptr_t>(agg_out) & 15) == 0) {
+      const long long gg = (m + 7) / 8;
+      if (gg < 2147483647LL) {
+        if (Fin == 64) k_csr_gather<2><<<(unsigned)gg, 256, 0, stream>>>(a);
+        else k_csr_gather<1><<<(unsigned)gg, 256, 0, stream>>>(a);
+        const int rc = gcm_check_launch("k_csr_gather");
+        if (rc != GCM_OK) return rc;
+        a.agg_in = agg_out;
+        a.agg_out = nullptr;
+        node_off = nullptr;            // the block-local kernel is a gather variant
+      }
+    }
+  }
   {
     static const bool no_blk = getenv("GCM_B200_GRAPHCONV_NO_BLOCKS") != nullptr;     // A/B switch
     if (node_off && !rows && !no_blk && n_graphs > 0 && max_nodes > 0 && (size_t)max_nodes * Fin * 4 <= GB_XBYTES &&
@@ -642,13 +733,17 @@ int gcm_graphconv_fwd_tc(const float* x, const int64_t* rowptr, const int64_t* c
   long long grid = gcm_num_sms();
   if (grid > a.tiles) grid = a.tiles;
   cudaError_t e;
+#define GT_LAUNCH(V, ST)                                                                                                  \
+  do {                                                                                                                    \
+    e = cudaFuncSetAttribute(k_graphconv_fwd_tc<V, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess) k_graphconv_fwd_tc<V, ST><<<(unsigned)grid, GT_THREADS, smem, stream>>>(a);                     \
+  } while (0)
   if (Fin == 64) {
-    e = cudaFuncSetAttribute(k_graphconv_fwd_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_graphconv_fwd_tc<2><<<(unsigned)grid, GT_THREADS, smem, stream>>>(a);
+    if (a.agg_in) GT_LAUNCH(2, true); else GT_LAUNCH(2, false);
   } else {
-    e = cudaFuncSetAttribute(k_graphconv_fwd_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) k_graphconv_fwd_tc<1><<<(unsigned)grid, GT_THREADS, smem, stream>>>(a);
+    if (a.agg_in) GT_LAUNCH(1, true); else GT_LAUNCH(1, false);
   }
+#undef GT_LAUNCH
   if (e != cudaSuccess) {
     gcm_set_error("cudaFuncSetAttribute(graphconv_fwd_tc): %s", cudaGetErrorString(e));
     return GCM_ERR_CUDA;

@@ -184,6 +184,9 @@ def _kmajor(w_rel: torch.Tensor, w_root: torch.Tensor) -> torch.Tensor:
     return torch.cat([w_rel.detach().t(), w_root.detach().t()], dim=0).contiguous()
 
 
+_TWO_PASS_ROWS = 8192      # gcm_sparse_tc.cu: two-pass threshold (64 tiles of 128 rows)
+
+
 class _GraphConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_rel, bias, w_root, csr: Csr, rows, act: int):
@@ -193,7 +196,9 @@ class _GraphConvFn(torch.autograd.Function):
         m = n if rows is None else rows.numel()
         dev = x.device
         need_grad = any(t is not None and t.requires_grad for t in (x, w_rel, bias, w_root))
-        agg = torch.empty(m, Fin, device=dev) if need_grad else None
+        # room for the neighbour sums: kept for the backward while recording; large no-grad calls get it as scratch, which
+        # lets the library run its two-pass form (k_csr_gather at full occupancy + the streaming product kernel)
+        agg = torch.empty(m, Fin, device=dev) if (need_grad or m >= _TWO_PASS_ROWS) else None
         out = torch.empty(m, Fout, device=dev)
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
@@ -204,7 +209,7 @@ class _GraphConvFn(torch.autograd.Function):
             wt.data_ptr(), _cabi.ptr(b), act, _cabi.ptr(agg), out.data_ptr(), _cabi.stream_ptr(dev)),
             "gcm_sparse_graphconv_fwd")
         ctx.csr, ctx.rows, ctx.act, ctx.has_bias = csr, rows, act, bias is not None
-        ctx.save_for_backward(x, agg, out, w_rel, w_root)
+        ctx.save_for_backward(x, agg if need_grad else None, out, w_rel, w_root)
         return out
 
     @staticmethod
@@ -246,13 +251,14 @@ def graph_conv_csr(x, csr: Csr, rows, w_rel, bias, w_root, act: str = "none", ed
         x = x.contiguous()
         m = x.shape[0] if rows is None else rows.numel()
         out = torch.empty(m, w_rel.shape[0], device=x.device)
+        scratch = torch.empty(m, x.shape[1], device=x.device) if m >= _TWO_PASS_ROWS else None
         wt = _kmajor(w_rel, w_root)
         b = None if bias is None else bias.detach().contiguous()
         _cabi.lib().gcm_sparse_graphconv_hint_rows(x.shape[0])
         _hint_blocks(csr, rows)
         _cabi.check(_cabi.lib().gcm_sparse_graphconv_fwd(
             x.data_ptr(), csr.rowptr.data_ptr(), csr.col.data_ptr(), edge_mask.data_ptr(), _cabi.ptr(rows), m, x.shape[1],
-            w_rel.shape[0], wt.data_ptr(), _cabi.ptr(b), _cabi.ACT[act], None, out.data_ptr(),
+            w_rel.shape[0], wt.data_ptr(), _cabi.ptr(b), _cabi.ACT[act], _cabi.ptr(scratch), out.data_ptr(),
             _cabi.stream_ptr(x.device)), "gcm_sparse_graphconv_fwd")
         return out
     return _GraphConvFn.apply(x, w_rel, bias, w_root, csr, rows, _cabi.ACT[act])

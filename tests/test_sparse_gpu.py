@@ -305,9 +305,15 @@ def test_pack_unpack_round_trip_at_scale_and_through_sparse_gcm():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.parametrize("F,H,act,use_rows,masked", [(64, 64, "tanh", False, False), (32, 32, "relu", False, False),
-                                                      (64, 32, "none", True, False), (32, 64, "tanh", True, True)])
-def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_rows, masked):
+@pytest.mark.parametrize("F,H,act,use_rows,masked,n", [(64, 64, "tanh", False, False, 128 * 9 + 37),
+                                                        (32, 32, "relu", False, False, 128 * 9 + 37),
+                                                        (64, 32, "none", True, False, 128 * 9 + 37),
+                                                        (32, 64, "tanh", True, True, 128 * 9 + 37),
+                                                        # >= 8192 evaluated rows: the two-pass form (k_csr_gather + product)
+                                                        (64, 64, "tanh", False, False, 128 * 70 + 37),
+                                                        (32, 48, "relu", True, False, 128 * 150 + 5),
+                                                        (64, 64, "none", False, True, 128 * 70 + 37)])
+def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_rows, masked, n):
     """k_graphconv_fwd_tc (tcgen05, 3xTF32, SS-form MMAs on a padded K-major tile) against k_graphconv_fwd (CUDA cores) and
     the definition out = act(W_rel sum_j w_j x_j + b + W_root x_i), on a random block-diagonal causal graph: all rows /
     a row subset, unit weights / a 0-1 edge mask, a ragged tail tile."""
@@ -316,8 +322,8 @@ def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_ro
     dev = torch.device("cuda:0")
     lib = _cabi.lib()
     gen = torch.Generator().manual_seed(F + H)
-    n = 128 * 9 + 37
     deg = torch.randint(0, 40, (n,), generator=gen)
+    deg[n - 3] = 75                               # more than two 32-edge chunks
     deg[0] = 0
     sink = torch.repeat_interleave(torch.arange(n), deg)
     src = (torch.rand(sink.numel(), generator=gen) * sink.float()).long().clamp(max=n - 1)     # source < sink
@@ -328,7 +334,7 @@ def test_graphconv_tensor_core_kernel_matches_cuda_core_kernel(F, H, act, use_ro
     w_rel = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
     w_root = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
     bias = torch.randn(H, generator=gen).to(dev)
-    rows = torch.randperm(n, generator=gen)[: 128 * 5 + 11].sort().values.to(dev) if use_rows else None
+    rows = torch.randperm(n, generator=gen)[: (128 * 5 + 11 if n < 8192 else 128 * 66 + 11)].sort().values.to(dev) if use_rows else None
     mask = (torch.rand(sink.numel(), generator=gen) < 0.7).float().to(dev) if masked else None
     outs = {}
     try:
