@@ -31,6 +31,30 @@ __global__ void __launch_bounds__(256) k_sparse_write_flatten(float* nodes, cons
   }
 }
 
+// Out-of-place form of the same step: nodes_out = nodes_in with the new rows written, flat = its valid rows, in ONE pass
+// over the rows (the in-place form needs the caller's clone of `nodes` first and reads the written rows back: 3 passes
+// over a [B,N,F] tensor, 1.33 + 0.34 ms at cfg5).  blockIdx.y splits a graph's rows; VEC = 16-byte pieces when F % 4 == 0.
+constexpr int WF_ROWS = 128;
+template <typename VT>
+__global__ void __launch_bounds__(256) k_sparse_write_flatten_oop(const VT* nodes_in, VT* nodes_out, const VT* x,
+                                                                  const int64_t* T, const int64_t* taus,
+                                                                  const int64_t* offsets, int N, int Fv, int tmax, VT* flat) {
+  const int b = blockIdx.x;
+  const int t0 = (int)T[b], tau = (int)taus[b];
+  const int j0 = blockIdx.y * WF_ROWS, j1 = min(N, j0 + WF_ROWS);
+  const VT* in_b = nodes_in + (size_t)b * N * Fv;
+  VT* out_b = nodes_out + (size_t)b * N * Fv;
+  const VT* x_b = x + (size_t)b * tmax * Fv;
+  VT* flat_b = flat ? flat + offsets[b] * Fv : nullptr;
+  const int n_valid = min(t0 + tau, N);
+  const int lo = j0 * Fv, hi = j1 * Fv, new_lo = t0 * Fv, new_hi = (t0 + tau) * Fv, valid_hi = n_valid * Fv;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const VT v = (i >= new_lo && i < new_hi) ? x_b[i - new_lo] : in_b[i];
+    out_b[i] = v;
+    if (flat_b && i < valid_hi) flat_b[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused edge generation
 // ------------------------------------------------------------------------------------------------
@@ -862,6 +886,27 @@ extern "C" int gcm_sparse_write_flatten(float* nodes, const float* x, const int6
   if (B == 0) return GCM_OK;
   k_sparse_write_flatten<<<B, 256, 0, (cudaStream_t)stream>>>(nodes, x, T, taus, offsets, N, F, tmax, flat);
   return gcm_check_launch("k_sparse_write_flatten");
+}
+
+extern "C" int gcm_sparse_write_flatten_oop(const float* nodes_in, float* nodes_out, const float* x, const int64_t* T,
+                                            const int64_t* taus, const int64_t* offsets, int B, int N, int F, int tmax,
+                                            float* flat, void* stream) {
+  GCM_REQUIRE(nodes_in && nodes_out && nodes_in != nodes_out && x && T && taus && offsets && B >= 0 && N >= 1 && F >= 1 &&
+                  tmax >= 0, "sparse_write_flatten_oop: bad arguments");
+  GCM_REQUIRE((long long)N * F < 2147483647LL, "sparse_write_flatten_oop: N * F too large");
+  if (B == 0) return GCM_OK;
+  dim3 grid(B, (N + WF_ROWS - 1) / WF_ROWS);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(nodes_in) | reinterpret_cast<uintptr_t>(nodes_out) |
+                       reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(flat);
+  if (F % 4 == 0 && (al & 15) == 0) {
+    k_sparse_write_flatten_oop<float4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(nodes_in), reinterpret_cast<float4*>(nodes_out), reinterpret_cast<const float4*>(x),
+        T, taus, offsets, N, F / 4, tmax, reinterpret_cast<float4*>(flat));
+  } else {
+    k_sparse_write_flatten_oop<float><<<grid, 256, 0, (cudaStream_t)stream>>>(nodes_in, nodes_out, x, T, taus, offsets, N,
+                                                                            F, tmax, flat);
+  }
+  return gcm_check_launch("k_sparse_write_flatten_oop");
 }
 
 static int g_edge_builder = GCM_EB_AUTO;

@@ -40,13 +40,26 @@ def write_flatten(nodes: torch.Tensor, x: torch.Tensor, T: torch.Tensor, taus: t
     return flat
 
 
+def write_flatten_oop(nodes: torch.Tensor, x: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, offsets: torch.Tensor,
+                      n_flat: int):
+    """(nodes_out, flat): nodes_out = nodes with nodes_out[b, T_b + k] = x[b, k], flat = its valid rows; one pass, no clone."""
+    _cabi.require_cuda(nodes, "SparseGCM nodes")
+    B, N, F = nodes.shape
+    nodes = nodes.contiguous()
+    out = torch.empty_like(nodes)
+    flat = torch.empty(n_flat, F, device=nodes.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().gcm_sparse_write_flatten_oop(
+        nodes.data_ptr(), out.data_ptr(), x.data_ptr(), T.data_ptr(), taus.data_ptr(), offsets.data_ptr(), B, N, F,
+        x.shape[1], flat.data_ptr(), _cabi.stream_ptr(nodes.device)), "gcm_sparse_write_flatten_oop")
+    return out, flat
+
+
 class _WriteFlattenFn(torch.autograd.Function):
     """nodes_out = nodes with the new observations written; flat = valid rows of nodes_out."""
 
     @staticmethod
     def forward(ctx, nodes, x, T, taus, offsets, n_flat):
-        out = nodes.detach().clone()
-        flat = write_flatten(out, x.detach().contiguous(), T, taus, offsets, n_flat)
+        out, flat = write_flatten_oop(nodes.detach(), x.detach().contiguous(), T, taus, offsets, n_flat)
         ctx.meta = (T, taus, offsets, nodes.shape, x.shape)
         return out, flat
 

@@ -409,6 +409,12 @@ int gcm_sparse_write_flatten(float* nodes, const float* x, const int64_t* T, con
                              const int64_t* offsets, int B, int N, int F, int tmax, float* flat,
                              void* stream);
 
+/* The same step out of place (sparse_gcm.py:109-123 in one pass): nodes_out [B,N,F] = nodes_in with the new rows written
+ * (every row of nodes_out is written, so the caller needs no clone), flat as above.  nodes_in != nodes_out. */
+int gcm_sparse_write_flatten_oop(const float* nodes_in, float* nodes_out, const float* x, const int64_t* T,
+                                 const int64_t* taus, const int64_t* offsets, int B, int N, int F, int tmax,
+                                 float* flat, void* stream);
+
 /* Fused edge selectors for the new nodes s in [T_b, T_b + tau_b): sources k < s with
  * (s - k in hops) [TemporalEdge, sparse_edge_selectors/temporal.py:19-63] OR
  * ||pos_s - pos_k||_2 < radius [SpatialRadiusEdge causal, sparse_edge_selectors/spatial.py:74-115;
