@@ -7,6 +7,8 @@
 //   * GraphConv as a CSR segmented gather-reduce fused with the two Linear layers + activation
 //     (torch_geometric.nn.GraphConv; invoked at sparse_gcm.py:178,199), deterministic, and its
 //     backward (transposed-CSR gather for dL/dx, split-K accumulation for the weight gradients).
+#include <type_traits>
+
 #include "gcm_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -707,24 +709,28 @@ __global__ void __launch_bounds__(256) k_graphconv_bwd_rows(const GraphConvBwdAr
 
 // transposed gather: t_rowptr/t_col group the edges by SOURCE node; t_col holds the LOCAL index (into
 // the m evaluated rows) of each edge's sink.  d_x[j] += sum w * d_agg[t_col[e]]
-template <int V>
+// IDX32: every element offset t_col * Fin fits 32 bits (checked at launch): one shuffle and one IMAD.WIDE per gather
+// instead of two shuffles and an emulated 64-bit multiply; the last cnt % 8 gathers of a batch are issued together
+// (predicated) instead of one dependent load at a time (ncu: the serial tail was a third of this kernel's stall samples).
+template <int V, bool IDX32>
 __device__ __forceinline__ void gc_bwd_gather_row(const float* d_agg, const int64_t* t_col, const float* t_ew, int64_t e0,
                                                   int64_t e1, int lane, float* dst) {
   // same scheme as gc_gather_row: lane owns V contiguous features, 32 column indices per coalesced load, 8 gathers in flight
-  const int Fin = 32 * V;
+  constexpr int Fin = 32 * V;
+  using idx_t = typename std::conditional<IDX32, unsigned, int64_t>::type;
   float acc[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.0f;
   const float* xl = d_agg + lane * V;
   for (int64_t base = e0; base < e1; base += 32) {
     const int cnt = (int)min((int64_t)32, e1 - base);
-    const int64_t my = lane < cnt ? t_col[base + lane] : 0;
+    const idx_t my = lane < cnt ? (idx_t)t_col[base + lane] : (idx_t)0;
     const float myw = (t_ew && lane < cnt) ? t_ew[base + lane] : 1.0f;
     int u = 0;
     for (; u + 8 <= cnt; u += 8) {
       float v[8][V];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u + q) * Fin, v[q]);
+      for (int q = 0; q < 8; ++q) gc_load_vec<V>(xl + (size_t)(__shfl_sync(GCM_FULL_MASK, my, u + q) * (idx_t)Fin), v[q]);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float w = t_ew ? __shfl_sync(GCM_FULL_MASK, myw, u + q) : 1.0f;
@@ -732,18 +738,30 @@ __device__ __forceinline__ void gc_bwd_gather_row(const float* d_agg, const int6
         for (int j = 0; j < V; ++j) acc[j] += t_ew ? v[q][j] * w : v[q][j];
       }
     }
-    for (; u < cnt; ++u) {
-      float v[V];
-      gc_load_vec<V>(xl + __shfl_sync(GCM_FULL_MASK, my, u) * Fin, v);
-      const float w = t_ew ? __shfl_sync(GCM_FULL_MASK, myw, u) : 1.0f;
+    if (u < cnt) {
+      float v[7][V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] += t_ew ? v[j] * w : v[j];
+      for (int q = 0; q < 7; ++q) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[q][j] = 0.0f;
+        const idx_t c = __shfl_sync(GCM_FULL_MASK, my, (u + q) & 31);
+        if (u + q < cnt) gc_load_vec<V>(xl + (size_t)(c * (idx_t)Fin), v[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const float w = t_ew ? __shfl_sync(GCM_FULL_MASK, myw, (u + q) & 31) : 1.0f;
+        if (u + q < cnt) {
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += t_ew ? v[q][j] * w : v[q][j];
+        }
+      }
     }
   }
 #pragma unroll
   for (int j = 0; j < V; ++j) dst[lane * V + j] += acc[j];
 }
 
+template <bool IDX32>
 __global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg, const int64_t* t_rowptr,
                                                              const int64_t* t_col, const float* t_ew,
                                                              int64_t n, int Fin, float* d_x) {
@@ -752,9 +770,9 @@ __global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg
   if (j >= n) return;
   const int64_t e0 = t_rowptr[j], e1 = t_rowptr[j + 1];
   if (e0 == e1) return;
-  if (Fin == 64) return gc_bwd_gather_row<2>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
-  if (Fin == 128) return gc_bwd_gather_row<4>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
-  if (Fin == 32) return gc_bwd_gather_row<1>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  if (Fin == 64) return gc_bwd_gather_row<2, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  if (Fin == 128) return gc_bwd_gather_row<4, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  if (Fin == 32) return gc_bwd_gather_row<1, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
   for (int f0 = 0; f0 < Fin; f0 += 32) {
     const int f = f0 + lane;
     if (f >= Fin) break;
@@ -1022,6 +1040,9 @@ extern "C" int gcm_sparse_graphconv_fwd(const float* x, const int64_t* rowptr, c
   return gcm_check_launch("k_graphconv_fwd");
 }
 
+extern "C" int gcm_outer_reduce_tc32_pair(const float* A, long long lda, int Ho, const float* X1, long long ldx1, int Hi1,
+                                          const float* X2, long long ldx2, int Hi2, long long rows, float* workspace,
+                                          float* dW1, float* dW2, float* db, void* stream);
 extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const float* out, const float* d_out,
                                         const int64_t* rows, int64_t m, int64_t n, const int64_t* t_rowptr,
                                         const int64_t* t_col, const float* t_ew, int Fin, int Fout,
@@ -1055,7 +1076,12 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
     }
     // weight gradients: 3xTF32 reductions over the m rows on the tensor cores for wide layers; at 64 x 64 half of that
     // kernel's row-owning threads would idle and the CUDA-core tile (1.67 ms per reduction at cfg5) beats it (2.10 ms)
-    if (outer_ws && tc_ok && (Fin > 64 || Fout > 64)) {
+    if (outer_ws && tc_ok && 2 * Fin <= 128) {
+      // both reductions share dz: ONE pass over the rows on the tensor cores, X operand = [agg | x] (threads 0 .. Fin - 1
+      // of a group own an agg column, the next Fin an x column): 2 x 1.67 ms -> one launch at cfg5
+      if (int rc = gcm_outer_reduce_tc32_pair(dz_scratch, Fout, Fout, agg, Fin, Fin, x, Fin, Fin, m, outer_ws, d_w_rel,
+                                              d_w_root, d_b, stream)) return rc;
+    } else if (outer_ws && tc_ok && (Fin > 64 || Fout > 64)) {
       if (int rc = gcm_outer_reduce_tc32(dz_scratch, Fout, Fout, agg, Fin, Fin, m, outer_ws, d_w_rel, d_b, stream)) return rc;
       if (int rc = gcm_outer_reduce_tc32(dz_scratch, Fout, Fout, x, Fin, Fin, m, outer_ws, d_w_root, nullptr, stream)) return rc;
     } else {
@@ -1064,7 +1090,10 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
     }
     const int64_t g2 = (n + 7) / 8;
     GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
-    k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+    if ((unsigned long long)m * (unsigned long long)Fin < (1ull << 32))      // t_col holds sink rows < m
+      k_graphconv_bwd_gather<true><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+    else
+      k_graphconv_bwd_gather<false><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
     return gcm_check_launch("k_graphconv_bwd_gather");
   }
   GraphConvBwdArgs a{x, agg, out, d_out, rows, m, n, Fin, Fout, w_rel, w_root, act, d_agg, d_x, d_w_rel, d_w_root, d_b};
@@ -1081,7 +1110,10 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
   if (int rc = gcm_check_launch("k_graphconv_bwd_rows")) return rc;
   const int64_t g2 = (n + 7) / 8;
   GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
-  k_graphconv_bwd_gather<<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+  if ((unsigned long long)m * (unsigned long long)Fin < (1ull << 32))
+    k_graphconv_bwd_gather<true><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
+  else
+    k_graphconv_bwd_gather<false><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
   return gcm_check_launch("k_graphconv_bwd_gather");
 }
 

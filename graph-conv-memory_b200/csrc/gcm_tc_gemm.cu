@@ -427,6 +427,9 @@ struct OuterTcArgs {
   long long rows, rows_per_cta;
   float* part;        // [gridDim.x, 128, Hi]
   float* part_b;      // [gridDim.x, 128]
+  // k_outer_tc32 only: channels i >= Hi1 of the X operand come from a second matrix (X2[r, i - Hi1]) -- two reductions
+  // against the same A in one pass over the rows (the sparse GraphConv backward: dz^T [agg | x])
+  const float* X2 = nullptr; long long ldx2 = 0; int Hi1 = 0;
 };
 
 __global__ void __launch_bounds__(TCG_THREADS, 2) k_outer_tc(const OuterTcArgs a) {
@@ -592,13 +595,15 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
       for (int q2 = 0; q2 < 2; ++q2) {                             // 32 rows (k) at a time: 64 loads in flight per thread
         const long long rq = r0 + q2 * 32;
         const float* pa = a.A + rq * a.lda + ch;
-        const float* px = a.X + rq * a.ldx + ch;
+        const bool second = a.X2 != nullptr && ch >= a.Hi1;
+        const long long ldx = second ? a.ldx2 : a.ldx;
+        const float* px = second ? a.X2 + rq * ldx + (ch - a.Hi1) : a.X + rq * ldx + ch;
         float av[32], xv[32];
         const bool whole = rq + 32 <= r_end;
 #pragma unroll
         for (int u = 0; u < 32; ++u) av[u] = (a_ok && (whole || rq + u < r_end)) ? __ldcs(pa + u * a.lda) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) xv[u] = (x_ok && (whole || rq + u < r_end)) ? __ldcs(px + u * a.ldx) : 0.0f;
+        for (int u = 0; u < 32; ++u) xv[u] = (x_ok && (whole || rq + u < r_end)) ? __ldcs(px + u * ldx) : 0.0f;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           const int q = q2 * 2 + h2;
@@ -680,6 +685,24 @@ __global__ void __launch_bounds__(256) k_outer_tc_reduce(const float* part, cons
     float s = 0.0f;
     for (int k = 0; k < ctas; ++k) s += part[((size_t)k * 128 + o) * Hi + c];
     dW[i] += s;
+  }
+  if (db && i < Ho) {
+    float s = 0.0f;
+    for (int k = 0; k < ctas; ++k) s += part_b[(size_t)k * 128 + i];
+    db[i] += s;
+  }
+}
+
+// pair form: columns [0, Hi1) of the partial products go to dW1 [Ho, Hi1], columns [Hi1, Hi) to dW2 [Ho, Hi - Hi1]
+__global__ void __launch_bounds__(256) k_outer_tc_reduce_pair(const float* part, const float* part_b, int ctas, int Ho, int Hi,
+                                                              int Hi1, float* dW1, float* dW2, float* db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Ho * Hi) {
+    const int o = i / Hi, c = i - o * Hi;
+    float s = 0.0f;
+    for (int k = 0; k < ctas; ++k) s += part[((size_t)k * 128 + o) * Hi + c];
+    if (c < Hi1) dW1[o * Hi1 + c] += s;
+    else dW2[o * (Hi - Hi1) + (c - Hi1)] += s;
   }
   if (db && i < Ho) {
     float s = 0.0f;
@@ -793,6 +816,38 @@ static int outer_reduce_tc_impl(const float* A, long long lda, int Ho, const flo
   }
   k_outer_tc_reduce<<<(Ho * Hi + 255) / 256, 256, 0, s>>>(part, part_b, (int)ctas, Ho, Hi, dW, db);
   return gcm_check_launch("k_outer_tc_reduce");
+}
+
+extern "C" int gcm_outer_reduce_tc32_pair(const float* A, long long lda, int Ho, const float* X1, long long ldx1, int Hi1,
+                                          const float* X2, long long ldx2, int Hi2, long long rows, float* workspace,
+                                          float* dW1, float* dW2, float* db, void* stream) {
+  GCM_REQUIRE(A && X1 && X2 && dW1 && dW2 && workspace && rows >= 0, "outer_reduce_tc32_pair: null pointer");
+  const int Hi = Hi1 + Hi2;
+  GCM_REQUIRE(Ho >= 1 && Ho <= 128 && Hi1 >= 16 && Hi2 >= 16 && Hi <= 128 && Hi1 % 16 == 0 && Hi2 % 16 == 0,
+              "outer_reduce_tc32_pair: Ho=%d must be <= 128, Hi1=%d and Hi2=%d multiples of 16 with a sum <= 128", Ho, Hi1, Hi2);
+  if (rows == 0) return GCM_OK;
+  long long ctas = gcm_outer_reduce_tc_workspace(rows) / (128 * 129);
+  if (ctas > gcm_num_sms()) ctas = gcm_num_sms();       // 512 TMEM columns: one CTA per SM
+  long long per = (rows + ctas - 1) / ctas;
+  per = (per + OT_KC - 1) / OT_KC * OT_KC;
+  ctas = (rows + per - 1) / per;
+  float* part = workspace;
+  float* part_b = workspace + (size_t)ctas * 128 * Hi;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (db && cudaMemsetAsync(part_b, 0, (size_t)ctas * 128 * sizeof(float), s) != cudaSuccess) {
+    gcm_set_error("outer_reduce_tc32_pair: cudaMemsetAsync failed");
+    return GCM_ERR_CUDA;
+  }
+  OuterTcArgs a{A, lda, Ho, X1, ldx1, Hi, rows, per, part, db ? part_b : nullptr, X2, ldx2, Hi1};
+  const size_t smem = (size_t)4 * 128 * OT_KC * sizeof(float) + 128;
+  if (cudaFuncSetAttribute(k_outer_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    gcm_set_error("outer_reduce_tc32_pair: cannot raise the dynamic shared memory limit");
+    return GCM_ERR_CUDA;
+  }
+  k_outer_tc32<<<(unsigned)ctas, TCG_THREADS, smem, s>>>(a);
+  if (int rc = gcm_check_launch("k_outer_tc32")) return rc;
+  k_outer_tc_reduce_pair<<<(Ho * Hi + 255) / 256, 256, 0, s>>>(part, part_b, (int)ctas, Ho, Hi, Hi1, dW1, dW2, db);
+  return gcm_check_launch("k_outer_tc_reduce_pair");
 }
 
 extern "C" int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi,

@@ -148,6 +148,8 @@ _SIGNATURES = {
     "gcm_outer_reduce_tc_workspace": (C.c_longlong, [C.c_longlong]),
     "gcm_outer_reduce_tc": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_outer_reduce_tc32": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P, _P, _P, _P]),
+    "gcm_outer_reduce_tc32_pair": (_I, [_P, C.c_longlong, _I, _P, C.c_longlong, _I, _P, C.c_longlong, _I, C.c_longlong, _P,
+                                        _P, _P, _P, _P]),
     "gcm_dense_fill_masks": (_I, [C.POINTER(DenseStateC), _P]),
     "gcm_dense_step_fwd_zc": (_I, [C.POINTER(DenseStateC), _P, C.POINTER(SelectorC), C.POINTER(GnnC), _P, _P, _P, _P]),
     "gcm_set_edge_builder": (_I, [_I]),

@@ -386,6 +386,13 @@ int gcm_outer_reduce_tc(const float* A, long long lda, int Ho, const float* X, l
 /* the same in 3xTF32 (fp32-accurate), same workspace */
 int gcm_outer_reduce_tc32(const float* A, long long lda, int Ho, const float* X, long long ldx, int Hi, long long rows,
                           float* workspace, float* dW, float* db, void* stream);
+
+/* Two such reductions against the same A in one pass over the rows (3xTF32): dW1 [Ho,Hi1] += A^T X1, dW2 [Ho,Hi2] += A^T X2,
+ * db [Ho] += column sums of A.  Hi1, Hi2 multiples of 16, Hi1 + Hi2 <= 128.  The sparse GraphConv backward's weight
+ * gradients dz^T [agg | x] (torch_geometric GraphConv lin_rel / lin_root; autograd of sparse_gcm.py:178,199). */
+int gcm_outer_reduce_tc32_pair(const float* A, long long lda, int Ho, const float* X1, long long ldx1, int Hi1,
+                               const float* X2, long long ldx2, int Hi2, long long rows, float* workspace,
+                               float* dW1, float* dW2, float* db, void* stream);
 /* writes the bit masks of the all-ones valid block (every node of the window linked to every node, self loops) */
 int gcm_dense_fill_masks(const gcm_dense_state* st, void* stream);
 
