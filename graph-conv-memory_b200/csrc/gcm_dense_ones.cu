@@ -738,6 +738,22 @@ __global__ void __launch_bounds__(256) k_act_bwd(const float* d_out, const float
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) res[i] = d_out[i] * gcm_act_grad(out[i], act);
 }
+// 16-byte pieces, two per thread in flight (the scalar form moved 3.5 TB/s on the 268 M elements of a cfg5 layer)
+__global__ void __launch_bounds__(256) k_act_bwd_v4(const float4* d_out, const float4* out, int act, long long n4, float4* res) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n4) {
+    const float4 d0 = __ldcs(d_out + i), d1 = __ldcs(d_out + i + 1);
+    const float4 o0 = out[i], o1 = out[i + 1];
+    res[i] = make_float4(d0.x * gcm_act_grad(o0.x, act), d0.y * gcm_act_grad(o0.y, act), d0.z * gcm_act_grad(o0.z, act),
+                         d0.w * gcm_act_grad(o0.w, act));
+    res[i + 1] = make_float4(d1.x * gcm_act_grad(o1.x, act), d1.y * gcm_act_grad(o1.y, act), d1.z * gcm_act_grad(o1.z, act),
+                             d1.w * gcm_act_grad(o1.w, act));
+  } else if (i < n4) {
+    const float4 d0 = d_out[i], o0 = out[i];
+    res[i] = make_float4(d0.x * gcm_act_grad(o0.x, act), d0.y * gcm_act_grad(o0.y, act), d0.z * gcm_act_grad(o0.z, act),
+                         d0.w * gcm_act_grad(o0.w, act));
+  }
+}
 __global__ void __launch_bounds__(256) k_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1,
                                                  long long n, float* dc, const float* dcs_next, float* dcs) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -925,6 +941,18 @@ extern "C" int gcm_dense_ones_node_bwd(const gcm_dense_state* st, int H1, int ac
 extern "C" int gcm_act_backward(const float* d_out, const float* out, int act, long long n, float* res, void* stream) {
   GCM_REQUIRE(d_out && out && res && n >= 0, "act_backward: bad arguments");
   if (n == 0) return GCM_OK;
+  const long long n4 = n / 4;
+  const bool al = ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res)) & 15) == 0;
+  if (al && n4 >= 1024 && (n4 + 511) / 512 < 2147483647LL) {
+    k_act_bwd_v4<<<(unsigned)((n4 + 511) / 512), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float4*>(out), act, n4, reinterpret_cast<float4*>(res));
+    if (int rc = gcm_check_launch("k_act_bwd_v4")) return rc;
+    const long long done = n4 * 4;
+    if (done == n) return GCM_OK;
+    k_act_bwd<<<1, 256, 0, (cudaStream_t)stream>>>(d_out + done, out + done, act, n - done, res + done);
+    return gcm_check_launch("k_act_bwd");
+  }
+  GCM_REQUIRE((n + 255) / 256 < 2147483647LL, "act_backward: too many elements");
   k_act_bwd<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_out, out, act, n, res);
   return gcm_check_launch("k_act_bwd");
 }

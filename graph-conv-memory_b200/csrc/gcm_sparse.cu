@@ -7,6 +7,7 @@
 //   * GraphConv as a CSR segmented gather-reduce fused with the two Linear layers + activation
 //     (torch_geometric.nn.GraphConv; invoked at sparse_gcm.py:178,199), deterministic, and its
 //     backward (transposed-CSR gather for dL/dx, split-K accumulation for the weight gradients).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "gcm_common.cuh"
@@ -761,29 +762,49 @@ __device__ __forceinline__ void gc_bwd_gather_row(const float* d_agg, const int6
   for (int j = 0; j < V; ++j) dst[lane * V + j] += acc[j];
 }
 
-template <bool IDX32>
-__global__ void __launch_bounds__(256) k_graphconv_bwd_gather(const float* d_agg, const int64_t* t_rowptr,
-                                                             const int64_t* t_col, const float* t_ew,
-                                                             int64_t n, int Fin, float* d_x) {
+// V = Fin / 32 in {1, 2, 4}; V = 0: any Fin (scalar loop).  One instantiation per width so that the narrow ones keep 40
+// registers (48 warps per SM; a single kernel holding the V = 4 path ran at 64 registers, 32 warps).
+template <int V, bool IDX32>
+__global__ void __launch_bounds__(256, V == 4 || V == 0 ? 4 : 6) k_graphconv_bwd_gather(
+    const float* d_agg, const int64_t* t_rowptr, const int64_t* t_col, const float* t_ew, int64_t n, int Fin, float* d_x) {
   const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= n) return;
   const int64_t e0 = t_rowptr[j], e1 = t_rowptr[j + 1];
   if (e0 == e1) return;
-  if (Fin == 64) return gc_bwd_gather_row<2, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
-  if (Fin == 128) return gc_bwd_gather_row<4, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
-  if (Fin == 32) return gc_bwd_gather_row<1, IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
-  for (int f0 = 0; f0 < Fin; f0 += 32) {
-    const int f = f0 + lane;
-    if (f >= Fin) break;
-    float acc = 0.0f;
-    for (int64_t e = e0; e < e1; ++e) {
-      float v = d_agg[t_col[e] * Fin + f];
-      if (t_ew) v *= t_ew[e];
-      acc += v;
+  if (V > 0) {
+    gc_bwd_gather_row<(V > 0 ? V : 1), IDX32>(d_agg, t_col, t_ew, e0, e1, lane, d_x + j * Fin);
+  } else {
+    for (int f0 = 0; f0 < Fin; f0 += 32) {
+      const int f = f0 + lane;
+      if (f >= Fin) break;
+      float acc = 0.0f;
+      for (int64_t e = e0; e < e1; ++e) {
+        float v = d_agg[t_col[e] * Fin + f];
+        if (t_ew) v *= t_ew[e];
+        acc += v;
+      }
+      d_x[j * Fin + f] += acc;
     }
-    d_x[j * Fin + f] += acc;
   }
+}
+
+static int launch_bwd_gather(const float* d_agg, const int64_t* t_rowptr, const int64_t* t_col, const float* t_ew, int64_t n,
+                             int64_t m, int Fin, float* d_x, cudaStream_t stream) {
+  const int64_t g2 = (n + 7) / 8;
+  GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
+  const bool i32 = (unsigned long long)m * (unsigned long long)Fin < (1ull << 32);      // t_col holds sink rows < m
+#define BG_LAUNCH(V)                                                                                                      \
+  do {                                                                                                                    \
+    if (i32) k_graphconv_bwd_gather<V, true><<<(unsigned)g2, 256, 0, stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);  \
+    else k_graphconv_bwd_gather<V, false><<<(unsigned)g2, 256, 0, stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);     \
+  } while (0)
+  if (Fin == 64) BG_LAUNCH(2);
+  else if (Fin == 32) BG_LAUNCH(1);
+  else if (Fin == 128) BG_LAUNCH(4);
+  else BG_LAUNCH(0);
+#undef BG_LAUNCH
+  return gcm_check_launch("k_graphconv_bwd_gather");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -884,11 +905,128 @@ __global__ void __launch_bounds__(512) k_csr_transpose(const int64_t* rowptr, co
   }
 }
 
+// The same transposition with the source rows assembled and sorted in SHARED memory (16-bit local sink ids, up to 96 K
+// entries = every edge of a cfg5 graph at once; more edges go in several source ranges, each a pass over the graph's edge
+// list) and written out coalesced: k_csr_transpose sorts every row in a thread-local buffer read from / written to global
+// memory one thread per row (3.86 ms at cfg5).  Needs the builder's sink list and graphs of at most TC_MAXN nodes.
+constexpr int TS_THREADS = 1024;
+constexpr int TS_CAP = 96 * 1024;
+__global__ void __launch_bounds__(TS_THREADS) k_csr_transpose_smem(const int64_t* rowptr, const int64_t* col,
+                                                                   const int64_t* node_off, const int64_t* sink_local,
+                                                                   int64_t* t_rowptr, int64_t* t_col, int64_t n_total,
+                                                                   int cap) {
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  int* cnt = reinterpret_cast<int*>(ts_smem);                                   // [TC_MAXN + 1]
+  uint16_t* buf = reinterpret_cast<uint16_t*>(cnt + TC_MAXN + 4);               // [TS_CAP]
+  __shared__ int scan_tmp[TS_THREADS / 32];
+  __shared__ int sh_jb;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n0 = node_off[b], n1 = node_off[b + 1];
+  const int nb = (int)(n1 - n0);
+  const int64_t e0 = rowptr[n0], e1 = rowptr[n1];
+  for (int i = tid; i <= nb; i += TS_THREADS) cnt[i] = 0;
+  __syncthreads();
+  for (int64_t e = e0 + tid; e < e1; e += TS_THREADS) atomicAdd(&cnt[(int)(col[e] - n0) + 1], 1);
+  __syncthreads();
+  // inclusive scan of cnt[1..nb] in place (cnt[0] = 0)
+  const int per = (nb + TS_THREADS - 1) / TS_THREADS;
+  const int base = 1 + tid * per;
+  int sum = 0;
+  for (int i = 0; i < per; ++i)
+    if (base + i <= nb) sum += cnt[base + i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(GCM_FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) scan_tmp[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += scan_tmp[w];
+  int run = woff + incl - sum;
+  for (int i = 0; i < per; ++i)
+    if (base + i <= nb) {
+      run += cnt[base + i];
+      cnt[base + i] = run;                      // cnt[j] = start of source j's row (local), cnt[nb] = number of edges
+    }
+  __syncthreads();
+  for (int i = tid; i < nb; i += TS_THREADS) t_rowptr[n0 + i] = e0 + cnt[i];
+  if (b == gridDim.x - 1 && tid == 0) t_rowptr[n_total] = e1;
+  const int n_edges = (int)(e1 - e0);
+  int ja = 0, base_a = 0;                        // sources < ja are done; base_a = start of row ja
+  while (ja < nb) {
+    __syncthreads();
+    if (tid == 0) {
+      // the largest jb in (ja, nb] whose rows ja .. jb - 1 fit the buffer: cnt[j] (j >= ja) still holds the row starts
+      int lo = ja + 1, hi = nb;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cnt[mid] - base_a <= cap) lo = mid;
+        else hi = mid - 1;
+      }
+      sh_jb = lo;
+    }
+    __syncthreads();
+    const int jb = sh_jb;
+    const int end_b = jb < nb ? cnt[jb] : n_edges;      // start of row jb = end of the range (read before the fill moves it)
+    __syncthreads();
+    for (int64_t e = e0 + tid; e < e1; e += TS_THREADS) {
+      const int j = (int)(col[e] - n0);
+      if (j >= ja && j < jb) {
+        const int at = atomicAdd(&cnt[j], 1);
+        buf[at - base_a] = (uint16_t)sink_local[e];
+      }
+    }
+    __syncthreads();
+    // cnt[j] is now the END of row j for ja <= j < jb; insertion sort of every row by sink, in shared memory
+    for (int j = ja + tid; j < jb; j += TS_THREADS) {
+      const int r0 = (j == ja ? base_a : cnt[j - 1]) - base_a, r1 = cnt[j] - base_a;
+      for (int a = r0 + 1; a < r1; ++a) {
+        const uint16_t v = buf[a];
+        int p = a - 1;
+        while (p >= r0 && buf[p] > v) {
+          buf[p + 1] = buf[p];
+          --p;
+        }
+        buf[p + 1] = v;
+      }
+    }
+    __syncthreads();
+    int64_t* out = t_col + e0 + base_a;
+    for (int i = tid; i < end_b - base_a; i += TS_THREADS) out[i] = n0 + buf[i];
+    ja = jb;
+    base_a = end_b;
+  }
+}
+
+static int g_transpose_cap = TS_CAP;
+/* Test hook: entries of the shared-memory row buffer of k_csr_transpose_smem (0 = the default, 96 K); a small value forces
+ * several source ranges per graph.  Must be >= the longest source row (<= TC_MAXN). */
+extern "C" int gcm_set_csr_transpose_cap(int entries) {
+  GCM_REQUIRE(entries == 0 || (entries >= TC_MAXN && entries <= TS_CAP), "set_csr_transpose_cap: %d outside [%d, %d]", entries,
+              TC_MAXN, TS_CAP);
+  g_transpose_cap = entries ? entries : TS_CAP;
+  return GCM_OK;
+}
+
 extern "C" int gcm_sparse_csr_transpose(const int64_t* rowptr, const int64_t* col, const int64_t* node_off,
                                         const int64_t* sink_local, int B, int64_t n_total, int64_t* t_rowptr,
                                         int64_t* t_col, void* stream) {
   GCM_REQUIRE(rowptr && col && node_off && t_rowptr && t_col && B >= 0 && n_total >= 0, "sparse_csr_transpose: bad arguments");
   if (B == 0) return GCM_OK;
+  static const bool no_smem = getenv("GCM_B200_TRANSPOSE_GLOBAL_SORT") != nullptr;     // A/B switch
+  if (sink_local && !no_smem) {
+    const size_t smem = (size_t)(TC_MAXN + 4) * 4 + (size_t)TS_CAP * 2;
+    cudaError_t e = cudaFuncSetAttribute(k_csr_transpose_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      gcm_set_error("cudaFuncSetAttribute(csr_transpose_smem): %s", cudaGetErrorString(e));
+      return GCM_ERR_CUDA;
+    }
+    k_csr_transpose_smem<<<B, TS_THREADS, smem, (cudaStream_t)stream>>>(rowptr, col, node_off, sink_local, t_rowptr, t_col,
+                                                                        n_total, g_transpose_cap);
+    return gcm_check_launch("k_csr_transpose_smem");
+  }
   k_csr_transpose<<<B, 512, 0, (cudaStream_t)stream>>>(rowptr, col, node_off, sink_local, t_rowptr, t_col, n_total);
   return gcm_check_launch("k_csr_transpose");
 }
@@ -1088,13 +1226,7 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
       if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, agg, Fin, Fin, m, d_w_rel, d_b, stream)) return rc;
       if (int rc = gcm_outer_reduce(dz_scratch, Fout, Fout, x, Fin, Fin, m, d_w_root, nullptr, stream)) return rc;
     }
-    const int64_t g2 = (n + 7) / 8;
-    GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
-    if ((unsigned long long)m * (unsigned long long)Fin < (1ull << 32))      // t_col holds sink rows < m
-      k_graphconv_bwd_gather<true><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
-    else
-      k_graphconv_bwd_gather<false><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
-    return gcm_check_launch("k_graphconv_bwd_gather");
+    return launch_bwd_gather(d_agg, t_rowptr, t_col, t_ew, n, m, Fin, d_x, (cudaStream_t)stream);
   }
   GraphConvBwdArgs a{x, agg, out, d_out, rows, m, n, Fin, Fout, w_rel, w_root, act, d_agg, d_x, d_w_rel, d_w_root, d_b};
   const size_t smem = ((size_t)GB_TM * Fout + (size_t)GB_TM * 2 * Fin + (size_t)2 * Fin * Fout + Fout) * 4;
@@ -1108,13 +1240,7 @@ extern "C" int gcm_sparse_graphconv_bwd(const float* x, const float* agg, const 
   if (grid > n_tiles) grid = (int)n_tiles;
   k_graphconv_bwd_rows<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   if (int rc = gcm_check_launch("k_graphconv_bwd_rows")) return rc;
-  const int64_t g2 = (n + 7) / 8;
-  GCM_REQUIRE(g2 < 2147483647LL, "sparse_graphconv_bwd: too many nodes");
-  if ((unsigned long long)m * (unsigned long long)Fin < (1ull << 32))
-    k_graphconv_bwd_gather<true><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
-  else
-    k_graphconv_bwd_gather<false><<<(unsigned)g2, 256, 0, (cudaStream_t)stream>>>(d_agg, t_rowptr, t_col, t_ew, n, Fin, d_x);
-  return gcm_check_launch("k_graphconv_bwd_gather");
+  return launch_bwd_gather(d_agg, t_rowptr, t_col, t_ew, n, m, Fin, d_x, (cudaStream_t)stream);
 }
 
 extern "C" int gcm_sparse_expand_edges(const int64_t* T, const int64_t* taus, const int64_t* new_off, int B, int tmax,

@@ -158,6 +158,7 @@ _SIGNATURES = {
     "gcm_sparse_graphconv_hint_blocks": (_I, [_P, _I, _I]),
     "gcm_sparse_graphconv_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "gcm_sparse_csr_transpose": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P]),
+    "gcm_set_csr_transpose_cap": (_I, [_I]),
     "gcm_sparse_graphconv_bwd": (_I, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P,
                                       _P, _P, _P, _P, _P, _P, _P, _P]),
     "gcm_pack_edges": (_I, [_P, _P, _L, _I, _I, _L, C.c_float, _P, _P, _P, _P]),

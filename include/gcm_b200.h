@@ -486,6 +486,10 @@ int gcm_sparse_csr_transpose(const int64_t* rowptr, const int64_t* col, const in
                              const int64_t* sink_local, int B, int64_t n_total, int64_t* t_rowptr, int64_t* t_col,
                              void* stream);
 
+/* Test hook: entries of the shared-memory row buffer of the transposition kernel (0 = default); a small value forces
+ * several source ranges per graph. */
+int gcm_set_csr_transpose_cap(int entries);
+
 /* Backward of the above.  t_rowptr [n+1] / t_col [E] / t_ew group the same edges by SOURCE node, with
  * t_col holding the position (in 0..m-1) of the edge's sink among the evaluated rows.  d_x [n, Fin]
  * must be zero on entry and receives dL/dx; d_agg [m, Fin] is scratch; weight gradients accumulate.

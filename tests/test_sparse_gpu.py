@@ -212,28 +212,40 @@ def test_spatial_hash_edges_equal_all_pairs_edges(B, N, PL, radius, walk):
         assert torch.equal(got[("pairs", 1)], got[k]), k
 
 
-def test_csr_transpose_kernel_equals_the_global_sort():
-    """gcm_sparse_csr_transpose (per-graph counting sort + per-row sort of the sinks) must give exactly the grouping the
-    stable global argsort gives: same row pointers, sinks ascending within every source.  Ragged graphs, one empty."""
-    from gcm import sparse_ops
+@pytest.mark.parametrize("N,taus,radius,cap,min_edges", [
+    (300, [300, 1, 257, 0, 64, 299, 128], 0.3, 0, 1000),
+    # > 8192 edges per graph with the smallest row buffer: several source ranges per graph in k_csr_transpose_smem
+    (1500, [1500, 0, 1499, 700], 0.8, 8192, 3 * 8192)])
+def test_csr_transpose_kernel_equals_the_global_sort(N, taus, radius, cap, min_edges):
+    """gcm_sparse_csr_transpose (per-graph counting sort + per-row sort of the sinks, in shared memory when the builder's
+    sink list is at hand) must give exactly the grouping the stable global argsort gives: same row pointers, sinks
+    ascending within every source.  Ragged graphs, one empty."""
+    from gcm import _cabi, sparse_ops
 
     dev = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(5)
-    B, N, F = 7, 300, 8
+    B, F = len(taus), 8
     nodes = torch.randn(B, N, F, generator=gen)
     nodes[..., 0:2] = torch.cumsum(0.1 * torch.randn(B, N, 2, generator=gen), dim=1)
     T = torch.zeros(B, dtype=torch.long)
-    taus = torch.tensor([300, 1, 257, 0, 64, 299, 128])
+    taus = torch.tensor(taus)
     nodes, T, taus = nodes.to(dev), T.to(dev), taus.to(dev)
     new_off = sparse_ops._excl_cumsum(taus)
     offsets = sparse_ops._excl_cumsum(T + taus)
     n = int(taus.sum())
     edges, edge_off, flat_col = sparse_ops.build_edges(nodes, T, taus, new_off, n, int(taus.max()), (1, 2),
-                                                       (slice(0, 2), 0.3), offsets)
-    fast = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N).transposed(None)
-    fast2 = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N, sink_local=edges[1].contiguous()).transposed(None)
+                                                       (slice(0, 2), radius), offsets)
+    assert edges.shape[1] > min_edges
+    try:
+        _cabi.check(_cabi.lib().gcm_set_csr_transpose_cap(cap), "gcm_set_csr_transpose_cap")
+        fast = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N).transposed(None)
+        assert _cabi.lib().gcm_last_kernel().decode() == "k_csr_transpose"
+        fast2 = sparse_ops.Csr(edge_off, flat_col, n, node_off=offsets, max_nodes=N,
+                               sink_local=edges[1].contiguous()).transposed(None)
+        assert _cabi.lib().gcm_last_kernel().decode() == "k_csr_transpose_smem"
+    finally:
+        _cabi.lib().gcm_set_csr_transpose_cap(0)
     slow = sparse_ops.Csr(edge_off, flat_col, n).transposed(None)
-    assert edges.shape[1] > 1000
     for got in (fast, fast2):
         assert torch.equal(got[0], slow[0]) and torch.equal(got[1], slow[1])
 
