@@ -126,7 +126,9 @@ __device__ __forceinline__ void gt_gather(const GcTcArgs& a, int64_t i, int64_t 
 // it, and every SHFL that broadcasts a column index is one more wavefront on the same pipe.  Measured and rejected here:
 // LDG.128 with two rows per warp instruction (2.80 ms per layer at cfg5 against 2.22), broadcasting the index with a warp
 // reduction instead of the shuffle (REDUX of `lane == src ? index : 0`: 2.76 against 2.44 for the same loop shape), one
-// loop of predicated 8-slot batches instead of full batches + a tail (2.44 against 2.22).  Same loads and the same sums in
+// loop of predicated 8-slot batches instead of full batches + a tail (2.44 against 2.22), two scalar loads of 128
+// contiguous bytes per warp instead of one 8-byte load per lane (2.27 against 2.22: the L1 returns ~64 B per clock to
+// global loads whatever their shape -- 21.6 GB of rows per layer at cfg5 = 1.16 ms at best for this design).  Same loads and the same sums in
 // the same order as the fused kernel: bit-identical aggregation.
 template <int V>
 __global__ void __launch_bounds__(256, 6) k_csr_gather(const GcTcArgs a) {
