@@ -128,7 +128,11 @@ __device__ __forceinline__ void gt_gather(const GcTcArgs& a, int64_t i, int64_t 
 // reduction instead of the shuffle (REDUX of `lane == src ? index : 0`: 2.76 against 2.44 for the same loop shape), one
 // loop of predicated 8-slot batches instead of full batches + a tail (2.44 against 2.22), two scalar loads of 128
 // contiguous bytes per warp instead of one 8-byte load per lane (2.27 against 2.22: the L1 returns ~64 B per clock to
-// global loads whatever their shape -- 21.6 GB of rows per layer at cfg5 = 1.16 ms at best for this design).  Same loads and the same sums in
+// global loads whatever their shape -- 21.6 GB of rows per layer at cfg5 = 1.16 ms at best for this design).  Also built,
+// measured and removed: the source rows staged in SHARED memory (256 sink rows of one graph per CTA, the graph's rows
+// walked in double-buffered tiles of 384 rows brought by bulk copies, per-row cursors over the ascending column lists,
+// index runs read back by uniform 16-byte loads): bit-identical sums, but 4.4 ms per layer -- at ~20 edges per row a
+// 96 KB tile serves ~25 edges per warp, so a CTA spends its time waiting for tiles (one CTA of 200 KB per SM).  Same loads and the same sums in
 // the same order as the fused kernel: bit-identical aggregation.
 template <int V>
 __global__ void __launch_bounds__(256, 6) k_csr_gather(const GcTcArgs a) {

@@ -443,6 +443,72 @@ def test_graphconv_block_local_kernel_matches_the_others(F, H, act, masked):
             assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
 
 
+@pytest.mark.parametrize("F,H,act,masked", [(64, 64, "tanh", False), (32, 48, "relu", False), (64, 32, "none", True)])
+def test_graphconv_two_pass_on_ragged_blocks_matches_the_others(F, H, act, masked):
+    """The two-pass forward (k_csr_gather + the streaming product kernel) and the backward (shared-memory transposition,
+    transposed gather, paired weight-gradient reduction) on a block-diagonal graph of >= 8192 rows with ragged blocks --
+    empty, one row, sizes that are not multiples of any tile -- and sources before AND after the sink, against the
+    CUDA-core kernel and the float64 definition: forward values and gradients."""
+    from gcm import _cabi, sparse_ops
+
+    dev = torch.device("cuda:0")
+    lib = _cabi.lib()
+    gen = torch.Generator().manual_seed(5 * F + H)
+    sizes = torch.tensor([1000, 0, 1, 513, 700, 384, 385, 2049, 1500, 900, 1300, 256, 767])
+    node_off = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(sizes, 0)])
+    n = int(node_off[-1])
+    assert n >= 8192
+    gid = torch.repeat_interleave(torch.arange(sizes.numel()), sizes)
+    deg = torch.randint(0, 45, (n,), generator=gen)
+    deg[node_off[3] + 7] = 200                                   # several 32-edge chunks in one row
+    deg[sizes[gid] == 1] = 0
+    sink = torch.repeat_interleave(torch.arange(n), deg)
+    src = node_off[gid[sink]] + (torch.rand(sink.numel(), generator=gen) * sizes[gid[sink]].float()).long().clamp(max=10 ** 9)
+    src = torch.minimum(src, node_off[gid[sink] + 1] - 1)
+    key = torch.unique(sink * n + src)                           # sorted by (sink, source), duplicates merged
+    sink, src = key // n, key % n
+    csr = sparse_ops.Csr.from_sorted_edges(sink.to(dev), src.to(dev), n)
+    csr.node_off, csr.max_nodes = node_off.to(dev), int(sizes.max())
+    x = torch.randn(n, F, generator=gen).to(dev)
+    w_rel = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    w_root = (torch.randn(H, F, generator=gen) / F ** 0.5).to(dev)
+    bias = torch.randn(H, generator=gen).to(dev)
+    mask = (torch.rand(sink.numel(), generator=gen) < 0.7).float().to(dev) if masked else None
+    outs, grads = {}, {}
+    try:
+        for which in (_cabi.GC_CUDA_CORES, _cabi.GC_TC):
+            lib.gcm_set_graphconv_kernel(which)
+            with torch.no_grad():
+                outs[which] = sparse_ops.graph_conv_csr(x, csr, None, w_rel, bias, w_root, act, edge_mask=mask)
+            if mask is None:
+                xg = x.clone().requires_grad_(True)
+                wr, wo, bb = (t.clone().requires_grad_(True) for t in (w_rel, w_root, bias))
+                out = sparse_ops.graph_conv_csr(xg, csr, None, wr, bb, wo, act)
+                (out * torch.linspace(-1, 1, out.numel(), device=dev).view_as(out)).sum().backward()
+                grads[which] = (xg.grad, wr.grad, wo.grad, bb.grad)
+    finally:
+        lib.gcm_set_graphconv_kernel(_cabi.GC_AUTO)
+    w = torch.ones(sink.numel(), device=dev) if mask is None else mask
+    agg = torch.zeros(n, F, device=dev, dtype=torch.float64).index_add_(0, sink.to(dev), (x[src.to(dev)] * w[:, None]).double())
+    ref = agg @ w_rel.double().t() + bias.double() + x.double() @ w_root.double().t()
+    ref = {"tanh": torch.tanh, "relu": torch.relu, "none": lambda t: t}[act](ref)
+    a, b = outs[_cabi.GC_CUDA_CORES], outs[_cabi.GC_TC]
+    scale = max(1.0, float(ref.abs().max()))
+    assert float((b.double() - ref).abs().max()) / scale < 2e-5
+    assert float((a - b).abs().max()) / scale < 1e-5
+    if mask is None:
+        # dL/dx against the definition: d_x = (dz W_root) + A^T (dz W_rel), in float64
+        xd = x.double().requires_grad_(True)
+        aggd = torch.zeros(n, F, device=dev, dtype=torch.float64).index_add(0, sink.to(dev), xd[src.to(dev)])
+        outd = aggd @ w_rel.double().t() + bias.double() + xd @ w_root.double().t()
+        outd = {"tanh": torch.tanh, "relu": torch.relu, "none": lambda t: t}[act](outd)
+        (outd * torch.linspace(-1, 1, outd.numel(), device=dev, dtype=torch.float64).view_as(outd)).sum().backward()
+        gx = grads[_cabi.GC_TC][0]
+        assert float((gx.double() - xd.grad).abs().max()) / max(1.0, float(xd.grad.abs().max())) < 2e-5
+        for ga, gb in zip(grads[_cabi.GC_CUDA_CORES], grads[_cabi.GC_TC]):
+            assert float((ga - gb).abs().max()) / max(1.0, float(ga.abs().max())) < 1e-4
+
+
 def test_finite_check_kernel_finds_nan_and_inf_anywhere():
     """gcm_any_nonfinite (the one-pass form of sparse_gcm.py:203's assert) against torch.isfinite: clean data, one NaN /
     +inf / -inf at the start, in the middle, in the unaligned tail."""
