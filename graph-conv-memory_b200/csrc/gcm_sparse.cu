@@ -58,6 +58,52 @@ __global__ void __launch_bounds__(256) k_sparse_write_flatten_oop(const VT* node
   }
 }
 
+// Adjoint of the step above, one pass: d_x[b, k] = d_nodes_out[b, T_b + k] + d_flat[off_b + T_b + k] (rows that came from
+// x), d_nodes_in[b, j] = d_nodes_out[b, j] + d_flat[off_b + j] on the other rows and 0 on the rows x overwrote.  Any of
+// d_nodes_out / d_flat / d_nodes_in / d_x may be NULL (treated as zero / not wanted).
+template <typename VT>
+__device__ __forceinline__ VT wf_add(const VT& a, const VT& b);
+template <>
+__device__ __forceinline__ float wf_add<float>(const float& a, const float& b) { return a + b; }
+template <>
+__device__ __forceinline__ float4 wf_add<float4>(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+template <typename VT>
+__device__ __forceinline__ VT wf_zero();
+template <>
+__device__ __forceinline__ float wf_zero<float>() { return 0.0f; }
+template <>
+__device__ __forceinline__ float4 wf_zero<float4>() { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+
+template <typename VT>
+__global__ void __launch_bounds__(256) k_sparse_write_flatten_bwd(const VT* d_nodes_out, const VT* d_flat, const int64_t* T,
+                                                                  const int64_t* taus, const int64_t* offsets, int N, int Fv,
+                                                                  int tmax, VT* d_nodes_in, VT* d_x) {
+  const int b = blockIdx.x;
+  const int t0 = (int)T[b], tau = (int)taus[b];
+  const int rows = max(N, tmax);
+  const int j0 = blockIdx.y * WF_ROWS, j1 = min(rows, j0 + WF_ROWS);
+  const VT* dn_b = d_nodes_out ? d_nodes_out + (size_t)b * N * Fv : nullptr;
+  const VT* df_b = d_flat ? d_flat + offsets[b] * Fv : nullptr;
+  VT* di_b = d_nodes_in ? d_nodes_in + (size_t)b * N * Fv : nullptr;
+  VT* dx_b = d_x ? d_x + (size_t)b * tmax * Fv : nullptr;
+  const int n_valid = min(t0 + tau, N);
+  for (int i = j0 * Fv + threadIdx.x; i < j1 * Fv; i += 256) {
+    const int j = i / Fv;
+    if (j < N && (di_b || dx_b)) {
+      // gradient that arrives at node row j of nodes_out
+      VT gsum = dn_b ? dn_b[i] : wf_zero<VT>();
+      if (df_b && j < n_valid) gsum = wf_add<VT>(gsum, df_b[i]);
+      const bool is_new = j >= t0 && j < t0 + tau;
+      if (di_b) di_b[i] = is_new ? wf_zero<VT>() : gsum;
+      if (dx_b && is_new) dx_b[i - t0 * Fv] = gsum;
+    }
+    // rows of x that were never written (k >= tau, or T_b + k >= N): zero gradient
+    if (dx_b && j < tmax && (j >= tau || t0 + j >= N)) dx_b[i] = wf_zero<VT>();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused edge generation
 // ------------------------------------------------------------------------------------------------
@@ -1063,6 +1109,27 @@ extern "C" int gcm_sparse_write_flatten_oop(const float* nodes_in, float* nodes_
                                                                             F, tmax, flat);
   }
   return gcm_check_launch("k_sparse_write_flatten_oop");
+}
+
+extern "C" int gcm_sparse_write_flatten_bwd(const float* d_nodes_out, const float* d_flat, const int64_t* T,
+                                            const int64_t* taus, const int64_t* offsets, int B, int N, int F, int tmax,
+                                            float* d_nodes_in, float* d_x, void* stream) {
+  GCM_REQUIRE(T && taus && offsets && B >= 0 && N >= 1 && F >= 1 && tmax >= 0, "sparse_write_flatten_bwd: bad arguments");
+  GCM_REQUIRE((long long)(N > tmax ? N : tmax) * F < 2147483647LL, "sparse_write_flatten_bwd: N * F too large");
+  if (B == 0 || (!d_nodes_in && !d_x)) return GCM_OK;
+  const int rows = N > tmax ? N : tmax;
+  dim3 grid(B, (rows + WF_ROWS - 1) / WF_ROWS);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d_nodes_out) | reinterpret_cast<uintptr_t>(d_flat) |
+                       reinterpret_cast<uintptr_t>(d_nodes_in) | reinterpret_cast<uintptr_t>(d_x);
+  if (F % 4 == 0 && (al & 15) == 0) {
+    k_sparse_write_flatten_bwd<float4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(d_nodes_out), reinterpret_cast<const float4*>(d_flat), T, taus, offsets, N, F / 4, tmax,
+        reinterpret_cast<float4*>(d_nodes_in), reinterpret_cast<float4*>(d_x));
+  } else {
+    k_sparse_write_flatten_bwd<float><<<grid, 256, 0, (cudaStream_t)stream>>>(d_nodes_out, d_flat, T, taus, offsets, N, F, tmax,
+                                                                            d_nodes_in, d_x);
+  }
+  return gcm_check_launch("k_sparse_write_flatten_bwd");
 }
 
 static int g_edge_builder = GCM_EB_AUTO;

@@ -123,6 +123,7 @@ _SIGNATURES = {
     "gcm_select_dense": (_I, [_P, _P, _P, _I, _I, _I, C.POINTER(SelectorC), _P]),
     "gcm_sparse_write_flatten": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_sparse_write_flatten_oop": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "gcm_sparse_write_flatten_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "gcm_sparse_build_edges": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, C.c_float, _P,
                                     _P, _P, _L, _P, _P, _P, _I, _P]),
     "gcm_sparse_expand_edges": (_I, [_P, _P, _P, _I, _I, _P, _I, _P, _P, _L, _P, _P, _P]),

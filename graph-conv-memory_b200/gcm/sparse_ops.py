@@ -65,17 +65,20 @@ class _WriteFlattenFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_nodes_out, d_flat):
+        # one pass (gcm_sparse_write_flatten_bwd) instead of ragged index arithmetic over [B,N,F] tensors in torch
         T, taus, offsets, nshape, xshape = ctx.meta
         B, N, F = nshape
         dev = T.device
-        vb, vk = ragged_arange(T + taus)                    # every valid row of the flat layout
-        d_nodes = torch.zeros(nshape, device=dev) if d_nodes_out is None else d_nodes_out.clone()
-        if d_flat is not None:
-            d_nodes[vb, vk] += d_flat
-        nb, nk = ragged_arange(taus)                        # the rows that came from x
-        d_x = torch.zeros(xshape, device=dev)
-        d_x[nb, nk] = d_nodes[nb, nk + T[nb]]
-        d_nodes[nb, nk + T[nb]] = 0
+        want_nodes, want_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_nodes or want_x):
+            return None, None, None, None, None, None
+        dn = None if d_nodes_out is None else d_nodes_out.contiguous().float()
+        df = None if d_flat is None else d_flat.contiguous().float()
+        d_nodes = torch.empty(nshape, device=dev) if want_nodes else None
+        d_x = torch.empty(xshape, device=dev) if want_x else None
+        _cabi.check(_cabi.lib().gcm_sparse_write_flatten_bwd(
+            _cabi.ptr(dn), _cabi.ptr(df), T.data_ptr(), taus.data_ptr(), offsets.data_ptr(), B, N, F, xshape[1],
+            _cabi.ptr(d_nodes), _cabi.ptr(d_x), _cabi.stream_ptr(dev)), "gcm_sparse_write_flatten_bwd")
         return d_nodes, d_x, None, None, None, None
 
 

@@ -422,6 +422,14 @@ int gcm_sparse_write_flatten_oop(const float* nodes_in, float* nodes_out, const 
                                  const int64_t* taus, const int64_t* offsets, int B, int N, int F, int tmax,
                                  float* flat, void* stream);
 
+/* Adjoint of gcm_sparse_write_flatten_oop in one pass (autograd of sparse_gcm.py:109-123): d_x [B,tmax,F] receives the
+ * gradient of the rows that came from x (d_nodes_out[b, T_b + k] + d_flat[offsets[b] + T_b + k]; 0 for unwritten rows),
+ * d_nodes_in [B,N,F] the gradient of the other rows (0 on the rows x overwrote).  d_nodes_out, d_flat, d_nodes_in, d_x
+ * may each be NULL (zero / not wanted). */
+int gcm_sparse_write_flatten_bwd(const float* d_nodes_out, const float* d_flat, const int64_t* T, const int64_t* taus,
+                                 const int64_t* offsets, int B, int N, int F, int tmax, float* d_nodes_in, float* d_x,
+                                 void* stream);
+
 /* Fused edge selectors for the new nodes s in [T_b, T_b + tau_b): sources k < s with
  * (s - k in hops) [TemporalEdge, sparse_edge_selectors/temporal.py:19-63] OR
  * ||pos_s - pos_k||_2 < radius [SpatialRadiusEdge causal, sparse_edge_selectors/spatial.py:74-115;
