@@ -814,9 +814,11 @@ def run_sparse(ctx, workload, B, K, W, args):
     total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     t_hi = time.perf_counter()
     E = int(hid[1]._nnz())
-    kernel_name = "k_graphconv_fwd x2 (+ edge build)" + (
-        " + backward (k_linear2, k_outer_reduce, k_graphconv_bwd_gather)" if train else "")
-    return {"total_ms": total_ms, "kern_ms": total_ms / K, "launches": K * 5, "kernel_name": kernel_name,
+    kernel_name = "whole call: edge search + expansion, node write, 2 x (k_csr_gather + k_graphconv_fwd_tc)" + (
+        " + backward (k_csr_transpose_smem, k_act_bwd_v4, k_linear_tc32, k_outer_tc32, k_graphconv_bwd_gather,"
+        " k_sparse_write_flatten_bwd)" if train else "")
+    lib_launches = 8 + (15 if train else 0)       # this library's kernels per call (torch's scans / fills not counted)
+    return {"total_ms": total_ms, "kern_ms": total_ms / K, "launches": K * lib_launches, "kernel_name": kernel_name,
             "unit_per_step": B * N, "t_lo": t_lo, "t_hi": t_hi, "extra": (B * N, E), "state": mode,
             "timed_call": f"{K} SparseGCM.forward calls (all {N} observations of every graph at once)", "e2e": None}
 
