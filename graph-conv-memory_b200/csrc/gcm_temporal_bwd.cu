@@ -119,19 +119,33 @@ __global__ void __launch_bounds__(256) k_shift_sum(const float* __restrict__ src
 // The same for sign = +1, H = 32, tiled output, hops <= 4: a thread owns one 16-byte chunk of one graph and WALKS the
 // output positions downwards, keeping the source rows pos .. pos + 4 in registers, so every source row is read once (the
 // row-parallel kernel above re-reads each row once per hop through L2: 0.59 ms for a cfg2 window, this one 0.4)
+// SM: how the source is addressed.  0: [n_src, B, 32] contiguous.  1: element strides (s_t, s_b, 1) with 16-byte aligned rows
+// (a [B, T, 32] gradient read in place: no transposing copy).  2: any strides (s_t, s_b, s_h), e.g. all zero for the
+// broadcast gradient of a sum loss, which is then never materialised.  act_out is always contiguous.
+template <int SM>
 __global__ void __launch_bounds__(256) k_shift_sum_walk(const float* __restrict__ src, int src_pos0, int n_src, int valid_lo,
                                                         unsigned hop_mask, float* __restrict__ out, int out_pos0, int n_out,
-                                                        int B, const float* __restrict__ act_out, int act) {
+                                                        int B, const float* __restrict__ act_out, int act, long long s_t,
+                                                        long long s_b, long long s_h) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;       // (graph, 16-byte chunk)
   if (j >= B * 8) return;
   const float4* s4 = reinterpret_cast<const float4*>(src) + j;
   const float4* a4 = reinterpret_cast<const float4*>(act_out) + j;
   const size_t row = (size_t)B * 8;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* sp = src + (long long)(j >> 3) * s_b + (long long)((j & 7) * 4) * s_h;      // SM != 0
   auto fetch = [&](int q) {
     const int jq = q - src_pos0;
     if (q < valid_lo || jq < 0 || jq >= n_src) return zero;
-    float4 v = __ldcs(s4 + (size_t)jq * row);
+    float4 v;
+    if (SM == 0) {
+      v = __ldcs(s4 + (size_t)jq * row);
+    } else if (SM == 1) {
+      v = __ldcs(reinterpret_cast<const float4*>(sp + (long long)jq * s_t));
+    } else {
+      const float* p = sp + (long long)jq * s_t;
+      v = make_float4(p[0], p[s_h], p[2 * s_h], p[3 * s_h]);
+    }
     if (act_out) {
       const float4 o = __ldcs(a4 + (size_t)jq * row);
       v.x *= gcm_act_grad(o.x, act);
@@ -192,12 +206,14 @@ extern "C" int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hop
   return gcm_check_launch("k_temporal_gather");
 }
 
-extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo,
+static int shift_sum_impl(const float* src, long long s_t, long long s_b, long long s_h, bool strided, long long src_pos0,
+                          int n_src, long long valid_lo,
                                       const int32_t* hops, int n_hops, int sign, float* out, long long out_pos0,
                                       int n_out, int B, int H, int tiled, const float* act_out, int act, void* stream) {
   GCM_REQUIRE(src && out && n_src >= 0 && n_out >= 0 && B >= 0 && H >= 4 && (H & 3) == 0 && (sign == 1 || sign == -1),
               "temporal_shift_sum: bad arguments (H must be a multiple of 4)");
-  GCM_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+  const bool scalar_src = strided && !(s_h == 1 && ((s_t | s_b) & 3) == 0);
+  GCM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & (scalar_src ? 3 : 15)) == 0,
               "temporal_shift_sum: pointers must be 16-byte aligned");
   HopList hl;
   GCM_REQUIRE(hop_list(hops, n_hops, hl), "temporal_shift_sum: bad hop list");
@@ -218,12 +234,36 @@ extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int 
   }
   static const bool no_walk = getenv("GCM_B200_NO_SHIFT_WALK") != nullptr;     // A/B switch
   if (tiled && sign == 1 && H == 32 && max_hop <= 4 && n_out >= 8 && !no_walk) {
-    k_shift_sum_walk<<<(unsigned)(((long long)B * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        src, (int)src_pos0, n_src, (int)valid_lo, hop_mask, out, (int)out_pos0, n_out, B, act_out, act);
+    const unsigned wg = (unsigned)(((long long)B * 8 + 255) / 256);
+    if (!strided)
+      k_shift_sum_walk<0><<<wg, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hop_mask, out,
+                                                                (int)out_pos0, n_out, B, act_out, act, 0, 0, 0);
+    else if (s_h == 1 && ((s_t | s_b) & 3) == 0)
+      k_shift_sum_walk<1><<<wg, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hop_mask, out,
+                                                                (int)out_pos0, n_out, B, act_out, act, s_t, s_b, s_h);
+    else
+      k_shift_sum_walk<2><<<wg, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hop_mask, out,
+                                                                (int)out_pos0, n_out, B, act_out, act, s_t, s_b, s_h);
     return gcm_check_launch("k_shift_sum_walk");
   }
+  if (strided) return GCM_ERR_UNSUPPORTED;      // only the walking kernel reads through strides
   const dim3 grid((unsigned)(((long long)B * (H >> 2) + 255) / 256), (unsigned)n_out);
   k_shift_sum<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (int)src_pos0, n_src, (int)valid_lo, hl, sign, out,
                                                       (int)out_pos0, B, H, tiled, act_out, act);
   return gcm_check_launch("k_shift_sum");
+}
+
+extern "C" int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo,
+                                      const int32_t* hops, int n_hops, int sign, float* out, long long out_pos0,
+                                      int n_out, int B, int H, int tiled, const float* act_out, int act, void* stream) {
+  return shift_sum_impl(src, 0, 0, 0, false, src_pos0, n_src, valid_lo, hops, n_hops, sign, out, out_pos0, n_out, B, H, tiled,
+                        act_out, act, stream);
+}
+
+extern "C" int gcm_temporal_shift_sum_strided(const float* src, long long s_t, long long s_b, long long s_h,
+                                              long long src_pos0, int n_src, long long valid_lo, const int32_t* hops,
+                                              int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H,
+                                              int tiled, const float* act_out, int act, void* stream) {
+  return shift_sum_impl(src, s_t, s_b, s_h, true, src_pos0, n_src, valid_lo, hops, n_hops, sign, out, out_pos0, n_out, B, H,
+                        tiled, act_out, act, stream);
 }

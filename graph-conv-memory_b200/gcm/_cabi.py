@@ -107,6 +107,7 @@ _SIGNATURES = {
     "gcm_state_log_write_seq": (_I, [C.POINTER(DenseStateC), _P, _L, _L, _I, _P]),
     "gcm_temporal_gather": (_I, [C.POINTER(DenseStateC), _P, _I, _L, _I, _P, _I, _P]),
     "gcm_temporal_shift_sum": (_I, [_P, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _I, _P, _I, _P]),
+    "gcm_temporal_shift_sum_strided": (_I, [_P, _L, _L, _L, _L, _I, _L, _P, _I, _I, _P, _L, _I, _I, _I, _I, _P, _I, _P]),
     "gcm_temporal_window_bwd_workspace": (_L, []),
     "gcm_temporal_window_bwd_set_trace": (_I, [_P, _I]),
     "gcm_temporal_window_bwd": (_I, [_P, _P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

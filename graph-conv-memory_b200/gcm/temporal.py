@@ -259,6 +259,21 @@ def _shift_sum(plan, src, src_pos0, sign, out, out_pos0, n_out=None, act_out=Non
     act_out given: the source rows are src * act'(act_out)"""
     hops, nh = _hops(plan, src.device)
     n_src, B, H = src.shape
+    if src.dtype != torch.float32:
+        src = src.float()
+    if not src.is_contiguous():
+        # dL/dbelief as autograd delivered it -- a [B, T, H] tensor seen time-major, or the expanded scalar of a sum loss --
+        # is read through its strides where the kernel can (no transposing copy, no materialised broadcast)
+        rc = _cabi.ERR_UNSUPPORTED
+        if src.dtype == torch.float32 and n_out is not None:
+            rc = _cabi.lib().gcm_temporal_shift_sum_strided(
+                src.data_ptr(), src.stride(0), src.stride(1), src.stride(2), src_pos0, n_src, 0, hops.data_ptr(), nh, sign,
+                out.data_ptr(), out_pos0, n_out, B, H, 1, None if act_out is None else act_out.data_ptr(), act,
+                _cabi.stream_ptr(src.device))
+        if rc != _cabi.ERR_UNSUPPORTED:
+            _cabi.check(rc, "gcm_temporal_shift_sum_strided")
+            return
+        src = src.contiguous().float()
     _cabi.check(_cabi.lib().gcm_temporal_shift_sum(src.data_ptr(), src_pos0, n_src, 0, hops.data_ptr(), nh, sign,
                                                    out.data_ptr(), out_pos0, out.shape[0] if n_out is None else n_out, B, H,
                                                    0 if n_out is None else 1,
@@ -411,7 +426,7 @@ class _TRootFn(torch.autograd.Function):
             win.kmax, win.dz2, win.cache, win.lazy, win.xrec = -1, None, None, None, None
             return (torch.zeros_like(d_token), None, None, None, *ones._param_grads(g, fused[0]))
         if win.lazy is not None:
-            _deliver(plan, st, win, 0, Kc, *win.lazy)
+            _deliver(plan, st, win, 0, Kc, win.lazy[0].contiguous().float(), win.lazy[1])
             win.lazy = None
         if Kc > 0:
             p_lo, p_hi = win.P0 - mh, win.P0 + Kc
@@ -500,12 +515,12 @@ class _TSeqFn(torch.autograd.Function):
             raise RuntimeError("backward through a GCM window after a newer window was recorded on the same state")
         d_x = d_hist = None
         want_hist = ctx.has_hist and ctx.needs_input_grad[5]
-        d_tm = d_beliefs.transpose(0, 1).contiguous().float()
         if k0 == 0 and T == st.steps - win.chain_start and win.kmax < 0 and _fused_shape(plan, st):
-            # this node is the whole window: the fused kernel's shift-sum forms dz2 on the fly
-            win.lazy, win.kmax, win.xrec = (d_tm, ctx.buf), T - 1, ctx.xrec
+            # this node is the whole window: the fused kernel's shift-sum forms dz2 on the fly, reading dL/dbelief
+            # through its strides (time-major VIEW: not copied here)
+            win.lazy, win.kmax, win.xrec = (d_beliefs.transpose(0, 1), ctx.buf), T - 1, ctx.xrec
         else:
-            _deliver(plan, st, win, k0, T, d_tm, ctx.buf)
+            _deliver(plan, st, win, k0, T, d_beliefs.transpose(0, 1).contiguous().float(), ctx.buf)
         ctx.buf = ctx.xrec = None
         if ctx.needs_input_grad[0] or want_hist:
             Kc, mh = win.kmax + 1, plan.max_hop
@@ -519,7 +534,7 @@ class _TSeqFn(torch.autograd.Function):
                     win.cache, rows = ("fused", fz[0]), fz[1]     # the weight gradients are done: the root returns them
                 else:
                     if win.lazy is not None:
-                        _deliver(plan, st, win, 0, Kc, *win.lazy)
+                        _deliver(plan, st, win, 0, Kc, win.lazy[0].contiguous().float(), win.lazy[1])
                         win.lazy = None
                     full = _rows(plan, st, win, win.P0 - mh, win.P0 + Kc, Kc)
                     win.cache = full

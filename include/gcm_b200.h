@@ -233,6 +233,15 @@ int gcm_temporal_gather(const gcm_dense_state* st, const int32_t* hops, int n_ho
 int gcm_temporal_shift_sum(const float* src, long long src_pos0, int n_src, long long valid_lo, const int32_t* hops,
                            int n_hops, int sign, float* out, long long out_pos0, int n_out, int B, int H, int tiled,
                            const float* act_out, int act, void* stream);
+/* The same with the source read through element strides: src[j, b, h] at src + j * s_t + b * s_b + h * s_h (a [B, T, H]
+ * gradient of the beliefs read in place, or the stride-0 gradient of a sum loss, which autograd hands over as an
+ * expanded scalar: neither is copied).  Only the shape the fused window backward uses is covered (tiled = 1, sign = +1,
+ * H = 32, hops <= 4, n_out >= 8); anything else returns GCM_ERR_UNSUPPORTED and the caller passes a contiguous copy to
+ * gcm_temporal_shift_sum.  act_out stays contiguous [n_src, B, H]. */
+int gcm_temporal_shift_sum_strided(const float* src, long long s_t, long long s_b, long long s_h, long long src_pos0,
+                                   int n_src, long long valid_lo, const int32_t* hops, int n_hops, int sign, float* out,
+                                   long long out_pos0, int n_out, int B, int H, int tiled, const float* act_out, int act,
+                                   void* stream);
 
 /* ---- the row products and weight-gradient reductions of that backward as ONE kernel (csrc/gcm_temporal_bwd_tc.cu) ----
  * Replaces gcm_linear_tc32 x 2 + gcm_act_backward + gcm_temporal_shift_sum + gcm_outer_reduce_tc32 x 2 of the window

@@ -116,6 +116,69 @@ def test_fused_window_kernel_serves_f32_shapes_and_matches_the_separate_products
         assert rel_err(res[True][1], res[False][1]) < 2e-5
 
 
+@pytest.mark.parametrize("layout", ["sum", "batch_major", "sliced", "bf16"])
+def test_window_backward_reads_the_belief_gradient_through_its_strides(layout, monkeypatch):
+    """dL/dbelief reaches the sequence node as autograd made it: the expanded scalar of a sum loss (all strides 0; torch's
+    mean backward divides AFTER expanding, so a mean loss arrives dense), a
+    [B, T, H] tensor (seen time-major: transposed strides), a slice of a wider tensor (rows not 16-byte aligned).  The fused
+    window backward reads it in place (gcm_temporal_shift_sum_strided: no materialised broadcast, no transposing copy);
+    other dtypes are converted first.  Same gradients as the separate-products path, which works on a contiguous copy."""
+    from gcm import _cabi
+    from gcm.gcm import DenseGCM
+
+    dev = torch.device("cuda:0")
+    B, N, F, T, hops = 200, 16, 32, 23, (1, 2, 4)
+    spec = [("temporal", hops, "forward")]
+    gen = torch.Generator().manual_seed(11)
+    obs = (torch.randn(T, B, F, generator=gen) * 0.5).to(dev)
+    w_bt = torch.randn(B, T, 32, generator=gen).to(dev)
+    w_wide = torch.randn(T, B, 33, generator=gen).to(dev)
+    p = oracle.make_params(F, 32)
+    lib = _cabi.lib()
+    real, calls = lib.gcm_temporal_shift_sum_strided, []
+
+    def spy(*a):
+        calls.append(a[1:4])
+        return real(*a)
+    monkeypatch.setattr(lib, "gcm_temporal_shift_sum_strided", spy)
+    res = {}
+    for fused in (True, False):
+        calls.clear()
+        if fused:
+            monkeypatch.delenv("GCM_B200_NO_WINDOW_BWD_TC", raising=False)
+        else:
+            monkeypatch.setenv("GCM_B200_NO_WINDOW_BWD_TC", "1")
+        gnn, convs = make_dense_gnn(F, 32, p, ("tanh", "tanh"))
+        mod = DenseGCM(gnn.to(dev), edge_selectors=make_selector(spec), graph_size=N)
+        with torch.no_grad():                                   # a running rollout first: the window is ONE sequence node
+            _, hidden = mod.forward_sequence(obs[:7].transpose(0, 1), None)
+        x = obs.clone().requires_grad_(True)
+        if layout == "batch_major":
+            outs, hidden = mod.forward_sequence(x.transpose(0, 1), hidden)                 # [B, T, H]
+            (outs * w_bt).sum().backward()
+            want = [(32, T * 32, 1)]
+        else:
+            outs, hidden = mod.forward_sequence(x, hidden, time_major=True)                # [T, B, H]
+            if layout == "sum":
+                (outs.sum() / outs.numel()).backward()
+                want = [(0, 0, 0)]
+            elif layout == "sliced":
+                (torch.cat([outs, outs.new_zeros(T, B, 1)], dim=2) * w_wide).sum().backward()   # gradient: a slice of [T,B,33]
+                want = [(B * 33, 33, 1)]
+            else:
+                (outs.to(torch.bfloat16) * w_wide[..., :32].to(torch.bfloat16)).sum().backward()
+                want = []                                                                  # converted to float32: contiguous
+        if fused and layout != "bf16":
+            assert calls == want, calls
+        elif not fused:
+            assert calls == []
+        res[fused] = (named_grads(convs), x.grad.clone())
+    tol = 2e-5 if layout != "bf16" else 1e-2
+    for k in res[True][0]:
+        assert rel_err(res[True][0][k], res[False][0][k]) < tol, k
+    assert rel_err(res[True][1], res[False][1]) < tol
+
+
 def test_truncated_bptt_over_windows_with_weight_updates():
     """A running rollout trained window by window (m_t.detach(), SGD step in between): fill without autograd, then three
     windows; every window's gradients against the fp64 oracle doing the same."""
