@@ -17,7 +17,8 @@ JSON line (rank 0):
   roofline     algorithmic bytes per launch / kernel duration (CUDA events around
                back-to-back launches), against MEASURED_PEAKS.json
   cpu_baseline the reference step on the host cores (bounded sample)
-  also         fwd+bwd records of the same run: cfg2-bptt (BPTT over T=64 steps of the cfg2 chain) and cfg3 (DenseEdge
+  also         records of the other BASELINE configs in the same run (cfg4-cosine, cfg5, cfg5-train: one GPU only) and the
+               fwd+bwd records: cfg2-bptt (BPTT over T=64 steps of the cfg2 chain) and cfg3 (DenseEdge
                N=256 H=128 T=64 with the NCCL gradient all-reduce), each with its own roofline / clocks / e2e
 
 Other workloads (`--workload cfg1|cfg2-pre|cfg2-bptt|cfg2-pre-bptt|cfg3|cfg3-seq|cfg4-cosine|cfg4-euclid|cfg5|cfg5-train`) report the
@@ -935,8 +936,19 @@ def main():
     also = []
     if args.workload == "cfg2" and not args.no_also and args.batch is None:
         # the fwd+bwd half of BASELINE.json's metric, measured in the same run
-        for wl, k in (("cfg2-bptt", 4), ("cfg3", 3), ("cfg3-seq", 3)):
-            rec = run_workload(ctx, wl, k, 3, args)
+        wls = [("cfg2-bptt", 4), ("cfg3", 3), ("cfg3-seq", 3)]
+        if world == 1:
+            # the distance-selector and sparse configs of BASELINE.json in the same driver-run record (one GPU: they shard
+            # like cfg2, no collective on their forward path)
+            wls += [("cfg4-cosine", 20), ("cfg5", 3), ("cfg5-train", 3)]
+        for wl, k in wls:
+            try:
+                rec = run_workload(ctx, wl, k, 3, args)
+            except Exception as exc:      # an auxiliary record must not take the headline line down with it
+                if wl in ("cfg2-bptt", "cfg3", "cfg3-seq"):
+                    raise
+                progress(f"{wl}: skipped ({type(exc).__name__}: {exc})")
+                rec = None
             if rec is not None:
                 rec = {key: rec[key] for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
                                                  "dtype", "config", "clocks", "gpu_launches", "roofline", "e2e")}
