@@ -550,23 +550,30 @@ __global__ void __launch_bounds__(TCG_THREADS, 2) k_outer_tc(const OuterTcArgs a
 // The same reduction in 3xTF32 (fp32-accurate: hi/lo split of both operands, lo*Bhi + hi*Blo + hi*Bhi), for callers that
 // stay in float32 (the sparse GraphConv backward, DenseEdge states with a float32 cache).  A^T hi | lo take 64 + 64 TMEM
 // columns per group, the X chunk hi | lo 2 x 32 KB of shared memory per group.
-__global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs a) {
+// THREE loader groups (TMEM: D [0,128) + 3 x 128 operand columns = 512; shared memory 3 x 64 KB): with two, a group's chain
+// load -> split -> tcgen05.st / shared stores -> MMA -> done took 7.7 us per 64-row chunk at cfg5 and the kernel moved
+// 1.9 TB/s.
+constexpr int OT32_NG = 3;
+constexpr int OT32_THREADS = (4 * OT32_NG + 1) * 32;
+__global__ void __launch_bounds__(OT32_THREADS, 1) k_outer_tc32(const OuterTcArgs a) {
   extern __shared__ __align__(128) unsigned char o32_smem[];
   float* Bs = reinterpret_cast<float*>(o32_smem);                 // [group][hi, lo][128 x 64] canonical K-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 4 * 128 * OT_KC);
-  uint64_t* full = bars;      // [2]
-  uint64_t* done = bars + 2;  // [2]
-  uint64_t* fin = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + OT32_NG * 2 * 128 * OT_KC);
+  uint64_t* full = bars;             // [NG]
+  uint64_t* done = bars + OT32_NG;   // [NG]
+  uint64_t* fin = bars + 2 * OT32_NG;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * OT32_NG + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ho = a.Ho, Hi = a.Hi;
   if (tid == 0) {
-    tc::mbar_init(&full[0], 128); tc::mbar_init(&full[1], 128);
-    tc::mbar_init(&done[0], 1);   tc::mbar_init(&done[1], 1);
+    for (int g = 0; g < OT32_NG; ++g) {
+      tc::mbar_init(&full[g], 128);
+      tc::mbar_init(&done[g], 1);
+    }
     tc::mbar_init(fin, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 4 * OT32_NG) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -575,7 +582,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
   const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
   const long long nchunks = r_end > r_begin ? (r_end - r_begin + OT_KC - 1) / OT_KC : 0;
 
-  if (warp < 8) {
+  if (warp < 4 * OT32_NG) {
     const int g = warp >> 2;
     const int ch = tid & 127;                                      // output channel o (A) / input channel i (X)
     const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
@@ -584,8 +591,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
     float colsum = 0.0f;
     float* bhi = Bs + (size_t)g * 2 * 128 * OT_KC + ((ch >> 3) * (OT_KC >> 2)) * 32 + (ch & 7) * 4;
     float* blo = bhi + 128 * OT_KC;
-    for (long long j = g; j < nchunks; j += 2) {
-      const long long it = j >> 1;
+    for (long long j = g; j < nchunks; j += OT32_NG) {
+      const long long it = j / OT32_NG;
       const long long r0 = r_begin + j * OT_KC;
       if (it > 0) {
         tc::mbar_wait(&done[g], (uint32_t)((it - 1) & 1));
@@ -654,8 +661,8 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
     const uint32_t idesc = tc::idesc_tf32(128, Hi);
     const uint32_t sbo = (uint32_t)(OT_KC / 4) * 128u;
     for (long long j = 0; j < nchunks; ++j) {
-      const int g = (int)(j & 1);
-      tc::mbar_wait(&full[g], (uint32_t)((j >> 1) & 1));
+      const int g = (int)(j % OT32_NG);
+      tc::mbar_wait(&full[g], (uint32_t)((j / OT32_NG) & 1));
       tc::fence_after_sync();
       const float* bh = Bs + (size_t)g * 2 * 128 * OT_KC;
       const float* bl = bh + 128 * OT_KC;
@@ -673,7 +680,7 @@ __global__ void __launch_bounds__(TCG_THREADS, 1) k_outer_tc32(const OuterTcArgs
     if (nchunks > 0) tc::mma_commit(fin);
   }
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tbase, 512);
+  if (warp == 4 * OT32_NG) tc::tmem_dealloc(tbase, 512);
 }
 
 // dW[o, i] += sum_c part[c][o][i];  db[o] += sum_c part_b[c][o]
@@ -799,7 +806,7 @@ static int outer_reduce_tc_impl(const float* A, long long lda, int Ho, const flo
   }
   OuterTcArgs a{A, lda, Ho, X, ldx, Hi, rows, per, part, db ? part_b : nullptr};
   if (tf32x3) {
-    const size_t smem = (size_t)4 * 128 * OT_KC * sizeof(float) + 128;
+    const size_t smem = (size_t)OT32_NG * 2 * 128 * OT_KC * sizeof(float) + 128;
     static bool attr_done = false;
     if (!attr_done) {
       if (cudaFuncSetAttribute(k_outer_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -808,7 +815,7 @@ static int outer_reduce_tc_impl(const float* A, long long lda, int Ho, const flo
       }
       attr_done = true;
     }
-    k_outer_tc32<<<(unsigned)ctas, TCG_THREADS, smem, s>>>(a);
+    k_outer_tc32<<<(unsigned)ctas, OT32_THREADS, smem, s>>>(a);
     if (int rc = gcm_check_launch("k_outer_tc32")) return rc;
   } else {
     k_outer_tc<<<(unsigned)ctas, TCG_THREADS, 0, s>>>(a);
@@ -839,12 +846,12 @@ extern "C" int gcm_outer_reduce_tc32_pair(const float* A, long long lda, int Ho,
     return GCM_ERR_CUDA;
   }
   OuterTcArgs a{A, lda, Ho, X1, ldx1, Hi, rows, per, part, db ? part_b : nullptr, X2, ldx2, Hi1};
-  const size_t smem = (size_t)4 * 128 * OT_KC * sizeof(float) + 128;
+  const size_t smem = (size_t)OT32_NG * 2 * 128 * OT_KC * sizeof(float) + 128;
   if (cudaFuncSetAttribute(k_outer_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     gcm_set_error("outer_reduce_tc32_pair: cannot raise the dynamic shared memory limit");
     return GCM_ERR_CUDA;
   }
-  k_outer_tc32<<<(unsigned)ctas, TCG_THREADS, smem, s>>>(a);
+  k_outer_tc32<<<(unsigned)ctas, OT32_THREADS, smem, s>>>(a);
   if (int rc = gcm_check_launch("k_outer_tc32")) return rc;
   k_outer_tc_reduce_pair<<<(Ho * Hi + 255) / 256, 256, 0, s>>>(part, part_b, (int)ctas, Ho, Hi, Hi1, dW1, dW2, db);
   return gcm_check_launch("k_outer_tc_reduce_pair");

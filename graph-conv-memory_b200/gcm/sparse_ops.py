@@ -237,7 +237,8 @@ class _GraphConvFn(torch.autograd.Function):
         m = out.shape[0]
         dev = x.device
         t_rowptr, t_col = csr.transposed(rows)
-        d_x = torch.zeros(n, Fin, device=dev)
+        # every row evaluated (rows is None): d_x = dz W_root overwrites all n rows before the transposed gather adds to it
+        d_x = (torch.empty if rows is None else torch.zeros)(n, Fin, device=dev)
         d_agg = torch.empty(m, Fin, device=dev)
         d_w_rel = torch.zeros_like(w_rel)
         d_w_root = torch.zeros_like(w_root)
