@@ -28,7 +28,8 @@ def _oracle_grads(obs, w, p, spec, N, hidden=None):
 @pytest.mark.parametrize("mode", ["step", "seq", "mixed"])
 @pytest.mark.parametrize("x_grad", [True, False])
 @pytest.mark.parametrize("B,N,F,T,hops", [(9, 16, 32, 24, (1, 2, 4)), (5, 128, 32, 40, (1, 2, 4)), (7, 12, 8, 30, (1,)),
-                                          (3, 20, 16, 26, (1, 3)), (300, 16, 32, 21, (1, 2, 4)), (130, 12, 32, 9, (3,))])
+                                          (3, 20, 16, 26, (1, 3)), (300, 16, 32, 21, (1, 2, 4)), (130, 12, 32, 9, (3,)),
+                                          (256, 64, 32, 45, (1, 2, 4))])               # whole tiles of 128 rows per position
 def test_temporal_window_backward_matches_fp64_oracle(mode, x_grad, B, N, F, T, hops):
     from gcm.gcm import DenseGCM
 
