@@ -957,6 +957,36 @@ extern "C" int gcm_act_backward(const float* d_out, const float* out, int act, l
   return gcm_check_launch("k_act_bwd");
 }
 
+// res[t, b, :] = d_out[t * s_t + b * s_b + :] * act'(out[t, b, :]): d_out read through its element strides (rows of H floats
+// contiguous and 16-byte aligned), out / res contiguous [T, B, H]
+__global__ void __launch_bounds__(256) k_act_bwd_strided(const float* __restrict__ d_out, long long s_t, long long s_b,
+                                                         const float4* __restrict__ out, int act, int B, int H4,
+                                                         long long n4, float4* __restrict__ res) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // (t, b, 16-byte chunk)
+  if (i >= n4) return;
+  const long long row = i / H4;
+  const int c = (int)(i - row * H4);
+  const long long t = row / B, b = row - t * B;
+  const float4 d = __ldcs(reinterpret_cast<const float4*>(d_out + t * s_t + b * s_b) + c);
+  const float4 o = out[i];
+  res[i] = make_float4(d.x * gcm_act_grad(o.x, act), d.y * gcm_act_grad(o.y, act), d.z * gcm_act_grad(o.z, act),
+                       d.w * gcm_act_grad(o.w, act));
+}
+
+extern "C" int gcm_act_backward_strided(const float* d_out, long long s_t, long long s_b, const float* out, int act, int T,
+                                        int B, int H, float* res, void* stream) {
+  GCM_REQUIRE(d_out && out && res && T >= 0 && B >= 0 && H >= 4 && (H & 3) == 0, "act_backward_strided: bad arguments");
+  GCM_REQUIRE((s_t & 3) == 0 && (s_b & 3) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res)) & 15) == 0,
+              "act_backward_strided: rows must be 16-byte aligned");
+  const long long n4 = (long long)T * B * (H / 4);
+  if (n4 == 0) return GCM_OK;
+  GCM_REQUIRE((n4 + 255) / 256 < 2147483647LL, "act_backward_strided: too many elements");
+  k_act_bwd_strided<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_out, s_t, s_b, reinterpret_cast<const float4*>(out), act, B, H / 4, n4, reinterpret_cast<float4*>(res));
+  return gcm_check_launch("k_act_bwd_strided");
+}
+
 extern "C" int gcm_dense_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1, long long n,
                                  float* dc, const float* dcs_next, float* dcs, void* stream) {
   GCM_REQUIRE(dG && dht && P && h_t && dc && n >= 0, "dense_ones_dc: bad arguments");

@@ -142,6 +142,7 @@ _SIGNATURES = {
     "gcm_dense_ones_window_fwd": (_I, [C.POINTER(DenseStateC), _I, _I, _I, _P, _I, _I, _P, _P, C.c_longlong, _P, _P, _P,
                                        C.c_longlong, _P]),
     "gcm_act_backward": (_I, [_P, _P, _I, C.c_longlong, _P, _P]),
+    "gcm_act_backward_strided": (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _P, _P]),
     "gcm_dense_ones_dc": (_I, [_P, _P, _P, _P, _I, C.c_longlong, _P, _P, _P, _P]),
     "gcm_to_bf16": (_I, [_P, _P, C.c_longlong, _P]),
     "gcm_linear_tc": (_I, [_P, _I, C.c_longlong, _P, _P, _I, C.c_longlong, _I, _P, C.c_longlong, _I, _P]),

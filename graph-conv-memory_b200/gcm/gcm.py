@@ -465,6 +465,34 @@ class DenseGCM(torch.nn.Module):
             or (isinstance(hidden, DenseHidden) and hidden.token is not None))
         if recording and T > int(self.bptt_capacity):
             return loop(hidden)
+        if (hidden.__class__ is DenseHidden and hidden.live() and plan.validated and self._plan is plan
+                and x_seq.is_contiguous()):
+            # a live handle of a validated plan: nothing to ingest or validate, all T steps go through the sequence
+            # kernels -- no separate first step, no concatenation of its belief with the others, and the [B, T, H] result
+            # is a VIEW of the time-major buffer the kernels write
+            st = hidden._state
+            tok = hidden.token
+            bf16 = ones.want_bf16(self, plan)
+            cap = st.C - st.N + 1
+            whole = (st.dense_ok and st.B == x_seq.shape[0] and st.F == x_seq.shape[2]
+                     and (tok is None or getattr(tok, "_gcm_ones", False)) and ones.sequence_supported(plan, st, T, bf16))
+            if whole and recording:
+                win = getattr(st, "win", None)
+                used = 0 if (tok is None or win is None) else st.steps - win.chain_start
+                whole = st.C - st.N >= 1 and used + T <= cap
+            elif whole:
+                whole = tok is None
+            if whole:
+                st = hidden.claim()
+                if not DenseGCM.did_warn and st.host_count is not None and st.host_count + T > st.N:
+                    print("Overflow detected, wrapping around. Will not warn again")
+                    DenseGCM.did_warn = True
+                if recording:
+                    beliefs, tok = ones.sequence_grad(plan, st, x_seq, tok, bf16)
+                    tok._gcm_ones = True
+                else:
+                    beliefs, tok = ones.sequence_nograd(plan, st, x_seq.detach(), bf16), None
+                return beliefs.transpose(0, 1), DenseHidden(st, tok)
         # enter the state exactly as forward() does, by taking the first step through it
         out0, hidden = self(x_seq[:, 0], hidden)
         state = hidden.claim() if isinstance(hidden, DenseHidden) else None

@@ -520,9 +520,17 @@ class _OnesSeqFn(torch.autograd.Function):
         lib = _cabi.lib()
         stream = _cabi.stream_ptr(dev)
         win.ensure_bwd()
-        db_ = d_beliefs.contiguous().float()
-        _cabi.check(lib.gcm_act_backward(db_.data_ptr(), beliefs.data_ptr(), _cabi.ACT[g.act2], T * st.B * g.H2,
-                                         win.do[k0:k0 + T].data_ptr(), stream), "gcm_act_backward")
+        if (d_beliefs.dtype == torch.float32 and not d_beliefs.is_contiguous() and d_beliefs.stride(2) == 1
+                and g.H2 % 4 == 0 and d_beliefs.stride(0) % 4 == 0 and d_beliefs.stride(1) % 4 == 0
+                and d_beliefs.data_ptr() % 16 == 0):
+            # a [B, T, H] gradient seen time-major: read through its strides, no transposing copy
+            _cabi.check(lib.gcm_act_backward_strided(d_beliefs.data_ptr(), d_beliefs.stride(0), d_beliefs.stride(1),
+                                                     beliefs.data_ptr(), _cabi.ACT[g.act2], T, st.B, g.H2,
+                                                     win.do[k0:k0 + T].data_ptr(), stream), "gcm_act_backward_strided")
+        else:
+            db_ = d_beliefs.contiguous().float()
+            _cabi.check(lib.gcm_act_backward(db_.data_ptr(), beliefs.data_ptr(), _cabi.ACT[g.act2], T * st.B * g.H2,
+                                             win.do[k0:k0 + T].data_ptr(), stream), "gcm_act_backward")
         d_x = None
         if win.need_dx:
             # observations require grad: finish the steps newest-first, like T single-step nodes would

@@ -367,6 +367,10 @@ int gcm_dense_ones_window_fwd(const gcm_dense_state* st, int H1, int act1, int c
                               float* wP, float* wht, long long step_stride, void* stream);
 /* res = d_out * act'(out) elementwise (act' expressed through the activation's output) */
 int gcm_act_backward(const float* d_out, const float* out, int act, long long n, float* res, void* stream);
+/* The same with d_out read through element strides: d_out[t, b, :] at d_out + t * s_t + b * s_b (rows of H floats contiguous,
+ * 16-byte aligned; a [B, T, H] gradient of the beliefs seen time-major is not copied); out and res contiguous [T, B, H]. */
+int gcm_act_backward_strided(const float* d_out, long long s_t, long long s_b, const float* out, int act, int T, int B,
+                             int H, float* res, void* stream);
 /* per-step pieces of the backward, elementwise over n = B*H1: dht <- dzo = dht * act1'(h_t); dc = dG * P + dzo;
  * dcs = dc + dcs_next (suffix sum over the later steps; dcs / dcs_next may be NULL) */
 int gcm_dense_ones_dc(const float* dG, float* dht, const float* P, const float* h_t, int act1, long long n, float* dc,

@@ -268,11 +268,14 @@ def test_ones_path_window_backward_wide(acts, bf16):
 
 @pytest.mark.parametrize("bf16", [False, True])
 @pytest.mark.parametrize("x_grad", [True, False])
-def test_forward_sequence_matches_step_loop_and_oracle(bf16, x_grad):
+@pytest.mark.parametrize("contig", [False, True])
+def test_forward_sequence_matches_step_loop_and_oracle(bf16, x_grad, contig):
     """DenseGCM.forward_sequence (the caller is RayDenseGCM's loop over T, ray_gcm.py:200-202) on a
     DenseEdge state: T steps at once must give what T forward() calls give -- beliefs, the hidden state, and every
     gradient (fp64 oracle: 1e-5 class for the float32 cache, 2e-2 for bfloat16).  Ragged pre-filled counts; the
-    window wraps inside the sequence; a second sequence continues the same BPTT chain."""
+    window wraps inside the sequence; a second sequence continues the same BPTT chain.  contig: the chunks are contiguous
+    tensors of their own, so the second call (live handle) takes ALL its steps through the sequence kernels and returns a
+    view of the time-major buffer; otherwise they are slices and every call enters through one forward() step."""
     from gcm.gcm import DenseGCM
 
     dev = torch.device("cuda:0")
@@ -301,17 +304,25 @@ def test_forward_sequence_matches_step_loop_and_oracle(bf16, x_grad):
     mod.bptt_capacity = T
     if bf16:
         mod.compute_dtype = torch.bfloat16
-    x = obs.to(dev).transpose(0, 1).contiguous().requires_grad_(x_grad)            # [B, T, F]
+    x = obs.to(dev).transpose(0, 1).contiguous().requires_grad_(x_grad and not contig)            # [B, T, F]
     hidden = (nodes0.to(dev), adj0.to(dev), torch.zeros(0, device=dev), nn0.to(dev))
-    b1, hidden = mod.forward_sequence(x[:, :T1], hidden)
+    if contig:
+        x1 = x[:, :T1].detach().contiguous().requires_grad_(x_grad)
+        x2 = x[:, T1:].detach().contiguous().requires_grad_(x_grad)
+    else:
+        x1, x2 = x[:, :T1], x[:, T1:]
+    b1, hidden = mod.forward_sequence(x1, hidden)
     assert hidden.claim().win is not None and hidden.claim().steps == T1
-    b2, hidden = mod.forward_sequence(x[:, T1:], hidden)
+    b2, hidden = mod.forward_sequence(x2, hidden)
+    if contig:
+        assert not b2.is_contiguous() and b2.transpose(0, 1).is_contiguous()        # a view of the [T, B, H] buffer
     got = torch.cat([b1, b2], dim=1)                                                # [B, T, H]
     assert got.shape == (B, T, H)
     assert rel_err(got.transpose(0, 1), outs.detach()) < tol
     (got.transpose(0, 1) * w.to(dev)).sum().backward()
     if x_grad:
-        assert rel_err(x.grad.transpose(0, 1), o.grad) < tol
+        xg = torch.cat([x1.grad, x2.grad], dim=1) if contig else x.grad
+        assert rel_err(xg.transpose(0, 1), o.grad) < tol
     grads = named_grads(convs)
     for k in grads:
         assert rel_err(grads[k], pp[k].grad) < tol, k
@@ -339,7 +350,8 @@ def test_forward_sequence_rollout_ring_and_generic_fallback():
         with torch.no_grad():
             h_seq, h_loop, seq_out, loop_out = None, None, [], []
             for c in range(3):
-                out, h_seq = mods[0].forward_sequence(obs[:, c * T:(c + 1) * T], h_seq)
+                chunk = obs[:, c * T:(c + 1) * T]
+                out, h_seq = mods[0].forward_sequence(chunk.contiguous() if c == 1 else chunk, h_seq)   # c == 1: whole-sequence entry
                 seq_out.append(out)
             for t in range(3 * T):
                 out, h_loop = mods[1](obs[:, t], h_loop)
