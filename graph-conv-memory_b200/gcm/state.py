@@ -127,6 +127,14 @@ class DenseState:
         new.zc_ok = False
         if self.raw is not None:
             new.raw, new.pre_key = self.raw.clone(), self.pre_key
+        if self.dense_ok:
+            # DenseEdge states: the running sum of the window's rows depends on the log only -- formed once on the source
+            # (a pass over the whole node log: 0.37 ms at BASELINE cfg3) and carried by every clone
+            if self.xsum is None:
+                self.xsum = torch.empty(self.B, self.F, device=self.device, dtype=torch.float32)
+                _cabi.check(_cabi.lib().gcm_dense_ones_xsum(self.c_ref(), self.xsum.data_ptr(),
+                                                            _cabi.stream_ptr(self.device)), "gcm_dense_ones_xsum")
+            new.xsum = self.xsum.clone()
         return new
 
     # -- materialisation ------------------------------------------------------------------------
