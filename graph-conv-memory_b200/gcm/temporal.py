@@ -107,7 +107,7 @@ def fast_step(plan, state, x: torch.Tensor):
             or torch.cuda.is_current_stream_capturing()):
         return None
     dev = state.device
-    if plan.gnn.current_key(dev) != ro.key or state.hc_key != ro.key:
+    if not plan.gnn.key_is(ro.key, dev) or (state.hc_key is not ro.key and state.hc_key != ro.key):
         return None                              # weights changed: the general route handles it
     hc = state.host_count
     if hc is not None and hc < plan.max_hop:

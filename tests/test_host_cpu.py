@@ -283,3 +283,29 @@ def test_ones_window_buffers_grow_without_losing_recorded_steps():
     win.need_dx = True
     win.ensure_bwd()
     assert win.do.shape == (200, 3, 8) and win.dcs.shape == (200, 3, 8)
+
+
+def test_gnn_key_is_matches_current_key():
+    """GnnPlan.key_is (the per-call rollout path's weights check) agrees with current_key: same parameters -> True; an
+    in-place update, a replaced parameter, another device, a bias that appears -> False."""
+    import torch
+    from gcm import fused
+    from gcm.gcm import DenseGCM
+    from helpers import make_dense_gnn, make_selector
+    import gcm_oracle as oracle
+
+    gnn, convs = make_dense_gnn(8, 16, oracle.make_params(8, 16), ("tanh", "tanh"))
+    mod = DenseGCM(gnn, edge_selectors=make_selector([("temporal", (1,), "forward")]), graph_size=8)
+    plan = mod.fused_plan()
+    assert plan is not None
+    g = plan.gnn
+    dev = torch.device("cpu")
+    key = g.current_key(dev)
+    assert g.key_is(key, dev) and not g.key_is(key, torch.device("cuda:0")) and not g.key_is(None, dev)
+    assert not g.key_is(key[:-3] + key[-1:], dev)
+    with torch.no_grad():
+        convs[0].lin_rel.weight.add_(1.0)                    # in-place update: version counter
+    assert not g.key_is(key, dev) and g.key_is(g.current_key(dev), dev)
+    key = g.current_key(dev)
+    convs[1].lin_root.weight = torch.nn.Parameter(convs[1].lin_root.weight.detach().clone())     # replaced parameter
+    assert not g.key_is(key, dev) and g.key_is(g.current_key(dev), dev)
