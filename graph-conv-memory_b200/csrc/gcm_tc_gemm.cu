@@ -34,25 +34,34 @@ __device__ __forceinline__ float tcg_exp2x(float z) {   // exp(2 clamp(z, +-40))
 // whole duration of the small launches); 4 (tf32) / 8 (bf16) consecutive k are contiguous in the canonical layout.
 template <int NTHREADS>
 __device__ __forceinline__ void stage_w_tf32(const float* __restrict__ W, int Ho, int K, float* Whi, float* Wlo, int tid) {
+  // Item i = one 16-byte piece (row n, columns 4 kq .. 4 kq + 3).  Consecutive items walk the 8 rows of a core-matrix row
+  // first, then 4 neighbouring pieces, so a warp's 32 stores cover 512 CONTIGUOUS bytes of the K-major layout (with items
+  // in row-major order -- consecutive k of one row -- the stores were 128 bytes apart: 32-way bank conflicts, 8 K of the
+  // 8.3 K shared-memory wavefronts of a one-tile launch, and a launch over few rows is dominated by this loop: 20.5 us at
+  // [128 x 128] whatever the row count).  8 independent loads in flight per thread.  Needs Ho % 8 == 0, K % 16 == 0.
+  constexpr int U = 8;
   const int n4 = Ho * K / 4;
-  for (int i0 = tid; i0 < n4; i0 += 4 * NTHREADS) {
-    float4 v[4];
+  const int kqb_n = K >> 4;                 // blocks of 4 pieces along k
+  for (int i0 = tid; i0 < n4; i0 += U * NTHREADS) {
+    float4 v[U];
+    int off[U];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < U; ++q) {
       const int i = i0 + q * NTHREADS;
-      v[q] = i < n4 ? __ldg(reinterpret_cast<const float4*>(W) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int blk = i >> 5, l = i & 31;
+      const int nb = blk / kqb_n, kqb = blk - nb * kqb_n;
+      const int n = nb * 8 + (l & 7), kq = kqb * 4 + (l >> 3);
+      off[q] = tc::kmajor_off(n, kq * 4, K);
+      v[q] = i < n4 ? __ldg(reinterpret_cast<const float4*>(W + (size_t)n * K) + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = i0 + q * NTHREADS;
-      if (i < n4) {
-        const int e = i * 4, n = e / K, k = e - n * K;
+    for (int q = 0; q < U; ++q) {
+      if (i0 + q * NTHREADS < n4) {
         uint32_t h[4], l[4];
         tc::split_tf32(v[q].x, h[0], l[0]); tc::split_tf32(v[q].y, h[1], l[1]);
         tc::split_tf32(v[q].z, h[2], l[2]); tc::split_tf32(v[q].w, h[3], l[3]);
-        const int off = tc::kmajor_off(n, k, K);
-        *reinterpret_cast<uint4*>(Whi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(Wlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4*>(Whi + off[q]) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(Wlo + off[q]) = make_uint4(l[0], l[1], l[2], l[3]);
       }
     }
   }
@@ -236,8 +245,9 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
   uint64_t* wready = bars + 1;   // weights are in shared memory (160 arrivals, once)
   uint64_t* done = bars + 2;     // all MMAs of the current tile completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 64);   // [128] bias (0 when absent)
   // staging tile (a.stage): rows padded by 4 floats so that a thread reading ITS row with 16-byte loads is conflict-free
-  float* tile = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 64);
+  float* tile = bias_s + 128;
   const int tile_ld = (K1 > Ho ? K1 : Ho) + 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
         tc::wait_ld();
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(d[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.0f);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(d[j]) + bias_s[n0 + j];
         if (a.act == GCM_ACT_EXP2X) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = tcg_exp2x(f[j]);
@@ -379,6 +389,7 @@ __global__ void __launch_bounds__(TC32_THREADS) k_linear_tc32(const LinearTc32Ar
     }
     if (a.status && bad) atomicOr(reinterpret_cast<unsigned int*>(a.status), GCM_FLAG_NONFINITE);
   } else {
+    for (int i = tid - 128; i < 128; i += TC32_THREADS - 128) bias_s[i] = (a.bias && i < Ho) ? __ldg(a.bias + i) : 0.0f;
     stage_w_tf32<TC32_THREADS - 128>(a.W1, Ho, K1, Whi, Wlo, tid - 128);
     if (K2) stage_w_bf16<TC32_THREADS - 128>(a.W2, Ho, K2, W2s, tid - 128);
     tc::fence_proxy_async();
@@ -756,11 +767,11 @@ extern "C" int gcm_linear_tc32(const float* X1, int K1, long long ldx1, const fl
   // narrow streaming products (many rows, K1 <= 64, Ho <= 64): row / result tiles staged through shared memory
   static const bool no_stage = getenv("GCM_B200_NO_LINEAR_STAGE") != nullptr;
   a.stage = (!X2 && K1 <= 64 && Ho <= 64 && (K1 & (K1 - 1)) == 0 && (Ho & (Ho - 1)) == 0 && rows >= 4096 && !no_stage) ? 1 : 0;
-  const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64 + 64 +
+  const size_t smem = (size_t)Ho * K1 * 8 + (size_t)Ho * a.K2 * 2 + 64 + 64 + 512 +
                       (a.stage ? (size_t)128 * ((K1 > Ho ? K1 : Ho) + 4) * 4 : 0);
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(k_linear_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 10 + 256) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_linear_tc32, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 10 + 1024) != cudaSuccess) {
       gcm_set_error("linear_tc32: cannot raise the dynamic shared memory limit");
       return GCM_ERR_CUDA;
     }
