@@ -68,7 +68,36 @@ __device__ __forceinline__ void stage_w_tf32(const float* __restrict__ W, int Ho
 }
 template <int NTHREADS>
 __device__ __forceinline__ void stage_w_bf16(const float* __restrict__ W, int Ho, int K, __nv_bfloat16* Ws, int tid) {
+  // item = one 16-byte core-matrix row (row n, columns 8 k8 .. 8 k8 + 7); consecutive items walk the 8 rows of a core
+  // matrix, then 4 neighbouring matrices: a warp's stores cover 512 contiguous bytes (see stage_w_tf32)
+  constexpr int U = 4;
   const int n8 = Ho * K / 8;
+  const int kb_n = K >> 5;                  // blocks of 4 core matrices along k (K % 32 == 0), else the plain order below
+  if ((K & 31) == 0) {
+    for (int i0 = tid; i0 < n8; i0 += U * NTHREADS) {
+      float4 v[2 * U];
+      int off[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int i = i0 + q * NTHREADS;
+        const int blk = i >> 5, l = i & 31;
+        const int nb = blk / kb_n, kb = blk - nb * kb_n;
+        const int n = nb * 8 + (l & 7), k8 = kb * 4 + (l >> 3);
+        off[q] = tc::kmajor_off_bf16(n, k8 * 8, K);
+        const float4* src = reinterpret_cast<const float4*>(W + (size_t)n * K) + 2 * k8;
+        v[2 * q] = i < n8 ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[2 * q + 1] = i < n8 ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        if (i0 + q * NTHREADS < n8)
+          *reinterpret_cast<uint4*>(Ws + off[q]) =
+              make_uint4(tc::pack_bf16(v[2 * q].x, v[2 * q].y), tc::pack_bf16(v[2 * q].z, v[2 * q].w),
+                         tc::pack_bf16(v[2 * q + 1].x, v[2 * q + 1].y), tc::pack_bf16(v[2 * q + 1].z, v[2 * q + 1].w));
+      }
+    }
+    return;
+  }
   for (int i0 = tid; i0 < n8; i0 += 2 * NTHREADS) {
     float4 v[4];
 #pragma unroll
@@ -89,6 +118,7 @@ __device__ __forceinline__ void stage_w_bf16(const float* __restrict__ W, int Ho
     }
   }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // out[r, :Ho] = epi(X[r, :K] W^T + bias), W row-major [Ho, K] float32 (rounded to bf16 once per CTA).
@@ -112,6 +142,7 @@ __global__ void __launch_bounds__(TCG_THREADS) k_linear_tc(const LinearTcArgs a)
   uint64_t* full = bars;         // [2] A tile of group g is in TMEM
   uint64_t* done = bars + 2;     // [2] MMAs of group g's tile have completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 8);      // [128] bias (0 when absent): the epilogue reads it per element
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K, Ho = a.Ho;
 
@@ -121,6 +152,7 @@ __global__ void __launch_bounds__(TCG_THREADS) k_linear_tc(const LinearTcArgs a)
     tc::mbar_fence_init();
   }
   if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  if (tid < 128) bias_s[tid] = (a.bias && tid < Ho) ? __ldg(a.bias + tid) : 0.0f;
   stage_w_bf16<TCG_THREADS>(a.W, Ho, K, Ws, tid);
   tc::fence_proxy_async();
   tc::fence_before_sync();
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(TCG_THREADS) k_linear_tc(const LinearTcArgs a)
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float z = __uint_as_float(d[j]) + (a.bias ? __ldg(a.bias + n0 + j) : 0.0f);
+          const float z = __uint_as_float(d[j]) + bias_s[n0 + j];
           f[j] = a.act == GCM_ACT_EXP2X ? tcg_exp2x(z) : z;
         }
         if (ok) {
@@ -742,7 +774,7 @@ extern "C" int gcm_linear_tc(const float* X, int K, long long ldx, const float* 
               "linear_tc: X, W and out must be 16-byte aligned");
   if (rows == 0) return GCM_OK;
   LinearTcArgs a{X, ldx, K, W, bias, act, rows, Ho, out, ldo, out_bf16, (rows + 127) / 128};
-  const size_t smem = (size_t)Ho * K * 2 + 64;
+  const size_t smem = (size_t)Ho * K * 2 + 64 + 512;
   long long grid = a.tiles < gcm_num_sms() ? a.tiles : gcm_num_sms();
   k_linear_tc<<<(unsigned)grid, TCG_THREADS, smem, (cudaStream_t)stream>>>(a);
   return gcm_check_launch("k_linear_tc");

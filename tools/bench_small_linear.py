@@ -14,7 +14,11 @@ for K, Ho in ((128, 128), (64, 64), (32, 32)):
         x = torch.randn(rows, K, device=dev)
         out = torch.empty(rows, Ho, device=dev)
         res = {}
+        def bf16():
+            _cabi.check(lib.gcm_linear_tc(x.data_ptr(), K, K, w.data_ptr(), b.data_ptr(), 0, rows, Ho, out.data_ptr(), Ho, 0,
+                                          _cabi.stream_ptr(dev)), "gcm_linear_tc")
         for name, fn in (("tc32", lambda: ones._lin_tc32(x, w, bias=b, act=1, out=out)),
+                         ("tc_bf16", bf16),
                          ("lin2", lambda: ones._lin2(x, w, bias=b, act=1, out=out))):
             for _ in range(5):
                 fn()
@@ -26,4 +30,5 @@ for K, Ho in ((128, 128), (64, 64), (32, 32)):
             e1.record()
             torch.cuda.synchronize()
             res[name] = e0.elapsed_time(e1) / n * 1e3
-        print(f"K={K} Ho={Ho} rows={rows}: tc32 {res['tc32']:.1f} us, lin2 (CUDA cores) {res['lin2']:.1f} us")
+        print(f"K={K} Ho={Ho} rows={rows}: tc32 {res['tc32']:.1f} us, tc bf16 {res['tc_bf16']:.1f} us, "
+              f"lin2 (CUDA cores) {res['lin2']:.1f} us")
