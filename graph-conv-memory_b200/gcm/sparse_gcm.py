@@ -185,7 +185,12 @@ class SparseGCM(torch.nn.Module):
         new_off = sparse_ops._excl_cumsum(taus)
 
         # node write + flat gather
-        nodes, flat = sparse_ops._WriteFlattenFn.apply(nodes, x, T, taus, offsets, n_flat)
+        if torch.is_grad_enabled() and (x.requires_grad or nodes.requires_grad):
+            nodes, flat = sparse_ops._WriteFlattenFn.apply(nodes, x, T, taus, offsets, n_flat)
+        else:
+            # nothing to record: when every graph ends up full, the flat rows are the node tensor itself (no second copy)
+            nodes, flat = sparse_ops.write_flatten_oop(nodes.detach(), x.detach().contiguous(), T, taus, offsets, n_flat,
+                                                       alias_full=True)
 
         # edges: previous (sinks < T) + the new nodes' (sinks >= T), both sorted by (b, sink, source)
         old = adj.coalesce().indices() if adj._nnz() else torch.zeros(3, 0, dtype=torch.long, device=dev)

@@ -41,17 +41,20 @@ def write_flatten(nodes: torch.Tensor, x: torch.Tensor, T: torch.Tensor, taus: t
 
 
 def write_flatten_oop(nodes: torch.Tensor, x: torch.Tensor, T: torch.Tensor, taus: torch.Tensor, offsets: torch.Tensor,
-                      n_flat: int):
-    """(nodes_out, flat): nodes_out = nodes with nodes_out[b, T_b + k] = x[b, k], flat = its valid rows; one pass, no clone."""
+                      n_flat: int, alias_full: bool = False):
+    """(nodes_out, flat): nodes_out = nodes with nodes_out[b, T_b + k] = x[b, k], flat = its valid rows; one pass, no clone.
+    alias_full: when every graph is full after the write (n_flat == B * N) the flat layout IS nodes_out: return a view of it
+    instead of writing a second copy (callers that record autograd keep the two tensors apart)."""
     _cabi.require_cuda(nodes, "SparseGCM nodes")
     B, N, F = nodes.shape
     nodes = nodes.contiguous()
     out = torch.empty_like(nodes)
-    flat = torch.empty(n_flat, F, device=nodes.device, dtype=torch.float32)
+    alias = alias_full and n_flat == B * N
+    flat = None if alias else torch.empty(n_flat, F, device=nodes.device, dtype=torch.float32)
     _cabi.check(_cabi.lib().gcm_sparse_write_flatten_oop(
         nodes.data_ptr(), out.data_ptr(), x.data_ptr(), T.data_ptr(), taus.data_ptr(), offsets.data_ptr(), B, N, F,
-        x.shape[1], flat.data_ptr(), _cabi.stream_ptr(nodes.device)), "gcm_sparse_write_flatten_oop")
-    return out, flat
+        x.shape[1], _cabi.ptr(flat), _cabi.stream_ptr(nodes.device)), "gcm_sparse_write_flatten_oop")
+    return out, (out.view(B * N, F) if alias else flat)
 
 
 class _WriteFlattenFn(torch.autograd.Function):
